@@ -1,0 +1,536 @@
+// cofdm_host.cu -- implementation of the C ABI in include/cofdm.h: handle management, host-side
+// constant tables (host_consts.hpp), kernel launches for sm_100a, and the COFDM_HOST staging path
+// (chunked H2D -> kernel -> D2H over three streams).  No CPU compute fallback exists: without a
+// usable CUDA device every computing entry point returns COFDM_ERR_CUDA.
+#include "../../include/cofdm.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "host_consts.hpp"
+
+using namespace cofdmk;
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string &msg) { g_err = msg; return code; }
+
+#define CU_TRY(expr)                                                                              \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return fail(COFDM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
+    } while (0)
+
+constexpr int kPipe = 3;   // streams / buffer sets of the COFDM_HOST pipeline
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaMalloc(&p, n);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+}  // namespace
+
+struct cofdm {
+    int device = 0;
+    HostTables T;
+    Params P{};
+    std::vector<void *> table_allocs;
+    const float2 *constell_dev[9] = {};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t pipe_stream[kPipe] = {};
+    DevBuf pipe_in[kPipe], pipe_out[kPipe];
+    DevBuf scratch_a, scratch_b, scratch_c;
+    unsigned long long *amb_dev = nullptr;       // ambiguity counter
+    unsigned long long *pos_dev = nullptr;       // find_t2sin result
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timing = false, timed = false;
+    unsigned long long launches = 0;
+};
+
+namespace {
+
+template <class T>
+int upload(cofdm *h, const std::vector<T> &v, const T **dst) {
+    void *d = nullptr;
+    const size_t bytes = std::max<size_t>(v.size() * sizeof(T), 16);
+    CU_TRY(cudaMalloc(&d, bytes));
+    h->table_allocs.push_back(d);
+    if (!v.empty()) CU_TRY(cudaMemcpy(d, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    *dst = reinterpret_cast<const T *>(d);
+    return COFDM_OK;
+}
+
+struct Timed {
+    cofdm *h;
+    explicit Timed(cofdm *h_) : h(h_) { if (h->timing) cudaEventRecord(h->ev0, h->stream); }
+    ~Timed() { if (h->timing) { cudaEventRecord(h->ev1, h->stream); h->timed = true; } }
+};
+
+int check_launch(cofdm *h, const char *what) {
+    h->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(COFDM_ERR_CUDA, std::string(what) + " launch: " + cudaGetErrorString(e));
+    return COFDM_OK;
+}
+
+size_t sample_bytes(int fmt) { return fmt == COFDM_CI16 ? 4 : 8; }
+
+// ---- device-side launches (all pointers are device pointers, stream given) ----------------------
+int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
+              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps) {
+    if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "rx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
+    if (n_frames == 0) return COFDM_OK;
+    const int nsym = h->P.n_sym_rx;
+    const size_t sm = rx_fused512_smem_bytes(nsym);
+    const dim3 grid((unsigned)n_frames), block(32 * nsym);
+    if (fmt == COFDM_CI16) {
+        if (((uintptr_t)samples & 15) || (stride * 4) % 16) return fail(COFDM_ERR_ARG, "rx: int16 frames must be 16-byte aligned");
+        rx_fused512_kernel<kCI16, false><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
+    } else if (((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0) {
+        rx_fused512_kernel<kCF32, true><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
+    } else {
+        return fail(COFDM_ERR_ARG, "rx: cf32 frames must be 16-byte aligned");
+    }
+    return check_launch(h, "rx_fused512");
+}
+
+int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt) {
+    if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "tx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
+    if (n_frames == 0) return COFDM_OK;
+    const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
+    const dim3 grid((unsigned)n_frames), block(32 * (h->P.num_symb + 1));
+    if (fmt == COFDM_CI16) tx512_kernel<kCI16><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+    else tx512_kernel<kCF32><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+    return check_launch(h, "tx512");
+}
+
+int launch_t2(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t start, size_t n_blocks, float *rel) {
+    if (h->P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "t2sin: only T2sin_size = 256 is built so far");
+    if (n_blocks == 0) return COFDM_OK;
+    const unsigned grid = (unsigned)((n_blocks + kT2WarpsPerCta - 1) / kT2WarpsPerCta);
+    if (fmt == COFDM_CI16) t2sin_metric_kernel<kCI16><<<grid, 32 * kT2WarpsPerCta, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
+    else t2sin_metric_kernel<kCF32><<<grid, 32 * kT2WarpsPerCta, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
+    return check_launch(h, "t2sin_metric");
+}
+
+int launch_pc(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_samples, const long long *starts,
+              size_t n_starts, float *cor, long long *first) {
+    if (n_starts == 0) return COFDM_OK;
+    const size_t sm = (size_t)(h->P.cor_size + 2 * h->P.pr_sin_len) * sizeof(float2);
+    if (sm > 200 * 1024) return fail(COFDM_ERR_UNSUPPORTED, "preamble search window exceeds shared memory");
+    if (fmt == COFDM_CI16) preamble_corr_kernel<kCI16><<<(unsigned)n_starts, kPcThreads, sm, st>>>(h->P, samples, (long long)n_samples, starts, (int)n_starts, cor, first);
+    else preamble_corr_kernel<kCF32><<<(unsigned)n_starts, kPcThreads, sm, st>>>(h->P, samples, (long long)n_samples, starts, (int)n_starts, cor, first);
+    return check_launch(h, "preamble_corr");
+}
+
+int set_device(const cofdm *h) {
+    cudaError_t e = cudaSetDevice(h->device);
+    if (e != cudaSuccess) return fail(COFDM_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(e));
+    return COFDM_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *cofdm_last_error(void) { return g_err.c_str(); }
+const char *cofdm_version(void) { return "cofdm_b200 0.1 (sm_100a)"; }
+
+void cofdm_destroy(cofdm_t *h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (void *p : h->table_allocs) cudaFree(p);
+    for (int i = 0; i < kPipe; i++) {
+        h->pipe_in[i].release(); h->pipe_out[i].release();
+        if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
+    }
+    h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release();
+    if (h->amb_dev) cudaFree(h->amb_dev);
+    if (h->pos_dev) cudaFree(h->pos_dev);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+int cofdm_create(const char *config_path, int device, cofdm_t **out) {
+    if (!config_path || !out) return fail(COFDM_ERR_ARG, "cofdm_create: null argument");
+    *out = nullptr;
+    cofdm *h = new cofdm;
+    try {
+        h->T = build_tables(parse_config_file(config_path));
+    } catch (const std::exception &e) {
+        delete h;
+        return fail(COFDM_ERR_CONFIG, e.what());
+    }
+    h->device = device;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || device < 0 || device >= ndev) {
+        delete h;
+        return fail(COFDM_ERR_CUDA, std::string("no usable CUDA device ") + std::to_string(device) + ": " +
+                                        (e != cudaSuccess ? cudaGetErrorString(e) : "ordinal out of range") +
+                                        " (this library has no CPU fallback)");
+    }
+    auto bail = [&](int rc) { cofdm_destroy(h); return rc; };
+    if (set_device(h)) return bail(COFDM_ERR_CUDA);
+    cudaDeviceProp prop{};
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess || prop.major < 10)
+        return bail(fail(COFDM_ERR_CUDA, "device is not sm_100 class; this library is built for sm_100a only"));
+    HostTables &T = h->T;
+    h->P = T.p;
+    Params &P = h->P;
+    int rc = 0;
+    rc |= upload(h, T.tw_fft, &P.tw_fft);   rc |= upload(h, T.tw_p1, &P.tw_p1);   rc |= upload(h, T.tw_p2, &P.tw_p2);
+    rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
+    rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
+    rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
+    rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
+    for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
+    if (rc) return bail(COFDM_ERR_CUDA);
+    P.constell = h->constell_dev[P.mod_type];
+    if (cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "stream create"));
+    h->stream = h->own_stream;
+    for (int i = 0; i < kPipe; i++)
+        if (cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "stream create"));
+    if (cudaMalloc(&h->amb_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "cudaMalloc"));
+    if (cudaMalloc(&h->pos_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "cudaMalloc"));
+    cudaEventCreate(&h->ev0);
+    cudaEventCreate(&h->ev1);
+    if (T.fused512_ok) {
+        const int smr = (int)rx_fused512_smem_bytes(P.n_sym_rx), smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
+        cudaError_t a = cudaFuncSetAttribute(rx_fused512_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        cudaError_t b = cudaFuncSetAttribute(rx_fused512_kernel<kCI16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
+        cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
+        if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)
+            return bail(fail(COFDM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(a != cudaSuccess ? a : (b != cudaSuccess ? b : (c != cudaSuccess ? c : d)))));
+    }
+    {
+        const int smp = (int)((size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2));
+        if (smp > 48 * 1024) {
+            cudaFuncSetAttribute(preamble_corr_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp);
+            cudaFuncSetAttribute(preamble_corr_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp);
+        }
+    }
+    *out = h;
+    return COFDM_OK;
+}
+
+int cofdm_query(const cofdm_t *h, cofdm_sizes *o) {
+    if (!h || !o) return fail(COFDM_ERR_ARG, "cofdm_query: null argument");
+    const Params &P = h->P;
+    std::memset(o, 0, sizeof *o);
+    o->fft_size = P.fft_size; o->num_data_subc = P.num_data_subc; o->num_pilot_subc = P.num_pilot_subc;
+    o->cp_size = P.cp_size; o->num_symb = P.num_symb; o->num_pr_symb = P.num_pr_symb;
+    o->pr_sin_len = P.pr_sin_len; o->t2sin_size = P.t2sin_size; o->mod_type = P.mod_type;
+    o->ofdm_len = P.ofdm_len; o->rx_len = P.rx_len; o->output_size = P.frame_len;
+    o->usefull_size = P.bytes_per_frame; o->constell_size = P.num_data_subc * P.num_symb; o->cor_size = P.cor_size;
+    o->mult = (int)P.mult; o->rx_buf_size = h->T.rx_buf_size; o->iterations = h->T.iterations;
+    o->fused_path = h->T.fused512_ok ? 1 : 0; o->device = h->device;
+    return COFDM_OK;
+}
+
+int cofdm_set_stream(cofdm_t *h, void *cuda_stream) {
+    if (!h) return fail(COFDM_ERR_ARG, "null handle");
+    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    return COFDM_OK;
+}
+
+int cofdm_synchronize(cofdm_t *h) {
+    if (!h) return fail(COFDM_ERR_ARG, "null handle");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return COFDM_OK;
+}
+
+int cofdm_enable_timing(cofdm_t *h, int on) {
+    if (!h) return fail(COFDM_ERR_ARG, "null handle");
+    h->timing = on != 0; h->timed = false;
+    return COFDM_OK;
+}
+float cofdm_last_kernel_ms(const cofdm_t *h) {
+    if (!h || !h->timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+unsigned long long cofdm_launch_count(const cofdm_t *h) { return h ? h->launches : 0; }
+
+int cofdm_get_constants(const cofdm_t *h, double *t2sin_tone, uint8_t *preamble_bytes, double *ofdm_preamble,
+                        double *mod_preamble, double *matched, double *constell) {
+    if (!h) return fail(COFDM_ERR_ARG, "null handle");
+    const HostTables &T = h->T;
+    auto put = [](double *dst, const std::vector<cd> &v) { if (dst) std::memcpy(dst, v.data(), v.size() * sizeof(cd)); };
+    put(t2sin_tone, T.t2_tone_d); put(ofdm_preamble, T.preamble_td_d); put(mod_preamble, T.mod_preamble_d);
+    put(matched, T.matched_d); put(constell, T.constell_d[T.p.mod_type]);
+    if (preamble_bytes) std::memcpy(preamble_bytes, T.preamble_bytes.data(), T.preamble_bytes.size());
+    return COFDM_OK;
+}
+
+static bool valid_mod(int m) { return m == 1 || m == 2 || m == 4 || m == 6 || m == 8; }
+
+int cofdm_mod(cofdm_t *h, int mod, const uint8_t *bytes, size_t n_bytes, float *points, int space) {
+    if (!h || !bytes || !points || !valid_mod(mod)) return fail(COFDM_ERR_ARG, "cofdm_mod: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    const size_t n_pts = (n_bytes * 8 + mod - 1) / mod;
+    if (n_pts == 0) return COFDM_OK;
+    const uint8_t *din = bytes; float2 *dout = reinterpret_cast<float2 *>(points);
+    if (space == COFDM_HOST) {
+        CU_TRY(h->scratch_a.reserve(n_bytes)); CU_TRY(h->scratch_b.reserve(n_pts * sizeof(float2)));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, bytes, n_bytes, cudaMemcpyHostToDevice, h->stream));
+        din = (const uint8_t *)h->scratch_a.p; dout = (float2 *)h->scratch_b.p;
+    }
+    {
+        Timed t(h);
+        mod_kernel<<<(unsigned)((n_pts + 255) / 256), 256, 0, h->stream>>>(h->constell_dev[mod], mod, din, (long long)n_bytes, dout, (long long)n_pts);
+        if (int rc = check_launch(h, "mod")) return rc;
+    }
+    if (space == COFDM_HOST) {
+        CU_TRY(cudaMemcpyAsync(points, dout, n_pts * sizeof(float2), cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return COFDM_OK;
+}
+
+int cofdm_demod(cofdm_t *h, int mod, const float *points, size_t n_points, uint8_t *bytes,
+                unsigned long long *ambiguous, int space) {
+    if (!h || !points || !bytes || !valid_mod(mod)) return fail(COFDM_ERR_ARG, "cofdm_demod: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    const size_t n_bytes = (n_points * mod + 7) / 8;
+    if (n_points == 0) return COFDM_OK;
+    const float2 *din = reinterpret_cast<const float2 *>(points); uint8_t *dout = bytes;
+    if (space == COFDM_HOST) {
+        CU_TRY(h->scratch_a.reserve(n_points * sizeof(float2))); CU_TRY(h->scratch_b.reserve(n_bytes));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, points, n_points * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+        din = (const float2 *)h->scratch_a.p; dout = (uint8_t *)h->scratch_b.p;
+    }
+    CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
+    {
+        Timed t(h);
+        const size_t groups = (n_points + 7) / 8;
+        demod_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, h->stream>>>(mod, din, (long long)n_points, dout, (long long)n_bytes, h->amb_dev);
+        if (int rc = check_launch(h, "demod")) return rc;
+    }
+    if (space == COFDM_HOST) CU_TRY(cudaMemcpyAsync(bytes, dout, n_bytes, cudaMemcpyDeviceToHost, h->stream));
+    if (ambiguous || space == COFDM_HOST) {
+        unsigned long long a = 0;
+        CU_TRY(cudaMemcpyAsync(&a, h->amb_dev, sizeof a, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+        if (ambiguous) *ambiguous += a;
+    }
+    return COFDM_OK;
+}
+
+int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *frames, int fmt, int space) {
+    if (!h || !payload || !frames || (fmt != COFDM_CF32 && fmt != COFDM_CI16)) return fail(COFDM_ERR_ARG, "cofdm_tx_batch: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    if (space == COFDM_DEVICE) {
+        Timed t(h);
+        return launch_tx(h, h->stream, payload, n_frames, frames, fmt);
+    }
+    const size_t bpf = (size_t)h->P.bytes_per_frame, fb = (size_t)h->P.frame_len * sample_bytes(fmt);
+    const size_t chunk = std::min<size_t>(n_frames, 2048);
+    for (int i = 0; i < kPipe; i++) { CU_TRY(h->pipe_in[i].reserve(chunk * bpf)); CU_TRY(h->pipe_out[i].reserve(chunk * fb)); }
+    size_t c = 0;
+    for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
+        const size_t n = std::min(chunk, n_frames - f0);
+        const int s = (int)(c % kPipe);
+        cudaStream_t st = h->pipe_stream[s];
+        CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, payload + f0 * bpf, n * bpf, cudaMemcpyHostToDevice, st));
+        if (int rc = launch_tx(h, st, (const uint8_t *)h->pipe_in[s].p, n, h->pipe_out[s].p, fmt)) return rc;
+        CU_TRY(cudaMemcpyAsync((char *)frames + f0 * fb, h->pipe_out[s].p, n * fb, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kPipe; i++) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));
+    return COFDM_OK;
+}
+
+int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
+                           uint8_t *bytes, unsigned long long *ambiguous, const cofdm_rx_taps *taps, int space) {
+    if (!h || !samples || !bytes || (fmt != COFDM_CF32 && fmt != COFDM_CI16)) return fail(COFDM_ERR_ARG, "cofdm_rx_aligned_batch: bad argument");
+    if (frame_stride < (size_t)h->P.rx_len) return fail(COFDM_ERR_ARG, "frame_stride < rx_len");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    const Params &P = h->P;
+    const bool want_taps = taps && (taps->scal || taps->grid || taps->chan || taps->constell || taps->synced);
+    if (space == COFDM_DEVICE) {
+        RxTaps t{};
+        if (want_taps) {
+            t.scal = taps->scal; t.grid = (float2 *)taps->grid; t.chan = (float2 *)taps->chan;
+            t.constell = (float2 *)taps->constell; t.synced = (float2 *)taps->synced;
+        }
+        if (ambiguous) CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
+        {
+            Timed tm(h);
+            if (int rc = launch_rx(h, h->stream, samples, fmt, n_frames, frame_stride, bytes, ambiguous ? h->amb_dev : nullptr, t)) return rc;
+        }
+        if (ambiguous) {
+            unsigned long long a = 0;
+            CU_TRY(cudaMemcpyAsync(&a, h->amb_dev, sizeof a, cudaMemcpyDeviceToHost, h->stream));
+            CU_TRY(cudaStreamSynchronize(h->stream));
+            *ambiguous += a;
+        }
+        return COFDM_OK;
+    }
+    // ---- COFDM_HOST: chunked pipeline; with taps a single chunk and extra device buffers ----------
+    const size_t sb = sample_bytes(fmt), bpf = (size_t)P.bytes_per_frame;
+    const size_t chunk = want_taps ? n_frames : std::min<size_t>(n_frames, 2048);
+    if (n_frames == 0) return COFDM_OK;
+    for (int i = 0; i < (want_taps ? 1 : kPipe); i++) {
+        CU_TRY(h->pipe_in[i].reserve(chunk * frame_stride * sb));
+        CU_TRY(h->pipe_out[i].reserve(chunk * bpf));
+    }
+    CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    RxTaps t{};
+    const size_t n_sc = 8, n_grid = (size_t)P.num_symb * P.fft_size, n_ch = (size_t)P.num_data_subc,
+                 n_con = (size_t)P.num_data_subc * P.num_symb, n_syn = (size_t)P.rx_len;
+    size_t off_grid = 0, off_ch = 0, off_con = 0, off_syn = 0;
+    if (want_taps) {
+        off_grid = n_frames * n_sc * sizeof(float);
+        off_ch = off_grid + n_frames * n_grid * sizeof(float2);
+        off_con = off_ch + n_frames * n_ch * sizeof(float2);
+        off_syn = off_con + n_frames * n_con * sizeof(float2);
+        CU_TRY(h->scratch_c.reserve(off_syn + n_frames * n_syn * sizeof(float2)));
+        char *b = (char *)h->scratch_c.p;
+        t.scal = (float *)b; t.grid = (float2 *)(b + off_grid); t.chan = (float2 *)(b + off_ch);
+        t.constell = (float2 *)(b + off_con); t.synced = (float2 *)(b + off_syn);
+    }
+    size_t c = 0;
+    for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
+        const size_t n = std::min(chunk, n_frames - f0);
+        const int s = (int)(c % kPipe);
+        cudaStream_t st = h->pipe_stream[s];
+        // the last record only needs rx_len samples (the caller's buffer may end there)
+        const size_t in_bytes = ((n - 1) * frame_stride + (size_t)P.rx_len) * sb;
+        CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, (const char *)samples + f0 * frame_stride * sb, in_bytes, cudaMemcpyHostToDevice, st));
+        if (int rc = launch_rx(h, st, h->pipe_in[s].p, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t)) return rc;
+        CU_TRY(cudaMemcpyAsync(bytes + f0 * bpf, h->pipe_out[s].p, n * bpf, cudaMemcpyDeviceToHost, st));
+    }
+    for (int i = 0; i < kPipe; i++) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));
+    if (want_taps) {
+        char *b = (char *)h->scratch_c.p;
+        if (taps->scal) CU_TRY(cudaMemcpy(taps->scal, b, n_frames * n_sc * sizeof(float), cudaMemcpyDeviceToHost));
+        if (taps->grid) CU_TRY(cudaMemcpy(taps->grid, b + off_grid, n_frames * n_grid * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (taps->chan) CU_TRY(cudaMemcpy(taps->chan, b + off_ch, n_frames * n_ch * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (taps->constell) CU_TRY(cudaMemcpy(taps->constell, b + off_con, n_frames * n_con * sizeof(float2), cudaMemcpyDeviceToHost));
+        if (taps->synced) CU_TRY(cudaMemcpy(taps->synced, b + off_syn, n_frames * n_syn * sizeof(float2), cudaMemcpyDeviceToHost));
+    }
+    if (ambiguous) {
+        unsigned long long a = 0;
+        CU_TRY(cudaMemcpy(&a, h->amb_dev, sizeof a, cudaMemcpyDeviceToHost));
+        *ambiguous += a;
+    }
+    return COFDM_OK;
+}
+
+int cofdm_t2sin_metric(cofdm_t *h, const void *samples, int fmt, size_t n_samples, size_t start, float *rel, int space) {
+    if (!h || !samples || !rel || (fmt != COFDM_CF32 && fmt != COFDM_CI16)) return fail(COFDM_ERR_ARG, "cofdm_t2sin_metric: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    if (start > n_samples || h->P.t2sin_size <= 0) return fail(COFDM_ERR_ARG, "start beyond the capture");
+    const size_t n_blocks = (n_samples - start) / (size_t)h->P.t2sin_size;        // Frame.hpp:152
+    if (n_blocks == 0) return COFDM_OK;
+    if (space == COFDM_DEVICE) {
+        Timed t(h);
+        return launch_t2(h, h->stream, samples, fmt, start, n_blocks, rel);
+    }
+    const size_t sb = sample_bytes(fmt);
+    CU_TRY(h->scratch_a.reserve(n_samples * sb)); CU_TRY(h->scratch_b.reserve(n_blocks * sizeof(float)));
+    CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = launch_t2(h, h->stream, h->scratch_a.p, fmt, start, n_blocks, (float *)h->scratch_b.p)) return rc;
+    CU_TRY(cudaMemcpyAsync(rel, h->scratch_b.p, n_blocks * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return COFDM_OK;
+}
+
+int cofdm_find_t2sin(cofdm_t *h, const void *samples, int fmt, size_t n_samples, size_t start, long long *pos, int space) {
+    if (!h || !samples || !pos || (fmt != COFDM_CF32 && fmt != COFDM_CI16)) return fail(COFDM_ERR_ARG, "cofdm_find_t2sin: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    *pos = COFDM_NOT_FOUND_T2SIN;
+    if (start > n_samples || h->P.t2sin_size <= 0) return COFDM_OK;
+    const size_t n_blocks = (n_samples - start) / (size_t)h->P.t2sin_size;
+    if (n_blocks == 0) return COFDM_OK;
+    const void *dsamp = samples;
+    const size_t sb = sample_bytes(fmt);
+    if (space == COFDM_HOST) {
+        CU_TRY(h->scratch_a.reserve(n_samples * sb));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
+        dsamp = h->scratch_a.p;
+    }
+    CU_TRY(h->scratch_b.reserve(n_blocks * sizeof(float)));
+    CU_TRY(cudaMemsetAsync(h->pos_dev, 0xff, sizeof(unsigned long long), h->stream));
+    if (int rc = launch_t2(h, h->stream, dsamp, fmt, start, n_blocks, (float *)h->scratch_b.p)) return rc;
+    first_above_kernel<<<(unsigned)((n_blocks + 255) / 256), 256, 0, h->stream>>>((const float *)h->scratch_b.p, (long long)n_blocks, h->P.t2_level,
+                                                                                 (long long)start, h->P.t2sin_size, h->pos_dev);
+    if (int rc = check_launch(h, "first_above")) return rc;
+    unsigned long long v = 0;
+    CU_TRY(cudaMemcpyAsync(&v, h->pos_dev, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    *pos = v == ~0ull ? COFDM_NOT_FOUND_T2SIN : (long long)v;
+    return COFDM_OK;
+}
+
+int cofdm_preamble_search(cofdm_t *h, const void *samples, int fmt, size_t n_samples, const long long *starts,
+                          size_t n_starts, float *cor, long long *first, int space) {
+    if (!h || !samples || !starts || (fmt != COFDM_CF32 && fmt != COFDM_CI16)) return fail(COFDM_ERR_ARG, "cofdm_preamble_search: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    if (n_starts == 0) return COFDM_OK;
+    if (space == COFDM_DEVICE) {
+        Timed t(h);
+        return launch_pc(h, h->stream, samples, fmt, n_samples, starts, n_starts, cor, first);
+    }
+    const size_t sb = sample_bytes(fmt), ncor = (size_t)h->P.cor_size;
+    const size_t o_first = n_starts * sizeof(long long), o_cor = 2 * o_first;
+    CU_TRY(h->scratch_a.reserve(n_samples * sb));
+    CU_TRY(h->scratch_b.reserve(o_cor + n_starts * ncor * sizeof(float)));
+    char *b = (char *)h->scratch_b.p;
+    CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemcpyAsync(b, starts, o_first, cudaMemcpyHostToDevice, h->stream));
+    if (int rc = launch_pc(h, h->stream, h->scratch_a.p, fmt, n_samples, (const long long *)b, n_starts,
+                           cor ? (float *)(b + o_cor) : nullptr, (long long *)(b + o_first))) return rc;
+    if (first) CU_TRY(cudaMemcpyAsync(first, b + o_first, o_first, cudaMemcpyDeviceToHost, h->stream));
+    if (cor) CU_TRY(cudaMemcpyAsync(cor, b + o_cor, n_starts * ncor * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return COFDM_OK;
+}
+
+int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n, int space) {
+    if (!h || !in || !out) return fail(COFDM_ERR_ARG, "cofdm_i16_to_cf32: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    if (n == 0) return COFDM_OK;
+    const unsigned *din = (const unsigned *)in; float2 *dout = (float2 *)out;
+    if (space == COFDM_HOST) {
+        CU_TRY(h->scratch_a.reserve(n * 4)); CU_TRY(h->scratch_b.reserve(n * 8));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, in, n * 4, cudaMemcpyHostToDevice, h->stream));
+        din = (const unsigned *)h->scratch_a.p; dout = (float2 *)h->scratch_b.p;
+    }
+    {
+        Timed t(h);
+        i16_to_cf32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(din, dout, (long long)n);
+        if (int rc = check_launch(h, "i16_to_cf32")) return rc;
+    }
+    if (space == COFDM_HOST) {
+        CU_TRY(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, h->stream));
+        CU_TRY(cudaStreamSynchronize(h->stream));
+    }
+    return COFDM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,233 @@
+// fft.cuh -- hand-written FFT building blocks (no cuFFT).
+//
+//  * dft2/4/5/8/16: in-register butterflies, forward (W = e^{-j2pi/R}) or inverse (conjugate).
+//  * warp_fft512<INV>: one warp computes one 512-point FFT as radix 8x8x8.  Each lane owns two
+//    radix-8 butterflies per pass; the two exchanges go through a 640-slot float2 shared-memory
+//    region private to the warp, with padded layouts chosen so every 64-bit access of a warp is
+//    bank-conflict free (see the address maps below).  Only __syncwarp() is needed between passes.
+//  * stockham_pass<R>: generic mixed-radix autosort pass over a thread group, used for the
+//    640-point (5x8x16) coarse-CFO spectrum, the 256-point sync-tone detector and the generic path.
+//
+// These replace the reference's FFTW plans F1-F5 (OFDM/Frame.cpp:16-24,108-112,147-150;
+// OFDM/Frame.hpp:289-295).  All transforms are unnormalised like FFTW's.
+#pragma once
+#include "compat.cuh"
+
+namespace cofdmk {
+
+// multiply by -j (forward W4) or +j (inverse)
+template <bool INV> COFDM_DEV float2 mul_w4(float2 a) { return INV ? make_float2(-a.y, a.x) : make_float2(a.y, -a.x); }
+// multiply by W8^1 = e^{-+j pi/4}
+template <bool INV> COFDM_DEV float2 mul_w8_1(float2 a) {
+    const float r = 0.70710678118654752440f;
+    return INV ? make_float2((a.x - a.y) * r, (a.x + a.y) * r) : make_float2((a.x + a.y) * r, (a.y - a.x) * r);
+}
+// multiply by W8^3 = e^{-+j 3pi/4}
+template <bool INV> COFDM_DEV float2 mul_w8_3(float2 a) {
+    const float r = 0.70710678118654752440f;
+    return INV ? make_float2((-a.x - a.y) * r, (a.x - a.y) * r) : make_float2((a.y - a.x) * r, (-a.x - a.y) * r);
+}
+template <bool INV> COFDM_DEV float2 twid(float2 w) { return INV ? make_float2(w.x, -w.y) : w; }
+
+template <bool INV> COFDM_DEV void dft2(float2 *v) {
+    float2 a = v[0], b = v[1];
+    v[0] = cadd(a, b);
+    v[1] = csub(a, b);
+}
+
+// v[k] = sum_n v[n] W4^{nk}
+template <bool INV> COFDM_DEV void dft4(float2 *v) {
+    float2 e0 = cadd(v[0], v[2]), e1 = csub(v[0], v[2]);
+    float2 o0 = cadd(v[1], v[3]), o1 = mul_w4<INV>(csub(v[1], v[3]));
+    v[0] = cadd(e0, o0);
+    v[1] = cadd(e1, o1);
+    v[2] = csub(e0, o0);
+    v[3] = csub(e1, o1);
+}
+
+template <bool INV> COFDM_DEV void dft5(float2 *v) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
+    float2 t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+    float2 t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+    float2 x0 = cadd(v[0], cadd(t1, t2));
+    float2 m1 = make_float2(v[0].x + c1 * t1.x + c2 * t2.x, v[0].y + c1 * t1.y + c2 * t2.y);
+    float2 m2 = make_float2(v[0].x + c2 * t1.x + c1 * t2.x, v[0].y + c2 * t1.y + c1 * t2.y);
+    float2 q1 = make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y);
+    float2 q2 = make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y);
+    // forward: X1 = m1 - j q1, X4 = m1 + j q1, X2 = m2 - j q2, X3 = m2 + j q2 ; inverse swaps signs
+    float2 jq1 = mul_w4<INV>(q1), jq2 = mul_w4<INV>(q2);   // (-j q) forward, (+j q) inverse
+    v[0] = x0;
+    v[1] = cadd(m1, jq1);
+    v[4] = csub(m1, jq1);
+    v[2] = cadd(m2, jq2);
+    v[3] = csub(m2, jq2);
+}
+
+// v[k] = sum_n v[n] W8^{nk}: radix-2 split (even/odd outputs) followed by two 4-point DFTs
+template <bool INV> COFDM_DEV void dft8(float2 *v) {
+    float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    float2 a1 = cadd(v[1], v[5]), a5 = mul_w8_1<INV>(csub(v[1], v[5]));
+    float2 a2 = cadd(v[2], v[6]), a6 = mul_w4<INV>(csub(v[2], v[6]));
+    float2 a3 = cadd(v[3], v[7]), a7 = mul_w8_3<INV>(csub(v[3], v[7]));
+    float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_w4<INV>(csub(a1, a3));
+    float2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_w4<INV>(csub(a5, a7));
+    v[0] = cadd(b0, b1);
+    v[4] = csub(b0, b1);
+    v[2] = cadd(b2, b3);
+    v[6] = csub(b2, b3);
+    v[1] = cadd(b4, b5);
+    v[5] = csub(b4, b5);
+    v[3] = cadd(b6, b7);
+    v[7] = csub(b6, b7);
+}
+
+// 16 = 4 x 4: n = 4*n1 + n2, k = k1 + 4*k2
+template <bool INV> COFDM_DEV void dft16(float2 *v) {
+    // W16^m, m = 1,2,3,4,6,9 (forward values; conjugated for the inverse by twid<INV>)
+    const float2 w1 = make_float2(0.92387953251128675613f, -0.38268343236508977173f);
+    const float2 w2 = make_float2(0.70710678118654752440f, -0.70710678118654752440f);
+    const float2 w3 = make_float2(0.38268343236508977173f, -0.92387953251128675613f);
+    const float2 w6 = make_float2(-0.70710678118654752440f, -0.70710678118654752440f);
+    const float2 w9 = make_float2(-0.92387953251128675613f, 0.38268343236508977173f);
+    float2 u[4][4];
+#pragma unroll
+    for (int n2 = 0; n2 < 4; n2++) {
+        float2 c[4] = {v[n2], v[4 + n2], v[8 + n2], v[12 + n2]};
+        dft4<INV>(c);
+#pragma unroll
+        for (int k1 = 0; k1 < 4; k1++) u[n2][k1] = c[k1];
+    }
+    u[1][1] = cmul(u[1][1], twid<INV>(w1));
+    u[1][2] = cmul(u[1][2], twid<INV>(w2));
+    u[1][3] = cmul(u[1][3], twid<INV>(w3));
+    u[2][1] = cmul(u[2][1], twid<INV>(w2));
+    u[2][2] = mul_w4<INV>(u[2][2]);
+    u[2][3] = cmul(u[2][3], twid<INV>(w6));
+    u[3][1] = cmul(u[3][1], twid<INV>(w3));
+    u[3][2] = cmul(u[3][2], twid<INV>(w6));
+    u[3][3] = cmul(u[3][3], twid<INV>(w9));
+#pragma unroll
+    for (int k1 = 0; k1 < 4; k1++) {
+        float2 c[4] = {u[0][k1], u[1][k1], u[2][k1], u[3][k1]};
+        dft4<INV>(c);
+#pragma unroll
+        for (int k2 = 0; k2 < 4; k2++) v[k1 + 4 * k2] = c[k2];
+    }
+}
+
+template <int R, bool INV> COFDM_DEV void dftR(float2 *v) {
+    if (R == 2) dft2<INV>(v);
+    else if (R == 4) dft4<INV>(v);
+    else if (R == 5) dft5<INV>(v);
+    else if (R == 8) dft8<INV>(v);
+    else dft16<INV>(v);
+}
+
+// One Stockham autosort pass (decimation in time) of an n-point transform, radix R, where `ns` is
+// the product of the radices already applied.  Butterflies j = tid, tid+nthr, ... < n/R.
+// tw[k] = exp(-j*2*pi*k/n) (forward table, conjugated on the fly for INV).  in != out.
+template <int R, bool INV>
+COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const float2 *tw, int tid, int nthr) {
+    const int m = n / R;
+    const int tstep = n / (ns * R);
+    for (int j = tid; j < m; j += nthr) {
+        const int k = j % ns;
+        float2 v[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            v[q] = in[j + q * m];
+            if (q > 0 && ns > 1) v[q] = cmul(v[q], twid<INV>(__ldg(&tw[(q * k * tstep) % n])));
+        }
+        dftR<R, INV>(v);
+        const int o = (j / ns) * ns * R + k;
+#pragma unroll
+        for (int q = 0; q < R; q++) out[o + q * ns] = v[q];
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp_fft512
+//
+// Index algebra: n = 64*n1 + 8*n2 + n3, k = k1 + 8*k2 + 64*k3 (all digits 0..7)
+//   pass 1  A [k1;n2,n3] = sum_n1 x[n]          W8^{n1 k1}   then * W512^{(8 n2+n3) k1}
+//   pass 2  B [k1,k2;n3] = sum_n2 A'[k1;n2,n3]  W8^{n2 k2}   then * W64^{n3 k2}
+//   pass 3  X [k]        = sum_n3 B'[k1,k2;n3]  W8^{n3 k3}
+// Lane l, half h in {0,1}:  q = l & 7,  p = (l >> 3) + 4h.
+//   pass 1 butterfly (n2=p, n3=q)  i.e. t = 8p+q = l + 32h, inputs at t + 64*n1
+//   pass 2 butterfly (k1=p, n3=q)
+//   pass 3 butterfly (k1=p, k2=q)  -> outputs k = p + 8q + 64*k3
+// Exchange layouts (float2 slots inside the warp's 640-slot region):
+//   E1(k1,n2,n3) = n3 + 8*n2 + 72*k1      writer: fixed k1 -> q + 8p   reader: fixed n2 -> q + 72p
+//   E2(k1,k2,n3) = n3 + 9*k2 + 72*k1      writer: fixed k2 -> q + 72p  reader: fixed n3 -> 9q + 72p
+//   spectrum slot(k) = k + (k >> 2)       writer: fixed k3 -> p + 10q (+const)
+// each of which maps the 32 lanes of a 64-bit access onto the 16 bank pairs exactly twice.
+// ------------------------------------------------------------------------------------------------
+constexpr int kFft512Slots = 640;
+COFDM_DEV int spec_slot(int k) { return k + (k >> 2); }
+
+// Passes 2 and 3 + the two exchanges.  On entry v[h][k1] holds the twiddled pass-1 outputs A' of the
+// lane's two butterflies.  On exit the spectrum is in `work` at spec_slot(k) and visible to the warp.
+// The caller must guarantee that no lane still needs the previous contents of `work`.
+template <bool INV>
+COFDM_DEV void warp_fft512_tail(float2 (&v)[2][8], float2 *work, const float2 *tw_p2, int lane) {
+    const int q = lane & 7, p0 = lane >> 3;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = p0 + 4 * h;
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) work[q + 8 * p + 72 * k1] = v[h][k1];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = p0 + 4 * h;
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) v[h][n2] = work[q + 8 * n2 + 72 * p];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) dft8<INV>(v[h]);
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) {
+        const float2 w = twid<INV>(__ldg(&tw_p2[k2 * 8 + q]));   // same for both halves
+        v[0][k2] = cmul(v[0][k2], w);
+        v[1][k2] = cmul(v[1][k2], w);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = p0 + 4 * h;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) work[q + 9 * k2 + 72 * p] = v[h][k2];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = p0 + 4 * h;
+#pragma unroll
+        for (int n3 = 0; n3 < 8; n3++) v[h][n3] = work[n3 + 9 * q + 72 * p];
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int p = p0 + 4 * h;
+        dft8<INV>(v[h]);
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) work[spec_slot(p + 8 * q + 64 * k3)] = v[h][k3];
+    }
+    __syncwarp();
+}
+
+// Pass 1 on data already in registers: v[h][n1] = x[l + 32h + 64*n1].
+template <bool INV>
+COFDM_DEV void warp_fft512_head(float2 (&v)[2][8], const float2 *tw_p1, int lane) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        dft8<INV>(v[h]);
+        const int t = lane + 32 * h;
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) v[h][k1] = cmul(v[h][k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
+    }
+}
+
+}  // namespace cofdmk

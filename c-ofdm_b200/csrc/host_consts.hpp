@@ -1,0 +1,274 @@
+// host_consts.hpp -- host-side (fp64) construction of everything that is constant for a config:
+// config parsing, sub-carrier maps, twiddles, sync tone, preamble, matched filter, constellations.
+// Product code (no oracle involved): included by cofdm_host.cu and by the emulator harness.
+//
+// Reference behaviour mirrored here (file:line in /root/reference):
+//   config/parser.cpp:4-33      parse_config ("key = long", '#' comments, missing key -> 0)
+//   OFDM/Frame.cpp:31-44        pilot / data-segment sub-carrier map
+//   OFDM/Frame.cpp:99-154       T2SIN mask and tone
+//   OFDM/Frame.cpp:259-294      preamble bytes (mt19937), OFDM preamble, matched filter
+//   OFDM/modulation.cpp:4-36    constellations
+//   OFDM/Frame.hpp:311-321      coarse-CFO window borders
+#pragma once
+#include <cctype>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <fstream>
+#include <map>
+#include <random>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "params.h"
+
+namespace cofdmk {
+
+using ConfigMap = std::map<std::string, long>;
+
+inline ConfigMap parse_config_file(const std::string &path) {
+    std::ifstream f(path);
+    if (!f.is_open()) throw std::runtime_error("Cannot open config file");   // same text as parser.cpp:6
+    ConfigMap cfg;
+    std::string line;
+    while (std::getline(f, line)) {
+        size_t a = 0, b = line.size();
+        while (a < b && std::isspace((unsigned char)line[a])) a++;
+        while (b > a && std::isspace((unsigned char)line[b - 1])) b--;
+        if (a == b || line[a] == '#') continue;
+        const size_t eq = line.find('=', a);
+        if (eq == std::string::npos || eq >= b) continue;
+        std::string key, val;
+        for (size_t i = a; i < eq; i++) if (!std::isspace((unsigned char)line[i])) key += line[i];
+        for (size_t i = eq + 1; i < b; i++) if (!std::isspace((unsigned char)line[i])) val += line[i];
+        cfg[key] = std::stol(val);                                             // throws like parser.cpp:30
+    }
+    return cfg;
+}
+inline long cfg_get(const ConfigMap &c, const char *k) {
+    auto it = c.find(k);
+    return it == c.end() ? 0 : it->second;                                     // operator[] semantics
+}
+
+struct cd { double re, im; };
+inline cd cd_mul(cd a, cd b) { return {a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re}; }
+
+// plain O(n^2)-free host DFT: recursive radix-2 for powers of two, direct sum otherwise (n <= 8192)
+inline void host_dft(std::vector<cd> &x, int sign) {
+    const int n = (int)x.size();
+    if (n <= 1) return;
+    if (n % 2 == 0) {
+        std::vector<cd> e(n / 2), o(n / 2);
+        for (int i = 0; i < n / 2; i++) { e[i] = x[2 * i]; o[i] = x[2 * i + 1]; }
+        host_dft(e, sign);
+        host_dft(o, sign);
+        for (int k = 0; k < n / 2; k++) {
+            const long double ang = sign * 2.0L * 3.14159265358979323846264338327950288L * k / n;
+            const cd w = {(double)cosl(ang), (double)sinl(ang)};
+            const cd t = cd_mul(w, o[k]);
+            x[k] = {e[k].re + t.re, e[k].im + t.im};
+            x[k + n / 2] = {e[k].re - t.re, e[k].im - t.im};
+        }
+        return;
+    }
+    std::vector<cd> y(n);
+    for (int k = 0; k < n; k++) {
+        long double sr = 0, si = 0;
+        for (int j = 0; j < n; j++) {
+            const long double ang = sign * 2.0L * 3.14159265358979323846264338327950288L * ((long long)j * k % n) / n;
+            sr += x[j].re * cosl(ang) - x[j].im * sinl(ang);
+            si += x[j].re * sinl(ang) + x[j].im * cosl(ang);
+        }
+        y[k] = {(double)sr, (double)si};
+    }
+    x = y;
+}
+
+struct HostTables {
+    Params p{};                       // sizes filled, device pointers left null
+    ConfigMap cfg;
+    std::vector<float2> tw_fft, tw_p1, tw_p2, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
+    std::vector<float2> constell[9];  // index = mod type 1,2,4,6,8
+    std::vector<float> t2_mask;
+    std::vector<int16_t> bin_map, data_bin, pilot_bin;
+    std::vector<uint8_t> preamble_bytes;
+    // fp64 originals for the double-precision facade
+    std::vector<cd> t2_tone_d, preamble_td_d, matched_d, mod_preamble_d, constell_d[9];
+    int rx_buf_size = 0, iterations = 0;
+    bool fused512_ok = false;         // the specialised kernels apply to this config
+};
+
+inline float2 f2(cd v) { return make_float2((float)v.re, (float)v.im); }
+inline std::vector<float2> twiddles(int n) {
+    std::vector<float2> t((size_t)(n > 0 ? n : 0));
+    for (int k = 0; k < n; k++) {
+        const long double ang = -2.0L * 3.14159265358979323846264338327950288L * k / n;
+        t[k] = make_float2((float)cosl(ang), (float)sinl(ang));
+    }
+    return t;
+}
+
+inline std::vector<cd> constellation_d(int mod) {
+    std::vector<cd> t((size_t)1 << mod);
+    for (int i = 0; i < (1 << mod); i++) {
+        if (mod == 1) {                                     // psk(i, 5*pi/4, 2)  modulation.cpp:4-9,30-31
+            const double step = M_PI * 2 / 2.0, ang = step * i + M_PI_4 * 5;
+            t[i] = {std::cos(ang), std::sin(ang)};
+        } else {                                            // qam(i, mod)  modulation.cpp:12-20
+            const int num = 1 << (mod / 2);
+            t[i] = {2.0 / (num - 1) * (double)(i % num) - 1.0, 2.0 / (num - 1) * (double)(i >> (mod / 2)) - 1.0};
+        }
+    }
+    return t;
+}
+
+inline HostTables build_tables(const ConfigMap &cfg) {
+    HostTables T;
+    T.cfg = cfg;
+    Params &p = T.p;
+    p.fft_size = (int)cfg_get(cfg, "fft_size");
+    p.num_data_subc = (int)cfg_get(cfg, "num_data_subc");
+    p.num_pilot_subc = (int)cfg_get(cfg, "num_pilot_subc");
+    p.cp_size = (int)cfg_get(cfg, "cp_size");
+    p.num_symb = (int)cfg_get(cfg, "num_symb");
+    p.num_pr_symb = (int)cfg_get(cfg, "num_pr_symb");
+    p.pr_sin_len = (int)cfg_get(cfg, "pr_sin_len");
+    p.t2sin_size = (int)cfg_get(cfg, "T2sin_size");
+    p.mod_type = (int)cfg_get(cfg, "modType");
+    p.mult = (float)cfg_get(cfg, "mult");
+    p.pilot_ampl = (float)((double)cfg_get(cfg, "pilot_ampl") / 1000);
+    p.t2_level = (float)((double)cfg_get(cfg, "T2_sin_level") / 1000);
+    p.pr_level = (float)((double)cfg_get(cfg, "pr_level") / 1000);
+    T.rx_buf_size = (int)cfg_get(cfg, "rx_buf_size");
+    T.iterations = (int)cfg_get(cfg, "iterations");
+    const int N = p.fft_size, ND = p.num_data_subc, NP = p.num_pilot_subc;
+    if (N <= 0 || N > 8192 || NP <= 0 || NP > kMaxPilots || ND <= 0 || p.num_symb <= 0 || p.num_pr_symb <= 0 ||
+        p.cp_size < 0 || p.t2sin_size < 0)
+        throw std::runtime_error("config: unsupported sizes");
+    if (!(p.mod_type == 1 || p.mod_type == 2 || p.mod_type == 4 || p.mod_type == 6 || p.mod_type == 8))
+        throw std::runtime_error("config: modType must be 1, 2, 4, 6 or 8");
+    p.ofdm_len = N + p.cp_size;
+    p.n_sym_rx = p.num_pr_symb + p.num_symb;
+    p.rx_len = p.ofdm_len * p.n_sym_rx;
+    p.frame_len = p.t2sin_size + p.rx_len;
+    p.seg_step = ND / NP + 1;                               // Frame.cpp:9
+    p.seg_size = p.seg_step - 1;                            // Frame.cpp:10
+    p.bytes_per_frame = ND * p.num_symb * p.mod_type / 8;   // Frame.cpp:223
+    p.pts_per_sym = ND;
+    p.cor_size = p.t2sin_size * 2 + p.pr_sin_len;           // Frame.cpp:266
+    if (1 + p.seg_step * (NP / 2) > N / 2 + 1 || NP % 2)
+        throw std::runtime_error("config: sub-carrier map does not fit the FFT");
+    // coarse-CFO windows, evaluated in double exactly as Frame.hpp:311-321 does
+    p.pf_size = p.ofdm_len * p.num_pr_symb;
+    {
+        const double rel_bw = double(ND + NP) / (N);
+        const double rel_pilot_w = rel_bw / NP;
+        p.pf_pilot_w = int(p.pf_size * rel_pilot_w);
+        p.pf_border0 = int((1.0 - rel_bw - rel_pilot_w) / 2.0 * p.pf_size);
+        p.pf_den = NP * p.pf_size;
+    }
+
+    // sub-carrier map (Frame.cpp:31-44): pilot follows its segment in the positive half, precedes it
+    // in the negative half; data points are consumed segment by segment (Frame.cpp:59-62)
+    T.bin_map.assign((size_t)N, (int16_t)-1);
+    T.data_bin.assign((size_t)NP * p.seg_size, 0);
+    T.pilot_bin.assign((size_t)NP, 0);
+    {
+        int j = 0;
+        for (int pos = 1 + p.seg_size; j < NP / 2; j++, pos += p.seg_step) {
+            T.pilot_bin[j] = (int16_t)pos;
+            for (int e = 0; e < p.seg_size; e++) T.data_bin[(size_t)j * p.seg_size + e] = (int16_t)(pos - p.seg_size + e);
+        }
+        for (int pos = N - p.seg_step * (NP / 2); j < NP; j++, pos += p.seg_step) {
+            T.pilot_bin[j] = (int16_t)pos;
+            for (int e = 0; e < p.seg_size; e++) T.data_bin[(size_t)j * p.seg_size + e] = (int16_t)(pos + 1 + e);
+        }
+        for (int i = 0; i < NP * p.seg_size; i++) T.bin_map[T.data_bin[i]] = (int16_t)i;
+        for (int q = 0; q < NP; q++) T.bin_map[T.pilot_bin[q]] = (int16_t)-2;
+    }
+
+    T.tw_fft = twiddles(N);
+    T.tw_pf = twiddles(p.pf_size);
+    T.tw_t2 = twiddles(p.t2sin_size);
+    T.tw_p1.resize(8 * 64);
+    T.tw_p2.resize(8 * 8);
+    for (int k1 = 0; k1 < 8; k1++)
+        for (int t = 0; t < 64; t++) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((t * k1) % 512) / 512.0L;
+            T.tw_p1[k1 * 64 + t] = make_float2((float)cosl(ang), (float)sinl(ang));
+        }
+    for (int k2 = 0; k2 < 8; k2++)
+        for (int n3 = 0; n3 < 8; n3++) {
+            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((n3 * k2) % 64) / 64.0L;
+            T.tw_p2[k2 * 8 + n3] = make_float2((float)cosl(ang), (float)sinl(ang));
+        }
+
+    for (int m : {1, 2, 4, 6, 8}) {
+        T.constell_d[m] = constellation_d(m);
+        for (auto v : T.constell_d[m]) T.constell[m].push_back(f2(v));
+    }
+
+    // T2SIN mask (Frame.cpp:120-133) and tone (Frame.cpp:139-154: unnormalised backward DFT of two
+    // deltas of 0.5 => s[n] = .5 e^{j2pi f1 n/N} + .5 e^{j2pi f2 n/N})
+    {
+        const int n = p.t2sin_size, f1 = (int)cfg_get(cfg, "T2_sin_f1"), f2b = (int)cfg_get(cfg, "T2_sin_f2");
+        const int sm = (int)cfg_get(cfg, "smooth");
+        T.t2_mask.assign((size_t)n, 0.f);
+        T.t2_tone_d.assign((size_t)n, cd{0, 0});
+        if (n > 0) {
+            auto clampi = [&](int v) { return v < 0 ? 0 : (v > n - 1 ? n - 1 : v); };
+            for (int i = std::max(0, f1 - sm); i <= clampi(f1 + sm); i++) T.t2_mask[i] += 1.0f;
+            for (int i = std::max(0, f2b - sm); i <= clampi(f2b + sm); i++) T.t2_mask[i] += 1.0f;
+            std::vector<cd> spec((size_t)n, cd{0, 0});
+            if (f1 >= 0 && f1 < n) spec[f1] = {0.5, 0};
+            if (f2b >= 0 && f2b < n) spec[f2b] = {0.5, 0};   // same bin twice: the second store wins, as in Frame.cpp:143-144
+            host_dft(spec, +1);
+            T.t2_tone_d = spec;
+        }
+        for (auto v : T.t2_tone_d) T.t2_tone.push_back(f2(v));
+    }
+
+    // preamble: bytes from std::mt19937(pr_seed) through uniform_int_distribution<int>(0,255)
+    // (Frame.cpp:269-272; libstdc++ >= 11 maps a draw to rng() >> 24), BPSK, IFFT/sqrt(N), CP
+    {
+        const int nb = ND * p.num_pr_symb / 8;
+        T.preamble_bytes.resize((size_t)nb);
+        std::mt19937 rng((uint32_t)cfg_get(cfg, "pr_seed"));
+        for (auto &b : T.preamble_bytes) b = (uint8_t)(rng() >> 24);
+        const auto &tab = T.constell_d[1];
+        T.mod_preamble_d.resize((size_t)nb * 8);
+        for (int i = 0; i < nb * 8; i++) T.mod_preamble_d[i] = tab[(T.preamble_bytes[i >> 3] >> (7 - (i & 7))) & 1];
+        T.preamble_td_d.assign((size_t)p.pf_size, cd{0, 0});
+        const double amp = (double)cfg_get(cfg, "pilot_ampl") / 1000, nf = std::sqrt((double)N);
+        for (int s = 0; s < p.num_pr_symb; s++) {
+            std::vector<cd> grid((size_t)N, cd{0, 0});
+            for (int q = 0; q < NP; q++) grid[T.pilot_bin[q]] = {amp, 0};
+            for (int i = 0; i < NP * p.seg_size; i++) grid[T.data_bin[i]] = T.mod_preamble_d[(size_t)s * ND + i];
+            host_dft(grid, +1);
+            cd *dst = T.preamble_td_d.data() + (size_t)s * p.ofdm_len;
+            for (int n = 0; n < N; n++) dst[p.cp_size + n] = {grid[n].re / nf, grid[n].im / nf};
+            for (int n = 0; n < p.cp_size; n++) dst[n] = dst[n + N];
+        }
+        // matched filter = conj(first pr_sin_len samples) / ||.||_2  (Frame.cpp:285-293)
+        T.matched_d.resize((size_t)p.pr_sin_len);
+        double norm = 0;
+        for (int i = 0; i < p.pr_sin_len; i++) {
+            const cd v = i < p.pf_size ? T.preamble_td_d[i] : cd{0, 0};
+            T.matched_d[i] = {v.re, -v.im};
+            norm += v.re * v.re + v.im * v.im;
+        }
+        norm = std::sqrt(norm);
+        for (auto &v : T.matched_d) { v.re /= norm; v.im /= norm; }
+        for (auto v : T.preamble_td_d) T.preamble_td.push_back(f2(v));
+        for (auto v : T.matched_d) T.matched.push_back(f2(v));
+        for (auto v : T.mod_preamble_d) T.mod_preamble.push_back(f2(v));
+    }
+
+    T.fused512_ok = (N == 512 && p.cp_size == 128 && ND == 256 && NP == 8 && p.num_pr_symb == 1 &&
+                     p.num_symb >= 1 && p.num_symb <= kMaxFusedSymb && p.t2sin_size % 2 == 0 && p.pr_sin_len <= 128 * 5);
+    return T;
+}
+
+}  // namespace cofdmk

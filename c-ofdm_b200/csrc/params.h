@@ -1,0 +1,64 @@
+// params.h -- plain-old-data description of one modem configuration, shared by host and device.
+// Everything here is derived from the reference's config file (config/config.txt keys, consumed
+// at OFDM/Frame.cpp:99-105,157-176,213-226,259-267) by cofdm_host.cu; the kernels never parse anything.
+#pragma once
+#include <stdint.h>
+
+namespace cofdmk {
+
+constexpr int kMaxPilots = 128;
+constexpr int kMaxFusedSymb = 15;   // message symbols per frame the fused 512 kernels accept (one warp each)
+
+struct Params {
+    // ---- config keys (names as in config/config.txt) ----
+    int fft_size, num_data_subc, num_pilot_subc, cp_size, num_symb, num_pr_symb;
+    int pr_sin_len, t2sin_size, mod_type;
+    float mult;            // int16 scale of FRAME_FORM::get_int16 (Frame.cpp:252)
+    float pilot_ampl;      // pilot_ampl/1000 (Frame.cpp:172)
+    float t2_level;        // T2_sin_level/1000 (Frame.cpp:105)
+    float pr_level;        // pr_level/1000 (Frame.cpp:261)
+    // ---- derived sizes (Frame.cpp:9-10,168-170,219-225,266) ----
+    int ofdm_len;          // fft_size + cp_size
+    int n_sym_rx;          // num_pr_symb + num_symb (message_with_preamble)
+    int rx_len;            // ofdm_len * n_sym_rx   samples the rx chain consumes per frame
+    int frame_len;         // t2sin_size + rx_len   (output_size)
+    int seg_size, seg_step;
+    int bytes_per_frame;   // usefull_size
+    int pts_per_sym;       // num_data_subc
+    int cor_size;          // 2*t2sin_size + pr_sin_len lags of find_preamble
+    // ---- coarse-CFO windows of pilot_freq_sinh on the preamble (Frame.hpp:311-334) ----
+    int pf_size;           // preamble size = ofdm_len*num_pr_symb
+    int pf_pilot_w;        // window width in bins
+    int pf_border0;        // first border (clamped at 0)
+    // shift = (sum_argmax / num_pilot_subc - pf_size/2) / pf_size  ==  pf_num / pf_den cycles/sample,
+    // pf_num = sum_argmax - num_pilot_subc*(pf_size/2), pf_den = num_pilot_subc*pf_size
+    int pf_den;
+    // ---- device tables (all fp32 roundings of host fp64 values) ----
+    const float2 *tw_fft;        // [fft_size]  exp(-j*2*pi*k/fft_size)
+    const float2 *tw_p1;         // [8][64]     exp(-j*2*pi*t*k1/512)     (fused 512 path, pass-1 twiddles)
+    const float2 *tw_p2;         // [8][8]      exp(-j*2*pi*n3*k2/64)     (fused 512 path, pass-2 twiddles)
+    const float2 *tw_pf;         // [pf_size]   exp(-j*2*pi*k/pf_size)
+    const float2 *tw_t2;         // [t2sin_size]
+    const float *t2_mask;        // [t2sin_size] detect_mask (Frame.cpp:120-133)
+    const float2 *t2_tone;       // [t2sin_size] sync tone (Frame.cpp:139-154)
+    const float2 *preamble_td;   // [pf_size]   ofdm_preamble (Frame.cpp:282)
+    const float2 *matched;       // [pr_sin_len] conjected_sinh_part (Frame.cpp:285-293)
+    const float2 *mod_preamble;  // [num_data_subc*num_pr_symb] (Frame.cpp:283)
+    const float2 *constell;      // [1<<mod_type] (modulation.cpp:23-36)
+    const int16_t *bin_map;      // [fft_size] -1 null, -2 pilot, else data index within the symbol
+    const int16_t *data_bin;     // [num_data_subc] bin of data index i
+    const int16_t *pilot_bin;    // [num_pilot_subc]
+};
+
+// Optional debug/parity taps of the fused rx kernel (device pointers, any may be null).
+struct RxTaps {
+    float *scal;       // [n][8]: shift, a, b, theta, g, pf_num, 0, 0
+    float2 *grid;      // [n][num_symb*fft_size]   normalised message bins (FFT_FORM::read's FFT_buf)
+    float2 *chan;      // [n][num_data_subc]       chan_char_lq
+    float2 *constell;  // [n][num_data_subc*num_symb] equalised points before the demap clamp
+    float2 *synced;    // [n][rx_len]              samples after the three time-domain corrections
+};
+
+enum SampleFormat { kCF32 = 0, kCI16 = 1 };
+
+}  // namespace cofdmk

@@ -364,7 +364,8 @@ static void ofdm_form_freq_shift(ofdm_form *o, double shift) {
 /* ---------------------------------------------------------------------------------------------
  * The handle = FRAME_FORM (Frame.hpp:442-519, Frame.cpp:213-256) + T2SIN_FORM + PREAMBLE_FORM
  * ------------------------------------------------------------------------------------------- */
-struct oc_handle {
+/* one FRAME_FORM */
+typedef struct frame_form {
     config_t config;
     /* T2SIN_FORM (Frame.hpp:58-199, Frame.cpp:99-154) */
     int t2_size, t2_f1, t2_f2, t2_smooth;
@@ -385,15 +386,18 @@ struct oc_handle {
     cpx *buf; int16_t *int16_buf;
     cpx *from_sdr_buf; int16_t *from_sdr_int16_buf; long from_sdr_size;
     int usefull_size, output_size;
-};
+} frame_form;
+
+/* like reference main.cpp:23-24 the handle owns a tx FRAME_FORM and an rx FRAME_FORM */
+struct oc_handle { frame_form *tx_frame, *rx_frame; };
 
 static __thread char g_err[256];
 
 const char *oc_kind(void) { return "port"; }
 const char *oc_last_error(void) { return g_err; }
 
-oc_handle *oc_create(const char *config_path) {
-    oc_handle *h = (oc_handle *)calloc(1, sizeof *h);
+static frame_form *frame_form_create(const char *config_path) {
+    frame_form *h = (frame_form *)calloc(1, sizeof *h);
     if (cfg_parse(config_path, &h->config, g_err, sizeof g_err)) { free(h); return NULL; }
     const config_t *c = &h->config;
     /* T2SIN_FORM::T2SIN_FORM  Frame.cpp:99-136 */
@@ -468,7 +472,7 @@ oc_handle *oc_create(const char *config_path) {
     return h;
 }
 
-void oc_destroy(oc_handle *h) {
+static void frame_form_destroy(frame_form *h) {
     if (!h) return;
     fftw_destroy_plan(h->detect_plan);
     fft_form_free(&h->preamble.fft_task); fft_form_free(&h->message.fft_task); fft_form_free(&h->message_with_preamble.fft_task);
@@ -478,7 +482,22 @@ void oc_destroy(oc_handle *h) {
     free(h);
 }
 
-void oc_get_sizes(const oc_handle *h, oc_sizes *o) {
+oc_handle *oc_create(const char *config_path) {
+    frame_form *tx = frame_form_create(config_path);
+    if (!tx) return NULL;
+    frame_form *rx = frame_form_create(config_path);
+    if (!rx) { frame_form_destroy(tx); return NULL; }
+    oc_handle *h = (oc_handle *)calloc(1, sizeof *h);
+    h->tx_frame = tx; h->rx_frame = rx;
+    return h;
+}
+void oc_destroy(oc_handle *h) {
+    if (!h) return;
+    frame_form_destroy(h->tx_frame); frame_form_destroy(h->rx_frame); free(h);
+}
+
+void oc_get_sizes(const oc_handle *hh, oc_sizes *o) {
+    const frame_form *h = hh->rx_frame;
     const config_t *c = &h->config;
     memset(o, 0, sizeof *o);
     o->fft_size = h->message.fft_size; o->num_data_subc = h->message.num_data_subc;
@@ -497,8 +516,9 @@ void oc_get_sizes(const oc_handle *h, oc_sizes *o) {
 
 static void put(double *dst, const cpx *src, size_t n) { if (dst) memcpy(dst, src, n * sizeof(cpx)); }
 
-void oc_get_constants(oc_handle *h, double *t2sin_tone, double *t2_mask, uint8_t *preamble_bytes,
+void oc_get_constants(oc_handle *hh, double *t2sin_tone, double *t2_mask, uint8_t *preamble_bytes,
                       double *ofdm_preamble, double *mod_preamble, double *matched, double *constell) {
+    frame_form *h = hh->tx_frame;
     /* the tone and the preamble are frame invariant: rebuild them as the constructor did */
     if (t2sin_tone) {
         cpx *tmp = (cpx *)calloc((size_t)h->t2_size + 1, sizeof(cpx));
@@ -529,7 +549,8 @@ int oc_demod(int mod_type, double *points_inout, int n_points, uint8_t *bytes) {
 }
 
 /* FRAME_FORM::write / get / get_int16  Frame.cpp:235-256 */
-void oc_tx(oc_handle *h, const uint8_t *bytes, double *frame, int16_t *frame_i16) {
+void oc_tx(oc_handle *hh, const uint8_t *bytes, double *frame, int16_t *frame_i16) {
+    frame_form *h = hh->tx_frame;
     ofdm_form_write(&h->message, bytes, (size_t)h->usefull_size);               /* :236 */
     put(frame, h->buf, (size_t)h->output_size);                                 /* :244-246 */
     if (frame_i16) {
@@ -545,7 +566,7 @@ void oc_tx(oc_handle *h, const uint8_t *bytes, double *frame, int16_t *frame_i16
 
 /* one block of T2SIN_FORM::corr / find_t2sin  Frame.hpp:112-143 / 164-193.
  * returns 1 and *rel when the block has a usable ratio, 0 when it is skipped (`continue`). */
-static int t2sin_block(oc_handle *h, const cpx *sig, double *rel) {
+static int t2sin_block(frame_form *h, const cpx *sig, double *rel) {
     double total_energy = 0.0, sin_energy = 0.0;
     memcpy(h->detect_buf, sig, (size_t)h->t2_size * sizeof(cpx));
     fftw_execute(h->detect_plan);
@@ -561,7 +582,8 @@ static int t2sin_block(oc_handle *h, const cpx *sig, double *rel) {
     return 1;
 }
 /* T2SIN_FORM::corr  Frame.hpp:96-147 */
-int oc_t2sin_corr(oc_handle *h, const double *sig, long n, double *out) {
+int oc_t2sin_corr(oc_handle *hh, const double *sig, long n, double *out) {
+    frame_form *h = hh->rx_frame;
     int cycles = (int)(n / h->t2_size);
     const cpx *p = (const cpx *)sig;
     for (int i = 0; i < cycles; i++, p += h->t2_size) {
@@ -572,7 +594,7 @@ int oc_t2sin_corr(oc_handle *h, const double *sig, long n, double *out) {
     return cycles;
 }
 /* T2SIN_FORM::find_t2sin  Frame.hpp:150-197 */
-static int find_t2sin(oc_handle *h, const cpx *sig, long n, int start) {
+static int find_t2sin(frame_form *h, const cpx *sig, long n, int start) {
     int cycles = (int)((n - start) / h->t2_size);
     const cpx *p = sig + start;
     for (int i = 0; i < cycles; i++, p += h->t2_size) {
@@ -581,11 +603,11 @@ static int find_t2sin(oc_handle *h, const cpx *sig, long n, int start) {
     }
     return -1;
 }
-int oc_find_t2sin(oc_handle *h, const double *sig, long n, int start) { return find_t2sin(h, (const cpx *)sig, n, start); }
+int oc_find_t2sin(oc_handle *hh, const double *sig, long n, int start) { return find_t2sin(hh->rx_frame, (const cpx *)sig, n, start); }
 
 /* PREAMBLE_FORM::find_corr (store == 1, Frame.cpp:297-335) and find_preamble (store == 0,
  * Frame.cpp:338-378) share one loop in the reference apart from store-vs-return. */
-static int preamble_scan(oc_handle *h, const cpx *input, int start, double *cor) {
+static int preamble_scan(frame_form *h, const cpx *input, int start, double *cor) {
     double norm = 0, re, im;
     const cpx *p = input + start;
     for (int i = 0; i < h->pr_sin_len; i++, p++) { re = creal(*p); im = cimag(*p); norm += re * re + im * im; }
@@ -603,15 +625,17 @@ static int preamble_scan(oc_handle *h, const cpx *input, int start, double *cor)
     }
     return -10;
 }
-void oc_find_corr(oc_handle *h, const double *sig, long n, int start, double *cor) {
+void oc_find_corr(oc_handle *hh, const double *sig, long n, int start, double *cor) {
+    frame_form *h = hh->rx_frame;
     (void)n; preamble_scan(h, (const cpx *)sig, start, cor);
 }
-int oc_find_preamble(oc_handle *h, const double *sig, long n, int start) {
+int oc_find_preamble(oc_handle *hh, const double *sig, long n, int start) {
+    frame_form *h = hh->rx_frame;
     (void)n; return preamble_scan(h, (const cpx *)sig, start, NULL);
 }
 
 /* PREAMBLE_FORM::chan_char_lq  Frame.hpp:389-434 (sums are used where means belong -- kept) */
-static cpx *chan_char_lq(oc_handle *h) {
+static cpx *chan_char_lq(frame_form *h) {
     cpx *pr = ofdm_form_fft(&h->preamble);
     int nce = h->preamble.num_data_subc, nph = nce / 2;
     double mean_x = 0.0, mean_y = 0.0, mean_xy = 0.0, mean_x2 = 0.0, a, b;
@@ -639,7 +663,7 @@ static cpx *chan_char_lq(oc_handle *h) {
 }
 
 /* main.cpp:60-80 == rx.cpp:200-220 on the samples sitting in buf[t2_size ...] */
-static void demod_chain(oc_handle *h, double *scal, double *synced, double *grid, double *chan,
+static void demod_chain(frame_form *h, double *scal, double *synced, double *grid, double *chan,
                         double *constell_out, uint8_t *bytes) {
     double fs = ofdm_form_pilot_freq_sinh(&h->preamble);                                 /* main.cpp:60 */
     ofdm_form_freq_shift(&h->message_with_preamble, fs);                                 /* :61 */
@@ -664,14 +688,16 @@ static void demod_chain(oc_handle *h, double *scal, double *synced, double *grid
     free(constell);
 }
 
-void oc_rx_aligned(oc_handle *h, const double *rx_samples, double *scal, double *synced, double *grid,
+void oc_rx_aligned(oc_handle *hh, const double *rx_samples, double *scal, double *synced, double *grid,
                    double *chan, double *constell, uint8_t *bytes) {
+    frame_form *h = hh->rx_frame;
     memcpy(h->buf + h->t2_size, rx_samples, (size_t)h->message_with_preamble.size * sizeof(cpx));   /* main.cpp:55-58 */
     demod_chain(h, scal, synced, grid, chan, constell, bytes);
 }
 
 /* FRAME_FORM::read  Frame.cpp:239-242 -> OFDM_FORM::read Frame.cpp:201-208 */
-void oc_read(oc_handle *h, const double *frame, double *restored, uint8_t *bytes) {
+void oc_read(oc_handle *hh, const double *frame, double *restored, uint8_t *bytes) {
+    frame_form *h = hh->rx_frame;
     memcpy(h->buf, frame, sizeof(cpx) * (size_t)h->output_size);
     cpx *r = ofdm_form_fft(&h->message);
     put(restored, r, (size_t)h->message.usefull_size);
@@ -679,7 +705,8 @@ void oc_read(oc_handle *h, const double *frame, double *restored, uint8_t *bytes
 }
 
 /* PREAMBLE_FORM::chan_char  Frame.hpp:375-385 */
-void oc_chan_char(oc_handle *h, const double *rx_samples, double *chan) {
+void oc_chan_char(oc_handle *hh, const double *rx_samples, double *chan) {
+    frame_form *h = hh->rx_frame;
     memcpy(h->buf + h->t2_size, rx_samples, (size_t)h->preamble.size * sizeof(cpx));
     cpx *pr = ofdm_form_fft(&h->preamble);
     int nd = h->preamble.num_data_subc, ns = h->preamble.num_symb;
@@ -690,15 +717,16 @@ void oc_chan_char(oc_handle *h, const double *rx_samples, double *chan) {
 }
 
 /* FRAME_FORM::form_int16_to_double  Frame.hpp:472-481 */
-static void form_int16_to_double(oc_handle *h) {
+static void form_int16_to_double(frame_form *h) {
     long len = h->from_sdr_size * 2;
     double *d = (double *)h->from_sdr_buf;
     for (long i = 0; i < len; ++i) d[i] = (double)h->from_sdr_int16_buf[i];
 }
 
 /* rx.cpp:101-235: acquisition state machine over an in-memory capture (see oracle_api.h) */
-int oc_rx_stream(oc_handle *h, const int16_t *capture, long n_samples, int max_frames,
+int oc_rx_stream(oc_handle *hh, const int16_t *capture, long n_samples, int max_frames,
                  long *pr_begin_abs, uint8_t *bytes) {
+    frame_form *h = hh->rx_frame;
     const long block = (long)h->output_size * cfg_get(&h->config, "rx_buf_size");   /* sdr.hpp:141 */
     const long n_blocks = n_samples / block;
     long next_block = 0, cur_block = -1;

@@ -1,0 +1,98 @@
+// emu_kernels.cpp -- compiles the REAL kernel source (c-ofdm_b200/csrc/kernels.cuh) for the CPU
+// thread emulator (cuda_emu.h) and exposes it to pytest through a C ABI.  TEST INFRASTRUCTURE ONLY;
+// see the header of cuda_emu.h.  Built by tests/emu/build_emu.py into tests/emu/libcofdm_emu.so.
+#define COFDM_EMU 1
+#include "cuda_emu.h"
+#include "kernels.cuh"
+#include "host_consts.hpp"
+
+using namespace cofdmk;
+
+struct EmuHandle {
+    HostTables T;
+    Params P;
+};
+
+static void wire(EmuHandle *h) {
+    HostTables &T = h->T;
+    h->P = T.p;
+    Params &P = h->P;
+    P.tw_fft = T.tw_fft.data(); P.tw_p1 = T.tw_p1.data(); P.tw_p2 = T.tw_p2.data();
+    P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
+    P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
+    P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
+    P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
+}
+
+extern "C" {
+
+void *emu_create(const char *config_path) {
+    try {
+        auto *h = new EmuHandle{build_tables(parse_config_file(config_path)), {}};
+        wire(h);
+        return h;
+    } catch (const std::exception &) { return nullptr; }
+}
+void emu_destroy(void *h) { delete (EmuHandle *)h; }
+int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
+
+int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
+                    uint8_t *out, unsigned long long *amb, float *scal, float2 *grid, float2 *chan,
+                    float2 *constell, float2 *synced) {
+    auto *h = (EmuHandle *)hv;
+    if (!h->T.fused512_ok) return -1;
+    const Params P = h->P;
+    RxTaps taps{scal, grid, chan, constell, synced};
+    const int nsym = P.n_sym_rx;
+    auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(32 * nsym), rx_fused512_smem_bytes(nsym), kern); };
+    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false>(P, samples, stride, n_frames, out, amb, taps); });
+    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true>(P, samples, stride, n_frames, out, amb, taps); });
+    else run([&] { rx_fused512_kernel<kCF32, false>(P, samples, stride, n_frames, out, amb, taps); });
+    return 0;
+}
+
+int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int fmt) {
+    auto *h = (EmuHandle *)hv;
+    if (!h->T.fused512_ok) return -1;
+    const Params P = h->P;
+    const size_t sm = tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
+    if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(32 * (P.num_symb + 1)), sm, [&] { tx512_kernel<kCI16>(P, payload, n_frames, frames); });
+    else emu::launch(dim3(n_frames), dim3(32 * (P.num_symb + 1)), sm, [&] { tx512_kernel<kCF32>(P, payload, n_frames, frames); });
+    return 0;
+}
+
+int emu_t2sin_metric(void *hv, const void *samples, int fmt, long long start, long long n_blocks, float *rel) {
+    auto *h = (EmuHandle *)hv;
+    const Params P = h->P;
+    if (P.t2sin_size != 256) return -1;
+    const unsigned grid = (unsigned)((n_blocks + kT2WarpsPerCta - 1) / kT2WarpsPerCta);
+    if (fmt == kCI16) emu::launch(dim3(grid), dim3(32 * kT2WarpsPerCta), 0, [&] { t2sin_metric_kernel<kCI16>(P, samples, start, n_blocks, rel); });
+    else emu::launch(dim3(grid), dim3(32 * kT2WarpsPerCta), 0, [&] { t2sin_metric_kernel<kCF32>(P, samples, start, n_blocks, rel); });
+    return 0;
+}
+
+int emu_preamble_corr(void *hv, const void *samples, int fmt, long long n_samples, const long long *starts,
+                      int n_starts, float *cor, long long *first) {
+    auto *h = (EmuHandle *)hv;
+    const Params P = h->P;
+    const size_t sm = (size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2);
+    if (fmt == kCI16) emu::launch(dim3(n_starts), dim3(kPcThreads), sm, [&] { preamble_corr_kernel<kCI16>(P, samples, n_samples, starts, n_starts, cor, first); });
+    else emu::launch(dim3(n_starts), dim3(kPcThreads), sm, [&] { preamble_corr_kernel<kCF32>(P, samples, n_samples, starts, n_starts, cor, first); });
+    return 0;
+}
+
+int emu_mod(void *hv, int mod, const uint8_t *bytes, long long n_bytes, float2 *points, long long n_points) {
+    auto *h = (EmuHandle *)hv;
+    const float2 *table = h->T.constell[mod].data();
+    emu::launch(dim3((unsigned)((n_points + 127) / 128)), dim3(128), 0, [&] { mod_kernel(table, mod, bytes, n_bytes, points, n_points); });
+    return 0;
+}
+
+int emu_demod(void *, int mod, const float2 *points, long long n_points, uint8_t *bytes, long long n_bytes,
+              unsigned long long *amb) {
+    const long long groups = (n_points + 7) / 8;
+    emu::launch(dim3((unsigned)((groups + 127) / 128)), dim3(128), 0, [&] { demod_kernel(mod, points, n_points, bytes, n_bytes, amb); });
+    return 0;
+}
+
+}  // extern "C"
