@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the C-OFDM baseband hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
+
+Metric (BASELINE.json): tx+rx Msamples/s (complex baseband samples, 6016 per frame) and OFDM symbols/s,
+with the fused rx kernel's achieved HBM GB/s against the measured peak.
+
+Workload (BASELINE.json configs[2], SURVEY.md section 8d "config 3"): synthetic batched rx of
+--frames (default 1 Mi) frames per GPU at the shipped config (fft 512, cp 128, 8 symbols + preamble,
+16-QAM), frames produced on the GPU by the tx kernel from seeded payloads and passed through a light
+channel (per-frame CFO + phase + AWGN, torch ops, untimed), complex64 in HBM.
+One "step" = one tx pass (payload bytes -> frames) + one rx pass (frames -> payload bytes) over the
+whole batch.  value = samples through tx and rx per second with everything resident in HBM;
+e2e = the same through the C ABI with HOST (pinned) buffers, H2D and D2H inside the timed region.
+The input (tens of GB) is far larger than the 126 MB L2, so no explicit flush is needed.
+
+--impl reference times the reference's own CPU implementation of the same path (oracle/_ref = the
+unmodified reference sources + stand-in FFT when built, else the C restatement) on the host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+CONFIG = os.path.join(ROOT, "config", "config.txt")
+
+RX_BYTES_PER_FRAME = 46080 + 1024      # (N+CP)(NS+NPR)*8 read + ND*NS*mod/8 written, 16-QAM
+TX_BYTES_PER_FRAME = 1024 + 6016 * 8   # payload read + frame written
+
+
+def n_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the reference's implementation of tx + aligned rx on the host cores
+# ---------------------------------------------------------------------------------------------------
+def cpu_run(n_frames_total, threads, seed=0):
+    """tx + aligned rx of n_frames_total frames split over `threads` workers; returns (seconds, kind,
+    bit_errors).  Each worker owns its own FRAME_FORM pair (the class is not thread-safe)."""
+    from oracle import oracle as O
+    kind = "reference" if O.available("reference") else "port"
+    if kind == "port":
+        O.build("port")
+    per = max(1, n_frames_total // threads)
+    workers = [O.Oracle(kind, CONFIG) for _ in range(threads)]
+    s = workers[0].sizes
+    rng = np.random.default_rng(seed)
+    pay = rng.integers(0, 256, (threads, per, s.usefull_size), dtype=np.uint8)
+    errs = [0] * threads
+
+    def work(t):
+        errs[t] = workers[t].txrx_loop(pay[t])          # whole loop inside the C library (no GIL held)
+
+    th = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+    t0 = time.perf_counter()
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    dt = time.perf_counter() - t0
+    return dt, kind, per * threads, sum(errs), s
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = n_cores()
+    frames = args.cpu_frames or 4000 * cores
+    times = []
+    for _ in range(args.warmup):
+        cpu_run(max(cores, frames // 8), cores)
+    n_done = 0
+    for _ in range(args.steps):
+        dt, kind, n_done, errs, s = cpu_run(frames, cores)
+        times.append(dt)
+    dt = float(np.mean(times))
+    samples = 2 * n_done * s.output_size
+    v = samples / dt / 1e6
+    line = {"impl": "reference", "metric": "tx+rx Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "batched tx + aligned rx, default config.txt (fft512 cp128 8sym+preamble 16-QAM)",
+                       "frames_per_step": n_done, "frame_samples": s.output_size},
+            "ofdm_symbols_s": 2 * n_done * 9 / dt,
+            "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind,
+                             "sample": f"{n_done} frames tx+rx per step on {cores} threads; FFT = stand-in mixed-radix (FFTW3 not installed)"},
+            "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+def native_arm(args):
+    import torch
+    import torch.distributed as dist
+    import cofdm_b200 as cb
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (native arm) needs a CUDA device: there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    m = cb.Modem(CONFIG, device=local)
+    m.use_torch_stream()
+    s = m.sizes
+    F = args.frames
+    # ---- workload: payloads -> tx kernel -> light channel (untimed) -----------------------------------
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    payload = torch.randint(0, 256, (F, s.usefull_size), dtype=torch.uint8, device=dev, generator=g)
+    rx_in = torch.empty((F, s.output_size), dtype=torch.complex64, device=dev)
+    tx_out = torch.empty((F, s.output_size), dtype=torch.complex64, device=dev)
+    m.tx_batch(payload, cb.CF32, out=rx_in)
+    n = torch.arange(s.output_size, device=dev, dtype=torch.float64)
+    CH = 8192
+    for f0 in range(0, F, CH):
+        f1 = min(F, f0 + CH)
+        cfo = (torch.rand((f1 - f0, 1), device=dev, generator=g, dtype=torch.float64) - 0.5) * 0.006
+        ph = torch.rand((f1 - f0, 1), device=dev, generator=g, dtype=torch.float64)
+        rot = torch.polar(torch.ones_like(cfo * n), 2 * torch.pi * (cfo * n + ph)).to(torch.complex64)
+        blk = rx_in[f0:f1] * rot * float(s.mult)
+        noise = torch.randn((f1 - f0, s.output_size, 2), device=dev, generator=g) * 1.5
+        rx_in[f0:f1] = torch.view_as_complex(torch.round(torch.view_as_real(blk) + noise))   # int16-grid samples, like an ADC
+    out_bytes = torch.empty((F, s.usefull_size), dtype=torch.uint8, device=dev)
+    torch.cuda.synchronize()
+
+    def step():
+        m.tx_batch(payload, cb.CF32, out=tx_out)
+        m.rx_aligned_batch(rx_in, n_frames=F, frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes, count_ambiguous=False)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = m.launch_count()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3 * args.steps + 1)]
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    ev[0].record()
+    for k in range(args.steps):
+        m.tx_batch(payload, cb.CF32, out=tx_out)
+        ev[3 * k + 1].record()
+        m.rx_aligned_batch(rx_in, n_frames=F, frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes, count_ambiguous=False)
+        ev[3 * k + 2].record()
+        ev[3 * k + 3].record()
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter() - t_wall0
+    launches = m.launch_count() - l0
+    if world > 1:
+        dist.barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    total_ms = ev[0].elapsed_time(ev[3 * args.steps])
+    tx_ms = float(np.mean([ev[3 * k].elapsed_time(ev[3 * k + 1]) for k in range(args.steps)]))
+    rx_ms = float(np.mean([ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)]))
+    # correctness of what was timed: decoded bytes vs payload (bit errors), boundary-ambiguous symbols
+    _, amb = m.rx_aligned_batch(rx_in, n_frames=min(F, 65536), frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes[:min(F, 65536)])
+    m.rx_aligned_batch(rx_in, n_frames=F, frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes, count_ambiguous=False)
+    diff = (out_bytes ^ payload)
+    bit_err = int(torch.sum(torch.bitwise_count(diff).to(torch.int64)).item()) if hasattr(torch, "bitwise_count") else int((diff != 0).sum().item())
+    frames_bad = int((diff != 0).any(dim=1).sum().item())
+
+    stats = torch.tensor([total_ms, tx_ms, rx_ms], dtype=torch.float64, device=dev)
+    counters = torch.tensor([bit_err, frames_bad, F, amb], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)       # device time, max over ranks
+        dist.all_reduce(counters, op=dist.ReduceOp.SUM)    # the only data-path-adjacent collective: 4 counters over NCCL
+    total_ms, tx_ms, rx_ms = [float(x) for x in stats.tolist()]
+    bit_err, frames_bad, frames_all, amb = [int(x) for x in counters.tolist()]
+
+    # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region ---
+    E = min(args.e2e_frames, F)
+    h_pay = torch.empty((E, s.usefull_size), dtype=torch.uint8).pin_memory()
+    h_frames = torch.empty((E, s.output_size), dtype=torch.complex64).pin_memory()
+    h_rx = torch.empty((E, s.output_size), dtype=torch.complex64).pin_memory()
+    h_out = torch.empty((E, s.usefull_size), dtype=torch.uint8).pin_memory()
+    h_pay.copy_(payload[:E])
+    h_rx.copy_(rx_in[:E])
+    np_pay, np_frames, np_rx, np_out = h_pay.numpy(), h_frames.numpy(), h_rx.numpy(), h_out.numpy()
+
+    def e2e_step():
+        m.tx_batch(np_pay, cb.CF32, out=np_frames)
+        m.rx_aligned_batch(np_rx, n_frames=E, frame_stride=s.output_size, offset=s.t2sin_size, out=np_out, count_ambiguous=False)
+
+    for _ in range(max(1, min(args.warmup, 2))):
+        e2e_step()
+    if world > 1:
+        dist.barrier()
+    e_steps = max(1, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        e2e_step()
+    e_dt = (time.perf_counter() - t0) / e_steps
+    e_ok = bool(np.array_equal(np_out, np_pay)) or int((np_out != np_pay).any(axis=1).sum())
+    e_t = torch.tensor([e_dt], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
+    e_dt = float(e_t.item())
+    e2e_value = world * 2 * E * s.output_size / e_dt / 1e6
+    h2d = E * s.usefull_size + E * s.output_size * 8
+    d2h = E * s.output_size * 8 + E * s.usefull_size
+
+    if rank == 0:
+        peak, peak_src = load_peaks()
+        step_ms = total_ms / args.steps
+        samples_per_step = world * 2 * F * s.output_size
+        value = samples_per_step / (step_ms * 1e-3) / 1e6
+        rx_gbs = RX_BYTES_PER_FRAME * F / (rx_ms * 1e-3) / 1e9
+        tx_gbs = TX_BYTES_PER_FRAME * F / (tx_ms * 1e-3) / 1e9
+        line = {
+            "metric": "tx+rx Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "synthetic batched tx + fused aligned rx, default config.txt (fft512 cp128 8sym+preamble 16-QAM), complex64 in HBM",
+                       "frames_per_gpu": F, "frame_samples": s.output_size, "l2": "inputs (GBs) far larger than the 126 MB L2, no flush needed",
+                       "channel": "per-frame CFO +-0.003 cyc/sample, random phase, AWGN sigma 1.5 LSB, int16 grid"},
+            "ofdm_symbols_s": world * 2 * F * 9 / (step_ms * 1e-3),
+            "rx_msamples_s": world * F * s.output_size / (rx_ms * 1e-3) / 1e6,
+            "tx_msamples_s": world * F * s.output_size / (tx_ms * 1e-3) / 1e6,
+            "rx_frames_s": world * F / (rx_ms * 1e-3), "rx_ms": rx_ms, "tx_ms": tx_ms,
+            "bit_errors": bit_err, "frames_with_errors": frames_bad, "frames_checked": frames_all,
+            "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb,
+            "roofline": {"bound": "hbm", "kernel": "rx_fused512_kernel", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
+                         "frac": rx_gbs / peak, "traffic": None, "peak_source": peak_src,
+                         "algorithmic_bytes_per_frame": RX_BYTES_PER_FRAME, "tx_kernel_gbs": tx_gbs, "tx_frac": tx_gbs / peak},
+            "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "frames_per_step": E, "ms_per_step": e_dt * 1e3, "payload_roundtrip_ok": e_ok if isinstance(e_ok, bool) else f"{e_ok} frames differ",
+                    "path": "cofdm_tx_batch + cofdm_rx_aligned_batch with COFDM_HOST pinned buffers (chunked 3-stream H2D/kernel/D2H)"},
+            "gpu_launches": launches, "wall_ms_per_step": t_wall / args.steps * 1e3, "clocks": clocks,
+        }
+        if not args.no_cpu and world == 1:
+            cores = n_cores()
+            cf = args.cpu_frames or 10000 * cores
+            cpu_run(max(cores, cf // 8), cores)
+            dt, kind, n_done, errs, cs = cpu_run(cf, cores)
+            line["cpu_baseline"] = {"value": 2 * n_done * cs.output_size / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
+                                    "sample": f"{n_done} frames tx+rx on {cores} threads in {dt:.1f} s; FFT = stand-in mixed-radix (FFTW3 not installed)",
+                                    "payload_bytes_wrong": errs}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=1 << 15)
+    ap.add_argument("--cpu-frames", type=int, default=0)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        native_arm(args)
+
+
+if __name__ == "__main__":
+    main()

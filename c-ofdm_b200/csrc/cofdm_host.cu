@@ -100,11 +100,14 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     const int nsym = h->P.n_sym_rx;
     const size_t sm = rx_fused512_smem_bytes(nsym);
     const dim3 grid((unsigned)n_frames), block(32 * nsym);
+    const bool small = nsym <= 9;
     if (fmt == COFDM_CI16) {
         if (((uintptr_t)samples & 15) || (stride * 4) % 16) return fail(COFDM_ERR_ARG, "rx: int16 frames must be 16-byte aligned");
-        rx_fused512_kernel<kCI16, false><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
+        if (small) rx_fused512_kernel<kCI16, false, 9><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
+        else rx_fused512_kernel<kCI16, false, kRxMaxSym><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
     } else if (((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0) {
-        rx_fused512_kernel<kCF32, true><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
+        if (small) rx_fused512_kernel<kCF32, true, 9><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
+        else rx_fused512_kernel<kCF32, true, kRxMaxSym><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
     } else {
         return fail(COFDM_ERR_ARG, "rx: cf32 frames must be 16-byte aligned");
     }
@@ -216,8 +219,10 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     cudaEventCreate(&h->ev1);
     if (T.fused512_ok) {
         const int smr = (int)rx_fused512_smem_bytes(P.n_sym_rx), smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
-        cudaError_t a = cudaFuncSetAttribute(rx_fused512_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
-        cudaError_t b = cudaFuncSetAttribute(rx_fused512_kernel<kCI16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        cudaError_t a = cudaFuncSetAttribute(rx_fused512_kernel<kCF32, true, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        cudaError_t b = cudaFuncSetAttribute(rx_fused512_kernel<kCI16, false, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<kCF32, true, kRxMaxSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        if (b == cudaSuccess) b = cudaFuncSetAttribute(rx_fused512_kernel<kCI16, false, kRxMaxSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)

@@ -67,8 +67,10 @@ COFDM_DEV void load_symbol_direct(float2 *dst, const void *src_frame, int sym, i
 }
 
 // FMT: sample format of `samples`; USE_TMA: stage cf32 frames with cp.async.bulk + mbarrier.
-template <int FMT, bool USE_TMA>
-__global__ void __launch_bounds__(32 * kRxMaxSym)
+// MAXSYM bounds the symbols (= warps) per frame so the register budget can target 3 resident
+// CTAs per SM for the shipped 9-symbol frame.
+template <int FMT, bool USE_TMA, int MAXSYM>
+__global__ void __launch_bounds__(32 * MAXSYM, MAXSYM <= 9 ? 3 : 1)
 rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/,
                    int n_frames, uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous,
                    const RxTaps taps) {

@@ -778,3 +778,28 @@ int oc_rx_stream(oc_handle *hh, const int16_t *capture, long n_samples, int max_
 #undef CARRY
     return found;
 }
+
+/* bench.py CPU baseline: tx -> int16 -> double -> aligned rx, n_frames times (see oracle_api.h) */
+long oc_txrx_loop(oc_handle *hh, const uint8_t *payloads, int n_frames, uint8_t *bytes_out) {
+    frame_form *t = hh->tx_frame, *r = hh->rx_frame;
+    const int us = t->usefull_size, n = t->output_size;
+    double mult = (double)cfg_get(&t->config, "mult");
+    long bad = 0;
+    uint8_t *tmp = (uint8_t *)malloc((size_t)us + 1);
+    for (int f = 0; f < n_frames; f++) {
+        const uint8_t *pay = payloads + (size_t)f * us;
+        ofdm_form_write(&t->message, pay, (size_t)us);                    /* Frame.cpp:235-237 */
+        for (int i = 0; i < n; i++) {                                      /* Frame.cpp:249-256 */
+            cpx v = t->buf[i] * (cpx)mult;
+            t->int16_buf[2 * i] = (int16_t)creal(v);
+            t->int16_buf[2 * i + 1] = (int16_t)cimag(v);
+        }
+        double *d = (double *)r->buf;                                      /* Frame.hpp:472-481 */
+        for (int i = 0; i < 2 * n; i++) d[i] = (double)t->int16_buf[i];
+        uint8_t *out = bytes_out ? bytes_out + (size_t)f * us : tmp;
+        demod_chain(r, NULL, NULL, NULL, NULL, NULL, out);                 /* main.cpp:60-80 */
+        for (int i = 0; i < us; i++) bad += out[i] != pay[i];
+    }
+    free(tmp);
+    return bad;
+}

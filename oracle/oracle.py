@@ -70,6 +70,8 @@ class Oracle:
         lib.oc_chan_char.argtypes = [C.c_void_p] + [C.c_void_p] * 2
         lib.oc_rx_stream.restype = C.c_int
         lib.oc_rx_stream.argtypes = [C.c_void_p, C.c_void_p, C.c_long, C.c_int, C.c_void_p, C.c_void_p]
+        lib.oc_txrx_loop.restype = C.c_long
+        lib.oc_txrx_loop.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         assert lib.oc_kind().decode() == kind
         self.h = None
         if config_path is not None:
@@ -189,3 +191,10 @@ class Oracle:
         out = np.zeros(max_frames * s.usefull_size, dtype=np.uint8)
         k = self.lib.oc_rx_stream(self.h, cap.ctypes.data, n, max_frames, pos.ctypes.data, out.ctypes.data)
         return pos[:k].copy(), out[:k * s.usefull_size].reshape(k, s.usefull_size).copy()
+
+    def txrx_loop(self, payloads, want_bytes=False):
+        """bench.py CPU baseline: tx -> int16 -> double -> aligned rx for every payload row, in C."""
+        payloads = np.ascontiguousarray(payloads, dtype=np.uint8).reshape(-1, self.sizes.usefull_size)
+        out = np.zeros_like(payloads) if want_bytes else None
+        bad = self.lib.oc_txrx_loop(self.h, payloads.ctypes.data, len(payloads), out.ctypes.data if want_bytes else None)
+        return (bad, out) if want_bytes else bad

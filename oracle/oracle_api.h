@@ -95,6 +95,12 @@ void oc_chan_char(oc_handle *h, const double *rx_samples, double *chan);
 int oc_rx_stream(oc_handle *h, const int16_t *capture, long n_samples, int max_frames,
                  long *pr_begin_abs, uint8_t *bytes);
 
+/* CPU-baseline loop (bench.py): for each of n_frames payloads do FRAME_FORM::write -> get_int16 ->
+ * (int16 -> double, Frame.hpp:472-481) -> the aligned rx chain of main.cpp:60-80 -> bytes.
+ * Everything runs inside the library so a caller thread holds no interpreter lock.  Returns the number
+ * of payload bytes that did not come back. */
+long oc_txrx_loop(oc_handle *h, const uint8_t *payloads, int n_frames, uint8_t *bytes_out);
+
 #ifdef __cplusplus
 }
 #endif

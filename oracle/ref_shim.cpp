@@ -303,4 +303,25 @@ int oc_rx_stream(oc_handle *h, const int16_t *capture, long n_samples, int max_f
     return found;
 }
 
+long oc_txrx_loop(oc_handle *h, const uint8_t *payloads, int n_frames, uint8_t *bytes_out) {
+    FRAME_FORM &t = h->tx_frame, &r = h->rx_frame;
+    const int us = t.usefull_size;
+    long bad = 0;
+    std::vector<uint8_t> tmp(us);
+    bit_vector v(us);
+    for (int f = 0; f < n_frames; f++) {
+        const uint8_t *pay = payloads + (size_t)f * us;
+        std::memcpy(v.data(), pay, us);
+        t.write(v);                                                       // tx.cpp:35
+        t.get_int16();                                                    // tx.cpp:37 (fills int16_buf)
+        int16_t *q = (int16_t *)t.int16_buf.data();
+        double *d = (double *)r.buf.data();                               // as form_int16_to_double, Frame.hpp:472-481
+        for (int i = 0; i < 2 * t.output_size; i++) d[i] = (double)q[i];
+        uint8_t *out = bytes_out ? bytes_out + (size_t)f * us : tmp.data();
+        demod_chain(r, nullptr, nullptr, nullptr, nullptr, nullptr, out); // main.cpp:60-80
+        for (int i = 0; i < us; i++) bad += out[i] != pay[i];
+    }
+    return bad;
+}
+
 }  // extern "C"

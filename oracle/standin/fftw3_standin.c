@@ -10,6 +10,7 @@
  */
 #include "fftw3.h"
 #include <math.h>
+#include <pthread.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -32,6 +33,28 @@ static void factorize(struct standin_plan_s *p) {
     if (n > 1) p->fac[p->nfac++] = n;
 }
 
+/* Twiddle tables are cached per (n, sign) for the life of the process, so that re-planning the same
+ * size (the reference plans a 640-point transform on every pilot_freq_sinh call, Frame.hpp:289-298)
+ * costs what a wisdom hit costs in FFTW rather than n long-double sin/cos evaluations. */
+static cpx *cached_twiddles(int n, int sign) {
+    static pthread_mutex_t mu = PTHREAD_MUTEX_INITIALIZER;
+    static struct { int n, sign; cpx *tw; } cache[64];
+    static int ncache = 0;
+    pthread_mutex_lock(&mu);
+    for (int i = 0; i < ncache; i++)
+        if (cache[i].n == n && cache[i].sign == sign) { cpx *t = cache[i].tw; pthread_mutex_unlock(&mu); return t; }
+    cpx *tw = (cpx *)malloc(sizeof(cpx) * (size_t)n);
+    const long double two_pi = 6.283185307179586476925286766559005768L;
+    for (int k = 0; k < n; k++) {
+        long double a = two_pi * (long double)k / (long double)n;
+        tw[k].re = (double)cosl(a);
+        tw[k].im = (double)(sign < 0 ? -sinl(a) : sinl(a));
+    }
+    if (ncache < 64) { cache[ncache].n = n; cache[ncache].sign = sign; cache[ncache].tw = tw; ncache++; }
+    pthread_mutex_unlock(&mu);
+    return tw;
+}
+
 static struct standin_plan_s *make_plan(int n, int howmany, cpx *in, int istride, int idist,
                                         cpx *out, int ostride, int odist, int sign) {
     struct standin_plan_s *p = (struct standin_plan_s *)calloc(1, sizeof *p);
@@ -39,15 +62,9 @@ static struct standin_plan_s *make_plan(int n, int howmany, cpx *in, int istride
     p->istride = istride; p->idist = idist; p->ostride = ostride; p->odist = odist; p->sign = sign;
     if (n <= 0) return p;
     factorize(p);
-    p->tw = (cpx *)malloc(sizeof(cpx) * (size_t)n);
+    p->tw = cached_twiddles(n, sign);
     p->wa = (cpx *)malloc(sizeof(cpx) * (size_t)n);
     p->wb = (cpx *)malloc(sizeof(cpx) * (size_t)n);
-    const long double two_pi = 6.283185307179586476925286766559005768L;
-    for (int k = 0; k < n; k++) {
-        long double a = two_pi * (long double)k / (long double)n;
-        p->tw[k].re = (double)cosl(a);
-        p->tw[k].im = (double)(sign < 0 ? -sinl(a) : sinl(a));
-    }
     return p;
 }
 
@@ -67,7 +84,7 @@ fftw_plan fftw_plan_dft_1d(int n, fftw_complex *in, fftw_complex *out, int sign,
 
 void fftw_destroy_plan(fftw_plan p) {
     if (!p) return;
-    free(p->tw); free(p->wa); free(p->wb); free(p);
+    free(p->wa); free(p->wb); free(p);   /* p->tw belongs to the cache */
 }
 
 static inline cpx cmul(cpx a, cpx b) { cpx r = { a.re * b.re - a.im * b.im, a.re * b.im + a.im * b.re }; return r; }

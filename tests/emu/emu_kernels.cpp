@@ -45,9 +45,9 @@ int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_f
     RxTaps taps{scal, grid, chan, constell, synced};
     const int nsym = P.n_sym_rx;
     auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(32 * nsym), rx_fused512_smem_bytes(nsym), kern); };
-    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false>(P, samples, stride, n_frames, out, amb, taps); });
-    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true>(P, samples, stride, n_frames, out, amb, taps); });
-    else run([&] { rx_fused512_kernel<kCF32, false>(P, samples, stride, n_frames, out, amb, taps); });
+    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym>(P, samples, stride, n_frames, out, amb, taps); });
+    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym>(P, samples, stride, n_frames, out, amb, taps); });
+    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym>(P, samples, stride, n_frames, out, amb, taps); });
     return 0;
 }
 

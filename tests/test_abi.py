@@ -1,0 +1,54 @@
+"""The C-ABI shared library: builds for sm_100a, loads, exports every symbol include/cofdm.h declares,
+and fails loudly (never falls back) without a GPU.  No compute calls here."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+import cofdm_b200 as cb
+from conftest import ROOT, has_gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    cb.build.build_library()
+    return cb.load_library()
+
+
+def test_every_declared_symbol_is_exported(lib):
+    hdr = open(os.path.join(ROOT, "include", "cofdm.h")).read()
+    names = sorted(set(re.findall(r"\b(cofdm_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/cofdm.h but not exported"
+
+
+def test_library_has_sm100a_code_and_no_fft_library():
+    out = os.popen(f"cuobjdump -lelf {cb.LIB_PATH} 2>/dev/null").read()
+    assert "sm_100a" in out
+    deps = os.popen(f"ldd {cb.LIB_PATH}").read()
+    assert "cufft" not in deps and "cublas" not in deps and "torch" not in deps
+
+
+def test_config_error_is_reported(lib):
+    h = C.c_void_p()
+    rc = lib.cofdm_create(b"/nonexistent/config.txt", 0, C.byref(h))
+    assert rc == -1 and b"Cannot open config file" in lib.cofdm_last_error()
+
+
+@pytest.mark.skipif(has_gpu(), reason="checks the no-GPU behaviour")
+def test_no_gpu_means_loud_failure():
+    with pytest.raises(cb.CofdmError, match="no CPU fallback"):
+        cb.Modem(os.path.join(ROOT, "config", "config.txt"))
+
+
+def test_package_never_touches_the_oracle():
+    """the product tree must not import, link or load anything under oracle/"""
+    pkg = os.path.join(ROOT, "c-ofdm_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                txt = open(os.path.join(dp, f), errors="ignore").read()
+                assert "oracle/" not in txt.replace("no oracle", "") or f == "synth.py" and "from oracle" not in txt, f
+                assert "import oracle" not in txt and "from oracle" not in txt and "libcofdm_oracle" not in txt, f

@@ -1,0 +1,79 @@
+"""The real kernel source (c-ofdm_b200/csrc/*.cuh) executed by the CPU thread emulator and checked
+against the oracle: index maps, exchange layouts, bit packing, arithmetic.  Small sizes only."""
+import numpy as np
+import pytest
+
+import parity_checks as pc
+from emu_backend import EmuModem
+
+
+@pytest.fixture(scope="module")
+def emu(cfg_dir, port):
+    ms = {mt: EmuModem(cfg_dir[mt], port[mt].sizes) for mt in (1, 2, 4, 6, 8)}
+    yield ms
+    for m in ms.values():
+        m.close()
+
+
+@pytest.mark.parametrize("mt", [1, 2, 4, 6, 8])
+def test_mod_demod(emu, port, mt):
+    pc.check_mod_demod(emu[mt], port[mt], mt)
+
+
+@pytest.mark.parametrize("mt", [1, 4, 8])
+def test_tx(emu, port, mt):
+    st = pc.check_tx(emu[mt], port[mt], n_frames=2)
+    assert st["rel_l2"] < 5e-7
+
+
+@pytest.mark.parametrize("mt,fmt", [(4, "i16"), (4, "cf32"), (2, "i16"), (6, "cf32"), (1, "i16"), (8, "i16")])
+def test_rx_fused_against_oracle(emu, port, mt, fmt):
+    pay, rec = pc.impaired_records(port[mt], 3, seed=10 * mt)
+    st = pc.check_rx_against_oracle(emu[mt], port[mt], rec, fmt)
+    assert st["shift_mismatch"] == 0
+    assert max(st["synced"], st["grid"], st["constell"]) < 2e-6
+
+
+def test_rx_fused_golden_vectors(emu, port, golden_vectors):
+    """committed outputs of the compiled reference (default modType) as the expected values"""
+    g = golden_vectors
+    want = [{k: g[f"m4_rx_{k}"][i] for k in ("scal", "synced", "grid", "chan", "constell", "bytes")} for i in range(2)]
+    st = pc.check_rx_against_oracle(emu[4], port[4], g["m4_rx_in_i16"], "i16", want=want)
+    assert st["shift_mismatch"] == 0 and st["differing"] == 0
+
+
+def test_rx_non_tma_path_is_identical(emu, port):
+    pay, rec = pc.impaired_records(port[4], 2, seed=3)
+    x = pc.cplx(rec).astype(np.complex64)
+    a, _ = emu[4].rx_aligned_batch(x)
+    emu[4].use_tma = 0
+    b, _ = emu[4].rx_aligned_batch(x)
+    emu[4].use_tma = 1
+    assert np.array_equal(a, b)
+
+
+def test_loopback_clean(emu, port):
+    """tx kernel -> rx kernel, noiseless: every payload byte comes back (all modTypes)"""
+    for mt in (1, 2, 4, 6, 8):
+        s = port[mt].sizes
+        pay = pc.synth.payloads(2, s.usefull_size, seed=mt)
+        fr = emu[mt].tx_batch(pay, 1)
+        out, _ = emu[mt].rx_aligned_batch(fr.reshape(-1, 2), n_frames=2, frame_stride=s.output_size, offset=s.t2sin_size)
+        assert np.array_equal(out, pay), mt
+
+
+def test_sync_kernels_on_reference_capture(emu, port, golden_capture):
+    cap16 = golden_capture["capture_i16"][:40960]
+    cap = pc.cplx(cap16)
+    o = port[4]
+    for x in (cap16, cap.astype(np.complex64)):
+        rel = emu[4].t2sin_metric(x)
+        want = o.t2sin_corr(cap)
+        assert np.nonzero(rel > 0.8)[0].tolist() == np.nonzero(want)[0].tolist() == [42, 74]
+        assert np.abs(rel[want > 0] - want[want > 0]).max() < 1e-6
+        assert emu[4].find_t2sin(x, 0) == 10752 and emu[4].find_t2sin(x, 11000) == o.find_t2sin(cap, 11000)
+        starts = np.array([10752, 18976, 5000, 0])
+        first, cor = emu[4].preamble_search(x, starts, want_cor=True)
+        assert first.tolist() == [o.find_preamble(cap, int(p)) for p in starts] == [11039, 19301, -10, -10]
+        for p, c in zip(starts, cor):
+            assert np.abs(c - o.find_corr(cap, int(p))).max() < 1e-6
