@@ -61,6 +61,8 @@ def load_library():
     lib.cofdm_query.argtypes = [vp, C.POINTER(Sizes)]
     lib.cofdm_set_stream.argtypes = [vp, vp]
     lib.cofdm_synchronize.argtypes = [vp]
+    lib.cofdm_own_stream.argtypes = [vp]
+    lib.cofdm_own_stream.restype = vp
     lib.cofdm_get_constants.argtypes = [vp] + [vp] * 6
     lib.cofdm_mod.argtypes = [vp, ci, vp, sz, vp, ci]
     lib.cofdm_demod.argtypes = [vp, ci, vp, sz, vp, vp, ci]
@@ -151,6 +153,9 @@ class Modem:
         import torch
         self._chk(self.lib.cofdm_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)))
 
+    def use_own_stream(self):
+        self._chk(self.lib.cofdm_set_stream(self.h, C.c_void_p(self.lib.cofdm_own_stream(self.h))))
+
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.cofdm_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
@@ -169,8 +174,17 @@ class Modem:
     def _new(self, like, shape, dtype):
         if _is_torch(like):
             import torch
+            if like.is_cuda:
+                # device-space calls are stream-ordered with the caller's torch work
+                self.lib.cofdm_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(like.device).cuda_stream))
             return torch.empty(shape, dtype=getattr(torch, dtype), device=like.device)
         return np.empty(shape, dtype=getattr(np, dtype))
+
+    def _follow(self, x):
+        """enqueue on torch's current stream when `x` is a CUDA tensor (no-op for host arrays)"""
+        if _is_torch(x) and x.is_cuda:
+            import torch
+            self.lib.cofdm_set_stream(self.h, C.c_void_p(torch.cuda.current_stream(x.device).cuda_stream))
 
     # ---- constants ------------------------------------------------------------------------------------
     def constants(self):
@@ -186,6 +200,7 @@ class Modem:
 
     # ---- Modulation::mod / demod ------------------------------------------------------------------------
     def mod(self, data, mod_type=None):
+        self._follow(data)
         mod_type = mod_type or self.sizes.mod_type
         n_bytes = int(np.prod(tuple(data.shape)))
         n_pts = (n_bytes * 8 + mod_type - 1) // mod_type
@@ -194,6 +209,7 @@ class Modem:
         return out
 
     def demod(self, points, mod_type=None):
+        self._follow(points)
         """-> (bytes, ambiguous_count)"""
         mod_type = mod_type or self.sizes.mod_type
         n_pts = _n_samples(points, CF32)
@@ -204,6 +220,7 @@ class Modem:
 
     # ---- FRAME_FORM::write + get / get_int16 ------------------------------------------------------------
     def tx_batch(self, payload, fmt=CF32, out=None):
+        self._follow(payload)
         s = self.sizes
         n_bytes = int(np.prod(tuple(payload.shape)))
         if n_bytes % s.usefull_size:
@@ -219,6 +236,7 @@ class Modem:
         """samples: [n_frames, rx_len] records (or any flat layout with frame_stride/offset in samples).
         -> bytes [n_frames, usefull_size]  (+ dict of taps, + ambiguous count)"""
         s = self.sizes
+        self._follow(samples)
         fmt = _fmt_of(samples)
         total = _n_samples(samples, fmt)
         frame_stride = frame_stride or s.rx_len
@@ -231,7 +249,7 @@ class Modem:
         space = _space(samples, out)
         tap_bufs, tp = None, None
         if taps:
-            tap_bufs = dict(scal=self._new(samples, (n_frames, 8), "float32"),
+            tap_bufs = dict(scal=self._new(samples, (n_frames, 48), "float32"),
                             grid=self._new(samples, (n_frames, s.num_symb * s.fft_size), "complex64"),
                             chan=self._new(samples, (n_frames, s.num_data_subc), "complex64"),
                             constell=self._new(samples, (n_frames, s.constell_size), "complex64"),
@@ -248,6 +266,7 @@ class Modem:
 
     # ---- sync ------------------------------------------------------------------------------------------------
     def t2sin_metric(self, samples, start=0):
+        self._follow(samples)
         fmt = _fmt_of(samples)
         n = _n_samples(samples, fmt)
         nb = max(0, (n - start) // self.sizes.t2sin_size)
@@ -256,6 +275,7 @@ class Modem:
         return out
 
     def find_t2sin(self, samples, start=0):
+        self._follow(samples)
         fmt = _fmt_of(samples)
         n = _n_samples(samples, fmt)
         pos = C.c_longlong(0)
@@ -263,6 +283,7 @@ class Modem:
         return int(pos.value)
 
     def preamble_search(self, samples, starts, want_cor=False):
+        self._follow(samples)
         fmt = _fmt_of(samples)
         n = _n_samples(samples, fmt)
         ns = int(np.prod(tuple(starts.shape)))
@@ -273,6 +294,7 @@ class Modem:
         return (first, cor) if want_cor else first
 
     def i16_to_cf32(self, samples):
+        self._follow(samples)
         n = _n_samples(samples, CI16)
         out = self._new(samples, (n,), "complex64")
         self._chk(self.lib.cofdm_i16_to_cf32(self.h, _ptr(samples), _ptr(out), n, _space(samples, out)))

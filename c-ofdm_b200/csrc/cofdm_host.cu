@@ -98,27 +98,37 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "rx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
     if (n_frames == 0) return COFDM_OK;
     const int nsym = h->P.n_sym_rx;
-    const size_t sm = rx_fused512_smem_bytes(nsym);
-    const dim3 grid((unsigned)n_frames), block(32 * nsym);
+    const size_t sm = rx512_smem_bytes(nsym);
+    const dim3 grid((unsigned)n_frames), block(rx512_threads(nsym));
+    if ((uintptr_t)bytes & 3) return fail(COFDM_ERR_ARG, "rx: the output byte buffer must be 4-byte aligned");
     const bool small = nsym <= 9;
-    if (fmt == COFDM_CI16) {
-        if (((uintptr_t)samples & 15) || (stride * 4) % 16) return fail(COFDM_ERR_ARG, "rx: int16 frames must be 16-byte aligned");
-        if (small) rx_fused512_kernel<kCI16, false, 9><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
-        else rx_fused512_kernel<kCI16, false, kRxMaxSym><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
-    } else if (((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0) {
-        if (small) rx_fused512_kernel<kCF32, true, 9><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
-        else rx_fused512_kernel<kCF32, true, kRxMaxSym><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps);
-    } else {
-        return fail(COFDM_ERR_ARG, "rx: cf32 frames must be 16-byte aligned");
+    const bool want = taps.scal || taps.grid || taps.chan || taps.constell || taps.synced;
+    const bool tma = fmt == COFDM_CF32 && ((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0;
+    // cf32 records that are not 16-byte aligned (a frame cut out of a capture) and int16 records use plain loads
+#define COFDM_RX_LAUNCH(F, T, S, W) rx_fused512_kernel<F, T, S, W><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps)
+#define COFDM_RX_PICK(F, T)                                                                    \
+    do {                                                                                       \
+        if (small) { if (want) COFDM_RX_LAUNCH(F, T, 9, true); else COFDM_RX_LAUNCH(F, T, 9, false); } \
+        else { if (want) COFDM_RX_LAUNCH(F, T, kRxMaxSym, true); else COFDM_RX_LAUNCH(F, T, kRxMaxSym, false); } \
+    } while (0)
+    if (fmt == COFDM_CI16) COFDM_RX_PICK(kCI16, false);
+    else if (tma) COFDM_RX_PICK(kCF32, true);
+    else COFDM_RX_PICK(kCF32, false);
+#undef COFDM_RX_PICK
+#undef COFDM_RX_LAUNCH
+    if (int rc = check_launch(h, "rx_fused512")) return rc;
+    if (taps.synced != nullptr && taps.scal != nullptr) {
+        rx_synced_fixup_kernel<<<grid, 128, 0, st>>>(h->P, (int)n_frames, taps);
+        return check_launch(h, "rx_synced_fixup");
     }
-    return check_launch(h, "rx_fused512");
+    return COFDM_OK;
 }
 
 int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt) {
     if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "tx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
     if (n_frames == 0) return COFDM_OK;
     const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
-    const dim3 grid((unsigned)n_frames), block(32 * (h->P.num_symb + 1));
+    const dim3 grid((unsigned)n_frames), block(tx512_threads(h->P.num_symb));
     if (fmt == COFDM_CI16) tx512_kernel<kCI16><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
     else tx512_kernel<kCF32><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
     return check_launch(h, "tx512");
@@ -218,11 +228,16 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     if (T.fused512_ok) {
-        const int smr = (int)rx_fused512_smem_bytes(P.n_sym_rx), smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
-        cudaError_t a = cudaFuncSetAttribute(rx_fused512_kernel<kCF32, true, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
-        cudaError_t b = cudaFuncSetAttribute(rx_fused512_kernel<kCI16, false, 9>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<kCF32, true, kRxMaxSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
-        if (b == cudaSuccess) b = cudaFuncSetAttribute(rx_fused512_kernel<kCI16, false, kRxMaxSym>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr);
+        const int smr = (int)rx512_smem_bytes(P.n_sym_rx), smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
+        cudaError_t a = cudaSuccess, b = cudaSuccess;
+#define COFDM_RX_ATTR(F, T, S, W) \
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<F, T, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr)
+#define COFDM_RX_ATTR4(F, T) COFDM_RX_ATTR(F, T, 9, true); COFDM_RX_ATTR(F, T, 9, false); COFDM_RX_ATTR(F, T, kRxMaxSym, true); COFDM_RX_ATTR(F, T, kRxMaxSym, false)
+        COFDM_RX_ATTR4(kCF32, true);
+        COFDM_RX_ATTR4(kCF32, false);
+        COFDM_RX_ATTR4(kCI16, false);
+#undef COFDM_RX_ATTR4
+#undef COFDM_RX_ATTR
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)
@@ -255,9 +270,11 @@ int cofdm_query(const cofdm_t *h, cofdm_sizes *o) {
 
 int cofdm_set_stream(cofdm_t *h, void *cuda_stream) {
     if (!h) return fail(COFDM_ERR_ARG, "null handle");
-    h->stream = cuda_stream ? (cudaStream_t)cuda_stream : h->own_stream;
+    h->stream = (cudaStream_t)cuda_stream;       // NULL is CUDA's (legacy) default stream, as everywhere in CUDA
     return COFDM_OK;
 }
+
+void *cofdm_own_stream(const cofdm_t *h) { return h ? (void *)h->own_stream : nullptr; }
 
 int cofdm_synchronize(cofdm_t *h) {
     if (!h) return fail(COFDM_ERR_ARG, "null handle");
@@ -405,7 +422,7 @@ int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_fr
     CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     RxTaps t{};
-    const size_t n_sc = 8, n_grid = (size_t)P.num_symb * P.fft_size, n_ch = (size_t)P.num_data_subc,
+    const size_t n_sc = 48, n_grid = (size_t)P.num_symb * P.fft_size, n_ch = (size_t)P.num_data_subc,
                  n_con = (size_t)P.num_data_subc * P.num_symb, n_syn = (size_t)P.rx_len;
     size_t off_grid = 0, off_ch = 0, off_con = 0, off_syn = 0;
     if (want_taps) {

@@ -38,6 +38,48 @@ COFDM_DEV void cmac_conj(float2 &acc, float2 a, float2 b) {
     acc.y += a.x * b.y - a.y * b.x;
 }
 
+// ---- packed f32x2 math (Blackwell FADD2/FMUL2/FFMA2: two fp32 lanes per issue slot) --------------
+// A float2 used as a PACKED PAIR carries the same quantity of two independent problems
+// (.x = symbol A, .y = symbol B of the pair a warp works on).  Scalar fallback under the emulator.
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ >= 1000)
+COFDM_DEV float2 p_add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+COFDM_DEV float2 p_sub(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+COFDM_DEV float2 p_mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
+COFDM_DEV float2 p_fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+COFDM_DEV float2 p_fms(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, make_float2(-c.x, -c.y)); }   // a*b - c
+#else
+COFDM_DEV float2 p_add(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+COFDM_DEV float2 p_sub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+COFDM_DEV float2 p_mul(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
+COFDM_DEV float2 p_fma(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x + c.x, a.y * b.y + c.y); }
+COFDM_DEV float2 p_fms(float2 a, float2 b, float2 c) { return make_float2(a.x * b.x - c.x, a.y * b.y - c.y); }
+#endif
+COFDM_DEV float2 p_bcast(float s) { return make_float2(s, s); }
+COFDM_DEV float2 p_neg(float2 a) { return make_float2(-a.x, -a.y); }
+
+// packed complex pair: two complex numbers (A, B) held as (re_A, re_B), (im_A, im_B)
+struct pc { float2 re, im; };
+COFDM_DEV pc make_pc(float2 a, float2 b) { pc r; r.re = make_float2(a.x, b.x); r.im = make_float2(a.y, b.y); return r; }
+COFDM_DEV float2 pc_a(pc v) { return make_float2(v.re.x, v.im.x); }
+COFDM_DEV float2 pc_b(pc v) { return make_float2(v.re.y, v.im.y); }
+COFDM_DEV pc cadd(pc a, pc b) { pc r; r.re = p_add(a.re, b.re); r.im = p_add(a.im, b.im); return r; }
+COFDM_DEV pc csub(pc a, pc b) { pc r; r.re = p_sub(a.re, b.re); r.im = p_sub(a.im, b.im); return r; }
+// both members times the same complex scalar w
+COFDM_DEV pc cmul(pc a, float2 w) {
+    pc r;
+    r.re = p_fms(a.re, p_bcast(w.x), p_mul(a.im, p_bcast(w.y)));
+    r.im = p_fma(a.re, p_bcast(w.y), p_mul(a.im, p_bcast(w.x)));
+    return r;
+}
+// member-wise complex product
+COFDM_DEV pc cmul(pc a, pc w) {
+    pc r;
+    r.re = p_fms(a.re, w.re, p_mul(a.im, w.im));
+    r.im = p_fma(a.re, w.im, p_mul(a.im, w.re));
+    return r;
+}
+COFDM_DEV pc cconj(pc a) { pc r; r.re = a.re; r.im = p_neg(a.im); return r; }
+
 // exp(-j*2*pi*turns): the angle is carried in TURNS as a double so that long ramps (thousands of
 // samples times a CFO) lose nothing before the reduction to (-0.5, 0.5]; the sin/cos itself is fp32.
 COFDM_DEV float2 cis_neg_turns(double turns) {
@@ -51,6 +93,42 @@ COFDM_DEV float2 cis_turns(double turns) {
     float s, c;
     sincospif(2.0f * (float)turns, &s, &c);
     return make_float2(c, s);
+}
+
+// exp(+j*2*pi*t) for moderate |t| (a few turns) in ~20 instructions: quarter-turn reduction, then minimax
+// polynomials in f^2 on |f| <= 1/8 turn (fitted offline; fp32 evaluation error 1e-7 abs, i.e. rounding level).
+COFDM_DEV float2 fast_cis_turns(float t) {
+    const float k = rintf(4.0f * t);
+    const float f = fmaf(k, -0.25f, t);
+    const float u = f * f;
+    const float s = f * fmaf(u, fmaf(u, fmaf(u, fmaf(u, 4.1414680329e+01f, -7.6695821688e+01f), 8.1605180747e+01f), -4.1341702049e+01f), 6.2831853070e+00f);
+    const float c = fmaf(u, fmaf(u, fmaf(u, fmaf(u, 5.9220407194e+01f, -8.5442852118e+01f), 6.4939316208e+01f), -1.9739208650e+01f), 9.9999999995e-01f);
+    const int q = (int)k;
+    float cr = (q & 1) ? -s : c, sr = (q & 1) ? c : s;
+    if (q & 2) { cr = -cr; sr = -sr; }
+    return make_float2(cr, sr);
+}
+COFDM_DEV float2 cis_neg_turns_f(float turns) { return fast_cis_turns(-turns); }
+
+// atan2(y, x) / (2*pi) in (-0.5, 0.5]: one fast division + a degree-17 odd minimax polynomial on [0,1]
+// (fp32 evaluation error 2.3e-8 turns = 1.4e-7 rad, the level of atan2f itself)
+COFDM_DEV float fast_atan2_turns(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = mx > 0.0f ? __fdividef(mn, mx) : 0.0f;
+    const float u = a * a;
+    float r = fmaf(u, 3.9099854500e-04f, -2.2920431106e-03f);
+    r = fmaf(u, r, 6.3313740304e-03f);
+    r = fmaf(u, r, -1.1514632549e-02f);
+    r = fmaf(u, r, 1.6709593699e-02f);
+    r = fmaf(u, r, -2.2538297827e-02f);
+    r = fmaf(u, r, 3.1808559006e-02f);
+    r = fmaf(u, r, -5.3050475890e-02f);
+    r = fmaf(u, r, 1.5915492501e-01f);
+    r *= a;
+    if (ay > ax) r = 0.25f - r;
+    if (x < 0.0f) r = 0.5f - r;
+    return y < 0.0f ? -r : r;
 }
 
 COFDM_DEV float2 warp_sum(float2 v) {
@@ -71,6 +149,13 @@ COFDM_DEV double warp_sum(double v) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
     return v;
 }
+
+// ---- named barrier for a sub-team of warps (bar.sync id, nthreads) --------------------------------
+#ifdef COFDM_EMU
+COFDM_DEV void named_bar_sync(int id, int nthreads) { emu::named_barrier(id, nthreads); }
+#else
+COFDM_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+#endif
 
 // ---- mbarrier + TMA 1-D bulk copy (global -> shared) ---------------------------------------------
 // SASS: UBLKCP (cp.async.bulk) + SYNCS (mbarrier).  Under the emulator the copy is a memcpy done by

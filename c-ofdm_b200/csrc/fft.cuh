@@ -29,6 +29,27 @@ template <bool INV> COFDM_DEV float2 mul_w8_3(float2 a) {
 }
 template <bool INV> COFDM_DEV float2 twid(float2 w) { return INV ? make_float2(w.x, -w.y) : w; }
 
+// the same three rotations on a packed complex pair (two problems per instruction)
+template <bool INV> COFDM_DEV pc mul_w4(pc a) {
+    pc r;
+    if (INV) { r.re = p_neg(a.im); r.im = a.re; } else { r.re = a.im; r.im = p_neg(a.re); }
+    return r;
+}
+template <bool INV> COFDM_DEV pc mul_w8_1(pc a) {
+    const float2 r = p_bcast(0.70710678118654752440f);
+    pc o;
+    if (INV) { o.re = p_mul(p_sub(a.re, a.im), r); o.im = p_mul(p_add(a.re, a.im), r); }
+    else { o.re = p_mul(p_add(a.re, a.im), r); o.im = p_mul(p_sub(a.im, a.re), r); }
+    return o;
+}
+template <bool INV> COFDM_DEV pc mul_w8_3(pc a) {
+    const float2 r = p_bcast(0.70710678118654752440f), nr = p_bcast(-0.70710678118654752440f);
+    pc o;
+    if (INV) { o.re = p_mul(p_add(a.re, a.im), nr); o.im = p_mul(p_sub(a.re, a.im), r); }
+    else { o.re = p_mul(p_sub(a.im, a.re), r); o.im = p_mul(p_add(a.re, a.im), nr); }
+    return o;
+}
+
 template <bool INV> COFDM_DEV void dft2(float2 *v) {
     float2 a = v[0], b = v[1];
     v[0] = cadd(a, b);
@@ -65,13 +86,13 @@ template <bool INV> COFDM_DEV void dft5(float2 *v) {
 }
 
 // v[k] = sum_n v[n] W8^{nk}: radix-2 split (even/odd outputs) followed by two 4-point DFTs
-template <bool INV> COFDM_DEV void dft8(float2 *v) {
-    float2 a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
-    float2 a1 = cadd(v[1], v[5]), a5 = mul_w8_1<INV>(csub(v[1], v[5]));
-    float2 a2 = cadd(v[2], v[6]), a6 = mul_w4<INV>(csub(v[2], v[6]));
-    float2 a3 = cadd(v[3], v[7]), a7 = mul_w8_3<INV>(csub(v[3], v[7]));
-    float2 b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_w4<INV>(csub(a1, a3));
-    float2 b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_w4<INV>(csub(a5, a7));
+template <bool INV, class T> COFDM_DEV void dft8(T *v) {
+    T a0 = cadd(v[0], v[4]), a4 = csub(v[0], v[4]);
+    T a1 = cadd(v[1], v[5]), a5 = mul_w8_1<INV>(csub(v[1], v[5]));
+    T a2 = cadd(v[2], v[6]), a6 = mul_w4<INV>(csub(v[2], v[6]));
+    T a3 = cadd(v[3], v[7]), a7 = mul_w8_3<INV>(csub(v[3], v[7]));
+    T b0 = cadd(a0, a2), b2 = csub(a0, a2), b1 = cadd(a1, a3), b3 = mul_w4<INV>(csub(a1, a3));
+    T b4 = cadd(a4, a6), b6 = csub(a4, a6), b5 = cadd(a5, a7), b7 = mul_w4<INV>(csub(a5, a7));
     v[0] = cadd(b0, b1);
     v[4] = csub(b0, b1);
     v[2] = cadd(b2, b3);
@@ -116,18 +137,40 @@ template <bool INV> COFDM_DEV void dft16(float2 *v) {
     }
 }
 
+// 10 = 2 x 5: X[k], X[k+5] = E[k] +- W10^k O[k], E/O = 5-point DFTs of the even/odd inputs
+template <bool INV> COFDM_DEV void dft10(float2 *v) {
+    float2 e[5] = {v[0], v[2], v[4], v[6], v[8]}, o[5] = {v[1], v[3], v[5], v[7], v[9]};
+    dft5<INV>(e);
+    dft5<INV>(o);
+    const float2 w1 = make_float2(0.80901699437494742410f, -0.58778525229247312917f);   // W10^1 (forward)
+    const float2 w2 = make_float2(0.30901699437494742410f, -0.95105651629515357212f);
+    const float2 w3 = make_float2(-0.30901699437494742410f, -0.95105651629515357212f);
+    const float2 w4 = make_float2(-0.80901699437494742410f, -0.58778525229247312917f);
+    o[1] = cmul(o[1], twid<INV>(w1));
+    o[2] = cmul(o[2], twid<INV>(w2));
+    o[3] = cmul(o[3], twid<INV>(w3));
+    o[4] = cmul(o[4], twid<INV>(w4));
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + 5] = csub(e[k], o[k]);
+    }
+}
+
 template <int R, bool INV> COFDM_DEV void dftR(float2 *v) {
     if (R == 2) dft2<INV>(v);
     else if (R == 4) dft4<INV>(v);
     else if (R == 5) dft5<INV>(v);
     else if (R == 8) dft8<INV>(v);
+    else if (R == 10) dft10<INV>(v);
     else dft16<INV>(v);
 }
 
 // One Stockham autosort pass (decimation in time) of an n-point transform, radix R, where `ns` is
 // the product of the radices already applied.  Butterflies j = tid, tid+nthr, ... < n/R.
 // tw[k] = exp(-j*2*pi*k/n) (forward table, conjugated on the fly for INV).  in != out.
-template <int R, bool INV>
+// NOWRAP: the caller guarantees (R-1)*(ns-1)*tstep < n, so the twiddle index needs no reduction mod n.
+template <int R, bool INV, bool NOWRAP = false>
 COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const float2 *tw, int tid, int nthr) {
     const int m = n / R;
     const int tstep = n / (ns * R);
@@ -137,7 +180,7 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
 #pragma unroll
         for (int q = 0; q < R; q++) {
             v[q] = in[j + q * m];
-            if (q > 0 && ns > 1) v[q] = cmul(v[q], twid<INV>(__ldg(&tw[(q * k * tstep) % n])));
+            if (q > 0 && ns > 1) v[q] = cmul(v[q], twid<INV>(__ldg(&tw[NOWRAP ? q * k * tstep : (q * k * tstep) % n])));
         }
         dftR<R, INV>(v);
         const int o = (j / ns) * ns * R + k;
@@ -212,8 +255,10 @@ COFDM_DEV void warp_fft512_tail(float2 (&v)[2][8], float2 *work, const float2 *t
     for (int h = 0; h < 2; h++) {
         const int p = p0 + 4 * h;
         dft8<INV>(v[h]);
+        const int k0 = p + 8 * q;
+        const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
 #pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) work[spec_slot(p + 8 * q + 64 * k3)] = v[h][k3];
+        for (int k3 = 0; k3 < 8; k3++) work[s0 + 80 * k3] = v[h][k3];
     }
     __syncwarp();
 }
@@ -228,6 +273,127 @@ COFDM_DEV void warp_fft512_head(float2 (&v)[2][8], const float2 *tw_p1, int lane
 #pragma unroll
         for (int k1 = 1; k1 < 8; k1++) v[h][k1] = cmul(v[h][k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// warp_fft512p: the same 8x8x8 transform on TWO symbols at once.  Every register holds a packed pair
+// (symbol A, symbol B) so each FADD2/FMUL2/FFMA2 advances both transforms; twiddles are shared.
+// Exchanges use the layouts E1/E2/spec_slot above on two planes of packed pairs inside the warp's
+// 1280-slot region: re-plane Wre[slot] = (re_A, re_B), im-plane Wim[slot] = (im_A, im_B).
+// ------------------------------------------------------------------------------------------------
+template <bool INV>
+COFDM_DEV void warp_fft512p_head(pc (&v)[2][8], const float2 *tw_p1, int lane) {
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        dft8<INV>(v[h]);
+        const int t = lane + 32 * h;
+#pragma unroll
+        for (int k1 = 1; k1 < 8; k1++) v[h][k1] = cmul(v[h][k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
+    }
+}
+
+template <bool INV>
+COFDM_DEV void warp_fft512p_tail(pc (&v)[2][8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane) {
+    const int q = lane & 7, p0 = lane >> 3;
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = q + 8 * (p0 + 4 * h);
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[h][k1].re; Wim[b + 72 * k1] = v[h][k1].im; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = q + 72 * (p0 + 4 * h);
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) { v[h][n2].re = Wre[b + 8 * n2]; v[h][n2].im = Wim[b + 8 * n2]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) dft8<INV>(v[h]);
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) {
+        const float2 w = twid<INV>(__ldg(&tw_p2[k2 * 8 + q]));
+        v[0][k2] = cmul(v[0][k2], w);
+        v[1][k2] = cmul(v[1][k2], w);
+    }
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = q + 72 * (p0 + 4 * h);
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) { Wre[b + 9 * k2] = v[h][k2].re; Wim[b + 9 * k2] = v[h][k2].im; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        const int b = 9 * q + 72 * (p0 + 4 * h);
+#pragma unroll
+        for (int n3 = 0; n3 < 8; n3++) { v[h][n3].re = Wre[b + n3]; v[h][n3].im = Wim[b + n3]; }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; h++) {
+        dft8<INV>(v[h]);
+        const int k0 = (p0 + 4 * h) + 8 * q;
+        const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) { Wre[s0 + 80 * k3] = v[h][k3].re; Wim[s0 + 80 * k3] = v[h][k3].im; }
+    }
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------------
+// team_fft512p: as warp_fft512p, but the 64 butterflies of a pass are spread over a TEAM of two warps
+// (warp h owns butterflies 32h..32h+31, one per lane), which halves the registers and the dependent
+// chain per warp.  The exchanges are shared by the team, so each is fenced by the team's named barrier.
+// ------------------------------------------------------------------------------------------------
+template <bool INV>
+COFDM_DEV void team_fft512p_head(pc (&v)[8], const float2 *tw_p1, int t /* = lane + 32h */) {
+    dft8<INV>(v);
+#pragma unroll
+    for (int k1 = 1; k1 < 8; k1++) v[k1] = cmul(v[k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
+}
+
+// On entry v[k1] = twiddled pass-1 outputs; the caller has already made sure (team barrier) that nobody
+// still reads the planes.  On exit the spectrum of both symbols sits at spec_slot(k) and is visible to the team.
+template <bool INV>
+COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int bar_id) {
+    const int q = lane & 7, p = (lane >> 3) + 4 * h;
+    {
+        const int b = q + 8 * p;
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[k1].re; Wim[b + 72 * k1] = v[k1].im; }
+    }
+    named_bar_sync(bar_id, 64);
+    {
+        const int b = q + 72 * p;
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) { v[n2].re = Wre[b + 8 * n2]; v[n2].im = Wim[b + 8 * n2]; }
+    }
+    named_bar_sync(bar_id, 64);
+    dft8<INV>(v);
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) v[k2] = cmul(v[k2], twid<INV>(__ldg(&tw_p2[k2 * 8 + q])));
+    {
+        const int b = q + 72 * p;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) { Wre[b + 9 * k2] = v[k2].re; Wim[b + 9 * k2] = v[k2].im; }
+    }
+    named_bar_sync(bar_id, 64);
+    {
+        const int b = 9 * q + 72 * p;
+#pragma unroll
+        for (int n3 = 0; n3 < 8; n3++) { v[n3].re = Wre[b + n3]; v[n3].im = Wim[b + n3]; }
+    }
+    named_bar_sync(bar_id, 64);
+    dft8<INV>(v);
+    {
+        const int k0 = p + 8 * q;
+        const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) { Wre[s0 + 80 * k3] = v[k3].re; Wim[s0 + 80 * k3] = v[k3].im; }
+    }
+    named_bar_sync(bar_id, 64);
 }
 
 }  // namespace cofdmk

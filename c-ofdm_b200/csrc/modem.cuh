@@ -21,25 +21,34 @@ COFDM_DEV int extract_bits(const uint8_t *bytes, int n_bytes, int bitpos, int mo
 // pipeline and the reference's fp64 pipeline may legitimately land on different sides.
 constexpr float kAmbigMargin = 2e-4f;
 
+// per-modulation constants, computed once per thread
+struct DemapK { int mod, qshift; float half; };
+COFDM_DEV DemapK make_demapk(int mod) {
+    DemapK k;
+    k.mod = mod;
+    k.qshift = mod >> 1;                                   // lq * L == lq << (mod/2)
+    k.half = 0.5f * (float)((1 << (mod >> 1)) - 1);        // str_size_1 = 1/step = (L-1)/2
+    return k;
+}
+
 // hard demap of one equalised point -> symbol value; `amb` is set when the point lies within
-// kAmbigMargin of a decision boundary.
-COFDM_DEV int demap_point(float2 z, int mod, bool &amb) {
-    if (mod == 1) {
+// kAmbigMargin of a decision boundary.  u = (clamp(v)+1)*half + 0.5 lies in [0.5, L-0.5], so its
+// fractional part is near 0 or 1 exactly when v is near one of the L-1 interior boundaries.
+COFDM_DEV int demap_point(float2 z, const DemapK &k, bool &amb) {
+    if (k.mod == 1) {
         const float s = z.x + z.y;
         amb = fabsf(s) < kAmbigMargin;
         return s > 0.0f ? 1 : 0;
     }
-    const int L = 1 << (mod >> 1);
-    const float half = 0.5f * (float)(L - 1);              // str_size_1 = 1/step = (L-1)/2
     const float re = fminf(fmaxf(z.x, -1.0f), 1.0f);
     const float im = fminf(fmaxf(z.y, -1.0f), 1.0f);
-    const float ui = (re + 1.0f) * half + 0.5f;
-    const float uq = (im + 1.0f) * half + 0.5f;
+    const float ui = fmaf(re + 1.0f, k.half, 0.5f);
+    const float uq = fmaf(im + 1.0f, k.half, 0.5f);
     const int li = (int)ui, lq = (int)uq;                  // uint8_t(...) truncation
-    const float ri = rintf(ui), rq = rintf(uq);
-    amb = (fabsf(ui - ri) < kAmbigMargin && ri >= 1.0f && ri <= (float)(L - 1)) ||
-          (fabsf(uq - rq) < kAmbigMargin && rq >= 1.0f && rq <= (float)(L - 1));
-    return (li | (lq * L)) & 0xff;
+    const float fi = ui - (float)li, fq = uq - (float)lq;
+    amb = fminf(fminf(fi, 1.0f - fi), fminf(fq, 1.0f - fq)) < kAmbigMargin;
+    return (li | (lq << k.qshift)) & 0xff;
 }
+COFDM_DEV int demap_point(float2 z, int mod, bool &amb) { return demap_point(z, make_demapk(mod), amb); }
 
 }  // namespace cofdmk

@@ -52,7 +52,7 @@ struct Params {
 
 // Optional debug/parity taps of the fused rx kernel (device pointers, any may be null).
 struct RxTaps {
-    float *scal;       // [n][8]: shift, a, b, theta, g, pf_num, 0, 0
+    float *scal;       // [n][48]: shift, a, b, theta, g, kc, ..; [16+s] m_s; [32+s] Arg(C_s) (turns)
     float2 *grid;      // [n][num_symb*fft_size]   normalised message bins (FFT_FORM::read's FFT_buf)
     float2 *chan;      // [n][num_data_subc]       chan_char_lq
     float2 *constell;  // [n][num_data_subc*num_symb] equalised points before the demap clamp

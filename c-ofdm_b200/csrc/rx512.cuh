@@ -1,0 +1,581 @@
+// rx512.cuh -- the fused aligned-frame receive kernel (fft 512 / cp 128 / 8 pilots / 256 data sub-carriers,
+// one preamble symbol): samples -> payload bytes in ONE pass, each sample read from HBM once.
+//
+// Reference chain being fused (main.cpp:60-80 == rx.cpp:200-220):
+//   pilot_freq_sinh (Frame.hpp:285-337)  coarse CFO = arg-max of the 640-point preamble spectrum in 8 windows
+//   freq_shift      (Frame.hpp:340-348)  x[i] *= exp(-j 2pi shift i)
+//   cp_freq_sinh    (Frame.hpp:238-263)  per symbol: phi = arg sum conj(x[j]) x[j+512]; x[j] *= exp(-j phi j/512)
+//   pr_phase_sinh   (Frame.hpp:265-274)  theta = arg sum conj(ref[i]) x[i]; x *= exp(-j theta)
+//   chan_char_lq    (Frame.hpp:389-434)  line fit through the preamble's sub-carrier phases
+//   message.fft     (Frame.hpp:276-282, Frame.cpp:73-96)  8 x FFT-512, pilot normalisation, segment correction
+//   equalise + demod (rx.cpp:214-216, modulation.cpp:53-87)
+//
+// Work split of one CTA = one frame:
+//   * FFT teams: two warps per PAIR of OFDM symbols; all FFT arithmetic is packed f32x2 (FADD2/FMUL2/FFMA2)
+//     with symbol A in the low and symbol B in the high half of every register pair.  Each lane owns one
+//     radix-8 butterfly per pass (warp h of the team owns butterflies 32h..32h+31); the two warps meet at
+//     a named barrier (bar.sync id, 64) around each shared-memory exchange.
+//   * two "coarse" warps compute the 640-point spectrum (10x8x8 Stockham) and the 8 arg-maxima
+//     concurrently with the FFT warps, on their own TMA copy of the preamble.
+//   That concurrency is possible because the per-sample rotation of symbol s,
+//       nu_s = shift + phi_s/(2 pi 512),  phi_s = Arg(C_s exp(-j 2pi shift 512)),  C_s = raw CP correlation,
+//   equals  (Arg(C_s)/(2 pi) + m_s)/512  for an INTEGER m_s: the fractional-bin part is known from the
+//   symbol's own CP correlation, and the coarse estimate only contributes m_s whole FFT bins, which is an
+//   index shift (and a factor (-j)^m_s) applied after the transform.
+//   Per-symbol constant phases cancel between a data bin and its segment pilot (Frame.cpp:89-92) except
+//   for message symbol 0, whose pilots are the reference of every segment, and the preamble.
+// Three block-wide barriers per frame; everything else is warp-local.
+#pragma once
+#include "compat.cuh"
+#include "params.h"
+#include "fft.cuh"
+#include "modem.cuh"
+
+namespace cofdmk {
+
+constexpr int kRxMaxSym = 16;
+constexpr int kRxMaxPair = kRxMaxSym / 2;
+constexpr int kCoarseWarps = 2;
+constexpr int kPairSlots = 2 * kFft512Slots;   // float2 slots of one symbol pair
+
+struct RxMisc {
+    uint64_t mbar[kRxMaxSym + 1];
+    float4 qtab[kRxMaxSym][8];       // per FFT warp: Q^r (r<8) -- (reA, reB, imA, imB)
+    float4 wtab[kRxMaxSym][8];       // per FFT warp: equaliser coefficient per segment (reA, reB, imA, imB)
+    float2 pilots[kRxMaxSym][8];     // pilot bins per symbol (shifted bins, before the (-j)^m factor)
+    float pabs[kRxMaxSym];           // sum |pilot| per symbol
+    float theta_t[kRxMaxSym];        // Arg(C_s) in turns
+    int mshift[kRxMaxSym];           // m_s
+    int amax[8];
+    int kc;                          // coarse shift numerator: shift = kc / pf_den
+    double a, b;                     // chan_char_lq line
+    float2 rot_theta;                // exp(-j theta)
+    float theta;
+};
+
+COFDM_HD int rx512_npair(int nsym) { return (nsym + 1) / 2; }
+COFDM_HD int rx512_threads(int nsym) { return 32 * (2 * rx512_npair(nsym) + kCoarseWarps); }
+COFDM_HD size_t rx512_smem_bytes(int nsym) {
+    return (size_t)rx512_npair(nsym) * kPairSlots * sizeof(float2)   // symbol pairs / FFT work planes
+           + 2 * 640 * sizeof(float2)                                // coarse-CFO scratch SA, SB
+           + (size_t)rx512_npair(nsym) * 512                         // demapped symbols
+           + sizeof(RxMisc);
+}
+
+// 640 (or n) samples of one symbol -> shared memory without TMA: int16 wire format, or any source that
+// is not 16-byte aligned (a frame cut out of a capture at an arbitrary sample).
+template <int FMT>
+COFDM_DEV void load_symbol_direct(float2 *dst, const void *src_frame, int sym, int tid, int nthr) {
+    if (FMT == kCI16) {
+        const unsigned *src = reinterpret_cast<const unsigned *>(src_frame) + (size_t)sym * 640;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const uint4 *s4 = reinterpret_cast<const uint4 *>(src);
+            for (int idx = tid; idx < 160; idx += nthr) {
+                const uint4 raw = __ldg(s4 + idx);
+                const unsigned w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+                for (int e = 0; e < 4; e++)
+                    dst[4 * idx + e] = make_float2((float)(short)(w[e] & 0xffffu), (float)(short)(w[e] >> 16));
+            }
+        } else {
+            for (int i = tid; i < 640; i += nthr) {
+                const unsigned w = __ldg(src + i);
+                dst[i] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+            }
+        }
+    } else {
+        const float2 *src = reinterpret_cast<const float2 *>(src_frame) + (size_t)sym * 640;
+        if ((reinterpret_cast<uintptr_t>(src) & 15) == 0) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(src);
+            float4 *d4 = reinterpret_cast<float4 *>(dst);
+            for (int idx = tid; idx < 320; idx += nthr) d4[idx] = __ldg(s4 + idx);
+        } else {
+            for (int i = tid; i < 640; i += nthr) dst[i] = __ldg(src + i);
+        }
+    }
+}
+
+// Constant phase (turns, mod 1) carried into symbol s by freq_shift's global sample index (Frame.hpp:341-347)
+// and by cp_freq_sinh's accumulated `shift` (Frame.hpp:248,261):
+//     Psi_s = shift*640*s + (640/512) * sum_{t<s} phi_t,   phi_t = theta_t - 512*shift + m_t  (turns)
+//           = (640/512) * sum_{t<s} (theta_t + m_t)
+// -- the coarse shift cancels exactly; the integer part is reduced mod 1 in integers.
+COFDM_DEV float sym_turns(const float *theta_t, const int *mshift, int s) {
+    float acc = 0.f;
+    int msum = 0;
+    for (int t = 0; t < s; t++) {
+        acc += theta_t[t] * (640.0f / 512.0f);
+        acc -= rintf(acc);                       // stay within half a turn: keeps the float spacing at ~3e-8 turns
+        msum += mshift[t];
+    }
+    return acc + (float)((5 * msum) & 3) * 0.25f;
+}
+
+// multiply by (-j)^m
+COFDM_DEV float2 mul_negj_pow(float2 v, int m) {
+    switch (m & 3) {
+        case 0: return v;
+        case 1: return make_float2(v.y, -v.x);
+        case 2: return make_float2(-v.x, -v.y);
+        default: return make_float2(-v.y, v.x);
+    }
+}
+
+// TAPS: compile the debug/parity taps in (tests) or out (production, benchmark).
+template <int FMT, bool USE_TMA, int MAXSYM, bool TAPS>
+__global__ void __launch_bounds__(32 * (2 * ((MAXSYM + 1) / 2) + kCoarseWarps), MAXSYM <= 9 ? 3 : 1)
+rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/,
+                   int n_frames, uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous,
+                   const RxTaps taps) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int nsym = P.n_sym_rx;                 // 1 preamble + num_symb message symbols
+    const int npair = rx512_npair(nsym);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x;
+    if (frame >= n_frames) return;
+
+    float2 *X = reinterpret_cast<float2 *>(smem_raw);
+    float2 *SA = X + (size_t)npair * kPairSlots;
+    float2 *SB = SA + 640;
+    uint8_t *symbuf = reinterpret_cast<uint8_t *>(SB + 640);
+    RxMisc *M = reinterpret_cast<RxMisc *>(symbuf + (size_t)npair * 512);
+
+    const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
+    const char *frame_src = reinterpret_cast<const char *>(samples) + (size_t)frame * (size_t)frame_stride * sample_bytes;
+    const bool is_coarse = warp >= 2 * npair;
+    const float inv2pi = 0.15915494309189533577f;
+
+    // ---- stage the frame: one bulk copy per symbol + a private copy of the preamble for the coarse warps ----
+    if (USE_TMA) {
+        if (tid == 0) {
+            for (int s = 0; s <= nsym; s++) mbar_init(&M->mbar[s], 1);
+            mbar_fence_init();
+            for (int s = 0; s < nsym; s++) {
+                mbar_arrive_expect_tx(&M->mbar[s], 640 * 8);
+                tma_load_1d(X + (size_t)(s >> 1) * kPairSlots + (s & 1) * 640, frame_src + (size_t)s * 640 * 8, 640 * 8, &M->mbar[s]);
+            }
+            mbar_arrive_expect_tx(&M->mbar[nsym], 640 * 8);
+            tma_load_1d(SA, frame_src, 640 * 8, &M->mbar[nsym]);
+        }
+        __syncthreads();
+    }
+
+    const int team = warp >> 1, h = warp & 1;      // FFT warps: team = symbol pair, h = which half of the butterflies
+    const int bar_id = 2 + team;
+    const int A = 2 * team, B = 2 * team + 1;
+    const bool hasB = B < nsym;
+    float2 *Wre = X + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
+    float thA = 0.f, thB = 0.f;                    // Arg(C_s) in turns
+    float2 zc[4];                                  // warp 0: conj(ref[j]) * rotated preamble CP sample, j<128
+
+    if (is_coarse) {
+        // ================= coarse CFO: 640-point spectrum of the received preamble, CP included =================
+        const int ct = tid - 64 * npair, cn = 32 * kCoarseWarps, cw = warp - 2 * npair;
+        if (USE_TMA) mbar_wait(&M->mbar[nsym], 0);
+        else { load_symbol_direct<FMT>(SA, frame_src, 0, ct, cn); named_bar_sync(1, cn); }
+        stockham_pass<10, false>(SA, SB, 640, 1, P.tw_pf, ct, cn);
+        named_bar_sync(1, cn);
+        stockham_pass<8, false, true>(SB, SA, 640, 10, P.tw_pf, ct, cn);   // twiddle index <= 7*9*8 < 640
+        named_bar_sync(1, cn);
+        {   // last pass (radix 8, ns = 80): only |X|^2 is kept, as float[640] in SB
+            float *mag = reinterpret_cast<float *>(SB);
+            for (int j = ct; j < 80; j += cn) {
+                float2 v[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    v[q] = SA[j + 80 * q];
+                    if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_pf[q * j]));       // q*j <= 7*79 < 640
+                }
+                dft8<false>(v);
+#pragma unroll
+                for (int q = 0; q < 8; q++) mag[j + 80 * q] = cnorm2(v[q]);
+            }
+        }
+        named_bar_sync(1, cn);
+        {   // arg-max of |spectrum| in the pilot windows, first maximum wins (Frame.hpp:311-331)
+            const float *mag = reinterpret_cast<const float *>(SB);
+            const int np = P.num_pilot_subc, half = P.pf_size / 2;
+            for (int wi = cw; wi < np; wi += kCoarseWarps) {
+                const int win = wi < np / 2 ? wi : wi + 1;             // window np/2 (DC) is skipped
+                int lo = P.pf_border0 + win * P.pf_pilot_w;
+                const int hi = lo + P.pf_pilot_w;
+                if (win == 0 && lo < 0) lo = 0;
+                float best = -1.0f;
+                int besti = 0x7fffffff;
+                for (int ks = lo + lane; ks < hi; ks += 32) {          // ks = fft-shifted index
+                    const float mv = mag[ks < half ? ks + half : ks - half];
+                    if (mv > best) { best = mv; besti = ks; }
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, besti, o);
+                    if (ob > best || (ob == best && oi < besti)) { best = ob; besti = oi; }
+                }
+                if (lane == 0) M->amax[wi] = besti;
+            }
+        }
+        named_bar_sync(1, cn);
+        if (ct == 0) {
+            int k = 0;
+            for (int i = 0; i < P.num_pilot_subc; i++) k += M->amax[i];
+            M->kc = k - P.num_pilot_subc * (P.pf_size / 2);           // shift = kc / pf_den (Frame.hpp:332-334)
+        }
+    } else {
+        // ================= FFT team: symbols A and B, this warp owns butterflies t = lane + 32 h =================
+        float2 *xa = Wre, *xb = Wre + 640;
+        if (USE_TMA) {
+            mbar_wait(&M->mbar[A], 0);
+            if (hasB) mbar_wait(&M->mbar[B], 0);
+        } else {
+            load_symbol_direct<FMT>(xa, frame_src, A, lane + 32 * h, 64);
+            if (hasB) load_symbol_direct<FMT>(xb, frame_src, B, lane + 32 * h, 64);
+            named_bar_sync(bar_id, 64);
+        }
+        // raw cyclic-prefix correlation (Frame.hpp:251-253) of both symbols (each warp of the team computes it)
+        {
+            float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                cmac_conj(ca, xa[lane + 32 * i], xa[lane + 32 * i + 512]);
+                if (hasB) cmac_conj(cb, xb[lane + 32 * i], xb[lane + 32 * i + 512]);
+            }
+            ca = warp_sum(ca);
+            cb = warp_sum(cb);
+            const float2 sel = (lane & 1) ? cb : ca;
+            const float ang = fast_atan2_turns(sel.y, sel.x);         // one evaluation serves both symbols
+            thA = __shfl_sync(0xffffffffu, ang, 0);
+            thB = hasB ? __shfl_sync(0xffffffffu, ang, 1) : 0.f;
+            if (lane == 0 && h == 0) { M->theta_t[A] = thA; if (hasB) M->theta_t[B] = thB; }
+        }
+        const float nuA = thA * (1.0f / 512.0f), nuB = thB * (1.0f / 512.0f);   // fractional-bin rotation, turns/sample
+        // phasor table of the warp: Q^r = exp(-j 2pi nu 64 r), r<8, both symbols
+        float4 *qt = M->qtab[warp];
+        {
+            const bool forB = (lane & 8) != 0;
+            const float2 ph = cis_neg_turns_f((forB ? nuB : nuA) * (float)(64 * (lane & 7)));
+            if (lane < 16) {
+                float *dst = reinterpret_cast<float *>(&qt[lane & 7]);
+                dst[forB ? 1 : 0] = ph.x;
+                dst[forB ? 3 : 2] = ph.y;
+            }
+        }
+        __syncwarp();
+        const int t = lane + 32 * h;
+        const pc Pt = make_pc(cis_neg_turns_f(nuA * (float)(128 + t)), cis_neg_turns_f(nuB * (float)(128 + t)));
+        // rotate while loading: v[r] = x[128 + t + 64 r] * exp(-j 2pi nu (128 + t + 64 r))
+        pc v[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const float4 qr = qt[r];
+            pc Qr; Qr.re = make_float2(qr.x, qr.y); Qr.im = make_float2(qr.z, qr.w);
+            const pc w = cmul(Pt, Qr);
+            const int j = 128 + t + 64 * r;
+            const float2 a = xa[j];
+            const float2 b = hasB ? xb[j] : make_float2(0.f, 0.f);
+            v[r].re = make_float2(a.x * w.re.x - a.y * w.im.x, b.x * w.re.y - b.y * w.im.y);
+            v[r].im = make_float2(a.x * w.im.x + a.y * w.re.x, b.x * w.im.y + b.y * w.re.y);
+        }
+        if (TAPS || team == 0) {
+            // CP samples j = t and j = t + 64: exp(-j 2pi nu j) = P(t) conj(Q^2) resp. P(t) conj(Q^1)
+            const float4 q1 = qt[1], q2 = qt[2];
+            pc Q1, Q2;
+            Q1.re = make_float2(q1.x, q1.y); Q1.im = make_float2(-q1.z, -q1.w);
+            Q2.re = make_float2(q2.x, q2.y); Q2.im = make_float2(-q2.z, -q2.w);
+            const pc w0 = cmul(Pt, Q2), w1 = cmul(Pt, Q1);
+            if (TAPS && taps.synced != nullptr) {
+                // debug tap, completed by rx_synced_fixup_kernel: samples rotated by the fractional-bin part only
+                float2 *da = taps.synced + (size_t)frame * P.rx_len + (size_t)A * 640, *db = da + 640;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    da[128 + t + 64 * r] = pc_a(v[r]);
+                    if (hasB) db[128 + t + 64 * r] = pc_b(v[r]);
+                }
+                da[t] = cmul(xa[t], pc_a(w0));
+                da[t + 64] = cmul(xa[t + 64], pc_a(w1));
+                if (hasB) { db[t] = cmul(xb[t], pc_b(w0)); db[t + 64] = cmul(xb[t + 64], pc_b(w1)); }
+            }
+            if (team == 0) {
+                // pr_phase_sinh, CP part: conj(ref[j]) x[j] exp(-j 2pi nu' j); the missing factor
+                // exp(-j 2pi m_0 j / 512) is applied once the coarse shift is known.  Parked in shared memory.
+                float2 *zs = reinterpret_cast<float2 *>(M->wtab);      // 128 float2 = wtab[0..7]; reused before wtab is
+                zs[t] = cmulc(cmul(xa[t], pc_a(w0)), __ldg(&P.preamble_td[t]));
+                zs[t + 64] = cmulc(cmul(xa[t + 64], pc_a(w1)), __ldg(&P.preamble_td[t + 64]));
+            }
+        }
+        named_bar_sync(bar_id, 64);                // the whole team has read its inputs before the planes are reused
+        team_fft512p_head<false>(v, P.tw_p1, t);
+        team_fft512p_tail<false>(v, Wre, Wim, P.tw_p2, lane, h, bar_id);
+    }
+    __syncthreads();                               // #2: spectra (shifted by the unknown m_s) and kc are ready
+
+    const int kc = M->kc;
+    int mA = 0, mB = 0;
+    if (!is_coarse) {
+        // m_s and the reference's phi_s (Frame.hpp:254): phi_t = theta_t - 512 shift + m_s in (-0.5, 0.5]
+        const float sh512 = (float)kc * (512.0f / (float)P.pf_den);
+        mA = (int)ceilf(-(thA - sh512) - 0.5f);
+        mB = (int)ceilf(-(thB - sh512) - 0.5f);
+        if (h == 0) {
+            if (lane == 0) { M->mshift[A] = mA; if (hasB) M->mshift[B] = mB; }
+            // pilot bins of both symbols
+            float pa = 0.f, pb = 0.f;
+            if (lane < 8) {
+                const int pbin = __ldg(&P.pilot_bin[lane]);
+                const int sa = spec_slot((pbin + mA) & 511), sb = spec_slot((pbin + mB) & 511);
+                const float2 va = make_float2(Wre[sa].x, Wim[sa].x), vb = make_float2(Wre[sb].y, Wim[sb].y);
+                M->pilots[A][lane] = va;
+                pa = sqrtf(cnorm2(va));
+                if (hasB) { M->pilots[B][lane] = vb; pb = sqrtf(cnorm2(vb)); }
+            }
+            pa = warp_sum(pa);
+            pb = warp_sum(pb);
+            if (lane == 0) { M->pabs[A] = pa; if (hasB) M->pabs[B] = pb; }
+        }
+    }
+    if (warp == 0) {
+        // ---- pr_phase_sinh (Frame.hpp:265-274): theta = arg sum_{i<640} conj(ref[i]) y[i] ----
+        // body part by Parseval: sum_n conj(r[n]) y[n] = (1/sqrt 512) sum_k conj(R[k]) Y[k], R = tx grid of the preamble
+        // true spectrum of the preamble: Y[k] = (-j)^m0 X'[k + m0]   (symbol 0 carries no other constant phase)
+        float2 d[8];
+        float2 z = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const int i = (e < 4 ? 0 : 128) + 4 * lane + (e & 3);
+            const int sl = spec_slot((__ldg(&P.data_bin[i]) + mA) & 511);
+            const float2 y = mul_negj_pow(make_float2(Wre[sl].x, Wim[sl].x), mA);
+            d[e] = cmulc(y, __ldg(&P.mod_preamble[i]));               // Y_i * conj(mod_preamble_i)
+            z = cadd(z, d[e]);
+        }
+        if (lane < 8) z = cadd(z, cscale(mul_negj_pow(M->pilots[0][lane], mA), P.pilot_ampl));
+        z = cscale(z, 0.04419417382415922028f);                       // 1/sqrt(512)
+        {
+            const float2 *zs = reinterpret_cast<const float2 *>(M->wtab);
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int j = lane + 32 * c;
+                z = cadd(z, cmul(zs[j], __ldg(&P.tw_fft[(mA * j) & 511])));
+            }
+        }
+        z = warp_sum(z);
+        const float inv = rsqrtf(fmaxf(cnorm2(z), 1e-30f));
+        const float2 rot = make_float2(z.x * inv, -z.y * inv);
+        if (lane == 0) { M->rot_theta = rot; if (TAPS) M->theta = atan2f(z.y, z.x); }
+        // ---- chan_char_lq (Frame.hpp:389-434): phase[i] = arg(pr[i]/mod_preamble[i]), i < 128 ----
+        float ph[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float2 dr = cmul(d[e], rot);
+            ph[e] = fast_atan2_turns(dr.y, dr.x) * 6.28318530717958647692f;
+        }
+        // one-step unwrap (Frame.hpp:407-414): phase[i] is moved by -+2pi when it is more than pi away from
+        // the (already adjusted) previous one.  Fast path: no raw step exceeds pi anywhere => nothing moves.
+        const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
+        const float prev_raw = __shfl_up_sync(0xffffffffu, ph[3], 1);
+        bool jump = false;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float dl = ph[e] - (e == 0 ? prev_raw : ph[e - 1]);
+            jump |= (fabsf(dl) > PI_F) && !(lane == 0 && e == 0);
+        }
+        float val[4] = {ph[0], ph[1], ph[2], ph[3]};
+        if (__ballot_sync(0xffffffffu, jump) != 0u) {
+            // slow path: the adjustment is a 3-state chain (state = multiple of 2pi carried by the previous
+            // element); each lane builds the transition map of its 4 elements for every incoming state, the
+            // maps are composed across lanes by a warp scan, then replayed.
+            unsigned map = 0;
+#pragma unroll
+            for (int cin = 0; cin < 3; cin++) {
+                int c = cin - 1;
+                float pv = prev_raw;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (lane == 0 && e == 0) { c = 0; pv = ph[0]; continue; }
+                    const float dlt = ph[e] - (pv + (float)c * TWO_PI_F);
+                    c = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                    pv = ph[e];
+                }
+                map |= (unsigned)(c + 1) << (2 * cin);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
+                if (lane >= o) {
+                    unsigned comp = 0;
+#pragma unroll
+                    for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
+                    map = comp;
+                }
+            }
+            const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
+            int c = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;
+            float pv = prev_raw;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (!(lane == 0 && e == 0)) {
+                    const float dlt = ph[e] - (pv + (float)c * TWO_PI_F);
+                    c = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                    val[e] = ph[e] + (float)c * TWO_PI_F;
+                } else {
+                    c = 0;
+                }
+                pv = ph[e];
+            }
+        }
+        // sums of Frame.hpp:416-421; float partial sums are enough (an error in sum(y) reaches `a` scaled by 0.01,
+        // one in sum(xy) by 1e-4), the cancelling final step is done in double
+        float sy = (val[0] + val[1]) + (val[2] + val[3]);
+        float sxy = 0.f;
+#pragma unroll
+        for (int e = 0; e < 4; e++) sxy += val[e] * (float)(4 * lane + e);
+        sy = warp_sum(sy);
+        sxy = warp_sum(sxy);
+        if (lane == 0) {
+            const double n = 128.0, sx = n * (n - 1.0) / 2.0, sx2 = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
+            const double b = ((double)sxy - sx * (double)sy) / (sx2 - sx * sx);   // Frame.hpp:422 (sums, not means)
+            M->b = b;
+            M->a = (double)sy - b * sx;                                           // Frame.hpp:423
+        }
+    }
+    __syncthreads();                               // #3: pilots, a, b, theta are ready
+
+    const double la = M->a, lb = M->b;
+    float g = 0.f;                                 // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
+    for (int s = 1; s < nsym; s++) g += M->pabs[s];
+    g /= (float)((nsym - 1) * 8) * P.pilot_ampl;
+    const float2 rot_theta = M->rot_theta;
+
+    if (TAPS) {
+        if (taps.scal != nullptr && tid == 0) {
+            float *sc = taps.scal + (size_t)frame * 48;
+            sc[0] = (float)((double)kc / (double)P.pf_den); sc[1] = (float)la; sc[2] = (float)lb; sc[3] = M->theta;
+            sc[4] = g; sc[5] = (float)kc; sc[6] = 0.f; sc[7] = 0.f;
+            for (int s = 0; s < nsym; s++) { sc[16 + s] = (float)M->mshift[s]; sc[32 + s] = M->theta_t[s]; }
+        }
+        if (taps.chan != nullptr) {
+            for (int i = tid; i < 256; i += blockDim.x)
+                taps.chan[(size_t)frame * 256 + i] = cis_turns((lb * (double)(i < 128 ? i : i - 256) + la) * 0.15915494309189533577);
+        }
+    }
+    if (is_coarse) return;
+
+    if (TAPS && taps.grid != nullptr) {
+        // FFT_buf after FFT_FORM::read's normalisation: every bin of every message symbol, fully rotated
+        const int s = h ? B : A;
+        if (s >= 1 && s < nsym) {
+            const float psi = sym_turns(M->theta_t, M->mshift, s);
+            const int ms = h ? mB : mA;
+            const float2 rs = cscale(cmul(mul_negj_pow(cis_neg_turns_f(psi), ms), rot_theta), 1.0f / g);
+            float2 *dst = taps.grid + ((size_t)frame * (nsym - 1) + (s - 1)) * 512;
+            for (int k = lane; k < 512; k += 32) {
+                const int sl = spec_slot((k + ms) & 511);
+                dst[k] = cmul(h ? make_float2(Wre[sl].y, Wim[sl].y) : make_float2(Wre[sl].x, Wim[sl].x), rs);
+            }
+        }
+    }
+
+    // ---- equaliser coefficients per segment (Frame.cpp:89-92 + rx.cpp:214-216) ----
+    //   out = (X/g) / ((P[s,p]/g)/(P[1,p]/g)) / H_i = X * [P[1,p] rot1 / (P[s,p] g)] * conj(H_i),
+    //   conj(H_i) = exp(-j(b i' + a)), i' = lane + 32 e', e' = e (e<4) or e-8: split into a per-segment
+    //   factor folded into the coefficient and a per-lane factor exp(-j b lane).
+    float4 *wt = M->wtab[warp];
+    if (lane < 8) {
+        // constant phase of message symbol 0 (its pilots are the reference of every segment)
+        const float psi1 = sym_turns(M->theta_t, M->mshift, 1);
+        const float2 rot1 = cmul(mul_negj_pow(cis_neg_turns_f(psi1), M->mshift[1]), rot_theta);
+        const float2 p1 = cmul(M->pilots[1][lane], rot1);
+        const int ep = lane < 4 ? lane : lane - 8;
+        const float2 ee = cis_neg_turns((lb * (double)(32 * ep) + la) * 0.15915494309189533577);
+        const float2 psa = M->pilots[A][lane], psb = M->pilots[hasB ? B : A][lane];
+        const float2 wa = cmul(cscale(cmulc(p1, psa), 1.0f / (cnorm2(psa) * g)), ee);
+        const float2 wb = cmul(cscale(cmulc(p1, psb), 1.0f / (cnorm2(psb) * g)), ee);
+        wt[lane] = make_float4(wa.x, wb.x, wa.y, wb.y);
+    }
+    const float2 Ll = cis_neg_turns_f((float)(lb * (double)lane) * inv2pi);
+    __syncwarp();
+
+    // ---- equalise + hard demap (modulation.cpp:53-87); warp h handles segments 4h..4h+3 of both symbols;
+    //      symbol A of team 0 is the preamble ----
+    const int mod = P.mod_type;
+    const DemapK dk = make_demapk(mod);
+    uint8_t *sbA = symbuf + (size_t)team * 512, *sbB = sbA + 256;
+    const bool doA = A >= 1;
+    int n_amb = 0;
+#pragma unroll
+    for (int ee = 0; ee < 4; ee++) {
+        const int e = 4 * h + ee;
+        const int i = lane + 32 * e;
+        const int bin = __ldg(&P.data_bin[32 * e]) + lane;            // segment e is 32 consecutive bins
+        const int sa = spec_slot((bin + mA) & 511), sb = spec_slot((bin + mB) & 511);
+        pc x;
+        x.re = make_float2(Wre[sa].x, Wre[sb].y);
+        x.im = make_float2(Wim[sa].x, Wim[sb].y);
+        const float4 w4 = wt[e];
+        pc w; w.re = make_float2(w4.x, w4.y); w.im = make_float2(w4.z, w4.w);
+        const pc z = cmul(cmul(x, w), Ll);
+        bool amb;
+        if (doA) {
+            if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (A - 1)) * 256 + i] = pc_a(z);
+            sbA[i] = (uint8_t)demap_point(pc_a(z), dk, amb);
+            n_amb += amb ? 1 : 0;
+        }
+        if (hasB) {
+            if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (B - 1)) * 256 + i] = pc_b(z);
+            sbB[i] = (uint8_t)demap_point(pc_b(z), dk, amb);
+            n_amb += amb ? 1 : 0;
+        }
+    }
+    if (ambiguous != nullptr) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_amb += __shfl_xor_sync(0xffffffffu, n_amb, o);
+        if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
+    }
+    named_bar_sync(bar_id, 64);
+    // ---- pack: 8 consecutive symbols of `mod` bits = `mod` whole bytes, MSB first (modulation.cpp:90-125);
+    //      warp h packs symbol (h ? B : A) ----
+    {
+        const int s = h ? B : A;
+        if (s >= 1 && s < nsym) {
+            const uint8_t *sb = h ? sbB : sbA;
+            const uint2 raw = *reinterpret_cast<const uint2 *>(sb + 8 * lane);
+            unsigned long long bits = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const unsigned sym = ((e < 4 ? raw.x : raw.y) >> (8 * (e & 3))) & 0xffu;
+                bits = (bits << mod) | (unsigned long long)sym;
+            }
+            uint8_t *dst = out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - 1) * 32 * mod + (size_t)lane * mod;
+            if (mod == 4) {
+                const unsigned b32 = (unsigned)bits;                   // big-endian byte order on the wire
+                *reinterpret_cast<unsigned *>(dst) = ((b32 & 0xffu) << 24) | ((b32 & 0xff00u) << 8) | ((b32 >> 8) & 0xff00u) | (b32 >> 24);
+            } else {
+                for (int bq = 0; bq < mod; bq++) dst[bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
+            }
+        }
+    }
+}
+
+// Completes the `synced` debug tap: the fused kernel stored every sample rotated by the fractional-bin
+// frequency only; apply the integer-bin part m_s, the per-symbol constant phase and theta so that the
+// tap equals the reference's buffer after freq_shift + cp_freq_sinh + pr_phase_sinh.
+__global__ void rx_synced_fixup_kernel(const Params P, int n_frames, const RxTaps taps) {
+    const int frame = blockIdx.x;
+    if (frame >= n_frames || taps.synced == nullptr || taps.scal == nullptr) return;
+    const float *sc = taps.scal + (size_t)frame * 48;
+    const int nsym = P.n_sym_rx;
+    float s_th, c_th;
+    sincosf(-sc[3], &s_th, &c_th);
+    for (int s = 0; s < nsym; s++) {
+        int mi[kRxMaxSym];
+        for (int t = 0; t < nsym; t++) mi[t] = (int)sc[16 + t];
+        const float psi = sym_turns(sc + 32, mi, s);
+        const float ms = sc[16 + s];
+        float2 *x = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
+        for (int j = threadIdx.x; j < 640; j += blockDim.x) {
+            const float2 r = cmul(cis_neg_turns((double)psi + (double)ms * (double)j / 512.0), make_float2(c_th, s_th));
+            x[j] = cmul(x[j], r);
+        }
+    }
+}
+
+}  // namespace cofdmk

@@ -63,8 +63,10 @@ typedef struct {
 } cofdm_sizes;
 
 /* optional outputs of cofdm_rx_aligned_batch for parity checks (same `space` as the call; any
- * pointer may be NULL): per frame scal[8] = {shift, a, b, theta, g, 0, 0, 0}, grid[num_symb*fft_size],
- * chan[num_data_subc], constell[constell_size], synced[rx_len] (complex64 each) */
+ * pointer may be NULL): per frame scal[48] = {shift, a, b, theta, g, shift*pf_den, 0, 0, ...; [16+s] = whole-bin
+ * part m_s of symbol s's rotation; [32+s] = Arg of symbol s's raw CP correlation in turns},
+ * grid[num_symb*fft_size], chan[num_data_subc], constell[constell_size], synced[rx_len] (complex64 each).
+ * `synced` needs `scal` (a second small kernel completes it from the per-symbol scalars). */
 typedef struct {
     float *scal;
     float *grid;
@@ -82,8 +84,11 @@ const char *cofdm_version(void);
 int cofdm_create(const char *config_path, int device, cofdm_t **out);
 void cofdm_destroy(cofdm_t *h);
 int cofdm_query(const cofdm_t *h, cofdm_sizes *out);
-/* stream used for COFDM_DEVICE calls (a cudaStream_t passed as void*); default = per-handle stream */
+/* stream used for COFDM_DEVICE calls and single-stream COFDM_HOST calls: a cudaStream_t passed as
+ * void*; NULL selects CUDA's default stream.  A new handle uses its own non-blocking stream, which
+ * cofdm_own_stream() returns so that it can be restored. */
 int cofdm_set_stream(cofdm_t *h, void *cuda_stream);
+void *cofdm_own_stream(const cofdm_t *h);
 int cofdm_synchronize(cofdm_t *h);
 
 /* frame-invariant constants in fp64 as the reference holds them (host pointers, any may be NULL):

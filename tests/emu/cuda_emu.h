@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <atomic>
 #include <cmath>
+#include <cstdio>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -52,6 +53,9 @@ struct dim3 {
 namespace emu {
 struct Block {
     pthread_barrier_t bar;
+    pthread_mutex_t nb_mu = PTHREAD_MUTEX_INITIALIZER;
+    pthread_barrier_t nbar[16];
+    bool nbar_init[16] = {};
     std::vector<pthread_barrier_t> wbar;
     std::vector<uint64_t> xbuf;   // 32 slots per warp
     unsigned char *smem;
@@ -70,6 +74,15 @@ static inline void __threadfence() {}
 static inline void __threadfence_block() {}
 
 namespace emu {
+// bar.sync id, nthreads: a barrier among a fixed sub-team of the block's threads
+inline void named_barrier(int id, int nthreads) {
+    Block *b = g_block;
+    pthread_mutex_lock(&b->nb_mu);
+    if (!b->nbar_init[id]) { pthread_barrier_init(&b->nbar[id], nullptr, (unsigned)nthreads); b->nbar_init[id] = true; }
+    pthread_mutex_unlock(&b->nb_mu);
+    pthread_barrier_wait(&b->nbar[id]);
+}
+
 template <class T>
 inline T shfl_idx(T v, int src) {
     static_assert(sizeof(T) <= 8, "shuffle payload");

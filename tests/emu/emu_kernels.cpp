@@ -44,10 +44,11 @@ int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_f
     const Params P = h->P;
     RxTaps taps{scal, grid, chan, constell, synced};
     const int nsym = P.n_sym_rx;
-    auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(32 * nsym), rx_fused512_smem_bytes(nsym), kern); };
-    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym>(P, samples, stride, n_frames, out, amb, taps); });
-    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym>(P, samples, stride, n_frames, out, amb, taps); });
-    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym>(P, samples, stride, n_frames, out, amb, taps); });
+    auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym)), rx512_smem_bytes(nsym), kern); };
+    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps); });
+    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps); });
+    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps); });
+    if (synced && scal) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup_kernel(P, n_frames, taps); });
     return 0;
 }
 
@@ -56,8 +57,8 @@ int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int 
     if (!h->T.fused512_ok) return -1;
     const Params P = h->P;
     const size_t sm = tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
-    if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(32 * (P.num_symb + 1)), sm, [&] { tx512_kernel<kCI16>(P, payload, n_frames, frames); });
-    else emu::launch(dim3(n_frames), dim3(32 * (P.num_symb + 1)), sm, [&] { tx512_kernel<kCF32>(P, payload, n_frames, frames); });
+    if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCI16>(P, payload, n_frames, frames); });
+    else emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCF32>(P, payload, n_frames, frames); });
     return 0;
 }
 

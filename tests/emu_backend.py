@@ -83,7 +83,7 @@ class EmuModem:
             n_frames = (total - offset - s.rx_len) // frame_stride + 1
         out = np.zeros((n_frames, s.usefull_size), np.uint8)
         amb = np.zeros(1, np.uint64)
-        t = dict(scal=np.zeros((n_frames, 8), np.float32), grid=np.zeros((n_frames, s.num_symb * s.fft_size), np.complex64),
+        t = dict(scal=np.zeros((n_frames, 48), np.float32), grid=np.zeros((n_frames, s.num_symb * s.fft_size), np.complex64),
                  chan=np.zeros((n_frames, s.num_data_subc), np.complex64), constell=np.zeros((n_frames, s.constell_size), np.complex64),
                  synced=np.zeros((n_frames, s.rx_len), np.complex64))
         base = samples.ctypes.data + offset * (4 if fmt == CI16 else 8)

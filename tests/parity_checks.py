@@ -129,7 +129,7 @@ def check_rx_against_oracle(m, o, rec_i16, fmt="i16", want=None):
             # boundary-ambiguous frame, counted, later stages are then not comparable sample by sample
             stats["shift_mismatch"] += 1
             continue
-        synced = taps["synced"][i] * np.exp(-1j * float(taps["scal"][i, 3]))
+        synced = taps["synced"][i]
         for k, g in (("synced", synced), ("grid", taps["grid"][i]), ("chan", taps["chan"][i]), ("constell", taps["constell"][i])):
             e = rel_l2(g, r[k])
             stats[k] = max(stats[k], e)

@@ -77,3 +77,11 @@ def test_sync_kernels_on_reference_capture(emu, port, golden_capture):
         assert first.tolist() == [o.find_preamble(cap, int(p)) for p in starts] == [11039, 19301, -10, -10]
         for p, c in zip(starts, cor):
             assert np.abs(c - o.find_corr(cap, int(p))).max() < 1e-6
+
+
+def test_rx_phase_unwrap_slow_path(emu, port):
+    """timing several samples early => the preamble phase ramps through +-pi more than once, so the
+    one-step unwrap of chan_char_lq (Frame.hpp:407-414) takes its slow (chain) path"""
+    pay, rec = pc.impaired_records(port[4], 4, seed=77, early=7, noise=0.5)
+    st = pc.check_rx_against_oracle(emu[4], port[4], rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["differing"] == 0
