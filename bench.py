@@ -152,17 +152,14 @@ def native_arm(args):
     import torch
     import torch.distributed as dist
     import cofdm_b200 as cb
+    from cofdm_b200 import dist as cd
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (native arm) needs a CUDA device: there is no CPU fallback")
+    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=dev)
+    rank, world, local = cd.init_from_env(backend="nccl", device=dev)
 
     m = cb.Modem(CONFIG, device=local)
     m.use_torch_stream()
@@ -226,13 +223,9 @@ def native_arm(args):
     bit_err = int(torch.sum(torch.bitwise_count(diff).to(torch.int64)).item()) if hasattr(torch, "bitwise_count") else int((diff != 0).sum().item())
     frames_bad = int((diff != 0).any(dim=1).sum().item())
 
-    stats = torch.tensor([total_ms, tx_ms, rx_ms], dtype=torch.float64, device=dev)
-    counters = torch.tensor([bit_err, frames_bad, F, amb], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(stats, op=dist.ReduceOp.MAX)       # device time, max over ranks
-        dist.all_reduce(counters, op=dist.ReduceOp.SUM)    # the only data-path-adjacent collective: 4 counters over NCCL
-    total_ms, tx_ms, rx_ms = [float(x) for x in stats.tolist()]
-    bit_err, frames_bad, frames_all, amb = [int(x) for x in counters.tolist()]
+    # the only collective of the job: SUM of 4 counters + MAX of the device times, over NCCL
+    (bit_err, frames_bad, frames_all, amb), (total_ms, tx_ms, rx_ms) = cd.reduce_results(
+        [bit_err, frames_bad, F, amb], [total_ms, tx_ms, rx_ms], device=dev)
 
     # ---- end to end through the C ABI with host buffers (pinned), H2D + D2H inside the timed region ---
     E = min(args.e2e_frames, F)
@@ -258,10 +251,7 @@ def native_arm(args):
         e2e_step()
     e_dt = (time.perf_counter() - t0) / e_steps
     e_ok = bool(np.array_equal(np_out, np_pay)) or int((np_out != np_pay).any(axis=1).sum())
-    e_t = torch.tensor([e_dt], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(e_t, op=dist.ReduceOp.MAX)
-    e_dt = float(e_t.item())
+    _, (e_dt,) = cd.reduce_results([], [e_dt], device=dev)
     e2e_value = world * 2 * E * s.output_size / e_dt / 1e6
     h2d = E * s.usefull_size + E * s.output_size * 8
     d2h = E * s.output_size * 8 + E * s.usefull_size

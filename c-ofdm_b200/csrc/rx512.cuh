@@ -51,6 +51,11 @@ struct RxMisc {
     double a, b;                     // chan_char_lq line
     float2 rot_theta;                // exp(-j theta)
     float theta;
+    // chan_char_lq is computed by warps 0..3 together (one sub-carrier phase per lane)
+    float2 zpart[4];                 // partial sums of the pr_phase_sinh correlation
+    float ph[128];                   // raw phases arg(pr[i]/mod_preamble[i])
+    float sypart[4], sxypart[4];
+    int jumppart[4];
 };
 
 COFDM_HD int rx512_npair(int nsym) { return (nsym + 1) / 2; }
@@ -145,19 +150,33 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     const bool is_coarse = warp >= 2 * npair;
     const float inv2pi = 0.15915494309189533577f;
 
-    // ---- stage the frame: one bulk copy per symbol + a private copy of the preamble for the coarse warps ----
+    // ---- stage the frame: one bulk copy per symbol + a private copy of the preamble for the coarse warps.
+    //      Every team arms and issues its own copies (lane 0 of its first warp), so no block-wide barrier
+    //      is needed before the first wait: a team-wide named barrier makes the mbarrier init visible. ----
     if (USE_TMA) {
-        if (tid == 0) {
-            for (int s = 0; s <= nsym; s++) mbar_init(&M->mbar[s], 1);
-            mbar_fence_init();
-            for (int s = 0; s < nsym; s++) {
-                mbar_arrive_expect_tx(&M->mbar[s], 640 * 8);
-                tma_load_1d(X + (size_t)(s >> 1) * kPairSlots + (s & 1) * 640, frame_src + (size_t)s * 640 * 8, 640 * 8, &M->mbar[s]);
+        if (is_coarse) {
+            if (tid == 64 * npair) {
+                mbar_init(&M->mbar[nsym], 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(&M->mbar[nsym], 640 * 8);
+                tma_load_1d(SA, frame_src, 640 * 8, &M->mbar[nsym]);
             }
-            mbar_arrive_expect_tx(&M->mbar[nsym], 640 * 8);
-            tma_load_1d(SA, frame_src, 640 * 8, &M->mbar[nsym]);
+            named_bar_sync(1, 32 * kCoarseWarps);
+        } else {
+            if ((warp & 1) == 0 && lane == 0) {
+                const int s0 = warp, s1 = warp + 1;        // symbols 2*team and 2*team+1
+                mbar_init(&M->mbar[s0], 1);
+                if (s1 < nsym) mbar_init(&M->mbar[s1], 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(&M->mbar[s0], 640 * 8);
+                tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots, frame_src + (size_t)s0 * 640 * 8, 640 * 8, &M->mbar[s0]);
+                if (s1 < nsym) {
+                    mbar_arrive_expect_tx(&M->mbar[s1], 640 * 8);
+                    tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots + 640, frame_src + (size_t)s1 * 640 * 8, 640 * 8, &M->mbar[s1]);
+                }
+            }
+            named_bar_sync(2 + (warp >> 1), 64);
         }
-        __syncthreads();
     }
 
     const int team = warp >> 1, h = warp & 1;      // FFT warps: team = symbol pair, h = which half of the butterflies
@@ -166,7 +185,6 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     const bool hasB = B < nsym;
     float2 *Wre = X + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
     float thA = 0.f, thB = 0.f;                    // Arg(C_s) in turns
-    float2 zc[4];                                  // warp 0: conj(ref[j]) * rotated preamble CP sample, j<128
 
     if (is_coarse) {
         // ================= coarse CFO: 640-point spectrum of the received preamble, CP included =================
@@ -333,108 +351,115 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             if (lane == 0) { M->pabs[A] = pa; if (hasB) M->pabs[B] = pb; }
         }
     }
-    if (warp == 0) {
-        // ---- pr_phase_sinh (Frame.hpp:265-274): theta = arg sum_{i<640} conj(ref[i]) y[i] ----
-        // body part by Parseval: sum_n conj(r[n]) y[n] = (1/sqrt 512) sum_k conj(R[k]) Y[k], R = tx grid of the preamble
-        // true spectrum of the preamble: Y[k] = (-j)^m0 X'[k + m0]   (symbol 0 carries no other constant phase)
-        float2 d[8];
-        float2 z = make_float2(0.f, 0.f);
-#pragma unroll
-        for (int e = 0; e < 8; e++) {
-            const int i = (e < 4 ? 0 : 128) + 4 * lane + (e & 3);
-            const int sl = spec_slot((__ldg(&P.data_bin[i]) + mA) & 511);
-            const float2 y = mul_negj_pow(make_float2(Wre[sl].x, Wim[sl].x), mA);
-            d[e] = cmulc(y, __ldg(&P.mod_preamble[i]));               // Y_i * conj(mod_preamble_i)
-            z = cadd(z, d[e]);
-        }
-        if (lane < 8) z = cadd(z, cscale(mul_negj_pow(M->pilots[0][lane], mA), P.pilot_ampl));
-        z = cscale(z, 0.04419417382415922028f);                       // 1/sqrt(512)
+    if (warp < 4) {
+        // ---- pr_phase_sinh (Frame.hpp:265-274) and chan_char_lq (Frame.hpp:389-434) on warps 0..3 together:
+        //      thread gi = 32*warp + lane owns data sub-carriers gi and 128+gi of the preamble. ----
+        // theta = arg sum_{i<640} conj(ref[i]) y[i]; body part by Parseval:
+        //   sum_n conj(r[n]) y[n] = (1/sqrt 512) sum_k conj(R[k]) Y[k], R = tx grid of the preamble,
+        //   Y[k] = (-j)^m0 X'[k + m0] the true spectrum of the preamble (symbol 0 has no other constant phase)
+        const int m0 = (int)ceilf(-(M->theta_t[0] - (float)kc * (512.0f / (float)P.pf_den)) - 0.5f);
+        const float2 *P0re = X, *P0im = X + kFft512Slots;             // planes of team 0, symbol A = low half
+        const int gi = 32 * warp + lane;
+        float2 d0, z;
         {
-            const float2 *zs = reinterpret_cast<const float2 *>(M->wtab);
-#pragma unroll
-            for (int c = 0; c < 4; c++) {
-                const int j = lane + 32 * c;
-                z = cadd(z, cmul(zs[j], __ldg(&P.tw_fft[(mA * j) & 511])));
+            const int s0 = spec_slot((__ldg(&P.data_bin[gi]) + m0) & 511), s1 = spec_slot((__ldg(&P.data_bin[128 + gi]) + m0) & 511);
+            d0 = cmulc(mul_negj_pow(make_float2(P0re[s0].x, P0im[s0].x), m0), __ldg(&P.mod_preamble[gi]));
+            const float2 d1 = cmulc(mul_negj_pow(make_float2(P0re[s1].x, P0im[s1].x), m0), __ldg(&P.mod_preamble[128 + gi]));
+            z = cadd(d0, d1);
+            if (gi < 8) {
+                const int sp = spec_slot((__ldg(&P.pilot_bin[gi]) + m0) & 511);
+                z = cadd(z, cscale(mul_negj_pow(make_float2(P0re[sp].x, P0im[sp].x), m0), P.pilot_ampl));
             }
+            z = cscale(z, 0.04419417382415922028f);                   // 1/sqrt(512)
+            const float2 *zs = reinterpret_cast<const float2 *>(M->wtab);
+            z = cadd(z, cmul(zs[gi], __ldg(&P.tw_fft[(m0 * gi) & 511])));   // CP part, j = gi < 128
         }
         z = warp_sum(z);
+        if (lane == 0) M->zpart[warp] = z;
+        named_bar_sync(15, 128);
+        z = cadd(cadd(M->zpart[0], M->zpart[1]), cadd(M->zpart[2], M->zpart[3]));
         const float inv = rsqrtf(fmaxf(cnorm2(z), 1e-30f));
         const float2 rot = make_float2(z.x * inv, -z.y * inv);
-        if (lane == 0) { M->rot_theta = rot; if (TAPS) M->theta = atan2f(z.y, z.x); }
-        // ---- chan_char_lq (Frame.hpp:389-434): phase[i] = arg(pr[i]/mod_preamble[i]), i < 128 ----
-        float ph[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const float2 dr = cmul(d[e], rot);
-            ph[e] = fast_atan2_turns(dr.y, dr.x) * 6.28318530717958647692f;
-        }
-        // one-step unwrap (Frame.hpp:407-414): phase[i] is moved by -+2pi when it is more than pi away from
-        // the (already adjusted) previous one.  Fast path: no raw step exceeds pi anywhere => nothing moves.
+        if (tid == 0) { M->rot_theta = rot; if (TAPS) M->theta = atan2f(z.y, z.x); }
+        // phase[gi] = arg(pr[gi]/mod_preamble[gi])  (Frame.hpp:403-405)
+        const float2 dr = cmul(d0, rot);
+        const float ph = fast_atan2_turns(dr.y, dr.x) * 6.28318530717958647692f;
+        M->ph[gi] = ph;
+        // one-step unwrap (Frame.hpp:407-414): nothing moves unless some raw step exceeds pi
         const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
-        const float prev_raw = __shfl_up_sync(0xffffffffu, ph[3], 1);
-        bool jump = false;
+        const float prev = __shfl_up_sync(0xffffffffu, ph, 1);
+        const bool jump = lane > 0 && fabsf(ph - prev) > PI_F;
+        const unsigned jm = __ballot_sync(0xffffffffu, jump);
+        const float sy = warp_sum(ph), sxy = warp_sum(ph * (float)gi);
+        if (lane == 0) { M->sypart[warp] = sy; M->sxypart[warp] = sxy; M->jumppart[warp] = jm != 0u; }
+        named_bar_sync(15, 128);
+        if (warp == 0) {
+            // steps across the three warp boundaries
+            bool bj = false;
+            if (lane >= 1 && lane < 4) bj = fabsf(M->ph[32 * lane] - M->ph[32 * lane - 1]) > PI_F;
+            const bool any = (__ballot_sync(0xffffffffu, bj) != 0u) || M->jumppart[0] || M->jumppart[1] || M->jumppart[2] || M->jumppart[3];
+            float tsy = (M->sypart[0] + M->sypart[1]) + (M->sypart[2] + M->sypart[3]);
+            float tsxy = (M->sxypart[0] + M->sxypart[1]) + (M->sxypart[2] + M->sxypart[3]);
+            if (any) {
+                // slow path: the adjustment is a 3-state chain (state = multiple of 2pi carried by the previous
+                // element); each lane builds the transition map of its 4 elements for every incoming state, the
+                // maps are composed across lanes by a warp scan, then replayed.
+                float p4[4];
 #pragma unroll
-        for (int e = 0; e < 4; e++) {
-            const float dl = ph[e] - (e == 0 ? prev_raw : ph[e - 1]);
-            jump |= (fabsf(dl) > PI_F) && !(lane == 0 && e == 0);
-        }
-        float val[4] = {ph[0], ph[1], ph[2], ph[3]};
-        if (__ballot_sync(0xffffffffu, jump) != 0u) {
-            // slow path: the adjustment is a 3-state chain (state = multiple of 2pi carried by the previous
-            // element); each lane builds the transition map of its 4 elements for every incoming state, the
-            // maps are composed across lanes by a warp scan, then replayed.
-            unsigned map = 0;
+                for (int e = 0; e < 4; e++) p4[e] = M->ph[4 * lane + e];
+                const float prev_raw = __shfl_up_sync(0xffffffffu, p4[3], 1);
+                unsigned map = 0;
 #pragma unroll
-            for (int cin = 0; cin < 3; cin++) {
-                int c = cin - 1;
-                float pv = prev_raw;
+                for (int cin = 0; cin < 3; cin++) {
+                    int c = cin - 1;
+                    float pv = prev_raw;
+#pragma unroll
+                    for (int e = 0; e < 4; e++) {
+                        if (lane == 0 && e == 0) { c = 0; pv = p4[0]; continue; }
+                        const float dlt = p4[e] - (pv + (float)c * TWO_PI_F);
+                        c = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                        pv = p4[e];
+                    }
+                    map |= (unsigned)(c + 1) << (2 * cin);
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
+                    if (lane >= o) {
+                        unsigned comp = 0;
+#pragma unroll
+                        for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
+                        map = comp;
+                    }
+                }
+                const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
+                int c = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;
+                float pv = prev_raw, ssy = 0.f, ssxy = 0.f;
 #pragma unroll
                 for (int e = 0; e < 4; e++) {
-                    if (lane == 0 && e == 0) { c = 0; pv = ph[0]; continue; }
-                    const float dlt = ph[e] - (pv + (float)c * TWO_PI_F);
-                    c = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
-                    pv = ph[e];
+                    float val = p4[e];
+                    if (!(lane == 0 && e == 0)) {
+                        const float dlt = p4[e] - (pv + (float)c * TWO_PI_F);
+                        c = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                        val = p4[e] + (float)c * TWO_PI_F;
+                    } else {
+                        c = 0;
+                    }
+                    pv = p4[e];
+                    ssy += val;
+                    ssxy += val * (float)(4 * lane + e);
                 }
-                map |= (unsigned)(c + 1) << (2 * cin);
+                tsy = warp_sum(ssy);
+                tsxy = warp_sum(ssxy);
             }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
-                if (lane >= o) {
-                    unsigned comp = 0;
-#pragma unroll
-                    for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
-                    map = comp;
-                }
+            // sums of Frame.hpp:416-421; float partial sums are enough (an error in sum(y) reaches `a` scaled by
+            // 0.01, one in sum(xy) by 1e-4), the cancelling final step is done in double
+            if (lane == 0) {
+                const double n = 128.0, sx = n * (n - 1.0) / 2.0, sx2 = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
+                const double b = ((double)tsxy - sx * (double)tsy) / (sx2 - sx * sx);   // Frame.hpp:422 (sums, not means)
+                M->b = b;
+                M->a = (double)tsy - b * sx;                                            // Frame.hpp:423
             }
-            const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
-            int c = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;
-            float pv = prev_raw;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (!(lane == 0 && e == 0)) {
-                    const float dlt = ph[e] - (pv + (float)c * TWO_PI_F);
-                    c = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
-                    val[e] = ph[e] + (float)c * TWO_PI_F;
-                } else {
-                    c = 0;
-                }
-                pv = ph[e];
-            }
-        }
-        // sums of Frame.hpp:416-421; float partial sums are enough (an error in sum(y) reaches `a` scaled by 0.01,
-        // one in sum(xy) by 1e-4), the cancelling final step is done in double
-        float sy = (val[0] + val[1]) + (val[2] + val[3]);
-        float sxy = 0.f;
-#pragma unroll
-        for (int e = 0; e < 4; e++) sxy += val[e] * (float)(4 * lane + e);
-        sy = warp_sum(sy);
-        sxy = warp_sum(sxy);
-        if (lane == 0) {
-            const double n = 128.0, sx = n * (n - 1.0) / 2.0, sx2 = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
-            const double b = ((double)sxy - sx * (double)sy) / (sx2 - sx * sx);   // Frame.hpp:422 (sums, not means)
-            M->b = b;
-            M->a = (double)sy - b * sx;                                           // Frame.hpp:423
         }
     }
     __syncthreads();                               // #3: pilots, a, b, theta are ready

@@ -52,3 +52,12 @@ def test_package_never_touches_the_oracle():
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle/" not in txt.replace("no oracle", "") or f == "synth.py" and "from oracle" not in txt, f
                 assert "import oracle" not in txt and "from oracle" not in txt and "libcofdm_oracle" not in txt, f
+
+
+def test_cxx_facade_compiles_against_the_abi(tmp_path):
+    """the FRAME_FORM / Modulation look-alikes are plain C++17 over include/cofdm.h"""
+    import subprocess
+    cb.build.build_library()
+    r = subprocess.run(["g++", "-std=c++17", "-O1", f"-I{ROOT}/include", f"-I{ROOT}/c-ofdm_b200/cxx", f"{ROOT}/tests/cxx/main_like.cpp",
+                        "-o", str(tmp_path / "main_like"), f"-L{ROOT}/c-ofdm_b200", "-lcofdm_b200"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr

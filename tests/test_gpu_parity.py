@@ -172,3 +172,18 @@ def test_round_trip_at_scale(modems, mt):
     f32 = m.tx_batch(pay[:4096], cb.CF32)
     out2, _ = m.rx_aligned_batch(f32 * (0.37 * np.exp(1.1j)), n_frames=4096, frame_stride=s.output_size, offset=s.t2sin_size)
     assert torch.equal(out2, pay[:4096])
+
+
+def test_cxx_facade_replays_main_cpp(cfg_dir, golden_capture, tmp_path):
+    """the header-compatible FRAME_FORM look-alike (c-ofdm_b200/cxx) driven by the reference's own call
+    sequence (main.cpp:48-80) on the recorded capture: same positions, same shift, every payload byte"""
+    import subprocess
+    exe = str(tmp_path / "main_like")
+    subprocess.run(["g++", "-std=c++17", "-O2", f"-I{ROOT}/include", f"-I{ROOT}/c-ofdm_b200/cxx", f"{ROOT}/tests/cxx/main_like.cpp",
+                    "-o", exe, f"-L{ROOT}/c-ofdm_b200", "-lcofdm_b200", f"-Wl,-rpath,{ROOT}/c-ofdm_b200"], check=True)
+    cap, pay = tmp_path / "cap.bin", tmp_path / "pay.bin"
+    golden_capture["capture_i16"].astype(np.int16).tofile(cap)
+    golden_capture["mac_frame"].tofile(pay)
+    r = subprocess.run([exe, cfg_dir[1], str(cap), str(pay)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "t2_hits 2 t2_sin_begin 10752 pr_begin 11040 shift -0.0037109375 bytes_ok 256 of 256" in r.stdout, r.stdout
