@@ -72,6 +72,7 @@ def load_library():
     lib.cofdm_find_t2sin.argtypes = [vp, vp, ci, sz, sz, C.POINTER(C.c_longlong), ci]
     lib.cofdm_preamble_search.argtypes = [vp, vp, ci, sz, vp, sz, vp, vp, ci]
     lib.cofdm_i16_to_cf32.argtypes = [vp, vp, vp, sz, ci]
+    lib.cofdm_rx_stream.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz)]
     lib.cofdm_enable_timing.argtypes = [vp, ci]
     lib.cofdm_last_kernel_ms.argtypes = [vp]
     lib.cofdm_last_kernel_ms.restype = C.c_float
@@ -292,6 +293,19 @@ class Modem:
         self._chk(self.lib.cofdm_preamble_search(self.h, _ptr(samples), fmt, n, _ptr(starts), ns, _ptr(cor), _ptr(first),
                                                  _space(samples, starts, first)))
         return (first, cor) if want_cor else first
+
+    def rx_stream(self, capture_i16, max_frames=None):
+        """rx.cpp's acquisition loop over a host int16 capture [N, 2] -> (preamble positions, payload bytes)"""
+        s = self.sizes
+        cap = np.ascontiguousarray(capture_i16, dtype=np.int16).reshape(-1)
+        n = cap.size // 2
+        if max_frames is None:
+            max_frames = n // (s.ofdm_len * s.num_symb) + 2
+        pos = np.zeros(max_frames, dtype=np.int64)
+        out = np.zeros((max_frames, s.usefull_size), dtype=np.uint8)
+        k = C.c_size_t(0)
+        self._chk(self.lib.cofdm_rx_stream(self.h, cap.ctypes.data, n, max_frames, pos.ctypes.data, out.ctypes.data, C.byref(k)))
+        return pos[:k.value].copy(), out[:k.value].copy()
 
     def i16_to_cf32(self, samples):
         self._follow(samples)

@@ -533,6 +533,119 @@ int cofdm_preamble_search(cofdm_t *h, const void *samples, int fmt, size_t n_sam
     return COFDM_OK;
 }
 
+int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t max_frames,
+                    long long *pr_begin_abs, uint8_t *bytes, size_t *n_found) {
+    if (!h || !capture || !n_found) return fail(COFDM_ERR_ARG, "cofdm_rx_stream: bad argument");
+    *n_found = 0;
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    const Params &P = h->P;
+    if (!h->T.fused512_ok || P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "rx_stream: configuration not built yet");
+    const long long out_sz = P.frame_len, block = out_sz * h->T.rx_buf_size;   // SDR::rx_buf_size, sdr.hpp:141
+    const long long ring = out_sz * (h->T.rx_buf_size + 1);                     // from_sdr_buf.size(), Frame.cpp:221
+    const long long n_blocks = block > 0 ? (long long)n_samples / block : 0;
+    if (n_blocks == 0 || max_frames == 0) return COFDM_OK;
+    cudaStream_t st = h->stream;
+    // device ring (int16 I,Q = 4 bytes per sample) + batch of frames awaiting demodulation
+    const size_t batch_cap = 1024;
+    CU_TRY(h->scratch_a.reserve((size_t)ring * 4));
+    CU_TRY(h->scratch_b.reserve((size_t)ring / 256 * sizeof(float) + 64));
+    CU_TRY(h->pipe_in[0].reserve(batch_cap * (size_t)P.rx_len * 4));
+    CU_TRY(h->pipe_out[0].reserve(batch_cap * (size_t)P.bytes_per_frame));
+    CU_TRY(h->scratch_c.reserve(64));
+    char *d_ring = (char *)h->scratch_a.p;
+    CU_TRY(cudaMemsetAsync(d_ring, 0, (size_t)ring * 4, st));
+    long long next_block = 0, cur_block = -1;
+    auto buf_update = [&]() -> int {                                           // rx.cpp:73-91
+        if (next_block >= n_blocks) return 0;
+        if (cudaMemcpyAsync(d_ring + out_sz * 4, capture + 2 * next_block * block, (size_t)block * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) return -1;
+        cur_block = next_block++;
+        return 1;
+    };
+    const long long threshold = ring - out_sz;                                // rx.cpp:116
+    auto carry = [&]() {                                                       // rx.cpp:149-153 / 182-186
+        return cudaMemcpyAsync(d_ring, d_ring + threshold * 4, (size_t)out_sz * 4, cudaMemcpyDeviceToDevice, st);
+    };
+    size_t found = 0, in_batch = 0, flushed = 0;
+    auto flush = [&]() -> int {
+        if (in_batch == 0) return COFDM_OK;
+        RxTaps none{};
+        if (int rc = launch_rx(h, st, h->pipe_in[0].p, COFDM_CI16, in_batch, (size_t)P.rx_len, (uint8_t *)h->pipe_out[0].p, nullptr, none)) return rc;
+        if (bytes && cudaMemcpyAsync(bytes + flushed * P.bytes_per_frame, h->pipe_out[0].p, in_batch * P.bytes_per_frame, cudaMemcpyDeviceToHost, st) != cudaSuccess)
+            return fail(COFDM_ERR_CUDA, "rx_stream: D2H");
+        if (cudaStreamSynchronize(st) != cudaSuccess) return fail(COFDM_ERR_CUDA, "rx_stream: sync");
+        flushed += in_batch;
+        in_batch = 0;
+        return COFDM_OK;
+    };
+    // T2SIN_FORM::find_t2sin on the ring from `start` (Frame.hpp:150-197), in windows of 64 blocks
+    auto find_t2 = [&](long long start, long long *pos) -> int {
+        *pos = -1;
+        const long long cycles = (ring - start) / 256;
+        for (long long c0 = 0; c0 < cycles; c0 += 64) {
+            const long long nb = std::min<long long>(64, cycles - c0);
+            if (cudaMemsetAsync(h->pos_dev, 0xff, sizeof(unsigned long long), st) != cudaSuccess) return fail(COFDM_ERR_CUDA, "memset");
+            if (int rc = launch_t2(h, st, d_ring, COFDM_CI16, (size_t)(start + c0 * 256), (size_t)nb, (float *)h->scratch_b.p)) return rc;
+            first_above_kernel<<<1, 64, 0, st>>>((const float *)h->scratch_b.p, nb, P.t2_level, start + c0 * 256, 256, h->pos_dev);
+            if (int rc = check_launch(h, "first_above")) return rc;
+            unsigned long long v = 0;
+            if (cudaMemcpyAsync(&v, h->pos_dev, sizeof v, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+                return fail(COFDM_ERR_CUDA, "rx_stream: D2H");
+            if (v != ~0ull) { *pos = (long long)v; return COFDM_OK; }
+        }
+        return COFDM_OK;
+    };
+    auto find_pre = [&](long long start, long long *first) -> int {           // Frame.cpp:338-378
+        long long *d_start = (long long *)h->scratch_c.p, *d_first = d_start + 1;
+        if (cudaMemcpyAsync(d_start, &start, sizeof start, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(COFDM_ERR_CUDA, "H2D");
+        if (int rc = launch_pc(h, st, d_ring, COFDM_CI16, (size_t)ring, d_start, 1, nullptr, d_first)) return rc;
+        if (cudaMemcpyAsync(first, d_first, sizeof *first, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
+            return fail(COFDM_ERR_CUDA, "rx_stream: D2H");
+        return COFDM_OK;
+    };
+#define COFDM_UPDATE_OR_BREAK() { int u_ = buf_update(); if (u_ < 0) return fail(COFDM_ERR_CUDA, "rx_stream: H2D"); if (u_ == 0) break; }
+    if (buf_update() <= 0) return COFDM_OK;                                    // rx.cpp:103-112
+    long long pos = 0;
+    const long long cycles = h->T.iterations;                                  // rx.cpp:124
+    for (long long it = 0; it < cycles && found < max_frames; it++) {          // rx.cpp:126
+        if (int rc = find_t2(pos, &pos)) return rc;                            // :133
+        if (pos == -1) {                                                       // :137-145
+            pos = out_sz;
+            COFDM_UPDATE_OR_BREAK();
+            continue;
+        }
+        if (pos >= threshold) {                                                // :147-156
+            pos -= threshold;
+            CU_TRY(carry());
+            COFDM_UPDATE_OR_BREAK();
+        }
+        long long first = -10;
+        if (int rc = find_pre(pos, &first)) return rc;
+        const long long preamble_begin = first + 1;                            // :158
+        if (preamble_begin < -2) { pos += (long long)P.ofdm_len * P.num_symb; continue; }   // :160-166
+        pos = preamble_begin;                                                  // :168
+        if (pos == -1) {                                                       // :170-178
+            pos = out_sz;
+            COFDM_UPDATE_OR_BREAK();
+            continue;
+        }
+        if (pos >= threshold + P.t2sin_size) {                                 // :180-189
+            pos -= threshold;
+            CU_TRY(carry());
+            COFDM_UPDATE_OR_BREAK();
+        }
+        // rx.cpp:192-196: the frame's rx_len samples go to the demodulation batch
+        CU_TRY(cudaMemcpyAsync((char *)h->pipe_in[0].p + in_batch * (size_t)P.rx_len * 4, d_ring + pos * 4, (size_t)P.rx_len * 4, cudaMemcpyDeviceToDevice, st));
+        if (pr_begin_abs) pr_begin_abs[found] = cur_block * block + pos - out_sz;
+        pos += (long long)P.ofdm_len * P.num_symb;                             // :198
+        found++;
+        if (++in_batch == batch_cap) { if (int rc = flush()) return rc; }
+    }
+#undef COFDM_UPDATE_OR_BREAK
+    if (int rc = flush()) return rc;
+    *n_found = found;
+    return COFDM_OK;
+}
+
 int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n, int space) {
     if (!h || !in || !out) return fail(COFDM_ERR_ARG, "cofdm_i16_to_cf32: bad argument");
     if (set_device(h)) return COFDM_ERR_CUDA;

@@ -91,8 +91,8 @@ public:
 };
 
 class FRAME_FORM {
+    cofdm_sizes s_{};            // declared before h_: open() fills it while h_ is being initialised
     cofdm_t *h_ = nullptr;
-    cofdm_sizes s_{};
     // cache of the last fused run (see the header comment)
     std::vector<float> scal_, chan_, constell_, synced_;
     bit_vector bytes_;

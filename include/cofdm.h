@@ -135,6 +135,16 @@ int cofdm_find_t2sin(cofdm_t *h, const void *samples, int fmt, size_t n_samples,
 int cofdm_preamble_search(cofdm_t *h, const void *samples, int fmt, size_t n_samples, const long long *starts,
                           size_t n_starts, float *cor, long long *first, int space);
 
+/* The acquisition loop of the streaming receiver, rx.cpp:101-235, over an in-memory int16 capture (HOST
+ * pointer; interleaved I,Q) that stands in for consecutive SDR::recv blocks of output_size*rx_buf_size
+ * samples: ring of rx_buf_size+1 frames with carry-over (rx.cpp:116,147-156,180-189), find_t2sin -> find_preamble
+ * (+1) -> copy rx_len samples -> pos += message.size, sentinels -1 / -10 handled as rx.cpp:137-178 does, at
+ * most `iterations` (config) loop turns.  The state machine runs on the host, every search and the
+ * demodulation of the frames found run on the GPU (demodulation batched).  pr_begin_abs[i] = absolute sample
+ * index of frame i's preamble in the capture; bytes[i*usefull_size ...]; *n_found = number of frames. */
+int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t max_frames,
+                    long long *pr_begin_abs, uint8_t *bytes, size_t *n_found);
+
 /* FRAME_FORM::form_int16_to_double  OFDM/Frame.hpp:472-481 (fp32 on the device) */
 int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n_samples, int space);
 

@@ -187,3 +187,34 @@ def test_cxx_facade_replays_main_cpp(cfg_dir, golden_capture, tmp_path):
     r = subprocess.run([exe, cfg_dir[1], str(cap), str(pay)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "t2_hits 2 t2_sin_begin 10752 pr_begin 11040 shift -0.0037109375 bytes_ok 256 of 256" in r.stdout, r.stdout
+
+
+def test_rx_stream_matches_reference_loop(cfg_dir, oracle_lib, golden_vectors, golden_capture):
+    """cofdm_rx_stream = rx.cpp's acquisition state machine with every search and the demodulation on the GPU:
+    identical list of preamble positions and identical bytes as the compiled reference's loop."""
+    g = golden_vectors
+    m = cb.Modem(cfg_dir["stream"], device=0)
+    pos, by = m.rx_stream(g["sync_capture_i16"])
+    assert pos.tolist() == g["sync_stream_pos"].tolist()
+    assert np.array_equal(by, g["sync_stream_bytes"])
+    m.close()
+    # the reference's own recorded capture (one SDR block of 40 frames, BPSK): both copies of the frame
+    m = cb.Modem(cfg_dir[1], device=0)
+    pos, by = m.rx_stream(golden_capture["capture_i16"][:240640])
+    assert pos.tolist() == [11040, 19302]
+    assert all(np.array_equal(b, golden_capture["mac_frame"]) for b in by)
+    m.close()
+    # a longer synthetic capture spanning several SDR blocks, against the oracle's loop
+    o = oracle_lib.Oracle("port", cfg_dir["stream"])
+    s = o.sizes
+    pay = pc.synth.payloads(40, s.usefull_size, seed=3)
+    tx16 = np.stack([o.tx(p)[1] for p in pay]).reshape(40, -1, 2)
+    rng = np.random.default_rng(11)
+    fr = pc.synth.channel(tx16, seed=4, cfo=rng.uniform(-0.003, 0.003, 40), phase=rng.uniform(0, 1, 40), noise_sigma=1.0)
+    cap, _ = pc.synth.capture(fr, gaps=rng.integers(260, 9000, 40), noise_sigma=3.0, seed=5, tail=s.output_size * 12)
+    m = cb.Modem(cfg_dir["stream"], device=0)
+    want_pos, want_by = o.rx_stream(cap)
+    pos, by = m.rx_stream(cap)
+    assert len(want_pos) >= 30
+    assert pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
+    m.close()
