@@ -68,6 +68,7 @@ def load_library():
     lib.cofdm_demod.argtypes = [vp, ci, vp, sz, vp, vp, ci]
     lib.cofdm_tx_batch.argtypes = [vp, vp, sz, vp, ci, ci]
     lib.cofdm_rx_aligned_batch.argtypes = [vp, vp, ci, sz, sz, vp, vp, C.POINTER(RxTaps), ci]
+    lib.cofdm_read_batch.argtypes = [vp, vp, ci, sz, vp, vp, vp, vp, ci]
     lib.cofdm_t2sin_metric.argtypes = [vp, vp, ci, sz, sz, vp, ci]
     lib.cofdm_find_t2sin.argtypes = [vp, vp, ci, sz, sz, C.POINTER(C.c_longlong), ci]
     lib.cofdm_preamble_search.argtypes = [vp, vp, ci, sz, vp, sz, vp, vp, ci]
@@ -264,6 +265,20 @@ class Modem:
         if taps:
             return out, tap_bufs, int(amb.value)
         return out, int(amb.value)
+
+    # ---- FRAME_FORM::read (sync-less) + PREAMBLE_FORM::chan_char ---------------------------------------------
+    def read_batch(self, frames, taps=False):
+        """frames: [n, output_size] whole frames -> bytes [n, usefull_size] (+ restored points, chan_char)"""
+        s = self.sizes
+        self._follow(frames)
+        fmt = _fmt_of(frames)
+        n = _n_samples(frames, fmt) // s.output_size
+        out = self._new(frames, (n, s.usefull_size), "uint8")
+        restored = self._new(frames, (n, s.constell_size), "complex64") if taps else None
+        chan = self._new(frames, (n, s.num_data_subc), "complex64") if taps else None
+        amb = C.c_ulonglong(0)
+        self._chk(self.lib.cofdm_read_batch(self.h, _ptr(frames), fmt, n, _ptr(out), C.addressof(amb), _ptr(restored), _ptr(chan), _space(frames, out)))
+        return (out, restored, chan, int(amb.value)) if taps else (out, int(amb.value))
 
     # ---- sync ------------------------------------------------------------------------------------------------
     def t2sin_metric(self, samples, start=0):

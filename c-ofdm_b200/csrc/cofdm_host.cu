@@ -94,7 +94,7 @@ size_t sample_bytes(int fmt) { return fmt == COFDM_CI16 ? 4 : 8; }
 
 // ---- device-side launches (all pointers are device pointers, stream given) ----------------------
 int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps) {
+              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0) {
     if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "rx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
     if (n_frames == 0) return COFDM_OK;
     const int nsym = h->P.n_sym_rx;
@@ -105,7 +105,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     const bool want = taps.scal || taps.grid || taps.chan || taps.constell || taps.synced;
     const bool tma = fmt == COFDM_CF32 && ((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0;
     // cf32 records that are not 16-byte aligned (a frame cut out of a capture) and int16 records use plain loads
-#define COFDM_RX_LAUNCH(F, T, S, W) rx_fused512_kernel<F, T, S, W><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps)
+#define COFDM_RX_LAUNCH(F, T, S, W) rx_fused512_kernel<F, T, S, W><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less)
 #define COFDM_RX_PICK(F, T)                                                                    \
     do {                                                                                       \
         if (small) { if (want) COFDM_RX_LAUNCH(F, T, 9, true); else COFDM_RX_LAUNCH(F, T, 9, false); } \
@@ -117,7 +117,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 #undef COFDM_RX_PICK
 #undef COFDM_RX_LAUNCH
     if (int rc = check_launch(h, "rx_fused512")) return rc;
-    if (taps.synced != nullptr && taps.scal != nullptr) {
+    if (taps.synced != nullptr && taps.scal != nullptr && !sync_less) {
         rx_synced_fixup_kernel<<<grid, 128, 0, st>>>(h->P, (int)n_frames, taps);
         return check_launch(h, "rx_synced_fixup");
     }
@@ -385,8 +385,25 @@ int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *fr
     return COFDM_OK;
 }
 
+static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
+                         uint8_t *bytes, unsigned long long *ambiguous, const cofdm_rx_taps *taps, int space, int sync_less);
+
 int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
                            uint8_t *bytes, unsigned long long *ambiguous, const cofdm_rx_taps *taps, int space) {
+    return rx_batch_impl(h, samples, fmt, n_frames, frame_stride, bytes, ambiguous, taps, space, 0);
+}
+
+int cofdm_read_batch(cofdm_t *h, const void *frames, int fmt, size_t n_frames, uint8_t *bytes,
+                     unsigned long long *ambiguous, float *restored, float *chan_char, int space) {
+    if (!h || !frames) return fail(COFDM_ERR_ARG, "cofdm_read_batch: bad argument");
+    cofdm_rx_taps t{nullptr, nullptr, chan_char, restored, nullptr};
+    // FRAME_FORM::read copies a whole frame (Frame.cpp:240); the chain starts at the preamble slot
+    const char *p = (const char *)frames + (size_t)h->P.t2sin_size * sample_bytes(fmt);
+    return rx_batch_impl(h, p, fmt, n_frames, (size_t)h->P.frame_len, bytes, ambiguous, (restored || chan_char) ? &t : nullptr, space, 1);
+}
+
+static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
+                         uint8_t *bytes, unsigned long long *ambiguous, const cofdm_rx_taps *taps, int space, int sync_less) {
     if (!h || !samples || !bytes || (fmt != COFDM_CF32 && fmt != COFDM_CI16)) return fail(COFDM_ERR_ARG, "cofdm_rx_aligned_batch: bad argument");
     if (frame_stride < (size_t)h->P.rx_len) return fail(COFDM_ERR_ARG, "frame_stride < rx_len");
     if (set_device(h)) return COFDM_ERR_CUDA;
@@ -401,7 +418,7 @@ int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_fr
         if (ambiguous) CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
         {
             Timed tm(h);
-            if (int rc = launch_rx(h, h->stream, samples, fmt, n_frames, frame_stride, bytes, ambiguous ? h->amb_dev : nullptr, t)) return rc;
+            if (int rc = launch_rx(h, h->stream, samples, fmt, n_frames, frame_stride, bytes, ambiguous ? h->amb_dev : nullptr, t, sync_less)) return rc;
         }
         if (ambiguous) {
             unsigned long long a = 0;
@@ -443,7 +460,7 @@ int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_fr
         // the last record only needs rx_len samples (the caller's buffer may end there)
         const size_t in_bytes = ((n - 1) * frame_stride + (size_t)P.rx_len) * sb;
         CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, (const char *)samples + f0 * frame_stride * sb, in_bytes, cudaMemcpyHostToDevice, st));
-        if (int rc = launch_rx(h, st, h->pipe_in[s].p, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t)) return rc;
+        if (int rc = launch_rx(h, st, h->pipe_in[s].p, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t, sync_less)) return rc;
         CU_TRY(cudaMemcpyAsync(bytes + f0 * bpf, h->pipe_out[s].p, n * bpf, cudaMemcpyDeviceToHost, st));
     }
     for (int i = 0; i < kPipe; i++) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));

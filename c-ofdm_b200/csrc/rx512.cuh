@@ -131,7 +131,9 @@ template <int FMT, bool USE_TMA, int MAXSYM, bool TAPS>
 __global__ void __launch_bounds__(32 * (2 * ((MAXSYM + 1) / 2) + kCoarseWarps), MAXSYM <= 9 ? 3 : 1)
 rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/,
                    int n_frames, uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous,
-                   const RxTaps taps) {
+                   const RxTaps taps, const int sync_less) {
+    // sync_less != 0: FRAME_FORM::read / OFDM_FORM::read (Frame.cpp:201-208,239-242): no CFO, phase or channel
+    // correction at all -- CP strip, FFT, pilot normalisation, segment correction, demap.
     COFDM_DYN_SMEM(smem_raw);
     const int nsym = P.n_sym_rx;                 // 1 preamble + num_symb message symbols
     const int npair = rx512_npair(nsym);
@@ -191,6 +193,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         const int ct = tid - 64 * npair, cn = 32 * kCoarseWarps, cw = warp - 2 * npair;
         if (USE_TMA) mbar_wait(&M->mbar[nsym], 0);
         else { load_symbol_direct<FMT>(SA, frame_src, 0, ct, cn); named_bar_sync(1, cn); }
+        if (sync_less) { if (ct == 0) M->kc = 0; goto coarse_done; }
         stockham_pass<10, false>(SA, SB, 640, 1, P.tw_pf, ct, cn);
         named_bar_sync(1, cn);
         stockham_pass<8, false, true>(SB, SA, 640, 10, P.tw_pf, ct, cn);   // twiddle index <= 7*9*8 < 640
@@ -239,6 +242,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             for (int i = 0; i < P.num_pilot_subc; i++) k += M->amax[i];
             M->kc = k - P.num_pilot_subc * (P.pf_size / 2);           // shift = kc / pf_den (Frame.hpp:332-334)
         }
+    coarse_done:;
     } else {
         // ================= FFT team: symbols A and B, this warp owns butterflies t = lane + 32 h =================
         float2 *xa = Wre, *xb = Wre + 640;
@@ -261,7 +265,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             ca = warp_sum(ca);
             cb = warp_sum(cb);
             const float2 sel = (lane & 1) ? cb : ca;
-            const float ang = fast_atan2_turns(sel.y, sel.x);         // one evaluation serves both symbols
+            const float ang = sync_less ? 0.f : fast_atan2_turns(sel.y, sel.x);   // one evaluation serves both symbols
             thA = __shfl_sync(0xffffffffu, ang, 0);
             thB = hasB ? __shfl_sync(0xffffffffu, ang, 1) : 0.f;
             if (lane == 0 && h == 0) { M->theta_t[A] = thA; if (hasB) M->theta_t[B] = thB; }
@@ -351,7 +355,9 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             if (lane == 0) { M->pabs[A] = pa; if (hasB) M->pabs[B] = pb; }
         }
     }
-    if (warp < 4) {
+    if (sync_less) {
+        if (tid == 0) { M->a = 0.0; M->b = 0.0; M->rot_theta = make_float2(1.f, 0.f); M->theta = 0.f; }
+    } else if (warp < 4) {
         // ---- pr_phase_sinh (Frame.hpp:265-274) and chan_char_lq (Frame.hpp:389-434) on warps 0..3 together:
         //      thread gi = 32*warp + lane owns data sub-carriers gi and 128+gi of the preamble. ----
         // theta = arg sum_{i<640} conj(ref[i]) y[i]; body part by Parseval:
@@ -477,9 +483,20 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             sc[4] = g; sc[5] = (float)kc; sc[6] = 0.f; sc[7] = 0.f;
             for (int s = 0; s < nsym; s++) { sc[16 + s] = (float)M->mshift[s]; sc[32 + s] = M->theta_t[s]; }
         }
-        if (taps.chan != nullptr) {
+        if (taps.chan != nullptr && !sync_less) {
             for (int i = tid; i < 256; i += blockDim.x)
                 taps.chan[(size_t)frame * 256 + i] = cis_turns((lb * (double)(i < 128 ? i : i - 256) + la) * 0.15915494309189533577);
+        }
+        if (taps.chan != nullptr && sync_less) {
+            // PREAMBLE_FORM::chan_char (Frame.hpp:375-385) on the preamble as it stands: pr = preamble.fft()
+            // (own pilot normalisation, Frame.cpp:76-84; coef == 1), chan_est[i] = pr[i] / mod_preamble[i]
+            const float gp = M->pabs[0] / (8.0f * P.pilot_ampl);
+            for (int i = tid; i < 256; i += blockDim.x) {
+                const int sl = spec_slot(__ldg(&P.data_bin[i]));
+                const float2 y = cscale(make_float2(X[sl].x, X[kFft512Slots + sl].x), 1.0f / gp);
+                const float2 mp = __ldg(&P.mod_preamble[i]);
+                taps.chan[(size_t)frame * 256 + i] = cscale(cmulc(y, mp), 1.0f / cnorm2(mp));
+            }
         }
     }
     if (is_coarse) return;

@@ -88,6 +88,7 @@ public:
         return (int)first;
     }
     inline complex_vector &chan_char_lq();                                        // Frame.hpp:389-434
+    inline complex_vector chan_char();                                            // Frame.hpp:375-385
 };
 
 class FRAME_FORM {
@@ -172,8 +173,21 @@ public:
     }
     const bit_vector &cached_bytes() const { return bytes_; }
 
-    bit_vector read(void *) {                                                    // Frame.cpp:239-242
-        throw std::runtime_error("FRAME_FORM::read (sync-less path) is not built yet; use demodulate()");
+    bit_vector read(void *transmitted_data) {                                    // Frame.cpp:239-242
+        std::memcpy((void *)buf.data(), transmitted_data, sizeof(complex_double) * buf.size());
+        auto f = cofdm_facade::to_f32(buf.data(), buf.size());
+        bit_vector out((size_t)usefull_size);
+        cofdm_facade::check(cofdm_read_batch(h_, f.data(), COFDM_CF32, 1, out.data(), nullptr, nullptr, nullptr, COFDM_HOST), "cofdm_read_batch");
+        return out;
+    }
+    complex_vector chan_char_of_buf() {                                          // PREAMBLE_FORM::chan_char, Frame.hpp:375-385
+        auto f = cofdm_facade::to_f32(buf.data(), buf.size());
+        bit_vector tmp((size_t)usefull_size);
+        std::vector<float> cc(2 * (size_t)s_.num_data_subc);
+        cofdm_facade::check(cofdm_read_batch(h_, f.data(), COFDM_CF32, 1, tmp.data(), nullptr, nullptr, cc.data(), COFDM_HOST), "cofdm_read_batch");
+        complex_vector out((size_t)s_.num_data_subc);
+        for (int i = 0; i < s_.num_data_subc; i++) out[i] = complex_double(cc[2 * i], cc[2 * i + 1]);
+        return out;
     }
 };
 
@@ -183,3 +197,4 @@ inline void OFDM_FORM::cp_freq_sinh() {}
 inline void OFDM_FORM::pr_phase_sinh(complex_double *, int) { frame_->copy_synced_to_buf(); }
 inline complex_vector OFDM_FORM::fft() { return frame_->cached_points_times_channel(); }
 inline complex_vector &PREAMBLE_FORM::chan_char_lq() { return chan_est; }
+inline complex_vector PREAMBLE_FORM::chan_char() { chan_est = frame_->chan_char_of_buf(); return chan_est; }

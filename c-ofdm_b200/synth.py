@@ -84,3 +84,35 @@ def capture(frames_c, gaps, noise_sigma=3.0, seed=0, tail=0):
         starts.append(pos)
         pos += L
     return to_i16(np.round(cap.real) + 1j * np.round(cap.imag)), np.array(starts, dtype=np.int64)
+
+
+# ---- MAC framing stand-in (the reference's mac/mac_frame.hpp is missing from its tree; layout recovered in
+# 8-byte little-endian header {u16 tx_id, rx_id, seq_num, cs}, cs = 16-bit sum of
+# every byte of the frame taken with cs = 0).  Host-side byte shuffling for the loopback harnesses only.
+def mac_write(payload, tx_id=1, rx_id=0, seq=0):
+    payload = np.asarray(payload, dtype=np.uint8)
+    hdr = np.array([tx_id & 255, tx_id >> 8, rx_id & 255, rx_id >> 8, seq & 255, (seq >> 8) & 255, 0, 0], dtype=np.uint8)
+    cs = (int(hdr.sum()) + int(payload.sum())) & 0xFFFF
+    hdr[6], hdr[7] = cs & 255, cs >> 8
+    return np.concatenate([hdr, payload])
+
+
+def mac_read(frame):
+    """-> (payload, tx_id, rx_id, seq, checksum_ok)"""
+    frame = np.asarray(frame, dtype=np.uint8)
+    tx_id, rx_id, seq, cs = (int(frame[2 * i]) | int(frame[2 * i + 1]) << 8 for i in range(4))
+    ok = ((int(frame[:6].sum()) + int(frame[8:].sum())) & 0xFFFF) == cs
+    return frame[8:], tx_id, rx_id, seq, ok
+
+
+def text_payload(n_bytes, seed=3):
+    """deterministic ASCII text standing in for the reference's WARANDPEACE.txt (not shipped here)"""
+    rng = np.random.default_rng(seed)
+    words = ["peace", "war", "prince", "andrew", "natasha", "pierre", "moscow", "the", "and", "of", "a", "said", "was", "his", "her"]
+    out = []
+    size = 0
+    while size < n_bytes:
+        w = words[int(rng.integers(len(words)))] + (" " if rng.random() > 0.08 else ".\n")
+        out.append(w)
+        size += len(w)
+    return np.frombuffer("".join(out).encode()[:n_bytes], dtype=np.uint8).copy()

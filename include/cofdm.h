@@ -122,6 +122,15 @@ int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *fr
 int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
                            uint8_t *bytes, unsigned long long *ambiguous, const cofdm_rx_taps *taps, int space);
 
+/* FRAME_FORM::read(void*)  OFDM/Frame.cpp:239-242 -> OFDM_FORM::read :201-208, batched: whole frames
+ * [n_frames*output_size] in, NO synchronisation or channel correction: CP strip, FFT, pilot normalisation and
+ * segment correction (FFT_FORM::read, Frame.cpp:73-96), hard demap -> bytes[n_frames*usefull_size].
+ * Optional outputs (same space, may be NULL): restored[n_frames*constell_size] complex64 = restored_buf before
+ * the demap, chan_char[n_frames*num_data_subc] complex64 = PREAMBLE_FORM::chan_char() (Frame.hpp:375-385) of
+ * the frame's preamble as it stands. */
+int cofdm_read_batch(cofdm_t *h, const void *frames, int fmt, size_t n_frames, uint8_t *bytes,
+                     unsigned long long *ambiguous, float *restored, float *chan_char, int space);
+
 /* T2SIN_FORM::corr / find_t2sin block metric  OFDM/Frame.hpp:96-197: rel[i] = masked / total spectral
  * energy of the 256-sample block starting at start + i*t2sin_size, i < (n_samples-start)/t2sin_size;
  * 0 for blocks the reference skips (zero / NaN energy).  No threshold applied. */

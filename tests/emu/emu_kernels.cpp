@@ -36,7 +36,7 @@ void *emu_create(const char *config_path) {
 void emu_destroy(void *h) { delete (EmuHandle *)h; }
 int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
-int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
+int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride, int sync_less,
                     uint8_t *out, unsigned long long *amb, float *scal, float2 *grid, float2 *chan,
                     float2 *constell, float2 *synced) {
     auto *h = (EmuHandle *)hv;
@@ -45,11 +45,17 @@ int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_f
     RxTaps taps{scal, grid, chan, constell, synced};
     const int nsym = P.n_sym_rx;
     auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym)), rx512_smem_bytes(nsym), kern); };
-    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps); });
-    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps); });
-    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps); });
-    if (synced && scal) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup_kernel(P, n_frames, taps); });
+    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+    if (synced && scal && !sync_less) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup_kernel(P, n_frames, taps); });
     return 0;
+}
+
+int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
+                    uint8_t *out, unsigned long long *amb, float *scal, float2 *grid, float2 *chan,
+                    float2 *constell, float2 *synced) {
+    return emu_rx_fused512_mode(hv, samples, fmt, use_tma, n_frames, stride, 0, out, amb, scal, grid, chan, constell, synced);
 }
 
 int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int fmt) {

@@ -29,6 +29,7 @@ class EmuModem:
         L.emu_destroy.argtypes = [vp]
         L.emu_rx_fused512.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong] + [vp] * 7
         L.emu_tx512.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.emu_rx_fused512_mode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int] + [vp] * 7
         L.emu_t2sin_metric.argtypes = [vp, vp, C.c_int, C.c_longlong, C.c_longlong, vp]
         L.emu_preamble_corr.argtypes = [vp, vp, C.c_int, C.c_longlong, vp, C.c_int, vp, vp]
         L.emu_mod.argtypes = [vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong]
@@ -91,6 +92,20 @@ class EmuModem:
         assert self.lib.emu_rx_fused512(self.h, base, fmt, self.use_tma, n_frames, frame_stride, out.ctypes.data,
                                         amb.ctypes.data, *ptrs) == 0
         return (out, t, int(amb[0])) if taps else (out, int(amb[0]))
+
+    def read_batch(self, frames, taps=False):
+        s = self.sizes
+        fmt = CI16 if frames.dtype == np.int16 else CF32
+        frames = np.ascontiguousarray(frames)
+        n = (frames.size // 2 if fmt == CI16 else frames.size) // s.output_size
+        out = np.zeros((n, s.usefull_size), np.uint8)
+        amb = np.zeros(1, np.uint64)
+        restored = np.zeros((n, s.constell_size), np.complex64)
+        chan = np.zeros((n, s.num_data_subc), np.complex64)
+        base = frames.ctypes.data + s.t2sin_size * (4 if fmt == CI16 else 8)
+        assert self.lib.emu_rx_fused512_mode(self.h, base, fmt, self.use_tma, n, s.output_size, 1, out.ctypes.data, amb.ctypes.data,
+                                             None, None, chan.ctypes.data, restored.ctypes.data, None) == 0
+        return (out, restored, chan, int(amb[0])) if taps else (out, int(amb[0]))
 
     def t2sin_metric(self, samples, start=0):
         fmt = CI16 if samples.dtype == np.int16 else CF32

@@ -136,3 +136,29 @@ def check_rx_against_oracle(m, o, rec_i16, fmt="i16", want=None):
             assert e < TOL, (i, k, e)
         stats["differing"] += assert_bytes_match(out[i], r["bytes"], r["constell"], s.mod_type, f"rx frame {i}")
     return stats
+
+
+def check_read_and_chan_char(m, o, seed=9):
+    """FRAME_FORM::read (sync-less demodulation of whole frames) and PREAMBLE_FORM::chan_char"""
+    s = o.sizes
+    pay = synth.payloads(3, s.usefull_size, seed=seed)
+    frames, i16 = [], []
+    for p in pay:
+        f, q = o.tx(p)
+        frames.append(f)
+        i16.append(q.reshape(-1, 2))
+    # a static gain only: read() has no synchronisation at all; the pilot normalisation absorbs the gain
+    frames = np.stack(frames) * 0.8
+    out, restored, chan, amb = m.read_batch(frames.astype(np.complex64), taps=True)
+    worst = 0.0
+    for i in range(3):
+        want_b, want_r = o.read(frames[i])
+        worst = max(worst, rel_l2(to_np(restored)[i], want_r))
+        assert_bytes_match(to_np(out)[i], want_b, want_r, s.mod_type, "read")
+        assert np.array_equal(want_b, pay[i])
+        cc = o.chan_char(frames[i][s.t2sin_size: s.t2sin_size + s.preamble_size])
+        worst = max(worst, rel_l2(to_np(chan)[i], cc))
+    assert worst < TOL, worst
+    out16, _ = m.read_batch(np.stack(i16))
+    assert np.array_equal(to_np(out16), pay)
+    return dict(rel_l2=worst)

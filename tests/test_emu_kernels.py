@@ -85,3 +85,9 @@ def test_rx_phase_unwrap_slow_path(emu, port):
     pay, rec = pc.impaired_records(port[4], 4, seed=77, early=7, noise=0.5)
     st = pc.check_rx_against_oracle(emu[4], port[4], rec, "i16")
     assert st["shift_mismatch"] == 0 and st["differing"] == 0
+
+
+@pytest.mark.parametrize("mt", [2, 4, 6])
+def test_read_syncless_and_chan_char(emu, port, mt):
+    st = pc.check_read_and_chan_char(emu[mt], port[mt])
+    assert st["rel_l2"] < 2e-6

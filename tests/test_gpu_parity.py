@@ -218,3 +218,52 @@ def test_rx_stream_matches_reference_loop(cfg_dir, oracle_lib, golden_vectors, g
     assert len(want_pos) >= 30
     assert pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
     m.close()
+
+
+@pytest.mark.parametrize("mt", [1, 2, 4, 6, 8])
+def test_read_syncless_and_chan_char(modems, port, mt):
+    st = pc.check_read_and_chan_char(modems[mt], port[mt])
+    assert st["rel_l2"] < 2e-6
+
+
+def test_config1_text_loopback_with_mac(cfg_dir, oracle_lib):
+    """BASELINE.json configs[0]: text file in MAC frames (8-byte header + 1016 payload bytes) -> tx -> int16
+    -> capture with gaps -> streaming receiver; GPU vs the oracle's rx.cpp loop; every byte must come back."""
+    m = cb.Modem(cfg_dir["stream"], device=0)
+    o = oracle_lib.Oracle("port", cfg_dir["stream"])
+    s = m.sizes
+    n = 24
+    text = pc.synth.text_payload(n * (s.usefull_size - 8))
+    mac = np.stack([pc.synth.mac_write(text[i * 1016:(i + 1) * 1016], seq=i) for i in range(n)])
+    assert pc.synth.mac_write(np.frombuffer(b"\x00" * 1016, np.uint8))[6] == 1          # cs = sum of bytes incl. tx_id=1
+    frames = m.tx_batch(mac, cb.CI16)
+    rng = np.random.default_rng(21)
+    cap, _ = pc.synth.capture(pc.cplx(frames), gaps=rng.integers(300, 4000, n), noise_sigma=3.0, seed=2, tail=s.output_size * 11)
+    pos, by = m.rx_stream(cap)
+    wpos, wby = o.rx_stream(cap)
+    assert pos.tolist() == wpos.tolist() and np.array_equal(by, wby)
+    got = [pc.synth.mac_read(b) for b in by]
+    assert all(g[4] for g in got) and [g[3] for g in got] == list(range(len(got)))
+    assert len(got) >= n - 2
+    assert np.array_equal(np.concatenate([g[0] for g in got]), text[: 1016 * len(got)])
+
+
+def test_config2_audio_payload_through_multipath_channel(modems, port):
+    """BASELINE.json configs[1]: a mono PCM WAV image as payload, 3-tap multipath + CFO + AWGN at fixed SNR;
+    identical impaired samples to the oracle and the GPU; points within 1e-5, identical decisions, BER of both."""
+    m, o = modems[4], port[4]
+    s = m.sizes
+    wav = np.frombuffer(pc.synth.wav_payload(seconds=0.25), dtype=np.uint8)
+    n = len(wav) // s.usefull_size
+    pay = wav[: n * s.usefull_size].reshape(n, s.usefull_size)
+    tx16 = m.tx_batch(pay, cb.CI16)
+    rng = np.random.default_rng(1234)
+    # Es/N0 = 25 dB for 16-QAM: rms sample amplitude ~160 LSB -> sigma per component = 160 / sqrt(2) / 10^(25/20)
+    rx = pc.synth.channel(tx16, seed=1234, cfo=rng.uniform(-0.004, 0.004, n), phase=rng.uniform(0, 1, n),
+                          taps=(1.0, 0.2 - 0.1j, 0.05j), noise_sigma=160 / np.sqrt(2) / 10 ** (25 / 20))
+    rec = pc.synth.to_i16(rx[:, s.t2sin_size:])
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    out, _ = m.rx_aligned_batch(rec)
+    ber_gpu = np.unpackbits(out ^ pay).mean()
+    ber_ref = np.mean([np.unpackbits(o.rx_aligned(pc.cplx(r))["bytes"] ^ p).mean() for r, p in zip(rec, pay)])
+    assert abs(ber_gpu - ber_ref) < 1e-4 and st["shift_mismatch"] <= 1
