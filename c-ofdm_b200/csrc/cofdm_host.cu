@@ -57,6 +57,7 @@ struct cofdm {
     cudaStream_t pipe_stream[kPipe] = {};
     DevBuf pipe_in[kPipe], pipe_out[kPipe];
     DevBuf scratch_a, scratch_b, scratch_c;
+    DevBuf gen_frames, gen_spec, gen_pre;        // generic path intermediates
     unsigned long long *amb_dev = nullptr;       // ambiguity counter
     unsigned long long *pos_dev = nullptr;       // find_t2sin result
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -93,10 +94,16 @@ int check_launch(cofdm *h, const char *what) {
 size_t sample_bytes(int fmt) { return fmt == COFDM_CI16 ? 4 : 8; }
 
 // ---- device-side launches (all pointers are device pointers, stream given) ----------------------
+int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
+                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps);
+int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt);
 int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
               uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0) {
-    if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "rx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
     if (n_frames == 0) return COFDM_OK;
+    if (!h->T.fused512_ok) {
+        if (h->T.generic_ok && !sync_less) return launch_rx_generic(h, st, samples, fmt, n_frames, stride, bytes, amb, taps);
+        return fail(COFDM_ERR_UNSUPPORTED, "rx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
+    }
     const int nsym = h->P.n_sym_rx;
     const size_t sm = rx512_smem_bytes(nsym);
     const dim3 grid((unsigned)n_frames), block(rx512_threads(nsym));
@@ -124,9 +131,65 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     return COFDM_OK;
 }
 
+// the any-size path (generic.cuh): five kernels per sub-batch with the spectra in HBM between them
+int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
+                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps) {
+    const Params &P = h->P;
+    const size_t sub = 512, N = (size_t)P.fft_size, L = (size_t)P.ofdm_len, nsym = (size_t)P.n_sym_rx;
+    const size_t nb = std::min(sub, n_frames);
+    CU_TRY(h->gen_frames.reserve(nb * sizeof(GenFrame)));
+    CU_TRY(h->gen_spec.reserve(nb * nsym * N * sizeof(float2)));
+    CU_TRY(h->gen_pre.reserve(nb * L * sizeof(float2)));
+    GenFrame *gf = (GenFrame *)h->gen_frames.p;
+    float2 *spec = (float2 *)h->gen_spec.p, *pre = (float2 *)h->gen_pre.p;
+    const size_t sm_c = 2 * (size_t)P.pf_size * sizeof(float2), sm_s = (L + N) * sizeof(float2), sm_h = (size_t)P.num_data_subc / 2 * sizeof(float) + 16;
+    const size_t sb = sample_bytes(fmt);
+    for (size_t f0 = 0; f0 < n_frames; f0 += sub) {
+        const int n = (int)std::min(sub, n_frames - f0);
+        const void *src = (const char *)samples + f0 * stride * sb;
+        RxTaps t = taps;
+        if (t.scal) t.scal += f0 * 48;
+        if (t.chan) t.chan += f0 * (size_t)P.num_data_subc;
+        if (t.constell) t.constell += f0 * (size_t)P.num_data_subc * P.num_symb;
+        if (fmt == COFDM_CI16) {
+            gen_coarse_kernel<kCI16><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
+            if (int rc = check_launch(h, "gen_coarse")) return rc;
+            gen_symbol_kernel<kCI16><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
+        } else {
+            gen_coarse_kernel<kCF32><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
+            if (int rc = check_launch(h, "gen_coarse")) return rc;
+            gen_symbol_kernel<kCF32><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
+        }
+        if (int rc = check_launch(h, "gen_symbol")) return rc;
+        gen_chan_kernel<<<n, kGenThreads, sm_h, st>>>(P, n, gf, spec, pre);
+        if (int rc = check_launch(h, "gen_chan")) return rc;
+        gen_demap_kernel<<<dim3((unsigned)P.num_symb, n), kGenThreads, 0, st>>>(P, n, gf, spec, bytes + f0 * (size_t)P.bytes_per_frame, amb, t);
+        if (int rc = check_launch(h, "gen_demap")) return rc;
+    }
+    return COFDM_OK;
+}
+
+int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt) {
+    const Params &P = h->P;
+    const size_t sm = 2 * (size_t)P.fft_size * sizeof(float2);
+    for (size_t f0 = 0; f0 < n_frames; f0 += 32768) {                  // grid.y limit
+        const int n = (int)std::min<size_t>(32768, n_frames - f0);
+        const uint8_t *pl = payload + f0 * (size_t)P.bytes_per_frame;
+        void *out = (char *)frames + f0 * (size_t)P.frame_len * sample_bytes(fmt);
+        const dim3 grid((unsigned)P.num_symb + 1, n);
+        if (fmt == COFDM_CI16) gen_tx_kernel<kCI16><<<grid, kGenThreads, sm, st>>>(P, pl, n, out);
+        else gen_tx_kernel<kCF32><<<grid, kGenThreads, sm, st>>>(P, pl, n, out);
+        if (int rc = check_launch(h, "gen_tx")) return rc;
+    }
+    return COFDM_OK;
+}
+
 int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt) {
-    if (!h->T.fused512_ok) return fail(COFDM_ERR_UNSUPPORTED, "tx: only the fft_size=512/cp=128/8-pilot/256-data configuration is built so far");
     if (n_frames == 0) return COFDM_OK;
+    if (!h->T.fused512_ok) {
+        if (h->T.generic_ok) return launch_tx_generic(h, st, payload, n_frames, frames, fmt);
+        return fail(COFDM_ERR_UNSUPPORTED, "tx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
+    }
     const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
     const dim3 grid((unsigned)n_frames), block(tx512_threads(h->P.num_symb));
     if (fmt == COFDM_CI16) tx512_kernel<kCI16><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
@@ -175,6 +238,7 @@ void cofdm_destroy(cofdm_t *h) {
         if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
     }
     h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release();
+    h->gen_frames.release(); h->gen_spec.release(); h->gen_pre.release();
     if (h->amb_dev) cudaFree(h->amb_dev);
     if (h->pos_dev) cudaFree(h->pos_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -243,6 +307,16 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)
             return bail(fail(COFDM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(a != cudaSuccess ? a : (b != cudaSuccess ? b : (c != cudaSuccess ? c : d)))));
     }
+    if (!T.fused512_ok && T.generic_ok) {
+        const int sm_c = (int)(2 * (size_t)P.pf_size * sizeof(float2)), sm_s = (int)((size_t)(P.ofdm_len + P.fft_size) * sizeof(float2));
+        const int sm_t = (int)(2 * (size_t)P.fft_size * sizeof(float2));
+        cudaFuncSetAttribute(gen_coarse_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_c);
+        cudaFuncSetAttribute(gen_coarse_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_c);
+        cudaFuncSetAttribute(gen_symbol_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
+        cudaFuncSetAttribute(gen_symbol_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
+        cudaFuncSetAttribute(gen_tx_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_t);
+        cudaFuncSetAttribute(gen_tx_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_t);
+    }
     {
         const int smp = (int)((size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2));
         if (smp > 48 * 1024) {
@@ -264,7 +338,7 @@ int cofdm_query(const cofdm_t *h, cofdm_sizes *o) {
     o->ofdm_len = P.ofdm_len; o->rx_len = P.rx_len; o->output_size = P.frame_len;
     o->usefull_size = P.bytes_per_frame; o->constell_size = P.num_data_subc * P.num_symb; o->cor_size = P.cor_size;
     o->mult = (int)P.mult; o->rx_buf_size = h->T.rx_buf_size; o->iterations = h->T.iterations;
-    o->fused_path = h->T.fused512_ok ? 1 : 0; o->device = h->device;
+    o->fused_path = h->T.fused512_ok ? 1 : (h->T.generic_ok ? 0 : -1); o->device = h->device;
     return COFDM_OK;
 }
 

@@ -98,6 +98,7 @@ struct HostTables {
     std::vector<cd> t2_tone_d, preamble_td_d, matched_d, mod_preamble_d, constell_d[9];
     int rx_buf_size = 0, iterations = 0;
     bool fused512_ok = false;         // the specialised kernels apply to this config
+    bool generic_ok = false;          // the any-size multi-kernel path applies to this config
 };
 
 inline float2 f2(cd v) { return make_float2((float)v.re, (float)v.im); }
@@ -266,6 +267,15 @@ inline HostTables build_tables(const ConfigMap &cfg) {
         for (auto v : T.mod_preamble_d) T.mod_preamble.push_back(f2(v));
     }
 
+    // radix schedules for the generic path (Stockham passes of radix 16/8/4/2/5)
+    auto schedule = [](int n, int *rad, int &nr) {
+        nr = 0;
+        for (int r : {16, 8, 4, 2, 5})
+            while (n % r == 0 && nr < 8 && n > 1) { rad[nr++] = r; n /= r; }
+        return n == 1;
+    };
+    T.generic_ok = schedule(N, p.fft_radix, p.fft_nr) && schedule(p.pf_size, p.pf_radix, p.pf_nr) && p.num_pr_symb == 1 &&
+                   ND % 8 == 0 && ND % NP == 0 && p.pf_size <= 12288 && N <= 8192;
     T.fused512_ok = (N == 512 && p.cp_size == 128 && ND == 256 && NP == 8 && p.num_pr_symb == 1 &&
                      p.num_symb >= 1 && p.num_symb <= kMaxFusedSymb && p.t2sin_size % 2 == 0 && p.pr_sin_len <= 128 * 5);
     return T;

@@ -33,6 +33,9 @@ struct Params {
     // shift = (sum_argmax / num_pilot_subc - pf_size/2) / pf_size  ==  pf_num / pf_den cycles/sample,
     // pf_num = sum_argmax - num_pilot_subc*(pf_size/2), pf_den = num_pilot_subc*pf_size
     int pf_den;
+    // ---- radix schedules of the generic (any-size) path: products equal fft_size resp. pf_size ----
+    int fft_nr, fft_radix[8];
+    int pf_nr, pf_radix[8];
     // ---- device tables (all fp32 roundings of host fp64 values) ----
     const float2 *tw_fft;        // [fft_size]  exp(-j*2*pi*k/fft_size)
     const float2 *tw_p1;         // [8][64]     exp(-j*2*pi*t*k1/512)     (fused 512 path, pass-1 twiddles)

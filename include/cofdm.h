@@ -58,7 +58,7 @@ typedef struct {
     int constell_size; /* message.usefull_size (points per frame)      OFDM/Frame.cpp:170 */
     int cor_size;      /* PREAMBLE_FORM::cor.size()                    OFDM/Frame.cpp:266 */
     int mult, rx_buf_size, iterations;
-    int fused_path;    /* 1 when the fused fft-512 kernels serve this configuration */
+    int fused_path;    /* 1: fused fft-512 kernels; 0: generic any-size path (slower, generic.cuh); -1: tx/rx unsupported */
     int device;
 } cofdm_sizes;
 

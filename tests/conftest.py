@@ -50,6 +50,13 @@ def cfg_dir(tmp_path_factory):
     for mt in (1, 2, 4, 6, 8):
         paths[mt] = synth.write_config(str(d / f"config_m{mt}.txt"), modType=mt)
     paths["stream"] = synth.write_config(str(d / "config_stream.txt"), rx_buf_size=10)
+    # a small non-default geometry for the generic (any-size) path: the coarse-CFO window width
+    # size*(ND+NP)/N/NP = 160*64/128/8 = 10 is an exact integer, as the reference's estimator needs
+    paths["small"] = synth.write_config(str(d / "config_small.txt"), fft_size=128, cp_size=32, num_data_subc=56, num_pilot_subc=8,
+                                        num_symb=3, pr_sin_len=32, modType=4)
+    # BASELINE.json configs[4]: 4096-point, 64-QAM, dense pilots (window width 5120*2048/4096/128 = 20)
+    paths["big"] = synth.write_config(str(d / "config_big.txt"), fft_size=4096, cp_size=1024, num_data_subc=1920, num_pilot_subc=128,
+                                      num_symb=8, pr_sin_len=128, modType=6)
     return paths
 
 

@@ -102,4 +102,38 @@ int emu_demod(void *, int mod, const float2 *points, long long n_points, uint8_t
     return 0;
 }
 
+int emu_generic_ok(void *h) { return ((EmuHandle *)h)->T.generic_ok ? 1 : 0; }
+
+int emu_rx_generic(void *hv, const void *samples, int fmt, int n_frames, long long stride, uint8_t *out,
+                   unsigned long long *amb, float *scal, float2 *chan, float2 *constell) {
+    auto *h = (EmuHandle *)hv;
+    if (!h->T.generic_ok) return -1;
+    const Params P = h->P;
+    const size_t N = P.fft_size, L = P.ofdm_len, nsym = P.n_sym_rx;
+    std::vector<GenFrame> gf(n_frames);
+    std::vector<float2> spec((size_t)n_frames * nsym * N), pre((size_t)n_frames * L);
+    RxTaps taps{scal, nullptr, chan, constell, nullptr};
+    const dim3 blk(kGenThreads);
+    if (fmt == kCI16) {
+        emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCI16>(P, samples, stride, n_frames, gf.data()); });
+        emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCI16>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
+    } else {
+        emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCF32>(P, samples, stride, n_frames, gf.data()); });
+        emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCF32>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
+    }
+    emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel(P, n_frames, gf.data(), spec.data(), pre.data()); });
+    emu::launch(dim3(P.num_symb, n_frames), blk, 0, [&] { gen_demap_kernel(P, n_frames, gf.data(), spec.data(), out, amb, taps); });
+    return 0;
+}
+
+int emu_tx_generic(void *hv, const uint8_t *payload, int n_frames, void *frames, int fmt) {
+    auto *h = (EmuHandle *)hv;
+    if (!h->T.generic_ok) return -1;
+    const Params P = h->P;
+    const size_t sm = 2 * (size_t)P.fft_size * sizeof(float2);
+    if (fmt == kCI16) emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kGenThreads), sm, [&] { gen_tx_kernel<kCI16>(P, payload, n_frames, frames); });
+    else emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kGenThreads), sm, [&] { gen_tx_kernel<kCF32>(P, payload, n_frames, frames); });
+    return 0;
+}
+
 }  // extern "C"

@@ -32,6 +32,9 @@ class EmuModem:
         L.emu_rx_fused512_mode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int] + [vp] * 7
         L.emu_t2sin_metric.argtypes = [vp, vp, C.c_int, C.c_longlong, C.c_longlong, vp]
         L.emu_preamble_corr.argtypes = [vp, vp, C.c_int, C.c_longlong, vp, C.c_int, vp, vp]
+        L.emu_rx_generic.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong] + [vp] * 5
+        L.emu_tx_generic.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.emu_fused_ok.argtypes = [vp]
         L.emu_mod.argtypes = [vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong]
         L.emu_demod.argtypes = [vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp]
         self.h = L.emu_create(os.fsencode(config_path))
@@ -43,6 +46,8 @@ class EmuModem:
             setattr(s, n, getattr(o, n))
         s.rx_len = o.preamble_size + o.message_size
         self.use_tma = 1
+        self.fused = bool(L.emu_fused_ok(self.h))
+        s.fused_path = 1 if self.fused else 0
 
     def close(self):
         if self.h:
@@ -71,7 +76,8 @@ class EmuModem:
         payload = np.ascontiguousarray(payload, np.uint8)
         n = payload.size // s.usefull_size
         out = np.zeros((n, s.output_size), np.complex64) if fmt == CF32 else np.zeros((n, s.output_size, 2), np.int16)
-        assert self.lib.emu_tx512(self.h, payload.ctypes.data, n, out.ctypes.data, fmt) == 0
+        fn = self.lib.emu_tx512 if self.fused else self.lib.emu_tx_generic
+        assert fn(self.h, payload.ctypes.data, n, out.ctypes.data, fmt) == 0
         return out
 
     def rx_aligned_batch(self, samples, n_frames=None, frame_stride=None, offset=0, out=None, taps=False, count_ambiguous=True):
@@ -89,6 +95,11 @@ class EmuModem:
                  synced=np.zeros((n_frames, s.rx_len), np.complex64))
         base = samples.ctypes.data + offset * (4 if fmt == CI16 else 8)
         ptrs = [v.ctypes.data for v in t.values()] if taps else [None] * 5
+        if not self.fused:
+            assert self.lib.emu_rx_generic(self.h, base, fmt, n_frames, frame_stride, out.ctypes.data, amb.ctypes.data,
+                                           ptrs[0], ptrs[2], ptrs[3]) == 0
+            t.pop("grid"); t.pop("synced")
+            return (out, t, int(amb[0])) if taps else (out, int(amb[0]))
         assert self.lib.emu_rx_fused512(self.h, base, fmt, self.use_tma, n_frames, frame_stride, out.ctypes.data,
                                         amb.ctypes.data, *ptrs) == 0
         return (out, t, int(amb[0])) if taps else (out, int(amb[0]))

@@ -91,3 +91,20 @@ def test_rx_phase_unwrap_slow_path(emu, port):
 def test_read_syncless_and_chan_char(emu, port, mt):
     st = pc.check_read_and_chan_char(emu[mt], port[mt])
     assert st["rel_l2"] < 2e-6
+
+
+def test_generic_path_small_geometry(cfg_dir, oracle_lib):
+    """the any-size kernels (generic.cuh) on a 128-point configuration: tx and the full rx chain vs the oracle"""
+    o = oracle_lib.Oracle("port", cfg_dir["small"])
+    m = EmuModem(cfg_dir["small"], o.sizes)
+    assert not m.fused
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6
+    pay, rec = pc.impaired_records(o, 3, seed=5, cfo_max=0.004, noise=1.0, taps=(1.0, 0.1j), early=1)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["constell"] < 3e-6
+    fr = m.tx_batch(pay, 1)
+    s = o.sizes
+    out, _ = m.rx_aligned_batch(fr.reshape(-1, 2), n_frames=3, frame_stride=s.output_size, offset=s.t2sin_size)
+    assert np.array_equal(out, pay)
+    m.close()

@@ -267,3 +267,25 @@ def test_config2_audio_payload_through_multipath_channel(modems, port):
     ber_gpu = np.unpackbits(out ^ pay).mean()
     ber_ref = np.mean([np.unpackbits(o.rx_aligned(pc.cplx(r))["bytes"] ^ p).mean() for r, p in zip(rec, pay)])
     assert abs(ber_gpu - ber_ref) < 1e-4 and st["shift_mismatch"] <= 1
+
+
+@pytest.mark.parametrize("which", ["small", "big"])
+def test_generic_path(cfg_dir, oracle_lib, which):
+    """configurations outside the fused fft-512 kernels (BASELINE.json configs[4]: 4096-point, 64-QAM, 128 pilots)
+    run on the any-size path: tx, full rx chain with taps, clean loopback -- against the oracle"""
+    o = oracle_lib.Oracle("port", cfg_dir[which])
+    m = cb.Modem(cfg_dir[which], device=0)
+    assert m.sizes.fused_path == 0
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6
+    if which == "big":
+        pay, rec = pc.impaired_records(o, 4, seed=8, cfo_max=0.0005, noise=0.5, taps=(1.0,), early=0)
+    else:
+        pay, rec = pc.impaired_records(o, 4, seed=8, cfo_max=0.004, noise=1.0, taps=(1.0, 0.1j), early=1)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6
+    s = m.sizes
+    fr = m.tx_batch(pay, cb.CI16)
+    out, _ = m.rx_aligned_batch(fr.reshape(-1, 2), n_frames=4, frame_stride=s.output_size, offset=s.t2sin_size)
+    assert np.array_equal(out, pay)
+    m.close()
