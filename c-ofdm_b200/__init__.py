@@ -256,7 +256,10 @@ class Modem:
                             chan=self._new(samples, (n_frames, s.num_data_subc), "complex64"),
                             constell=self._new(samples, (n_frames, s.constell_size), "complex64"),
                             synced=self._new(samples, (n_frames, s.rx_len), "complex64"))
+            if s.fused_path != 1:                      # the generic path has no time-domain / grid taps
+                tap_bufs["grid"] = tap_bufs["synced"] = None
             tp = RxTaps(*[_ptr(v) for v in tap_bufs.values()])
+            tap_bufs = {k: v for k, v in tap_bufs.items() if v is not None}
         amb = C.c_ulonglong(0)
         base = _ptr(samples) + offset * (4 if fmt == CI16 else 8)
         self._chk(self.lib.cofdm_rx_aligned_batch(self.h, base, fmt, n_frames, frame_stride, _ptr(out),
