@@ -356,7 +356,9 @@ COFDM_DEV void team_fft512p_head(pc (&v)[8], const float2 *tw_p1, int t /* = lan
 
 // On entry v[k1] = twiddled pass-1 outputs; the caller has already made sure (team barrier) that nobody
 // still reads the planes.  On exit the spectrum of both symbols sits at spec_slot(k) and is visible to the team.
-template <bool INV>
+// PRUNE: outputs k = k0 + 64*k3 with k3 = 3, 4 (bins 192..319) are not stored; the receiver never looks at
+// them (data and pilots live in bins 1..132 and 380..511, and the coarse shift moves them by < 60 bins).
+template <bool INV, bool PRUNE = false>
 COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int bar_id) {
     const int q = lane & 7, p = (lane >> 3) + 4 * h;
     {
@@ -391,7 +393,10 @@ COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const flo
         const int k0 = p + 8 * q;
         const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
 #pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) { Wre[s0 + 80 * k3] = v[k3].re; Wim[s0 + 80 * k3] = v[k3].im; }
+        for (int k3 = 0; k3 < 8; k3++) {
+            if (PRUNE && (k3 == 3 || k3 == 4)) continue;
+            Wre[s0 + 80 * k3] = v[k3].re; Wim[s0 + 80 * k3] = v[k3].im;
+        }
     }
     named_bar_sync(bar_id, 64);
 }

@@ -51,4 +51,17 @@ COFDM_DEV int demap_point(float2 z, const DemapK &k, bool &amb) {
 }
 COFDM_DEV int demap_point(float2 z, int mod, bool &amb) { return demap_point(z, make_demapk(mod), amb); }
 
+// the decision alone / the ambiguity test alone (the fused kernel only pays for the latter when asked to count)
+COFDM_DEV int demap_fast(float2 z, const DemapK &k) {
+    if (k.mod == 1) return z.x + z.y > 0.0f ? 1 : 0;
+    const float re = fminf(fmaxf(z.x, -1.0f), 1.0f), im = fminf(fmaxf(z.y, -1.0f), 1.0f);
+    const int li = (int)fmaf(re + 1.0f, k.half, 0.5f), lq = (int)fmaf(im + 1.0f, k.half, 0.5f);
+    return (li | (lq << k.qshift)) & 0xff;
+}
+COFDM_DEV bool demap_ambiguous(float2 z, const DemapK &k) {
+    bool amb;
+    demap_point(z, k, amb);
+    return amb;
+}
+
 }  // namespace cofdmk

@@ -52,6 +52,7 @@ struct RxMisc {
     float2 rot_theta;                // exp(-j theta)
     float theta;
     // chan_char_lq is computed by warps 0..3 together (one sub-carrier phase per lane)
+    float4 cpart[kRxMaxPair][2];     // CP correlation partial sums of a team's two warps (A.re, A.im, B.re, B.im)
     float2 zpart[4];                 // partial sums of the pr_phase_sinh correlation
     float ph[128];                   // raw phases arg(pr[i]/mod_preamble[i])
     float sypart[4], sxypart[4];
@@ -254,17 +255,31 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             if (hasB) load_symbol_direct<FMT>(xb, frame_src, B, lane + 32 * h, 64);
             named_bar_sync(bar_id, 64);
         }
-        // raw cyclic-prefix correlation (Frame.hpp:251-253) of both symbols (each warp of the team computes it)
+        // Every sample is read from shared memory ONCE: this warp's 8 body samples per symbol (pass-1 layout,
+        // j = 128 + t + 64 r) and the two CP samples j = t, t + 64, which pair with r = 6, 7 in the CP
+        // correlation (Frame.hpp:251-253).  The team's two partial correlations meet in shared memory.
+        const int t = lane + 32 * h;
+        float2 ra[8], rb[8], cpa[2], cpb[2];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            ra[r] = xa[128 + t + 64 * r];
+            rb[r] = hasB ? xb[128 + t + 64 * r] : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < 2; c++) {
+            cpa[c] = xa[t + 64 * c];
+            cpb[c] = hasB ? xb[t + 64 * c] : make_float2(0.f, 0.f);
+        }
         {
             float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                cmac_conj(ca, xa[lane + 32 * i], xa[lane + 32 * i + 512]);
-                if (hasB) cmac_conj(cb, xb[lane + 32 * i], xb[lane + 32 * i + 512]);
-            }
+            cmac_conj(ca, cpa[0], ra[6]); cmac_conj(ca, cpa[1], ra[7]);
+            cmac_conj(cb, cpb[0], rb[6]); cmac_conj(cb, cpb[1], rb[7]);
             ca = warp_sum(ca);
             cb = warp_sum(cb);
-            const float2 sel = (lane & 1) ? cb : ca;
+            if (lane == 0) M->cpart[team][h] = make_float4(ca.x, ca.y, cb.x, cb.y);
+            named_bar_sync(bar_id, 64);           // also: the whole team has read its inputs, the planes may be reused
+            const float4 p0 = M->cpart[team][0], p1 = M->cpart[team][1];
+            const float2 sel = (lane & 1) ? make_float2(p0.z + p1.z, p0.w + p1.w) : make_float2(p0.x + p1.x, p0.y + p1.y);
             const float ang = sync_less ? 0.f : fast_atan2_turns(sel.y, sel.x);   // one evaluation serves both symbols
             thA = __shfl_sync(0xffffffffu, ang, 0);
             thB = hasB ? __shfl_sync(0xffffffffu, ang, 1) : 0.f;
@@ -283,20 +298,16 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             }
         }
         __syncwarp();
-        const int t = lane + 32 * h;
         const pc Pt = make_pc(cis_neg_turns_f(nuA * (float)(128 + t)), cis_neg_turns_f(nuB * (float)(128 + t)));
-        // rotate while loading: v[r] = x[128 + t + 64 r] * exp(-j 2pi nu (128 + t + 64 r))
+        // rotate in registers: v[r] = x[128 + t + 64 r] * exp(-j 2pi nu (128 + t + 64 r))
         pc v[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const float4 qr = qt[r];
             pc Qr; Qr.re = make_float2(qr.x, qr.y); Qr.im = make_float2(qr.z, qr.w);
             const pc w = cmul(Pt, Qr);
-            const int j = 128 + t + 64 * r;
-            const float2 a = xa[j];
-            const float2 b = hasB ? xb[j] : make_float2(0.f, 0.f);
-            v[r].re = make_float2(a.x * w.re.x - a.y * w.im.x, b.x * w.re.y - b.y * w.im.y);
-            v[r].im = make_float2(a.x * w.im.x + a.y * w.re.x, b.x * w.im.y + b.y * w.re.y);
+            v[r].re = make_float2(ra[r].x * w.re.x - ra[r].y * w.im.x, rb[r].x * w.re.y - rb[r].y * w.im.y);
+            v[r].im = make_float2(ra[r].x * w.im.x + ra[r].y * w.re.x, rb[r].x * w.im.y + rb[r].y * w.re.y);
         }
         if (TAPS || team == 0) {
             // CP samples j = t and j = t + 64: exp(-j 2pi nu j) = P(t) conj(Q^2) resp. P(t) conj(Q^1)
@@ -313,21 +324,20 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
                     da[128 + t + 64 * r] = pc_a(v[r]);
                     if (hasB) db[128 + t + 64 * r] = pc_b(v[r]);
                 }
-                da[t] = cmul(xa[t], pc_a(w0));
-                da[t + 64] = cmul(xa[t + 64], pc_a(w1));
-                if (hasB) { db[t] = cmul(xb[t], pc_b(w0)); db[t + 64] = cmul(xb[t + 64], pc_b(w1)); }
+                da[t] = cmul(cpa[0], pc_a(w0));
+                da[t + 64] = cmul(cpa[1], pc_a(w1));
+                if (hasB) { db[t] = cmul(cpb[0], pc_b(w0)); db[t + 64] = cmul(cpb[1], pc_b(w1)); }
             }
             if (team == 0) {
                 // pr_phase_sinh, CP part: conj(ref[j]) x[j] exp(-j 2pi nu' j); the missing factor
                 // exp(-j 2pi m_0 j / 512) is applied once the coarse shift is known.  Parked in shared memory.
                 float2 *zs = reinterpret_cast<float2 *>(M->wtab);      // 128 float2 = wtab[0..7]; reused before wtab is
-                zs[t] = cmulc(cmul(xa[t], pc_a(w0)), __ldg(&P.preamble_td[t]));
-                zs[t + 64] = cmulc(cmul(xa[t + 64], pc_a(w1)), __ldg(&P.preamble_td[t + 64]));
+                zs[t] = cmulc(cmul(cpa[0], pc_a(w0)), __ldg(&P.preamble_td[t]));
+                zs[t + 64] = cmulc(cmul(cpa[1], pc_a(w1)), __ldg(&P.preamble_td[t + 64]));
             }
         }
-        named_bar_sync(bar_id, 64);                // the whole team has read its inputs before the planes are reused
         team_fft512p_head<false>(v, P.tw_p1, t);
-        team_fft512p_tail<false>(v, Wre, Wim, P.tw_p2, lane, h, bar_id);
+        team_fft512p_tail<false, !TAPS>(v, Wre, Wim, P.tw_p2, lane, h, bar_id);   // the grid tap wants all 512 bins
     }
     __syncthreads();                               // #2: spectra (shifted by the unknown m_s) and kc are ready
 
@@ -527,7 +537,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         const float2 rot1 = cmul(mul_negj_pow(cis_neg_turns_f(psi1), M->mshift[1]), rot_theta);
         const float2 p1 = cmul(M->pilots[1][lane], rot1);
         const int ep = lane < 4 ? lane : lane - 8;
-        const float2 ee = cis_neg_turns((lb * (double)(32 * ep) + la) * 0.15915494309189533577);
+        const float2 ee = cis_neg_turns_f((float)((lb * (double)(32 * ep) + la) * 0.15915494309189533577));
         const float2 psa = M->pilots[A][lane], psb = M->pilots[hasB ? B : A][lane];
         const float2 wa = cmul(cscale(cmulc(p1, psa), 1.0f / (cnorm2(psa) * g)), ee);
         const float2 wb = cmul(cscale(cmulc(p1, psb), 1.0f / (cnorm2(psb) * g)), ee);
@@ -541,7 +551,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     const int mod = P.mod_type;
     const DemapK dk = make_demapk(mod);
     uint8_t *sbA = symbuf + (size_t)team * 512, *sbB = sbA + 256;
-    const bool doA = A >= 1;
+    const bool doA = A >= 1, count_amb = ambiguous != nullptr;
     int n_amb = 0;
 #pragma unroll
     for (int ee = 0; ee < 4; ee++) {
@@ -550,24 +560,22 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         const int bin = __ldg(&P.data_bin[32 * e]) + lane;            // segment e is 32 consecutive bins
         const int sa = spec_slot((bin + mA) & 511), sb = spec_slot((bin + mB) & 511);
         pc x;
-        x.re = make_float2(Wre[sa].x, Wre[sb].y);
-        x.im = make_float2(Wim[sa].x, Wim[sb].y);
+        if (mA == mB) { x.re = Wre[sa]; x.im = Wim[sa]; }             // the usual case: one 64-bit load per plane
+        else { x.re = make_float2(Wre[sa].x, Wre[sb].y); x.im = make_float2(Wim[sa].x, Wim[sb].y); }
         const float4 w4 = wt[e];
         pc w; w.re = make_float2(w4.x, w4.y); w.im = make_float2(w4.z, w4.w);
         const pc z = cmul(cmul(x, w), Ll);
-        bool amb;
         if (doA) {
             if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (A - 1)) * 256 + i] = pc_a(z);
-            sbA[i] = (uint8_t)demap_point(pc_a(z), dk, amb);
-            n_amb += amb ? 1 : 0;
+            sbA[i] = (uint8_t)demap_fast(pc_a(z), dk);
         }
         if (hasB) {
             if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (B - 1)) * 256 + i] = pc_b(z);
-            sbB[i] = (uint8_t)demap_point(pc_b(z), dk, amb);
-            n_amb += amb ? 1 : 0;
+            sbB[i] = (uint8_t)demap_fast(pc_b(z), dk);
         }
+        if (count_amb) n_amb += (doA && demap_ambiguous(pc_a(z), dk) ? 1 : 0) + (hasB && demap_ambiguous(pc_b(z), dk) ? 1 : 0);
     }
-    if (ambiguous != nullptr) {
+    if (count_amb) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_amb += __shfl_xor_sync(0xffffffffu, n_amb, o);
         if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);

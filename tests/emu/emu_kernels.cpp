@@ -58,6 +58,21 @@ int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_f
     return emu_rx_fused512_mode(hv, samples, fmt, use_tma, n_frames, stride, 0, out, amb, scal, grid, chan, constell, synced);
 }
 
+// the production instantiation (no taps, pruned last FFT pass)
+int emu_rx_fused512_notaps(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
+                           uint8_t *out, unsigned long long *amb) {
+    auto *h = (EmuHandle *)hv;
+    if (!h->T.fused512_ok) return -1;
+    const Params P = h->P;
+    RxTaps taps{};
+    const int nsym = P.n_sym_rx;
+    auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym)), rx512_smem_bytes(nsym), kern); };
+    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, false>(P, samples, stride, n_frames, out, amb, taps, 0); });
+    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, false>(P, samples, stride, n_frames, out, amb, taps, 0); });
+    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, false>(P, samples, stride, n_frames, out, amb, taps, 0); });
+    return 0;
+}
+
 int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int fmt) {
     auto *h = (EmuHandle *)hv;
     if (!h->T.fused512_ok) return -1;

@@ -22,13 +22,15 @@ class EmuModem:
     is_emulator = True
 
     def __init__(self, config_path, oracle_sizes):
-        self.lib = L = C.CDLL(build_emu.build())
+        # COFDM_EMU_LIB: use a pre-built variant of the emulator library (the ASan build of tests/test_emu_asan.py)
+        self.lib = L = C.CDLL(os.environ.get("COFDM_EMU_LIB") or build_emu.build())
         vp = C.c_void_p
         L.emu_create.restype = vp
         L.emu_create.argtypes = [C.c_char_p]
         L.emu_destroy.argtypes = [vp]
         L.emu_rx_fused512.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong] + [vp] * 7
         L.emu_tx512.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.emu_rx_fused512_notaps.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, vp, vp]
         L.emu_rx_fused512_mode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int] + [vp] * 7
         L.emu_t2sin_metric.argtypes = [vp, vp, C.c_int, C.c_longlong, C.c_longlong, vp]
         L.emu_preamble_corr.argtypes = [vp, vp, C.c_int, C.c_longlong, vp, C.c_int, vp, vp]
@@ -95,6 +97,10 @@ class EmuModem:
                  synced=np.zeros((n_frames, s.rx_len), np.complex64))
         base = samples.ctypes.data + offset * (4 if fmt == CI16 else 8)
         ptrs = [v.ctypes.data for v in t.values()] if taps else [None] * 5
+        if self.fused and not taps:
+            assert self.lib.emu_rx_fused512_notaps(self.h, base, fmt, self.use_tma, n_frames, frame_stride, out.ctypes.data,
+                                                   amb.ctypes.data if count_ambiguous else None) == 0
+            return out, int(amb[0])
         if not self.fused:
             assert self.lib.emu_rx_generic(self.h, base, fmt, n_frames, frame_stride, out.ctypes.data, amb.ctypes.data,
                                            ptrs[0], ptrs[2], ptrs[3]) == 0

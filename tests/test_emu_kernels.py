@@ -108,3 +108,13 @@ def test_generic_path_small_geometry(cfg_dir, oracle_lib):
     out, _ = m.rx_aligned_batch(fr.reshape(-1, 2), n_frames=3, frame_stride=s.output_size, offset=s.t2sin_size)
     assert np.array_equal(out, pay)
     m.close()
+
+
+def test_production_instantiation_matches_tapped_one(emu, port):
+    """no-taps kernel (pruned last FFT pass, ambiguity counting optional) decodes the same bytes"""
+    for mt in (2, 4, 6):
+        pay, rec = pc.impaired_records(port[mt], 3, seed=31 + mt)
+        a, taps, amb_t = emu[mt].rx_aligned_batch(rec, taps=True)
+        b, amb = emu[mt].rx_aligned_batch(rec)
+        c, _ = emu[mt].rx_aligned_batch(rec, count_ambiguous=False)
+        assert np.array_equal(a, b) and np.array_equal(a, c) and amb == amb_t
