@@ -100,18 +100,23 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
     }
     team_fft512p_head<true>(v, P.tw_p1, t);                                          // Frame.cpp:64 (backward, unnormalised)
     team_fft512p_tail<true>(v, Wre, Wim, P.tw_p2, lane, h, bar_id);
-    const int s = h ? B : A;                                                         // this warp writes one symbol of the pair
-    if (s >= ns) return;
-    const float sc = 0.04419417382415922028f;                                        // 1/sqrt(512), Frame.cpp:66-68
-    const int base = P.t2sin_size + P.pf_size + s * 640;
+    // output: warp h writes samples 256h .. 256h+255 of BOTH symbols, so every 64-bit plane word it loads
+    // (value of A, value of B) is used whole.  /sqrt(512) (Frame.cpp:66-68), body after the CP slot
+    // (Frame.cpp:191-192), the last 128 samples also into the CP slot (Frame.cpp:196-197).
+    const float sc = 0.04419417382415922028f;
+    const int baseA = P.t2sin_size + P.pf_size + A * 640, baseB = baseA + 640;
 #pragma unroll
-    for (int it = 0; it < 8; it++) {
-        const int n = 2 * lane + 64 * it;
+    for (int it = 0; it < 4; it++) {
+        const int n = 256 * h + 2 * lane + 64 * it;
         const float2 r0 = Wre[spec_slot(n)], i0 = Wim[spec_slot(n)], r1 = Wre[spec_slot(n + 1)], i1 = Wim[spec_slot(n + 1)];
-        const float2 a = h ? make_float2(r0.y * sc, i0.y * sc) : make_float2(r0.x * sc, i0.x * sc);
-        const float2 b = h ? make_float2(r1.y * sc, i1.y * sc) : make_float2(r1.x * sc, i1.x * sc);
-        store_sample_pair<FMT>(fout, base + 128 + n, a, b, P.mult);                   // Frame.cpp:191-192
-        if (n >= 384) store_sample_pair<FMT>(fout, base + n - 384, a, b, P.mult);     // Frame.cpp:196-197 cyclic prefix
+        const float2 a0 = make_float2(r0.x * sc, i0.x * sc), a1 = make_float2(r1.x * sc, i1.x * sc);
+        const float2 b0 = make_float2(r0.y * sc, i0.y * sc), b1 = make_float2(r1.y * sc, i1.y * sc);
+        store_sample_pair<FMT>(fout, baseA + 128 + n, a0, a1, P.mult);
+        if (n >= 384) store_sample_pair<FMT>(fout, baseA + n - 384, a0, a1, P.mult);
+        if (hasB) {
+            store_sample_pair<FMT>(fout, baseB + 128 + n, b0, b1, P.mult);
+            if (n >= 384) store_sample_pair<FMT>(fout, baseB + n - 384, b0, b1, P.mult);
+        }
     }
 }
 
@@ -143,19 +148,37 @@ t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long 
 #pragma unroll
         for (int i = 0; i < 8; i++) A[lane + 32 * i] = __ldg(src + lane + 32 * i);
     }
+    // total spectral energy by Parseval: sum_k |X_k|^2 = 256 * sum_n |x_n|^2 (saves evaluating unmasked bins)
+    float tot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; i++) tot += cnorm2(A[lane + 32 * i]);
+    tot *= 256.0f;
     __syncwarp();
     stockham_pass<8, false>(A, B, 256, 1, P.tw_t2, lane, 32);
     __syncwarp();
-    stockham_pass<8, false>(B, A, 256, 8, P.tw_t2, lane, 32);
+    stockham_pass<8, false, true>(B, A, 256, 8, P.tw_t2, lane, 32);         // twiddle index <= 7*7*4 < 256
     __syncwarp();
-    stockham_pass<4, false>(A, B, 256, 64, P.tw_t2, lane, 32);
-    __syncwarp();
-    float tot = 0.f, sine = 0.f;
+    // last pass (radix 4, ns = 64): butterfly j yields bins j, j+64, j+128, j+192; only butterflies that feed a
+    // masked bin are evaluated (the shipped mask covers bins 12..22 and 46..56: 22 of 64 butterflies)
+    float sine = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) {
-        const float e = cnorm2(B[lane + 32 * i]);
-        tot += e;
-        sine += __ldg(&P.t2_mask[lane + 32 * i]) * e;
+    for (int jj = 0; jj < 2; jj++) {
+        const int j = lane + 32 * jj;
+        float mk[4];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { mk[q] = __ldg(&P.t2_mask[j + 64 * q]); any |= mk[q] != 0.f; }
+        if (any) {
+            float2 v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q] = A[j + 64 * q];
+                if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_t2[q * j]));           // q*j <= 3*63 < 256
+            }
+            dft4<false>(v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) sine += mk[q] * cnorm2(v[q]);
+        }
     }
     tot = warp_sum(tot);
     sine = warp_sum(sine);

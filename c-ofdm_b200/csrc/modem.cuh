@@ -13,7 +13,7 @@ COFDM_DEV int extract_bits(const uint8_t *bytes, int n_bytes, int bitpos, int mo
     const int b0 = bitpos >> 3, off = bitpos & 7;
     unsigned w = 0;
     if (b0 < n_bytes) w = (unsigned)bytes[b0] << 8;
-    if (b0 + 1 < n_bytes) w |= (unsigned)bytes[b0 + 1];
+    if ((8 % mod) != 0 && b0 + 1 < n_bytes) w |= (unsigned)bytes[b0 + 1];   // mod 1,2,4,8 never straddle a byte
     return (int)((w >> (16 - mod - off)) & ((1u << mod) - 1u));
 }
 

@@ -1,0 +1,98 @@
+"""Sharding the streaming receiver (rx.cpp's acquisition loop, cofdm_rx_stream) over ranks / GPUs.
+
+The loop is a sequential state machine: where it looks next depends on the frame it found last
+(rx.cpp:126-198).  Two chains that start from different states nevertheless coincide from the first
+frame both of them detect (after a detection the state is `preamble position + message.size`, whatever
+came before).  So a long capture is cut into contiguous ranges of whole SDR blocks; every rank runs the
+unmodified loop on its range PLUS one extra block, starting cold; where two neighbouring ranks overlap,
+the earlier rank's chain (the true one) is followed until it reaches a preamble position the later rank
+also found, and the later rank's list is used from there on.  No data-path communication: each rank
+reads its own slice; the lists (a few bytes per frame) are gathered at the end.
+"""
+import numpy as np
+
+from .dist import shard_range
+
+
+def block_samples(sizes):
+    """samples per SDR block: output_size * rx_buf_size (sdr.hpp:141)"""
+    return sizes.output_size * sizes.rx_buf_size
+
+
+def shard_slice(n_samples, sizes, rank, world, overlap_blocks=1):
+    """-> (first_sample, last_sample_exclusive, first_block, last_block_exclusive) of `rank`'s slice of a capture,
+    including `overlap_blocks` extra blocks at the end (except for the last rank)."""
+    blk = block_samples(sizes)
+    n_blocks = n_samples // blk
+    b0, b1 = shard_range(n_blocks, rank, world)
+    b1x = min(n_blocks, b1 + (overlap_blocks if b1 < n_blocks else 0))
+    return b0 * blk, b1x * blk, b0, b1
+
+
+def merge_shards(shards, sizes):
+    """shards: list over ranks (in order) of (positions [absolute sample indices], bytes [n, usefull_size],
+    first_block, last_block_exclusive).  Returns (positions, bytes) of the whole capture, identical to one
+    sequential pass, plus the number of boundaries that did not re-synchronise inside the overlap (should be 0)."""
+    blk = block_samples(sizes)
+    out_pos, out_bytes, unmerged = [], [], 0
+    carry_pos, carry_bytes = np.zeros(0, np.int64), None          # the previous rank's frames beyond its own range
+    for pos, by, b0, b1 in shards:
+        pos = np.asarray(pos, dtype=np.int64)
+        start = 0
+        if len(carry_pos):
+            # follow the previous (true) chain until it meets this rank's chain
+            common = np.intersect1d(carry_pos, pos)
+            if len(common):
+                first = common[0]
+                k = int(np.nonzero(carry_pos == first)[0][0])
+                out_pos.extend(carry_pos[:k].tolist())
+                out_bytes.extend(carry_bytes[:k])
+                start = int(np.nonzero(pos == first)[0][0])
+            else:
+                unmerged += 1
+                out_pos.extend(carry_pos.tolist())
+                out_bytes.extend(carry_bytes)
+                start = int(np.searchsorted(pos, carry_pos[-1] + 1))
+        own_end = b1 * blk
+        own = np.nonzero(pos[start:] < own_end)[0]
+        n_own = start + (int(own[-1]) + 1 if len(own) else 0)
+        # a frame is owned by the range that contains its preamble; the rest of the list is carried over
+        out_pos.extend(pos[start:n_own].tolist())
+        out_bytes.extend(by[start:n_own])
+        carry_pos, carry_bytes = pos[n_own:], by[n_own:]
+    out_pos.extend(carry_pos.tolist())
+    if carry_bytes is not None:
+        out_bytes.extend(carry_bytes)
+    b = np.stack(out_bytes) if out_bytes else np.zeros((0, sizes.usefull_size), np.uint8)
+    return np.array(out_pos, dtype=np.int64), b, unmerged
+
+
+def rx_stream_sharded(run, capture_i16, sizes, world):
+    """run(capture_slice) -> (positions, bytes).  Emulates `world` ranks in one process (tests, single GPU)."""
+    n = capture_i16.shape[0]
+    shards = []
+    for r in range(world):
+        s0, s1, b0, b1 = shard_slice(n, sizes, r, world)
+        pos, by = run(capture_i16[s0:s1])
+        shards.append((np.asarray(pos) + s0, by, b0, b1))
+    return merge_shards(shards, sizes)
+
+
+def rx_stream_distributed(modem, capture_i16):
+    """torchrun entry: every rank receives its slice of the capture on its own GPU, rank 0 merges.
+    The only communication is the gather of the per-rank frame lists.  Returns (positions, bytes, unmerged)
+    on rank 0 and (None, None, None) elsewhere."""
+    import torch.distributed as dist
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    s = modem.sizes
+    s0, s1, b0, b1 = shard_slice(capture_i16.shape[0], s, rank, world)
+    pos, by = modem.rx_stream(capture_i16[s0:s1])
+    mine = (np.asarray(pos) + s0, by, b0, b1)
+    if world == 1:
+        return merge_shards([mine], s)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object(mine, gathered, dst=0)
+    if rank != 0:
+        return None, None, None
+    return merge_shards(gathered, s)

@@ -289,3 +289,23 @@ def test_generic_path(cfg_dir, oracle_lib, which):
     out, _ = m.rx_aligned_batch(fr.reshape(-1, 2), n_frames=4, frame_stride=s.output_size, offset=s.t2sin_size)
     assert np.array_equal(out, pay)
     m.close()
+
+
+def test_stream_sharded_over_ranks_on_gpu(cfg_dir, oracle_lib):
+    """config 4: the acquisition loop sharded over 3 (emulated) ranks, GPU engine, vs one sequential oracle pass"""
+    from cofdm_b200 import stream
+    o = oracle_lib.Oracle("port", cfg_dir["stream"])
+    m = cb.Modem(cfg_dir["stream"], device=0)
+    s = o.sizes
+    n = 70
+    pay = pc.synth.payloads(n, s.usefull_size, seed=19)
+    tx16 = m.tx_batch(pay, cb.CI16)
+    rng = np.random.default_rng(29)
+    fr = pc.synth.channel(tx16, seed=6, cfo=rng.uniform(-0.003, 0.003, n), phase=rng.uniform(0, 1, n), noise_sigma=1.0)
+    cap, _ = pc.synth.capture(fr, gaps=rng.integers(260, 1500, n), noise_sigma=3.0, seed=7, tail=s.output_size * 12)
+    blk = stream.block_samples(s)
+    cap = cap[: (cap.shape[0] // blk) * blk]
+    want_pos, want_by = o.rx_stream(cap)
+    pos, by, unmerged = stream.rx_stream_sharded(lambda c: m.rx_stream(c), cap, s, 3)
+    assert unmerged == 0 and pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
+    m.close()
