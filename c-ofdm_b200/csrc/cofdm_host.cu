@@ -8,6 +8,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -58,6 +59,8 @@ struct cofdm {
     DevBuf pipe_in[kPipe], pipe_out[kPipe];
     DevBuf scratch_a, scratch_b, scratch_c;
     DevBuf gen_frames, gen_spec, gen_pre;        // generic path intermediates
+    DevBuf fscal;                                // per-frame scalars handed from the acquire to the demod kernel
+    int rx_split = 1;                            // 1: acquire + demod kernels, 0: single fused kernel
     unsigned long long *amb_dev = nullptr;       // ambiguity counter
     unsigned long long *pos_dev = nullptr;       // find_t2sin result
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -105,27 +108,44 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
         return fail(COFDM_ERR_UNSUPPORTED, "rx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
     }
     const int nsym = h->P.n_sym_rx;
-    const size_t sm = rx512_smem_bytes(nsym);
-    const dim3 grid((unsigned)n_frames), block(rx512_threads(nsym));
     if ((uintptr_t)bytes & 3) return fail(COFDM_ERR_ARG, "rx: the output byte buffer must be 4-byte aligned");
     const bool small = nsym <= 9;
     const bool want = taps.scal || taps.grid || taps.chan || taps.constell || taps.synced;
     const bool tma = fmt == COFDM_CF32 && ((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0;
     // cf32 records that are not 16-byte aligned (a frame cut out of a capture) and int16 records use plain loads
-#define COFDM_RX_LAUNCH(F, T, S, W) rx_fused512_kernel<F, T, S, W><<<grid, block, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less)
-#define COFDM_RX_PICK(F, T)                                                                    \
+    const bool split = h->rx_split && small;
+    FrameScal *fsc = nullptr;
+    if (split) {
+        CU_TRY(h->fscal.reserve(n_frames * sizeof(FrameScal)));
+        fsc = (FrameScal *)h->fscal.p;
+    }
+#define COFDM_RX_LAUNCH(F, T, S, W, MD) \
+    rx_fused512_kernel<F, T, S, W, MD><<<(unsigned)n_frames, rx512_threads(nsym, MD), rx512_smem_bytes(nsym, MD), st>>>( \
+        h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
+#define COFDM_RX_PICK(F, T, MD)                                                                \
     do {                                                                                       \
-        if (small) { if (want) COFDM_RX_LAUNCH(F, T, 9, true); else COFDM_RX_LAUNCH(F, T, 9, false); } \
-        else { if (want) COFDM_RX_LAUNCH(F, T, kRxMaxSym, true); else COFDM_RX_LAUNCH(F, T, kRxMaxSym, false); } \
+        if (small) { if (want) COFDM_RX_LAUNCH(F, T, 9, true, MD); else COFDM_RX_LAUNCH(F, T, 9, false, MD); } \
+        else { if (want) COFDM_RX_LAUNCH(F, T, kRxMaxSym, true, 0); else COFDM_RX_LAUNCH(F, T, kRxMaxSym, false, 0); } \
     } while (0)
-    if (fmt == COFDM_CI16) COFDM_RX_PICK(kCI16, false);
-    else if (tma) COFDM_RX_PICK(kCF32, true);
-    else COFDM_RX_PICK(kCF32, false);
+#define COFDM_RX_MODE(MD)                                   \
+    do {                                                    \
+        if (fmt == COFDM_CI16) COFDM_RX_PICK(kCI16, false, MD); \
+        else if (tma) COFDM_RX_PICK(kCF32, true, MD);       \
+        else COFDM_RX_PICK(kCF32, false, MD);               \
+    } while (0)
+    if (split) {
+        COFDM_RX_MODE(1);                                   // acquire: preamble -> 48 bytes of scalars per frame
+        if (int rc = check_launch(h, "rx512_acquire")) return rc;
+        COFDM_RX_MODE(2);                                   // demod: message symbols -> payload bytes
+    } else {
+        COFDM_RX_MODE(0);
+    }
+#undef COFDM_RX_MODE
 #undef COFDM_RX_PICK
 #undef COFDM_RX_LAUNCH
     if (int rc = check_launch(h, "rx_fused512")) return rc;
     if (taps.synced != nullptr && taps.scal != nullptr && !sync_less) {
-        rx_synced_fixup_kernel<<<grid, 128, 0, st>>>(h->P, (int)n_frames, taps);
+        rx_synced_fixup_kernel<<<(unsigned)n_frames, 128, 0, st>>>(h->P, (int)n_frames, taps);
         return check_launch(h, "rx_synced_fixup");
     }
     return COFDM_OK;
@@ -238,7 +258,7 @@ void cofdm_destroy(cofdm_t *h) {
         if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
     }
     h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release();
-    h->gen_frames.release(); h->gen_spec.release(); h->gen_pre.release();
+    h->gen_frames.release(); h->gen_spec.release(); h->gen_pre.release(); h->fscal.release();
     if (h->amb_dev) cudaFree(h->amb_dev);
     if (h->pos_dev) cudaFree(h->pos_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -292,15 +312,23 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     if (T.fused512_ok) {
-        const int smr = (int)rx512_smem_bytes(P.n_sym_rx), smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
+        const int smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
         cudaError_t a = cudaSuccess, b = cudaSuccess;
-#define COFDM_RX_ATTR(F, T, S, W) \
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<F, T, S, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smr)
-#define COFDM_RX_ATTR4(F, T) COFDM_RX_ATTR(F, T, 9, true); COFDM_RX_ATTR(F, T, 9, false); COFDM_RX_ATTR(F, T, kRxMaxSym, true); COFDM_RX_ATTR(F, T, kRxMaxSym, false)
-        COFDM_RX_ATTR4(kCF32, true);
-        COFDM_RX_ATTR4(kCF32, false);
-        COFDM_RX_ATTR4(kCI16, false);
-#undef COFDM_RX_ATTR4
+        {
+            const char *e = std::getenv("COFDM_RX_SPLIT");
+            if (e) h->rx_split = std::atoi(e) != 0;
+        }
+        // maximum shared-memory carve-out: occupancy of every mode is bounded by shared memory, not by L1
+#define COFDM_RX_ATTR(F, T, S, W, MD) \
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<F, T, S, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rx512_smem_bytes(P.n_sym_rx, MD)); \
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<F, T, S, W, MD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+#define COFDM_RX_ATTR_ALL(F, T) \
+        COFDM_RX_ATTR(F, T, 9, true, 0); COFDM_RX_ATTR(F, T, 9, false, 0); COFDM_RX_ATTR(F, T, kRxMaxSym, true, 0); COFDM_RX_ATTR(F, T, kRxMaxSym, false, 0); \
+        COFDM_RX_ATTR(F, T, 9, true, 1); COFDM_RX_ATTR(F, T, 9, false, 1); COFDM_RX_ATTR(F, T, 9, true, 2); COFDM_RX_ATTR(F, T, 9, false, 2)
+        COFDM_RX_ATTR_ALL(kCF32, true);
+        COFDM_RX_ATTR_ALL(kCF32, false);
+        COFDM_RX_ATTR_ALL(kCI16, false);
+#undef COFDM_RX_ATTR_ALL
 #undef COFDM_RX_ATTR
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);

@@ -154,7 +154,25 @@ COFDM_DEV double warp_sum(double v) {
 #ifdef COFDM_EMU
 COFDM_DEV void named_bar_sync(int id, int nthreads) { emu::named_barrier(id, nthreads); }
 #else
-COFDM_DEV void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+// id must be a compile-time constant at every call site (see team_bar_sync below)
+#define named_bar_sync(id, nthreads) asm volatile("bar.sync %0, %1;" ::"n"(id), "r"(nthreads) : "memory")
+#endif
+
+// Team barriers with IMMEDIATE ids.  An SM has 64 hardware barriers; a kernel whose barrier id is a run-time
+// value is charged all 16 per CTA (ptxas cannot bound it), which caps residency at 4 CTAs per SM.  With
+// immediates ptxas counts max id + 1.  Ids: 0 = __syncthreads, 1 = coarse-CFO warps, 2 = channel-fit warps,
+// 3 + team = FFT team.  MAXT = number of teams the instantiation can have.
+#ifdef COFDM_EMU
+template <int MAXT> COFDM_DEV void team_bar_sync(int team) { emu::named_barrier(3 + team, 64); }
+#else
+template <int ID> COFDM_DEV void bar_sync_imm(int nthreads) { asm volatile("bar.sync %0, %1;" ::"n"(ID), "r"(nthreads) : "memory"); }
+template <int MAXT> COFDM_DEV void team_bar_sync(int team) {
+    // a single-team kernel (the acquire kernel) gets an immediate id and therefore a small barrier count (it wants
+    // 8 CTAs per SM); multi-team kernels are held to <= 4 CTAs per SM by registers / shared memory anyway, so a
+    // run-time id (all 16 barriers charged) costs them nothing and saves the dispatch on `team`.
+    if (MAXT == 1) bar_sync_imm<3>(64);
+    else asm volatile("bar.sync %0, %1;" ::"r"(3 + team), "r"(64) : "memory");
+}
 #endif
 
 // ---- mbarrier + TMA 1-D bulk copy (global -> shared) ---------------------------------------------

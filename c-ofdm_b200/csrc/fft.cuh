@@ -358,21 +358,21 @@ COFDM_DEV void team_fft512p_head(pc (&v)[8], const float2 *tw_p1, int t /* = lan
 // still reads the planes.  On exit the spectrum of both symbols sits at spec_slot(k) and is visible to the team.
 // PRUNE: outputs k = k0 + 64*k3 with k3 = 3, 4 (bins 192..319) are not stored; the receiver never looks at
 // them (data and pilots live in bins 1..132 and 380..511, and the coarse shift moves them by < 60 bins).
-template <bool INV, bool PRUNE = false>
-COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int bar_id) {
+template <bool INV, int MAXT, bool PRUNE = false>
+COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int team) {
     const int q = lane & 7, p = (lane >> 3) + 4 * h;
     {
         const int b = q + 8 * p;
 #pragma unroll
         for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[k1].re; Wim[b + 72 * k1] = v[k1].im; }
     }
-    named_bar_sync(bar_id, 64);
+    team_bar_sync<MAXT>(team);
     {
         const int b = q + 72 * p;
 #pragma unroll
         for (int n2 = 0; n2 < 8; n2++) { v[n2].re = Wre[b + 8 * n2]; v[n2].im = Wim[b + 8 * n2]; }
     }
-    named_bar_sync(bar_id, 64);
+    team_bar_sync<MAXT>(team);
     dft8<INV>(v);
 #pragma unroll
     for (int k2 = 1; k2 < 8; k2++) v[k2] = cmul(v[k2], twid<INV>(__ldg(&tw_p2[k2 * 8 + q])));
@@ -381,13 +381,13 @@ COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const flo
 #pragma unroll
         for (int k2 = 0; k2 < 8; k2++) { Wre[b + 9 * k2] = v[k2].re; Wim[b + 9 * k2] = v[k2].im; }
     }
-    named_bar_sync(bar_id, 64);
+    team_bar_sync<MAXT>(team);
     {
         const int b = 9 * q + 72 * p;
 #pragma unroll
         for (int n3 = 0; n3 < 8; n3++) { v[n3].re = Wre[b + n3]; v[n3].im = Wim[b + n3]; }
     }
-    named_bar_sync(bar_id, 64);
+    team_bar_sync<MAXT>(team);
     dft8<INV>(v);
     {
         const int k0 = p + 8 * q;
@@ -398,7 +398,7 @@ COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const flo
             Wre[s0 + 80 * k3] = v[k3].re; Wim[s0 + 80 * k3] = v[k3].im;
         }
     }
-    named_bar_sync(bar_id, 64);
+    team_bar_sync<MAXT>(team);
 }
 
 }  // namespace cofdmk

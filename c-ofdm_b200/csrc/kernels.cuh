@@ -81,7 +81,8 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
         }
         return;
     }
-    const int team = warp >> 1, h = warp & 1, bar_id = 2 + team;
+    const int team = warp >> 1, h = warp & 1;
+    constexpr int kMaxTeams = (kMaxFusedSymb + 1) / 2;
     const int A = 2 * team, B = A + 1;
     const bool hasB = B < ns;
     float2 *Wre = W + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
@@ -99,7 +100,7 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
         v[r] = make_pc(va, vb);
     }
     team_fft512p_head<true>(v, P.tw_p1, t);                                          // Frame.cpp:64 (backward, unnormalised)
-    team_fft512p_tail<true>(v, Wre, Wim, P.tw_p2, lane, h, bar_id);
+    team_fft512p_tail<true, kMaxTeams>(v, Wre, Wim, P.tw_p2, lane, h, team);
     // output: warp h writes samples 256h .. 256h+255 of BOTH symbols, so every 64-bit plane word it loads
     // (value of A, value of B) is used whole.  /sqrt(512) (Frame.cpp:66-68), body after the CP slot
     // (Frame.cpp:191-192), the last 128 samples also into the CP slot (Frame.cpp:196-197).

@@ -59,14 +59,36 @@ struct RxMisc {
     int jumppart[4];
 };
 
+// The chain runs either as ONE kernel per frame (MODE 0) or as TWO kernels that together still read every
+// sample exactly once (MODE 1 + MODE 2):
+//   MODE 1 "acquire": the preamble only -- coarse CFO, its FFT, theta, the channel line -> 48 bytes per frame
+//   MODE 2 "demod":   the message symbols only -- CP correlation, rotation, FFT, pilots, equalise, demap
+// The split removes the two in-CTA waits of the fused form (message warps idling until the coarse estimate
+// and the channel fit of the preamble are done) and lets 4 demod CTAs (instead of 3 fused ones) share an SM.
+struct FrameScal {
+    int kc, m0;             // coarse shift numerator; whole-bin shift of the preamble
+    float th0, theta;       // Arg of the preamble's CP correlation (turns); pr_phase_sinh angle (radians)
+    float2 rot_theta;       // exp(-j theta)
+    double a, b;            // chan_char_lq line
+};
+
 COFDM_HD int rx512_npair(int nsym) { return (nsym + 1) / 2; }
-COFDM_HD int rx512_threads(int nsym) { return 32 * (2 * rx512_npair(nsym) + kCoarseWarps); }
-COFDM_HD size_t rx512_smem_bytes(int nsym) {
-    return (size_t)rx512_npair(nsym) * kPairSlots * sizeof(float2)   // symbol pairs / FFT work planes
-           + 2 * 640 * sizeof(float2)                                // coarse-CFO scratch SA, SB
-           + (size_t)rx512_npair(nsym) * 512                         // demapped symbols
+// symbols handled by a kernel of the given mode, for a frame of nsym_all symbols (preamble included)
+COFDM_HD int rx512_mode_nsym(int nsym_all, int mode) { return mode == 1 ? 1 : (mode == 2 ? nsym_all - 1 : nsym_all); }
+COFDM_HD int rx512_threads(int nsym_all, int mode = 0) {
+    return 32 * (2 * rx512_npair(rx512_mode_nsym(nsym_all, mode)) + (mode == 2 ? 0 : kCoarseWarps));
+}
+COFDM_HD size_t rx512_smem_bytes(int nsym_all, int mode = 0) {
+    const int np = rx512_npair(rx512_mode_nsym(nsym_all, mode));
+    return (size_t)np * kPairSlots * sizeof(float2)                  // symbol pairs / FFT work planes
+           + (mode == 2 ? 0 : 2 * 640 * sizeof(float2))              // coarse-CFO scratch SA, SB
+           + (size_t)np * 512                                        // demapped symbols
            + sizeof(RxMisc);
 }
+COFDM_HD constexpr int rx512_max_threads(int maxsym, int mode) {
+    return 32 * (2 * (((mode == 1 ? 1 : (mode == 2 ? maxsym - 1 : maxsym)) + 1) / 2) + (mode == 2 ? 0 : kCoarseWarps));
+}
+COFDM_HD constexpr int rx512_min_blocks(int maxsym, int mode) { return maxsym > 9 ? 1 : (mode == 1 ? 8 : (mode == 2 ? 4 : 3)); }
 
 // 640 (or n) samples of one symbol -> shared memory without TMA: int16 wire format, or any source that
 // is not 16-byte aligned (a frame cut out of a capture at an arbitrary sample).
@@ -128,15 +150,18 @@ COFDM_DEV float2 mul_negj_pow(float2 v, int m) {
 }
 
 // TAPS: compile the debug/parity taps in (tests) or out (production, benchmark).
-template <int FMT, bool USE_TMA, int MAXSYM, bool TAPS>
-__global__ void __launch_bounds__(32 * (2 * ((MAXSYM + 1) / 2) + kCoarseWarps), MAXSYM <= 9 ? 3 : 1)
+template <int FMT, bool USE_TMA, int MAXSYM, bool TAPS, int MODE = 0>
+__global__ void __launch_bounds__(rx512_max_threads(MAXSYM, MODE), rx512_min_blocks(MAXSYM, MODE))
 rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/,
                    int n_frames, uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous,
-                   const RxTaps taps, const int sync_less) {
+                   const RxTaps taps, const int sync_less, FrameScal *__restrict__ fscal = nullptr) {
     // sync_less != 0: FRAME_FORM::read / OFDM_FORM::read (Frame.cpp:201-208,239-242): no CFO, phase or channel
     // correction at all -- CP strip, FFT, pilot normalisation, segment correction, demap.
     COFDM_DYN_SMEM(smem_raw);
-    const int nsym = P.n_sym_rx;                 // 1 preamble + num_symb message symbols
+    constexpr int kMaxTeams = (rx512_max_threads(MAXSYM, MODE) / 32 - (MODE == 2 ? 0 : kCoarseWarps)) / 2;
+    const int nsym_all = P.n_sym_rx;             // 1 preamble + num_symb message symbols
+    const int sym0 = MODE == 2 ? 1 : 0;          // first frame symbol this kernel handles
+    const int nsym = rx512_mode_nsym(nsym_all, MODE);   // number of symbols it handles (local index 0..nsym-1)
     const int npair = rx512_npair(nsym);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int frame = blockIdx.x;
@@ -145,12 +170,12 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     float2 *X = reinterpret_cast<float2 *>(smem_raw);
     float2 *SA = X + (size_t)npair * kPairSlots;
     float2 *SB = SA + 640;
-    uint8_t *symbuf = reinterpret_cast<uint8_t *>(SB + 640);
+    uint8_t *symbuf = reinterpret_cast<uint8_t *>(MODE == 2 ? SA : SB + 640);
     RxMisc *M = reinterpret_cast<RxMisc *>(symbuf + (size_t)npair * 512);
 
     const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
     const char *frame_src = reinterpret_cast<const char *>(samples) + (size_t)frame * (size_t)frame_stride * sample_bytes;
-    const bool is_coarse = warp >= 2 * npair;
+    const bool is_coarse = MODE != 2 && warp >= 2 * npair;
     const float inv2pi = 0.15915494309189533577f;
 
     // ---- stage the frame: one bulk copy per symbol + a private copy of the preamble for the coarse warps.
@@ -167,25 +192,25 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             named_bar_sync(1, 32 * kCoarseWarps);
         } else {
             if ((warp & 1) == 0 && lane == 0) {
-                const int s0 = warp, s1 = warp + 1;        // symbols 2*team and 2*team+1
+                const int s0 = warp, s1 = warp + 1;        // local symbols 2*team and 2*team+1
                 mbar_init(&M->mbar[s0], 1);
                 if (s1 < nsym) mbar_init(&M->mbar[s1], 1);
                 mbar_fence_init();
                 mbar_arrive_expect_tx(&M->mbar[s0], 640 * 8);
-                tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots, frame_src + (size_t)s0 * 640 * 8, 640 * 8, &M->mbar[s0]);
+                tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots, frame_src + (size_t)(sym0 + s0) * 640 * 8, 640 * 8, &M->mbar[s0]);
                 if (s1 < nsym) {
                     mbar_arrive_expect_tx(&M->mbar[s1], 640 * 8);
-                    tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots + 640, frame_src + (size_t)s1 * 640 * 8, 640 * 8, &M->mbar[s1]);
+                    tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots + 640, frame_src + (size_t)(sym0 + s1) * 640 * 8, 640 * 8, &M->mbar[s1]);
                 }
             }
-            named_bar_sync(2 + (warp >> 1), 64);
+            team_bar_sync<kMaxTeams>(warp >> 1);
         }
     }
 
     const int team = warp >> 1, h = warp & 1;      // FFT warps: team = symbol pair, h = which half of the butterflies
-    const int bar_id = 2 + team;
-    const int A = 2 * team, B = 2 * team + 1;
-    const bool hasB = B < nsym;
+    const int lA = 2 * team, lB = 2 * team + 1;   // local symbol indices (buffers, mbarriers)
+    const bool hasB = lB < nsym;
+    const int A = sym0 + lA, B = sym0 + lB;        // frame symbol indices (0 = preamble)
     float2 *Wre = X + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
     float thA = 0.f, thB = 0.f;                    // Arg(C_s) in turns
 
@@ -248,12 +273,12 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         // ================= FFT team: symbols A and B, this warp owns butterflies t = lane + 32 h =================
         float2 *xa = Wre, *xb = Wre + 640;
         if (USE_TMA) {
-            mbar_wait(&M->mbar[A], 0);
-            if (hasB) mbar_wait(&M->mbar[B], 0);
+            mbar_wait(&M->mbar[lA], 0);
+            if (hasB) mbar_wait(&M->mbar[lB], 0);
         } else {
             load_symbol_direct<FMT>(xa, frame_src, A, lane + 32 * h, 64);
             if (hasB) load_symbol_direct<FMT>(xb, frame_src, B, lane + 32 * h, 64);
-            named_bar_sync(bar_id, 64);
+            team_bar_sync<kMaxTeams>(team);
         }
         // Every sample is read from shared memory ONCE: this warp's 8 body samples per symbol (pass-1 layout,
         // j = 128 + t + 64 r) and the two CP samples j = t, t + 64, which pair with r = 6, 7 in the CP
@@ -277,7 +302,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             ca = warp_sum(ca);
             cb = warp_sum(cb);
             if (lane == 0) M->cpart[team][h] = make_float4(ca.x, ca.y, cb.x, cb.y);
-            named_bar_sync(bar_id, 64);           // also: the whole team has read its inputs, the planes may be reused
+            team_bar_sync<kMaxTeams>(team);           // also: the whole team has read its inputs, the planes may be reused
             const float4 p0 = M->cpart[team][0], p1 = M->cpart[team][1];
             const float2 sel = (lane & 1) ? make_float2(p0.z + p1.z, p0.w + p1.w) : make_float2(p0.x + p1.x, p0.y + p1.y);
             const float ang = sync_less ? 0.f : fast_atan2_turns(sel.y, sel.x);   // one evaluation serves both symbols
@@ -309,7 +334,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             v[r].re = make_float2(ra[r].x * w.re.x - ra[r].y * w.im.x, rb[r].x * w.re.y - rb[r].y * w.im.y);
             v[r].im = make_float2(ra[r].x * w.im.x + ra[r].y * w.re.x, rb[r].x * w.im.y + rb[r].y * w.re.y);
         }
-        if (TAPS || team == 0) {
+        if (TAPS || A == 0) {
             // CP samples j = t and j = t + 64: exp(-j 2pi nu j) = P(t) conj(Q^2) resp. P(t) conj(Q^1)
             const float4 q1 = qt[1], q2 = qt[2];
             pc Q1, Q2;
@@ -328,7 +353,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
                 da[t + 64] = cmul(cpa[1], pc_a(w1));
                 if (hasB) { db[t] = cmul(cpb[0], pc_b(w0)); db[t + 64] = cmul(cpb[1], pc_b(w1)); }
             }
-            if (team == 0) {
+            if (A == 0) {
                 // pr_phase_sinh, CP part: conj(ref[j]) x[j] exp(-j 2pi nu' j); the missing factor
                 // exp(-j 2pi m_0 j / 512) is applied once the coarse shift is known.  Parked in shared memory.
                 float2 *zs = reinterpret_cast<float2 *>(M->wtab);      // 128 float2 = wtab[0..7]; reused before wtab is
@@ -337,11 +362,19 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             }
         }
         team_fft512p_head<false>(v, P.tw_p1, t);
-        team_fft512p_tail<false, !TAPS>(v, Wre, Wim, P.tw_p2, lane, h, bar_id);   // the grid tap wants all 512 bins
+        team_fft512p_tail<false, kMaxTeams, !TAPS>(v, Wre, Wim, P.tw_p2, lane, h, team);   // the grid tap wants all 512 bins
     }
     __syncthreads();                               // #2: spectra (shifted by the unknown m_s) and kc are ready
 
-    const int kc = M->kc;
+    FrameScal fs{};
+    if (MODE == 2) {
+        fs = fscal[frame];                         // written by the acquire kernel (same stream, earlier launch)
+        if (tid == 0) {                            // symbol 0's entries, for the constant phase of message symbol 0
+            M->theta_t[0] = fs.th0; M->mshift[0] = fs.m0;
+            M->a = fs.a; M->b = fs.b; M->rot_theta = fs.rot_theta; M->theta = fs.theta;
+        }
+    }
+    const int kc = MODE == 2 ? fs.kc : M->kc;
     int mA = 0, mB = 0;
     if (!is_coarse) {
         // m_s and the reference's phi_s (Frame.hpp:254): phi_t = theta_t - 512 shift + m_s in (-0.5, 0.5]
@@ -365,7 +398,9 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             if (lane == 0) { M->pabs[A] = pa; if (hasB) M->pabs[B] = pb; }
         }
     }
-    if (sync_less) {
+    if (MODE == 2) {
+        // nothing: theta and the channel line come from the acquire kernel
+    } else if (sync_less) {
         if (tid == 0) { M->a = 0.0; M->b = 0.0; M->rot_theta = make_float2(1.f, 0.f); M->theta = 0.f; }
     } else if (warp < 4) {
         // ---- pr_phase_sinh (Frame.hpp:265-274) and chan_char_lq (Frame.hpp:389-434) on warps 0..3 together:
@@ -392,7 +427,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         }
         z = warp_sum(z);
         if (lane == 0) M->zpart[warp] = z;
-        named_bar_sync(15, 128);
+        named_bar_sync(2, 128);
         z = cadd(cadd(M->zpart[0], M->zpart[1]), cadd(M->zpart[2], M->zpart[3]));
         const float inv = rsqrtf(fmaxf(cnorm2(z), 1e-30f));
         const float2 rot = make_float2(z.x * inv, -z.y * inv);
@@ -408,7 +443,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         const unsigned jm = __ballot_sync(0xffffffffu, jump);
         const float sy = warp_sum(ph), sxy = warp_sum(ph * (float)gi);
         if (lane == 0) { M->sypart[warp] = sy; M->sxypart[warp] = sxy; M->jumppart[warp] = jm != 0u; }
-        named_bar_sync(15, 128);
+        named_bar_sync(2, 128);
         if (warp == 0) {
             // steps across the three warp boundaries
             bool bj = false;
@@ -482,22 +517,27 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
 
     const double la = M->a, lb = M->b;
     float g = 0.f;                                 // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
-    for (int s = 1; s < nsym; s++) g += M->pabs[s];
-    g /= (float)((nsym - 1) * 8) * P.pilot_ampl;
+    for (int s = 1; s < nsym_all; s++) g += M->pabs[s];
+    g /= (float)((nsym_all - 1) * 8) * P.pilot_ampl;
     const float2 rot_theta = M->rot_theta;
 
     if (TAPS) {
         if (taps.scal != nullptr && tid == 0) {
             float *sc = taps.scal + (size_t)frame * 48;
-            sc[0] = (float)((double)kc / (double)P.pf_den); sc[1] = (float)la; sc[2] = (float)lb; sc[3] = M->theta;
-            sc[4] = g; sc[5] = (float)kc; sc[6] = 0.f; sc[7] = 0.f;
-            for (int s = 0; s < nsym; s++) { sc[16 + s] = (float)M->mshift[s]; sc[32 + s] = M->theta_t[s]; }
+            if (MODE != 2) {
+                sc[0] = (float)((double)kc / (double)P.pf_den); sc[1] = (float)la; sc[2] = (float)lb; sc[3] = M->theta;
+                sc[5] = (float)kc; sc[6] = 0.f; sc[7] = 0.f;
+            }
+            if (MODE != 1) sc[4] = g;
+            for (int s = sym0; s < sym0 + nsym; s++) { sc[16 + s] = (float)M->mshift[s]; sc[32 + s] = M->theta_t[s]; }
         }
-        if (taps.chan != nullptr && !sync_less) {
+        if (MODE == 2) {
+            // the channel taps belong to the acquire kernel
+        } else if (taps.chan != nullptr && !sync_less) {
             for (int i = tid; i < 256; i += blockDim.x)
                 taps.chan[(size_t)frame * 256 + i] = cis_turns((lb * (double)(i < 128 ? i : i - 256) + la) * 0.15915494309189533577);
         }
-        if (taps.chan != nullptr && sync_less) {
+        if (MODE != 2 && taps.chan != nullptr && sync_less) {
             // PREAMBLE_FORM::chan_char (Frame.hpp:375-385) on the preamble as it stands: pr = preamble.fft()
             // (own pilot normalisation, Frame.cpp:76-84; coef == 1), chan_est[i] = pr[i] / mod_preamble[i]
             const float gp = M->pabs[0] / (8.0f * P.pilot_ampl);
@@ -509,16 +549,25 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             }
         }
     }
+    if (MODE == 1) {
+        if (tid == 0) {
+            FrameScal o;
+            o.kc = kc; o.m0 = sync_less ? 0 : M->mshift[0]; o.th0 = M->theta_t[0]; o.theta = M->theta;
+            o.rot_theta = rot_theta; o.a = la; o.b = lb;
+            fscal[frame] = o;
+        }
+        return;
+    }
     if (is_coarse) return;
 
     if (TAPS && taps.grid != nullptr) {
         // FFT_buf after FFT_FORM::read's normalisation: every bin of every message symbol, fully rotated
         const int s = h ? B : A;
-        if (s >= 1 && s < nsym) {
+        if (s >= 1 && s < nsym_all && (h == 0 || hasB)) {
             const float psi = sym_turns(M->theta_t, M->mshift, s);
             const int ms = h ? mB : mA;
             const float2 rs = cscale(cmul(mul_negj_pow(cis_neg_turns_f(psi), ms), rot_theta), 1.0f / g);
-            float2 *dst = taps.grid + ((size_t)frame * (nsym - 1) + (s - 1)) * 512;
+            float2 *dst = taps.grid + ((size_t)frame * (nsym_all - 1) + (s - 1)) * 512;
             for (int k = lane; k < 512; k += 32) {
                 const int sl = spec_slot((k + ms) & 511);
                 dst[k] = cmul(h ? make_float2(Wre[sl].y, Wim[sl].y) : make_float2(Wre[sl].x, Wim[sl].x), rs);
@@ -566,11 +615,11 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         pc w; w.re = make_float2(w4.x, w4.y); w.im = make_float2(w4.z, w4.w);
         const pc z = cmul(cmul(x, w), Ll);
         if (doA) {
-            if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (A - 1)) * 256 + i] = pc_a(z);
+            if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym_all - 1) + (A - 1)) * 256 + i] = pc_a(z);
             sbA[i] = (uint8_t)demap_fast(pc_a(z), dk);
         }
         if (hasB) {
-            if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (B - 1)) * 256 + i] = pc_b(z);
+            if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym_all - 1) + (B - 1)) * 256 + i] = pc_b(z);
             sbB[i] = (uint8_t)demap_fast(pc_b(z), dk);
         }
         if (count_amb) n_amb += (doA && demap_ambiguous(pc_a(z), dk) ? 1 : 0) + (hasB && demap_ambiguous(pc_b(z), dk) ? 1 : 0);
@@ -580,12 +629,12 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         for (int o = 16; o > 0; o >>= 1) n_amb += __shfl_xor_sync(0xffffffffu, n_amb, o);
         if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
     }
-    named_bar_sync(bar_id, 64);
+    team_bar_sync<kMaxTeams>(team);
     // ---- pack: 8 consecutive symbols of `mod` bits = `mod` whole bytes, MSB first (modulation.cpp:90-125);
     //      warp h packs symbol (h ? B : A) ----
     {
         const int s = h ? B : A;
-        if (s >= 1 && s < nsym) {
+        if (s >= 1 && (h == 0 || hasB)) {
             const uint8_t *sb = h ? sbB : sbA;
             const uint2 raw = *reinterpret_cast<const uint2 *>(sb + 8 * lane);
             unsigned long long bits = 0;

@@ -36,6 +36,9 @@ void *emu_create(const char *config_path) {
 void emu_destroy(void *h) { delete (EmuHandle *)h; }
 int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
+static int g_emu_split = 0;
+void emu_set_split(int on) { g_emu_split = on; }
+
 int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride, int sync_less,
                     uint8_t *out, unsigned long long *amb, float *scal, float2 *grid, float2 *chan,
                     float2 *constell, float2 *synced) {
@@ -44,10 +47,19 @@ int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, in
     const Params P = h->P;
     RxTaps taps{scal, grid, chan, constell, synced};
     const int nsym = P.n_sym_rx;
-    auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym)), rx512_smem_bytes(nsym), kern); };
-    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
-    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
-    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+    std::vector<FrameScal> fs(n_frames);
+    auto run = [&](int md, auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym, md)), rx512_smem_bytes(nsym, md), kern); };
+#define EMU_RX(F, T, MD) run(MD, [&] { rx_fused512_kernel<F, T, 9, true, MD>(P, samples, stride, n_frames, out, amb, taps, sync_less, fs.data()); })
+#define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
+    if (g_emu_split && nsym <= 9) { EMU_RX_MODE(1); EMU_RX_MODE(2); }
+    else if (nsym <= 9) EMU_RX_MODE(0);
+    else {
+        if (fmt == kCI16) run(0, [&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+        else if (use_tma) run(0, [&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+        else run(0, [&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
+    }
+#undef EMU_RX_MODE
+#undef EMU_RX
     if (synced && scal && !sync_less) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup_kernel(P, n_frames, taps); });
     return 0;
 }
@@ -66,10 +78,13 @@ int emu_rx_fused512_notaps(void *hv, const void *samples, int fmt, int use_tma, 
     const Params P = h->P;
     RxTaps taps{};
     const int nsym = P.n_sym_rx;
-    auto run = [&](auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym)), rx512_smem_bytes(nsym), kern); };
-    if (fmt == kCI16) run([&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, false>(P, samples, stride, n_frames, out, amb, taps, 0); });
-    else if (use_tma) run([&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, false>(P, samples, stride, n_frames, out, amb, taps, 0); });
-    else run([&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, false>(P, samples, stride, n_frames, out, amb, taps, 0); });
+    std::vector<FrameScal> fs(n_frames);
+    auto run = [&](int md, auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym, md)), rx512_smem_bytes(nsym, md), kern); };
+#define EMU_RX(F, T, MD) run(MD, [&] { rx_fused512_kernel<F, T, 9, false, MD>(P, samples, stride, n_frames, out, amb, taps, 0, fs.data()); })
+#define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
+    if (g_emu_split) { EMU_RX_MODE(1); EMU_RX_MODE(2); } else EMU_RX_MODE(0);
+#undef EMU_RX_MODE
+#undef EMU_RX
     return 0;
 }
 

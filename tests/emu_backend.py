@@ -48,8 +48,13 @@ class EmuModem:
             setattr(s, n, getattr(o, n))
         s.rx_len = o.preamble_size + o.message_size
         self.use_tma = 1
+        L.emu_set_split.argtypes = [C.c_int]
         self.fused = bool(L.emu_fused_ok(self.h))
         s.fused_path = 1 if self.fused else 0
+
+    def set_split(self, on):
+        """1: acquire + demod kernels (the product default), 0: the single fused kernel"""
+        self.lib.emu_set_split(int(on))
 
     def close(self):
         if self.h:

@@ -7,9 +7,12 @@ import parity_checks as pc
 from emu_backend import EmuModem
 
 
-@pytest.fixture(scope="module")
-def emu(cfg_dir, port):
+@pytest.fixture(scope="module", params=[1, 0], ids=["split", "fused"])
+def emu(cfg_dir, port, request):
+    """every test runs on both forms of the receive chain: acquire + demod kernels (product default) and the
+    single fused kernel"""
     ms = {mt: EmuModem(cfg_dir[mt], port[mt].sizes) for mt in (1, 2, 4, 6, 8)}
+    ms[4].set_split(request.param)
     yield ms
     for m in ms.values():
         m.close()
