@@ -232,7 +232,7 @@ def native_arm(args):
     # Host-side samples use the SDR wire format (int16 I,Q: FRAME_FORM::get_int16 / from_sdr_int16_buf), which
     # is what the reference apps and the CPU arm move between modem and radio.  The tx pass (payload -> frames)
     # and the rx pass (frames -> payload) of a step are independent, so they run concurrently on two handles
-    # (two host threads, three streams each): PCIe is full duplex and tx is D2H-heavy, rx H2D-heavy.
+    # (two host threads, two streams each): PCIe is full duplex and tx is D2H-heavy, rx H2D-heavy.
     E = min(args.e2e_frames, F)
     m2 = cb.Modem(CONFIG, device=local)
     h_pay = torch.empty((E, s.usefull_size), dtype=torch.uint8).pin_memory()
@@ -286,12 +286,12 @@ def native_arm(args):
             "rx_frames_s": world * F / (rx_ms * 1e-3), "rx_ms": rx_ms, "tx_ms": tx_ms,
             "bit_errors": bit_err, "frames_with_errors": frames_bad, "frames_checked": frames_all,
             "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb,
-            "roofline": {"bound": "hbm", "kernel": "rx_fused512_kernel", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "rx pass = rx_acquire512x2_kernel + rx_fused512_kernel<demod> (together they read every sample exactly once)", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
                          "frac": rx_gbs / peak, "traffic": None, "peak_source": peak_src,
                          "algorithmic_bytes_per_frame": RX_BYTES_PER_FRAME, "tx_kernel_gbs": tx_gbs, "tx_frac": tx_gbs / peak},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_step": E, "ms_per_step": e_dt * 1e3, "payload_roundtrip_ok": e_ok, "host_sample_format": "ci16 (SDR wire format)",
-                    "path": "cofdm_tx_batch || cofdm_rx_aligned_batch, COFDM_HOST pinned buffers, two handles run concurrently (3-stream chunked H2D/kernel/D2H each)"},
+                    "path": "cofdm_tx_batch || cofdm_rx_aligned_batch, COFDM_HOST pinned buffers, two handles run concurrently (double-buffered chunked H2D/kernel/D2H each)"},
             "gpu_launches": launches, "wall_ms_per_step": t_wall / args.steps * 1e3, "clocks": clocks,
         }
         if not args.no_cpu and world == 1:

@@ -13,8 +13,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libcofdm_b200.so")
-SOURCES = [os.path.join(HERE, "csrc", f) for f in
-           ("cofdm_host.cu", "kernels.cuh", "fft.cuh", "modem.cuh", "compat.cuh", "params.h", "host_consts.hpp")]
+SOURCES = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc"))
+                 if f.endswith((".cu", ".cuh", ".h", ".hpp")))
 SOURCES.append(os.path.join(ROOT, "include", "cofdm.h"))
 
 

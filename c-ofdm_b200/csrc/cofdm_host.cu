@@ -1,6 +1,6 @@
 // cofdm_host.cu -- implementation of the C ABI in include/cofdm.h: handle management, host-side
 // constant tables (host_consts.hpp), kernel launches for sm_100a, and the COFDM_HOST staging path
-// (chunked H2D -> kernel -> D2H over three streams).  No CPU compute fallback exists: without a
+// (chunked H2D -> kernel -> D2H, double-buffered over two streams).  No CPU compute fallback exists: without a
 // usable CUDA device every computing entry point returns COFDM_ERR_CUDA.
 #include "../../include/cofdm.h"
 
@@ -30,7 +30,7 @@ int fail(int code, const std::string &msg) { g_err = msg; return code; }
             return fail(COFDM_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e_));      \
     } while (0)
 
-constexpr int kPipe = 3;   // streams / buffer sets of the COFDM_HOST pipeline
+constexpr int kPipe = 8;   // maximum streams / buffer sets of the COFDM_HOST pipeline (depth in use: cofdm::pipe_depth)
 
 struct DevBuf {
     void *p = nullptr;
@@ -61,6 +61,9 @@ struct cofdm {
     DevBuf gen_frames, gen_spec, gen_pre;        // generic path intermediates
     DevBuf fscal;                                // per-frame scalars handed from the acquire to the demod kernel
     int rx_split = 1;                            // 1: acquire + demod kernels, 0: single fused kernel
+    int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
+                                                 // 2 reaches the PCIe full-duplex ceiling, 3 and more lose 10-15 %
+    size_t pipe_chunk = 2048;                    // frames per chunk of the COFDM_HOST pipeline (env COFDM_PIPE_CHUNK)
     unsigned long long *amb_dev = nullptr;       // ambiguity counter
     unsigned long long *pos_dev = nullptr;       // find_t2sin result
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -134,7 +137,19 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
         else COFDM_RX_PICK(kCF32, false, MD);               \
     } while (0)
     if (split) {
-        COFDM_RX_MODE(1);                                   // acquire: preamble -> 48 bytes of scalars per frame
+        // acquire: preamble -> 48 bytes of scalars per frame; two frames per CTA unless every synchronisation stage is off
+        if (!sync_less) {
+            const unsigned g2 = (unsigned)((n_frames + 1) / 2);
+#define COFDM_ACQ(F, T) \
+            do { if (want) rx_acquire512x2_kernel<F, T, true><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); \
+                 else rx_acquire512x2_kernel<F, T, false><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); } while (0)
+            if (fmt == COFDM_CI16) COFDM_ACQ(kCI16, false);
+            else if (tma) COFDM_ACQ(kCF32, true);
+            else COFDM_ACQ(kCF32, false);
+#undef COFDM_ACQ
+        } else {
+            COFDM_RX_MODE(1);
+        }
         if (int rc = check_launch(h, "rx512_acquire")) return rc;
         COFDM_RX_MODE(2);                                   // demod: message symbols -> payload bytes
     } else {
@@ -317,6 +332,10 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         {
             const char *e = std::getenv("COFDM_RX_SPLIT");
             if (e) h->rx_split = std::atoi(e) != 0;
+            const char *c = std::getenv("COFDM_PIPE_CHUNK");
+            if (c && std::atoll(c) > 0) h->pipe_chunk = (size_t)std::atoll(c);
+            const char *d = std::getenv("COFDM_PIPE_DEPTH");
+            if (d && std::atoi(d) > 0) h->pipe_depth = std::min(std::atoi(d), kPipe);
         }
         // maximum shared-memory carve-out: occupancy of every mode is bounded by shared memory, not by L1
 #define COFDM_RX_ATTR(F, T, S, W, MD) \
@@ -330,6 +349,11 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         COFDM_RX_ATTR_ALL(kCI16, false);
 #undef COFDM_RX_ATTR_ALL
 #undef COFDM_RX_ATTR
+#define COFDM_ACQ_ATTR(F, T, W) \
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512x2_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+        COFDM_ACQ_ATTR(kCF32, true, true); COFDM_ACQ_ATTR(kCF32, true, false); COFDM_ACQ_ATTR(kCF32, false, true);
+        COFDM_ACQ_ATTR(kCF32, false, false); COFDM_ACQ_ATTR(kCI16, false, true); COFDM_ACQ_ATTR(kCI16, false, false);
+#undef COFDM_ACQ_ATTR
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)
@@ -472,12 +496,12 @@ int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *fr
         return launch_tx(h, h->stream, payload, n_frames, frames, fmt);
     }
     const size_t bpf = (size_t)h->P.bytes_per_frame, fb = (size_t)h->P.frame_len * sample_bytes(fmt);
-    const size_t chunk = std::min<size_t>(n_frames, 2048);
-    for (int i = 0; i < kPipe; i++) { CU_TRY(h->pipe_in[i].reserve(chunk * bpf)); CU_TRY(h->pipe_out[i].reserve(chunk * fb)); }
+    const size_t chunk = std::min<size_t>(n_frames, h->pipe_chunk);
+    for (int i = 0; i < h->pipe_depth; i++) { CU_TRY(h->pipe_in[i].reserve(chunk * bpf)); CU_TRY(h->pipe_out[i].reserve(chunk * fb)); }
     size_t c = 0;
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
         const size_t n = std::min(chunk, n_frames - f0);
-        const int s = (int)(c % kPipe);
+        const int s = (int)(c % h->pipe_depth);
         cudaStream_t st = h->pipe_stream[s];
         CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, payload + f0 * bpf, n * bpf, cudaMemcpyHostToDevice, st));
         if (int rc = launch_tx(h, st, (const uint8_t *)h->pipe_in[s].p, n, h->pipe_out[s].p, fmt)) return rc;
@@ -532,9 +556,9 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
     }
     // ---- COFDM_HOST: chunked pipeline; with taps a single chunk and extra device buffers ----------
     const size_t sb = sample_bytes(fmt), bpf = (size_t)P.bytes_per_frame;
-    const size_t chunk = want_taps ? n_frames : std::min<size_t>(n_frames, 2048);
+    const size_t chunk = want_taps ? n_frames : std::min<size_t>(n_frames, h->pipe_chunk);
     if (n_frames == 0) return COFDM_OK;
-    for (int i = 0; i < (want_taps ? 1 : kPipe); i++) {
+    for (int i = 0; i < (want_taps ? 1 : h->pipe_depth); i++) {
         CU_TRY(h->pipe_in[i].reserve(chunk * frame_stride * sb));
         CU_TRY(h->pipe_out[i].reserve(chunk * bpf));
     }
@@ -557,7 +581,7 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
     size_t c = 0;
     for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
         const size_t n = std::min(chunk, n_frames - f0);
-        const int s = (int)(c % kPipe);
+        const int s = (int)(c % h->pipe_depth);
         cudaStream_t st = h->pipe_stream[s];
         // the last record only needs rx_len samples (the caller's buffer may end there)
         const size_t in_bytes = ((n - 1) * frame_stride + (size_t)P.rx_len) * sb;

@@ -157,6 +157,39 @@ template <bool INV> COFDM_DEV void dft10(float2 *v) {
     }
 }
 
+// packed (two problems per instruction) 5- and 10-point butterflies
+template <bool INV> COFDM_DEV void dft5(pc *v) {
+    const float2 c1 = p_bcast(0.30901699437494742410f), c2 = p_bcast(-0.80901699437494742410f);
+    const float2 s1 = p_bcast(0.95105651629515357212f), s2 = p_bcast(0.58778525229247312917f);
+    const pc t1 = cadd(v[1], v[4]), t2 = cadd(v[2], v[3]);
+    const pc t3 = csub(v[1], v[4]), t4 = csub(v[2], v[3]);
+    pc x0 = cadd(v[0], cadd(t1, t2)), m1, m2, q1, q2;
+    m1.re = p_fma(c2, t2.re, p_fma(c1, t1.re, v[0].re)); m1.im = p_fma(c2, t2.im, p_fma(c1, t1.im, v[0].im));
+    m2.re = p_fma(c1, t2.re, p_fma(c2, t1.re, v[0].re)); m2.im = p_fma(c1, t2.im, p_fma(c2, t1.im, v[0].im));
+    q1.re = p_fma(s2, t4.re, p_mul(s1, t3.re));          q1.im = p_fma(s2, t4.im, p_mul(s1, t3.im));
+    q2.re = p_fms(s2, t3.re, p_mul(s1, t4.re));          q2.im = p_fms(s2, t3.im, p_mul(s1, t4.im));
+    const pc jq1 = mul_w4<INV>(q1), jq2 = mul_w4<INV>(q2);
+    v[0] = x0;
+    v[1] = cadd(m1, jq1);
+    v[4] = csub(m1, jq1);
+    v[2] = cadd(m2, jq2);
+    v[3] = csub(m2, jq2);
+}
+template <bool INV> COFDM_DEV void dft10(pc *v) {
+    pc e[5] = {v[0], v[2], v[4], v[6], v[8]}, o[5] = {v[1], v[3], v[5], v[7], v[9]};
+    dft5<INV>(e);
+    dft5<INV>(o);
+    o[1] = cmul(o[1], twid<INV>(make_float2(0.80901699437494742410f, -0.58778525229247312917f)));
+    o[2] = cmul(o[2], twid<INV>(make_float2(0.30901699437494742410f, -0.95105651629515357212f)));
+    o[3] = cmul(o[3], twid<INV>(make_float2(-0.30901699437494742410f, -0.95105651629515357212f)));
+    o[4] = cmul(o[4], twid<INV>(make_float2(-0.80901699437494742410f, -0.58778525229247312917f)));
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        v[k] = cadd(e[k], o[k]);
+        v[k + 5] = csub(e[k], o[k]);
+    }
+}
+
 template <int R, bool INV> COFDM_DEV void dftR(float2 *v) {
     if (R == 2) dft2<INV>(v);
     else if (R == 4) dft4<INV>(v);

@@ -18,6 +18,7 @@
 #include "fft.cuh"
 #include "modem.cuh"
 #include "rx512.cuh"
+#include "rx512_acquire.cuh"
 #include "generic.cuh"
 
 namespace cofdmk {
