@@ -74,6 +74,7 @@ def load_library():
     lib.cofdm_preamble_search.argtypes = [vp, vp, ci, sz, vp, sz, vp, vp, ci]
     lib.cofdm_i16_to_cf32.argtypes = [vp, vp, vp, sz, ci]
     lib.cofdm_rx_stream.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz)]
+    lib.cofdm_rx_stream_sharded.argtypes = [vp, vp, sz, C.c_int, C.c_int, sz, vp, vp, C.POINTER(sz), C.POINTER(sz)]
     lib.cofdm_enable_timing.argtypes = [vp, ci]
     lib.cofdm_last_kernel_ms.argtypes = [vp]
     lib.cofdm_last_kernel_ms.restype = C.c_float
@@ -312,18 +313,27 @@ class Modem:
                                                  _space(samples, starts, first)))
         return (first, cor) if want_cor else first
 
-    def rx_stream(self, capture_i16, max_frames=None):
-        """rx.cpp's acquisition loop over a host int16 capture [N, 2] -> (preamble positions, payload bytes)"""
+    def rx_stream(self, capture_i16, max_frames=None, shards=1, want_bytes=True, return_unmerged=False):
+        """rx.cpp's acquisition loop over an int16 capture [N, 2] (numpy = host, torch cuda tensor = device)
+        -> (preamble positions, payload bytes).  shards > 1: the capture is cut into that many ranges of whole
+        SDR blocks, each scanned by its own CTA, the chains merged (cofdm_rx_stream_sharded)."""
         s = self.sizes
-        cap = np.ascontiguousarray(capture_i16, dtype=np.int16).reshape(-1)
-        n = cap.size // 2
+        if isinstance(capture_i16, np.ndarray):
+            cap = np.ascontiguousarray(capture_i16, dtype=np.int16).reshape(-1)
+            n, space, ptr = cap.size // 2, HOST, cap.ctypes.data
+        else:
+            self._follow(capture_i16)
+            cap = capture_i16.contiguous()
+            n, space, ptr = cap.numel() // 2, DEVICE, cap.data_ptr()
         if max_frames is None:
             max_frames = n // (s.ofdm_len * s.num_symb) + 2
         pos = np.zeros(max_frames, dtype=np.int64)
-        out = np.zeros((max_frames, s.usefull_size), dtype=np.uint8)
-        k = C.c_size_t(0)
-        self._chk(self.lib.cofdm_rx_stream(self.h, cap.ctypes.data, n, max_frames, pos.ctypes.data, out.ctypes.data, C.byref(k)))
-        return pos[:k.value].copy(), out[:k.value].copy()
+        out = np.zeros((max_frames if want_bytes else 0, s.usefull_size), dtype=np.uint8)
+        k, um = C.c_size_t(0), C.c_size_t(0)
+        self._chk(self.lib.cofdm_rx_stream_sharded(self.h, ptr, n, space, int(shards), max_frames, pos.ctypes.data,
+                                                   out.ctypes.data if want_bytes else None, C.byref(k), C.byref(um)))
+        res = (pos[:k.value].copy(), out[:k.value].copy() if want_bytes else None)
+        return res + (um.value,) if return_unmerged else res
 
     def i16_to_cf32(self, samples):
         self._follow(samples)

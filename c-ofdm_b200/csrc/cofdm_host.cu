@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "stream.cuh"
 #include "host_consts.hpp"
 
 using namespace cofdmk;
@@ -369,6 +370,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         cudaFuncSetAttribute(gen_tx_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_t);
         cudaFuncSetAttribute(gen_tx_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_t);
     }
+    cudaFuncSetAttribute(stream_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_scan_smem_bytes(P.cor_size, P.pr_sin_len));
     {
         const int smp = (int)((size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2));
         if (smp > 48 * 1024) {
@@ -676,13 +678,11 @@ int cofdm_preamble_search(cofdm_t *h, const void *samples, int fmt, size_t n_sam
     return COFDM_OK;
 }
 
-int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t max_frames,
-                    long long *pr_begin_abs, uint8_t *bytes, size_t *n_found) {
-    if (!h || !capture || !n_found) return fail(COFDM_ERR_ARG, "cofdm_rx_stream: bad argument");
-    *n_found = 0;
-    if (set_device(h)) return COFDM_ERR_CUDA;
+// The host-sequenced form of the loop (one search launch + one 8-byte read-back per step).  Kept for
+// configurations the device scanner does not cover and as an independent cross-check (env COFDM_STREAM_HOSTSEQ=1).
+static int rx_stream_hostseq(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t max_frames,
+                             long long *pr_begin_abs, uint8_t *bytes, size_t *n_found) {
     const Params &P = h->P;
-    if (!h->T.fused512_ok || P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "rx_stream: configuration not built yet");
     const long long out_sz = P.frame_len, block = out_sz * h->T.rx_buf_size;   // SDR::rx_buf_size, sdr.hpp:141
     const long long ring = out_sz * (h->T.rx_buf_size + 1);                     // from_sdr_buf.size(), Frame.cpp:221
     const long long n_blocks = block > 0 ? (long long)n_samples / block : 0;
@@ -787,6 +787,132 @@ int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t
     if (int rc = flush()) return rc;
     *n_found = found;
     return COFDM_OK;
+}
+
+// merge of per-shard chains (same rule as c-ofdm_b200/stream.py::merge_shards): follow the earlier shard's chain
+// (the true one) until it meets a preamble position the later shard also found, then switch to the later shard's list;
+// a frame is owned by the shard whose block range contains its preamble.
+static void merge_stream_shards(const std::vector<std::vector<long long>> &lists, const std::vector<long long> &own_end,
+                                std::vector<long long> &out, size_t *unmerged) {
+    std::vector<long long> carry;
+    *unmerged = 0;
+    for (size_t r = 0; r < lists.size(); r++) {
+        const std::vector<long long> &pos = lists[r];
+        size_t start = 0;
+        if (!carry.empty()) {
+            size_t k = carry.size(), j = 0;
+            for (size_t a = 0; a < carry.size() && k == carry.size(); a++) {
+                auto it = std::lower_bound(pos.begin(), pos.end(), carry[a]);
+                if (it != pos.end() && *it == carry[a]) { k = a; j = (size_t)(it - pos.begin()); }
+            }
+            if (k < carry.size()) {
+                out.insert(out.end(), carry.begin(), carry.begin() + (long)k);
+                start = j;
+            } else {
+                (*unmerged)++;
+                out.insert(out.end(), carry.begin(), carry.end());
+                start = (size_t)(std::upper_bound(pos.begin(), pos.end(), carry.back()) - pos.begin());
+            }
+        }
+        size_t n_own = start;
+        for (size_t a = start; a < pos.size(); a++) if (pos[a] < own_end[r]) n_own = a + 1;
+        out.insert(out.end(), pos.begin() + (long)start, pos.begin() + (long)n_own);
+        carry.assign(pos.begin() + (long)n_own, pos.end());
+    }
+    out.insert(out.end(), carry.begin(), carry.end());
+}
+
+int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples, int space, int n_shards, size_t max_frames,
+                            long long *pr_begin_abs, uint8_t *bytes, size_t *n_found, size_t *n_unmerged) {
+    if (!h || !capture || !n_found || n_shards < 1 || (space != COFDM_HOST && space != COFDM_DEVICE))
+        return fail(COFDM_ERR_ARG, "cofdm_rx_stream_sharded: bad argument");
+    *n_found = 0;
+    if (n_unmerged) *n_unmerged = 0;
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    const Params &P = h->P;
+    if (!h->T.fused512_ok || P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "rx_stream: configuration not built yet");
+    const bool scanner_ok = (P.pr_sin_len % 4) == 0 && (P.cor_size % 4) == 0 && h->T.rx_buf_size >= 1;
+    static const bool force_hostseq = [] { const char *e = std::getenv("COFDM_STREAM_HOSTSEQ"); return e && std::atoi(e) != 0; }();
+    if ((!scanner_ok || force_hostseq) && space == COFDM_HOST && n_shards == 1)
+        return rx_stream_hostseq(h, capture, n_samples, max_frames, pr_begin_abs, bytes, n_found);
+    if (!scanner_ok) return fail(COFDM_ERR_UNSUPPORTED, "rx_stream: the device scanner needs pr_sin_len and the lag count to be multiples of 4");
+    const long long out_sz = P.frame_len, block = out_sz * h->T.rx_buf_size;
+    const long long total_blocks = (long long)n_samples / block;
+    if (total_blocks == 0 || max_frames == 0) return COFDM_OK;
+    cudaStream_t st = h->stream;
+    const unsigned *d_cap = reinterpret_cast<const unsigned *>(capture);
+    if (space == COFDM_HOST) {
+        CU_TRY(h->scratch_a.reserve((size_t)total_blocks * block * 4));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, capture, (size_t)total_blocks * block * 4, cudaMemcpyHostToDevice, st));
+        d_cap = reinterpret_cast<const unsigned *>(h->scratch_a.p);
+    }
+    const long long ns = std::min<long long>(n_shards, total_blocks);
+    std::vector<StreamShard> shards((size_t)ns);
+    std::vector<long long> own_end((size_t)ns);
+    const long long msg = (long long)P.ofdm_len * P.num_symb;
+    long long max_per = 0;
+    for (long long r = 0; r < ns; r++) {                       // cofdm_b200.dist.shard_range + one overlap block
+        const long long base = total_blocks / ns, rem = total_blocks % ns;
+        const long long b0 = r * base + std::min(r, rem), b1 = b0 + base + (r < rem ? 1 : 0);
+        const long long b1x = std::min(total_blocks, b1 + (b1 < total_blocks ? 1 : 0));
+        shards[(size_t)r] = StreamShard{b0 * block, b1x - b0};
+        own_end[(size_t)r] = b1 * block;
+        max_per = std::max(max_per, (b1x - b0) * block / msg + 2);
+    }
+    if (ns == 1) max_per = std::min<long long>(max_per, (long long)max_frames);
+    const size_t list_bytes = (size_t)ns * (size_t)max_per * sizeof(long long);
+    CU_TRY(h->scratch_b.reserve(list_bytes + (size_t)ns * sizeof(int) + (size_t)ns * sizeof(StreamShard) + 64));
+    long long *d_pos = (long long *)h->scratch_b.p;
+    StreamShard *d_sh = (StreamShard *)((char *)h->scratch_b.p + list_bytes);
+    int *d_cnt = (int *)(d_sh + ns);
+    CU_TRY(cudaMemcpyAsync(d_sh, shards.data(), (size_t)ns * sizeof(StreamShard), cudaMemcpyHostToDevice, st));
+    {
+        Timed t(h);
+        stream_scan_kernel<<<(unsigned)ns, kScanThreads, stream_scan_smem_bytes(P.cor_size, P.pr_sin_len), st>>>(
+            P, d_cap, d_sh, (int)ns, h->T.rx_buf_size, (long long)h->T.iterations, d_pos, (int)max_per, d_cnt);
+        if (int rc = check_launch(h, "stream_scan")) return rc;
+    }
+    std::vector<int> cnt((size_t)ns);
+    CU_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<std::vector<long long>> lists((size_t)ns);
+    for (long long r = 0; r < ns; r++) {
+        lists[(size_t)r].resize((size_t)cnt[(size_t)r]);
+        if (cnt[(size_t)r])
+            CU_TRY(cudaMemcpyAsync(lists[(size_t)r].data(), d_pos + (size_t)r * (size_t)max_per, (size_t)cnt[(size_t)r] * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    }
+    CU_TRY(cudaStreamSynchronize(st));
+    std::vector<long long> merged;
+    size_t unmerged = 0;
+    merge_stream_shards(lists, own_end, merged, &unmerged);
+    if (merged.size() > max_frames) merged.resize(max_frames);
+    if (n_unmerged) *n_unmerged = unmerged;
+    const size_t found = merged.size();
+    if (pr_begin_abs) std::copy(merged.begin(), merged.end(), pr_begin_abs);
+    if (bytes && found) {
+        // gather the frames found and demodulate them in batches
+        const size_t batch_cap = 8192;
+        CU_TRY(h->scratch_c.reserve(found * sizeof(long long)));
+        CU_TRY(cudaMemcpyAsync(h->scratch_c.p, merged.data(), found * sizeof(long long), cudaMemcpyHostToDevice, st));
+        CU_TRY(h->pipe_in[0].reserve(std::min(found, batch_cap) * (size_t)P.rx_len * 4));
+        CU_TRY(h->pipe_out[0].reserve(std::min(found, batch_cap) * (size_t)P.bytes_per_frame));
+        RxTaps none{};
+        for (size_t f0 = 0; f0 < found; f0 += batch_cap) {
+            const size_t n = std::min(batch_cap, found - f0);
+            stream_gather_kernel<<<(unsigned)n, 256, 0, st>>>(d_cap, total_blocks * block, (const long long *)h->scratch_c.p + f0, (int)n, P.rx_len, (unsigned *)h->pipe_in[0].p);
+            if (int rc = check_launch(h, "stream_gather")) return rc;
+            if (int rc = launch_rx(h, st, h->pipe_in[0].p, COFDM_CI16, n, (size_t)P.rx_len, (uint8_t *)h->pipe_out[0].p, nullptr, none)) return rc;
+            CU_TRY(cudaMemcpyAsync(bytes + f0 * (size_t)P.bytes_per_frame, h->pipe_out[0].p, n * (size_t)P.bytes_per_frame, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+        }
+    }
+    *n_found = found;
+    return COFDM_OK;
+}
+
+int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t max_frames,
+                    long long *pr_begin_abs, uint8_t *bytes, size_t *n_found) {
+    return cofdm_rx_stream_sharded(h, capture, n_samples, COFDM_HOST, 1, max_frames, pr_begin_abs, bytes, n_found, nullptr);
 }
 
 int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n, int space) {

@@ -122,34 +122,9 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
     }
 }
 
-// ------------------------------------------------------------------------------------------------
-// t2sin_metric_kernel: T2SIN_FORM::corr / find_t2sin block metric (Frame.hpp:112-143).
-// One warp per non-overlapping 256-sample block: FFT-256 (8x8x4 Stockham in the warp's private
-// shared memory), rel = sum(mask*|X|^2) / sum(|X|^2); blocks with zero or NaN energy report 0.
-// ------------------------------------------------------------------------------------------------
-constexpr int kT2WarpsPerCta = 8;
-template <int FMT>
-__global__ void __launch_bounds__(32 * kT2WarpsPerCta)
-t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
-                    float *__restrict__ rel_out) {
-    __shared__ float2 buf[kT2WarpsPerCta][2][256];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const long long blk = (long long)blockIdx.x * kT2WarpsPerCta + warp;
-    if (blk >= n_blocks) return;
-    float2 *A = buf[warp][0], *B = buf[warp][1];
-    const long long s0 = start + blk * 256;
-    if (FMT == kCI16) {
-        const unsigned *src = reinterpret_cast<const unsigned *>(samples) + s0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) {
-            const unsigned w = __ldg(src + lane + 32 * i);
-            A[lane + 32 * i] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
-        }
-    } else {
-        const float2 *src = reinterpret_cast<const float2 *>(samples) + s0;
-#pragma unroll
-        for (int i = 0; i < 8; i++) A[lane + 32 * i] = __ldg(src + lane + 32 * i);
-    }
+// rel = sum(mask*|X|^2) / sum(|X|^2) of the 256 samples a warp has staged in A (B = scratch); every lane returns it.
+// Blocks with zero or NaN energy report 0 (Frame.hpp:132-138 `continue`).
+COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane) {
     // total spectral energy by Parseval: sum_k |X_k|^2 = 256 * sum_n |x_n|^2 (saves evaluating unmasked bins)
     float tot = 0.f;
 #pragma unroll
@@ -184,11 +159,41 @@ t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long 
     }
     tot = warp_sum(tot);
     sine = warp_sum(sine);
-    if (lane == 0) {
-        float rel = sine / tot;
-        if (tot == 0.f || rel != rel) rel = 0.f;          // Frame.hpp:132-138 `continue`
-        rel_out[blk] = rel;
+    float rel = sine / tot;
+    if (tot == 0.f || rel != rel) rel = 0.f;
+    return rel;
+}
+
+// ------------------------------------------------------------------------------------------------
+// t2sin_metric_kernel: T2SIN_FORM::corr / find_t2sin block metric (Frame.hpp:112-143).
+// One warp per non-overlapping 256-sample block: FFT-256 (8x8x4 Stockham in the warp's private
+// shared memory), rel = sum(mask*|X|^2) / sum(|X|^2); blocks with zero or NaN energy report 0.
+// ------------------------------------------------------------------------------------------------
+constexpr int kT2WarpsPerCta = 8;
+template <int FMT>
+__global__ void __launch_bounds__(32 * kT2WarpsPerCta)
+t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
+                    float *__restrict__ rel_out) {
+    __shared__ float2 buf[kT2WarpsPerCta][2][256];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long blk = (long long)blockIdx.x * kT2WarpsPerCta + warp;
+    if (blk >= n_blocks) return;
+    float2 *A = buf[warp][0], *B = buf[warp][1];
+    const long long s0 = start + blk * 256;
+    if (FMT == kCI16) {
+        const unsigned *src = reinterpret_cast<const unsigned *>(samples) + s0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const unsigned w = __ldg(src + lane + 32 * i);
+            A[lane + 32 * i] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+        }
+    } else {
+        const float2 *src = reinterpret_cast<const float2 *>(samples) + s0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) A[lane + 32 * i] = __ldg(src + lane + 32 * i);
     }
+    const float rel = t2sin_block_rel(P, A, B, lane);
+    if (lane == 0) rel_out[blk] = rel;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -148,11 +148,22 @@ int cofdm_preamble_search(cofdm_t *h, const void *samples, int fmt, size_t n_sam
  * pointer; interleaved I,Q) that stands in for consecutive SDR::recv blocks of output_size*rx_buf_size
  * samples: ring of rx_buf_size+1 frames with carry-over (rx.cpp:116,147-156,180-189), find_t2sin -> find_preamble
  * (+1) -> copy rx_len samples -> pos += message.size, sentinels -1 / -10 handled as rx.cpp:137-178 does, at
- * most `iterations` (config) loop turns.  The state machine runs on the host, every search and the
- * demodulation of the frames found run on the GPU (demodulation batched).  pr_begin_abs[i] = absolute sample
+ * most `iterations` (config) loop turns.  The state machine runs on the device (one CTA, stream.cuh), the frames
+ * found are gathered and demodulated in one batch.  pr_begin_abs[i] = absolute sample
  * index of frame i's preamble in the capture; bytes[i*usefull_size ...]; *n_found = number of frames. */
 int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t max_frames,
                     long long *pr_begin_abs, uint8_t *bytes, size_t *n_found);
+
+/* The same loop over a capture cut into `n_shards` contiguous ranges of whole SDR blocks (+ one overlap block each),
+ * every range scanned by its own CTA running the state machine of rx.cpp:126-198 on the device (stream.cuh), the
+ * per-range chains merged on the host: the earlier range's chain is followed until it meets a preamble position the
+ * later range also found (two chains coincide from the first frame both detect); a frame belongs to the range
+ * that contains its preamble.  n_shards = 1 is exactly cofdm_rx_stream.  `capture` is a host pointer (COFDM_HOST,
+ * uploaded once) or a device pointer (COFDM_DEVICE); pr_begin_abs / bytes / counters are host memory.
+ * *n_unmerged = boundaries whose chains did not meet inside the overlap (0 in practice). */
+int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples, int space, int n_shards,
+                            size_t max_frames, long long *pr_begin_abs, uint8_t *bytes, size_t *n_found,
+                            size_t *n_unmerged);
 
 /* FRAME_FORM::form_int16_to_double  OFDM/Frame.hpp:472-481 (fp32 on the device) */
 int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n_samples, int space);

@@ -51,19 +51,40 @@ def main():
     flop = nw * s.cor_size * s.pr_sin_len * 8
     out["preamble_search_ci16"] = {"windows": nw, "ms": ms, "windows_s": nw / ms * 1e3, "gb_s": nw * (s.cor_size + s.pr_sin_len) * 4 / ms / 1e6,
                                    "tflop_s": flop / ms / 1e9}
-    # streaming receiver: synthetic capture, frames every ~1.2 frame lengths
-    nfr = 4000
+    # streaming receiver (cofdm_rx_stream / cofdm_rx_stream_sharded): synthetic capture, frames every ~1.2 frame lengths
+    nfr, reps = 4000, 8
     pay = synth.payloads(nfr, s.usefull_size, seed=5)
     fr = m.tx_batch(pay, cb.CI16)
     rng = np.random.default_rng(3)
     cap, _ = synth.capture(fr[..., 0].astype(np.float64) + 1j * fr[..., 1], gaps=rng.integers(300, 2500, nfr), noise_sigma=3.0, seed=4, tail=s.output_size * 41)
+    blk = s.output_size * s.rx_buf_size
+    cap = cap[: cap.shape[0] // blk * blk]
     t0 = time.perf_counter()
     pos, by = m.rx_stream(cap)
     dt = time.perf_counter() - t0
     ok = int(sum(np.array_equal(b, p) for b, p in zip(by, pay[: len(by)])))
-    out["rx_stream"] = {"capture_samples": int(cap.shape[0]), "frames_found": int(len(pos)), "frames_sent": nfr, "payload_ok": ok, "seconds": dt,
-                        "frames_s": len(pos) / dt, "msamples_s": cap.shape[0] / dt / 1e6,
-                        "note": "host-sequenced state machine, two small launches + one 8-byte D2H per frame; latency bound"}
+    out["rx_stream_host_capture_1shard"] = {"capture_samples": int(cap.shape[0]), "frames_found": int(len(pos)), "frames_sent": nfr, "payload_ok": ok,
+                                            "seconds": dt, "frames_s": len(pos) / dt, "msamples_s": cap.shape[0] / dt / 1e6,
+                                            "note": "device-side state machine (one CTA), capture uploaded from pageable host memory inside the timed region"}
+    big = torch.from_numpy(cap).cuda().repeat(reps, 1)            # the same capture back to back: reps*nfr frames
+    m.enable_timing(True)
+    rows = []
+    for shards in (1, 8, 74, 148, 296, 592, 1184):
+        m.rx_stream(big, shards=shards)                           # warm-up (buffers)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        pos, by, unmerged = m.rx_stream(big, shards=shards, return_unmerged=True)
+        dt = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        pos2, _ = m.rx_stream(big, shards=shards, want_bytes=False)
+        dt_scan = time.perf_counter() - t0
+        scan_ms = m.last_kernel_ms()
+        ok = int((by == np.tile(pay[: len(by) // reps + 1], (reps, 1))[: len(by)]).all(axis=1).sum()) if len(by) == reps * nfr else -1
+        rows.append({"shards": shards, "frames_found": int(len(pos)), "payload_ok": ok, "unmerged": int(unmerged), "seconds_scan_plus_demod": dt,
+                     "frames_s": len(pos) / dt, "msamples_s": big.shape[0] / dt / 1e6, "seconds_scan_only_wall": dt_scan, "scan_kernel_ms": scan_ms,
+                     "scan_kernel_msamples_s": big.shape[0] / scan_ms / 1e3 if scan_ms else None})
+    out["rx_stream_device_capture"] = {"capture_samples": int(big.shape[0]), "frames_sent": reps * nfr, "by_shards": rows,
+                                       "note": "int16 capture resident in HBM; wall clock of the whole call (scan kernel, list merge on the host, gather + rx kernels, D2H of the bytes)"}
     print(json.dumps(out))
 
 

@@ -4,6 +4,7 @@
 #define COFDM_EMU 1
 #include "cuda_emu.h"
 #include "kernels.cuh"
+#include "stream.cuh"
 #include "host_consts.hpp"
 
 using namespace cofdmk;
@@ -128,6 +129,21 @@ int emu_preamble_corr(void *hv, const void *samples, int fmt, long long n_sample
     const size_t sm = (size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2);
     if (fmt == kCI16) emu::launch(dim3(n_starts), dim3(kPcThreads), sm, [&] { preamble_corr_kernel<kCI16>(P, samples, n_samples, starts, n_starts, cor, first); });
     else emu::launch(dim3(n_starts), dim3(kPcThreads), sm, [&] { preamble_corr_kernel<kCF32>(P, samples, n_samples, starts, n_starts, cor, first); });
+    return 0;
+}
+
+// the device-side acquisition loop (stream.cuh): per-shard lists of absolute preamble positions
+int emu_stream_scan(void *hv, const void *capture_i16, const long long *shard_first, const long long *shard_blocks, int n_shards,
+                    long long *pos_out, int max_per_shard, int *count_out) {
+    auto *h = (EmuHandle *)hv;
+    const Params P = h->P;
+    if (P.t2sin_size != 256 || (P.pr_sin_len % 4) || (P.cor_size % 4)) return -1;
+    std::vector<StreamShard> sh(n_shards);
+    for (int i = 0; i < n_shards; i++) sh[i] = StreamShard{shard_first[i], shard_blocks[i]};
+    emu::launch(dim3(n_shards), dim3(kScanThreads), stream_scan_smem_bytes(P.cor_size, P.pr_sin_len), [&] {
+        stream_scan_kernel(P, (const unsigned *)capture_i16, sh.data(), n_shards, h->T.rx_buf_size, (long long)h->T.iterations,
+                           pos_out, max_per_shard, count_out);
+    });
     return 0;
 }
 

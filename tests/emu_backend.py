@@ -44,11 +44,13 @@ class EmuModem:
         o = oracle_sizes
         s = self.sizes = EmuSizes()
         for n in ("fft_size", "num_data_subc", "num_pilot_subc", "cp_size", "num_symb", "num_pr_symb", "pr_sin_len",
-                  "t2sin_size", "mod_type", "ofdm_len", "output_size", "usefull_size", "constell_size", "cor_size"):
+                  "t2sin_size", "mod_type", "ofdm_len", "output_size", "usefull_size", "constell_size", "cor_size",
+                  "rx_buf_size", "iterations"):
             setattr(s, n, getattr(o, n))
         s.rx_len = o.preamble_size + o.message_size
         self.use_tma = 1
         L.emu_set_split.argtypes = [C.c_int]
+        L.emu_stream_scan.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]
         self.fused = bool(L.emu_fused_ok(self.h))
         s.fused_path = 1 if self.fused else 0
 
@@ -153,3 +155,16 @@ class EmuModem:
         assert self.lib.emu_preamble_corr(self.h, samples.ctypes.data, fmt, n, starts.ctypes.data, len(starts),
                                           cor.ctypes.data if want_cor else None, first.ctypes.data) == 0
         return (first, cor) if want_cor else first
+
+    def stream_scan(self, capture_i16, shards):
+        """device-side acquisition loop; shards = [(first_sample, n_blocks), ...] -> list of position arrays"""
+        cap = np.ascontiguousarray(capture_i16, dtype=np.int16)
+        first = np.array([a for a, _ in shards], dtype=np.int64)
+        nblk = np.array([b for _, b in shards], dtype=np.int64)
+        s = self.sizes
+        max_per = int(max(nblk) * s.output_size * s.rx_buf_size // (s.ofdm_len * s.num_symb) + 2)
+        pos = np.zeros((len(shards), max_per), dtype=np.int64)
+        cnt = np.zeros(len(shards), dtype=np.int32)
+        assert self.lib.emu_stream_scan(self.h, cap.ctypes.data, first.ctypes.data, nblk.ctypes.data, len(shards),
+                                        pos.ctypes.data, max_per, cnt.ctypes.data) == 0
+        return [pos[i, :cnt[i]].copy() for i in range(len(shards))]

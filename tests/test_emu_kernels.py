@@ -121,3 +121,32 @@ def test_production_instantiation_matches_tapped_one(emu, port):
         b, amb = emu[mt].rx_aligned_batch(rec)
         c, _ = emu[mt].rx_aligned_batch(rec, count_ambiguous=False)
         assert np.array_equal(a, b) and np.array_equal(a, c) and amb == amb_t
+
+
+def test_stream_scan_kernel_matches_reference_loop(cfg_dir, oracle_lib):
+    """stream.cuh: rx.cpp's acquisition state machine run by one CTA per shard, against the oracle's loop;
+    one shard = the sequential loop, two shards merge to the same list."""
+    from cofdm_b200 import stream as st
+    o = oracle_lib.Oracle("port", cfg_dir["stream"])
+    s = o.sizes
+    m = EmuModem(cfg_dir["stream"], s)
+    pay = pc.synth.payloads(12, s.usefull_size, seed=3)
+    tx16 = np.stack([o.tx(p)[1] for p in pay]).reshape(12, -1, 2)
+    rng = np.random.default_rng(11)
+    fr = pc.synth.channel(tx16, seed=4, cfo=rng.uniform(-0.003, 0.003, 12), phase=rng.uniform(0, 1, 12), noise_sigma=1.0)
+    cap, _ = pc.synth.capture(fr, gaps=rng.integers(260, 9000, 12), noise_sigma=3.0, seed=5, tail=s.output_size * 12)
+    want_pos, _ = o.rx_stream(cap)
+    assert len(want_pos) >= 9
+    blk = st.block_samples(s)
+    n_blocks = cap.shape[0] // blk
+    assert n_blocks >= 2
+    (got,) = m.stream_scan(cap, [(0, n_blocks)])
+    assert got.tolist() == want_pos.tolist()
+    shards = []
+    for r in range(2):
+        s0, s1, b0, b1 = st.shard_slice(cap.shape[0], s, r, 2)
+        shards.append((s0, (s1 - s0) // blk, b0, b1))
+    lists = m.stream_scan(cap, [(a, n) for a, n, _, _ in shards])
+    dummy = [np.zeros((len(l), s.usefull_size), np.uint8) for l in lists]
+    pos, _, unmerged = st.merge_shards([(l, d, b0, b1) for l, d, (_, _, b0, b1) in zip(lists, dummy, shards)], s)
+    assert unmerged == 0 and pos.tolist() == want_pos.tolist()

@@ -217,6 +217,13 @@ def test_rx_stream_matches_reference_loop(cfg_dir, oracle_lib, golden_vectors, g
     pos, by = m.rx_stream(cap)
     assert len(want_pos) >= 30
     assert pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
+    # the same capture cut into 2 and 3 shards (one CTA each), host or device resident: same list, same bytes
+    for shards in (2, 3):
+        pos, by, unmerged = m.rx_stream(cap, shards=shards, return_unmerged=True)
+        assert unmerged == 0 and pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
+    import torch
+    pos, by = m.rx_stream(torch.from_numpy(cap).cuda(), shards=2)
+    assert pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
     m.close()
 
 
