@@ -128,6 +128,7 @@ class Modem:
     def __init__(self, config_path, device=0):
         self.lib = load_library()
         h = C.c_void_p()
+        self.config_path = str(config_path)
         rc = self.lib.cofdm_create(os.fsencode(config_path), int(device), C.byref(h))
         if rc != 0:
             raise CofdmError(f"cofdm_create failed ({rc}): {self.lib.cofdm_last_error().decode()}")

@@ -316,3 +316,46 @@ def test_stream_sharded_over_ranks_on_gpu(cfg_dir, oracle_lib):
     pos, by, unmerged = stream.rx_stream_sharded(lambda c: m.rx_stream(c), cap, s, 3)
     assert unmerged == 0 and pos.tolist() == want_pos.tolist() and np.array_equal(by, want_by)
     m.close()
+
+
+def test_apps_main_dump_matches_reference_artefacts(cfg_dir, golden_capture, tmp_path):
+    """apps.main_dump = the receive half of main.cpp on the reference's recorded SDR block: the dump files are in
+    io.hpp's formats and hold the reference's own numbers (its data/*.bin, committed as the golden capture)."""
+    from cofdm_b200 import apps
+    g = golden_capture
+    m = cb.Modem(cfg_dir[1], device=0)
+    r = apps.main_dump(m, g["capture_i16"], tmp_path, tx_int16=g["source_i16"].reshape(-1, 2))
+    assert (r["t2_sin_begin"], r["pr_begin"], r["shift"]) == (10752, 11040, -0.0037109375)
+    assert np.array_equal(r["frame_bytes"], g["mac_frame"]) and r["checksum_ok"]
+    raw = np.fromfile(tmp_path / "data" / "data.bin", dtype=np.float64)                # ofdm.py's reader
+    assert np.array_equal(raw[::2] + 1j * raw[1::2], pc.cplx(g["capture_i16"]))
+    corr = np.fromfile(tmp_path / "data" / "t2_sin_corr.bin", dtype=np.float64)
+    assert corr.shape == g["t2_sin_corr"].shape and np.array_equal(corr > 0, g["t2_sin_corr"] > 0)
+    assert np.abs(corr - g["t2_sin_corr"]).max() < 1e-6
+    ph = apps.read_complex(tmp_path / "data" / "phases.bin")
+    co = apps.read_complex(tmp_path / "data" / "constell.bin")
+    assert pc.rel_l2(ph, g["phases"]) < 1e-5 and pc.rel_l2(co, g["constell"]) < 1e-5
+    assert np.array_equal(np.fromfile(tmp_path / "data" / "source.bin", dtype=np.int16), g["source_i16"])
+    assert np.array_equal(np.fromfile(tmp_path / "data.txt", dtype=np.uint8), g["data_txt"])
+    m.close()
+
+
+def test_apps_tx_file_rx_file_round_trip(cfg_dir, tmp_path):
+    """tx.cpp / rx.cpp with the radio replaced by a capture file: a text file goes through MAC framing, the
+    modulator, an int16 capture with idle gaps and noise, the stream receiver and MAC parsing, and comes back whole;
+    the trace is in LOG.txt's format."""
+    from cofdm_b200 import apps
+    m = cb.Modem(cfg_dir["stream"], device=0)
+    s = m.sizes
+    text = pc.synth.text_payload(60 * (s.usefull_size - 8) + 123)
+    src = tmp_path / "WARANDPEACE.txt"
+    np.asarray(text, dtype=np.uint8).tofile(src)
+    n = apps.tx_file(m, src, tmp_path / "rx.bin", gap=911, noise_sigma=2.0, seed=1)
+    assert n == 61
+    for shards in (1, 3):
+        r = apps.rx_file(m, tmp_path / "rx.bin", tmp_path / "data.txt", log_path=tmp_path / "LOG.txt", shards=shards,
+                         n_bytes=len(text))
+        assert r["frames"] == 61 and r["bad_checksums"] == 0 and r["seq"].tolist() == list(range(61))
+        assert np.array_equal(np.fromfile(tmp_path / "data.txt", dtype=np.uint8), np.asarray(text, dtype=np.uint8))
+        assert sum(1 for _ in open(tmp_path / "LOG.txt")) == 61
+    m.close()
