@@ -1,12 +1,12 @@
 // fft.cuh -- hand-written FFT building blocks (no cuFFT).
 //
 //  * dft2/4/5/8/16: in-register butterflies, forward (W = e^{-j2pi/R}) or inverse (conjugate).
-//  * warp_fft512<INV>: one warp computes one 512-point FFT as radix 8x8x8.  Each lane owns two
-//    radix-8 butterflies per pass; the two exchanges go through a 640-slot float2 shared-memory
-//    region private to the warp, with padded layouts chosen so every 64-bit access of a warp is
-//    bank-conflict free (see the address maps below).  Only __syncwarp() is needed between passes.
+//  * team_fft512p<INV>: a team of two warps computes TWO 512-point FFTs at once (packed f32x2, one in each half
+//    of every register pair) as radix 8x8x8.  Each lane owns one radix-8 butterfly per pass; the two exchanges
+//    go through two 640-slot float2 planes in shared memory with layouts chosen so that every 64-bit access
+//    of a warp is bank-conflict free (see the address maps below); the two warps meet at a named barrier.
 //  * stockham_pass<R>: generic mixed-radix autosort pass over a thread group, used for the
-//    640-point (5x8x16) coarse-CFO spectrum, the 256-point sync-tone detector and the generic path.
+//    640-point (10x8x8) coarse-CFO spectrum, the 256-point sync-tone detector and the generic path.
 //
 // These replace the reference's FFTW plans F1-F5 (OFDM/Frame.cpp:16-24,108-112,147-150;
 // OFDM/Frame.hpp:289-295).  All transforms are unnormalised like FFTW's.
@@ -223,7 +223,7 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
 }
 
 // ------------------------------------------------------------------------------------------------
-// warp_fft512
+// FFT-512 as radix 8x8x8 over a team of two warps
 //
 // Index algebra: n = 64*n1 + 8*n2 + n3, k = k1 + 8*k2 + 64*k3 (all digits 0..7)
 //   pass 1  A [k1;n2,n3] = sum_n1 x[n]          W8^{n1 k1}   then * W512^{(8 n2+n3) k1}
@@ -236,147 +236,15 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
 // Exchange layouts (float2 slots inside the warp's 640-slot region):
 //   E1(k1,n2,n3) = n3 + 8*n2 + 72*k1      writer: fixed k1 -> q + 8p   reader: fixed n2 -> q + 72p
 //   E2(k1,k2,n3) = n3 + 9*k2 + 72*k1      writer: fixed k2 -> q + 72p  reader: fixed n3 -> 9q + 72p
-//   spectrum slot(k) = k + (k >> 2)       writer: fixed k3 -> p + 10q (+const)
+//   spectrum slot(k) = k ^ (((k >> 3) & 7) << 1)   writer: fixed k3 -> (p + 8q) ^ 2q (+64 k3); readers of 16 consecutive,
+//                                                  16-aligned bins (64- or 128-bit accesses) are conflict-free as well
 // each of which maps the 32 lanes of a 64-bit access onto the 16 bank pairs exactly twice.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFft512Slots = 640;
-COFDM_DEV int spec_slot(int k) { return k + (k >> 2); }
-
-// Passes 2 and 3 + the two exchanges.  On entry v[h][k1] holds the twiddled pass-1 outputs A' of the
-// lane's two butterflies.  On exit the spectrum is in `work` at spec_slot(k) and visible to the warp.
-// The caller must guarantee that no lane still needs the previous contents of `work`.
-template <bool INV>
-COFDM_DEV void warp_fft512_tail(float2 (&v)[2][8], float2 *work, const float2 *tw_p2, int lane) {
-    const int q = lane & 7, p0 = lane >> 3;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = p0 + 4 * h;
-#pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) work[q + 8 * p + 72 * k1] = v[h][k1];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = p0 + 4 * h;
-#pragma unroll
-        for (int n2 = 0; n2 < 8; n2++) v[h][n2] = work[q + 8 * n2 + 72 * p];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) dft8<INV>(v[h]);
-#pragma unroll
-    for (int k2 = 1; k2 < 8; k2++) {
-        const float2 w = twid<INV>(__ldg(&tw_p2[k2 * 8 + q]));   // same for both halves
-        v[0][k2] = cmul(v[0][k2], w);
-        v[1][k2] = cmul(v[1][k2], w);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = p0 + 4 * h;
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) work[q + 9 * k2 + 72 * p] = v[h][k2];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = p0 + 4 * h;
-#pragma unroll
-        for (int n3 = 0; n3 < 8; n3++) v[h][n3] = work[n3 + 9 * q + 72 * p];
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int p = p0 + 4 * h;
-        dft8<INV>(v[h]);
-        const int k0 = p + 8 * q;
-        const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
-#pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) work[s0 + 80 * k3] = v[h][k3];
-    }
-    __syncwarp();
-}
-
-// Pass 1 on data already in registers: v[h][n1] = x[l + 32h + 64*n1].
-template <bool INV>
-COFDM_DEV void warp_fft512_head(float2 (&v)[2][8], const float2 *tw_p1, int lane) {
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        dft8<INV>(v[h]);
-        const int t = lane + 32 * h;
-#pragma unroll
-        for (int k1 = 1; k1 < 8; k1++) v[h][k1] = cmul(v[h][k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
-    }
-}
+COFDM_DEV int spec_slot(int k) { return k ^ (((k >> 3) & 7) << 1); }
 
 // ------------------------------------------------------------------------------------------------
-// warp_fft512p: the same 8x8x8 transform on TWO symbols at once.  Every register holds a packed pair
-// (symbol A, symbol B) so each FADD2/FMUL2/FFMA2 advances both transforms; twiddles are shared.
-// Exchanges use the layouts E1/E2/spec_slot above on two planes of packed pairs inside the warp's
-// 1280-slot region: re-plane Wre[slot] = (re_A, re_B), im-plane Wim[slot] = (im_A, im_B).
-// ------------------------------------------------------------------------------------------------
-template <bool INV>
-COFDM_DEV void warp_fft512p_head(pc (&v)[2][8], const float2 *tw_p1, int lane) {
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        dft8<INV>(v[h]);
-        const int t = lane + 32 * h;
-#pragma unroll
-        for (int k1 = 1; k1 < 8; k1++) v[h][k1] = cmul(v[h][k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
-    }
-}
-
-template <bool INV>
-COFDM_DEV void warp_fft512p_tail(pc (&v)[2][8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane) {
-    const int q = lane & 7, p0 = lane >> 3;
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int b = q + 8 * (p0 + 4 * h);
-#pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[h][k1].re; Wim[b + 72 * k1] = v[h][k1].im; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int b = q + 72 * (p0 + 4 * h);
-#pragma unroll
-        for (int n2 = 0; n2 < 8; n2++) { v[h][n2].re = Wre[b + 8 * n2]; v[h][n2].im = Wim[b + 8 * n2]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) dft8<INV>(v[h]);
-#pragma unroll
-    for (int k2 = 1; k2 < 8; k2++) {
-        const float2 w = twid<INV>(__ldg(&tw_p2[k2 * 8 + q]));
-        v[0][k2] = cmul(v[0][k2], w);
-        v[1][k2] = cmul(v[1][k2], w);
-    }
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int b = q + 72 * (p0 + 4 * h);
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) { Wre[b + 9 * k2] = v[h][k2].re; Wim[b + 9 * k2] = v[h][k2].im; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        const int b = 9 * q + 72 * (p0 + 4 * h);
-#pragma unroll
-        for (int n3 = 0; n3 < 8; n3++) { v[h][n3].re = Wre[b + n3]; v[h][n3].im = Wim[b + n3]; }
-    }
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; h++) {
-        dft8<INV>(v[h]);
-        const int k0 = (p0 + 4 * h) + 8 * q;
-        const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
-#pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) { Wre[s0 + 80 * k3] = v[h][k3].re; Wim[s0 + 80 * k3] = v[h][k3].im; }
-    }
-    __syncwarp();
-}
-
-// ------------------------------------------------------------------------------------------------
-// team_fft512p: as warp_fft512p, but the 64 butterflies of a pass are spread over a TEAM of two warps
+// team_fft512p: two packed transforms at once; the 64 butterflies of a pass are spread over a TEAM of two warps
 // (warp h owns butterflies 32h..32h+31, one per lane), which halves the registers and the dependent
 // chain per warp.  The exchanges are shared by the team, so each is fenced by the team's named barrier.
 // ------------------------------------------------------------------------------------------------
@@ -424,11 +292,11 @@ COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const flo
     dft8<INV>(v);
     {
         const int k0 = p + 8 * q;
-        const int s0 = k0 + (k0 >> 2);              // spec_slot(k0 + 64*k3) = s0 + 80*k3
+        const int s0 = k0 ^ (q << 1);               // spec_slot(k0 + 64*k3) = s0 + 64*k3
 #pragma unroll
         for (int k3 = 0; k3 < 8; k3++) {
             if (PRUNE && (k3 == 3 || k3 == 4)) continue;
-            Wre[s0 + 80 * k3] = v[k3].re; Wim[s0 + 80 * k3] = v[k3].im;
+            Wre[s0 + 64 * k3] = v[k3].re; Wim[s0 + 64 * k3] = v[k3].im;
         }
     }
     team_bar_sync<MAXT>(team);

@@ -110,9 +110,11 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
 #pragma unroll
     for (int it = 0; it < 4; it++) {
         const int n = 256 * h + 2 * lane + 64 * it;
-        const float2 r0 = Wre[spec_slot(n)], i0 = Wim[spec_slot(n)], r1 = Wre[spec_slot(n + 1)], i1 = Wim[spec_slot(n + 1)];
-        const float2 a0 = make_float2(r0.x * sc, i0.x * sc), a1 = make_float2(r1.x * sc, i1.x * sc);
-        const float2 b0 = make_float2(r0.y * sc, i0.y * sc), b1 = make_float2(r1.y * sc, i1.y * sc);
+        // spec_slot(n + 1) = spec_slot(n) + 1 for even n: samples n, n+1 of both symbols in one 128-bit load per plane
+        const float4 rr = *reinterpret_cast<const float4 *>(&Wre[spec_slot(n)]);   // (reA[n], reB[n], reA[n+1], reB[n+1])
+        const float4 ii = *reinterpret_cast<const float4 *>(&Wim[spec_slot(n)]);
+        const float2 a0 = make_float2(rr.x * sc, ii.x * sc), a1 = make_float2(rr.z * sc, ii.z * sc);
+        const float2 b0 = make_float2(rr.y * sc, ii.y * sc), b1 = make_float2(rr.w * sc, ii.w * sc);
         store_sample_pair<FMT>(fout, baseA + 128 + n, a0, a1, P.mult);
         if (n >= 384) store_sample_pair<FMT>(fout, baseA + n - 384, a0, a1, P.mult);
         if (hasB) {
