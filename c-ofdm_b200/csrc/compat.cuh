@@ -109,6 +109,30 @@ COFDM_DEV float2 fast_cis_turns(float t) {
     return make_float2(cr, sr);
 }
 COFDM_DEV float2 cis_neg_turns_f(float turns) { return fast_cis_turns(-turns); }
+// the same for two angles at once (packed f32x2 polynomial evaluation): result .re = (cos a, cos b), .im = (sin a, sin b)
+COFDM_DEV pc fast_cis_turns2(float ta, float tb) {
+    const float ka = rintf(4.0f * ta), kb = rintf(4.0f * tb);
+    const float2 f = p_fma(make_float2(ka, kb), p_bcast(-0.25f), make_float2(ta, tb));
+    const float2 u = p_mul(f, f);
+    float2 sp = p_fma(u, p_bcast(4.1414680329e+01f), p_bcast(-7.6695821688e+01f));
+    sp = p_fma(u, sp, p_bcast(8.1605180747e+01f));
+    sp = p_fma(u, sp, p_bcast(-4.1341702049e+01f));
+    sp = p_fma(u, sp, p_bcast(6.2831853070e+00f));
+    const float2 s = p_mul(f, sp);
+    float2 c = p_fma(u, p_bcast(5.9220407194e+01f), p_bcast(-8.5442852118e+01f));
+    c = p_fma(u, c, p_bcast(6.4939316208e+01f));
+    c = p_fma(u, c, p_bcast(-1.9739208650e+01f));
+    c = p_fma(u, c, p_bcast(9.9999999995e-01f));
+    const int qa = (int)ka, qb = (int)kb;
+    pc r;
+    float cra = (qa & 1) ? -s.x : c.x, sra = (qa & 1) ? c.x : s.x;
+    float crb = (qb & 1) ? -s.y : c.y, srb = (qb & 1) ? c.y : s.y;
+    if (qa & 2) { cra = -cra; sra = -sra; }
+    if (qb & 2) { crb = -crb; srb = -srb; }
+    r.re = make_float2(cra, crb);
+    r.im = make_float2(sra, srb);
+    return r;
+}
 
 // atan2(y, x) / (2*pi) in (-0.5, 0.5]: one fast division + a degree-17 odd minimax polynomial on [0,1]
 // (fp32 evaluation error 2.3e-8 turns = 1.4e-7 rad, the level of atan2f itself)

@@ -22,12 +22,13 @@ COFDM_DEV int extract_bits(const uint8_t *bytes, int n_bytes, int bitpos, int mo
 constexpr float kAmbigMargin = 2e-4f;
 
 // per-modulation constants, computed once per thread
-struct DemapK { int mod, qshift; float half; };
+struct DemapK { int mod, qshift, lmax; float half; };
 COFDM_DEV DemapK make_demapk(int mod) {
     DemapK k;
     k.mod = mod;
     k.qshift = mod >> 1;                                   // lq * L == lq << (mod/2)
-    k.half = 0.5f * (float)((1 << (mod >> 1)) - 1);        // str_size_1 = 1/step = (L-1)/2
+    k.lmax = (1 << (mod >> 1)) - 1;                        // L - 1
+    k.half = 0.5f * (float)k.lmax;                         // str_size_1 = 1/step = (L-1)/2
     return k;
 }
 
@@ -54,9 +55,11 @@ COFDM_DEV int demap_point(float2 z, int mod, bool &amb) { return demap_point(z, 
 // the decision alone / the ambiguity test alone (the fused kernel only pays for the latter when asked to count)
 COFDM_DEV int demap_fast(float2 z, const DemapK &k) {
     if (k.mod == 1) return z.x + z.y > 0.0f ? 1 : 0;
-    const float re = fminf(fmaxf(z.x, -1.0f), 1.0f), im = fminf(fmaxf(z.y, -1.0f), 1.0f);
-    const int li = (int)fmaf(re + 1.0f, k.half, 0.5f), lq = (int)fmaf(im + 1.0f, k.half, 0.5f);
-    return (li | (lq << k.qshift)) & 0xff;
+    // clamp to [-1,1], (v + 1) half + 0.5, truncate (modulation.cpp:60-75) == truncate v half + (half + 0.5) with the
+    // level clamped to [0, 2 half] afterwards: one fma, one conversion and an integer clamp per component
+    const int li = min(max(__float2int_rz(fmaf(z.x, k.half, k.half + 0.5f)), 0), k.lmax);
+    const int lq = min(max(__float2int_rz(fmaf(z.y, k.half, k.half + 0.5f)), 0), k.lmax);
+    return li | (lq << k.qshift);
 }
 COFDM_DEV bool demap_ambiguous(float2 z, const DemapK &k) {
     bool amb;

@@ -38,6 +38,19 @@ constexpr int kRxMaxPair = kRxMaxSym / 2;
 constexpr int kCoarseWarps = 2;
 constexpr int kPairSlots = 2 * kFft512Slots;   // float2 slots of one symbol pair
 
+// The chain runs either as ONE kernel per frame (MODE 0) or as TWO kernels that together still read every
+// sample exactly once (MODE 1 + MODE 2):
+//   MODE 1 "acquire": the preamble only -- coarse CFO, its FFT, theta, the channel line -> 48 bytes per frame
+//   MODE 2 "demod":   the message symbols only -- CP correlation, rotation, FFT, pilots, equalise, demap
+// The split removes the two in-CTA waits of the fused form (message warps idling until the coarse estimate
+// and the channel fit of the preamble are done) and lets 4 demod CTAs (instead of 3 fused ones) share an SM.
+struct FrameScal {
+    int kc, m0;             // coarse shift numerator; whole-bin shift of the preamble
+    float th0, theta;       // Arg of the preamble's CP correlation (turns); pr_phase_sinh angle (radians)
+    float2 rot_theta;       // exp(-j theta)
+    double a, b;            // chan_char_lq line
+};
+
 struct RxMisc {
     uint64_t mbar[kRxMaxSym + 1];
     float4 qtab[kRxMaxSym][8];       // per FFT warp: Q^r (r<8) -- (reA, reB, imA, imB)
@@ -57,19 +70,10 @@ struct RxMisc {
     float ph[128];                   // raw phases arg(pr[i]/mod_preamble[i])
     float sypart[4], sxypart[4];
     int jumppart[4];
-};
-
-// The chain runs either as ONE kernel per frame (MODE 0) or as TWO kernels that together still read every
-// sample exactly once (MODE 1 + MODE 2):
-//   MODE 1 "acquire": the preamble only -- coarse CFO, its FFT, theta, the channel line -> 48 bytes per frame
-//   MODE 2 "demod":   the message symbols only -- CP correlation, rotation, FFT, pilots, equalise, demap
-// The split removes the two in-CTA waits of the fused form (message warps idling until the coarse estimate
-// and the channel fit of the preamble are done) and lets 4 demod CTAs (instead of 3 fused ones) share an SM.
-struct FrameScal {
-    int kc, m0;             // coarse shift numerator; whole-bin shift of the preamble
-    float th0, theta;       // Arg of the preamble's CP correlation (turns); pr_phase_sinh angle (radians)
-    float2 rot_theta;       // exp(-j theta)
-    double a, b;            // chan_char_lq line
+    // MODE 2: frame-wide factors computed once per CTA (by warp 1) instead of once per warp
+    FrameScal fsc;                   // the acquire kernel's hand-over
+    float2 ltab[32];                 // exp(-j b lane)
+    float2 rot1ee[8];                // rot_1 * exp(-j(b 32 e' + a)) per segment (rot_1 = constant phase of message symbol 0)
 };
 
 COFDM_HD int rx512_npair(int nsym) { return (nsym + 1) / 2; }
@@ -207,6 +211,14 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         }
     }
 
+    if (MODE == 2 && warp == 1) {
+        // while the bulk copies are in flight: the acquire kernel's scalars and the factors every warp would
+        // otherwise recompute -- exp(-j b lane) and exp(-j(b 32 e' + a))
+        const FrameScal f = fscal[frame];          // written by the acquire kernel (same stream, earlier launch)
+        if (lane == 0) M->fsc = f;
+        M->ltab[lane] = cis_neg_turns_f((float)(f.b * (double)lane) * inv2pi);
+        if (lane < 8) M->rot1ee[lane] = cis_neg_turns_f((float)((f.b * (double)(32 * (lane < 4 ? lane : lane - 8)) + f.a) * 0.15915494309189533577));
+    }
     const int team = warp >> 1, h = warp & 1;      // FFT warps: team = symbol pair, h = which half of the butterflies
     const int lA = 2 * team, lB = 2 * team + 1;   // local symbol indices (buffers, mbarriers)
     const bool hasB = lB < nsym;
@@ -323,16 +335,14 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             }
         }
         __syncwarp();
-        const pc Pt = make_pc(cis_neg_turns_f(nuA * (float)(128 + t)), cis_neg_turns_f(nuB * (float)(128 + t)));
-        // rotate in registers: v[r] = x[128 + t + 64 r] * exp(-j 2pi nu (128 + t + 64 r))
+        const pc Pt = fast_cis_turns2(-nuA * (float)(128 + t), -nuB * (float)(128 + t));
+        // rotate in registers: v[r] = x[128 + t + 64 r] * exp(-j 2pi nu (128 + t + 64 r)), both symbols per instruction
         pc v[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
             const float4 qr = qt[r];
             pc Qr; Qr.re = make_float2(qr.x, qr.y); Qr.im = make_float2(qr.z, qr.w);
-            const pc w = cmul(Pt, Qr);
-            v[r].re = make_float2(ra[r].x * w.re.x - ra[r].y * w.im.x, rb[r].x * w.re.y - rb[r].y * w.im.y);
-            v[r].im = make_float2(ra[r].x * w.im.x + ra[r].y * w.re.x, rb[r].x * w.im.y + rb[r].y * w.re.y);
+            v[r] = cmul(make_pc(ra[r], rb[r]), cmul(Pt, Qr));
         }
         if (TAPS || A == 0) {
             // CP samples j = t and j = t + 64: exp(-j 2pi nu j) = P(t) conj(Q^2) resp. P(t) conj(Q^1)
@@ -366,21 +376,27 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     }
     __syncthreads();                               // #2: spectra (shifted by the unknown m_s) and kc are ready
 
-    FrameScal fs{};
-    if (MODE == 2) {
-        fs = fscal[frame];                         // written by the acquire kernel (same stream, earlier launch)
-        if (tid == 0) {                            // symbol 0's entries, for the constant phase of message symbol 0
-            M->theta_t[0] = fs.th0; M->mshift[0] = fs.m0;
-            M->a = fs.a; M->b = fs.b; M->rot_theta = fs.rot_theta; M->theta = fs.theta;
-        }
+    if (MODE == 2 && tid == 0) {                   // symbol 0's entries, for the constant phase of message symbol 0
+        const FrameScal fs = M->fsc;
+        M->theta_t[0] = fs.th0; M->mshift[0] = fs.m0;
+        M->a = fs.a; M->b = fs.b; M->rot_theta = fs.rot_theta; M->theta = fs.theta;
     }
-    const int kc = MODE == 2 ? fs.kc : M->kc;
+    const int kc = MODE == 2 ? M->fsc.kc : M->kc;
     int mA = 0, mB = 0;
     if (!is_coarse) {
         // m_s and the reference's phi_s (Frame.hpp:254): phi_t = theta_t - 512 shift + m_s in (-0.5, 0.5]
         const float sh512 = (float)kc * (512.0f / (float)P.pf_den);
         mA = (int)ceilf(-(thA - sh512) - 0.5f);
         mB = (int)ceilf(-(thB - sh512) - 0.5f);
+        if (MODE == 2 && warp == 1 && lane < 8) {
+            // constant phase of message symbol 0 (team 0's symbol A; its pilots are the reference of every segment):
+            // Psi_1 = sym_turns(.., 1) = 1.25 (theta_0 + m_0) mod 1
+            float acc = M->fsc.th0 * (640.0f / 512.0f);
+            acc -= rintf(acc);
+            const float psi1 = acc + (float)((5 * M->fsc.m0) & 3) * 0.25f;
+            const float2 rot1 = cmul(mul_negj_pow(cis_neg_turns_f(psi1), mA), M->fsc.rot_theta);
+            M->rot1ee[lane] = cmul(rot1, M->rot1ee[lane]);
+        }
         if (h == 0) {
             if (lane == 0) { M->mshift[A] = mA; if (hasB) M->mshift[B] = mB; }
             // pilot bins of both symbols
@@ -581,18 +597,23 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     //   factor folded into the coefficient and a per-lane factor exp(-j b lane).
     float4 *wt = M->wtab[warp];
     if (lane < 8) {
-        // constant phase of message symbol 0 (its pilots are the reference of every segment)
-        const float psi1 = sym_turns(M->theta_t, M->mshift, 1);
-        const float2 rot1 = cmul(mul_negj_pow(cis_neg_turns_f(psi1), M->mshift[1]), rot_theta);
-        const float2 p1 = cmul(M->pilots[1][lane], rot1);
-        const int ep = lane < 4 ? lane : lane - 8;
-        const float2 ee = cis_neg_turns_f((float)((lb * (double)(32 * ep) + la) * 0.15915494309189533577));
+        float2 p1e;                                // P[1,p] * rot_1 * exp(-j(b 32 e' + a))
+        if (MODE == 2) {
+            p1e = cmul(M->pilots[1][lane], M->rot1ee[lane]);
+        } else {
+            // constant phase of message symbol 0 (its pilots are the reference of every segment)
+            const float psi1 = sym_turns(M->theta_t, M->mshift, 1);
+            const float2 rot1 = cmul(mul_negj_pow(cis_neg_turns_f(psi1), M->mshift[1]), rot_theta);
+            const int ep = lane < 4 ? lane : lane - 8;
+            const float2 ee = cis_neg_turns_f((float)((lb * (double)(32 * ep) + la) * 0.15915494309189533577));
+            p1e = cmul(cmul(M->pilots[1][lane], rot1), ee);
+        }
         const float2 psa = M->pilots[A][lane], psb = M->pilots[hasB ? B : A][lane];
-        const float2 wa = cmul(cscale(cmulc(p1, psa), 1.0f / (cnorm2(psa) * g)), ee);
-        const float2 wb = cmul(cscale(cmulc(p1, psb), 1.0f / (cnorm2(psb) * g)), ee);
+        const float2 wa = cscale(cmulc(p1e, psa), 1.0f / (cnorm2(psa) * g));
+        const float2 wb = cscale(cmulc(p1e, psb), 1.0f / (cnorm2(psb) * g));
         wt[lane] = make_float4(wa.x, wb.x, wa.y, wb.y);
     }
-    const float2 Ll = cis_neg_turns_f((float)(lb * (double)lane) * inv2pi);
+    const float2 Ll = MODE == 2 ? M->ltab[lane] : cis_neg_turns_f((float)(lb * (double)lane) * inv2pi);
     __syncwarp();
 
     // ---- equalise + hard demap (modulation.cpp:53-87); warp h handles segments 4h..4h+3 of both symbols;
