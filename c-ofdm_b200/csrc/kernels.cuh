@@ -48,6 +48,23 @@ COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/,
     }
 }
 
+// the 8 frequency-domain points (bins t + 64 r) of symbols A and B that one lane feeds to the first IFFT pass:
+// null, pilot, or the constellation point of MOD payload bits (Frame.cpp:55-62 + modulation.cpp:39-50)
+template <int MOD>
+COFDM_DEV void tx512_grid_points(const Params &P, const uint8_t *pl, int A, int B, bool hasB, int t, pc (&v)[8]) {
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+        const int m = __ldg(&P.bin_map[t + 64 * r]);
+        float2 va = make_float2(0.f, 0.f), vb = va;                                  // Frame.cpp:55
+        if (m == -2) va = vb = make_float2(P.pilot_ampl, 0.f);                        // Frame.cpp:56-57
+        else if (m >= 0) {
+            va = __ldg(&P.constell[extract_bits_t<MOD>(pl, P.bytes_per_frame, (A * P.num_data_subc + m) * MOD)]);
+            if (hasB) vb = __ldg(&P.constell[extract_bits_t<MOD>(pl, P.bytes_per_frame, (B * P.num_data_subc + m) * MOD)]);
+        }
+        v[r] = make_pc(va, vb);
+    }
+}
+
 // One CTA per frame.  The last warp copies the frame-invariant sync tone + preamble; the other warps form
 // teams of two per PAIR of OFDM symbols (packed f32x2 arithmetic, symbol A in the low half, B in the high
 // half, exactly as in the rx kernel): map bits, insert pilots, IFFT-512, /sqrt(512), prepend CP.
@@ -89,16 +106,12 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
     float2 *Wre = W + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
     const int mod = P.mod_type, t = lane + 32 * h;
     pc v[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int m = __ldg(&P.bin_map[t + 64 * r]);
-        float2 va = make_float2(0.f, 0.f), vb = va;                                  // Frame.cpp:55
-        if (m == -2) va = vb = make_float2(P.pilot_ampl, 0.f);                        // Frame.cpp:56-57
-        else if (m >= 0) {                                                           // Frame.cpp:59-62 + modulation.cpp:39-50
-            va = __ldg(&P.constell[extract_bits(pl, P.bytes_per_frame, (A * P.num_data_subc + m) * mod, mod)]);
-            if (hasB) vb = __ldg(&P.constell[extract_bits(pl, P.bytes_per_frame, (B * P.num_data_subc + m) * mod, mod)]);
-        }
-        v[r] = make_pc(va, vb);
+    switch (mod) {                                  // uniform: the symbol width becomes a compile-time constant
+        case 1: tx512_grid_points<1>(P, pl, A, B, hasB, t, v); break;
+        case 2: tx512_grid_points<2>(P, pl, A, B, hasB, t, v); break;
+        case 4: tx512_grid_points<4>(P, pl, A, B, hasB, t, v); break;
+        case 6: tx512_grid_points<6>(P, pl, A, B, hasB, t, v); break;
+        default: tx512_grid_points<8>(P, pl, A, B, hasB, t, v); break;
     }
     team_fft512p_head<true>(v, P.tw_p1, t);                                          // Frame.cpp:64 (backward, unnormalised)
     team_fft512p_tail<true, kMaxTeams>(v, Wre, Wim, P.tw_p2, lane, h, team);

@@ -17,6 +17,16 @@ COFDM_DEV int extract_bits(const uint8_t *bytes, int n_bytes, int bitpos, int mo
     return (int)((w >> (16 - mod - off)) & ((1u << mod) - 1u));
 }
 
+// the same with the symbol width known at compile time (shifts and masks fold to constants)
+template <int MOD>
+COFDM_DEV int extract_bits_t(const uint8_t *bytes, int n_bytes, int bitpos) {
+    const int b0 = bitpos >> 3, off = bitpos & 7;
+    unsigned w = 0;
+    if (b0 < n_bytes) w = (unsigned)bytes[b0] << 8;
+    if ((8 % MOD) != 0 && b0 + 1 < n_bytes) w |= (unsigned)bytes[b0 + 1];
+    return (int)((w >> (16 - MOD - off)) & ((1u << MOD) - 1u));
+}
+
 // margin (in level units) inside which a hard decision is reported as boundary-ambiguous: an fp32
 // pipeline and the reference's fp64 pipeline may legitimately land on different sides.
 constexpr float kAmbigMargin = 2e-4f;
