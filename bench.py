@@ -302,9 +302,13 @@ def native_arm(args):
             cf = args.cpu_frames or 10000 * cores
             cpu_run(max(cores, cf // 8), cores)
             dt, kind, n_done, errs, cs = cpu_run(cf, cores)
+            dt1, _, n1, errs1, _ = cpu_run(2000, 1)                       # (i) one thread, (ii) every core
             line["cpu_baseline"] = {"value": 2 * n_done * cs.output_size / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
                                     "sample": f"{n_done} frames tx+rx on {cores} threads in {dt:.1f} s; FFT = stand-in mixed-radix (FFTW3 not installed)",
-                                    "payload_bytes_wrong": errs}
+                                    "payload_bytes_wrong": errs + errs1,
+                                    "one_thread": {"value": 2 * n1 * cs.output_size / dt1 / 1e6, "unit": "Msamples/s",
+                                                   "us_per_frame_tx_plus_rx": dt1 / n1 * 1e6, "sample": f"{n1} frames on 1 thread in {dt1:.1f} s"},
+                                    "reference_authors_own_figure": "LOG.txt: 238 us per received frame with FFTW3 on the author's CPU (rx only)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

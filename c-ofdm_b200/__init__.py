@@ -122,6 +122,20 @@ def _n_samples(x, fmt):
     return n
 
 
+def _host_buffer(shape):
+    """uint8 host array for results; page-locked (through torch's caching host allocator) when torch is there,
+    so that the device-to-host copy of large results runs at PCIe speed"""
+    n = int(np.prod(shape))
+    if n >= (1 << 20):
+        try:
+            import torch
+            if torch.cuda.is_available():
+                return torch.empty(shape, dtype=torch.uint8, pin_memory=True).numpy()
+        except Exception:
+            pass
+    return np.zeros(shape, dtype=np.uint8)
+
+
 class Modem:
     """One FRAME_FORM-equivalent handle: owns the config, the device tables and a stream."""
 
@@ -329,11 +343,11 @@ class Modem:
         if max_frames is None:
             max_frames = n // (s.ofdm_len * s.num_symb) + 2
         pos = np.zeros(max_frames, dtype=np.int64)
-        out = np.zeros((max_frames if want_bytes else 0, s.usefull_size), dtype=np.uint8)
+        out = _host_buffer((max_frames if want_bytes else 0, s.usefull_size))
         k, um = C.c_size_t(0), C.c_size_t(0)
         self._chk(self.lib.cofdm_rx_stream_sharded(self.h, ptr, n, space, int(shards), max_frames, pos.ctypes.data,
                                                    out.ctypes.data if want_bytes else None, C.byref(k), C.byref(um)))
-        res = (pos[:k.value].copy(), out[:k.value].copy() if want_bytes else None)
+        res = (pos[:k.value].copy(), out[:k.value] if want_bytes else None)   # a view: no second pass over the payload
         return res + (um.value,) if return_unmerged else res
 
     def i16_to_cf32(self, samples):

@@ -876,12 +876,16 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
     CU_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
     std::vector<std::vector<long long>> lists((size_t)ns);
-    for (long long r = 0; r < ns; r++) {
-        lists[(size_t)r].resize((size_t)cnt[(size_t)r]);
-        if (cnt[(size_t)r])
-            CU_TRY(cudaMemcpyAsync(lists[(size_t)r].data(), d_pos + (size_t)r * (size_t)max_per, (size_t)cnt[(size_t)r] * sizeof(long long), cudaMemcpyDeviceToHost, st));
+    {
+        // one strided copy: the first max(cnt) entries of every shard's list
+        const size_t w = (size_t)*std::max_element(cnt.begin(), cnt.end());
+        std::vector<long long> all((size_t)ns * std::max<size_t>(w, 1));
+        if (w) CU_TRY(cudaMemcpy2DAsync(all.data(), w * sizeof(long long), d_pos, (size_t)max_per * sizeof(long long), w * sizeof(long long),
+                                        (size_t)ns, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        for (long long r = 0; r < ns; r++)
+            lists[(size_t)r].assign(all.begin() + (long)((size_t)r * w), all.begin() + (long)((size_t)r * w + (size_t)cnt[(size_t)r]));
     }
-    CU_TRY(cudaStreamSynchronize(st));
     std::vector<long long> merged;
     size_t unmerged = 0;
     merge_stream_shards(lists, own_end, merged, &unmerged);
@@ -891,7 +895,7 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
     if (pr_begin_abs) std::copy(merged.begin(), merged.end(), pr_begin_abs);
     if (bytes && found) {
         // gather the frames found and demodulate them in batches
-        const size_t batch_cap = 8192;
+        const size_t batch_cap = 32768;
         CU_TRY(h->scratch_c.reserve(found * sizeof(long long)));
         CU_TRY(cudaMemcpyAsync(h->scratch_c.p, merged.data(), found * sizeof(long long), cudaMemcpyHostToDevice, st));
         CU_TRY(h->pipe_in[0].reserve(std::min(found, batch_cap) * (size_t)P.rx_len * 4));

@@ -207,16 +207,20 @@ template <int R, bool INV, bool NOWRAP = false>
 COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const float2 *tw, int tid, int nthr) {
     const int m = n / R;
     const int tstep = n / (ns * R);
+    const bool pow2 = (n & (n - 1)) == 0 && (ns & (ns - 1)) == 0;   // masks instead of integer division (uniform)
     for (int j = tid; j < m; j += nthr) {
-        const int k = j % ns;
+        const int k = pow2 ? (j & (ns - 1)) : j % ns;
         float2 v[R];
 #pragma unroll
         for (int q = 0; q < R; q++) {
             v[q] = in[j + q * m];
-            if (q > 0 && ns > 1) v[q] = cmul(v[q], twid<INV>(__ldg(&tw[NOWRAP ? q * k * tstep : (q * k * tstep) % n])));
+            if (q > 0 && ns > 1) {
+                const int ti = q * k * tstep;
+                v[q] = cmul(v[q], twid<INV>(__ldg(&tw[NOWRAP ? ti : (pow2 ? (ti & (n - 1)) : ti % n)])));
+            }
         }
         dftR<R, INV>(v);
-        const int o = (j / ns) * ns * R + k;
+        const int o = (j - k) * R + k;              // (j / ns) * ns * R + k
 #pragma unroll
         for (int q = 0; q < R; q++) out[o + q * ns] = v[q];
     }

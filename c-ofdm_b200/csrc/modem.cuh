@@ -27,6 +27,18 @@ COFDM_DEV int extract_bits_t(const uint8_t *bytes, int n_bytes, int bitpos) {
     return (int)((w >> (16 - MOD - off)) & ((1u << MOD) - 1u));
 }
 
+// run-time width, dispatched once to the compile-time variants (avoids an integer modulo per symbol)
+COFDM_DEV int extract_bits_sw(const uint8_t *bytes, int n_bytes, int bitpos, int mod) {
+    switch (mod) {
+        case 1: return extract_bits_t<1>(bytes, n_bytes, bitpos);
+        case 2: return extract_bits_t<2>(bytes, n_bytes, bitpos);
+        case 4: return extract_bits_t<4>(bytes, n_bytes, bitpos);
+        case 6: return extract_bits_t<6>(bytes, n_bytes, bitpos);
+        case 8: return extract_bits_t<8>(bytes, n_bytes, bitpos);
+        default: return extract_bits(bytes, n_bytes, bitpos, mod);
+    }
+}
+
 // margin (in level units) inside which a hard decision is reported as boundary-ambiguous: an fp32
 // pipeline and the reference's fp64 pipeline may legitimately land on different sides.
 constexpr float kAmbigMargin = 2e-4f;

@@ -5,7 +5,7 @@
 // one-frame carry-over each time the position passes the last frame of the ring (rx.cpp:147-156,180-189) and
 // a fresh SDR block whenever the ring is exhausted (buf_update, rx.cpp:73-91).  Where it looks next depends on
 // what it found last, so the loop itself cannot be spread over threads -- but
-//   * each of its two searches is data parallel (20 candidate sync-tone blocks at a time, one FFT-256 per warp;
+//   * each of its two searches is data parallel (10 candidate sync-tone blocks at a time, one FFT-256 per warp;
 //     the 640 lags of the preamble correlation over 160 threads), and
 //   * a long capture can be cut into shards of whole SDR blocks that are scanned independently and merged
 //     (two chains that start from different states coincide from the first frame both detect; see
@@ -25,7 +25,7 @@ struct StreamShard {
     long long n_blocks;       // whole SDR blocks it spans (overlap block included)
 };
 
-constexpr int kScanWarps = 20;
+constexpr int kScanWarps = 10;
 constexpr int kScanThreads = 32 * kScanWarps;
 
 COFDM_HD size_t stream_scan_smem_bytes(int cor_size, int pr_sin_len) {
@@ -35,7 +35,7 @@ COFDM_HD size_t stream_scan_smem_bytes(int cor_size, int pr_sin_len) {
 }
 
 // preconditions (checked by the host): t2sin_size == 256, pr_sin_len % 4 == 0, cor_size % 4 == 0
-__global__ void __launch_bounds__(kScanThreads, 1)
+__global__ void __launch_bounds__(kScanThreads, 2)
 stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16 I,Q pairs */,
                    const StreamShard *__restrict__ shards, int n_shards, int rx_buf_size, long long iterations,
                    long long *__restrict__ pos_out /* [n_shards][max_per_shard] */, int max_per_shard,
