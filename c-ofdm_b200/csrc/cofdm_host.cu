@@ -116,7 +116,9 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     const bool small = nsym <= 9;
     const bool want = taps.scal || taps.grid || taps.chan || taps.constell || taps.synced;
     const bool tma = fmt == COFDM_CF32 && ((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0;
-    // cf32 records that are not 16-byte aligned (a frame cut out of a capture) and int16 records use plain loads
+    // records that are not 16-byte aligned (a frame cut out of a capture at an arbitrary sample) use plain loads;
+    // aligned int16 records are bulk-copied as raw wire data and widened when read (split path only)
+    const bool tma16 = fmt == COFDM_CI16 && ((uintptr_t)samples & 15) == 0 && (stride * 4) % 16 == 0;
     const bool split = h->rx_split && small;
     FrameScal *fsc = nullptr;
     if (split) {
@@ -144,7 +146,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 #define COFDM_ACQ(F, T) \
             do { if (want) rx_acquire512x2_kernel<F, T, true><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); \
                  else rx_acquire512x2_kernel<F, T, false><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); } while (0)
-            if (fmt == COFDM_CI16) COFDM_ACQ(kCI16, false);
+            if (fmt == COFDM_CI16) { if (tma16) COFDM_ACQ(kCI16, true); else COFDM_ACQ(kCI16, false); }
             else if (tma) COFDM_ACQ(kCF32, true);
             else COFDM_ACQ(kCF32, false);
 #undef COFDM_ACQ
@@ -152,7 +154,9 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
             COFDM_RX_MODE(1);
         }
         if (int rc = check_launch(h, "rx512_acquire")) return rc;
-        COFDM_RX_MODE(2);                                   // demod: message symbols -> payload bytes
+        // demod: message symbols -> payload bytes
+        if (tma16) { if (want) COFDM_RX_LAUNCH(kCI16, true, 9, true, 2); else COFDM_RX_LAUNCH(kCI16, true, 9, false, 2); }   // split implies <= 9 symbols
+        else COFDM_RX_MODE(2);
     } else {
         COFDM_RX_MODE(0);
     }
@@ -348,12 +352,14 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         COFDM_RX_ATTR_ALL(kCF32, true);
         COFDM_RX_ATTR_ALL(kCF32, false);
         COFDM_RX_ATTR_ALL(kCI16, false);
+        COFDM_RX_ATTR(kCI16, true, 9, true, 2); COFDM_RX_ATTR(kCI16, true, 9, false, 2);
 #undef COFDM_RX_ATTR_ALL
 #undef COFDM_RX_ATTR
 #define COFDM_ACQ_ATTR(F, T, W) \
         if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512x2_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
         COFDM_ACQ_ATTR(kCF32, true, true); COFDM_ACQ_ATTR(kCF32, true, false); COFDM_ACQ_ATTR(kCF32, false, true);
         COFDM_ACQ_ATTR(kCF32, false, false); COFDM_ACQ_ATTR(kCI16, false, true); COFDM_ACQ_ATTR(kCI16, false, false);
+        COFDM_ACQ_ATTR(kCI16, true, true); COFDM_ACQ_ATTR(kCI16, true, false);
 #undef COFDM_ACQ_ATTR
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);

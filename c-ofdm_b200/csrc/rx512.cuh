@@ -127,6 +127,16 @@ COFDM_DEV void load_symbol_direct(float2 *dst, const void *src_frame, int sym, i
     }
 }
 
+// one sample of a symbol staged in shared memory: float2, or -- RAW16: a bulk copy of int16 wire data -- int16 I,Q
+template <bool RAW16>
+COFDM_DEV float2 staged_sample(const float2 *region, int idx) {
+    if (RAW16) {
+        const unsigned w = reinterpret_cast<const unsigned *>(region)[idx];
+        return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+    }
+    return region[idx];
+}
+
 // Constant phase (turns, mod 1) carried into symbol s by freq_shift's global sample index (Frame.hpp:341-347)
 // and by cp_freq_sinh's accumulated `shift` (Frame.hpp:248,261):
 //     Psi_s = shift*640*s + (640/512) * sum_{t<s} phi_t,   phi_t = theta_t - 512*shift + m_t  (turns)
@@ -162,6 +172,8 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     // sync_less != 0: FRAME_FORM::read / OFDM_FORM::read (Frame.cpp:201-208,239-242): no CFO, phase or channel
     // correction at all -- CP strip, FFT, pilot normalisation, segment correction, demap.
     COFDM_DYN_SMEM(smem_raw);
+    constexpr bool RAW16 = FMT == kCI16 && USE_TMA;   // int16 wire data bulk-copied as is, widened when read
+    static_assert(!RAW16 || MODE == 2, "raw int16 staging is for the demod kernel (the coarse warps transform their copy in place)");
     constexpr int kMaxTeams = (rx512_max_threads(MAXSYM, MODE) / 32 - (MODE == 2 ? 0 : kCoarseWarps)) / 2;
     const int nsym_all = P.n_sym_rx;             // 1 preamble + num_symb message symbols
     const int sym0 = MODE == 2 ? 1 : 0;          // first frame symbol this kernel handles
@@ -190,8 +202,8 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             if (tid == 64 * npair) {
                 mbar_init(&M->mbar[nsym], 1);
                 mbar_fence_init();
-                mbar_arrive_expect_tx(&M->mbar[nsym], 640 * 8);
-                tma_load_1d(SA, frame_src, 640 * 8, &M->mbar[nsym]);
+                mbar_arrive_expect_tx(&M->mbar[nsym], 640 * (unsigned)sample_bytes);
+                tma_load_1d(SA, frame_src, 640 * (unsigned)sample_bytes, &M->mbar[nsym]);
             }
             named_bar_sync(1, 32 * kCoarseWarps);
         } else {
@@ -200,11 +212,11 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
                 mbar_init(&M->mbar[s0], 1);
                 if (s1 < nsym) mbar_init(&M->mbar[s1], 1);
                 mbar_fence_init();
-                mbar_arrive_expect_tx(&M->mbar[s0], 640 * 8);
-                tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots, frame_src + (size_t)(sym0 + s0) * 640 * 8, 640 * 8, &M->mbar[s0]);
+                mbar_arrive_expect_tx(&M->mbar[s0], 640 * (unsigned)sample_bytes);
+                tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots, frame_src + (size_t)(sym0 + s0) * 640 * sample_bytes, 640 * (unsigned)sample_bytes, &M->mbar[s0]);
                 if (s1 < nsym) {
-                    mbar_arrive_expect_tx(&M->mbar[s1], 640 * 8);
-                    tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots + 640, frame_src + (size_t)(sym0 + s1) * 640 * 8, 640 * 8, &M->mbar[s1]);
+                    mbar_arrive_expect_tx(&M->mbar[s1], 640 * (unsigned)sample_bytes);
+                    tma_load_1d(X + (size_t)(s0 >> 1) * kPairSlots + 640, frame_src + (size_t)(sym0 + s1) * 640 * sample_bytes, 640 * (unsigned)sample_bytes, &M->mbar[s1]);
                 }
             }
             team_bar_sync<kMaxTeams>(warp >> 1);
@@ -299,13 +311,13 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         float2 ra[8], rb[8], cpa[2], cpb[2];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            ra[r] = xa[128 + t + 64 * r];
-            rb[r] = hasB ? xb[128 + t + 64 * r] : make_float2(0.f, 0.f);
+            ra[r] = staged_sample<RAW16>(xa, 128 + t + 64 * r);
+            rb[r] = hasB ? staged_sample<RAW16>(xb, 128 + t + 64 * r) : make_float2(0.f, 0.f);
         }
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            cpa[c] = xa[t + 64 * c];
-            cpb[c] = hasB ? xb[t + 64 * c] : make_float2(0.f, 0.f);
+            cpa[c] = staged_sample<RAW16>(xa, t + 64 * c);
+            cpb[c] = hasB ? staged_sample<RAW16>(xb, t + 64 * c) : make_float2(0.f, 0.f);
         }
         {
             float2 ca = make_float2(0.f, 0.f), cb = make_float2(0.f, 0.f);

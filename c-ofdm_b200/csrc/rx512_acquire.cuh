@@ -46,6 +46,7 @@ __global__ void __launch_bounds__(kAcqThreads, 6)
 rx_acquire512x2_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/,
                        int n_frames, const RxTaps taps, FrameScal *__restrict__ fscal) {
     COFDM_DYN_SMEM(smem_raw);
+    constexpr bool RAW16 = FMT == kCI16 && USE_TMA;   // int16 wire data bulk-copied as is, widened when read
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int fA = 2 * blockIdx.x;
     if (fA >= n_frames) return;
@@ -68,11 +69,11 @@ rx_acquire512x2_kernel(const Params P, const void *__restrict__ samples, long lo
             mbar_init(&M->mbar[0], 1);
             mbar_init(&M->mbar[1], 1);
             mbar_fence_init();
-            mbar_arrive_expect_tx(&M->mbar[0], 640 * 8);
-            tma_load_1d(xa, srcA, 640 * 8, &M->mbar[0]);
+            mbar_arrive_expect_tx(&M->mbar[0], 640 * (unsigned)sample_bytes);
+            tma_load_1d(xa, srcA, 640 * (unsigned)sample_bytes, &M->mbar[0]);
             if (hasB) {
-                mbar_arrive_expect_tx(&M->mbar[1], 640 * 8);
-                tma_load_1d(xb, srcB, 640 * 8, &M->mbar[1]);
+                mbar_arrive_expect_tx(&M->mbar[1], 640 * (unsigned)sample_bytes);
+                tma_load_1d(xb, srcB, 640 * (unsigned)sample_bytes, &M->mbar[1]);
             }
         }
         __syncthreads();
@@ -91,13 +92,13 @@ rx_acquire512x2_kernel(const Params P, const void *__restrict__ samples, long lo
         float2 ra[8], rb[8], cpa[2], cpb[2];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-            ra[r] = xa[128 + t + 64 * r];
-            rb[r] = hasB ? xb[128 + t + 64 * r] : zero2;
+            ra[r] = staged_sample<RAW16>(xa, 128 + t + 64 * r);
+            rb[r] = hasB ? staged_sample<RAW16>(xb, 128 + t + 64 * r) : zero2;
         }
 #pragma unroll
         for (int c = 0; c < 2; c++) {
-            cpa[c] = xa[t + 64 * c];
-            cpb[c] = hasB ? xb[t + 64 * c] : zero2;
+            cpa[c] = staged_sample<RAW16>(xa, t + 64 * c);
+            cpb[c] = hasB ? staged_sample<RAW16>(xb, t + 64 * c) : zero2;
         }
         {
             float2 ca = zero2, cb = zero2;
@@ -172,7 +173,7 @@ rx_acquire512x2_kernel(const Params P, const void *__restrict__ samples, long lo
         const int ct = tid - 64, cw = warp - 2;
         pc u[10];
 #pragma unroll
-        for (int q = 0; q < 10; q++) u[q] = make_pc(xa[ct + 64 * q], hasB ? xb[ct + 64 * q] : zero2);
+        for (int q = 0; q < 10; q++) u[q] = make_pc(staged_sample<RAW16>(xa, ct + 64 * q), hasB ? staged_sample<RAW16>(xb, ct + 64 * q) : zero2);
         named_bar_sync(2, kAcqThreads);               // #1
         // pass 1: radix 10, ns = 1; output o = 10 ct + q stored at slot o + o/10 = 11 ct + q
         dft10<false>(u);

@@ -54,10 +54,15 @@ int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, in
 #define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
     auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
     if (g_emu_split && nsym <= 9 && !sync_less) {     // production split: paired acquire + demod
-        if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
-        else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
-        else acq2([&] { rx_acquire512x2_kernel<kCF32, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
-        EMU_RX_MODE(2);
+        if (fmt == kCI16 && use_tma) {                // raw int16 bulk copies, widened when read
+            acq2([&] { rx_acquire512x2_kernel<kCI16, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
+            EMU_RX(kCI16, true, 2);
+        } else {
+            if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
+            else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
+            else acq2([&] { rx_acquire512x2_kernel<kCF32, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
+            EMU_RX_MODE(2);
+        }
     }
     else if (g_emu_split && nsym <= 9) { EMU_RX_MODE(1); EMU_RX_MODE(2); }
     else if (nsym <= 9) EMU_RX_MODE(0);
@@ -92,10 +97,15 @@ int emu_rx_fused512_notaps(void *hv, const void *samples, int fmt, int use_tma, 
 #define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
     if (g_emu_split) {
         auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
-        if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
-        else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
-        else acq2([&] { rx_acquire512x2_kernel<kCF32, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
-        EMU_RX_MODE(2);
+        if (fmt == kCI16 && use_tma) {
+            acq2([&] { rx_acquire512x2_kernel<kCI16, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
+            EMU_RX(kCI16, true, 2);
+        } else {
+            if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
+            else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
+            else acq2([&] { rx_acquire512x2_kernel<kCF32, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
+            EMU_RX_MODE(2);
+        }
     } else EMU_RX_MODE(0);
 #undef EMU_RX_MODE
 #undef EMU_RX

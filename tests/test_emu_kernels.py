@@ -53,6 +53,13 @@ def test_rx_non_tma_path_is_identical(emu, port):
     b, _ = emu[4].rx_aligned_batch(x)
     emu[4].use_tma = 1
     assert np.array_equal(a, b)
+    # int16 wire records: bulk-copied raw and widened when read, or widened while loading -- same bytes, same taps
+    a, ta, _ = emu[4].rx_aligned_batch(rec, taps=True)
+    emu[4].use_tma = 0
+    b, tb, _ = emu[4].rx_aligned_batch(rec, taps=True)
+    emu[4].use_tma = 1
+    assert np.array_equal(a, b) and np.array_equal(a, pay)
+    assert np.array_equal(ta["constell"], tb["constell"]) and np.array_equal(ta["scal"], tb["scal"])
 
 
 def test_loopback_clean(emu, port):
