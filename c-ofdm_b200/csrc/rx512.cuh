@@ -638,15 +638,28 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
 #pragma unroll
     for (int ee = 0; ee < 4; ee++) {
         const int e = 4 * h + ee;
-        const int i = lane + 32 * e;
-        const int bin = __ldg(&P.data_bin[32 * e]) + lane;            // segment e is 32 consecutive bins
-        const int sa = spec_slot((bin + mA) & 511), sb = spec_slot((bin + mB) & 511);
+        const int seg0 = __ldg(&P.data_bin[32 * e]);                  // segment e is 32 consecutive bins
+        int idx = lane;                                               // data index inside the segment
+        float2 Lv = Ll;
         pc x;
-        if (mA == mB) { x.re = Wre[sa]; x.im = Wim[sa]; }             // the usual case: one 64-bit load per plane
-        else { x.re = make_float2(Wre[sa].x, Wre[sb].y); x.im = make_float2(Wim[sa].x, Wim[sb].y); }
+        if (MODE == 2 && mA == mB) {
+            // the usual case, one 64-bit load per plane.  The lane takes the bin congruent to itself mod 32 (the
+            // segment holds each residue once), so a half-warp reads 16 aligned consecutive bins: no bank conflict
+            // whatever the shift m is.  exp(-j b idx) then comes from the CTA's table.
+            const int b0 = seg0 + mA;
+            idx = (lane - b0) & 31;
+            const int sl = spec_slot((b0 + idx) & 511);
+            x.re = Wre[sl]; x.im = Wim[sl];
+            Lv = M->ltab[idx];
+        } else {
+            const int sa = spec_slot((seg0 + lane + mA) & 511), sb = spec_slot((seg0 + lane + mB) & 511);
+            if (mA == mB) { x.re = Wre[sa]; x.im = Wim[sa]; }
+            else { x.re = make_float2(Wre[sa].x, Wre[sb].y); x.im = make_float2(Wim[sa].x, Wim[sb].y); }
+        }
+        const int i = idx + 32 * e;
         const float4 w4 = wt[e];
         pc w; w.re = make_float2(w4.x, w4.y); w.im = make_float2(w4.z, w4.w);
-        const pc z = cmul(cmul(x, w), Ll);
+        const pc z = cmul(cmul(x, w), Lv);
         if (doA) {
             if (TAPS && taps.constell != nullptr) taps.constell[((size_t)frame * (nsym_all - 1) + (A - 1)) * 256 + i] = pc_a(z);
             sbA[i] = (uint8_t)demap_fast(pc_a(z), dk);
