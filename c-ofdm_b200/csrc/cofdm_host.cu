@@ -62,6 +62,7 @@ struct cofdm {
     DevBuf gen_frames, gen_spec, gen_pre;        // generic path intermediates
     DevBuf fscal;                                // per-frame scalars handed from the acquire to the demod kernel
     int rx_split = 1;                            // 1: acquire + demod kernels, 0: single fused kernel
+    int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
     int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
                                                  // 2 reaches the PCIe full-duplex ceiling, 3 and more lose 10-15 %
     size_t pipe_chunk = 2048;                    // frames per chunk of the COFDM_HOST pipeline (env COFDM_PIPE_CHUNK)
@@ -232,8 +233,16 @@ int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames
     }
     const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
     const dim3 grid((unsigned)n_frames), block(tx512_threads(h->P.num_symb));
-    if (fmt == COFDM_CI16) tx512_kernel<kCI16><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
-    else tx512_kernel<kCF32><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+    // frames leave the SM as TMA bulk stores when the buffer is 16-byte aligned (frame and symbol sizes are multiples of 16 bytes)
+    const bool bulk = h->tx_bulk && ((uintptr_t)frames & 15) == 0 && ((size_t)h->P.frame_len * sample_bytes(fmt)) % 16 == 0 &&
+                      ((size_t)(h->P.t2sin_size + h->P.pf_size) * sample_bytes(fmt)) % 16 == 0;
+    if (bulk) {
+        if (fmt == COFDM_CI16) tx512_kernel<kCI16, true><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+        else tx512_kernel<kCF32, true><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+    } else {
+        if (fmt == COFDM_CI16) tx512_kernel<kCI16><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+        else tx512_kernel<kCF32><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
+    }
     return check_launch(h, "tx512");
 }
 
@@ -337,6 +346,8 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         {
             const char *e = std::getenv("COFDM_RX_SPLIT");
             if (e) h->rx_split = std::atoi(e) != 0;
+            const char *tb = std::getenv("COFDM_TX_BULK");
+            if (tb) h->tx_bulk = std::atoi(tb) != 0;
             const char *c = std::getenv("COFDM_PIPE_CHUNK");
             if (c && std::atoll(c) > 0) h->pipe_chunk = (size_t)std::atoll(c);
             const char *d = std::getenv("COFDM_PIPE_DEPTH");
@@ -363,6 +374,8 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
 #undef COFDM_ACQ_ATTR
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
+        if (c == cudaSuccess) c = cudaFuncSetAttribute(tx512_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
+        if (d == cudaSuccess) d = cudaFuncSetAttribute(tx512_kernel<kCI16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)
             return bail(fail(COFDM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(a != cudaSuccess ? a : (b != cudaSuccess ? b : (c != cudaSuccess ? c : d)))));
     }

@@ -209,6 +209,9 @@ COFDM_DEV void mbar_fence_init() {}
 COFDM_DEV void mbar_arrive_expect_tx(uint64_t *, uint32_t) {}
 COFDM_DEV void tma_load_1d(void *dst, const void *src, uint32_t bytes, uint64_t *) { memcpy(dst, src, bytes); }
 COFDM_DEV void mbar_wait(uint64_t *, uint32_t) {}
+COFDM_DEV void tma_store_fence() {}
+COFDM_DEV void tma_store_1d(void *dst, const void *src, uint32_t bytes) { memcpy(dst, src, bytes); }
+COFDM_DEV void tma_store_commit_and_wait_read() {}
 #else
 COFDM_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 COFDM_DEV void mbar_init(uint64_t *bar, int count) {
@@ -235,6 +238,17 @@ COFDM_DEV void mbar_wait(uint64_t *bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "DONE:\n\t"
         "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy shared -> global (SASS: UBLKCP ... S2G).  Order: generic-proxy writes to shared memory, then
+// tma_store_fence() by the writers, a barrier, then ONE thread issues the copies, commits and waits until the
+// source has been read (the CTA's shared memory must outlive the copy).
+COFDM_DEV void tma_store_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+COFDM_DEV void tma_store_1d(void *dst, const void *src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
+}
+COFDM_DEV void tma_store_commit_and_wait_read() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 #endif
 

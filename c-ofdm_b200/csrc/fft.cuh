@@ -306,4 +306,51 @@ COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const flo
     team_bar_sync<MAXT>(team);
 }
 
+// ------------------------------------------------------------------------------------------------
+// team_fft512p_tail_linear: the tail for a transform whose result leaves the SM as a LINEAR image (tx).
+// Passes 2 and 3 as above, but the second exchange uses a layout that lets the last pass be done by
+// lane (k1 = lane & 7, k2 = (lane >> 3) + 4h), so that a half-warp owns 16 CONSECUTIVE outputs
+// n = k1 + 8 k2 + 64 k3 and can store them to a linear buffer without bank conflicts:
+//   E2'(k1,k2,n3) = (n3 ^ ((k1 >> 1) | ((k2 & 1) << 2))) + 8 k1 + 64 k2
+//   writer (pass-2 butterfly k1 = p, n3 = q, fixed k2): half-warp = q 0..7 x p {even, even+1}  -> banks (q^g) + 8 (p&1)
+//   reader (fixed n3): half-warp = k1 0..7 x k2 {c, c+1}: g takes 8 values x (k1 & 1)           -> 16 distinct banks
+// On exit v[k3] = X[k1 + 8 k2 + 64 k3] in registers; the planes are free (every lane has passed the last barrier).
+// ------------------------------------------------------------------------------------------------
+template <bool INV, int MAXT>
+COFDM_DEV void team_fft512p_tail_linear(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int team) {
+    const int q = lane & 7, p = (lane >> 3) + 4 * h;
+    {
+        const int b = q + 8 * p;
+#pragma unroll
+        for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[k1].re; Wim[b + 72 * k1] = v[k1].im; }
+    }
+    team_bar_sync<MAXT>(team);
+    {
+        const int b = q + 72 * p;
+#pragma unroll
+        for (int n2 = 0; n2 < 8; n2++) { v[n2].re = Wre[b + 8 * n2]; v[n2].im = Wim[b + 8 * n2]; }
+    }
+    team_bar_sync<MAXT>(team);
+    dft8<INV>(v);
+#pragma unroll
+    for (int k2 = 1; k2 < 8; k2++) v[k2] = cmul(v[k2], twid<INV>(__ldg(&tw_p2[k2 * 8 + q])));
+    {
+        const int b0 = (q ^ (p >> 1)) + 8 * p, b1 = (q ^ ((p >> 1) | 4)) + 8 * p;      // even / odd k2
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) {
+            const int a = ((k2 & 1) ? b1 : b0) + 64 * k2;
+            Wre[a] = v[k2].re; Wim[a] = v[k2].im;
+        }
+    }
+    team_bar_sync<MAXT>(team);
+    {
+        const int k1 = lane & 7, k2 = (lane >> 3) + 4 * h;
+        const int g = (k1 >> 1) | ((k2 & 1) << 2), b = 8 * k1 + 64 * k2;
+#pragma unroll
+        for (int n3 = 0; n3 < 8; n3++) { v[n3].re = Wre[b + (n3 ^ g)]; v[n3].im = Wim[b + (n3 ^ g)]; }
+    }
+    team_bar_sync<MAXT>(team);
+    dft8<INV>(v);
+}
+
 }  // namespace cofdmk

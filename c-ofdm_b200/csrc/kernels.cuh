@@ -68,7 +68,9 @@ COFDM_DEV void tx512_grid_points(const Params &P, const uint8_t *pl, int A, int 
 // One CTA per frame.  The last warp copies the frame-invariant sync tone + preamble; the other warps form
 // teams of two per PAIR of OFDM symbols (packed f32x2 arithmetic, symbol A in the low half, B in the high
 // half, exactly as in the rx kernel): map bits, insert pilots, IFFT-512, /sqrt(512), prepend CP.
-template <int FMT>
+// BULK: the last IFFT pass writes the symbols' wire images (CP + body) straight into the shared memory the planes
+// occupied, and each symbol leaves the SM as one TMA bulk store (needs a 16-byte aligned frame buffer).
+template <int FMT, bool BULK = false>
 __global__ void __launch_bounds__(32 * (2 * ((kMaxFusedSymb + 1) / 2) + 1))
 tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, void *__restrict__ frames) {
     COFDM_DYN_SMEM(smem_raw);
@@ -114,6 +116,36 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
         default: tx512_grid_points<8>(P, pl, A, B, hasB, t, v); break;
     }
     team_fft512p_head<true>(v, P.tw_p1, t);                                          // Frame.cpp:64 (backward, unnormalised)
+    if (BULK) {
+        team_fft512p_tail_linear<true, kMaxTeams>(v, Wre, Wim, P.tw_p2, lane, h, team);
+        // v[k3] = x[n], n = k0 + 64 k3; /sqrt(512) (Frame.cpp:66-68); body after the CP slot (Frame.cpp:191-192), the
+        // last 128 samples also into the CP slot (:196-197).  Image of A in the re plane's memory, of B in the im plane's.
+        const float sc = 0.04419417382415922028f;
+        const int k0 = (lane & 7) + 8 * ((lane >> 3) + 4 * h);
+#pragma unroll
+        for (int k3 = 0; k3 < 8; k3++) {
+            const int n = k0 + 64 * k3;
+            const float2 a = make_float2(v[k3].re.x * sc, v[k3].im.x * sc), b = make_float2(v[k3].re.y * sc, v[k3].im.y * sc);
+            if (FMT == kCI16) {
+                unsigned *ia = reinterpret_cast<unsigned *>(Wre), *ib = reinterpret_cast<unsigned *>(Wim);
+                const unsigned pa = ((unsigned)(unsigned short)(short)__float2int_rz(a.x * P.mult)) | ((unsigned)(unsigned short)(short)__float2int_rz(a.y * P.mult) << 16);
+                const unsigned pb = ((unsigned)(unsigned short)(short)__float2int_rz(b.x * P.mult)) | ((unsigned)(unsigned short)(short)__float2int_rz(b.y * P.mult) << 16);
+                ia[128 + n] = pa; ib[128 + n] = pb;
+                if (k3 >= 6) { ia[n - 384] = pa; ib[n - 384] = pb; }
+            } else {
+                Wre[128 + n] = a; Wim[128 + n] = b;
+                if (k3 >= 6) { Wre[n - 384] = a; Wim[n - 384] = b; }
+            }
+        }
+        tma_store_fence();
+        team_bar_sync<kMaxTeams>(team);
+        if (lane == 0 && (h == 0 || hasB)) {
+            const int base = P.t2sin_size + P.pf_size + (h ? B : A) * 640;
+            tma_store_1d(fout + (size_t)base * sample_bytes, h ? Wim : Wre, 640u * (unsigned)sample_bytes);
+            tma_store_commit_and_wait_read();
+        }
+        return;
+    }
     team_fft512p_tail<true, kMaxTeams>(v, Wre, Wim, P.tw_p2, lane, h, team);
     // output: warp h writes samples 256h .. 256h+255 of BOTH symbols, so every 64-bit plane word it loads
     // (value of A, value of B) is used whole.  /sqrt(512) (Frame.cpp:66-68), body after the CP slot

@@ -39,6 +39,8 @@ int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
 static int g_emu_split = 0;
 void emu_set_split(int on) { g_emu_split = on; }
+static int g_emu_tx_bulk = 1;
+void emu_set_tx_bulk(int on) { g_emu_tx_bulk = on; }
 
 int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride, int sync_less,
                     uint8_t *out, unsigned long long *amb, float *scal, float2 *grid, float2 *chan,
@@ -117,6 +119,12 @@ int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int 
     if (!h->T.fused512_ok) return -1;
     const Params P = h->P;
     const size_t sm = tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
+    // both output stages: register stores (tx_bulk = 0) and the TMA bulk store of linear images (the product default)
+    if (g_emu_tx_bulk) {
+        if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCI16, true>(P, payload, n_frames, frames); });
+        else emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCF32, true>(P, payload, n_frames, frames); });
+        return 0;
+    }
     if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCI16>(P, payload, n_frames, frames); });
     else emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCF32>(P, payload, n_frames, frames); });
     return 0;

@@ -58,6 +58,11 @@ class EmuModem:
         """1: acquire + demod kernels (the product default), 0: the single fused kernel"""
         self.lib.emu_set_split(int(on))
 
+    def set_tx_bulk(self, on):
+        """1: tx symbols leave as TMA bulk stores of linear images (the product default), 0: register stores"""
+        self.lib.emu_set_tx_bulk.argtypes = [C.c_int]
+        self.lib.emu_set_tx_bulk(int(on))
+
     def close(self):
         if self.h:
             self.lib.emu_destroy(self.h)

@@ -29,6 +29,20 @@ def test_tx(emu, port, mt):
     assert st["rel_l2"] < 5e-7
 
 
+def test_tx_register_store_variant(emu, port):
+    """the non-bulk output stage (used when the frame buffer is not 16-byte aligned) gives the same frames"""
+    pay = pc.synth.payloads(3, port[4].sizes.usefull_size, seed=9)
+    a = emu[4].tx_batch(pay, 1)
+    c = emu[4].tx_batch(pay, 0)
+    emu[4].set_tx_bulk(0)
+    try:
+        b = emu[4].tx_batch(pay, 1)
+        d = emu[4].tx_batch(pay, 0)
+    finally:
+        emu[4].set_tx_bulk(1)
+    assert np.array_equal(a, b) and np.array_equal(c, d)
+
+
 @pytest.mark.parametrize("mt,fmt", [(4, "i16"), (4, "cf32"), (2, "i16"), (6, "cf32"), (1, "i16"), (8, "i16")])
 def test_rx_fused_against_oracle(emu, port, mt, fmt):
     pay, rec = pc.impaired_records(port[mt], 3, seed=10 * mt)
