@@ -51,10 +51,10 @@ COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/,
 // the 8 frequency-domain points (bins t + 64 r) of symbols A and B that one lane feeds to the first IFFT pass:
 // null, pilot, or the constellation point of MOD payload bits (Frame.cpp:55-62 + modulation.cpp:39-50)
 template <int MOD>
-COFDM_DEV void tx512_grid_points(const Params &P, const uint8_t *pl, int A, int B, bool hasB, int t, pc (&v)[8]) {
+COFDM_DEV void tx512_grid_points(const Params &P, const uint8_t *pl, int A, int B, bool hasB, const int (&mm)[8], pc (&v)[8]) {
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        const int m = __ldg(&P.bin_map[t + 64 * r]);
+        const int m = mm[r];                                                         // bin_map[t + 64 r]
         float2 va = make_float2(0.f, 0.f), vb = va;                                  // Frame.cpp:55
         if (m == -2) va = vb = make_float2(P.pilot_ampl, 0.f);                        // Frame.cpp:56-57
         else if (m >= 0) {
@@ -83,14 +83,6 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
     const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
     char *fout = reinterpret_cast<char *>(frames) + (size_t)frame * P.frame_len * sample_bytes;
 
-    if ((P.bytes_per_frame & 15) == 0 && ((reinterpret_cast<uintptr_t>(payload) & 15) == 0)) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(payload + (size_t)frame * P.bytes_per_frame);
-        for (int i = tid; i < P.bytes_per_frame / 16; i += blockDim.x) reinterpret_cast<uint4 *>(pl)[i] = __ldg(src + i);
-    } else {
-        for (int i = tid; i < P.bytes_per_frame; i += blockDim.x) pl[i] = payload[(size_t)frame * P.bytes_per_frame + i];
-    }
-    __syncthreads();
-
     if (warp == 2 * npair) {
         // T2SIN tone + preamble are constants of the configuration (Frame.cpp:228-229)
         const int n_const = P.t2sin_size + P.pf_size;
@@ -101,19 +93,31 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
         }
         return;
     }
+    // the FFT warps stage the frame's payload; the sub-carrier map is fetched while those loads are in flight
+    const int nfft = 64 * npair;
+    if ((P.bytes_per_frame & 15) == 0 && ((reinterpret_cast<uintptr_t>(payload) & 15) == 0)) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(payload + (size_t)frame * P.bytes_per_frame);
+        for (int i = tid; i < P.bytes_per_frame / 16; i += nfft) reinterpret_cast<uint4 *>(pl)[i] = __ldg(src + i);
+    } else {
+        for (int i = tid; i < P.bytes_per_frame; i += nfft) pl[i] = payload[(size_t)frame * P.bytes_per_frame + i];
+    }
     const int team = warp >> 1, h = warp & 1;
     constexpr int kMaxTeams = (kMaxFusedSymb + 1) / 2;
     const int A = 2 * team, B = A + 1;
     const bool hasB = B < ns;
     float2 *Wre = W + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
     const int mod = P.mod_type, t = lane + 32 * h;
+    int mm[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) mm[r] = __ldg(&P.bin_map[t + 64 * r]);
+    named_bar_sync(1, nfft);                        // the FFT warps only: the constant-copy warp is already on its way
     pc v[8];
     switch (mod) {                                  // uniform: the symbol width becomes a compile-time constant
-        case 1: tx512_grid_points<1>(P, pl, A, B, hasB, t, v); break;
-        case 2: tx512_grid_points<2>(P, pl, A, B, hasB, t, v); break;
-        case 4: tx512_grid_points<4>(P, pl, A, B, hasB, t, v); break;
-        case 6: tx512_grid_points<6>(P, pl, A, B, hasB, t, v); break;
-        default: tx512_grid_points<8>(P, pl, A, B, hasB, t, v); break;
+        case 1: tx512_grid_points<1>(P, pl, A, B, hasB, mm, v); break;
+        case 2: tx512_grid_points<2>(P, pl, A, B, hasB, mm, v); break;
+        case 4: tx512_grid_points<4>(P, pl, A, B, hasB, mm, v); break;
+        case 6: tx512_grid_points<6>(P, pl, A, B, hasB, mm, v); break;
+        default: tx512_grid_points<8>(P, pl, A, B, hasB, mm, v); break;
     }
     team_fft512p_head<true>(v, P.tw_p1, t);                                          // Frame.cpp:64 (backward, unnormalised)
     if (BULK) {
