@@ -249,6 +249,12 @@ int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames
 int launch_t2(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t start, size_t n_blocks, float *rel) {
     if (h->P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "t2sin: only T2sin_size = 256 is built so far");
     if (n_blocks == 0) return COFDM_OK;
+    if (n_blocks >= 64) {                            // two blocks per warp, packed arithmetic
+        const unsigned g2 = (unsigned)(((n_blocks + 1) / 2 + kT2PairWarps - 1) / kT2PairWarps);
+        if (fmt == COFDM_CI16) t2sin_metric2_kernel<kCI16><<<g2, 32 * kT2PairWarps, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
+        else t2sin_metric2_kernel<kCF32><<<g2, 32 * kT2PairWarps, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
+        return check_launch(h, "t2sin_metric2");
+    }
     const unsigned grid = (unsigned)((n_blocks + kT2WarpsPerCta - 1) / kT2WarpsPerCta);
     if (fmt == COFDM_CI16) t2sin_metric_kernel<kCI16><<<grid, 32 * kT2WarpsPerCta, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
     else t2sin_metric_kernel<kCF32><<<grid, 32 * kT2WarpsPerCta, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
@@ -260,6 +266,13 @@ int launch_pc(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     if (n_starts == 0) return COFDM_OK;
     const size_t sm = (size_t)(h->P.cor_size + 2 * h->P.pr_sin_len) * sizeof(float2);
     if (sm > 200 * 1024) return fail(COFDM_ERR_UNSUPPORTED, "preamble search window exceeds shared memory");
+    if ((h->P.pr_sin_len % 4) == 0 && (h->P.cor_size % 4) == 0) {
+        // 4 consecutive lags per thread on a transposed window (kernels.cuh corr4_lags)
+        const size_t sm4 = preamble_corr4_smem_bytes(h->P.cor_size, h->P.pr_sin_len);
+        if (fmt == COFDM_CI16) preamble_corr4_kernel<kCI16><<<(unsigned)n_starts, kPc4Threads, sm4, st>>>(h->P, samples, (long long)n_samples, starts, (int)n_starts, cor, first);
+        else preamble_corr4_kernel<kCF32><<<(unsigned)n_starts, kPc4Threads, sm4, st>>>(h->P, samples, (long long)n_samples, starts, (int)n_starts, cor, first);
+        return check_launch(h, "preamble_corr4");
+    }
     if (fmt == COFDM_CI16) preamble_corr_kernel<kCI16><<<(unsigned)n_starts, kPcThreads, sm, st>>>(h->P, samples, (long long)n_samples, starts, (int)n_starts, cor, first);
     else preamble_corr_kernel<kCF32><<<(unsigned)n_starts, kPcThreads, sm, st>>>(h->P, samples, (long long)n_samples, starts, (int)n_starts, cor, first);
     return check_launch(h, "preamble_corr");
@@ -392,6 +405,11 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     cudaFuncSetAttribute(stream_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_scan_smem_bytes(P.cor_size, P.pr_sin_len));
     {
         const int smp = (int)((size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2));
+        const int smp4 = (int)preamble_corr4_smem_bytes(P.cor_size, P.pr_sin_len);
+        if (smp4 > 48 * 1024) {
+            cudaFuncSetAttribute(preamble_corr4_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp4);
+            cudaFuncSetAttribute(preamble_corr4_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp4);
+        }
         if (smp > 48 * 1024) {
             cudaFuncSetAttribute(preamble_corr_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp);
             cudaFuncSetAttribute(preamble_corr_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smp);

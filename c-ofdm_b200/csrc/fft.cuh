@@ -57,9 +57,9 @@ template <bool INV> COFDM_DEV void dft2(float2 *v) {
 }
 
 // v[k] = sum_n v[n] W4^{nk}
-template <bool INV> COFDM_DEV void dft4(float2 *v) {
-    float2 e0 = cadd(v[0], v[2]), e1 = csub(v[0], v[2]);
-    float2 o0 = cadd(v[1], v[3]), o1 = mul_w4<INV>(csub(v[1], v[3]));
+template <bool INV, class T> COFDM_DEV void dft4(T *v) {
+    T e0 = cadd(v[0], v[2]), e1 = csub(v[0], v[2]);
+    T o0 = cadd(v[1], v[3]), o1 = mul_w4<INV>(csub(v[1], v[3]));
     v[0] = cadd(e0, o0);
     v[1] = cadd(e1, o1);
     v[2] = csub(e0, o0);
@@ -223,6 +223,32 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
         const int o = (j - k) * R + k;              // (j / ns) * ns * R + k
 #pragma unroll
         for (int q = 0; q < R; q++) out[o + q * ns] = v[q];
+    }
+}
+
+// The same pass for TWO transforms at once (packed f32x2; operands in separate re / im planes of float2 pairs).
+template <int R, bool INV, bool NOWRAP = false>
+COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2 *out_re, float2 *out_im, int n, int ns,
+                                const float2 *tw, int tid, int nthr) {
+    static_assert(R == 8 || R == 4, "packed passes exist for radix 4 and 8");
+    const int m = n / R;
+    const int tstep = n / (ns * R);
+    for (int j = tid; j < m; j += nthr) {
+        const int k = j % ns;
+        pc v[R];
+#pragma unroll
+        for (int q = 0; q < R; q++) {
+            v[q].re = in_re[j + q * m];
+            v[q].im = in_im[j + q * m];
+            if (q > 0 && ns > 1) {
+                const int ti = q * k * tstep;
+                v[q] = cmul(v[q], twid<INV>(__ldg(&tw[NOWRAP ? ti : ti % n])));
+            }
+        }
+        if (R == 8) dft8<INV>(v); else dft4<INV>(v);
+        const int o = (j - k) * R + k;
+#pragma unroll
+        for (int q = 0; q < R; q++) { out_re[o + q * ns] = v[q].re; out_im[o + q * ns] = v[q].im; }
     }
 }
 

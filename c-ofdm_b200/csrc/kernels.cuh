@@ -247,6 +247,76 @@ t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long 
     if (lane == 0) rel_out[blk] = rel;
 }
 
+// t2sin_metric2_kernel: the same metric with TWO consecutive blocks per warp, packed f32x2 (block 2b in the low,
+// block 2b+1 in the high half of every register pair): half the FFT instructions per block.
+constexpr int kT2PairWarps = 4;
+template <int FMT>
+__global__ void __launch_bounds__(32 * kT2PairWarps)
+t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
+                     float *__restrict__ rel_out) {
+    __shared__ float2 buf[kT2PairWarps][4][256];                // per warp: re / im planes of two ping-pong buffers
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const long long blk = 2 * ((long long)blockIdx.x * kT2PairWarps + warp);
+    if (blk >= n_blocks) return;
+    const bool has1 = blk + 1 < n_blocks;
+    float2 *Are = buf[warp][0], *Aim = buf[warp][1], *Bre = buf[warp][2], *Bim = buf[warp][3];
+    const long long s0 = start + blk * 256;
+    float2 tot = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        float2 x0, x1 = make_float2(0.f, 0.f);
+        if (FMT == kCI16) {
+            const unsigned *src = reinterpret_cast<const unsigned *>(samples) + s0 + lane + 32 * i;
+            const unsigned w0 = __ldg(src);
+            x0 = make_float2((float)(short)(w0 & 0xffffu), (float)(short)(w0 >> 16));
+            if (has1) { const unsigned w1 = __ldg(src + 256); x1 = make_float2((float)(short)(w1 & 0xffffu), (float)(short)(w1 >> 16)); }
+        } else {
+            const float2 *src = reinterpret_cast<const float2 *>(samples) + s0 + lane + 32 * i;
+            x0 = __ldg(src);
+            if (has1) x1 = __ldg(src + 256);
+        }
+        Are[lane + 32 * i] = make_float2(x0.x, x1.x);
+        Aim[lane + 32 * i] = make_float2(x0.y, x1.y);
+        tot.x += cnorm2(x0); tot.y += cnorm2(x1);              // Parseval: sum_k |X_k|^2 = 256 sum_n |x_n|^2
+    }
+    __syncwarp();
+    stockham_pass_pc<8, false>(Are, Aim, Bre, Bim, 256, 1, P.tw_t2, lane, 32);
+    __syncwarp();
+    stockham_pass_pc<8, false, true>(Bre, Bim, Are, Aim, 256, 8, P.tw_t2, lane, 32);   // twiddle index <= 7*7*4 < 256
+    __syncwarp();
+    // last pass (radix 4, ns = 64), only butterflies that feed a masked bin (see t2sin_block_rel)
+    float2 sine = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int jj = 0; jj < 2; jj++) {
+        const int j = lane + 32 * jj;
+        float mk[4];
+        bool any = false;
+#pragma unroll
+        for (int q = 0; q < 4; q++) { mk[q] = __ldg(&P.t2_mask[j + 64 * q]); any |= mk[q] != 0.f; }
+        if (any) {
+            pc v[4];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                v[q].re = Are[j + 64 * q]; v[q].im = Aim[j + 64 * q];
+                if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_t2[q * j]));
+            }
+            dft4<false>(v);
+#pragma unroll
+            for (int q = 0; q < 4; q++) sine = p_fma(p_bcast(mk[q]), p_fma(v[q].re, v[q].re, p_mul(v[q].im, v[q].im)), sine);
+        }
+    }
+    tot = warp_sum(tot);
+    sine = warp_sum(sine);
+    if (lane == 0) {
+        const float t0 = tot.x * 256.0f, t1 = tot.y * 256.0f;
+        float r0 = sine.x / t0, r1 = sine.y / t1;
+        if (t0 == 0.f || r0 != r0) r0 = 0.f;                   // Frame.hpp:132-138 `continue`
+        if (t1 == 0.f || r1 != r1) r1 = 0.f;
+        rel_out[blk] = r0;
+        if (has1) rel_out[blk + 1] = r1;
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // preamble_corr_kernel: PREAMBLE_FORM::find_corr / find_preamble (Frame.cpp:297-378).
 // One CTA per candidate start.  The window (cor_size + pr_sin_len samples) and the matched filter
@@ -312,6 +382,98 @@ preamble_corr_kernel(const Params P, const void *__restrict__ samples, long long
             if (en[q] > 1.0f) {                           // Frame.cpp:319
                 cval = sqrtf(cnorm2(acc[q]) / en[q]);
                 if (cnorm2(acc[q]) > lvl2 * en[q]) atomicMin(&first, i);   // Frame.cpp:364
+            }
+            if (cor_out != nullptr) cor_out[(size_t)c * NC + i] = cval;
+        }
+    }
+    __syncthreads();
+    if (first_idx != nullptr && tid == 0) first_idx[c] = first == 0x7fffffff ? -10 : st + first;
+}
+
+// ------------------------------------------------------------------------------------------------
+// The matched-filter core with 4 CONSECUTIVE lags per thread (lags 4t .. 4t+3): the window is held transposed in 4
+// planes, sample idx at win4[(idx & 3) * plane + (idx >> 2)], so that the one new sample a thread needs per filter
+// tap is at consecutive addresses across threads (conflict-free), and each tap costs 2 shared-memory loads for
+// 4 lags instead of 5.  L (filter length) must be a multiple of 4; plane >= (4 t_max + L + 3) / 4 + 1.
+// ------------------------------------------------------------------------------------------------
+COFDM_DEV void corr4_lags(const float2 *win4, int plane, const float2 *hf, int L, int t, float2 (&a)[4], float (&e)[4]) {
+    const float2 *w0 = win4, *w1 = win4 + plane, *w2 = win4 + 2 * plane, *w3 = win4 + 3 * plane;
+    float2 x0 = w0[t], x1 = w1[t], x2 = w2[t], x3 = w3[t];
+    float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
+    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+    for (int j = 0; j < L; j += 4) {
+        const int k = t + (j >> 2) + 1;
+        float2 h = hf[j];                                      // Frame.cpp:320-321 (h is already conjugated)
+        cmac(a0, x0, h); cmac(a1, x1, h); cmac(a2, x2, h); cmac(a3, x3, h);
+        e0 += cnorm2(x0); e1 += cnorm2(x1); e2 += cnorm2(x2); e3 += cnorm2(x3);   // Frame.cpp:305-309,327-333
+        x0 = w0[k];
+        h = hf[j + 1];
+        cmac(a0, x1, h); cmac(a1, x2, h); cmac(a2, x3, h); cmac(a3, x0, h);
+        e0 += cnorm2(x1); e1 += cnorm2(x2); e2 += cnorm2(x3); e3 += cnorm2(x0);
+        x1 = w1[k];
+        h = hf[j + 2];
+        cmac(a0, x2, h); cmac(a1, x3, h); cmac(a2, x0, h); cmac(a3, x1, h);
+        e0 += cnorm2(x2); e1 += cnorm2(x3); e2 += cnorm2(x0); e3 += cnorm2(x1);
+        x2 = w2[k];
+        h = hf[j + 3];
+        cmac(a0, x3, h); cmac(a1, x0, h); cmac(a2, x1, h); cmac(a3, x2, h);
+        e0 += cnorm2(x3); e1 += cnorm2(x0); e2 += cnorm2(x1); e3 += cnorm2(x2);
+        x3 = w3[k];
+    }
+    a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
+    e[0] = e0; e[1] = e1; e[2] = e2; e[3] = e3;
+}
+
+// preamble_corr4_kernel: the same search as preamble_corr_kernel on the 4-lags-per-thread core (needs pr_sin_len and
+// the lag count to be multiples of 4).  One CTA per candidate start.
+constexpr int kPc4Threads = 160;
+COFDM_HD size_t preamble_corr4_smem_bytes(int cor_size, int pr_sin_len) {
+    return (4 * ((size_t)(cor_size + pr_sin_len) / 4 + 4) + (size_t)pr_sin_len) * sizeof(float2);
+}
+template <int FMT>
+__global__ void __launch_bounds__(kPc4Threads)
+preamble_corr4_kernel(const Params P, const void *__restrict__ samples, long long n_samples,
+                      const long long *__restrict__ starts, int n_starts,
+                      float *__restrict__ cor_out /* [n_starts][cor_size] or null */,
+                      long long *__restrict__ first_idx /* [n_starts] or null */) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int c = blockIdx.x;
+    if (c >= n_starts) return;
+    const int tid = threadIdx.x;
+    const int L = P.pr_sin_len, NC = P.cor_size, WN = NC + L, plane = WN / 4 + 4;
+    float2 *win4 = reinterpret_cast<float2 *>(smem_raw);
+    float2 *hf = win4 + 4 * (size_t)plane;
+    __shared__ int first;
+    if (tid == 0) first = 0x7fffffff;
+    const long long st = starts[c];
+    for (int i = tid; i < 4 * plane; i += kPc4Threads) {
+        const int q = i / plane, k = i - q * plane, idx = 4 * k + q;
+        const long long g = st + idx;
+        float2 x = make_float2(0.f, 0.f);
+        if (idx < WN && g >= 0 && g < n_samples) {
+            if (FMT == kCI16) {
+                const unsigned w = __ldg(reinterpret_cast<const unsigned *>(samples) + g);
+                x = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+            } else {
+                x = __ldg(reinterpret_cast<const float2 *>(samples) + g);
+            }
+        }
+        win4[i] = x;
+    }
+    for (int i = tid; i < L; i += kPc4Threads) hf[i] = __ldg(&P.matched[i]);
+    __syncthreads();
+    const float lvl2 = P.pr_level * P.pr_level;
+    for (int t = tid; 4 * t < NC; t += kPc4Threads) {
+        float2 a[4];
+        float e[4];
+        corr4_lags(win4, plane, hf, L, t, a, e);
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int i = 4 * t + q;
+            float cval = 0.f;
+            if (e[q] > 1.0f) {                                 // Frame.cpp:319
+                cval = sqrtf(cnorm2(a[q]) / e[q]);
+                if (cnorm2(a[q]) > lvl2 * e[q]) atomicMin(&first, i);   // Frame.cpp:364
             }
             if (cor_out != nullptr) cor_out[(size_t)c * NC + i] = cval;
         }

@@ -120,35 +120,14 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
             }
             __syncthreads();
             if (4 * tid < NC) {
-                const float2 *w0 = win4, *w1 = win4 + plane, *w2 = win4 + 2 * plane, *w3 = win4 + 3 * plane;
-                float2 x0 = w0[tid], x1 = w1[tid], x2 = w2[tid], x3 = w3[tid];
-                float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-                float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
-                for (int j = 0; j < L; j += 4) {
-                    const int k = tid + (j >> 2) + 1;
-                    float2 h = hf[j];                                      // Frame.cpp:320-321 (h is already conjugated)
-                    cmac(a0, x0, h); cmac(a1, x1, h); cmac(a2, x2, h); cmac(a3, x3, h);
-                    e0 += cnorm2(x0); e1 += cnorm2(x1); e2 += cnorm2(x2); e3 += cnorm2(x3);   // Frame.cpp:305-309,327-333
-                    x0 = w0[k];
-                    h = hf[j + 1];
-                    cmac(a0, x1, h); cmac(a1, x2, h); cmac(a2, x3, h); cmac(a3, x0, h);
-                    e0 += cnorm2(x1); e1 += cnorm2(x2); e2 += cnorm2(x3); e3 += cnorm2(x0);
-                    x1 = w1[k];
-                    h = hf[j + 2];
-                    cmac(a0, x2, h); cmac(a1, x3, h); cmac(a2, x0, h); cmac(a3, x1, h);
-                    e0 += cnorm2(x2); e1 += cnorm2(x3); e2 += cnorm2(x0); e3 += cnorm2(x1);
-                    x2 = w2[k];
-                    h = hf[j + 3];
-                    cmac(a0, x3, h); cmac(a1, x0, h); cmac(a2, x1, h); cmac(a3, x2, h);
-                    e0 += cnorm2(x3); e1 += cnorm2(x0); e2 += cnorm2(x1); e3 += cnorm2(x2);
-                    x3 = w3[k];
-                }
+                float2 a[4];
+                float e[4];
+                corr4_lags(win4, plane, hf, L, tid, a, e);
                 const float lvl2 = P.pr_level * P.pr_level;
                 int best = 0x7fffffff;                                     // Frame.cpp:319,364: first lag with c_i > pr_level
-                if (e3 > 1.0f && cnorm2(a3) > lvl2 * e3) best = 4 * tid + 3;
-                if (e2 > 1.0f && cnorm2(a2) > lvl2 * e2) best = 4 * tid + 2;
-                if (e1 > 1.0f && cnorm2(a1) > lvl2 * e1) best = 4 * tid + 1;
-                if (e0 > 1.0f && cnorm2(a0) > lvl2 * e0) best = 4 * tid;
+#pragma unroll
+                for (int q = 3; q >= 0; q--)
+                    if (e[q] > 1.0f && cnorm2(a[q]) > lvl2 * e[q]) best = 4 * tid + q;
                 if (best != 0x7fffffff) atomicMin(first, best);
             }
             __syncthreads();

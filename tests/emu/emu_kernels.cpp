@@ -39,6 +39,8 @@ int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
 static int g_emu_split = 0;
 void emu_set_split(int on) { g_emu_split = on; }
+static int g_emu_pc_plain = 0;
+void emu_set_pc_plain(int on) { g_emu_pc_plain = on; }
 static int g_emu_tx_bulk = 1;
 void emu_set_tx_bulk(int on) { g_emu_tx_bulk = on; }
 
@@ -134,6 +136,12 @@ int emu_t2sin_metric(void *hv, const void *samples, int fmt, long long start, lo
     auto *h = (EmuHandle *)hv;
     const Params P = h->P;
     if (P.t2sin_size != 256) return -1;
+    if (n_blocks >= 64) {                            // as launch_t2 does: two blocks per warp
+        const unsigned g2 = (unsigned)(((n_blocks + 1) / 2 + kT2PairWarps - 1) / kT2PairWarps);
+        if (fmt == kCI16) emu::launch(dim3(g2), dim3(32 * kT2PairWarps), 0, [&] { t2sin_metric2_kernel<kCI16>(P, samples, start, n_blocks, rel); });
+        else emu::launch(dim3(g2), dim3(32 * kT2PairWarps), 0, [&] { t2sin_metric2_kernel<kCF32>(P, samples, start, n_blocks, rel); });
+        return 0;
+    }
     const unsigned grid = (unsigned)((n_blocks + kT2WarpsPerCta - 1) / kT2WarpsPerCta);
     if (fmt == kCI16) emu::launch(dim3(grid), dim3(32 * kT2WarpsPerCta), 0, [&] { t2sin_metric_kernel<kCI16>(P, samples, start, n_blocks, rel); });
     else emu::launch(dim3(grid), dim3(32 * kT2WarpsPerCta), 0, [&] { t2sin_metric_kernel<kCF32>(P, samples, start, n_blocks, rel); });
@@ -144,6 +152,12 @@ int emu_preamble_corr(void *hv, const void *samples, int fmt, long long n_sample
                       int n_starts, float *cor, long long *first) {
     auto *h = (EmuHandle *)hv;
     const Params P = h->P;
+    if ((P.pr_sin_len % 4) == 0 && (P.cor_size % 4) == 0 && !g_emu_pc_plain) {   // as launch_pc does
+        const size_t sm4 = preamble_corr4_smem_bytes(P.cor_size, P.pr_sin_len);
+        if (fmt == kCI16) emu::launch(dim3(n_starts), dim3(kPc4Threads), sm4, [&] { preamble_corr4_kernel<kCI16>(P, samples, n_samples, starts, n_starts, cor, first); });
+        else emu::launch(dim3(n_starts), dim3(kPc4Threads), sm4, [&] { preamble_corr4_kernel<kCF32>(P, samples, n_samples, starts, n_starts, cor, first); });
+        return 0;
+    }
     const size_t sm = (size_t)(P.cor_size + 2 * P.pr_sin_len) * sizeof(float2);
     if (fmt == kCI16) emu::launch(dim3(n_starts), dim3(kPcThreads), sm, [&] { preamble_corr_kernel<kCI16>(P, samples, n_samples, starts, n_starts, cor, first); });
     else emu::launch(dim3(n_starts), dim3(kPcThreads), sm, [&] { preamble_corr_kernel<kCF32>(P, samples, n_samples, starts, n_starts, cor, first); });

@@ -58,6 +58,11 @@ class EmuModem:
         """1: acquire + demod kernels (the product default), 0: the single fused kernel"""
         self.lib.emu_set_split(int(on))
 
+    def set_pc_plain(self, on):
+        """1: the one-lag-per-slot preamble search kernel (fallback for odd sizes), 0: the 4-lags-per-thread one"""
+        self.lib.emu_set_pc_plain.argtypes = [C.c_int]
+        self.lib.emu_set_pc_plain(int(on))
+
     def set_tx_bulk(self, on):
         """1: tx symbols leave as TMA bulk stores of linear images (the product default), 0: register stores"""
         self.lib.emu_set_tx_bulk.argtypes = [C.c_int]

@@ -95,12 +95,21 @@ def test_sync_kernels_on_reference_capture(emu, port, golden_capture):
         want = o.t2sin_corr(cap)
         assert np.nonzero(rel > 0.8)[0].tolist() == np.nonzero(want)[0].tolist() == [42, 74]
         assert np.abs(rel[want > 0] - want[want > 0]).max() < 1e-6
+        # fewer than 64 blocks take the one-block-per-warp kernel, an odd count leaves the last warp half full
+        assert np.abs(emu[4].t2sin_metric(x[:63 * 256]) - rel[:63]).max() < 1e-6
+        assert np.abs(emu[4].t2sin_metric(x[:75 * 256]) - rel[:75]).max() < 1e-6
         assert emu[4].find_t2sin(x, 0) == 10752 and emu[4].find_t2sin(x, 11000) == o.find_t2sin(cap, 11000)
         starts = np.array([10752, 18976, 5000, 0])
         first, cor = emu[4].preamble_search(x, starts, want_cor=True)
         assert first.tolist() == [o.find_preamble(cap, int(p)) for p in starts] == [11039, 19301, -10, -10]
         for p, c in zip(starts, cor):
             assert np.abs(c - o.find_corr(cap, int(p))).max() < 1e-6
+        emu[4].set_pc_plain(1)                       # the fallback kernel for sizes that are not multiples of 4
+        try:
+            first2, cor2 = emu[4].preamble_search(x, starts, want_cor=True)
+        finally:
+            emu[4].set_pc_plain(0)
+        assert first2.tolist() == first.tolist() and np.abs(cor2 - cor).max() < 1e-6
 
 
 def test_rx_phase_unwrap_slow_path(emu, port):
