@@ -33,8 +33,9 @@ COFDM_HD size_t tx512_smem_bytes(int num_symb, int bytes_per_frame) {
     return (size_t)((num_symb + 1) / 2) * kPairSlots * sizeof(float2) + (size_t)((bytes_per_frame + 15) & ~15);
 }
 
+// wide: the frame buffer is 16-byte aligned (one 16- / 8-byte store for the pair); otherwise one store per sample
 template <int FMT>
-COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/, float2 a, float2 b, float mult) {
+COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/, float2 a, float2 b, float mult, bool wide) {
     if (FMT == kCI16) {
         // Frame.cpp:252: int16(trunc(re*mult)), int16(trunc(im*mult))
         short2 sa = make_short2((short)__float2int_rz(a.x * mult), (short)__float2int_rz(a.y * mult));
@@ -42,9 +43,11 @@ COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/,
         uint2 pk;
         pk.x = ((unsigned)(unsigned short)sa.x) | ((unsigned)(unsigned short)sa.y << 16);
         pk.y = ((unsigned)(unsigned short)sb.x) | ((unsigned)(unsigned short)sb.y << 16);
-        reinterpret_cast<uint2 *>(frame_out)[idx >> 1] = pk;
+        if (wide) reinterpret_cast<uint2 *>(frame_out)[idx >> 1] = pk;
+        else { reinterpret_cast<unsigned *>(frame_out)[idx] = pk.x; reinterpret_cast<unsigned *>(frame_out)[idx + 1] = pk.y; }
     } else {
-        reinterpret_cast<float4 *>(frame_out)[idx >> 1] = make_float4(a.x, a.y, b.x, b.y);
+        if (wide) reinterpret_cast<float4 *>(frame_out)[idx >> 1] = make_float4(a.x, a.y, b.x, b.y);
+        else { reinterpret_cast<float2 *>(frame_out)[idx] = a; reinterpret_cast<float2 *>(frame_out)[idx + 1] = b; }
     }
 }
 
@@ -82,6 +85,7 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
     uint8_t *pl = reinterpret_cast<uint8_t *>(W + (size_t)npair * kPairSlots);
     const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
     char *fout = reinterpret_cast<char *>(frames) + (size_t)frame * P.frame_len * sample_bytes;
+    const bool wide = (reinterpret_cast<uintptr_t>(fout) & 15) == 0;      // every pair store of this frame is then aligned
 
     if (warp == 2 * npair) {
         // T2SIN tone + preamble are constants of the configuration (Frame.cpp:228-229)
@@ -89,7 +93,7 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
         for (int i = 2 * lane; i < n_const; i += 64) {
             const float2 a = i < P.t2sin_size ? __ldg(&P.t2_tone[i]) : __ldg(&P.preamble_td[i - P.t2sin_size]);
             const float2 b = i + 1 < P.t2sin_size ? __ldg(&P.t2_tone[i + 1]) : __ldg(&P.preamble_td[i + 1 - P.t2sin_size]);
-            store_sample_pair<FMT>(fout, i, a, b, P.mult);
+            store_sample_pair<FMT>(fout, i, a, b, P.mult, wide);
         }
         return;
     }
@@ -164,11 +168,11 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
         const float4 ii = *reinterpret_cast<const float4 *>(&Wim[spec_slot(n)]);
         const float2 a0 = make_float2(rr.x * sc, ii.x * sc), a1 = make_float2(rr.z * sc, ii.z * sc);
         const float2 b0 = make_float2(rr.y * sc, ii.y * sc), b1 = make_float2(rr.w * sc, ii.w * sc);
-        store_sample_pair<FMT>(fout, baseA + 128 + n, a0, a1, P.mult);
-        if (n >= 384) store_sample_pair<FMT>(fout, baseA + n - 384, a0, a1, P.mult);
+        store_sample_pair<FMT>(fout, baseA + 128 + n, a0, a1, P.mult, wide);
+        if (n >= 384) store_sample_pair<FMT>(fout, baseA + n - 384, a0, a1, P.mult, wide);
         if (hasB) {
-            store_sample_pair<FMT>(fout, baseB + 128 + n, b0, b1, P.mult);
-            if (n >= 384) store_sample_pair<FMT>(fout, baseB + n - 384, b0, b1, P.mult);
+            store_sample_pair<FMT>(fout, baseB + 128 + n, b0, b1, P.mult, wide);
+            if (n >= 384) store_sample_pair<FMT>(fout, baseB + n - 384, b0, b1, P.mult, wide);
         }
     }
 }

@@ -78,8 +78,9 @@ def rx_stream_sharded(run, capture_i16, sizes, world):
     return merge_shards(shards, sizes)
 
 
-def rx_stream_distributed(modem, capture_i16):
-    """torchrun entry: every rank receives its slice of the capture on its own GPU, rank 0 merges.
+def rx_stream_distributed(modem, capture_i16, shards=1):
+    """torchrun entry: every rank receives its slice of the capture (a numpy array, or a torch tensor already on
+    its GPU) on its own GPU -- itself cut into `shards` ranges scanned concurrently -- and rank 0 merges.
     The only communication is the gather of the per-rank frame lists.  Returns (positions, bytes, unmerged)
     on rank 0 and (None, None, None) elsewhere."""
     import torch.distributed as dist
@@ -87,7 +88,7 @@ def rx_stream_distributed(modem, capture_i16):
     rank = dist.get_rank() if dist.is_initialized() else 0
     s = modem.sizes
     s0, s1, b0, b1 = shard_slice(capture_i16.shape[0], s, rank, world)
-    pos, by = modem.rx_stream(capture_i16[s0:s1])
+    pos, by = modem.rx_stream(capture_i16[s0:s1], shards=shards)
     mine = (np.asarray(pos) + s0, by, b0, b1)
     if world == 1:
         return merge_shards([mine], s)

@@ -156,6 +156,36 @@ def test_edge_cases(modems):
     assert m.preamble_search(np.zeros((4096, 2), np.int16), np.array([0], dtype=np.int64)).tolist() == [-10]
 
 
+def test_alignment_variants_agree(modems, port):
+    """Aligned buffers take the TMA paths (bulk loads of cf32 or raw int16 records, bulk stores of symbol images);
+    records cut at an arbitrary sample and frame buffers that are not 16-byte aligned take plain loads / register
+    stores.  Same bytes, same frames, for 1, 2 and 5 frames (the acquire kernel pairs frames)."""
+    m = modems[4]
+    m.use_torch_stream()
+    s = m.sizes
+    pay, rec = pc.impaired_records(port[4], 5, seed=21)                  # int16 [5, rx_len, 2]
+    want = np.stack([port[4].rx_aligned(pc.cplx(r))["bytes"] for r in rec])
+    for fmt in ("ci16", "cf32"):
+        for n in (1, 2, 5):
+            for shift in (0, 1, 2, 3):                                   # samples: 4 or 8 bytes each
+                if fmt == "ci16":
+                    big = torch.zeros((n * s.rx_len + 8, 2), dtype=torch.int16, device="cuda")
+                    big[shift:shift + n * s.rx_len] = torch.from_numpy(rec[:n].reshape(-1, 2)).cuda()
+                else:
+                    big = torch.zeros(n * s.rx_len + 8, dtype=torch.complex64, device="cuda")
+                    big[shift:shift + n * s.rx_len] = torch.from_numpy(pc.cplx(rec[:n]).reshape(-1).astype(np.complex64)).cuda()
+                out, _ = m.rx_aligned_batch(big, n_frames=n, frame_stride=s.rx_len, offset=shift)
+                assert np.array_equal(out.cpu().numpy(), want[:n]), (fmt, n, shift)
+    d_pay = torch.from_numpy(pay).cuda()
+    for fmt, dt, per in ((cb.CF32, torch.complex64, 1), (cb.CI16, torch.int16, 2)):
+        ref = m.tx_batch(d_pay, fmt)                                     # torch allocation: aligned -> bulk stores
+        flat = torch.zeros(ref.numel() + 4 * per, dtype=dt, device="cuda")
+        for shift in (1, 2):                                             # samples
+            view = flat[shift * per:shift * per + ref.numel()].view(ref.shape)
+            m.tx_batch(d_pay, fmt, out=view)
+            assert torch.equal(view, ref), (fmt, shift)
+
+
 @pytest.mark.parametrize("mt", [2, 4])
 def test_round_trip_at_scale(modems, mt):
     """size-independent property at a benchmark-like size: tx -> int16 wire -> rx returns every byte;
