@@ -32,39 +32,43 @@ def shard_slice(n_samples, sizes, rank, world, overlap_blocks=1):
 def merge_shards(shards, sizes):
     """shards: list over ranks (in order) of (positions [absolute sample indices], bytes [n, usefull_size],
     first_block, last_block_exclusive).  Returns (positions, bytes) of the whole capture, identical to one
-    sequential pass, plus the number of boundaries that did not re-synchronise inside the overlap (should be 0)."""
+    sequential pass, plus the number of boundaries that did not re-synchronise inside the overlap (should be 0).
+    `bytes` may be any per-frame rows (payloads, or tags telling which rank holds the payload)."""
     blk = block_samples(sizes)
-    out_pos, out_bytes, unmerged = [], [], 0
-    carry_pos, carry_bytes = np.zeros(0, np.int64), None          # the previous rank's frames beyond its own range
+    out_pos, out_rows, unmerged = [], [], 0
+    carry_pos, carry_rows = np.zeros(0, np.int64), None          # the previous rank's frames beyond its own range
+    width, dtype = sizes.usefull_size, np.uint8
     for pos, by, b0, b1 in shards:
         pos = np.asarray(pos, dtype=np.int64)
+        by = np.asarray(by)
+        if by.ndim == 2:
+            width, dtype = by.shape[1], by.dtype
         start = 0
         if len(carry_pos):
             # follow the previous (true) chain until it meets this rank's chain
-            common = np.intersect1d(carry_pos, pos)
-            if len(common):
-                first = common[0]
-                k = int(np.nonzero(carry_pos == first)[0][0])
-                out_pos.extend(carry_pos[:k].tolist())
-                out_bytes.extend(carry_bytes[:k])
-                start = int(np.nonzero(pos == first)[0][0])
+            hit = np.nonzero(np.isin(carry_pos, pos, assume_unique=True))[0]
+            if len(hit):
+                k = int(hit[0])
+                out_pos.append(carry_pos[:k])
+                out_rows.append(carry_rows[:k])
+                start = int(np.searchsorted(pos, carry_pos[k]))
             else:
                 unmerged += 1
-                out_pos.extend(carry_pos.tolist())
-                out_bytes.extend(carry_bytes)
+                out_pos.append(carry_pos)
+                out_rows.append(carry_rows)
                 start = int(np.searchsorted(pos, carry_pos[-1] + 1))
         own_end = b1 * blk
-        own = np.nonzero(pos[start:] < own_end)[0]
-        n_own = start + (int(own[-1]) + 1 if len(own) else 0)
         # a frame is owned by the range that contains its preamble; the rest of the list is carried over
-        out_pos.extend(pos[start:n_own].tolist())
-        out_bytes.extend(by[start:n_own])
-        carry_pos, carry_bytes = pos[n_own:], by[n_own:]
-    out_pos.extend(carry_pos.tolist())
-    if carry_bytes is not None:
-        out_bytes.extend(carry_bytes)
-    b = np.stack(out_bytes) if out_bytes else np.zeros((0, sizes.usefull_size), np.uint8)
-    return np.array(out_pos, dtype=np.int64), b, unmerged
+        n_own = max(start, int(np.searchsorted(pos, own_end)))    # positions are increasing
+        out_pos.append(pos[start:n_own])
+        out_rows.append(by[start:n_own])
+        carry_pos, carry_rows = pos[n_own:], by[n_own:]
+    out_pos.append(carry_pos)
+    if carry_rows is not None:
+        out_rows.append(carry_rows)
+    rows = [r for r in out_rows if len(r)]
+    b = np.concatenate(rows) if rows else np.zeros((0, width), dtype)
+    return np.concatenate(out_pos) if out_pos else np.zeros(0, np.int64), b, unmerged
 
 
 def rx_stream_sharded(run, capture_i16, sizes, world):
