@@ -19,7 +19,7 @@
 
 namespace cofdmk {
 
-constexpr int kGenThreads = 256;
+constexpr int kGenThreads = 512;
 
 // per-frame scalars exchanged between the generic kernels (device memory)
 struct GenFrame {

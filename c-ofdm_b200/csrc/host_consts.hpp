@@ -270,7 +270,7 @@ inline HostTables build_tables(const ConfigMap &cfg) {
     // radix schedules for the generic path (Stockham passes of radix 16/8/4/2/5)
     auto schedule = [](int n, int *rad, int &nr) {
         nr = 0;
-        for (int r : {16, 8, 4, 2, 5})
+        for (int r : {8, 4, 2, 5})          // radix 8 keeps twice as many threads busy per pass as radix 16 (measured faster)
             while (n % r == 0 && nr < 8 && n > 1) { rad[nr++] = r; n /= r; }
         return n == 1;
     };
