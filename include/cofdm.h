@@ -108,7 +108,8 @@ int cofdm_demod(cofdm_t *h, int mod_type, const float *points, size_t n_points, 
 
 /* FRAME_FORM::write + get / get_int16  OFDM/Frame.cpp:235-256 (OFDM_FORM::write :185-198,
  * FFT_FORM::write :54-70), batched: payload[n_frames*usefull_size] -> frames[n_frames*output_size]
- * complete frames [T2SIN | preamble | message] in `fmt`. */
+ * complete frames [T2SIN | preamble | message] in `fmt`.  Any sample-aligned `frames` pointer works; a 16-byte
+ * aligned one (cudaMalloc, torch) lets every symbol leave the SM as one TMA bulk store. */
 int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *frames, int fmt, int space);
 
 /* The aligned-frame receive chain of main.cpp:60-80 / rx.cpp:200-220, batched and fused:
@@ -118,7 +119,9 @@ int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *fr
  * samples: n_frames records of rx_len samples starting at the preamble (what the apps copy to
  * buf + t2sin.size, rx.cpp:192-196), consecutive records frame_stride samples apart
  * (frame_stride >= rx_len; pass output_size with samples+t2sin_size to read whole frames in place).
- * bytes[n_frames*usefull_size].  *ambiguous as in cofdm_demod. */
+ * bytes[n_frames*usefull_size] (4-byte aligned).  *ambiguous as in cofdm_demod.  Records may start at any sample;
+ * when `samples` and the record stride are 16-byte aligned the symbols are staged by TMA bulk copies (cf32, or raw
+ * int16 widened when read), otherwise by plain loads. */
 int cofdm_rx_aligned_batch(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
                            uint8_t *bytes, unsigned long long *ambiguous, const cofdm_rx_taps *taps, int space);
 
