@@ -221,12 +221,13 @@ rx_acquire512x2_kernel(const Params P, const void *__restrict__ samples, long lo
                     if (mv.x > bestA) { bestA = mv.x; iA = ks; }
                     if (mv.y > bestB) { bestB = mv.y; iB = ks; }
                 }
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    const float oa = __shfl_xor_sync(0xffffffffu, bestA, o), ob = __shfl_xor_sync(0xffffffffu, bestB, o);
-                    const int ja = __shfl_xor_sync(0xffffffffu, iA, o), jb = __shfl_xor_sync(0xffffffffu, iB, o);
-                    if (oa > bestA || (oa == bestA && ja < iA)) { bestA = oa; iA = ja; }
-                    if (ob > bestB || (ob == bestB && jb < iB)) { bestB = ob; iB = jb; }
+                // warp arg-max by two hardware reductions per frame (redux.sync): the magnitudes are non-negative floats, so
+                // their bit patterns order like unsigned integers; among the lanes that hold the maximum the smallest index wins
+                {
+                    const unsigned ba = bestA < 0.f ? 0u : __float_as_uint(bestA), bb = bestB < 0.f ? 0u : __float_as_uint(bestB);   // a lane without an entry
+                    const unsigned ma = __reduce_max_sync(0xffffffffu, ba), mb = __reduce_max_sync(0xffffffffu, bb);
+                    iA = __reduce_min_sync(0xffffffffu, ba == ma ? iA : 0x7fffffff);
+                    iB = __reduce_min_sync(0xffffffffu, bb == mb ? iB : 0x7fffffff);
                 }
                 if (lane == 0) { M->amax[0][wi] = iA; M->amax[1][wi] = iB; }
             }

@@ -115,6 +115,16 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return r;
 }
 
+static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
+static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
+    for (int o = 16; o > 0; o >>= 1) v = std::max(v, emu::shfl_idx(v, (int)(emu::t_tid & 31) ^ o));
+    return v;
+}
+static inline int __reduce_min_sync(unsigned, int v) {
+    for (int o = 16; o > 0; o >>= 1) v = std::min(v, emu::shfl_idx(v, (int)(emu::t_tid & 31) ^ o));
+    return v;
+}
+
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
 static inline int atomicAdd(int *p, int v) { return __atomic_fetch_add(p, v, __ATOMIC_SEQ_CST); }
