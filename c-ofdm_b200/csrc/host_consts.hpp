@@ -169,6 +169,8 @@ inline HostTables build_tables(const ConfigMap &cfg) {
         p.pf_pilot_w = int(p.pf_size * rel_pilot_w);
         p.pf_border0 = int((1.0 - rel_bw - rel_pilot_w) / 2.0 * p.pf_size);
         p.pf_den = NP * p.pf_size;
+        p.pf_bins512 = 512.0f / (float)p.pf_den;
+        p.inv_pilot_norm = 1.0f / ((float)(p.num_symb * NP) * p.pilot_ampl);
     }
 
     // sub-carrier map (Frame.cpp:31-44): pilot follows its segment in the positive half, precedes it

@@ -33,6 +33,8 @@ struct Params {
     // shift = (sum_argmax / num_pilot_subc - pf_size/2) / pf_size  ==  pf_num / pf_den cycles/sample,
     // pf_num = sum_argmax - num_pilot_subc*(pf_size/2), pf_den = num_pilot_subc*pf_size
     int pf_den;
+    float pf_bins512;      // 512 / pf_den: whole fft-512 bins per unit of the coarse-shift numerator
+    float inv_pilot_norm;  // 1 / (num_symb * num_pilot_subc * pilot_ampl): pilot amplitude normaliser (Frame.cpp:76-80)
     // ---- radix schedules of the generic (any-size) path: products equal fft_size resp. pf_size ----
     int fft_nr, fft_radix[8];
     int pf_nr, pf_radix[8];

@@ -55,8 +55,9 @@ struct RxMisc {
     uint64_t mbar[kRxMaxSym + 1];
     float4 qtab[kRxMaxSym][8];       // per FFT warp: Q^r (r<8) -- (reA, reB, imA, imB)
     float4 wtab[kRxMaxSym][8];       // per FFT warp: equaliser coefficient per segment (reA, reB, imA, imB)
+    float4 pabsm4[kRxMaxSym / 4];    // sum |pilot| per MESSAGE symbol (index s - 1), zero beyond the last one
     float2 pilots[kRxMaxSym][8];     // pilot bins per symbol (shifted bins, before the (-j)^m factor)
-    float pabs[kRxMaxSym];           // sum |pilot| per symbol
+    float pabs0;                     // sum |pilot| of the preamble (chan_char tap of the sync-less form)
     float theta_t[kRxMaxSym];        // Arg(C_s) in turns
     int mshift[kRxMaxSym];           // m_s
     int amax[8];
@@ -189,6 +190,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     uint8_t *symbuf = reinterpret_cast<uint8_t *>(MODE == 2 ? SA : SB + 640);
     RxMisc *M = reinterpret_cast<RxMisc *>(symbuf + (size_t)npair * 512);
 
+    if (tid < kRxMaxSym) reinterpret_cast<float *>(M->pabsm4)[tid] = 0.f;   // ordered before the writes by barrier #2
     const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
     const char *frame_src = reinterpret_cast<const char *>(samples) + (size_t)frame * (size_t)frame_stride * sample_bytes;
     const bool is_coarse = MODE != 2 && warp >= 2 * npair;
@@ -397,7 +399,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     int mA = 0, mB = 0;
     if (!is_coarse) {
         // m_s and the reference's phi_s (Frame.hpp:254): phi_t = theta_t - 512 shift + m_s in (-0.5, 0.5]
-        const float sh512 = (float)kc * (512.0f / (float)P.pf_den);
+        const float sh512 = (float)kc * P.pf_bins512;
         mA = (int)ceilf(-(thA - sh512) - 0.5f);
         mB = (int)ceilf(-(thB - sh512) - 0.5f);
         if (MODE == 2 && warp == 1 && lane < 8) {
@@ -423,7 +425,11 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             }
             pa = warp_sum(pa);
             pb = warp_sum(pb);
-            if (lane == 0) { M->pabs[A] = pa; if (hasB) M->pabs[B] = pb; }
+            if (lane == 0) {
+                float *pm = reinterpret_cast<float *>(M->pabsm4);
+                if (A >= 1) pm[A - 1] = pa; else M->pabs0 = pa;
+                if (hasB) pm[B - 1] = pb;
+            }
         }
     }
     if (MODE == 2) {
@@ -436,7 +442,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         // theta = arg sum_{i<640} conj(ref[i]) y[i]; body part by Parseval:
         //   sum_n conj(r[n]) y[n] = (1/sqrt 512) sum_k conj(R[k]) Y[k], R = tx grid of the preamble,
         //   Y[k] = (-j)^m0 X'[k + m0] the true spectrum of the preamble (symbol 0 has no other constant phase)
-        const int m0 = (int)ceilf(-(M->theta_t[0] - (float)kc * (512.0f / (float)P.pf_den)) - 0.5f);
+        const int m0 = (int)ceilf(-(M->theta_t[0] - (float)kc * P.pf_bins512) - 0.5f);
         const float2 *P0re = X, *P0im = X + kFft512Slots;             // planes of team 0, symbol A = low half
         const int gi = 32 * warp + lane;
         float2 d0, z;
@@ -544,9 +550,12 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
     __syncthreads();                               // #3: pilots, a, b, theta are ready
 
     const double la = M->a, lb = M->b;
-    float g = 0.f;                                 // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
-    for (int s = 1; s < nsym_all; s++) g += M->pabs[s];
-    g /= (float)((nsym_all - 1) * 8) * P.pilot_ampl;
+    float g;                                       // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
+    {
+        const float4 p0 = M->pabsm4[0], p1 = M->pabsm4[1], p2 = M->pabsm4[2], p3 = M->pabsm4[3];   // zero beyond the last symbol
+        g = (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w))) + (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
+        g *= P.inv_pilot_norm;
+    }
     const float2 rot_theta = M->rot_theta;
 
     if (TAPS) {
@@ -568,7 +577,7 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
         if (MODE != 2 && taps.chan != nullptr && sync_less) {
             // PREAMBLE_FORM::chan_char (Frame.hpp:375-385) on the preamble as it stands: pr = preamble.fft()
             // (own pilot normalisation, Frame.cpp:76-84; coef == 1), chan_est[i] = pr[i] / mod_preamble[i]
-            const float gp = M->pabs[0] / (8.0f * P.pilot_ampl);
+            const float gp = M->pabs0 / (8.0f * P.pilot_ampl);
             for (int i = tid; i < 256; i += blockDim.x) {
                 const int sl = spec_slot(__ldg(&P.data_bin[i]));
                 const float2 y = cscale(make_float2(X[sl].x, X[kFft512Slots + sl].x), 1.0f / gp);
@@ -621,8 +630,8 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
             p1e = cmul(cmul(M->pilots[1][lane], rot1), ee);
         }
         const float2 psa = M->pilots[A][lane], psb = M->pilots[hasB ? B : A][lane];
-        const float2 wa = cscale(cmulc(p1e, psa), 1.0f / (cnorm2(psa) * g));
-        const float2 wb = cscale(cmulc(p1e, psb), 1.0f / (cnorm2(psb) * g));
+        const float2 wa = cscale(cmulc(p1e, psa), __fdividef(1.0f, cnorm2(psa) * g));
+        const float2 wb = cscale(cmulc(p1e, psb), __fdividef(1.0f, cnorm2(psb) * g));
         wt[lane] = make_float4(wa.x, wb.x, wa.y, wb.y);
     }
     const float2 Ll = MODE == 2 ? M->ltab[lane] : cis_neg_turns_f((float)(lb * (double)lane) * inv2pi);

@@ -253,7 +253,7 @@ rx_acquire512x2_kernel(const Params P, const void *__restrict__ samples, long lo
 #pragma unroll
     for (int c = 0; c < 2; c++) {
         if (c >= nfr) break;
-        const int m0 = (int)ceilf(-(M->theta_t[c] - (float)M->kc[c] * (512.0f / (float)P.pf_den)) - 0.5f);
+        const int m0 = (int)ceilf(-(M->theta_t[c] - (float)M->kc[c] * P.pf_bins512) - 0.5f);
         m0v[c] = m0;
         const int s0 = spec_slot((db0 + m0) & 511), s1 = spec_slot((db1 + m0) & 511);
         const float2 y0 = c ? make_float2(Wre[s0].y, Wim[s0].y) : make_float2(Wre[s0].x, Wim[s0].x);
