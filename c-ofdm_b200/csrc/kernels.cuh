@@ -30,7 +30,7 @@ namespace cofdmk {
 // ------------------------------------------------------------------------------------------------
 COFDM_HD int tx512_threads(int num_symb) { return 32 * (2 * ((num_symb + 1) / 2) + 1); }
 COFDM_HD size_t tx512_smem_bytes(int num_symb, int bytes_per_frame) {
-    return (size_t)((num_symb + 1) / 2) * kPairSlots * sizeof(float2) + (size_t)((bytes_per_frame + 15) & ~15);
+    return (size_t)((num_symb + 1) / 2) * kPairSlots * sizeof(float2) + (size_t)((bytes_per_frame + 15) & ~15) + 16;   // +16: a straddling 6-bit symbol reads one byte on
 }
 
 // wide: the frame buffer is 16-byte aligned (one 16- / 8-byte store for the pair); otherwise one store per sample
@@ -55,15 +55,24 @@ COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/,
 // null, pilot, or the constellation point of MOD payload bits (Frame.cpp:55-62 + modulation.cpp:39-50)
 template <int MOD>
 COFDM_DEV void tx512_grid_points(const Params &P, const uint8_t *pl, int A, int B, bool hasB, const int (&mm)[8], pc (&v)[8]) {
+    // Branch-free: a warp's 32 bins mix data, a pilot and nulls, so a branch per kind would run every path anyway.
+    // The payload holds exactly num_data_subc * num_symb * MOD bits, so no bounds checks; symbol s starts at byte
+    // s * num_data_subc * MOD / 8 (num_data_subc is a multiple of 8), and the bit offset inside is the same for A and B.
+    const int sym_bytes = P.num_data_subc * MOD / 8;
+    const uint8_t *pa = pl + A * sym_bytes, *pb = pl + (hasB ? B : A) * sym_bytes;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
-        const int m = mm[r];                                                         // bin_map[t + 64 r]
-        float2 va = make_float2(0.f, 0.f), vb = va;                                  // Frame.cpp:55
-        if (m == -2) va = vb = make_float2(P.pilot_ampl, 0.f);                        // Frame.cpp:56-57
-        else if (m >= 0) {
-            va = __ldg(&P.constell[extract_bits_t<MOD>(pl, P.bytes_per_frame, (A * P.num_data_subc + m) * MOD)]);
-            if (hasB) vb = __ldg(&P.constell[extract_bits_t<MOD>(pl, P.bytes_per_frame, (B * P.num_data_subc + m) * MOD)]);
-        }
+        const int m = mm[r];                                                         // bin_map[t + 64 r]: data index, -2 pilot, -1 null
+        const bool isdata = m >= 0;
+        const int bit = (isdata ? m : 0) * MOD, b0 = bit >> 3, sh = 16 - MOD - (bit & 7);
+        unsigned wa = (unsigned)pa[b0] << 8, wb = (unsigned)pb[b0] << 8;
+        if ((8 % MOD) != 0) { wa |= pa[b0 + 1]; wb |= pb[b0 + 1]; }                  // a 6-bit symbol may straddle two bytes (the
+                                                                                     // staging buffer is padded by 16 bytes)
+        const float2 ca = __ldg(&P.constell[(wa >> sh) & ((1u << MOD) - 1u)]);       // Frame.cpp:59-62 + modulation.cpp:39-50
+        const float2 cb = __ldg(&P.constell[(wb >> sh) & ((1u << MOD) - 1u)]);
+        const float alt = m == -2 ? P.pilot_ampl : 0.f;                              // Frame.cpp:55-57
+        const float2 va = make_float2(isdata ? ca.x : alt, isdata ? ca.y : 0.f);
+        const float2 vb = hasB ? make_float2(isdata ? cb.x : alt, isdata ? cb.y : 0.f) : make_float2(0.f, 0.f);
         v[r] = make_pc(va, vb);
     }
 }
