@@ -35,6 +35,7 @@ CONFIG = os.path.join(ROOT, "config", "config.txt")
 
 RX_BYTES_PER_FRAME = 46080 + 1024      # (N+CP)(NS+NPR)*8 read + ND*NS*mod/8 written, 16-QAM
 TX_BYTES_PER_FRAME = 1024 + 6016 * 8   # payload read + frame written
+MOD_NAME = {1: "BPSK", 2: "QPSK", 4: "16-QAM", 6: "64-QAM", 8: "256-QAM"}
 RX_DRAM_BYTES_PER_FRAME_NCU = 47359     # measured DRAM read+write of the rx pass (acquire + demod kernels), see roofline.traffic_source
 
 
@@ -140,7 +141,7 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "tx+rx Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched tx + aligned rx, default config.txt (fft512 cp128 8sym+preamble 16-QAM)",
+            "config": {"workload": "batched tx + aligned rx, default config.txt (fft512 cp128 8sym+preamble " + MOD_NAME.get(s.mod_type, "?") + ")",
                        "frames_per_step": n_done, "frame_samples": s.output_size},
             "ofdm_symbols_s": 2 * n_done * 9 / dt,
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind,
@@ -278,7 +279,7 @@ def native_arm(args):
             "metric": "tx+rx Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic batched tx + fused aligned rx, default config.txt (fft512 cp128 8sym+preamble 16-QAM), complex64 in HBM",
+            "config": {"workload": "synthetic batched tx + fused aligned rx, default config.txt (fft512 cp128 8sym+preamble " + MOD_NAME.get(s.mod_type, "?") + "), complex64 in HBM",
                        "frames_per_gpu": F, "frame_samples": s.output_size, "l2": "inputs (GBs) far larger than the 126 MB L2, no flush needed",
                        "channel": "per-frame CFO +-0.003 cyc/sample, random phase, AWGN sigma 1.5 LSB, int16 grid"},
             "ofdm_symbols_s": world * 2 * F * 9 / (step_ms * 1e-3),
@@ -288,7 +289,7 @@ def native_arm(args):
             "bit_errors": bit_err, "frames_with_errors": frames_bad, "frames_checked": frames_all,
             "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb,
             "roofline": {"bound": "hbm", "kernel": "rx pass = rx_acquire512x2_kernel + rx_fused512_kernel<demod> (together they read every sample exactly once)", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": rx_gbs / peak, "traffic": RX_DRAM_BYTES_PER_FRAME_NCU * F, "peak_source": peak_src,
+                         "frac": rx_gbs / peak, "traffic": RX_DRAM_BYTES_PER_FRAME_NCU * F if s.mod_type == 4 else None, "peak_source": peak_src,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the two rx kernels over 32768 frames "
                                            "(profiles/r01_final_ncu_summary.txt) = 47359 B/frame, scaled to this launch's frames",
                          "algorithmic_bytes_per_frame": RX_BYTES_PER_FRAME, "tx_kernel_gbs": tx_gbs, "tx_frac": tx_gbs / peak},
@@ -324,7 +325,18 @@ def main():
     ap.add_argument("--e2e-frames", type=int, default=1 << 15)
     ap.add_argument("--cpu-frames", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--mod-type", type=int, default=0, choices=[0, 1, 2, 4, 6, 8],
+                    help="0: the shipped config.txt (16-QAM, the headline workload); otherwise the same geometry with this modType "
+                         "(BASELINE configs[2] also names QPSK)")
     args = ap.parse_args()
+    if args.mod_type:
+        import tempfile
+        from cofdm_b200 import synth
+        global CONFIG, RX_BYTES_PER_FRAME, TX_BYTES_PER_FRAME
+        rank = os.environ.get("RANK", "0")
+        CONFIG = synth.write_config(os.path.join(tempfile.mkdtemp(), f"config_mod{args.mod_type}_{rank}.txt"), modType=args.mod_type)
+        payload = 256 * 8 * args.mod_type // 8
+        RX_BYTES_PER_FRAME, TX_BYTES_PER_FRAME = 46080 + payload, payload + 6016 * 8
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -700,6 +700,11 @@ rx_fused512_kernel(const Params P, const void *__restrict__ samples, long long f
                 const unsigned uy = ((raw.y << 4) & 0x00f000f0u) | ((raw.y >> 8) & 0x000f000fu);
                 const unsigned lo = (ux & 0xffu) | ((ux >> 8) & 0xff00u), hi = (uy & 0xffu) | ((uy >> 8) & 0xff00u);
                 *reinterpret_cast<unsigned *>(dst) = lo | (hi << 16);
+            } else if (mod == 2) {
+                // QPSK: wire byte k = four 2-bit symbols, first symbol in the top bits
+                const unsigned b0 = ((raw.x & 3u) << 6) | ((raw.x >> 4) & 0x30u) | ((raw.x >> 14) & 0xcu) | (raw.x >> 24);
+                const unsigned b1 = ((raw.y & 3u) << 6) | ((raw.y >> 4) & 0x30u) | ((raw.y >> 14) & 0xcu) | (raw.y >> 24);
+                *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(b0 | (b1 << 8));
             } else {
                 unsigned long long bits = 0;
 #pragma unroll
