@@ -203,7 +203,10 @@ template <int R, bool INV> COFDM_DEV void dftR(float2 *v) {
 // the product of the radices already applied.  Butterflies j = tid, tid+nthr, ... < n/R.
 // tw[k] = exp(-j*2*pi*k/n) (forward table, conjugated on the fly for INV).  in != out.
 // NOWRAP: the caller guarantees (R-1)*(ns-1)*tstep < n, so the twiddle index needs no reduction mod n.
-template <int R, bool INV, bool NOWRAP = false>
+// PADSH > 0: element i lives at slot i + (i >> PADSH).  With PADSH = 3 the radix-8 scatter of the first passes
+// (stride 8, then stride 64 + 1) and the consecutive gathers are all free of bank conflicts; buffers need n + n/8 slots.
+template <int PADSH> COFDM_DEV int pad_slot(int i) { return PADSH > 0 ? i + (i >> PADSH) : i; }
+template <int R, bool INV, bool NOWRAP = false, int PADSH = 0>
 COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const float2 *tw, int tid, int nthr) {
     const int m = n / R;
     const int tstep = n / (ns * R);
@@ -213,7 +216,7 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
         float2 v[R];
 #pragma unroll
         for (int q = 0; q < R; q++) {
-            v[q] = in[j + q * m];
+            v[q] = in[pad_slot<PADSH>(j + q * m)];
             if (q > 0 && ns > 1) {
                 const int ti = q * k * tstep;
                 v[q] = cmul(v[q], twid<INV>(__ldg(&tw[NOWRAP ? ti : (pow2 ? (ti & (n - 1)) : ti % n)])));
@@ -222,12 +225,12 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
         dftR<R, INV>(v);
         const int o = (j - k) * R + k;              // (j / ns) * ns * R + k
 #pragma unroll
-        for (int q = 0; q < R; q++) out[o + q * ns] = v[q];
+        for (int q = 0; q < R; q++) out[pad_slot<PADSH>(o + q * ns)] = v[q];
     }
 }
 
 // The same pass for TWO transforms at once (packed f32x2; operands in separate re / im planes of float2 pairs).
-template <int R, bool INV, bool NOWRAP = false>
+template <int R, bool INV, bool NOWRAP = false, int PADSH = 0>
 COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2 *out_re, float2 *out_im, int n, int ns,
                                 const float2 *tw, int tid, int nthr) {
     static_assert(R == 8 || R == 4, "packed passes exist for radix 4 and 8");
@@ -238,8 +241,8 @@ COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2
         pc v[R];
 #pragma unroll
         for (int q = 0; q < R; q++) {
-            v[q].re = in_re[j + q * m];
-            v[q].im = in_im[j + q * m];
+            v[q].re = in_re[pad_slot<PADSH>(j + q * m)];
+            v[q].im = in_im[pad_slot<PADSH>(j + q * m)];
             if (q > 0 && ns > 1) {
                 const int ti = q * k * tstep;
                 v[q] = cmul(v[q], twid<INV>(__ldg(&tw[NOWRAP ? ti : ti % n])));
@@ -248,7 +251,7 @@ COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2
         if (R == 8) dft8<INV>(v); else dft4<INV>(v);
         const int o = (j - k) * R + k;
 #pragma unroll
-        for (int q = 0; q < R; q++) { out_re[o + q * ns] = v[q].re; out_im[o + q * ns] = v[q].im; }
+        for (int q = 0; q < R; q++) { out_re[pad_slot<PADSH>(o + q * ns)] = v[q].re; out_im[pad_slot<PADSH>(o + q * ns)] = v[q].im; }
     }
 }
 

@@ -186,18 +186,19 @@ tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, 
     }
 }
 
-// rel = sum(mask*|X|^2) / sum(|X|^2) of the 256 samples a warp has staged in A (B = scratch); every lane returns it.
+// rel = sum(mask*|X|^2) / sum(|X|^2) of the 256 samples a warp has staged in A at pad_slot<3>(i) (B = scratch, both
+// kT2Slots long); every lane returns it.
 // Blocks with zero or NaN energy report 0 (Frame.hpp:132-138 `continue`).
 COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane) {
     // total spectral energy by Parseval: sum_k |X_k|^2 = 256 * sum_n |x_n|^2 (saves evaluating unmasked bins)
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) tot += cnorm2(A[lane + 32 * i]);
+    for (int i = 0; i < 8; i++) tot += cnorm2(A[pad_slot<3>(lane + 32 * i)]);
     tot *= 256.0f;
     __syncwarp();
-    stockham_pass<8, false>(A, B, 256, 1, P.tw_t2, lane, 32);
+    stockham_pass<8, false, false, 3>(A, B, 256, 1, P.tw_t2, lane, 32);
     __syncwarp();
-    stockham_pass<8, false, true>(B, A, 256, 8, P.tw_t2, lane, 32);         // twiddle index <= 7*7*4 < 256
+    stockham_pass<8, false, true, 3>(B, A, 256, 8, P.tw_t2, lane, 32);      // twiddle index <= 7*7*4 < 256
     __syncwarp();
     // last pass (radix 4, ns = 64): butterfly j yields bins j, j+64, j+128, j+192; only butterflies that feed a
     // masked bin are evaluated (the shipped mask covers bins 12..22 and 46..56: 22 of 64 butterflies)
@@ -213,7 +214,7 @@ COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane)
             float2 v[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                v[q] = A[j + 64 * q];
+                v[q] = A[pad_slot<3>(j + 64 * q)];
                 if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_t2[q * j]));           // q*j <= 3*63 < 256
             }
             dft4<false>(v);
@@ -234,11 +235,12 @@ COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane)
 // shared memory), rel = sum(mask*|X|^2) / sum(|X|^2); blocks with zero or NaN energy report 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int kT2WarpsPerCta = 8;
+constexpr int kT2Slots = 288;                  // 256 samples at pad_slot<3>: conflict-free Stockham scatter
 template <int FMT>
 __global__ void __launch_bounds__(32 * kT2WarpsPerCta)
 t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
                     float *__restrict__ rel_out) {
-    __shared__ float2 buf[kT2WarpsPerCta][2][256];
+    __shared__ float2 buf[kT2WarpsPerCta][2][kT2Slots];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long blk = (long long)blockIdx.x * kT2WarpsPerCta + warp;
     if (blk >= n_blocks) return;
@@ -249,12 +251,12 @@ t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long 
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const unsigned w = __ldg(src + lane + 32 * i);
-            A[lane + 32 * i] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+            A[pad_slot<3>(lane + 32 * i)] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
         }
     } else {
         const float2 *src = reinterpret_cast<const float2 *>(samples) + s0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) A[lane + 32 * i] = __ldg(src + lane + 32 * i);
+        for (int i = 0; i < 8; i++) A[pad_slot<3>(lane + 32 * i)] = __ldg(src + lane + 32 * i);
     }
     const float rel = t2sin_block_rel(P, A, B, lane);
     if (lane == 0) rel_out[blk] = rel;
@@ -267,7 +269,7 @@ template <int FMT>
 __global__ void __launch_bounds__(32 * kT2PairWarps)
 t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
                      float *__restrict__ rel_out) {
-    __shared__ float2 buf[kT2PairWarps][4][256];                // per warp: re / im planes of two ping-pong buffers
+    __shared__ float2 buf[kT2PairWarps][4][288];                // per warp: re / im planes of two ping-pong buffers, padded (pad_slot<3>)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long blk = 2 * ((long long)blockIdx.x * kT2PairWarps + warp);
     if (blk >= n_blocks) return;
@@ -288,14 +290,14 @@ t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long
             x0 = __ldg(src);
             if (has1) x1 = __ldg(src + 256);
         }
-        Are[lane + 32 * i] = make_float2(x0.x, x1.x);
-        Aim[lane + 32 * i] = make_float2(x0.y, x1.y);
+        Are[pad_slot<3>(lane + 32 * i)] = make_float2(x0.x, x1.x);
+        Aim[pad_slot<3>(lane + 32 * i)] = make_float2(x0.y, x1.y);
         tot.x += cnorm2(x0); tot.y += cnorm2(x1);              // Parseval: sum_k |X_k|^2 = 256 sum_n |x_n|^2
     }
     __syncwarp();
-    stockham_pass_pc<8, false>(Are, Aim, Bre, Bim, 256, 1, P.tw_t2, lane, 32);
+    stockham_pass_pc<8, false, false, 3>(Are, Aim, Bre, Bim, 256, 1, P.tw_t2, lane, 32);
     __syncwarp();
-    stockham_pass_pc<8, false, true>(Bre, Bim, Are, Aim, 256, 8, P.tw_t2, lane, 32);   // twiddle index <= 7*7*4 < 256
+    stockham_pass_pc<8, false, true, 3>(Bre, Bim, Are, Aim, 256, 8, P.tw_t2, lane, 32);   // twiddle index <= 7*7*4 < 256
     __syncwarp();
     // last pass (radix 4, ns = 64), only butterflies that feed a masked bin (see t2sin_block_rel)
     float2 sine = make_float2(0.f, 0.f);
@@ -310,7 +312,7 @@ t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long
             pc v[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                v[q].re = Are[j + 64 * q]; v[q].im = Aim[j + 64 * q];
+                v[q].re = Are[pad_slot<3>(j + 64 * q)]; v[q].im = Aim[pad_slot<3>(j + 64 * q)];
                 if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_t2[q * j]));
             }
             dft4<false>(v);

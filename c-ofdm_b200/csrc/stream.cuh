@@ -30,7 +30,7 @@ constexpr int kScanThreads = 32 * kScanWarps;
 
 COFDM_HD size_t stream_scan_smem_bytes(int cor_size, int pr_sin_len) {
     const size_t plane = (size_t)(cor_size + pr_sin_len) / 4 + 4;
-    return (size_t)kScanWarps * 2 * 256 * sizeof(float2) + 4 * plane * sizeof(float2) + (size_t)pr_sin_len * sizeof(float2) +
+    return (size_t)kScanWarps * 2 * kT2Slots * sizeof(float2) + 4 * plane * sizeof(float2) + (size_t)pr_sin_len * sizeof(float2) +
            (size_t)kScanWarps * sizeof(float) + 16;
 }
 
@@ -45,8 +45,8 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
     if (s >= n_shards) return;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int L = P.pr_sin_len, NC = P.cor_size, WN = NC + L, plane = WN / 4 + 4;
-    float2 *fft = reinterpret_cast<float2 *>(smem_raw);                 // [kScanWarps][2][256]
-    float2 *win4 = fft + (size_t)kScanWarps * 512;                      // [4][plane]: sample idx at win4[idx & 3][idx >> 2]
+    float2 *fft = reinterpret_cast<float2 *>(smem_raw);                 // [kScanWarps][2][kT2Slots]
+    float2 *win4 = fft + (size_t)kScanWarps * 2 * kT2Slots;                      // [4][plane]: sample idx at win4[idx & 3][idx >> 2]
     float2 *hf = win4 + 4 * (size_t)plane;
     float *relv = reinterpret_cast<float *>(hf + L);
     int *first = reinterpret_cast<int *>(relv + kScanWarps);
@@ -90,9 +90,9 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
                 const long long c = c0 + warp;
                 float rel = 0.f;
                 if (c < cyc) {
-                    float2 *A = fft + (size_t)warp * 512, *B = A + 256;
+                    float2 *A = fft + (size_t)warp * 2 * kT2Slots, *B = A + kT2Slots;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) A[lane + 32 * i] = sample(pos + c * 256 + lane + 32 * i);
+                    for (int i = 0; i < 8; i++) A[pad_slot<3>(lane + 32 * i)] = sample(pos + c * 256 + lane + 32 * i);
                     rel = t2sin_block_rel(P, A, B, lane);
                 }
                 if (lane == 0) relv[warp] = rel;
