@@ -62,6 +62,7 @@ struct cofdm {
     DevBuf gen_frames, gen_spec, gen_pre;        // generic path intermediates
     DevBuf fscal;                                // per-frame scalars handed from the acquire to the demod kernel
     int rx_split = 1;                            // 1: acquire + demod kernels, 0: single fused kernel
+    int rx_warp = 1;                             // 1: one-warp-per-symbol demod kernel (rx512n.cuh), 0: two-warp-team kernel (env COFDM_RX_WARP)
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
     int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
                                                  // 2 reaches the PCIe full-duplex ceiling, 3 and more lose 10-15 %
@@ -156,6 +157,24 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
         }
         if (int rc = check_launch(h, "rx512_acquire")) return rc;
         // demod: message symbols -> payload bytes
+        if (h->rx_warp && !sync_less) {
+            const bool al = fmt == COFDM_CI16 ? tma16 : tma;
+            const size_t sm = rx_demod512_smem_bytes(h->P.num_symb);
+            const unsigned thr = 32u * (unsigned)h->P.num_symb;
+#define COFDM_DM(F, T, W, MW) rx_demod512_kernel<F, T, W, MW><<<(unsigned)n_frames, thr, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
+#define COFDM_DM_PICK(F, T) do { if (h->P.num_symb <= 8) { if (want) COFDM_DM(F, T, true, 8); else COFDM_DM(F, T, false, 8); } \
+                                 else { if (want) COFDM_DM(F, T, true, kMaxFusedSymb); else COFDM_DM(F, T, false, kMaxFusedSymb); } } while (0)
+            if (fmt == COFDM_CI16) { if (al) COFDM_DM_PICK(kCI16, true); else COFDM_DM_PICK(kCI16, false); }
+            else { if (al) COFDM_DM_PICK(kCF32, true); else COFDM_DM_PICK(kCF32, false); }
+#undef COFDM_DM_PICK
+#undef COFDM_DM
+            if (int rc = check_launch(h, "rx_demod512")) return rc;
+            if (taps.synced != nullptr && taps.scal != nullptr) {
+                rx_synced_fixup2_kernel<<<(unsigned)n_frames, 128, 0, st>>>(h->P, (int)n_frames, taps, 1);
+                return check_launch(h, "rx_synced_fixup2");
+            }
+            return COFDM_OK;
+        }
         if (tma16) { if (want) COFDM_RX_LAUNCH(kCI16, true, 9, true, 2); else COFDM_RX_LAUNCH(kCI16, true, 9, false, 2); }   // split implies <= 9 symbols
         else COFDM_RX_MODE(2);
     } else {
@@ -342,6 +361,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
     rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
+    rc |= upload(h, T.lane_desc, &P.lane_desc);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
     if (rc) return bail(COFDM_ERR_CUDA);
     P.constell = h->constell_dev[P.mod_type];
@@ -359,6 +379,8 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         {
             const char *e = std::getenv("COFDM_RX_SPLIT");
             if (e) h->rx_split = std::atoi(e) != 0;
+            const char *rw = std::getenv("COFDM_RX_WARP");
+            if (rw) h->rx_warp = std::atoi(rw) != 0;
             const char *tb = std::getenv("COFDM_TX_BULK");
             if (tb) h->tx_bulk = std::atoi(tb) != 0;
             const char *c = std::getenv("COFDM_PIPE_CHUNK");
@@ -379,6 +401,16 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         COFDM_RX_ATTR(kCI16, true, 9, true, 2); COFDM_RX_ATTR(kCI16, true, 9, false, 2);
 #undef COFDM_RX_ATTR_ALL
 #undef COFDM_RX_ATTR
+        {
+            const int smd = (int)rx_demod512_smem_bytes(P.num_symb);
+#define COFDM_DM_ATTR(F, T, W, MW) \
+            if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_demod512_kernel<F, T, W, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smd); \
+            if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_demod512_kernel<F, T, W, MW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+#define COFDM_DM_ATTR_ALL(F, T) COFDM_DM_ATTR(F, T, true, 8); COFDM_DM_ATTR(F, T, false, 8); COFDM_DM_ATTR(F, T, true, kMaxFusedSymb); COFDM_DM_ATTR(F, T, false, kMaxFusedSymb)
+            COFDM_DM_ATTR_ALL(kCF32, true); COFDM_DM_ATTR_ALL(kCF32, false); COFDM_DM_ATTR_ALL(kCI16, true); COFDM_DM_ATTR_ALL(kCI16, false);
+#undef COFDM_DM_ATTR_ALL
+#undef COFDM_DM_ATTR
+        }
 #define COFDM_ACQ_ATTR(F, T, W) \
         if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512x2_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
         COFDM_ACQ_ATTR(kCF32, true, true); COFDM_ACQ_ATTR(kCF32, true, false); COFDM_ACQ_ATTR(kCF32, false, true);

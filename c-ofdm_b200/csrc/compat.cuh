@@ -80,6 +80,32 @@ COFDM_DEV pc cmul(pc a, pc w) {
 }
 COFDM_DEV pc cconj(pc a) { pc r; r.re = a.re; r.im = p_neg(a.im); return r; }
 
+// ---- NATURAL-layout complex math on packed f32x2 ---------------------------------------------------
+// One complex number = one aligned register pair (re, im), exactly as LDS.64 / LDS.128 deliver it.  Blackwell's
+// FADD2 / FMUL2 / FFMA2 take per-operand modifiers -- swap halves (.LO_HI), negate one half (.NP), broadcast a
+// scalar (.F32) -- so a complex add is ONE instruction, a complex multiply TWO (FMUL2 + FFMA2), and a multiply
+// by -+j folds into the add that consumes it.  Same arithmetic rate as the (re_A, re_B)/(im_A, im_B) pairing of
+// `pc` below, without pairing two transforms and without the register shuffles that pairing needs after a load.
+// ptxas recognises the swap / half-negate patterns written here (checked in SASS: profiles/r02_sass_*.txt).
+COFDM_DEV float2 nadd(float2 a, float2 b) { return p_add(a, b); }
+COFDM_DEV float2 nsub(float2 a, float2 b) { return p_add(a, make_float2(-b.x, -b.y)); }
+COFDM_DEV float2 nadd_mj(float2 a, float2 b) { return p_add(a, make_float2(b.y, -b.x)); }    // a + (-j) b
+COFDM_DEV float2 nadd_pj(float2 a, float2 b) { return p_add(a, make_float2(-b.y, b.x)); }    // a + (+j) b
+COFDM_DEV float2 nmul(float2 a, float2 w) {                                                  // a * w
+    return p_fma(a, make_float2(w.x, w.x), p_mul(make_float2(a.y, a.x), make_float2(-w.y, w.y)));
+}
+COFDM_DEV float2 nmulc(float2 a, float2 w) {                                                 // a * conj(w)
+    return p_fma(a, make_float2(w.x, w.x), p_mul(make_float2(a.y, a.x), make_float2(w.y, -w.y)));
+}
+COFDM_DEV float2 nscale(float2 a, float s) { return p_mul(a, make_float2(s, s)); }
+// acc + a * w  /  acc + conj(a) * w
+COFDM_DEV float2 nmac(float2 acc, float2 a, float2 w) {
+    return p_fma(make_float2(a.y, a.x), make_float2(-w.y, w.y), p_fma(a, make_float2(w.x, w.x), acc));
+}
+COFDM_DEV float2 nmac_conj(float2 acc, float2 a, float2 w) {                                 // acc + conj(a) * w
+    return p_fma(make_float2(w.y, w.x), make_float2(a.y, -a.y), p_fma(w, make_float2(a.x, a.x), acc));
+}
+
 // exp(-j*2*pi*turns): the angle is carried in TURNS as a double so that long ramps (thousands of
 // samples times a CFO) lose nothing before the reduction to (-0.5, 0.5]; the sin/cos itself is fp32.
 COFDM_DEV float2 cis_neg_turns(double turns) {

@@ -97,6 +97,7 @@ struct HostTables {
     // fp64 originals for the double-precision facade
     std::vector<cd> t2_tone_d, preamble_td_d, matched_d, mod_preamble_d, constell_d[9];
     int rx_buf_size = 0, iterations = 0;
+    std::vector<uint4> lane_desc;     // rx512n.cuh: per pass-3 lane, the roles of its registers
     bool fused512_ok = false;         // the specialised kernels apply to this config
     bool generic_ok = false;          // the any-size multi-kernel path applies to this config
 };
@@ -123,6 +124,57 @@ inline std::vector<cd> constellation_d(int mod) {
         }
     }
     return t;
+}
+
+// Roles of the registers a lane holds after warp_fft512 (fft512w.cuh): lane l'' = k2 + 8a holds bins c0 + 64 k3 (slot a) and
+// c0 + 1 + 64 k3 (slot b), c0 = 2a + 8 k2.  Derived from the sub-carrier map (Frame.cpp:31-44); the kernels' hard-wired
+// pilot and straggler positions (COFDM_F512_PILOTS / COFDM_F512_STRAG in rx512n.cuh) are checked against it.
+inline void build_f512_roles(HostTables &T) {
+    Params &p = T.p;
+    static const int pil[8] = {33, 66, 99, 132, 380, 413, 446, 479};
+    static const int strag[7] = {128, 129, 130, 131, 381, 382, 383};
+    for (int q = 0; q < 8; q++)
+        if (T.pilot_bin[q] != pil[q]) throw std::runtime_error("fft-512 sub-carrier map differs from the kernels' pilot positions");
+    auto seg_of = [&](int i) { return i / p.seg_size; };
+    // combinations in order of first appearance over the bins
+    int ncombo = 0, combo_of[8][8];
+    for (auto &r : combo_of) for (auto &v : r) v = -1;
+    for (int k = 0; k < 512; k++) {
+        const int i = T.bin_map[k];
+        if (i < 0) continue;
+        const int e = seg_of(i), k3 = k >> 6;
+        const int off = (i < 128 ? i : i - 256) - ((k & 63) - 1);
+        if (combo_of[e][k3] < 0) {
+            if (ncombo >= 12) throw std::runtime_error("fft-512 map: more than 12 (segment, k3) combinations");
+            combo_of[e][k3] = ncombo;
+            p.combo_off[ncombo] = (short)off;
+            p.combo_seg[ncombo] = (signed char)e;
+            ncombo++;
+        } else if (p.combo_off[combo_of[e][k3]] != off) {
+            throw std::runtime_error("fft-512 map: data index is not linear inside a (segment, k3) combination");
+        }
+    }
+    for (int q = ncombo; q < 12; q++) { p.combo_off[q] = 0; p.combo_seg[q] = 0; }
+    auto lane_of = [](int k) { const int c0 = (k & 63) & ~1; return (c0 >> 3) + 8 * ((c0 & 7) >> 1); };
+    T.lane_desc.assign(32, make_uint4(0, 0, 0, 0));
+    int nstrag = 0;
+    for (int k = 0; k < 512; k++) {
+        const int i = T.bin_map[k];
+        if (i < 0) continue;
+        const int k3 = k >> 6, lane = lane_of(k), slot = k & 1;
+        const unsigned d = (unsigned)i | ((unsigned)combo_of[seg_of(i)][k3] << 8);
+        if (k3 == 2 || k3 == 5) {
+            if (nstrag >= 7 || strag[nstrag] != k) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
+            p.strag_desc[nstrag++] = d | ((unsigned)(lane * 2 + slot) << 16);
+            continue;
+        }
+        if (k3 == 3 || k3 == 4) throw std::runtime_error("fft-512 map: data in the pruned registers");
+        const int w = k3 < 2 ? k3 : k3 - 4;                    // word of the uint4: k3 = 0, 1, 6, 7
+        unsigned *u = &T.lane_desc[lane].x;
+        u[w] |= (d | 0x8000u) << (16 * slot);
+    }
+    if (nstrag != 7) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
+    p.strag_desc[7] = 0;
 }
 
 inline HostTables build_tables(const ConfigMap &cfg) {
@@ -280,6 +332,7 @@ inline HostTables build_tables(const ConfigMap &cfg) {
                    ND % 8 == 0 && ND % NP == 0 && p.pf_size <= 12288 && N <= 8192;
     T.fused512_ok = (N == 512 && p.cp_size == 128 && ND == 256 && NP == 8 && p.num_pr_symb == 1 &&
                      p.num_symb >= 1 && p.num_symb <= kMaxFusedSymb && p.t2sin_size % 2 == 0 && p.pr_sin_len <= 128 * 5);
+    if (T.fused512_ok) build_f512_roles(T);
     return T;
 }
 

@@ -19,6 +19,7 @@
 #include "modem.cuh"
 #include "rx512.cuh"
 #include "rx512_acquire.cuh"
+#include "rx512n.cuh"
 #include "generic.cuh"
 
 namespace cofdmk {

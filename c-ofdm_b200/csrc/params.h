@@ -53,6 +53,16 @@ struct Params {
     const int16_t *bin_map;      // [fft_size] -1 null, -2 pilot, else data index within the symbol
     const int16_t *data_bin;     // [num_data_subc] bin of data index i
     const int16_t *pilot_bin;    // [num_pilot_subc]
+    // ---- one-warp-per-symbol receive kernels of the fft-512 geometry (rx512n.cuh) ----
+    // After warp_fft512 a lane holds bins c0 + 64 k3 (slot a) and c0 + 1 + 64 k3 (slot b).  lane_desc: per lane 8 x 16 bits
+    // for k3 = 0, 1, 6, 7 x slot a, b: data index in the symbol | combination << 8 | 0x8000 if the bin carries data.
+    // A combination is a (segment, k3) pair; combo_off = i' - ((bin & 63) - 1) for its bins (i' = data index, minus 256 in the
+    // negative half: the channel line's abscissa, Frame.hpp:425-430), combo_seg its segment.  strag_desc: the data bins of
+    // registers k3 = 2 and 5: data index | combination << 8 | (origin lane * 2 + slot) << 16.
+    const uint4 *lane_desc;      // [32]
+    short combo_off[12];
+    signed char combo_seg[12];
+    unsigned strag_desc[8];
 };
 
 // Optional debug/parity taps of the fused rx kernel (device pointers, any may be null).

@@ -1,0 +1,352 @@
+// rx512n.cuh -- the receive chain for the fft-512 geometry, second formulation: ONE WARP PER OFDM SYMBOL.
+//
+// Reference chain (main.cpp:60-80 == rx.cpp:200-220): pilot_freq_sinh (Frame.hpp:285-337), freq_shift (:340-348),
+// cp_freq_sinh (:238-263), pr_phase_sinh (:265-274), chan_char_lq (:389-434), message.fft (:276-282 + Frame.cpp:73-96),
+// the equaliser loop (rx.cpp:214-216) and Modulation::demod (modulation.cpp:53-87).
+//
+// rx_demod512_kernel -- the message symbols of one frame per CTA, one warp each:
+//   TMA bulk copy of the symbol's 640 samples -> CP correlation -> theta_s -> (the coarse shift kc of the acquire kernel
+//   is already known, so the WHOLE-bin part m_s of the rotation is applied in the time domain too: after the transform
+//   every sub-carrier sits in a fixed lane and register) -> rotation merged into the first pass and its twiddles ->
+//   warp FFT-512 (fft512w.cuh) -> the 8 pilots and sum|pilot| to shared memory -> ONE block barrier ->
+//   equalise + hard-demap the lane's data bins STRAIGHT FROM REGISTERS -> one byte per symbol to shared memory ->
+//   MSB-first bit packing, one coalesced store per lane.
+//   The spectrum never goes to shared memory; the only cross-warp traffic is 8 pilots + 1 float per symbol.
+//
+// Algebra: symbol s is rotated by exp(-j 2 pi beta_s j / 512), beta_s = theta_s + m_s, j = sample index in
+// the symbol (CP included), theta_s = Arg(CP correlation) in turns, m_s = the integer that makes theta_s - 512 shift + m_s
+// fall into (-0.5, 0.5] (Frame.hpp:254).  Per-symbol constant phases cancel between a data bin and its segment pilot
+// (Frame.cpp:89-92) except for message symbol 0 (the reference of every segment): c_1 = exp(-j 2 pi 1.25 (theta_0 + m_0)) exp(-j theta).
+// Equalised point of data index i (bin k, segment e):
+//   z = X_s[k] * P_1[e] c_1 / (P_s[e] g) * exp(-j (b i' + a)),   i' = i (i < 128) or i - 256
+// and i' = (k mod 64) - 1 + off(e, k div 64), so exp(-j b i') splits into a per-LANE factor exp(-j b ((k mod 64) - 1)) and a
+// per-(segment, k div 64) factor that is folded into the segment coefficient: 12 coefficients per symbol, 2 phasors per lane.
+#pragma once
+#include "compat.cuh"
+#include "params.h"
+#include "fft512w.cuh"
+#include "modem.cuh"
+#include "rx512.cuh"     // FrameScal, sym_turns, staged_sample
+
+namespace cofdmk {
+
+// position of bin k after warp_fft512: lane, slot (0 = a, 1 = b), register k3
+COFDM_HD constexpr int f512_lane(int k) { return (((k & 63) & ~1) >> 3) + 8 * ((((k & 63) & ~1) & 7) >> 1); }
+COFDM_HD constexpr int f512_slot(int k) { return k & 1; }
+COFDM_HD constexpr int f512_k3(int k) { return k >> 6; }
+
+// The fft-512 / 256 data / 8 pilot sub-carrier map (Frame.cpp:31-44) is fixed by the geometry; build_tables() checks
+// these lists against the tables it derives from the config.
+#define COFDM_F512_PILOTS(X) X(0, 33) X(1, 66) X(2, 99) X(3, 132) X(4, 380) X(5, 413) X(6, 446) X(7, 479)
+// data bins whose register (k3 = 2 or 5) holds almost no other used bin: handled apart, seven lanes in one go
+#define COFDM_F512_STRAG(X) X(0, 128) X(1, 129) X(2, 130) X(3, 131) X(4, 381) X(5, 382) X(6, 383)
+constexpr int kF512Strag = 7;
+constexpr int kF512Combos = 12;
+
+constexpr int kDemodRegion = 640 * 8;          // bytes of a warp's staging / exchange region
+
+struct DemodShared {
+    uint64_t mbar[kRxMaxSym];
+    float2 pil[kRxMaxSym][8];        // pilot bins per message symbol (index s - 1)
+    float pabs[kRxMaxSym];           // sum |pilot| per message symbol, zero beyond the last one
+    float theta_t[kRxMaxSym + 1];    // Arg(C_s) in turns, by frame symbol index (taps)
+    int mshift[kRxMaxSym + 1];       // m_s
+    float4 lcl[32];                  // per pass-3 lane: exp(-j b (c0 - 1)), exp(-j b c0)
+    float2 ftab[16];                 // per (segment, k3) combination: c_1 exp(-j (b off + a))
+    float2 wtab[kRxMaxSym][16];      // per warp: segment coefficient times ftab
+    float2 strag[kRxMaxSym][8];      // per warp: the straggler bins' spectrum values
+    float4 qtab[kRxMaxSym][5];       // per warp, as float2[10]: Q^r (r < 8), D
+    alignas(16) uint8_t sym[kRxMaxSym][256];   // per warp: demapped symbols
+};
+
+COFDM_HD size_t rx_demod512_smem_bytes(int num_symb) { return (size_t)num_symb * kDemodRegion + sizeof(DemodShared); }
+
+// 640 samples of one symbol -> the warp's region, by the warp itself (sources that are not 16-byte aligned)
+template <int FMT>
+COFDM_DEV void warp_stage_symbol(void *dst, const char *src, int lane) {
+    if (FMT == kCI16) {
+        const unsigned *s = reinterpret_cast<const unsigned *>(src);
+        unsigned *d = reinterpret_cast<unsigned *>(dst);
+        for (int i = lane; i < 640; i += 32) d[i] = __ldg(s + i);
+    } else {
+        const float2 *s = reinterpret_cast<const float2 *>(src);
+        float2 *d = reinterpret_cast<float2 *>(dst);
+        for (int i = lane; i < 640; i += 32) d[i] = __ldg(s + i);
+    }
+}
+
+// two adjacent staged samples (index 2u, 2u + 1)
+template <int FMT>
+COFDM_DEV void staged_pair(const void *region, int u, float2 &a, float2 &b) {
+    if (FMT == kCI16) {
+        const uint2 w = reinterpret_cast<const uint2 *>(region)[u];
+        a = make_float2((float)(short)(w.x & 0xffffu), (float)(short)(w.x >> 16));
+        b = make_float2((float)(short)(w.y & 0xffffu), (float)(short)(w.y >> 16));
+    } else {
+        const float4 q = reinterpret_cast<const float4 *>(region)[u];
+        a = make_float2(q.x, q.y);
+        b = make_float2(q.z, q.w);
+    }
+}
+
+// exp(-j 2 pi (theta + m) J / 512) for an integer sample index J: the whole-bin part is reduced exactly in integers
+COFDM_DEV float2 rot_phasor(float theta, int m, int J) {
+    return fast_cis_turns(-(theta * ((float)J * (1.0f / 512.0f)) + (float)((m * J) & 511) * (1.0f / 512.0f)));
+}
+
+template <int FMT, bool USE_TMA, bool TAPS, int MAXW>
+__global__ void __launch_bounds__(32 * MAXW, MAXW <= 8 ? 4 : 1)
+rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
+                   uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous, const RxTaps taps,
+                   const int sync_less, const FrameScal *__restrict__ fscal) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x;
+    if (frame >= n_frames) return;
+    const int nw = P.num_symb;                     // one warp per message symbol
+    const int s = warp + 1;                        // frame symbol index (0 = preamble)
+    char *region = reinterpret_cast<char *>(smem_raw) + (size_t)warp * kDemodRegion;
+    DemodShared *M = reinterpret_cast<DemodShared *>(smem_raw + (size_t)nw * kDemodRegion);
+    const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
+    const char *src = reinterpret_cast<const char *>(samples) + ((size_t)frame * (size_t)frame_stride + (size_t)s * 640) * sample_bytes;
+
+    // ---- stage the symbol: one TMA bulk copy issued by the warp that consumes it ----
+    if (USE_TMA) {
+        if (lane == 0) {
+            mbar_init(&M->mbar[warp], 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(&M->mbar[warp], 640 * (unsigned)sample_bytes);
+            tma_load_1d(region, src, 640 * (unsigned)sample_bytes, &M->mbar[warp]);
+        }
+    } else {
+        warp_stage_symbol<FMT>(region, src, lane);
+    }
+    // ---- while the copy is in flight: the acquire kernel's scalars and the frame-wide tables ----
+    FrameScal fs;
+    if (sync_less) { fs.kc = 0; fs.m0 = 0; fs.th0 = 0.f; fs.theta = 0.f; fs.rot_theta = make_float2(1.f, 0.f); fs.a = 0.0; fs.b = 0.0; }
+    else fs = fscal[frame];
+    if (tid >= nw && tid < kRxMaxSym) M->pabs[tid] = 0.f;   // unused entries (the others are written by their warps); ordered by the block barrier
+    const float inv2pi = 0.15915494309189533577f;
+    const float bt = (float)fs.b * inv2pi;         // channel-line slope in turns per data index
+    if (warp == 0) {
+        // per pass-3 lane: exp(-j b (c0 - 1)), exp(-j b c0)
+        const int c0 = fft512w_c0(lane);
+        const float2 la = cis_neg_turns_f(bt * (float)(c0 - 1)), lb = cis_neg_turns_f(bt * (float)c0);
+        M->lcl[lane] = make_float4(la.x, la.y, lb.x, lb.y);
+    }
+    if (warp == nw - 1 && lane < kF512Combos) {
+        // c_1 exp(-j (b off + a)): the constant phase of message symbol 0 (Psi_1 = 1.25 (theta_0 + m_0) mod 1), theta, the channel line
+        float acc = fs.th0 * (640.0f / 512.0f);
+        acc -= rintf(acc);
+        const float psi1 = acc + (float)((5 * fs.m0) & 3) * 0.25f;
+        const float2 c1 = nmul(cis_neg_turns_f(psi1), fs.rot_theta);
+        const float2 ee = cis_neg_turns_f((float)((fs.b * (double)P.combo_off[lane] + fs.a) * 0.15915494309189533577));
+        M->ftab[lane] = nmul(c1, ee);
+    }
+    if (TAPS && tid == 0) { M->theta_t[0] = fs.th0; M->mshift[0] = fs.m0; }
+    __syncwarp();
+    if (USE_TMA) mbar_wait(&M->mbar[warp], 0);
+
+    // ---- the lane's 16 body samples (pass-1 layout: t = 2 lane, 2 lane + 1; index 128 + t + 64 r) and 4 CP samples ----
+    float2 va[8], vb[8], cpa[2], cpb[2];
+#pragma unroll
+    for (int r = 0; r < 8; r++) staged_pair<FMT>(region, 64 + lane + 32 * r, va[r], vb[r]);
+#pragma unroll
+    for (int c = 0; c < 2; c++) staged_pair<FMT>(region, lane + 32 * c, cpa[c], cpb[c]);
+    __syncwarp();                                  // the region may now be reused by the exchanges
+
+    // ---- CP correlation (Frame.hpp:251-253): CP sample j pairs with body sample j + 512, i.e. r = 6, 7 ----
+    float theta = 0.f;
+    int m = 0;
+    if (!sync_less) {
+        float2 c = nmac_conj(nmac_conj(make_float2(0.f, 0.f), cpa[0], va[6]), cpb[0], vb[6]);
+        c = nmac_conj(nmac_conj(c, cpa[1], va[7]), cpb[1], vb[7]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = nadd(c, make_float2(__shfl_xor_sync(0xffffffffu, c.x, o), __shfl_xor_sync(0xffffffffu, c.y, o)));
+        theta = fast_atan2_turns(c.y, c.x);
+        // m_s and the reference's phi_s (Frame.hpp:254): phi = theta - 512 shift + m in (-0.5, 0.5]
+        m = (int)ceilf(-(theta - (float)fs.kc * P.pf_bins512) - 0.5f);
+    }
+    if (TAPS && lane == 0) { M->theta_t[s] = theta; M->mshift[s] = m; }
+
+    // ---- rotation phasors: Q^r = exp(-j 2 pi beta 64 r / 512) (r < 8), D = exp(-j 2 pi beta / 512), P(t) ----
+    float2 *qt = reinterpret_cast<float2 *>(M->qtab[warp]);
+    if (lane < 9) qt[lane] = lane < 8 ? rot_phasor(theta, m, 64 * lane) : rot_phasor(theta, m, 1);
+    const float2 pa = rot_phasor(theta, m, 128 + 2 * lane);
+    __syncwarp();
+    const float2 pb = nmul(pa, qt[8]);
+    if (TAPS && taps.synced != nullptr) {
+        // debug tap, completed by rx_synced_fixup_kernel (per-symbol constant phase and theta)
+        float2 *d = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
+        const int t = 2 * lane;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            d[128 + t + 64 * r] = nmul(nmul(va[r], qt[r]), pa);
+            d[129 + t + 64 * r] = nmul(nmul(vb[r], qt[r]), pb);
+        }
+        // CP samples j = t + 64 c: exp(-j 2 pi beta j / 512) = P(t) conj(Q^(2 - c))
+        d[t] = nmul(nmulc(cpa[0], qt[2]), pa);      d[t + 1] = nmul(nmulc(cpb[0], qt[2]), pb);
+        d[t + 64] = nmul(nmulc(cpa[1], qt[1]), pa); d[t + 65] = nmul(nmulc(cpb[1], qt[1]), pb);
+    }
+    {
+        const float4 *q4 = reinterpret_cast<const float4 *>(qt);
+#pragma unroll
+        for (int rr = 0; rr < 4; rr++) {
+            const float4 q = q4[rr];
+            if (rr > 0) { va[2 * rr] = nmul(va[2 * rr], make_float2(q.x, q.y)); vb[2 * rr] = nmul(vb[2 * rr], make_float2(q.x, q.y)); }
+            va[2 * rr + 1] = nmul(va[2 * rr + 1], make_float2(q.z, q.w));
+            vb[2 * rr + 1] = nmul(vb[2 * rr + 1], make_float2(q.z, q.w));
+        }
+    }
+    warp_fft512(va, vb, pa, pb, reinterpret_cast<float2 *>(region), P.tw_fft, P.tw_p2, lane);
+    // now va[k3] = X[c0 + 64 k3], vb[k3] = X[c0 + 1 + 64 k3], c0 = 2 (lane >> 3) + 8 (lane & 7)
+
+    // ---- pilots, sum |pilot| (Frame.cpp:76-80) and the straggler bins to shared memory ----
+    {
+        float2 *pil = M->pil[warp];
+#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pil[p] = (f512_slot(bin) ? vb : va)[f512_k3(bin)];
+        COFDM_F512_PILOTS(COFDM_X)
+#undef COFDM_X
+        float2 *sg = M->strag[warp];
+#define COFDM_X(q, bin) if (lane == f512_lane(bin)) sg[q] = (f512_slot(bin) ? vb : va)[f512_k3(bin)];
+        COFDM_F512_STRAG(COFDM_X)
+#undef COFDM_X
+        __syncwarp();
+        float pm = 0.f;
+        if (lane < 8) pm = sqrtf(cnorm2(pil[lane]));
+        pm += __shfl_xor_sync(0xffffffffu, pm, 4);
+        pm += __shfl_xor_sync(0xffffffffu, pm, 2);
+        pm += __shfl_xor_sync(0xffffffffu, pm, 1);
+        if (lane == 0) M->pabs[warp] = pm;
+    }
+    __syncthreads();                               // pilots of every symbol, pabs, lcl, ftab are ready
+
+    float g;                                       // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
+    {
+        const float4 *p4 = reinterpret_cast<const float4 *>(M->pabs);
+        const float4 p0 = p4[0], p1 = p4[1], p2 = p4[2], p3 = p4[3];
+        g = (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w))) + (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
+        g *= P.inv_pilot_norm;
+    }
+    const float4 lcv = M->lcl[lane];
+    const float2 lca = make_float2(lcv.x, lcv.y), lcb = make_float2(lcv.z, lcv.w);
+
+    // ---- the 12 segment coefficients of this symbol (Frame.cpp:89-92 + rx.cpp:214-216):
+    //      W[q] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) * ftab[q],  e = segment of combination q ----
+    float2 *wt = M->wtab[warp];
+    if (lane < kF512Combos) {
+        const int e = P.combo_seg[lane];
+        const float2 p1 = M->pil[0][e], ps = M->pil[warp][e];
+        const float2 w = nscale(nmulc(p1, ps), __fdividef(1.0f, cnorm2(ps) * g));
+        wt[lane] = nmul(w, M->ftab[lane]);
+    }
+    __syncwarp();
+
+    if (TAPS) {
+        if (taps.scal != nullptr && lane == 0) {
+            float *sc = taps.scal + (size_t)frame * 48;
+            if (warp == 0) {
+                sc[4] = g;
+                if (sync_less) { sc[0] = 0.f; sc[1] = 0.f; sc[2] = 0.f; sc[3] = 0.f; sc[5] = 0.f; sc[6] = 0.f; sc[7] = 0.f; sc[16] = 0.f; sc[32] = 0.f; }
+            }
+            sc[16 + s] = (float)m;
+            sc[32 + s] = theta;
+        }
+        if (taps.grid != nullptr) {
+            // FFT_buf after FFT_FORM::read's normalisation: every bin, with the symbol's constant phase and theta
+            const float psi = sym_turns(M->theta_t, M->mshift, s);
+            const float2 rs = nscale(nmul(cis_neg_turns_f(psi), fs.rot_theta), 1.0f / g);
+            float2 *dst = taps.grid + ((size_t)frame * nw + (s - 1)) * 512;
+            const int c0 = fft512w_c0(lane);
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) { dst[c0 + 64 * k3] = nmul(va[k3], rs); dst[c0 + 1 + 64 * k3] = nmul(vb[k3], rs); }
+        }
+    }
+
+    // ---- equalise + hard demap (modulation.cpp:53-87) straight from the registers ----
+    const DemapK dk = make_demapk(P.mod_type);
+    uint8_t *sb = M->sym[warp];
+    const bool count_amb = ambiguous != nullptr;
+    int n_amb = 0;
+    const uint4 desc = __ldg(&P.lane_desc[lane]);  // 8 x 16 bits: data index | combination << 8 | valid << 15
+    float2 *ctap = (TAPS && taps.constell != nullptr) ? taps.constell + ((size_t)frame * nw + (s - 1)) * 256 : nullptr;
+#define COFDM_EQ(X, LC, D16)                                                             \
+    do {                                                                                 \
+        const unsigned d_ = (D16);                                                       \
+        if (d_ & 0x8000u) {                                                              \
+            const int i_ = (int)(d_ & 0xffu);                                            \
+            const float2 z_ = nmul(nmul((X), (LC)), wt[(d_ >> 8) & 15u]);                \
+            if (TAPS && ctap != nullptr) ctap[i_] = z_;                                  \
+            sb[i_] = (uint8_t)demap_fast(z_, dk);                                        \
+            if (count_amb) n_amb += demap_ambiguous(z_, dk) ? 1 : 0;                     \
+        }                                                                                \
+    } while (0)
+    COFDM_EQ(va[0], lca, desc.x & 0xffffu); COFDM_EQ(vb[0], lcb, desc.x >> 16);
+    COFDM_EQ(va[1], lca, desc.y & 0xffffu); COFDM_EQ(vb[1], lcb, desc.y >> 16);
+    COFDM_EQ(va[6], lca, desc.z & 0xffffu); COFDM_EQ(vb[6], lcb, desc.z >> 16);
+    COFDM_EQ(va[7], lca, desc.w & 0xffffu); COFDM_EQ(vb[7], lcb, desc.w >> 16);
+    if (lane < kF512Strag) {
+        // the seven data bins that live in registers k3 = 2 and 5 of four lanes
+        const unsigned d16 = P.strag_desc[lane];   // data index | combination << 8 | (origin lane * 2 + slot) << 16
+        const float2 lsrc = reinterpret_cast<const float2 *>(M->lcl)[d16 >> 16];
+        COFDM_EQ(M->strag[warp][lane], lsrc, (d16 & 0x7fffu) | 0x8000u);
+    }
+#undef COFDM_EQ
+    if (count_amb) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n_amb += __shfl_xor_sync(0xffffffffu, n_amb, o);
+        if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
+    }
+    __syncwarp();
+    // ---- pack: 8 consecutive symbols of `mod` bits = `mod` whole bytes, MSB first (modulation.cpp:90-125) ----
+    {
+        const int mod = P.mod_type;
+        const uint2 raw = *reinterpret_cast<const uint2 *>(sb + 8 * lane);
+        uint8_t *dst = out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - 1) * 32 * mod + (size_t)lane * mod;
+        if (mod == 4) {
+            // 16-QAM: wire byte k = (symbol 2k << 4) | symbol 2k+1
+            const unsigned ux = ((raw.x << 4) & 0x00f000f0u) | ((raw.x >> 8) & 0x000f000fu);
+            const unsigned uy = ((raw.y << 4) & 0x00f000f0u) | ((raw.y >> 8) & 0x000f000fu);
+            const unsigned lo = (ux & 0xffu) | ((ux >> 8) & 0xff00u), hi = (uy & 0xffu) | ((uy >> 8) & 0xff00u);
+            *reinterpret_cast<unsigned *>(dst) = lo | (hi << 16);
+        } else if (mod == 2) {
+            const unsigned b0 = ((raw.x & 3u) << 6) | ((raw.x >> 4) & 0x30u) | ((raw.x >> 14) & 0xcu) | (raw.x >> 24);
+            const unsigned b1 = ((raw.y & 3u) << 6) | ((raw.y >> 4) & 0x30u) | ((raw.y >> 14) & 0xcu) | (raw.y >> 24);
+            *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(b0 | (b1 << 8));
+        } else {
+            unsigned long long bits = 0;
+#pragma unroll
+            for (int e = 0; e < 8; e++) {
+                const unsigned sy = ((e < 4 ? raw.x : raw.y) >> (8 * (e & 3))) & 0xffu;
+                bits = (bits << mod) | (unsigned long long)sy;
+            }
+            for (int bq = 0; bq < mod; bq++) dst[bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
+        }
+    }
+}
+
+// Completes the `synced` debug tap of rx_demod512_kernel / rx_acquire512w_kernel: they store every sample with the symbol's
+// full rotation exp(-j 2 pi beta_s j / 512); apply the per-symbol constant phase Psi_s and theta so that the tap equals
+// the reference's buffer after freq_shift + cp_freq_sinh + pr_phase_sinh.
+// Symbols below `first_full` (the preamble while the paired acquire kernel serves it) carry the fractional-bin part only.
+__global__ void rx_synced_fixup2_kernel(const Params P, int n_frames, const RxTaps taps, int first_full) {
+    const int frame = blockIdx.x;
+    if (frame >= n_frames || taps.synced == nullptr || taps.scal == nullptr) return;
+    const float *sc = taps.scal + (size_t)frame * 48;
+    const int nsym = P.n_sym_rx;
+    float s_th, c_th;
+    sincosf(-sc[3], &s_th, &c_th);
+    int mi[kRxMaxSym + 1];
+    for (int t = 0; t < nsym; t++) mi[t] = (int)sc[16 + t];
+    for (int s = 0; s < nsym; s++) {
+        const float psi = sym_turns(sc + 32, mi, s);
+        const double ms = s < first_full ? (double)mi[s] : 0.0;
+        float2 *x = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
+        for (int j = threadIdx.x; j < 640; j += blockDim.x) {
+            const float2 r = cmul(cis_neg_turns((double)psi + ms * (double)j / 512.0), make_float2(c_th, s_th));
+            x[j] = cmul(x[j], r);
+        }
+    }
+}
+
+}  // namespace cofdmk

@@ -10,7 +10,7 @@ LIB = os.path.join(HERE, "libcofdm_emu.so")
 
 def build(force=False):
     srcs = [os.path.join(HERE, f) for f in ("emu_kernels.cpp", "cuda_emu.h")] + \
-           [os.path.join(CSRC, f) for f in ("kernels.cuh", "fft.cuh", "modem.cuh", "compat.cuh", "params.h", "host_consts.hpp")]
+           [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cuh", ".h", ".hpp"))]
     if not force and os.path.exists(LIB) and all(os.path.getmtime(s) <= os.path.getmtime(LIB) for s in srcs):
         return LIB
     subprocess.run(["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-pthread", "-I", HERE, "-I", CSRC,

@@ -23,6 +23,21 @@ static void wire(EmuHandle *h) {
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
     P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
+    P.lane_desc = T.lane_desc.data();
+}
+
+// the one-warp-per-symbol demod kernel (rx512n.cuh), production instantiations
+template <bool TAPS>
+static void emu_demod512(const Params &P, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
+                         uint8_t *out, unsigned long long *amb, const RxTaps &taps, const FrameScal *fs) {
+    const dim3 grid(n_frames), block(32 * P.num_symb);
+    const size_t sm = rx_demod512_smem_bytes(P.num_symb);
+#define EMU_DM(F, T, MW) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW>(P, samples, stride, n_frames, out, amb, taps, 0, fs); })
+#define EMU_DM_PICK(F, T) do { if (P.num_symb <= 8) EMU_DM(F, T, 8); else EMU_DM(F, T, kMaxFusedSymb); } while (0)
+    if (fmt == kCI16) { if (use_tma) EMU_DM_PICK(kCI16, true); else EMU_DM_PICK(kCI16, false); }
+    else { if (use_tma) EMU_DM_PICK(kCF32, true); else EMU_DM_PICK(kCF32, false); }
+#undef EMU_DM_PICK
+#undef EMU_DM
 }
 
 extern "C" {
@@ -60,12 +75,18 @@ int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, in
     if (g_emu_split && nsym <= 9 && !sync_less) {     // production split: paired acquire + demod
         if (fmt == kCI16 && use_tma) {                // raw int16 bulk copies, widened when read
             acq2([&] { rx_acquire512x2_kernel<kCI16, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
-            EMU_RX(kCI16, true, 2);
+            if (g_emu_split == 2) emu_demod512<true>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
+            else EMU_RX(kCI16, true, 2);
         } else {
             if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
             else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
             else acq2([&] { rx_acquire512x2_kernel<kCF32, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
-            EMU_RX_MODE(2);
+            if (g_emu_split == 2) emu_demod512<true>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
+            else EMU_RX_MODE(2);
+        }
+        if (g_emu_split == 2) {
+            if (synced && scal) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup2_kernel(P, n_frames, taps, 1); });
+            return 0;
         }
     }
     else if (g_emu_split && nsym <= 9) { EMU_RX_MODE(1); EMU_RX_MODE(2); }
@@ -103,12 +124,14 @@ int emu_rx_fused512_notaps(void *hv, const void *samples, int fmt, int use_tma, 
         auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
         if (fmt == kCI16 && use_tma) {
             acq2([&] { rx_acquire512x2_kernel<kCI16, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
-            EMU_RX(kCI16, true, 2);
+            if (g_emu_split == 2) emu_demod512<false>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
+            else EMU_RX(kCI16, true, 2);
         } else {
             if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
             else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
             else acq2([&] { rx_acquire512x2_kernel<kCF32, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
-            EMU_RX_MODE(2);
+            if (g_emu_split == 2) emu_demod512<false>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
+            else EMU_RX_MODE(2);
         }
     } else EMU_RX_MODE(0);
 #undef EMU_RX_MODE
