@@ -49,10 +49,12 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise CofdmError(f"{LIB_PATH} is missing: build it with `python c-ofdm_b200/build.py` "
+    # COFDM_LIB_PATH: a developer hook for A/B runs of an experimental build of the SAME library (build.py --out)
+    path = os.environ.get("COFDM_LIB_PATH") or LIB_PATH
+    if not os.path.exists(path):
+        raise CofdmError(f"{path} is missing: build it with `python c-ofdm_b200/build.py` "
                          "(__graft_entry__.build()); there is no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     vp, sz, ci = C.c_void_p, C.c_size_t, C.c_int
     lib.cofdm_last_error.restype = C.c_char_p
     lib.cofdm_version.restype = C.c_char_p

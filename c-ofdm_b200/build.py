@@ -32,11 +32,12 @@ def is_stale():
     return any(os.path.getmtime(s) > t for s in SOURCES)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not is_stale():
+def build_library(force=False, verbose=False, out=None, extra_flags=()):
+    """out / extra_flags: an experimental variant beside the product library (A/B runs through COFDM_LIB_PATH)"""
+    if out is None and not force and not is_stale():
         return LIB
     cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", LIB, os.path.join(HERE, "csrc", "cofdm_host.cu")]
+           "-Xcompiler", "-fPIC", "-shared", "-o", out or LIB, os.path.join(HERE, "csrc", "cofdm_host.cu")] + list(extra_flags)
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -45,8 +46,11 @@ def build_library(force=False, verbose=False):
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
     if verbose:
         sys.stderr.write(r.stderr)
-    return LIB
+    return out or LIB
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    a = sys.argv[1:]
+    out = a[a.index("--out") + 1] if "--out" in a else None
+    flags = a[a.index("--flags") + 1].split() if "--flags" in a else ()
+    print(build_library(force="--force" in a, verbose="-v" in a, out=out, extra_flags=flags))

@@ -161,9 +161,11 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
             const bool al = fmt == COFDM_CI16 ? tma16 : tma;
             const size_t sm = rx_demod512_smem_bytes(h->P.num_symb);
             const unsigned thr = 32u * (unsigned)h->P.num_symb;
-#define COFDM_DM(F, T, W, MW) rx_demod512_kernel<F, T, W, MW><<<(unsigned)n_frames, thr, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
-#define COFDM_DM_PICK(F, T) do { if (h->P.num_symb <= 8) { if (want) COFDM_DM(F, T, true, 8); else COFDM_DM(F, T, false, 8); } \
-                                 else { if (want) COFDM_DM(F, T, true, kMaxFusedSymb); else COFDM_DM(F, T, false, kMaxFusedSymb); } } while (0)
+#define COFDM_DM(F, T, W, MW, MD) rx_demod512_kernel<F, T, W, MW, MD><<<(unsigned)n_frames, thr, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
+            // production instances are specialised on the modulation order (QPSK, 16-QAM); everything else reads it from the configuration
+#define COFDM_DM_PICK(F, T) do { if (h->P.num_symb <= 8) { if (want) COFDM_DM(F, T, true, 8, 0); else if (h->P.mod_type == 4) COFDM_DM(F, T, false, 8, 4); \
+                                                           else if (h->P.mod_type == 2) COFDM_DM(F, T, false, 8, 2); else COFDM_DM(F, T, false, 8, 0); } \
+                                 else { if (want) COFDM_DM(F, T, true, kMaxFusedSymb, 0); else COFDM_DM(F, T, false, kMaxFusedSymb, 0); } } while (0)
             if (fmt == COFDM_CI16) { if (al) COFDM_DM_PICK(kCI16, true); else COFDM_DM_PICK(kCI16, false); }
             else { if (al) COFDM_DM_PICK(kCF32, true); else COFDM_DM_PICK(kCF32, false); }
 #undef COFDM_DM_PICK
@@ -356,7 +358,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     h->P = T.p;
     Params &P = h->P;
     int rc = 0;
-    rc |= upload(h, T.tw_fft, &P.tw_fft);   rc |= upload(h, T.tw_p1, &P.tw_p1);   rc |= upload(h, T.tw_p2, &P.tw_p2);
+    rc |= upload(h, T.tw_fft, &P.tw_fft);   rc |= upload(h, T.tw_p1, &P.tw_p1);   rc |= upload(h, T.tw_p2, &P.tw_p2); rc |= upload(h, T.tw_p2w, &P.tw_p2w);
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
@@ -403,10 +405,11 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
 #undef COFDM_RX_ATTR
         {
             const int smd = (int)rx_demod512_smem_bytes(P.num_symb);
-#define COFDM_DM_ATTR(F, T, W, MW) \
-            if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_demod512_kernel<F, T, W, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smd); \
-            if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_demod512_kernel<F, T, W, MW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-#define COFDM_DM_ATTR_ALL(F, T) COFDM_DM_ATTR(F, T, true, 8); COFDM_DM_ATTR(F, T, false, 8); COFDM_DM_ATTR(F, T, true, kMaxFusedSymb); COFDM_DM_ATTR(F, T, false, kMaxFusedSymb)
+#define COFDM_DM_ATTR(F, T, W, MW, MD) \
+            if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_demod512_kernel<F, T, W, MW, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smd); \
+            if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_demod512_kernel<F, T, W, MW, MD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+#define COFDM_DM_ATTR_ALL(F, T) COFDM_DM_ATTR(F, T, true, 8, 0); COFDM_DM_ATTR(F, T, false, 8, 0); COFDM_DM_ATTR(F, T, false, 8, 2); COFDM_DM_ATTR(F, T, false, 8, 4); \
+                                COFDM_DM_ATTR(F, T, true, kMaxFusedSymb, 0); COFDM_DM_ATTR(F, T, false, kMaxFusedSymb, 0)
             COFDM_DM_ATTR_ALL(kCF32, true); COFDM_DM_ATTR_ALL(kCF32, false); COFDM_DM_ATTR_ALL(kCI16, true); COFDM_DM_ATTR_ALL(kCI16, false);
 #undef COFDM_DM_ATTR_ALL
 #undef COFDM_DM_ATTR

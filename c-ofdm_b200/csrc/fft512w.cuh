@@ -3,10 +3,8 @@
 // Replaces FFTW plans F1/F2 (OFDM/Frame.cpp:16-24) on the receive side.  Every lane owns TWO radix-8
 // butterflies per pass (16 complex values = 32 registers); all arithmetic is packed f32x2 on natural-layout
 // complex numbers (compat.cuh: nadd / nmul / nadd_mj ...), so a butterfly with its 7 twiddles costs 41
-// instructions.  The two exchanges go through one 512-slot float2 region of shared memory that belongs to the
-// warp alone: no CTA or team barrier, only __syncwarp.  Every exchange access is 128 bits wide (two values of
-// the lane's butterfly pair sit next to each other) and bank-conflict free by XOR swizzles
-// (profiles/scripts/bank_check.py enumerates every access of every phase).
+// instructions.  The two exchanges go through one 5152-byte region of shared memory that belongs to the
+// warp alone: no CTA or team barrier, only __syncwarp.
 //
 // Index algebra (forward transform, unnormalised like FFTW's):
 //   n = 64 n1 + 8 n2 + n3,   k = k1 + 8 k2 + 64 k3   (all digits 0..7)
@@ -15,17 +13,20 @@
 //   pass 3  X [k]         = sum_n3 B'[k1,k2;n3]  W8^{n3 k3}
 // Lane maps (slot a / slot b of the lane):
 //   pass 1  lane l        : t = 8 n2 + n3 = 2l / 2l + 1          inputs x[t + 64 n1]   (adjacent samples: 128-bit loads)
-//   pass 2  lane l' = 4 k1 + j   : (k1, n3 = 2j) / (k1, n3 = 2j + 1)
+//   pass 2  lane l' = 4 k1 + j   : (k1, n3 = (j & 1) + 4 (j >> 1)) / (k1, n3 + 2)
 //   pass 3  lane l'' = k2 + 8 a  : (k1 = 2a, k2) / (k1 = 2a + 1, k2)   outputs X[c0 + 64 k3] / X[c0 + 1 + 64 k3], c0 = 2a + 8 k2
-// Exchange layouts (float2 slots):
-//   E1(k1, t)      = 64 k1 + (t ^ ((k1 & 1) << 3))
-//   E2(k1, k2, n3) = 64 k1 + 8 (k2 ^ (k1 & 1)) + 2 ((n3 >> 1) ^ ((k2 >> 1) & 3)) + (n3 & 1)
+// Exchanges: a lane WRITES its two slots with 64-bit stores into two planes (a 128-bit store would need the two values in
+// four consecutive registers, which costs moves) and READS 128 bits = two neighbours of one plane.  Layouts in float2 slots,
+// rows padded so that every access is base register + immediate and no phase of any access has a bank conflict
+// (profiles/scripts/bank_check.py enumerates them all):
+//   E1  plane A (t even) / B (t odd):   648 B' + 40 k1 + (t >> 1)            B' = 1 for plane B (plane B starts at slot 324)
+//   E2  plane A (n3 in {0,1,4,5}) / B (n3 in {2,3,6,7}):   272 B' + 34 k2 + 4 k1 + (n3 & 1) + 2 (n3 >> 2)
 #pragma once
 #include "compat.cuh"
 
 namespace cofdmk {
 
-constexpr int kFft512wSlots = 512;      // float2 slots of the exchange region (16-byte aligned)
+constexpr int kFft512wBytes = (324 + 320) * 8;   // bytes of the exchange region (16-byte aligned): 5152
 
 // multiply by W8^1 = (1 - j)/sqrt2 and W8^3 = (-1 - j)/sqrt2 (forward), natural layout
 COFDM_DEV float2 nmul_w8_1(float2 a) { return nscale(p_add(a, make_float2(a.y, -a.x)), 0.70710678118654752440f); }
@@ -45,10 +46,6 @@ COFDM_DEV void ndft8(float2 (&v)[8]) {
     v[3] = nadd_mj(b6, d57);  v[7] = nadd_pj(b6, d57);
 }
 
-COFDM_DEV int fft512w_e1(int k1, int t) { return 64 * k1 + (t ^ ((k1 & 1) << 3)); }
-COFDM_DEV int fft512w_e2(int k1, int k2, int n3) {
-    return 64 * k1 + 8 * (k2 ^ (k1 & 1)) + ((((n3 >> 1) ^ ((k2 >> 1) & 3)) << 1) | (n3 & 1));
-}
 // bins a lane holds after the transform: slot a = c0 + 64 k3, slot b = c0 + 1 + 64 k3
 COFDM_DEV int fft512w_c0(int lane) { return 2 * (lane >> 3) + 8 * (lane & 7); }
 
@@ -56,10 +53,10 @@ COFDM_DEV int fft512w_c0(int lane) { return 2 * (lane >> 3) + 8 * (lane & 7); }
 // on exit va[k3] / vb[k3] = X[c0 + 64 k3] / X[c0 + 1 + 64 k3].
 // pa, pb: extra factors applied with the pass-1 twiddles (the per-sample CFO rotation of the rx chain contributes
 // exp(-j 2 pi beta (128 + t) / 512) there); pass make_float2(1, 0) for a plain transform.
-// w512 = exp(-j 2 pi k / 512) table (global, 16-byte aligned), tw2 = [8][8] exp(-j 2 pi n3 k2 / 64) (global or shared).
+// w512 = exp(-j 2 pi k / 512) table (global, 16-byte aligned).
 // E: the warp's exchange region; the caller guarantees (by __syncwarp) that nobody still reads it.
 COFDM_DEV void warp_fft512(float2 (&va)[8], float2 (&vb)[8], float2 pa, float2 pb, float2 *E,
-                           const float2 *__restrict__ w512, const float2 *__restrict__ tw2, int lane) {
+                           const float2 *__restrict__ w512, int lane) {
     ndft8(va);
     ndft8(vb);
     {   // pass-1 twiddles by recurrence: T[k1] = p * V^k1, V = W512^t  (seven roundings at most: ~4e-7 relative)
@@ -76,18 +73,18 @@ COFDM_DEV void warp_fft512(float2 (&va)[8], float2 (&vb)[8], float2 pa, float2 p
             vb[k1] = nmul(vb[k1], tb);
         }
     }
-    float4 *E4 = reinterpret_cast<float4 *>(E);
     {
-        const int t = 2 * lane;
+        float2 *w = E + lane;
 #pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) E4[fft512w_e1(k1, t) >> 1] = make_float4(va[k1].x, va[k1].y, vb[k1].x, vb[k1].y);
+        for (int k1 = 0; k1 < 8; k1++) { w[40 * k1] = va[k1]; w[324 + 40 * k1] = vb[k1]; }
     }
     __syncwarp();
     const int k1p = lane >> 2, j = lane & 3;
     {
+        const float4 *r = reinterpret_cast<const float4 *>(E + 324 * (j & 1) + 40 * k1p + 2 * (j >> 1));
 #pragma unroll
         for (int n2 = 0; n2 < 8; n2++) {
-            const float4 q = E4[fft512w_e1(k1p, 8 * n2 + 2 * j) >> 1];
+            const float4 q = r[2 * n2];                                               // t = 8 n2 + n3 and t + 2
             va[n2] = make_float2(q.x, q.y);
             vb[n2] = make_float2(q.z, q.w);
         }
@@ -96,30 +93,37 @@ COFDM_DEV void warp_fft512(float2 (&va)[8], float2 (&vb)[8], float2 pa, float2 p
     ndft8(va);
     ndft8(vb);
     {
-        const float4 *t4 = reinterpret_cast<const float4 *>(tw2);
+        float2 *w = E + 4 * k1p + j;
 #pragma unroll
-        for (int k2 = 1; k2 < 8; k2++) {
-            const float4 w = t4[k2 * 4 + j];                                          // W64^{2j k2}, W64^{(2j+1) k2}
-            va[k2] = nmul(va[k2], make_float2(w.x, w.y));
-            vb[k2] = nmul(vb[k2], make_float2(w.z, w.w));
-        }
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) E4[fft512w_e2(k1p, k2, 2 * j) >> 1] = make_float4(va[k2].x, va[k2].y, vb[k2].x, vb[k2].y);
+        for (int k2 = 0; k2 < 8; k2++) { w[34 * k2] = va[k2]; w[272 + 34 * k2] = vb[k2]; }
     }
     __syncwarp();
     {
-        const int k2 = lane & 7, a = lane >> 3;
+        const float4 *r = reinterpret_cast<const float4 *>(E + 34 * (lane & 7) + 8 * (lane >> 3));   // k2, k1 = 2a
 #pragma unroll
-        for (int jj = 0; jj < 4; jj++) {
-            const float4 q = E4[fft512w_e2(2 * a, k2, 2 * jj) >> 1];
-            va[2 * jj] = make_float2(q.x, q.y);
-            va[2 * jj + 1] = make_float2(q.z, q.w);
-            const float4 r = E4[fft512w_e2(2 * a + 1, k2, 2 * jj) >> 1];
-            vb[2 * jj] = make_float2(r.x, r.y);
-            vb[2 * jj + 1] = make_float2(r.z, r.w);
+        for (int b = 0; b < 2; b++) {                                                 // k1 = 2a + b: slot a / b
+            float2 (&v)[8] = b ? vb : va;
+            const float4 q0 = r[2 * b], q1 = r[2 * b + 1], q2 = r[136 + 2 * b], q3 = r[136 + 2 * b + 1];
+            v[0] = make_float2(q0.x, q0.y); v[1] = make_float2(q0.z, q0.w);
+            v[4] = make_float2(q1.x, q1.y); v[5] = make_float2(q1.z, q1.w);
+            v[2] = make_float2(q2.x, q2.y); v[3] = make_float2(q2.z, q2.w);
+            v[6] = make_float2(q3.x, q3.y); v[7] = make_float2(q3.z, q3.w);
         }
     }
     __syncwarp();
+    {   // pass-2 twiddles W64^{n3 k2}, applied on the reading side where both slots share k2: the seven powers of
+        // w = W64^{k2} come from one 8-byte load and six products (<= 3 roundings) instead of seven 16-byte table loads
+        const float2 w1 = __ldg(w512 + 8 * (lane & 7));                                // W512^{8 k2} = W64^{k2}
+        const float2 w2 = nmul(w1, w1), w3 = nmul(w2, w1), w4 = nmul(w2, w2);
+        const float2 w5 = nmul(w4, w1), w6 = nmul(w3, w3), w7 = nmul(w4, w3);
+        va[1] = nmul(va[1], w1); vb[1] = nmul(vb[1], w1);
+        va[2] = nmul(va[2], w2); vb[2] = nmul(vb[2], w2);
+        va[3] = nmul(va[3], w3); vb[3] = nmul(vb[3], w3);
+        va[4] = nmul(va[4], w4); vb[4] = nmul(vb[4], w4);
+        va[5] = nmul(va[5], w5); vb[5] = nmul(vb[5], w5);
+        va[6] = nmul(va[6], w6); vb[6] = nmul(vb[6], w6);
+        va[7] = nmul(va[7], w7); vb[7] = nmul(vb[7], w7);
+    }
     ndft8(va);
     ndft8(vb);
 }

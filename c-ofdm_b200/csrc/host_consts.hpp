@@ -89,7 +89,7 @@ inline void host_dft(std::vector<cd> &x, int sign) {
 struct HostTables {
     Params p{};                       // sizes filled, device pointers left null
     ConfigMap cfg;
-    std::vector<float2> tw_fft, tw_p1, tw_p2, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
+    std::vector<float2> tw_fft, tw_p1, tw_p2, tw_p2w, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
     std::vector<float2> constell[9];  // index = mod type 1,2,4,6,8
     std::vector<float> t2_mask;
     std::vector<int16_t> bin_map, data_bin, pilot_bin;
@@ -155,23 +155,26 @@ inline void build_f512_roles(HostTables &T) {
         }
     }
     for (int q = ncombo; q < 12; q++) { p.combo_off[q] = 0; p.combo_seg[q] = 0; }
+    p.combo_seg_packed = 0;
+    for (int q = 0; q < 12; q++) p.combo_seg_packed |= (unsigned long long)p.combo_seg[q] << (4 * q);
     auto lane_of = [](int k) { const int c0 = (k & 63) & ~1; return (c0 >> 3) + 8 * ((c0 & 7) >> 1); };
-    T.lane_desc.assign(32, make_uint4(0, 0, 0, 0));
+    const unsigned dummy = 256u << 7;                          // data index 256: a slot nobody reads
+    T.lane_desc.assign(32, make_uint4(dummy | (dummy << 16), dummy | (dummy << 16), dummy | (dummy << 16), dummy | (dummy << 16)));
     int nstrag = 0;
     for (int k = 0; k < 512; k++) {
         const int i = T.bin_map[k];
         if (i < 0) continue;
         const int k3 = k >> 6, lane = lane_of(k), slot = k & 1;
-        const unsigned d = (unsigned)i | ((unsigned)combo_of[seg_of(i)][k3] << 8);
+        const unsigned d = ((unsigned)i << 7) | ((unsigned)combo_of[seg_of(i)][k3] << 3);
         if (k3 == 2 || k3 == 5) {
             if (nstrag >= 7 || strag[nstrag] != k) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
-            p.strag_desc[nstrag++] = d | ((unsigned)(lane * 2 + slot) << 16);
+            p.strag_desc[nstrag++] = d | ((unsigned)(32 * (2 * (k3 == 5) + slot) + lane) << 16) | ((unsigned)(lane * 2 + slot) << 24);
             continue;
         }
         if (k3 == 3 || k3 == 4) throw std::runtime_error("fft-512 map: data in the pruned registers");
         const int w = k3 < 2 ? k3 : k3 - 4;                    // word of the uint4: k3 = 0, 1, 6, 7
         unsigned *u = &T.lane_desc[lane].x;
-        u[w] |= (d | 0x8000u) << (16 * slot);
+        u[w] = (u[w] & ~(0xffffu << (16 * slot))) | (d << (16 * slot));
     }
     if (nstrag != 7) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
     p.strag_desc[7] = 0;
@@ -259,6 +262,15 @@ inline HostTables build_tables(const ConfigMap &cfg) {
             const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((n3 * k2) % 64) / 64.0L;
             T.tw_p2[k2 * 8 + n3] = make_float2((float)cosl(ang), (float)sinl(ang));
         }
+
+    T.tw_p2w.resize(8 * 4 * 2);
+    for (int k2 = 0; k2 < 8; k2++)
+        for (int j = 0; j < 4; j++)
+            for (int u = 0; u < 2; u++) {
+                const int n3 = (j & 1) + 4 * (j >> 1) + 2 * u;
+                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((n3 * k2) % 64) / 64.0L;
+                T.tw_p2w[(k2 * 4 + j) * 2 + u] = make_float2((float)cosl(ang), (float)sinl(ang));
+            }
 
     for (int m : {1, 2, 4, 6, 8}) {
         T.constell_d[m] = constellation_d(m);

@@ -42,6 +42,7 @@ struct Params {
     const float2 *tw_fft;        // [fft_size]  exp(-j*2*pi*k/fft_size)
     const float2 *tw_p1;         // [8][64]     exp(-j*2*pi*t*k1/512)     (fused 512 path, pass-1 twiddles)
     const float2 *tw_p2;         // [8][8]      exp(-j*2*pi*n3*k2/64)     (fused 512 path, pass-2 twiddles)
+    const float2 *tw_p2w;        // [8][4][2]   the same for the one-warp transform: n3 = (j & 1) + 4 (j >> 1), then n3 + 2
     const float2 *tw_pf;         // [pf_size]   exp(-j*2*pi*k/pf_size)
     const float2 *tw_t2;         // [t2sin_size]
     const float *t2_mask;        // [t2sin_size] detect_mask (Frame.cpp:120-133)
@@ -55,13 +56,14 @@ struct Params {
     const int16_t *pilot_bin;    // [num_pilot_subc]
     // ---- one-warp-per-symbol receive kernels of the fft-512 geometry (rx512n.cuh) ----
     // After warp_fft512 a lane holds bins c0 + 64 k3 (slot a) and c0 + 1 + 64 k3 (slot b).  lane_desc: per lane 8 x 16 bits
-    // for k3 = 0, 1, 6, 7 x slot a, b: data index in the symbol | combination << 8 | 0x8000 if the bin carries data.
+    // for k3 = 0, 1, 6, 7 x slot a, b: [15:7] data index in the symbol (256: the bin carries no data), [6:3] combination.
     // A combination is a (segment, k3) pair; combo_off = i' - ((bin & 63) - 1) for its bins (i' = data index, minus 256 in the
     // negative half: the channel line's abscissa, Frame.hpp:425-430), combo_seg its segment.  strag_desc: the data bins of
-    // registers k3 = 2 and 5: data index | combination << 8 | (origin lane * 2 + slot) << 16.
+    // registers k3 = 2 and 5: the same 16 bits | scratch slot (32 (2 [k3 = 5] + slot) + origin lane) << 16 | (origin lane * 2 + slot) << 24.
     const uint4 *lane_desc;      // [32]
     short combo_off[12];
     signed char combo_seg[12];
+    unsigned long long combo_seg_packed;   // 4 bits per combination
     unsigned strag_desc[8];
 };
 

@@ -43,20 +43,21 @@ COFDM_HD constexpr int f512_k3(int k) { return k >> 6; }
 constexpr int kF512Strag = 7;
 constexpr int kF512Combos = 12;
 
-constexpr int kDemodRegion = 640 * 8;          // bytes of a warp's staging / exchange region
+constexpr int kDemodTabOff = kFft512wBytes;    // phasor table of the rotation (21 float2), beside the exchange planes
+constexpr int kDemodRegion = 5376;             // bytes of a warp's region: staging (5120) / exchanges (5152) + phasor table (168); 42 x 128
+// after the transform the region holds: [0, 1024) registers k3 = 2, 5 of every lane as four planes (k3 = 2 slot a, b;
+// k3 = 5 slot a, b); [1024, 1152) the 12 segment coefficients; [1280, 1552) one byte per demapped symbol (+ dummy slots
+// for bins that carry no data)
+constexpr int kDemodWtOff = 1024, kDemodSymOff = 1280;
 
-struct DemodShared {
+struct alignas(16) DemodShared {
     uint64_t mbar[kRxMaxSym];
     float2 pil[kRxMaxSym][8];        // pilot bins per message symbol (index s - 1)
     float pabs[kRxMaxSym];           // sum |pilot| per message symbol, zero beyond the last one
-    float theta_t[kRxMaxSym + 1];    // Arg(C_s) in turns, by frame symbol index (taps)
-    int mshift[kRxMaxSym + 1];       // m_s
     float4 lcl[32];                  // per pass-3 lane: exp(-j b (c0 - 1)), exp(-j b c0)
     float2 ftab[16];                 // per (segment, k3) combination: c_1 exp(-j (b off + a))
-    float2 wtab[kRxMaxSym][16];      // per warp: segment coefficient times ftab
-    float2 strag[kRxMaxSym][8];      // per warp: the straggler bins' spectrum values
-    float4 qtab[kRxMaxSym][5];       // per warp, as float2[10]: Q^r (r < 8), D
-    alignas(16) uint8_t sym[kRxMaxSym][256];   // per warp: demapped symbols
+    float theta_t[kRxMaxSym + 1];    // Arg(C_s) in turns, by frame symbol index (taps)
+    int mshift[kRxMaxSym + 1];       // m_s
 };
 
 COFDM_HD size_t rx_demod512_smem_bytes(int num_symb) { return (size_t)num_symb * kDemodRegion + sizeof(DemodShared); }
@@ -75,15 +76,15 @@ COFDM_DEV void warp_stage_symbol(void *dst, const char *src, int lane) {
     }
 }
 
-// two adjacent staged samples (index 2u, 2u + 1)
-template <int FMT>
+// two adjacent samples (index 2u, 2u + 1) of a symbol staged in shared memory, or (GLOBAL) straight from the capture
+template <int FMT, bool GLOBAL = false>
 COFDM_DEV void staged_pair(const void *region, int u, float2 &a, float2 &b) {
     if (FMT == kCI16) {
-        const uint2 w = reinterpret_cast<const uint2 *>(region)[u];
+        const uint2 w = GLOBAL ? __ldg(reinterpret_cast<const uint2 *>(region) + u) : reinterpret_cast<const uint2 *>(region)[u];
         a = make_float2((float)(short)(w.x & 0xffffu), (float)(short)(w.x >> 16));
         b = make_float2((float)(short)(w.y & 0xffffu), (float)(short)(w.y >> 16));
     } else {
-        const float4 q = reinterpret_cast<const float4 *>(region)[u];
+        const float4 q = GLOBAL ? __ldg(reinterpret_cast<const float4 *>(region) + u) : reinterpret_cast<const float4 *>(region)[u];
         a = make_float2(q.x, q.y);
         b = make_float2(q.z, q.w);
     }
@@ -94,13 +95,57 @@ COFDM_DEV float2 rot_phasor(float theta, int m, int J) {
     return fast_cis_turns(-(theta * ((float)J * (1.0f / 512.0f)) + (float)((m * J) & 511) * (1.0f / 512.0f)));
 }
 
-template <int FMT, bool USE_TMA, bool TAPS, int MAXW>
-__global__ void __launch_bounds__(32 * MAXW, MAXW <= 8 ? 4 : 1)
+// hard decision of one equalised point, natural layout (modulation.cpp:53-87): clamp to [-1,1], (v + 1) half + 0.5, truncate
+// == truncate v half + (half + 0.5) with the level clamped to [0, 2 half]; the float -> unsigned conversion saturates at 0.
+// MOD > 0: modulation order known at compile time; MOD == 0: taken from dk.
+template <int MOD>
+COFDM_DEV unsigned demap_n(float2 z, const DemapK &dk) {
+    const int mod = MOD ? MOD : dk.mod;
+    if (mod == 1) return z.x + z.y > 0.0f ? 1u : 0u;
+    const float half = MOD ? 0.5f * (float)((1 << (MOD >> 1)) - 1) : dk.half;
+    const unsigned lmax = MOD ? (unsigned)((1 << (MOD >> 1)) - 1) : (unsigned)dk.lmax;
+    const float2 u = p_fma(z, make_float2(half, half), make_float2(half + 0.5f, half + 0.5f));
+    const unsigned li = min(__float2uint_rz(u.x), lmax), lq = min(__float2uint_rz(u.y), lmax);
+    return MOD ? lq * (unsigned)(1 << (MOD >> 1)) + li : (li | (lq << dk.qshift));
+}
+
+// MSB-first packing of 8 demapped symbols (one per byte of raw) into `mod` bytes (modulation.cpp:90-125)
+template <int MOD>
+COFDM_DEV void pack8(uint2 raw, uint8_t *dst, int mod_rt) {
+    const int mod = MOD ? MOD : mod_rt;
+    if (mod == 4) {
+        // 16-QAM: wire byte k = (symbol 2k << 4) | symbol 2k+1
+        const unsigned ux = ((raw.x << 4) & 0x00f000f0u) | ((raw.x >> 8) & 0x000f000fu);
+        const unsigned uy = ((raw.y << 4) & 0x00f000f0u) | ((raw.y >> 8) & 0x000f000fu);
+        const unsigned lo = (ux & 0xffu) | ((ux >> 8) & 0xff00u), hi = (uy & 0xffu) | ((uy >> 8) & 0xff00u);
+        *reinterpret_cast<unsigned *>(dst) = lo | (hi << 16);
+    } else if (mod == 2) {
+        const unsigned b0 = ((raw.x & 3u) << 6) | ((raw.x >> 4) & 0x30u) | ((raw.x >> 14) & 0xcu) | (raw.x >> 24);
+        const unsigned b1 = ((raw.y & 3u) << 6) | ((raw.y >> 4) & 0x30u) | ((raw.y >> 14) & 0xcu) | (raw.y >> 24);
+        *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(b0 | (b1 << 8));
+    } else {
+        unsigned long long bits = 0;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const unsigned sy = ((e < 4 ? raw.x : raw.y) >> (8 * (e & 3))) & 0xffu;
+            bits = (bits << mod) | (unsigned long long)sy;
+        }
+        for (int bq = 0; bq < mod; bq++) dst[bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
+    }
+}
+
+// MOD: modulation order the instance is specialised for (2, 4), or 0 = any (read from the configuration)
+#ifndef COFDM_DEMOD_MINB
+#define COFDM_DEMOD_MINB 4
+#endif
+template <int FMT, bool USE_TMA, bool TAPS, int MAXW, int MOD>
+__global__ void __launch_bounds__(32 * MAXW, MAXW <= 8 ? COFDM_DEMOD_MINB : 1)
 rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
                    uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous, const RxTaps taps,
                    const int sync_less, const FrameScal *__restrict__ fscal) {
     COFDM_DYN_SMEM(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction: lets the compiler keep the warp's bases in uniform registers
     const int frame = blockIdx.x;
     if (frame >= n_frames) return;
     const int nw = P.num_symb;                     // one warp per message symbol
@@ -111,6 +156,10 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     const char *src = reinterpret_cast<const char *>(samples) + ((size_t)frame * (size_t)frame_stride + (size_t)s * 640) * sample_bytes;
 
     // ---- stage the symbol: one TMA bulk copy issued by the warp that consumes it ----
+#ifdef COFDM_DEMOD_DIRECT
+    if (USE_TMA) {
+    } else
+#endif
     if (USE_TMA) {
         if (lane == 0) {
             mbar_init(&M->mbar[warp], 1);
@@ -122,38 +171,61 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         warp_stage_symbol<FMT>(region, src, lane);
     }
     // ---- while the copy is in flight: the acquire kernel's scalars and the frame-wide tables ----
-    FrameScal fs;
-    if (sync_less) { fs.kc = 0; fs.m0 = 0; fs.th0 = 0.f; fs.theta = 0.f; fs.rot_theta = make_float2(1.f, 0.f); fs.a = 0.0; fs.b = 0.0; }
-    else fs = fscal[frame];
+    // (FrameScal is 40 bytes: lanes 0..4 fetch 8 bytes each -- {kc, m0} {th0, theta} {rot_theta} {a} {b} -- and the fields
+    //  travel by shuffle to the few lanes that need them; every lane needs kc only)
+    uint2 fsw = make_uint2(0u, 0u);
+    if (!sync_less && lane < 5) fsw = __ldg(reinterpret_cast<const uint2 *>(fscal + frame) + lane);
+    if (sync_less && lane == 2) fsw.x = 0x3f800000u;        // sync-less: kc = m0 = 0, th0 = theta = 0, rot_theta = 1, a = b = 0
+    const int kc = (int)__shfl_sync(0xffffffffu, fsw.x, 0);
     if (tid >= nw && tid < kRxMaxSym) M->pabs[tid] = 0.f;   // unused entries (the others are written by their warps); ordered by the block barrier
-    const float inv2pi = 0.15915494309189533577f;
-    const float bt = (float)fs.b * inv2pi;         // channel-line slope in turns per data index
     if (warp == 0) {
         // per pass-3 lane: exp(-j b (c0 - 1)), exp(-j b c0)
+        const double fb = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 4), (int)__shfl_sync(0xffffffffu, fsw.x, 4));
+        const float bt = (float)fb * 0.15915494309189533577f;           // channel-line slope in turns per data index
         const int c0 = fft512w_c0(lane);
         const float2 la = cis_neg_turns_f(bt * (float)(c0 - 1)), lb = cis_neg_turns_f(bt * (float)c0);
         M->lcl[lane] = make_float4(la.x, la.y, lb.x, lb.y);
     }
-    if (warp == nw - 1 && lane < kF512Combos) {
-        // c_1 exp(-j (b off + a)): the constant phase of message symbol 0 (Psi_1 = 1.25 (theta_0 + m_0) mod 1), theta, the channel line
-        float acc = fs.th0 * (640.0f / 512.0f);
-        acc -= rintf(acc);
-        const float psi1 = acc + (float)((5 * fs.m0) & 3) * 0.25f;
-        const float2 c1 = nmul(cis_neg_turns_f(psi1), fs.rot_theta);
-        const float2 ee = cis_neg_turns_f((float)((fs.b * (double)P.combo_off[lane] + fs.a) * 0.15915494309189533577));
-        M->ftab[lane] = nmul(c1, ee);
+    float2 rot_theta = make_float2(1.f, 0.f);
+    if (warp == nw - 1 || TAPS) {
+        const int m0 = (int)__shfl_sync(0xffffffffu, fsw.y, 0);
+        const float th0 = __uint_as_float(__shfl_sync(0xffffffffu, fsw.x, 1));
+        rot_theta = make_float2(__uint_as_float(__shfl_sync(0xffffffffu, fsw.x, 2)), __uint_as_float(__shfl_sync(0xffffffffu, fsw.y, 2)));
+        const double fa = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 3), (int)__shfl_sync(0xffffffffu, fsw.x, 3));
+        const double fb = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 4), (int)__shfl_sync(0xffffffffu, fsw.x, 4));
+        if (warp == nw - 1 && lane < kF512Combos) {
+            // c_1 exp(-j (b off + a)): the constant phase of message symbol 0 (Psi_1 = 1.25 (theta_0 + m_0) mod 1), theta, the channel line
+            float acc = th0 * (640.0f / 512.0f);
+            acc -= rintf(acc);
+            const float psi1 = acc + (float)((5 * m0) & 3) * 0.25f;
+            const float2 c1 = nmul(cis_neg_turns_f(psi1), rot_theta);
+            const float2 ee = cis_neg_turns_f((float)((fb * (double)P.combo_off[lane] + fa) * 0.15915494309189533577));
+            M->ftab[lane] = nmul(c1, ee);
+        }
+        if (TAPS && tid == 0) { M->theta_t[0] = th0; M->mshift[0] = m0; }
     }
-    if (TAPS && tid == 0) { M->theta_t[0] = fs.th0; M->mshift[0] = fs.m0; }
     __syncwarp();
+#ifndef COFDM_DEMOD_DIRECT
     if (USE_TMA) mbar_wait(&M->mbar[warp], 0);
+#endif
 
     // ---- the lane's 16 body samples (pass-1 layout: t = 2 lane, 2 lane + 1; index 128 + t + 64 r) and 4 CP samples ----
     float2 va[8], vb[8], cpa[2], cpb[2];
+#ifdef COFDM_DEMOD_DIRECT
+    if (USE_TMA) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) staged_pair<FMT, true>(src, 64 + lane + 32 * r, va[r], vb[r]);
+#pragma unroll
+        for (int c = 0; c < 2; c++) staged_pair<FMT, true>(src, lane + 32 * c, cpa[c], cpb[c]);
+    } else
+#endif
+    {
 #pragma unroll
     for (int r = 0; r < 8; r++) staged_pair<FMT>(region, 64 + lane + 32 * r, va[r], vb[r]);
 #pragma unroll
     for (int c = 0; c < 2; c++) staged_pair<FMT>(region, lane + 32 * c, cpa[c], cpb[c]);
-    __syncwarp();                                  // the region may now be reused by the exchanges
+    }
+    __syncwarp();                                  // the region may now be reused (phasor table, exchanges)
 
     // ---- CP correlation (Frame.hpp:251-253): CP sample j pairs with body sample j + 512, i.e. r = 6, 7 ----
     float theta = 0.f;
@@ -165,18 +237,24 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         for (int o = 16; o > 0; o >>= 1) c = nadd(c, make_float2(__shfl_xor_sync(0xffffffffu, c.x, o), __shfl_xor_sync(0xffffffffu, c.y, o)));
         theta = fast_atan2_turns(c.y, c.x);
         // m_s and the reference's phi_s (Frame.hpp:254): phi = theta - 512 shift + m in (-0.5, 0.5]
-        m = (int)ceilf(-(theta - (float)fs.kc * P.pf_bins512) - 0.5f);
+        m = (int)ceilf(-(theta - (float)kc * P.pf_bins512) - 0.5f);
     }
     if (TAPS && lane == 0) { M->theta_t[s] = theta; M->mshift[s] = m; }
 
-    // ---- rotation phasors: Q^r = exp(-j 2 pi beta 64 r / 512) (r < 8), D = exp(-j 2 pi beta / 512), P(t) ----
-    float2 *qt = reinterpret_cast<float2 *>(M->qtab[warp]);
-    if (lane < 9) qt[lane] = lane < 8 ? rot_phasor(theta, m, 64 * lane) : rot_phasor(theta, m, 1);
-    const float2 pa = rot_phasor(theta, m, 128 + 2 * lane);
+    // ---- rotation phasors, ONE sincos per lane: table entry `lane` = exp(-j 2 pi beta J / 512) with
+    //      J = 64 lane (lane < 8: Q^r), 1 (lane 8: D), 16 (lane - 9) (9..12: U^u), 128 + 2 (lane - 13) (13..20: V^v);
+    //      P(t = 2 lane) = exp(-j 2 pi beta (128 + 2 lane) / 512) = V^(lane & 7) U^(lane >> 3) ----
+    float2 *qt = reinterpret_cast<float2 *>(region + kDemodTabOff);
+    {
+        const int J = lane < 8 ? 64 * lane : (lane == 8 ? 1 : (lane < 13 ? 16 * (lane - 9) : 128 + 2 * (lane - 13)));
+        const float2 ph = rot_phasor(theta, m, J);
+        if (lane < 21) qt[lane] = ph;
+    }
     __syncwarp();
+    const float2 pa = nmul(qt[13 + (lane & 7)], qt[9 + (lane >> 3)]);
     const float2 pb = nmul(pa, qt[8]);
     if (TAPS && taps.synced != nullptr) {
-        // debug tap, completed by rx_synced_fixup_kernel (per-symbol constant phase and theta)
+        // debug tap, completed by rx_synced_fixup2_kernel (per-symbol constant phase and theta)
         float2 *d = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
         const int t = 2 * lane;
 #pragma unroll
@@ -198,19 +276,18 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
             vb[2 * rr + 1] = nmul(vb[2 * rr + 1], make_float2(q.z, q.w));
         }
     }
-    warp_fft512(va, vb, pa, pb, reinterpret_cast<float2 *>(region), P.tw_fft, P.tw_p2, lane);
-    // now va[k3] = X[c0 + 64 k3], vb[k3] = X[c0 + 1 + 64 k3], c0 = 2 (lane >> 3) + 8 (lane & 7)
+    warp_fft512(va, vb, pa, pb, reinterpret_cast<float2 *>(region), P.tw_fft, lane);
+    // now va[k3] = X[c0 + 64 k3], vb[k3] = X[c0 + 1 + 64 k3], c0 = 2 (lane >> 3) + 8 (lane & 7); the region is free again
 
-    // ---- pilots, sum |pilot| (Frame.cpp:76-80) and the straggler bins to shared memory ----
+    // ---- pilots and sum |pilot| (Frame.cpp:76-80) to the CTA's shared memory; registers k3 = 2, 5 (the straggler data bins
+    //      128..131 and 381..383 live there) to the warp's region ----
+    float2 *scratch = reinterpret_cast<float2 *>(region);
     {
         float2 *pil = M->pil[warp];
 #define COFDM_X(p, bin) if (lane == f512_lane(bin)) pil[p] = (f512_slot(bin) ? vb : va)[f512_k3(bin)];
         COFDM_F512_PILOTS(COFDM_X)
 #undef COFDM_X
-        float2 *sg = M->strag[warp];
-#define COFDM_X(q, bin) if (lane == f512_lane(bin)) sg[q] = (f512_slot(bin) ? vb : va)[f512_k3(bin)];
-        COFDM_F512_STRAG(COFDM_X)
-#undef COFDM_X
+        scratch[lane] = va[2]; scratch[32 + lane] = vb[2]; scratch[64 + lane] = va[5]; scratch[96 + lane] = vb[5];
         __syncwarp();
         float pm = 0.f;
         if (lane < 8) pm = sqrtf(cnorm2(pil[lane]));
@@ -223,22 +300,22 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
 
     float g;                                       // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
     {
-        const float4 *p4 = reinterpret_cast<const float4 *>(M->pabs);
-        const float4 p0 = p4[0], p1 = p4[1], p2 = p4[2], p3 = p4[3];
-        g = (((p0.x + p0.y) + (p0.z + p0.w)) + ((p1.x + p1.y) + (p1.z + p1.w))) + (((p2.x + p2.y) + (p2.z + p2.w)) + ((p3.x + p3.y) + (p3.z + p3.w)));
-        g *= P.inv_pilot_norm;
+        float pv = M->pabs[lane & (kRxMaxSym - 1)];
+#pragma unroll
+        for (int o = kRxMaxSym / 2; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
+        g = pv * P.inv_pilot_norm;
     }
     const float4 lcv = M->lcl[lane];
     const float2 lca = make_float2(lcv.x, lcv.y), lcb = make_float2(lcv.z, lcv.w);
 
     // ---- the 12 segment coefficients of this symbol (Frame.cpp:89-92 + rx.cpp:214-216):
     //      W[q] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) * ftab[q],  e = segment of combination q ----
-    float2 *wt = M->wtab[warp];
+    char *wt = region + kDemodWtOff;
     if (lane < kF512Combos) {
-        const int e = P.combo_seg[lane];
+        const int e = (int)((P.combo_seg_packed >> (4 * lane)) & 7ull);
         const float2 p1 = M->pil[0][e], ps = M->pil[warp][e];
         const float2 w = nscale(nmulc(p1, ps), __fdividef(1.0f, cnorm2(ps) * g));
-        wt[lane] = nmul(w, M->ftab[lane]);
+        reinterpret_cast<float2 *>(wt)[lane] = nmul(w, M->ftab[lane]);
     }
     __syncwarp();
 
@@ -255,7 +332,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         if (taps.grid != nullptr) {
             // FFT_buf after FFT_FORM::read's normalisation: every bin, with the symbol's constant phase and theta
             const float psi = sym_turns(M->theta_t, M->mshift, s);
-            const float2 rs = nscale(nmul(cis_neg_turns_f(psi), fs.rot_theta), 1.0f / g);
+            const float2 rs = nscale(nmul(cis_neg_turns_f(psi), rot_theta), 1.0f / g);
             float2 *dst = taps.grid + ((size_t)frame * nw + (s - 1)) * 512;
             const int c0 = fft512w_c0(lane);
 #pragma unroll
@@ -263,65 +340,53 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         }
     }
 
-    // ---- equalise + hard demap (modulation.cpp:53-87) straight from the registers ----
+    // ---- equalise + hard demap (modulation.cpp:53-87) straight from the registers.  Per slot 16 descriptor bits:
+    //      [15:7] data index (>= 256: a dummy slot, the bin carries no data), [6:3] combination.  No branches. ----
     const DemapK dk = make_demapk(P.mod_type);
-    uint8_t *sb = M->sym[warp];
-    const bool count_amb = ambiguous != nullptr;
-    int n_amb = 0;
-    const uint4 desc = __ldg(&P.lane_desc[lane]);  // 8 x 16 bits: data index | combination << 8 | valid << 15
+    uint8_t *sb = reinterpret_cast<uint8_t *>(region + kDemodSymOff);
+    const uint4 desc = __ldg(&P.lane_desc[lane]);
     float2 *ctap = (TAPS && taps.constell != nullptr) ? taps.constell + ((size_t)frame * nw + (s - 1)) * 256 : nullptr;
-#define COFDM_EQ(X, LC, D16)                                                             \
-    do {                                                                                 \
-        const unsigned d_ = (D16);                                                       \
-        if (d_ & 0x8000u) {                                                              \
-            const int i_ = (int)(d_ & 0xffu);                                            \
-            const float2 z_ = nmul(nmul((X), (LC)), wt[(d_ >> 8) & 15u]);                \
-            if (TAPS && ctap != nullptr) ctap[i_] = z_;                                  \
-            sb[i_] = (uint8_t)demap_fast(z_, dk);                                        \
-            if (count_amb) n_amb += demap_ambiguous(z_, dk) ? 1 : 0;                     \
-        }                                                                                \
-    } while (0)
-    COFDM_EQ(va[0], lca, desc.x & 0xffffu); COFDM_EQ(vb[0], lcb, desc.x >> 16);
-    COFDM_EQ(va[1], lca, desc.y & 0xffffu); COFDM_EQ(vb[1], lcb, desc.y >> 16);
-    COFDM_EQ(va[6], lca, desc.z & 0xffffu); COFDM_EQ(vb[6], lcb, desc.z >> 16);
-    COFDM_EQ(va[7], lca, desc.w & 0xffffu); COFDM_EQ(vb[7], lcb, desc.w >> 16);
+    const float2 xa0 = nmul(va[0], lca), xa1 = nmul(va[1], lca), xa6 = nmul(va[6], lca), xa7 = nmul(va[7], lca);
+    const float2 xb0 = nmul(vb[0], lcb), xb1 = nmul(vb[1], lcb), xb6 = nmul(vb[6], lcb), xb7 = nmul(vb[7], lcb);
+    float2 xs = make_float2(0.f, 0.f);             // the straggler this lane equalises (lanes 0..6)
+    unsigned ds = 0x8000u;                         // dummy slot 256
     if (lane < kF512Strag) {
-        // the seven data bins that live in registers k3 = 2 and 5 of four lanes
-        const unsigned d16 = P.strag_desc[lane];   // data index | combination << 8 | (origin lane * 2 + slot) << 16
-        const float2 lsrc = reinterpret_cast<const float2 *>(M->lcl)[d16 >> 16];
-        COFDM_EQ(M->strag[warp][lane], lsrc, (d16 & 0x7fffu) | 0x8000u);
+        const unsigned d32 = P.strag_desc[lane];   // descriptor | scratch slot << 16 | (origin lane * 2 + slot) << 24
+        ds = d32 & 0xffffu;
+        xs = nmul(scratch[(d32 >> 16) & 0xffu], reinterpret_cast<const float2 *>(M->lcl)[d32 >> 24]);
     }
+#define COFDM_EQ(X, IDX, WOFF)                                                                   \
+    do {                                                                                         \
+        const float2 z_ = nmul((X), *reinterpret_cast<const float2 *>(wt + (WOFF)));             \
+        if (TAPS && ctap != nullptr && (IDX) < 256u) ctap[(IDX)] = z_;                           \
+        sb[(IDX)] = (uint8_t)demap_n<MOD>(z_, dk);                                               \
+    } while (0)
+#define COFDM_EQ_ALL(F)                                                                          \
+    F(xa0, (desc.x >> 7) & 0x1ffu, desc.x & 0x78u); F(xb0, desc.x >> 23, (desc.x >> 16) & 0x78u); \
+    F(xa1, (desc.y >> 7) & 0x1ffu, desc.y & 0x78u); F(xb1, desc.y >> 23, (desc.y >> 16) & 0x78u); \
+    F(xa6, (desc.z >> 7) & 0x1ffu, desc.z & 0x78u); F(xb6, desc.z >> 23, (desc.z >> 16) & 0x78u); \
+    F(xa7, (desc.w >> 7) & 0x1ffu, desc.w & 0x78u); F(xb7, desc.w >> 23, (desc.w >> 16) & 0x78u); \
+    F(xs, (ds >> 7) & 0x1ffu, ds & 0x78u)
+    COFDM_EQ_ALL(COFDM_EQ);
 #undef COFDM_EQ
-    if (count_amb) {
+    if (ambiguous != nullptr) {
+        // optional count of boundary-ambiguous decisions (margin kAmbigMargin): the points are recomputed, off the fast path
+        int n_amb = 0;
+#define COFDM_AMB(X, IDX, WOFF) \
+        if ((IDX) < 256u) n_amb += demap_ambiguous(nmul((X), *reinterpret_cast<const float2 *>(wt + (WOFF))), dk) ? 1 : 0
+        COFDM_EQ_ALL(COFDM_AMB);
+#undef COFDM_AMB
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) n_amb += __shfl_xor_sync(0xffffffffu, n_amb, o);
         if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
     }
+#undef COFDM_EQ_ALL
     __syncwarp();
     // ---- pack: 8 consecutive symbols of `mod` bits = `mod` whole bytes, MSB first (modulation.cpp:90-125) ----
     {
-        const int mod = P.mod_type;
+        const int mod = MOD ? MOD : P.mod_type;
         const uint2 raw = *reinterpret_cast<const uint2 *>(sb + 8 * lane);
-        uint8_t *dst = out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - 1) * 32 * mod + (size_t)lane * mod;
-        if (mod == 4) {
-            // 16-QAM: wire byte k = (symbol 2k << 4) | symbol 2k+1
-            const unsigned ux = ((raw.x << 4) & 0x00f000f0u) | ((raw.x >> 8) & 0x000f000fu);
-            const unsigned uy = ((raw.y << 4) & 0x00f000f0u) | ((raw.y >> 8) & 0x000f000fu);
-            const unsigned lo = (ux & 0xffu) | ((ux >> 8) & 0xff00u), hi = (uy & 0xffu) | ((uy >> 8) & 0xff00u);
-            *reinterpret_cast<unsigned *>(dst) = lo | (hi << 16);
-        } else if (mod == 2) {
-            const unsigned b0 = ((raw.x & 3u) << 6) | ((raw.x >> 4) & 0x30u) | ((raw.x >> 14) & 0xcu) | (raw.x >> 24);
-            const unsigned b1 = ((raw.y & 3u) << 6) | ((raw.y >> 4) & 0x30u) | ((raw.y >> 14) & 0xcu) | (raw.y >> 24);
-            *reinterpret_cast<unsigned short *>(dst) = (unsigned short)(b0 | (b1 << 8));
-        } else {
-            unsigned long long bits = 0;
-#pragma unroll
-            for (int e = 0; e < 8; e++) {
-                const unsigned sy = ((e < 4 ? raw.x : raw.y) >> (8 * (e & 3))) & 0xffu;
-                bits = (bits << mod) | (unsigned long long)sy;
-            }
-            for (int bq = 0; bq < mod; bq++) dst[bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
-        }
+        pack8<MOD>(raw, out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - 1) * 32 * mod + (size_t)lane * mod, mod);
     }
 }
 

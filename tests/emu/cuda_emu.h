@@ -115,6 +115,8 @@ static inline unsigned __ballot_sync(unsigned, int pred) {
     return r;
 }
 
+static inline double __hiloint2double(int hi, int lo) { uint64_t u = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo; double d; std::memcpy(&d, &u, 8); return d; }
+static inline float __uint_as_float(unsigned u) { float f; std::memcpy(&f, &u, 4); return f; }
 static inline unsigned __float_as_uint(float f) { unsigned u; std::memcpy(&u, &f, 4); return u; }
 static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     for (int o = 16; o > 0; o >>= 1) v = std::max(v, emu::shfl_idx(v, (int)(emu::t_tid & 31) ^ o));
@@ -148,6 +150,7 @@ static inline void sincospif(float x, float *s, float *c) { *s = (float)std::sin
 static inline void sincospi(double x, double *s, double *c) { *s = std::sin(M_PI * x); *c = std::cos(M_PI * x); }
 static inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
 static inline int __float2int_rz(float x) { return (int)x; }
+static inline unsigned __float2uint_rz(float x) { return x > 0.0f ? (x >= 4294967296.0f ? 0xffffffffu : (unsigned)x) : 0u; }   // saturating, NaN -> 0
 static inline int __float2int_rn(float x) { return (int)std::nearbyint(x); }
 static inline float __int2float_rn(int x) { return (float)x; }
 static inline float __fdividef(float a, float b) { return a / b; }

@@ -18,7 +18,7 @@ static void wire(EmuHandle *h) {
     HostTables &T = h->T;
     h->P = T.p;
     Params &P = h->P;
-    P.tw_fft = T.tw_fft.data(); P.tw_p1 = T.tw_p1.data(); P.tw_p2 = T.tw_p2.data();
+    P.tw_fft = T.tw_fft.data(); P.tw_p1 = T.tw_p1.data(); P.tw_p2 = T.tw_p2.data(); P.tw_p2w = T.tw_p2w.data();
     P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
@@ -32,8 +32,10 @@ static void emu_demod512(const Params &P, const void *samples, int fmt, int use_
                          uint8_t *out, unsigned long long *amb, const RxTaps &taps, const FrameScal *fs) {
     const dim3 grid(n_frames), block(32 * P.num_symb);
     const size_t sm = rx_demod512_smem_bytes(P.num_symb);
-#define EMU_DM(F, T, MW) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW>(P, samples, stride, n_frames, out, amb, taps, 0, fs); })
-#define EMU_DM_PICK(F, T) do { if (P.num_symb <= 8) EMU_DM(F, T, 8); else EMU_DM(F, T, kMaxFusedSymb); } while (0)
+#define EMU_DM(F, T, MW, MD) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW, MD>(P, samples, stride, n_frames, out, amb, taps, 0, fs); })
+    // as launch_rx does: production instances specialised on QPSK / 16-QAM, everything else generic
+#define EMU_DM_PICK(F, T) do { if (P.num_symb <= 8) { if (!TAPS && P.mod_type == 4) EMU_DM(F, T, 8, TAPS ? 0 : 4); else if (!TAPS && P.mod_type == 2) EMU_DM(F, T, 8, TAPS ? 0 : 2); else EMU_DM(F, T, 8, 0); } \
+                               else EMU_DM(F, T, kMaxFusedSymb, 0); } while (0)
     if (fmt == kCI16) { if (use_tma) EMU_DM_PICK(kCI16, true); else EMU_DM_PICK(kCI16, false); }
     else { if (use_tma) EMU_DM_PICK(kCF32, true); else EMU_DM_PICK(kCF32, false); }
 #undef EMU_DM_PICK
