@@ -143,7 +143,17 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     } while (0)
     if (split) {
         // acquire: preamble -> 48 bytes of scalars per frame; two frames per CTA unless every synchronisation stage is off
-        if (!sync_less) {
+        if (!sync_less && h->rx_warp) {
+            // one warp per frame (rx512n.cuh)
+            const bool al = fmt == COFDM_CI16 ? tma16 : tma;
+            const unsigned g4 = (unsigned)((n_frames + kAcqwWarps - 1) / kAcqwWarps);
+#define COFDM_ACQW(F, T) \
+            do { if (want) rx_acquire512w_kernel<F, T, true><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc, 0); \
+                 else rx_acquire512w_kernel<F, T, false><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc, 0); } while (0)
+            if (fmt == COFDM_CI16) { if (al) COFDM_ACQW(kCI16, true); else COFDM_ACQW(kCI16, false); }
+            else { if (al) COFDM_ACQW(kCF32, true); else COFDM_ACQW(kCF32, false); }
+#undef COFDM_ACQW
+        } else if (!sync_less) {
             const unsigned g2 = (unsigned)((n_frames + 1) / 2);
 #define COFDM_ACQ(F, T) \
             do { if (want) rx_acquire512x2_kernel<F, T, true><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); \
@@ -172,7 +182,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 #undef COFDM_DM
             if (int rc = check_launch(h, "rx_demod512")) return rc;
             if (taps.synced != nullptr && taps.scal != nullptr) {
-                rx_synced_fixup2_kernel<<<(unsigned)n_frames, 128, 0, st>>>(h->P, (int)n_frames, taps, 1);
+                rx_synced_fixup2_kernel<<<(unsigned)n_frames, 128, 0, st>>>(h->P, (int)n_frames, taps, 0);
                 return check_launch(h, "rx_synced_fixup2");
             }
             return COFDM_OK;
@@ -363,7 +373,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
     rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
-    rc |= upload(h, T.lane_desc, &P.lane_desc);
+    rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.acq_desc, &P.acq_desc); rc |= upload(h, T.grid_conj, &P.grid_conj);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
     if (rc) return bail(COFDM_ERR_CUDA);
     P.constell = h->constell_dev[P.mod_type];
@@ -414,6 +424,12 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
 #undef COFDM_DM_ATTR_ALL
 #undef COFDM_DM_ATTR
         }
+#define COFDM_ACQW_ATTR(F, T, W) \
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512w_kernel<F, T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rx_acquire512w_smem_bytes()); \
+        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512w_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+        COFDM_ACQW_ATTR(kCF32, true, true); COFDM_ACQW_ATTR(kCF32, true, false); COFDM_ACQW_ATTR(kCF32, false, true); COFDM_ACQW_ATTR(kCF32, false, false);
+        COFDM_ACQW_ATTR(kCI16, true, true); COFDM_ACQW_ATTR(kCI16, true, false); COFDM_ACQW_ATTR(kCI16, false, true); COFDM_ACQW_ATTR(kCI16, false, false);
+#undef COFDM_ACQW_ATTR
 #define COFDM_ACQ_ATTR(F, T, W) \
         if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512x2_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
         COFDM_ACQ_ATTR(kCF32, true, true); COFDM_ACQ_ATTR(kCF32, true, false); COFDM_ACQ_ATTR(kCF32, false, true);

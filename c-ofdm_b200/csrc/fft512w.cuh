@@ -46,6 +46,42 @@ COFDM_DEV void ndft8(float2 (&v)[8]) {
     v[3] = nadd_mj(b6, d57);  v[7] = nadd_pj(b6, d57);
 }
 
+// forward 5- and 10-point DFTs, natural layout (the 640-point coarse-CFO spectrum is 10 x 8 x 8)
+COFDM_DEV void ndft5(float2 (&v)[5]) {
+    const float c1 = 0.30901699437494742410f, c2 = -0.80901699437494742410f;   // cos(2pi/5), cos(4pi/5)
+    const float s1 = 0.95105651629515357212f, s2 = 0.58778525229247312917f;    // sin(2pi/5), sin(4pi/5)
+    const float2 t1 = nadd(v[1], v[4]), t2 = nadd(v[2], v[3]), t3 = nsub(v[1], v[4]), t4 = nsub(v[2], v[3]);
+    const float2 x0 = nadd(v[0], nadd(t1, t2));
+    const float2 m1 = p_fma(t2, p_bcast(c2), p_fma(t1, p_bcast(c1), v[0]));
+    const float2 m2 = p_fma(t2, p_bcast(c1), p_fma(t1, p_bcast(c2), v[0]));
+    const float2 q1 = p_fma(t4, p_bcast(s2), p_mul(t3, p_bcast(s1)));
+    const float2 q2 = p_fma(t4, p_bcast(-s1), p_mul(t3, p_bcast(s2)));
+    v[0] = x0;
+    v[1] = nadd_mj(m1, q1);   // m1 - j q1
+    v[4] = nadd_pj(m1, q1);
+    v[2] = nadd_mj(m2, q2);
+    v[3] = nadd_pj(m2, q2);
+}
+// X[k], X[k+5] = E[k] +- W10^k O[k]
+COFDM_DEV void ndft10(float2 (&v)[10]) {
+    float2 e[5] = {v[0], v[2], v[4], v[6], v[8]}, o[5] = {v[1], v[3], v[5], v[7], v[9]};
+    ndft5(e);
+    ndft5(o);
+    o[1] = nmul(o[1], make_float2(0.80901699437494742410f, -0.58778525229247312917f));
+    o[2] = nmul(o[2], make_float2(0.30901699437494742410f, -0.95105651629515357212f));
+    o[3] = nmul(o[3], make_float2(-0.30901699437494742410f, -0.95105651629515357212f));
+    o[4] = nmul(o[4], make_float2(-0.80901699437494742410f, -0.58778525229247312917f));
+#pragma unroll
+    for (int k = 0; k < 5; k++) { v[k] = nadd(e[k], o[k]); v[k + 5] = nsub(e[k], o[k]); }
+}
+// the powers w^1..w^7 of a unit phasor with at most three roundings each
+COFDM_DEV void npowers7(float2 w1, float2 (&w)[8]) {
+    w[0] = make_float2(1.f, 0.f);
+    w[1] = w1;
+    w[2] = nmul(w1, w1); w[3] = nmul(w[2], w1); w[4] = nmul(w[2], w[2]);
+    w[5] = nmul(w[4], w1); w[6] = nmul(w[3], w[3]); w[7] = nmul(w[4], w[3]);
+}
+
 // bins a lane holds after the transform: slot a = c0 + 64 k3, slot b = c0 + 1 + 64 k3
 COFDM_DEV int fft512w_c0(int lane) { return 2 * (lane >> 3) + 8 * (lane & 7); }
 

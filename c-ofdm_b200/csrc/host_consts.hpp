@@ -98,6 +98,8 @@ struct HostTables {
     std::vector<cd> t2_tone_d, preamble_td_d, matched_d, mod_preamble_d, constell_d[9];
     int rx_buf_size = 0, iterations = 0;
     std::vector<uint4> lane_desc;     // rx512n.cuh: per pass-3 lane, the roles of its registers
+    std::vector<uint2> acq_desc;      // rx512n.cuh: per lane, which phase each of its k3 = 0, 1 slots produces
+    std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N)
     bool fused512_ok = false;         // the specialised kernels apply to this config
     bool generic_ok = false;          // the any-size multi-kernel path applies to this config
 };
@@ -178,6 +180,27 @@ inline void build_f512_roles(HostTables &T) {
     }
     if (nstrag != 7) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
     p.strag_desc[7] = 0;
+    // acquire kernel: the first 128 data sub-carriers (segments 0..3) live in the slots k3 = 0, 1 -- except bins 128..131, whose
+    // phases are produced by the four slots of k3 = 0, 1 that hold no data (bin 0 and the pilots 33, 66, 99)
+    T.acq_desc.assign(32, make_uint2(0, 0));
+    {
+        int idle = 0;
+        for (int k = 0; k < 128; k++) {
+            const int i = T.bin_map[k], lane = lane_of(k), slot = k & 1, k3 = k >> 6;
+            unsigned d;
+            if (i >= 0) {
+                if (i >= 128) throw std::runtime_error("fft-512 map: bins 0..127 hold a data index >= 128");
+                d = (unsigned)i;
+            } else {
+                if (idle >= 4 || T.bin_map[128 + idle] != 124 + idle) throw std::runtime_error("fft-512 map differs from the acquire kernel's straggler bins");
+                d = 0x8000u | ((unsigned)idle << 8) | (unsigned)(124 + idle);
+                idle++;
+            }
+            unsigned *u = &T.acq_desc[lane].x;
+            u[k3] |= d << (16 * slot);
+        }
+        if (idle != 4) throw std::runtime_error("fft-512 map differs from the acquire kernel's straggler bins");
+    }
 }
 
 inline HostTables build_tables(const ConfigMap &cfg) {
@@ -328,6 +351,11 @@ inline HostTables build_tables(const ConfigMap &cfg) {
         }
         norm = std::sqrt(norm);
         for (auto &v : T.matched_d) { v.re /= norm; v.im /= norm; }
+        // conj(tx grid of the first preamble symbol) / sqrt(N): Parseval form of the pr_phase_sinh correlation
+        T.grid_conj.assign((size_t)N, make_float2(0.f, 0.f));
+        for (int q = 0; q < NP; q++) T.grid_conj[T.pilot_bin[q]] = make_float2((float)(amp / nf), 0.f);
+        for (int i = 0; i < NP * p.seg_size; i++)
+            T.grid_conj[T.data_bin[i]] = make_float2((float)(T.mod_preamble_d[i].re / nf), (float)(-T.mod_preamble_d[i].im / nf));
         for (auto v : T.preamble_td_d) T.preamble_td.push_back(f2(v));
         for (auto v : T.matched_d) T.matched.push_back(f2(v));
         for (auto v : T.mod_preamble_d) T.mod_preamble.push_back(f2(v));

@@ -61,6 +61,9 @@ struct Params {
     // negative half: the channel line's abscissa, Frame.hpp:425-430), combo_seg its segment.  strag_desc: the data bins of
     // registers k3 = 2 and 5: the same 16 bits | scratch slot (32 (2 [k3 = 5] + slot) + origin lane) << 16 | (origin lane * 2 + slot) << 24.
     const uint4 *lane_desc;      // [32]
+    const uint2 *acq_desc;       // [32] acquire kernel: per lane 4 x 16 bits (k3 = 0 slot a, b; k3 = 1 slot a, b): [7:0] index of the
+                                 //      phase the slot produces (0..127), [15] take the product of straggler bin 128 + [9:8] instead
+    const float2 *grid_conj;     // [fft_size] conj(tx grid of the preamble) / sqrt(fft_size), zero on unused bins
     short combo_off[12];
     signed char combo_seg[12];
     unsigned long long combo_seg_packed;   // 4 bits per combination

@@ -390,6 +390,333 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     }
 }
 
+// ================================================================================================================
+// rx_acquire512w_kernel -- the preamble of one frame per WARP (four frames per CTA, nothing shared between them):
+//   coarse CFO   pilot_freq_sinh (Frame.hpp:285-337): 640-point spectrum (10 x 8 x 8 Stockham, natural layout), |X|^2,
+//                arg-max in the pilot windows -> kc
+//   fine CFO     cp_freq_sinh (:238-263) on the preamble: CP correlation -> theta_0, m_0; rotation, warp FFT-512
+//   phase lock   pr_phase_sinh (:265-274): theta = arg sum conj(ref) y, body part by Parseval on the used bins
+//   channel fit  chan_char_lq (:389-434): 128 phases, the reference's one-step unwrap, the (bug-compatible) line
+// and hands 40 bytes of scalars (FrameScal) to the demod kernel.  The lane's 20 raw samples x[2 lane (+1) + 64 q] are the
+// inputs of BOTH transforms (radix-10 first pass of the 640-point one, CP + radix-8 first pass of the 512-point one):
+// they are read from the staged copy once and stay in registers.
+// Shared memory per warp: S (5120 B: staged samples -> second coarse plane -> phasor table, phases) and A (5376 B:
+// first coarse plane, padded -> |X|^2 -> FFT-512 exchanges).
+// ================================================================================================================
+constexpr int kAcqwWarps = 4;
+constexpr int kAcqwS = 5120, kAcqwA = 5376;
+constexpr int kAcqwRegion = kAcqwS + kAcqwA;
+COFDM_HD constexpr size_t rx_acquire512w_smem_bytes() { return (size_t)kAcqwWarps * kAcqwRegion + kAcqwWarps * sizeof(uint64_t); }
+
+template <int FMT, bool USE_TMA, bool TAPS>
+__global__ void __launch_bounds__(32 * kAcqwWarps, 5)
+rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
+                      const RxTaps taps, FrameScal *__restrict__ fscal, const int sync_less) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int frame = blockIdx.x * kAcqwWarps + warp;
+    if (frame >= n_frames) return;                     // whole warp; warps never meet at a block barrier
+    char *S = reinterpret_cast<char *>(smem_raw) + (size_t)warp * kAcqwRegion;
+    float2 *A = reinterpret_cast<float2 *>(S + kAcqwS);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kAcqwWarps * kAcqwRegion) + warp;
+    const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
+    const char *src = reinterpret_cast<const char *>(samples) + (size_t)frame * (size_t)frame_stride * sample_bytes;
+    if (USE_TMA) {
+        if (lane == 0) {
+            mbar_init(mbar, 1);
+            mbar_fence_init();
+            mbar_arrive_expect_tx(mbar, 640 * (unsigned)sample_bytes);
+            tma_load_1d(S, src, 640 * (unsigned)sample_bytes, mbar);
+        }
+    } else {
+        warp_stage_symbol<FMT>(S, src, lane);
+    }
+    __syncwarp();
+    if (USE_TMA) mbar_wait(mbar, 0);
+    // ---- the lane's 20 raw samples: ra[q] = x[2 lane + 64 q], rb[q] = x[2 lane + 1 + 64 q] ----
+    float2 ra[10], rb[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) staged_pair<FMT>(S, lane + 32 * q, ra[q], rb[q]);
+    __syncwarp();                                      // S may be overwritten from here on
+
+    int kc = 0;
+    if (!sync_less) {
+        // ================= coarse CFO: 640-point spectrum of the received preamble, CP included =================
+        // pass 1: radix 10, butterflies j = 2 lane, 2 lane + 1; output index I = 10 j + q lives at slot I + I / 20
+        {
+            float2 v[10];
+#pragma unroll
+            for (int q = 0; q < 10; q++) v[q] = ra[q];
+            ndft10(v);
+#pragma unroll
+            for (int q = 0; q < 10; q++) A[21 * lane + q] = v[q];
+#pragma unroll
+            for (int q = 0; q < 10; q++) v[q] = rb[q];
+            ndft10(v);
+#pragma unroll
+            for (int q = 0; q < 10; q++) A[21 * lane + 10 + q] = v[q];
+        }
+        __syncwarp();
+        float2 *B = reinterpret_cast<float2 *>(S);
+        // pass 2: radix 8, ns = 10: butterfly j (80 of them), k = j mod 10; inputs I = j + 80 q at slot I + I / 20 = (j + j / 20) + 84 q
+#pragma unroll 1
+        for (int j = lane; j < 80; j += 32) {
+            const int g = j / 10, k = j - 10 * g;
+            float2 v[8], w[8];
+            const float2 *in = A + j + j / 20;
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = in[84 * q];
+            npowers7(__ldg(&P.tw_pf[8 * k]), w);                          // W640^{8 k q}
+#pragma unroll
+            for (int q = 1; q < 8; q++) v[q] = nmul(v[q], w[q]);
+            ndft8(v);
+            float2 *out = B + 80 * g + k;
+#pragma unroll
+            for (int q = 0; q < 8; q++) out[10 * q] = v[q];
+        }
+        __syncwarp();
+        // pass 3: radix 8, ns = 80: only |X|^2 is kept, as float[640] in A
+        float *mag = reinterpret_cast<float *>(A);
+#pragma unroll 1
+        for (int j = lane; j < 80; j += 32) {
+            float2 v[8], w[8];
+#pragma unroll
+            for (int q = 0; q < 8; q++) v[q] = B[j + 80 * q];
+            npowers7(__ldg(&P.tw_pf[j]), w);                              // W640^{j q}
+#pragma unroll
+            for (int q = 1; q < 8; q++) v[q] = nmul(v[q], w[q]);
+            ndft8(v);
+#pragma unroll
+            for (int q = 0; q < 8; q++) { const float2 sq = p_mul(v[q], v[q]); mag[j + 80 * q] = sq.x + sq.y; }
+        }
+        __syncwarp();
+        // arg-max of |spectrum| in the pilot windows, first maximum wins (Frame.hpp:311-331); warp arg-max by two hardware
+        // reductions: the magnitudes are non-negative floats, so their bit patterns order like unsigned integers
+        const int np = P.num_pilot_subc, half = P.pf_size / 2;
+        int ksum = 0;
+        for (int wi = 0; wi < np; wi++) {
+            const int win = wi < np / 2 ? wi : wi + 1;                     // window np/2 (DC) is skipped
+            int lo = P.pf_border0 + win * P.pf_pilot_w;
+            const int hi = lo + P.pf_pilot_w;
+            if (win == 0 && lo < 0) lo = 0;
+            float best = -1.0f;
+            int bi = 0x7fffffff;
+            for (int ks = lo + lane; ks < hi; ks += 32) {                  // ks = fft-shifted index
+                const float mv = mag[ks < half ? ks + half : ks - half];
+                if (mv > best) { best = mv; bi = ks; }
+            }
+            const unsigned bb = best < 0.f ? 0u : __float_as_uint(best);
+            const unsigned mx = __reduce_max_sync(0xffffffffu, bb);
+            ksum += __reduce_min_sync(0xffffffffu, bb == mx ? bi : 0x7fffffff);
+        }
+        kc = ksum - np * half;                                             // shift = kc / pf_den (Frame.hpp:332-334)
+        __syncwarp();                                                      // the planes are free again
+    }
+
+    // ================= fine CFO of the preamble (cp_freq_sinh): CP sample j pairs with body sample j + 512 (q = 8, 9) =================
+    float theta0 = 0.f;
+    int m0 = 0;
+    if (!sync_less) {
+        float2 c = nmac_conj(nmac_conj(make_float2(0.f, 0.f), ra[0], ra[8]), rb[0], rb[8]);
+        c = nmac_conj(nmac_conj(c, ra[1], ra[9]), rb[1], rb[9]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c = nadd(c, make_float2(__shfl_xor_sync(0xffffffffu, c.x, o), __shfl_xor_sync(0xffffffffu, c.y, o)));
+        theta0 = fast_atan2_turns(c.y, c.x);
+        m0 = (int)ceilf(-(theta0 - (float)kc * P.pf_bins512) - 0.5f);
+    }
+    // rotation phasors (see rx_demod512_kernel): table entry `lane` = exp(-j 2 pi beta J / 512)
+    float2 *qt = reinterpret_cast<float2 *>(S);
+    {
+        const int J = lane < 8 ? 64 * lane : (lane == 8 ? 1 : (lane < 13 ? 16 * (lane - 9) : 128 + 2 * (lane - 13)));
+        const float2 ph = rot_phasor(theta0, m0, J);
+        if (lane < 21) qt[lane] = ph;
+    }
+    __syncwarp();
+    const float2 pa = nmul(qt[13 + (lane & 7)], qt[9 + (lane >> 3)]);
+    const float2 pb = nmul(pa, qt[8]);
+    // CP samples j = t + 64 c rotated: exp(-j 2 pi beta j / 512) = P(t) conj(Q^(2 - c))
+    const float2 y0a = nmul(nmulc(ra[0], qt[2]), pa), y0b = nmul(nmulc(rb[0], qt[2]), pb);
+    const float2 y1a = nmul(nmulc(ra[1], qt[1]), pa), y1b = nmul(nmulc(rb[1], qt[1]), pb);
+    float2 va[8], vb[8];
+    va[0] = ra[2]; vb[0] = rb[2];
+#pragma unroll
+    for (int r = 1; r < 8; r++) { va[r] = nmul(ra[r + 2], qt[r]); vb[r] = nmul(rb[r + 2], qt[r]); }
+    if (TAPS && taps.synced != nullptr) {
+        // debug tap, completed by rx_synced_fixup2_kernel (theta; the preamble has no other constant phase)
+        float2 *d = taps.synced + (size_t)frame * P.rx_len;
+        const int t = 2 * lane;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { d[128 + t + 64 * r] = nmul(va[r], pa); d[129 + t + 64 * r] = nmul(vb[r], pb); }
+        d[t] = y0a; d[t + 1] = y0b; d[t + 64] = y1a; d[t + 65] = y1b;
+    }
+    __syncwarp();                                                          // everybody has read the phasor table: A / S are free
+    warp_fft512(va, vb, pa, pb, A, P.tw_fft, lane);
+    // now va[k3] = Y[c0 + 64 k3], vb[k3] = Y[c0 + 1 + 64 k3], the true spectrum of the preamble (symbol 0 has no constant phase)
+
+    const int c0 = fft512w_c0(lane);
+    if (sync_less) {
+        // PREAMBLE_FORM::chan_char (Frame.hpp:375-385) on the preamble as it stands: pr = preamble.fft() (own pilot
+        // normalisation, Frame.cpp:76-84; coef == 1), chan_est[i] = pr[i] / mod_preamble[i]
+        if (TAPS && taps.chan != nullptr) {
+            float pm = 0.f;
+#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pm = sqrtf(cnorm2((f512_slot(bin) ? vb : va)[f512_k3(bin)]));
+            COFDM_F512_PILOTS(COFDM_X)
+#undef COFDM_X
+            pm = warp_sum(pm);
+            const float igp = (8.0f * P.pilot_ampl) / pm;
+#pragma unroll
+            for (int k3 = 0; k3 < 8; k3++) {
+                if (k3 == 3 || k3 == 4) continue;
+#pragma unroll
+                for (int sl = 0; sl < 2; sl++) {
+                    const int k = c0 + sl + 64 * k3, i = __ldg(&P.bin_map[k]);
+                    if (i >= 0) {
+                        const float2 mp = __ldg(&P.mod_preamble[i]);
+                        const float2 y = cscale(sl ? vb[k3] : va[k3], igp);
+                        taps.chan[(size_t)frame * 256 + i] = cscale(cmulc(y, mp), 1.0f / cnorm2(mp));
+                    }
+                }
+            }
+        }
+        return;
+    }
+
+    // ================= pr_phase_sinh: z = sum_{i<640} conj(ref[i]) y[i]; body by Parseval: (1/sqrt 512) sum_k conj(G[k]) Y[k],
+    //                   G = tx grid of the preamble (P.grid_conj = conj(G) / sqrt 512, zero on unused bins) =================
+    float2 prod[4];                                    // Y conj(G) of the slots k3 = 0, 1 (x slot a, b): the first 128 data sub-carriers live there
+    float2 z;
+    {
+        const float4 *g4 = reinterpret_cast<const float4 *>(P.grid_conj) + (c0 >> 1);
+        const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 32), g2 = __ldg(g4 + 64), g5 = __ldg(g4 + 160), g6 = __ldg(g4 + 192), g7 = __ldg(g4 + 224);
+        prod[0] = nmul(va[0], make_float2(g0.x, g0.y)); prod[1] = nmul(vb[0], make_float2(g0.z, g0.w));
+        prod[2] = nmul(va[1], make_float2(g1.x, g1.y)); prod[3] = nmul(vb[1], make_float2(g1.z, g1.w));
+        const float2 s2a = nmul(va[2], make_float2(g2.x, g2.y)), s2b = nmul(vb[2], make_float2(g2.z, g2.w));
+        z = nadd(nadd(prod[0], prod[1]), nadd(prod[2], prod[3]));
+        z = nadd(z, nadd(s2a, s2b));
+        z = nmac(nmac(z, va[5], make_float2(g5.x, g5.y)), vb[5], make_float2(g5.z, g5.w));
+        z = nmac(nmac(z, va[6], make_float2(g6.x, g6.y)), vb[6], make_float2(g6.z, g6.w));
+        z = nmac(nmac(z, va[7], make_float2(g7.x, g7.y)), vb[7], make_float2(g7.z, g7.w));
+        // CP part: conj(ref[j]) y[j], j = 2 lane (+1), 64 + 2 lane (+1)
+        const float4 *r4 = reinterpret_cast<const float4 *>(P.preamble_td) + lane;
+        const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 32);
+        z = nmac_conj(nmac_conj(z, make_float2(r0.x, r0.y), y0a), make_float2(r0.z, r0.w), y0b);
+        z = nmac_conj(nmac_conj(z, make_float2(r1.x, r1.y), y1a), make_float2(r1.z, r1.w), y1b);
+        // the data bins 128..131 (k3 = 2 of lanes 0 and 8) belong to the first 128 sub-carriers too: their products travel
+        // through shared memory to the four lanes whose slot holds no data (bin 0 and the pilots 33, 66, 99)
+        float2 *sx = qt + 24;
+        if (lane == f512_lane(128)) { sx[0] = s2a; sx[1] = s2b; }
+        if (lane == f512_lane(130)) { sx[2] = s2a; sx[3] = s2b; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) z = nadd(z, make_float2(__shfl_xor_sync(0xffffffffu, z.x, o), __shfl_xor_sync(0xffffffffu, z.y, o)));
+    const float inv = rsqrtf(fmaxf(cnorm2(z), 1e-30f));
+    const float2 rot = make_float2(z.x * inv, -z.y * inv);               // exp(-j theta)
+    const float theta = TAPS ? atan2f(z.y, z.x) : 0.f;
+
+    // ================= chan_char_lq: phase[i] = arg(pr[i] / mod_preamble[i]), i < 128 (Frame.hpp:403-405) =================
+    const float TWO_PI_F = 6.28318530717958647692f, PI_F = 3.14159265358979323846f;
+    float *phs = reinterpret_cast<float *>(qt + 32);                      // 128 phases
+    {
+        const uint2 ad = __ldg(&P.acq_desc[lane]);   // 4 x 16 bits (k3 = 0 a, b; k3 = 1 a, b): [7:0] phase index, [15] straggler, [9:8] which
+        const float2 *sx = qt + 24;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const unsigned d = ((u < 2 ? ad.x : ad.y) >> (16 * (u & 1))) & 0xffffu;
+            float2 pr = prod[u];
+            if (d & 0x8000u) pr = sx[(d >> 8) & 3u];
+            const float2 dr = nmul(pr, rot);
+            phs[d & 0xffu] = fast_atan2_turns(dr.y, dr.x) * TWO_PI_F;
+        }
+    }
+    __syncwarp();
+    // one-step unwrap (Frame.hpp:407-414) and the sums of Frame.hpp:416-421: lane l owns phases 4l .. 4l + 3
+    float tsy, tsxy;
+    {
+        const float4 p4v = reinterpret_cast<const float4 *>(phs)[lane];
+        float p4[4] = {p4v.x, p4v.y, p4v.z, p4v.w};
+        const float prev_raw = __shfl_up_sync(0xffffffffu, p4[3], 1);
+        bool jump = (lane > 0 && fabsf(p4[0] - prev_raw) > PI_F) || fabsf(p4[1] - p4[0]) > PI_F || fabsf(p4[2] - p4[1]) > PI_F || fabsf(p4[3] - p4[2]) > PI_F;
+        const bool any = __ballot_sync(0xffffffffu, jump) != 0u;
+        float ssy = (p4[0] + p4[1]) + (p4[2] + p4[3]);
+        float ssxy = fmaf(p4[3], 3.0f, fmaf(p4[2], 2.0f, p4[1])) + (float)(4 * lane) * ssy;
+        if (any) {
+            // slow path: the adjustment is a 3-state chain (state = multiple of 2 pi carried by the previous element); each lane
+            // builds the transition map of its 4 elements for every incoming state, the maps are composed across lanes by a
+            // warp scan, then replayed
+            unsigned map = 0;
+#pragma unroll
+            for (int cin = 0; cin < 3; cin++) {
+                int cc = cin - 1;
+                float pv = prev_raw;
+#pragma unroll
+                for (int e = 0; e < 4; e++) {
+                    if (lane == 0 && e == 0) { cc = 0; pv = p4[0]; continue; }
+                    const float dlt = p4[e] - (pv + (float)cc * TWO_PI_F);
+                    cc = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                    pv = p4[e];
+                }
+                map |= (unsigned)(cc + 1) << (2 * cin);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
+                if (lane >= o) {
+                    unsigned comp = 0;
+#pragma unroll
+                    for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
+                    map = comp;
+                }
+            }
+            const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
+            int cc = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;
+            float pv = prev_raw;
+            ssy = 0.f; ssxy = 0.f;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                float val = p4[e];
+                if (!(lane == 0 && e == 0)) {
+                    const float dlt = p4[e] - (pv + (float)cc * TWO_PI_F);
+                    cc = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                    val = p4[e] + (float)cc * TWO_PI_F;
+                } else {
+                    cc = 0;
+                }
+                pv = p4[e];
+                ssy += val;
+                ssxy += val * (float)(4 * lane + e);
+            }
+        }
+        tsy = warp_sum(ssy);
+        tsxy = warp_sum(ssxy);
+    }
+    // sums in float (an error in sum(y) reaches `a` scaled by 0.01, one in sum(xy) by 1e-4), the cancelling final step in double
+    const double n = 128.0, sx1 = n * (n - 1.0) / 2.0, sx2 = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
+    const double lb = ((double)tsxy - sx1 * (double)tsy) / (sx2 - sx1 * sx1);   // Frame.hpp:422 (sums, not means)
+    const double la = (double)tsy - lb * sx1;                                    // Frame.hpp:423
+    {
+        // FrameScal as five 8-byte words: {kc, m0} {th0, theta} {rot_theta} {a} {b}
+        uint2 wv;
+        if (lane == 0) wv = make_uint2((unsigned)kc, (unsigned)m0);
+        else if (lane == 1) wv = make_uint2(__float_as_uint(theta0), __float_as_uint(theta));
+        else if (lane == 2) wv = make_uint2(__float_as_uint(rot.x), __float_as_uint(rot.y));
+        else if (lane == 3) wv = make_uint2((unsigned)__double2loint(la), (unsigned)__double2hiint(la));
+        else wv = make_uint2((unsigned)__double2loint(lb), (unsigned)__double2hiint(lb));
+        if (lane < 5) reinterpret_cast<uint2 *>(fscal + frame)[lane] = wv;
+    }
+    if (TAPS) {
+        if (taps.scal != nullptr && lane == 0) {
+            float *sc = taps.scal + (size_t)frame * 48;
+            sc[0] = (float)((double)kc / (double)P.pf_den); sc[1] = (float)la; sc[2] = (float)lb; sc[3] = theta;
+            sc[5] = (float)kc; sc[6] = 0.f; sc[7] = 0.f;
+            sc[16] = (float)m0; sc[32] = theta0;
+        }
+        if (taps.chan != nullptr)
+            for (int i = lane; i < 256; i += 32)
+                taps.chan[(size_t)frame * 256 + i] = cis_turns((lb * (double)(i < 128 ? i : i - 256) + la) * 0.15915494309189533577);
+    }
+}
+
 // Completes the `synced` debug tap of rx_demod512_kernel / rx_acquire512w_kernel: they store every sample with the symbol's
 // full rotation exp(-j 2 pi beta_s j / 512); apply the per-symbol constant phase Psi_s and theta so that the tap equals
 // the reference's buffer after freq_shift + cp_freq_sinh + pr_phase_sinh.

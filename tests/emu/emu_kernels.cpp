@@ -23,7 +23,19 @@ static void wire(EmuHandle *h) {
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
     P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
-    P.lane_desc = T.lane_desc.data();
+    P.lane_desc = T.lane_desc.data(); P.acq_desc = T.acq_desc.data(); P.grid_conj = T.grid_conj.data();
+}
+
+// the one-warp-per-frame acquire kernel (rx512n.cuh)
+template <bool TAPS>
+static void emu_acquire512w(const Params &P, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
+                            const RxTaps &taps, FrameScal *fs, int sync_less) {
+    const dim3 grid((n_frames + kAcqwWarps - 1) / kAcqwWarps), block(32 * kAcqwWarps);
+    const size_t sm = rx_acquire512w_smem_bytes();
+#define EMU_AQ(F, T) emu::launch(grid, block, sm, [&] { rx_acquire512w_kernel<F, T, TAPS>(P, samples, stride, n_frames, taps, fs, sync_less); })
+    if (fmt == kCI16) { if (use_tma) EMU_AQ(kCI16, true); else EMU_AQ(kCI16, false); }
+    else { if (use_tma) EMU_AQ(kCF32, true); else EMU_AQ(kCF32, false); }
+#undef EMU_AQ
 }
 
 // the one-warp-per-symbol demod kernel (rx512n.cuh), production instantiations
@@ -74,6 +86,12 @@ int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, in
 #define EMU_RX(F, T, MD) run(MD, [&] { rx_fused512_kernel<F, T, 9, true, MD>(P, samples, stride, n_frames, out, amb, taps, sync_less, fs.data()); })
 #define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
     auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
+    if (g_emu_split == 3 && !sync_less) {             // product: one warp per frame (acquire) + one warp per symbol (demod)
+        emu_acquire512w<true>(P, samples, fmt, use_tma, n_frames, stride, taps, fs.data(), 0);
+        emu_demod512<true>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
+        if (synced && scal) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup2_kernel(P, n_frames, taps, 0); });
+        return 0;
+    }
     if (g_emu_split && nsym <= 9 && !sync_less) {     // production split: paired acquire + demod
         if (fmt == kCI16 && use_tma) {                // raw int16 bulk copies, widened when read
             acq2([&] { rx_acquire512x2_kernel<kCI16, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
@@ -122,7 +140,10 @@ int emu_rx_fused512_notaps(void *hv, const void *samples, int fmt, int use_tma, 
     auto run = [&](int md, auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym, md)), rx512_smem_bytes(nsym, md), kern); };
 #define EMU_RX(F, T, MD) run(MD, [&] { rx_fused512_kernel<F, T, 9, false, MD>(P, samples, stride, n_frames, out, amb, taps, 0, fs.data()); })
 #define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
-    if (g_emu_split) {
+    if (g_emu_split == 3) {
+        emu_acquire512w<false>(P, samples, fmt, use_tma, n_frames, stride, taps, fs.data(), 0);
+        emu_demod512<false>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
+    } else if (g_emu_split) {
         auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
         if (fmt == kCI16 && use_tma) {
             acq2([&] { rx_acquire512x2_kernel<kCI16, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
