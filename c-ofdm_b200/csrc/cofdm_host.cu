@@ -368,12 +368,13 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     h->P = T.p;
     Params &P = h->P;
     int rc = 0;
-    rc |= upload(h, T.tw_fft, &P.tw_fft);   rc |= upload(h, T.tw_p1, &P.tw_p1);   rc |= upload(h, T.tw_p2, &P.tw_p2); rc |= upload(h, T.tw_p2w, &P.tw_p2w);
+    rc |= upload(h, T.tw_fft, &P.tw_fft);   rc |= upload(h, T.tw_p1, &P.tw_p1);   rc |= upload(h, T.tw_p2, &P.tw_p2);
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
     rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
-    rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.acq_desc, &P.acq_desc); rc |= upload(h, T.grid_conj, &P.grid_conj);
+    rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.lane_aux, &P.lane_aux); rc |= upload(h, T.acq_desc, &P.acq_desc);
+    rc |= upload(h, T.grid_lane, &P.grid_lane);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
     if (rc) return bail(COFDM_ERR_CUDA);
     P.constell = h->constell_dev[P.mod_type];

@@ -89,7 +89,7 @@ inline void host_dft(std::vector<cd> &x, int sign) {
 struct HostTables {
     Params p{};                       // sizes filled, device pointers left null
     ConfigMap cfg;
-    std::vector<float2> tw_fft, tw_p1, tw_p2, tw_p2w, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
+    std::vector<float2> tw_fft, tw_p1, tw_p2, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
     std::vector<float2> constell[9];  // index = mod type 1,2,4,6,8
     std::vector<float> t2_mask;
     std::vector<int16_t> bin_map, data_bin, pilot_bin;
@@ -97,9 +97,11 @@ struct HostTables {
     // fp64 originals for the double-precision facade
     std::vector<cd> t2_tone_d, preamble_td_d, matched_d, mod_preamble_d, constell_d[9];
     int rx_buf_size = 0, iterations = 0;
-    std::vector<uint4> lane_desc;     // rx512n.cuh: per pass-3 lane, the roles of its registers
-    std::vector<uint2> acq_desc;      // rx512n.cuh: per lane, which phase each of its k3 = 0, 1 slots produces
-    std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N)
+    std::vector<uint4> lane_desc;     // rx512n.cuh: per lane, the roles of its registers after warp_fft512
+    std::vector<uint2> lane_aux;      //             combinations and straggler bins
+    std::vector<uint2> acq_desc;      //             acquire kernel: which phase each slot produces
+    std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N), by bin
+    std::vector<float2> grid_lane;    //             the same in lane order
     bool fused512_ok = false;         // the specialised kernels apply to this config
     bool generic_ok = false;          // the any-size multi-kernel path applies to this config
 };
@@ -128,8 +130,8 @@ inline std::vector<cd> constellation_d(int mod) {
     return t;
 }
 
-// Roles of the registers a lane holds after warp_fft512 (fft512w.cuh): lane l'' = k2 + 8a holds bins c0 + 64 k3 (slot a) and
-// c0 + 1 + 64 k3 (slot b), c0 = 2a + 8 k2.  Derived from the sub-carrier map (Frame.cpp:31-44); the kernels' hard-wired
+// Roles of the registers a lane holds after warp_fft512 (fft512w.cuh): lane 2 k1 + g holds mn[i] = X[k1 + 16 i + (g ? 384 : 0)]
+// and ot[i] = X[k1 + 16 i + (g ? 128 : 256)].  Derived from the sub-carrier map (Frame.cpp:31-44); the kernels' hard-wired
 // pilot and straggler positions (COFDM_F512_PILOTS / COFDM_F512_STRAG in rx512n.cuh) are checked against it.
 inline void build_f512_roles(HostTables &T) {
     Params &p = T.p;
@@ -137,69 +139,83 @@ inline void build_f512_roles(HostTables &T) {
     static const int strag[7] = {128, 129, 130, 131, 381, 382, 383};
     for (int q = 0; q < 8; q++)
         if (T.pilot_bin[q] != pil[q]) throw std::runtime_error("fft-512 sub-carrier map differs from the kernels' pilot positions");
-    auto seg_of = [&](int i) { return i / p.seg_size; };
+    if (p.pf_size != 640 || p.pf_pilot_w != 41 || p.pf_border0 != 134)          // kF512Pf* in rx512n.cuh
+        throw std::runtime_error("fft-512 geometry: coarse-CFO windows differ from the acquire kernel's");
+    auto g_of = [](int k) { return (k >> 7) & 1; };
+    auto main_of = [](int k) { return k < 128 || k >= 384; };
+    auto lane_of = [&](int k) { return 2 * (k & 15) + g_of(k); };
+    auto i_of = [](int k) { return (k & 127) >> 4; };
+    auto seg_of = [&](int di) { return di / p.seg_size; };
     // combinations in order of first appearance over the bins
-    int ncombo = 0, combo_of[8][8];
-    for (auto &r : combo_of) for (auto &v : r) v = -1;
-    for (int k = 0; k < 512; k++) {
-        const int i = T.bin_map[k];
-        if (i < 0) continue;
-        const int e = seg_of(i), k3 = k >> 6;
-        const int off = (i < 128 ? i : i - 256) - ((k & 63) - 1);
-        if (combo_of[e][k3] < 0) {
-            if (ncombo >= 12) throw std::runtime_error("fft-512 map: more than 12 (segment, k3) combinations");
-            combo_of[e][k3] = ncombo;
-            p.combo_off[ncombo] = (short)off;
-            p.combo_seg[ncombo] = (signed char)e;
-            ncombo++;
-        } else if (p.combo_off[combo_of[e][k3]] != off) {
-            throw std::runtime_error("fft-512 map: data index is not linear inside a (segment, k3) combination");
+    std::map<std::vector<int>, int> combo_of;
+    std::vector<int> c_seg, c_off;
+    auto combo = [&](int k) {
+        const int di = T.bin_map[k];
+        const std::vector<int> key = {main_of(k) ? 1 : 0, g_of(k), i_of(k), seg_of(di)};
+        const int off = (di < 128 ? di : di - 256) - (k & 15);
+        auto it = combo_of.find(key);
+        if (it == combo_of.end()) {
+            it = combo_of.emplace(key, (int)c_seg.size()).first;
+            c_seg.push_back(seg_of(di));
+            c_off.push_back(off);
+        } else if (c_off[it->second] != off) {
+            throw std::runtime_error("fft-512 map: data index is not linear inside a combination");
         }
-    }
-    for (int q = ncombo; q < 12; q++) { p.combo_off[q] = 0; p.combo_seg[q] = 0; }
-    p.combo_seg_packed = 0;
-    for (int q = 0; q < 12; q++) p.combo_seg_packed |= (unsigned long long)p.combo_seg[q] << (4 * q);
-    auto lane_of = [](int k) { const int c0 = (k & 63) & ~1; return (c0 >> 3) + 8 * ((c0 & 7) >> 1); };
+        return it->second;
+    };
     const unsigned dummy = 256u << 7;                          // data index 256: a slot nobody reads
     T.lane_desc.assign(32, make_uint4(dummy | (dummy << 16), dummy | (dummy << 16), dummy | (dummy << 16), dummy | (dummy << 16)));
+    T.lane_aux.assign(32, make_uint2(0, 0));
     int nstrag = 0;
     for (int k = 0; k < 512; k++) {
-        const int i = T.bin_map[k];
-        if (i < 0) continue;
-        const int k3 = k >> 6, lane = lane_of(k), slot = k & 1;
-        const unsigned d = ((unsigned)i << 7) | ((unsigned)combo_of[seg_of(i)][k3] << 3);
-        if (k3 == 2 || k3 == 5) {
-            if (nstrag >= 7 || strag[nstrag] != k) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
-            p.strag_desc[nstrag++] = d | ((unsigned)(32 * (2 * (k3 == 5) + slot) + lane) << 16) | ((unsigned)(lane * 2 + slot) << 24);
+        const int di = T.bin_map[k];
+        if (di < 0) continue;
+        const unsigned d = ((unsigned)di << 7) | ((unsigned)combo(k) << 2);
+        if (!main_of(k)) {
+            // used bins outside mn[]: ot[0] of odd lanes (128..131), ot[7] of even lanes (381..383)
+            if (nstrag >= 7 || strag[nstrag] != k || i_of(k) != (g_of(k) ? 0 : 7))
+                throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
+            T.lane_aux[nstrag++].y = d | ((unsigned)(k & 15) << 16);
             continue;
         }
-        if (k3 == 3 || k3 == 4) throw std::runtime_error("fft-512 map: data in the pruned registers");
-        const int w = k3 < 2 ? k3 : k3 - 4;                    // word of the uint4: k3 = 0, 1, 6, 7
-        unsigned *u = &T.lane_desc[lane].x;
-        u[w] = (u[w] & ~(0xffffu << (16 * slot))) | (d << (16 * slot));
+        unsigned *u = &T.lane_desc[lane_of(k)].x;
+        const int i = i_of(k);
+        u[i >> 1] = (u[i >> 1] & ~(0xffffu << (16 * (i & 1)))) | (d << (16 * (i & 1)));
     }
     if (nstrag != 7) throw std::runtime_error("fft-512 map differs from the kernels' straggler bins");
-    p.strag_desc[7] = 0;
-    // acquire kernel: the first 128 data sub-carriers (segments 0..3) live in the slots k3 = 0, 1 -- except bins 128..131, whose
-    // phases are produced by the four slots of k3 = 0, 1 that hold no data (bin 0 and the pilots 33, 66, 99)
+    for (int q : {3, 4})                                       // the two pilots outside mn[] sit in the same ot[] registers
+        if (main_of(pil[q]) || i_of(pil[q]) != (g_of(pil[q]) ? 0 : 7)) throw std::runtime_error("fft-512 map differs from the kernels' pilot registers");
+    p.n_combos = (int)c_seg.size();
+    if (p.n_combos > 24) throw std::runtime_error("fft-512 map: more than 24 combinations");
+    for (int q = 0; q < p.n_combos; q++) T.lane_aux[q].x = (unsigned)c_seg[q] | ((unsigned)(c_off[q] & 0xffff) << 16);
+    // acquire kernel: the first 128 data sub-carriers (segments 0..3) are mn[] of the even lanes (bins k1 + 16 i < 128) -- except bins
+    // 128..131, whose phases are produced by the four phase slots that hold no data (bin 0 and the pilots 33, 66, 99).  Even lane:
+    // slots mn[0..3]; odd lane: slots mn[4..7] of its even neighbour.
     T.acq_desc.assign(32, make_uint2(0, 0));
     {
         int idle = 0;
         for (int k = 0; k < 128; k++) {
-            const int i = T.bin_map[k], lane = lane_of(k), slot = k & 1, k3 = k >> 6;
+            const int di = T.bin_map[k], i = i_of(k), lane = 2 * (k & 15) + (i >> 2), u4 = i & 3;
             unsigned d;
-            if (i >= 0) {
-                if (i >= 128) throw std::runtime_error("fft-512 map: bins 0..127 hold a data index >= 128");
-                d = (unsigned)i;
+            if (di >= 0) {
+                if (di >= 128) throw std::runtime_error("fft-512 map: bins 0..127 hold a data index >= 128");
+                d = (unsigned)di;
             } else {
                 if (idle >= 4 || T.bin_map[128 + idle] != 124 + idle) throw std::runtime_error("fft-512 map differs from the acquire kernel's straggler bins");
                 d = 0x8000u | ((unsigned)idle << 8) | (unsigned)(124 + idle);
                 idle++;
             }
             unsigned *u = &T.acq_desc[lane].x;
-            u[k3] |= d << (16 * slot);
+            u[u4 >> 1] |= d << (16 * (u4 & 1));
         }
         if (idle != 4) throw std::runtime_error("fft-512 map differs from the acquire kernel's straggler bins");
+    }
+    // conj(tx grid) / sqrt(N) in lane order: mn[0..7], the used ot[] register, padding
+    T.grid_lane.assign(32 * 10, make_float2(0.f, 0.f));
+    for (int lane = 0; lane < 32; lane++) {
+        const int k1 = lane >> 1, g = lane & 1;
+        for (int i = 0; i < 8; i++) T.grid_lane[lane * 10 + i] = T.grid_conj[k1 + 16 * i + (g ? 384 : 0)];
+        T.grid_lane[lane * 10 + 8] = T.grid_conj[g ? k1 + 128 : k1 + 112 + 256];
     }
 }
 
@@ -285,15 +301,6 @@ inline HostTables build_tables(const ConfigMap &cfg) {
             const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((n3 * k2) % 64) / 64.0L;
             T.tw_p2[k2 * 8 + n3] = make_float2((float)cosl(ang), (float)sinl(ang));
         }
-
-    T.tw_p2w.resize(8 * 4 * 2);
-    for (int k2 = 0; k2 < 8; k2++)
-        for (int j = 0; j < 4; j++)
-            for (int u = 0; u < 2; u++) {
-                const int n3 = (j & 1) + 4 * (j >> 1) + 2 * u;
-                const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((n3 * k2) % 64) / 64.0L;
-                T.tw_p2w[(k2 * 4 + j) * 2 + u] = make_float2((float)cosl(ang), (float)sinl(ang));
-            }
 
     for (int m : {1, 2, 4, 6, 8}) {
         T.constell_d[m] = constellation_d(m);

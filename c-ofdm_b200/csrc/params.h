@@ -42,7 +42,6 @@ struct Params {
     const float2 *tw_fft;        // [fft_size]  exp(-j*2*pi*k/fft_size)
     const float2 *tw_p1;         // [8][64]     exp(-j*2*pi*t*k1/512)     (fused 512 path, pass-1 twiddles)
     const float2 *tw_p2;         // [8][8]      exp(-j*2*pi*n3*k2/64)     (fused 512 path, pass-2 twiddles)
-    const float2 *tw_p2w;        // [8][4][2]   the same for the one-warp transform: n3 = (j & 1) + 4 (j >> 1), then n3 + 2
     const float2 *tw_pf;         // [pf_size]   exp(-j*2*pi*k/pf_size)
     const float2 *tw_t2;         // [t2sin_size]
     const float *t2_mask;        // [t2sin_size] detect_mask (Frame.cpp:120-133)
@@ -55,19 +54,16 @@ struct Params {
     const int16_t *data_bin;     // [num_data_subc] bin of data index i
     const int16_t *pilot_bin;    // [num_pilot_subc]
     // ---- one-warp-per-symbol receive kernels of the fft-512 geometry (rx512n.cuh) ----
-    // After warp_fft512 a lane holds bins c0 + 64 k3 (slot a) and c0 + 1 + 64 k3 (slot b).  lane_desc: per lane 8 x 16 bits
-    // for k3 = 0, 1, 6, 7 x slot a, b: [15:7] data index in the symbol (256: the bin carries no data), [6:3] combination.
-    // A combination is a (segment, k3) pair; combo_off = i' - ((bin & 63) - 1) for its bins (i' = data index, minus 256 in the
-    // negative half: the channel line's abscissa, Frame.hpp:425-430), combo_seg its segment.  strag_desc: the data bins of
-    // registers k3 = 2 and 5: the same 16 bits | scratch slot (32 (2 [k3 = 5] + slot) + origin lane) << 16 | (origin lane * 2 + slot) << 24.
-    const uint4 *lane_desc;      // [32]
-    const uint2 *acq_desc;       // [32] acquire kernel: per lane 4 x 16 bits (k3 = 0 slot a, b; k3 = 1 slot a, b): [7:0] index of the
-                                 //      phase the slot produces (0..127), [15] take the product of straggler bin 128 + [9:8] instead
-    const float2 *grid_conj;     // [fft_size] conj(tx grid of the preamble) / sqrt(fft_size), zero on unused bins
-    short combo_off[12];
-    signed char combo_seg[12];
-    unsigned long long combo_seg_packed;   // 4 bits per combination
-    unsigned strag_desc[8];
+    // After warp_fft512 lane 2 k1 + g holds mn[i] = X[k1 + 16 i + (g ? 384 : 0)] and ot[i] = X[k1 + 16 i + (g ? 128 : 256)].
+    // A COMBINATION is a set of data bins that share (array, g, i, segment): inside it the data index i' (minus 256 in the
+    // negative half: the channel line's abscissa, Frame.hpp:425-430) is k1 + off.
+    const uint4 *lane_desc;      // [32] per lane 8 x 16 bits for mn[0..7]: [15:7] data index in the symbol (256: no data), [6:2] combination
+    const uint2 *lane_aux;       // [32] .x: combination number `lane`: [2:0] segment, [31:16] off (signed); .y (lanes 0..6): the straggler
+                                 //      data bin number `lane` (bins 128..131, 381..383, held in ot[]): descriptor as above | (its k1) << 16
+    const uint2 *acq_desc;       // [32] acquire kernel: per lane 4 x 16 bits (even lane: mn[0..3]; odd lane: mn[4..7] of lane - 1): [7:0] index of
+                                 //      the phase the slot produces (0..127), [15] take the product of straggler bin 128 + [9:8] instead
+    const float2 *grid_lane;     // [32][10] conj(tx grid of the preamble) / sqrt(fft_size) at the bins of mn[0..7] and of the used ot[] register
+    int n_combos;
 };
 
 // Optional debug/parity taps of the fused rx kernel (device pointers, any may be null).

@@ -1,17 +1,17 @@
-// rx512n.cuh -- the receive chain for the fft-512 geometry, second formulation: ONE WARP PER OFDM SYMBOL.
+// rx512n.cuh -- the receive chain for the fft-512 geometry: ONE WARP PER OFDM SYMBOL, spectrum kept in registers.
 //
 // Reference chain (main.cpp:60-80 == rx.cpp:200-220): pilot_freq_sinh (Frame.hpp:285-337), freq_shift (:340-348),
 // cp_freq_sinh (:238-263), pr_phase_sinh (:265-274), chan_char_lq (:389-434), message.fft (:276-282 + Frame.cpp:73-96),
 // the equaliser loop (rx.cpp:214-216) and Modulation::demod (modulation.cpp:53-87).
 //
-// rx_demod512_kernel -- the message symbols of one frame per CTA, one warp each:
-//   TMA bulk copy of the symbol's 640 samples -> CP correlation -> theta_s -> (the coarse shift kc of the acquire kernel
-//   is already known, so the WHOLE-bin part m_s of the rotation is applied in the time domain too: after the transform
-//   every sub-carrier sits in a fixed lane and register) -> rotation merged into the first pass and its twiddles ->
-//   warp FFT-512 (fft512w.cuh) -> the 8 pilots and sum|pilot| to shared memory -> ONE block barrier ->
-//   equalise + hard-demap the lane's data bins STRAIGHT FROM REGISTERS -> one byte per symbol to shared memory ->
-//   MSB-first bit packing, one coalesced store per lane.
-//   The spectrum never goes to shared memory; the only cross-warp traffic is 8 pilots + 1 float per symbol.
+// Two kernels that together read every sample exactly once:
+//   rx_acquire512w_kernel  the preamble of one frame per WARP -> 40 bytes of scalars (FrameScal)
+//   rx_demod512_kernel     the message symbols of one frame per CTA, one WARP per symbol -> payload bytes
+// Both use warp_fft512 (fft512w.cuh): radix 16 x 16 x 2 on natural-layout packed f32x2 complex numbers, one shared-memory
+// exchange private to the warp.  After the transform every sub-carrier sits in a FIXED lane and register (the acquire
+// kernel's coarse shift is known before the demod kernel starts, so the whole-bin part of the CFO rotation is applied in the
+// time domain as well), and the demod kernel equalises and demaps straight from registers: the spectrum never goes to
+// shared memory, the only cross-warp traffic of a frame is 8 pilots + 1 float per symbol and one block barrier.
 //
 // Algebra: symbol s is rotated by exp(-j 2 pi beta_s j / 512), beta_s = theta_s + m_s, j = sample index in
 // the symbol (CP included), theta_s = Arg(CP correlation) in turns, m_s = the integer that makes theta_s - 512 shift + m_s
@@ -19,43 +19,39 @@
 // (Frame.cpp:89-92) except for message symbol 0 (the reference of every segment): c_1 = exp(-j 2 pi 1.25 (theta_0 + m_0)) exp(-j theta).
 // Equalised point of data index i (bin k, segment e):
 //   z = X_s[k] * P_1[e] c_1 / (P_s[e] g) * exp(-j (b i' + a)),   i' = i (i < 128) or i - 256
-// and i' = (k mod 64) - 1 + off(e, k div 64), so exp(-j b i') splits into a per-LANE factor exp(-j b ((k mod 64) - 1)) and a
-// per-(segment, k div 64) factor that is folded into the segment coefficient: 12 coefficients per symbol, 2 phasors per lane.
+// A lane's bins are k1 + 16 i + const, so exp(-j b i') splits into a per-LANE factor exp(-j b k1) and a factor per
+// COMBINATION (array, lane parity, register, segment) that is folded into the segment coefficient: at most 24 coefficients
+// per symbol (one per lane), one phasor per lane.
 #pragma once
 #include "compat.cuh"
 #include "params.h"
 #include "fft512w.cuh"
 #include "modem.cuh"
-#include "rx512.cuh"     // FrameScal, sym_turns, staged_sample
+#include "rx512.cuh"     // FrameScal, sym_turns
 
 namespace cofdmk {
-
-// position of bin k after warp_fft512: lane, slot (0 = a, 1 = b), register k3
-COFDM_HD constexpr int f512_lane(int k) { return (((k & 63) & ~1) >> 3) + 8 * ((((k & 63) & ~1) & 7) >> 1); }
-COFDM_HD constexpr int f512_slot(int k) { return k & 1; }
-COFDM_HD constexpr int f512_k3(int k) { return k >> 6; }
 
 // The fft-512 / 256 data / 8 pilot sub-carrier map (Frame.cpp:31-44) is fixed by the geometry; build_tables() checks
 // these lists against the tables it derives from the config.
 #define COFDM_F512_PILOTS(X) X(0, 33) X(1, 66) X(2, 99) X(3, 132) X(4, 380) X(5, 413) X(6, 446) X(7, 479)
-// data bins whose register (k3 = 2 or 5) holds almost no other used bin: handled apart, seven lanes in one go
+// used bins that live in the ot[] registers (ot[0] of odd lanes, ot[7] of even lanes): seven data bins and two pilots
 #define COFDM_F512_STRAG(X) X(0, 128) X(1, 129) X(2, 130) X(3, 131) X(4, 381) X(5, 382) X(6, 383)
 constexpr int kF512Strag = 7;
-constexpr int kF512Combos = 12;
+constexpr int kF512MaxCombos = 24;
+constexpr int kF512PfSize = 640, kF512PfW = 41, kF512PfBorder0 = 134;   // coarse-CFO windows of the geometry (Frame.hpp:311-321)
 
-constexpr int kDemodTabOff = kFft512wBytes;    // phasor table of the rotation (21 float2), beside the exchange planes
-constexpr int kDemodRegion = 5376;             // bytes of a warp's region: staging (5120) / exchanges (5152) + phasor table (168); 42 x 128
-// after the transform the region holds: [0, 1024) registers k3 = 2, 5 of every lane as four planes (k3 = 2 slot a, b;
-// k3 = 5 slot a, b); [1024, 1152) the 12 segment coefficients; [1280, 1552) one byte per demapped symbol (+ dummy slots
-// for bins that carry no data)
-constexpr int kDemodWtOff = 1024, kDemodSymOff = 1280;
+// a warp's region: staged samples (5120 B); then the FFT exchange [0, 4672) + the rotation phasors [4672, 4776); after the
+// transform: [0, 64) the straggler bins, [64, 256) the segment coefficients, [256, 528) one byte per demapped symbol
+constexpr int kDemodRegion = 5120;
+constexpr int kDemodTabOff = kFft512wBytes;
+constexpr int kDemodWtOff = 64, kDemodSymOff = 256;
 
 struct alignas(16) DemodShared {
     uint64_t mbar[kRxMaxSym];
     float2 pil[kRxMaxSym][8];        // pilot bins per message symbol (index s - 1)
     float pabs[kRxMaxSym];           // sum |pilot| per message symbol, zero beyond the last one
-    float4 lcl[32];                  // per pass-3 lane: exp(-j b (c0 - 1)), exp(-j b c0)
-    float2 ftab[16];                 // per (segment, k3) combination: c_1 exp(-j (b off + a))
+    float2 lcl[16];                  // exp(-j b k1), k1 = lane >> 1
+    float2 ftab[kF512MaxCombos];     // per combination: c_1 exp(-j (b off + a))
     float theta_t[kRxMaxSym + 1];    // Arg(C_s) in turns, by frame symbol index (taps)
     int mshift[kRxMaxSym + 1];       // m_s
 };
@@ -76,23 +72,45 @@ COFDM_DEV void warp_stage_symbol(void *dst, const char *src, int lane) {
     }
 }
 
-// two adjacent samples (index 2u, 2u + 1) of a symbol staged in shared memory, or (GLOBAL) straight from the capture
-template <int FMT, bool GLOBAL = false>
-COFDM_DEV void staged_pair(const void *region, int u, float2 &a, float2 &b) {
+// sample `idx` of a symbol staged in shared memory: float2, or int16 I,Q wire data widened here
+template <int FMT>
+COFDM_DEV float2 staged_at(const void *region, int idx) {
     if (FMT == kCI16) {
-        const uint2 w = GLOBAL ? __ldg(reinterpret_cast<const uint2 *>(region) + u) : reinterpret_cast<const uint2 *>(region)[u];
-        a = make_float2((float)(short)(w.x & 0xffffu), (float)(short)(w.x >> 16));
-        b = make_float2((float)(short)(w.y & 0xffffu), (float)(short)(w.y >> 16));
-    } else {
-        const float4 q = GLOBAL ? __ldg(reinterpret_cast<const float4 *>(region) + u) : reinterpret_cast<const float4 *>(region)[u];
-        a = make_float2(q.x, q.y);
-        b = make_float2(q.z, q.w);
+        const unsigned w = reinterpret_cast<const unsigned *>(region)[idx];
+        return make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
     }
+    return reinterpret_cast<const float2 *>(region)[idx];
 }
 
 // exp(-j 2 pi (theta + m) J / 512) for an integer sample index J: the whole-bin part is reduced exactly in integers
 COFDM_DEV float2 rot_phasor(float theta, int m, int J) {
     return fast_cis_turns(-(theta * ((float)J * (1.0f / 512.0f)) + (float)((m * J) & 511) * (1.0f / 512.0f)));
+}
+
+// The per-sample rotation of one symbol, x[l + 32 u] *= exp(-j 2 pi beta (l + 32 u) / 512), split as P(l) R^u:
+//   table entry `lane` = exp(-j 2 pi beta J / 512), J = 32 * 2^lane (lanes 0..3: R, R^2, R^4, R^8), 8 (lane - 4) (lanes 4..7: U^u),
+//   128 + (lane - 8) (lanes 8..15: V^v);   P(l) = exp(-j 2 pi beta (128 + l) / 512) = V^(l & 7) U^(l >> 3)   (the body starts at sample 128)
+// One sincos per lane.  The other powers of R are products of at most four of the directly evaluated ones (a power formed by
+// repeated squaring of R alone would carry n times the error of R).  Applied to the body samples v[n1] (index 128 + l + 32 n1).
+// Returns P(l); rp[1..4] = R^1..R^4 for the callers that also rotate the cyclic prefix.
+COFDM_DEV float2 rotate_body(float2 (&v)[16], float theta, int m, float2 *qt, int lane, float2 (&rp)[5]) {
+    {
+        const int J = lane < 4 ? (32 << lane) : (lane < 8 ? 8 * (lane - 4) : 128 + (lane - 8));
+        const float2 ph = rot_phasor(theta, m, J);
+        if (lane < 16) qt[lane] = ph;
+    }
+    __syncwarp();
+    const float4 r12 = reinterpret_cast<const float4 *>(qt)[0], r48 = reinterpret_cast<const float4 *>(qt)[1];
+    const float2 R1 = make_float2(r12.x, r12.y), R2 = make_float2(r12.z, r12.w), R4 = make_float2(r48.x, r48.y), R8 = make_float2(r48.z, r48.w);
+    const float2 P = nmul(qt[8 + (lane & 7)], qt[4 + (lane >> 3)]);
+    const float2 R3 = nmul(R2, R1), R5 = nmul(R4, R1), R6 = nmul(R4, R2), R7 = nmul(R4, R3);
+    v[1] = nmul(v[1], R1); v[2] = nmul(v[2], R2); v[3] = nmul(v[3], R3); v[4] = nmul(v[4], R4);
+    v[5] = nmul(v[5], R5); v[6] = nmul(v[6], R6); v[7] = nmul(v[7], R7); v[8] = nmul(v[8], R8);
+    v[9] = nmul(nmul(v[9], R1), R8);   v[10] = nmul(nmul(v[10], R2), R8); v[11] = nmul(nmul(v[11], R3), R8);
+    v[12] = nmul(nmul(v[12], R4), R8); v[13] = nmul(nmul(v[13], R5), R8); v[14] = nmul(nmul(v[14], R6), R8);
+    v[15] = nmul(nmul(v[15], R7), R8);
+    rp[0] = make_float2(1.f, 0.f); rp[1] = R1; rp[2] = R2; rp[3] = R3; rp[4] = R4;
+    return P;
 }
 
 // hard decision of one equalised point, natural layout (modulation.cpp:53-87): clamp to [-1,1], (v + 1) half + 0.5, truncate
@@ -134,10 +152,10 @@ COFDM_DEV void pack8(uint2 raw, uint8_t *dst, int mod_rt) {
     }
 }
 
-// MOD: modulation order the instance is specialised for (2, 4), or 0 = any (read from the configuration)
 #ifndef COFDM_DEMOD_MINB
 #define COFDM_DEMOD_MINB 4
 #endif
+// MOD: modulation order the instance is specialised for (2, 4), or 0 = any (read from the configuration)
 template <int FMT, bool USE_TMA, bool TAPS, int MAXW, int MOD>
 __global__ void __launch_bounds__(32 * MAXW, MAXW <= 8 ? COFDM_DEMOD_MINB : 1)
 rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
@@ -156,10 +174,6 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     const char *src = reinterpret_cast<const char *>(samples) + ((size_t)frame * (size_t)frame_stride + (size_t)s * 640) * sample_bytes;
 
     // ---- stage the symbol: one TMA bulk copy issued by the warp that consumes it ----
-#ifdef COFDM_DEMOD_DIRECT
-    if (USE_TMA) {
-    } else
-#endif
     if (USE_TMA) {
         if (lane == 0) {
             mbar_init(&M->mbar[warp], 1);
@@ -177,14 +191,13 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     if (!sync_less && lane < 5) fsw = __ldg(reinterpret_cast<const uint2 *>(fscal + frame) + lane);
     if (sync_less && lane == 2) fsw.x = 0x3f800000u;        // sync-less: kc = m0 = 0, th0 = theta = 0, rot_theta = 1, a = b = 0
     const int kc = (int)__shfl_sync(0xffffffffu, fsw.x, 0);
+    const uint2 aux = __ldg(&P.lane_aux[lane]);             // .x: combination `lane` (segment, offset); .y: straggler `lane`
     if (tid >= nw && tid < kRxMaxSym) M->pabs[tid] = 0.f;   // unused entries (the others are written by their warps); ordered by the block barrier
     if (warp == 0) {
-        // per pass-3 lane: exp(-j b (c0 - 1)), exp(-j b c0)
+        // exp(-j b k1), k1 = 0..15
         const double fb = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 4), (int)__shfl_sync(0xffffffffu, fsw.x, 4));
         const float bt = (float)fb * 0.15915494309189533577f;           // channel-line slope in turns per data index
-        const int c0 = fft512w_c0(lane);
-        const float2 la = cis_neg_turns_f(bt * (float)(c0 - 1)), lb = cis_neg_turns_f(bt * (float)c0);
-        M->lcl[lane] = make_float4(la.x, la.y, lb.x, lb.y);
+        if (lane < 16) M->lcl[lane] = cis_neg_turns_f(bt * (float)lane);
     }
     float2 rot_theta = make_float2(1.f, 0.f);
     if (warp == nw - 1 || TAPS) {
@@ -193,46 +206,34 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         rot_theta = make_float2(__uint_as_float(__shfl_sync(0xffffffffu, fsw.x, 2)), __uint_as_float(__shfl_sync(0xffffffffu, fsw.y, 2)));
         const double fa = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 3), (int)__shfl_sync(0xffffffffu, fsw.x, 3));
         const double fb = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 4), (int)__shfl_sync(0xffffffffu, fsw.x, 4));
-        if (warp == nw - 1 && lane < kF512Combos) {
+        if (warp == nw - 1 && lane < P.n_combos) {
             // c_1 exp(-j (b off + a)): the constant phase of message symbol 0 (Psi_1 = 1.25 (theta_0 + m_0) mod 1), theta, the channel line
             float acc = th0 * (640.0f / 512.0f);
             acc -= rintf(acc);
             const float psi1 = acc + (float)((5 * m0) & 3) * 0.25f;
             const float2 c1 = nmul(cis_neg_turns_f(psi1), rot_theta);
-            const float2 ee = cis_neg_turns_f((float)((fb * (double)P.combo_off[lane] + fa) * 0.15915494309189533577));
+            const float2 ee = cis_neg_turns_f((float)((fb * (double)((int)aux.x >> 16) + fa) * 0.15915494309189533577));
             M->ftab[lane] = nmul(c1, ee);
         }
         if (TAPS && tid == 0) { M->theta_t[0] = th0; M->mshift[0] = m0; }
     }
     __syncwarp();
-#ifndef COFDM_DEMOD_DIRECT
     if (USE_TMA) mbar_wait(&M->mbar[warp], 0);
-#endif
 
-    // ---- the lane's 16 body samples (pass-1 layout: t = 2 lane, 2 lane + 1; index 128 + t + 64 r) and 4 CP samples ----
-    float2 va[8], vb[8], cpa[2], cpb[2];
-#ifdef COFDM_DEMOD_DIRECT
-    if (USE_TMA) {
+    // ---- the lane's 16 body samples v[n1] = x[128 + lane + 32 n1] and 4 CP samples cp[c] = x[lane + 32 c] ----
+    float2 v[16], cp[4];
 #pragma unroll
-        for (int r = 0; r < 8; r++) staged_pair<FMT, true>(src, 64 + lane + 32 * r, va[r], vb[r]);
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = staged_at<FMT>(region, 128 + lane + 32 * n1);
 #pragma unroll
-        for (int c = 0; c < 2; c++) staged_pair<FMT, true>(src, lane + 32 * c, cpa[c], cpb[c]);
-    } else
-#endif
-    {
-#pragma unroll
-    for (int r = 0; r < 8; r++) staged_pair<FMT>(region, 64 + lane + 32 * r, va[r], vb[r]);
-#pragma unroll
-    for (int c = 0; c < 2; c++) staged_pair<FMT>(region, lane + 32 * c, cpa[c], cpb[c]);
-    }
-    __syncwarp();                                  // the region may now be reused (phasor table, exchanges)
+    for (int c = 0; c < 4; c++) cp[c] = staged_at<FMT>(region, lane + 32 * c);
+    __syncwarp();                                  // the region may now be reused (phasor table, exchange)
 
-    // ---- CP correlation (Frame.hpp:251-253): CP sample j pairs with body sample j + 512, i.e. r = 6, 7 ----
+    // ---- CP correlation (Frame.hpp:251-253): CP sample j pairs with body sample j + 512, i.e. n1 = 12 + c ----
     float theta = 0.f;
     int m = 0;
     if (!sync_less) {
-        float2 c = nmac_conj(nmac_conj(make_float2(0.f, 0.f), cpa[0], va[6]), cpb[0], vb[6]);
-        c = nmac_conj(nmac_conj(c, cpa[1], va[7]), cpb[1], vb[7]);
+        float2 c = nmac_conj(nmac_conj(make_float2(0.f, 0.f), cp[0], v[12]), cp[1], v[13]);
+        c = nmac_conj(nmac_conj(c, cp[2], v[14]), cp[3], v[15]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c = nadd(c, make_float2(__shfl_xor_sync(0xffffffffu, c.x, o), __shfl_xor_sync(0xffffffffu, c.y, o)));
         theta = fast_atan2_turns(c.y, c.x);
@@ -241,53 +242,32 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     }
     if (TAPS && lane == 0) { M->theta_t[s] = theta; M->mshift[s] = m; }
 
-    // ---- rotation phasors, ONE sincos per lane: table entry `lane` = exp(-j 2 pi beta J / 512) with
-    //      J = 64 lane (lane < 8: Q^r), 1 (lane 8: D), 16 (lane - 9) (9..12: U^u), 128 + 2 (lane - 13) (13..20: V^v);
-    //      P(t = 2 lane) = exp(-j 2 pi beta (128 + 2 lane) / 512) = V^(lane & 7) U^(lane >> 3) ----
-    float2 *qt = reinterpret_cast<float2 *>(region + kDemodTabOff);
-    {
-        const int J = lane < 8 ? 64 * lane : (lane == 8 ? 1 : (lane < 13 ? 16 * (lane - 9) : 128 + 2 * (lane - 13)));
-        const float2 ph = rot_phasor(theta, m, J);
-        if (lane < 21) qt[lane] = ph;
-    }
-    __syncwarp();
-    const float2 pa = nmul(qt[13 + (lane & 7)], qt[9 + (lane >> 3)]);
-    const float2 pb = nmul(pa, qt[8]);
+    float2 rp[5];
+    const float2 pl = rotate_body(v, theta, m, reinterpret_cast<float2 *>(region + kDemodTabOff), lane, rp);
     if (TAPS && taps.synced != nullptr) {
         // debug tap, completed by rx_synced_fixup2_kernel (per-symbol constant phase and theta)
         float2 *d = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
-        const int t = 2 * lane;
 #pragma unroll
-        for (int r = 0; r < 8; r++) {
-            d[128 + t + 64 * r] = nmul(nmul(va[r], qt[r]), pa);
-            d[129 + t + 64 * r] = nmul(nmul(vb[r], qt[r]), pb);
-        }
-        // CP samples j = t + 64 c: exp(-j 2 pi beta j / 512) = P(t) conj(Q^(2 - c))
-        d[t] = nmul(nmulc(cpa[0], qt[2]), pa);      d[t + 1] = nmul(nmulc(cpb[0], qt[2]), pb);
-        d[t + 64] = nmul(nmulc(cpa[1], qt[1]), pa); d[t + 65] = nmul(nmulc(cpb[1], qt[1]), pb);
-    }
-    {
-        const float4 *q4 = reinterpret_cast<const float4 *>(qt);
+        for (int n1 = 0; n1 < 16; n1++) d[128 + lane + 32 * n1] = nmul(v[n1], pl);
+        // CP sample j = lane + 32 c: exp(-j 2 pi beta j / 512) = P(lane) conj(R^(4 - c))
 #pragma unroll
-        for (int rr = 0; rr < 4; rr++) {
-            const float4 q = q4[rr];
-            if (rr > 0) { va[2 * rr] = nmul(va[2 * rr], make_float2(q.x, q.y)); vb[2 * rr] = nmul(vb[2 * rr], make_float2(q.x, q.y)); }
-            va[2 * rr + 1] = nmul(va[2 * rr + 1], make_float2(q.z, q.w));
-            vb[2 * rr + 1] = nmul(vb[2 * rr + 1], make_float2(q.z, q.w));
-        }
+        for (int c = 0; c < 4; c++) d[lane + 32 * c] = nmul(nmulc(cp[c], rp[4 - c]), pl);
     }
-    warp_fft512(va, vb, pa, pb, reinterpret_cast<float2 *>(region), P.tw_fft, lane);
-    // now va[k3] = X[c0 + 64 k3], vb[k3] = X[c0 + 1 + 64 k3], c0 = 2 (lane >> 3) + 8 (lane & 7); the region is free again
+    float2 mn[8], ot[8];
+    warp_fft512(v, pl, reinterpret_cast<float2 *>(region), P.tw_fft, lane, mn, ot);
+    // now mn[i] = X[k1 + 16 i + (g ? 384 : 0)], ot[i] = X[k1 + 16 i + (g ? 128 : 256)], lane = 2 k1 + g; the region is free again
 
-    // ---- pilots and sum |pilot| (Frame.cpp:76-80) to the CTA's shared memory; registers k3 = 2, 5 (the straggler data bins
-    //      128..131 and 381..383 live there) to the warp's region ----
+    // ---- pilots and sum |pilot| (Frame.cpp:76-80) to the CTA's shared memory; the straggler data bins to the warp's region ----
     float2 *scratch = reinterpret_cast<float2 *>(region);
     {
         float2 *pil = M->pil[warp];
-#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pil[p] = (f512_slot(bin) ? vb : va)[f512_k3(bin)];
+        const float2 osel = (lane & 1) ? ot[0] : ot[7];          // the only ot[] registers that hold used bins
+#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pil[p] = f512_main(bin) ? mn[f512_i(bin)] : osel;
         COFDM_F512_PILOTS(COFDM_X)
 #undef COFDM_X
-        scratch[lane] = va[2]; scratch[32 + lane] = vb[2]; scratch[64 + lane] = va[5]; scratch[96 + lane] = vb[5];
+#define COFDM_X(q, bin) if (lane == f512_lane(bin)) scratch[q] = osel;
+        COFDM_F512_STRAG(COFDM_X)
+#undef COFDM_X
         __syncwarp();
         float pm = 0.f;
         if (lane < 8) pm = sqrtf(cnorm2(pil[lane]));
@@ -305,14 +285,13 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         for (int o = kRxMaxSym / 2; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
         g = pv * P.inv_pilot_norm;
     }
-    const float4 lcv = M->lcl[lane];
-    const float2 lca = make_float2(lcv.x, lcv.y), lcb = make_float2(lcv.z, lcv.w);
+    const float2 lc = M->lcl[lane >> 1];
 
-    // ---- the 12 segment coefficients of this symbol (Frame.cpp:89-92 + rx.cpp:214-216):
+    // ---- the segment coefficients of this symbol (Frame.cpp:89-92 + rx.cpp:214-216), one per combination:
     //      W[q] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) * ftab[q],  e = segment of combination q ----
     char *wt = region + kDemodWtOff;
-    if (lane < kF512Combos) {
-        const int e = (int)((P.combo_seg_packed >> (4 * lane)) & 7ull);
+    if (lane < P.n_combos) {
+        const int e = (int)(aux.x & 7u);
         const float2 p1 = M->pil[0][e], ps = M->pil[warp][e];
         const float2 w = nscale(nmulc(p1, ps), __fdividef(1.0f, cnorm2(ps) * g));
         reinterpret_cast<float2 *>(wt)[lane] = nmul(w, M->ftab[lane]);
@@ -334,46 +313,51 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
             const float psi = sym_turns(M->theta_t, M->mshift, s);
             const float2 rs = nscale(nmul(cis_neg_turns_f(psi), rot_theta), 1.0f / g);
             float2 *dst = taps.grid + ((size_t)frame * nw + (s - 1)) * 512;
-            const int c0 = fft512w_c0(lane);
+            const int k1 = lane >> 1, gg = lane & 1;
 #pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) { dst[c0 + 64 * k3] = nmul(va[k3], rs); dst[c0 + 1 + 64 * k3] = nmul(vb[k3], rs); }
+            for (int i = 0; i < 8; i++) {
+                dst[k1 + 16 * i + (gg ? 384 : 0)] = nmul(mn[i], rs);
+                dst[k1 + 16 * i + (gg ? 128 : 256)] = nmul(ot[i], rs);
+            }
         }
     }
 
-    // ---- equalise + hard demap (modulation.cpp:53-87) straight from the registers.  Per slot 16 descriptor bits:
-    //      [15:7] data index (>= 256: a dummy slot, the bin carries no data), [6:3] combination.  No branches. ----
+    // ---- equalise + hard demap (modulation.cpp:53-87) straight from the registers.  Per register 16 descriptor bits:
+    //      [15:7] data index (256: a dummy slot, the bin carries no data), [6:2] combination.  No branches. ----
     const DemapK dk = make_demapk(P.mod_type);
     uint8_t *sb = reinterpret_cast<uint8_t *>(region + kDemodSymOff);
     const uint4 desc = __ldg(&P.lane_desc[lane]);
     float2 *ctap = (TAPS && taps.constell != nullptr) ? taps.constell + ((size_t)frame * nw + (s - 1)) * 256 : nullptr;
-    const float2 xa0 = nmul(va[0], lca), xa1 = nmul(va[1], lca), xa6 = nmul(va[6], lca), xa7 = nmul(va[7], lca);
-    const float2 xb0 = nmul(vb[0], lcb), xb1 = nmul(vb[1], lcb), xb6 = nmul(vb[6], lcb), xb7 = nmul(vb[7], lcb);
     float2 xs = make_float2(0.f, 0.f);             // the straggler this lane equalises (lanes 0..6)
-    unsigned ds = 0x8000u;                         // dummy slot 256
+    unsigned ds = 256u << 7;                       // dummy slot
     if (lane < kF512Strag) {
-        const unsigned d32 = P.strag_desc[lane];   // descriptor | scratch slot << 16 | (origin lane * 2 + slot) << 24
-        ds = d32 & 0xffffu;
-        xs = nmul(scratch[(d32 >> 16) & 0xffu], reinterpret_cast<const float2 *>(M->lcl)[d32 >> 24]);
+        ds = aux.y & 0xffffu;                      // descriptor | (k1 of the lane that held the bin) << 16
+        xs = nmul(scratch[lane], M->lcl[aux.y >> 16]);
     }
-#define COFDM_EQ(X, IDX, WOFF)                                                                   \
+#define COFDM_EQ(X, D16)                                                                         \
     do {                                                                                         \
-        const float2 z_ = nmul((X), *reinterpret_cast<const float2 *>(wt + (WOFF)));             \
-        if (TAPS && ctap != nullptr && (IDX) < 256u) ctap[(IDX)] = z_;                           \
-        sb[(IDX)] = (uint8_t)demap_n<MOD>(z_, dk);                                               \
+        const unsigned d_ = (D16);                                                               \
+        const unsigned i_ = d_ >> 7;                                                             \
+        const float2 z_ = nmul((X), *reinterpret_cast<const float2 *>(wt + ((d_ & 0x7cu) << 1))); \
+        if (TAPS && ctap != nullptr && i_ < 256u) ctap[i_] = z_;                                 \
+        sb[i_] = (uint8_t)demap_n<MOD>(z_, dk);                                                  \
     } while (0)
 #define COFDM_EQ_ALL(F)                                                                          \
-    F(xa0, (desc.x >> 7) & 0x1ffu, desc.x & 0x78u); F(xb0, desc.x >> 23, (desc.x >> 16) & 0x78u); \
-    F(xa1, (desc.y >> 7) & 0x1ffu, desc.y & 0x78u); F(xb1, desc.y >> 23, (desc.y >> 16) & 0x78u); \
-    F(xa6, (desc.z >> 7) & 0x1ffu, desc.z & 0x78u); F(xb6, desc.z >> 23, (desc.z >> 16) & 0x78u); \
-    F(xa7, (desc.w >> 7) & 0x1ffu, desc.w & 0x78u); F(xb7, desc.w >> 23, (desc.w >> 16) & 0x78u); \
-    F(xs, (ds >> 7) & 0x1ffu, ds & 0x78u)
+    F(nmul(mn[0], lc), desc.x & 0xffffu); F(nmul(mn[1], lc), desc.x >> 16);                      \
+    F(nmul(mn[2], lc), desc.y & 0xffffu); F(nmul(mn[3], lc), desc.y >> 16);                      \
+    F(nmul(mn[4], lc), desc.z & 0xffffu); F(nmul(mn[5], lc), desc.z >> 16);                      \
+    F(nmul(mn[6], lc), desc.w & 0xffffu); F(nmul(mn[7], lc), desc.w >> 16);                      \
+    F(xs, ds)
     COFDM_EQ_ALL(COFDM_EQ);
 #undef COFDM_EQ
     if (ambiguous != nullptr) {
         // optional count of boundary-ambiguous decisions (margin kAmbigMargin): the points are recomputed, off the fast path
         int n_amb = 0;
-#define COFDM_AMB(X, IDX, WOFF) \
-        if ((IDX) < 256u) n_amb += demap_ambiguous(nmul((X), *reinterpret_cast<const float2 *>(wt + (WOFF))), dk) ? 1 : 0
+#define COFDM_AMB(X, D16)                                                                        \
+        do {                                                                                     \
+            const unsigned d_ = (D16);                                                           \
+            if ((d_ >> 7) < 256u) n_amb += demap_ambiguous(nmul((X), *reinterpret_cast<const float2 *>(wt + ((d_ & 0x7cu) << 1))), dk) ? 1 : 0; \
+        } while (0)
         COFDM_EQ_ALL(COFDM_AMB);
 #undef COFDM_AMB
 #pragma unroll
@@ -397,14 +381,14 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
 //   fine CFO     cp_freq_sinh (:238-263) on the preamble: CP correlation -> theta_0, m_0; rotation, warp FFT-512
 //   phase lock   pr_phase_sinh (:265-274): theta = arg sum conj(ref) y, body part by Parseval on the used bins
 //   channel fit  chan_char_lq (:389-434): 128 phases, the reference's one-step unwrap, the (bug-compatible) line
-// and hands 40 bytes of scalars (FrameScal) to the demod kernel.  The lane's 20 raw samples x[2 lane (+1) + 64 q] are the
-// inputs of BOTH transforms (radix-10 first pass of the 640-point one, CP + radix-8 first pass of the 512-point one):
-// they are read from the staged copy once and stay in registers.
-// Shared memory per warp: S (5120 B: staged samples -> second coarse plane -> phasor table, phases) and A (5376 B:
-// first coarse plane, padded -> |X|^2 -> FFT-512 exchanges).
+// and hands 40 bytes of scalars (FrameScal) to the demod kernel.  The lane's 20 raw samples x[lane + 32 u] are the inputs of
+// BOTH transforms (radix-10 first pass of the 640-point one: butterflies lane and lane + 32; CP + radix-16 first pass of the
+// 512-point one): they are read from the staged copy once and stay in registers.
+// Shared memory per warp: S (5120 B: staged samples -> second coarse plane -> phasor table, phases) and A (5632 B:
+// first coarse plane, rows padded 10 -> 11 -> |X|^2 -> FFT-512 exchange).
 // ================================================================================================================
 constexpr int kAcqwWarps = 4;
-constexpr int kAcqwS = 5120, kAcqwA = 5376;
+constexpr int kAcqwS = 5120, kAcqwA = 5632;
 constexpr int kAcqwRegion = kAcqwS + kAcqwA;
 COFDM_HD constexpr size_t rx_acquire512w_smem_bytes() { return (size_t)kAcqwWarps * kAcqwRegion + kAcqwWarps * sizeof(uint64_t); }
 
@@ -434,79 +418,83 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
     }
     __syncwarp();
     if (USE_TMA) mbar_wait(mbar, 0);
-    // ---- the lane's 20 raw samples: ra[q] = x[2 lane + 64 q], rb[q] = x[2 lane + 1 + 64 q] ----
-    float2 ra[10], rb[10];
+    // ---- the lane's 20 raw samples raw[u] = x[lane + 32 u] ----
+    float2 raw[20];
 #pragma unroll
-    for (int q = 0; q < 10; q++) staged_pair<FMT>(S, lane + 32 * q, ra[q], rb[q]);
+    for (int u = 0; u < 20; u++) raw[u] = staged_at<FMT>(S, lane + 32 * u);
     __syncwarp();                                      // S may be overwritten from here on
 
     int kc = 0;
     if (!sync_less) {
         // ================= coarse CFO: 640-point spectrum of the received preamble, CP included =================
-        // pass 1: radix 10, butterflies j = 2 lane, 2 lane + 1; output index I = 10 j + q lives at slot I + I / 20
+        // pass 1: radix 10, butterflies j = lane (inputs raw[2 q]) and j = lane + 32 (raw[2 q + 1]); output 10 j + q at slot 11 j + q
         {
-            float2 v[10];
+            float2 t[10];
 #pragma unroll
-            for (int q = 0; q < 10; q++) v[q] = ra[q];
-            ndft10(v);
+            for (int q = 0; q < 10; q++) t[q] = raw[2 * q];
+            ndft10(t);
 #pragma unroll
-            for (int q = 0; q < 10; q++) A[21 * lane + q] = v[q];
+            for (int q = 0; q < 10; q++) A[11 * lane + q] = t[q];
 #pragma unroll
-            for (int q = 0; q < 10; q++) v[q] = rb[q];
-            ndft10(v);
+            for (int q = 0; q < 10; q++) t[q] = raw[2 * q + 1];
+            ndft10(t);
 #pragma unroll
-            for (int q = 0; q < 10; q++) A[21 * lane + 10 + q] = v[q];
+            for (int q = 0; q < 10; q++) A[11 * (lane + 32) + q] = t[q];
         }
         __syncwarp();
         float2 *B = reinterpret_cast<float2 *>(S);
-        // pass 2: radix 8, ns = 10: butterfly j (80 of them), k = j mod 10; inputs I = j + 80 q at slot I + I / 20 = (j + j / 20) + 84 q
+        // pass 2: radix 8, ns = 10: butterfly j (80 of them), k = j mod 10; inputs I = j + 80 q at slot I + I / 10 = (j + j / 10) + 88 q
 #pragma unroll 1
         for (int j = lane; j < 80; j += 32) {
-            const int g = j / 10, k = j - 10 * g;
-            float2 v[8], w[8];
-            const float2 *in = A + j + j / 20;
+            const int gq = j / 10, k = j - 10 * gq;
+            float2 t[8], w[8];
+            const float2 *in = A + j + gq;
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = in[84 * q];
+            for (int q = 0; q < 8; q++) t[q] = in[88 * q];
             npowers7(__ldg(&P.tw_pf[8 * k]), w);                          // W640^{8 k q}
 #pragma unroll
-            for (int q = 1; q < 8; q++) v[q] = nmul(v[q], w[q]);
-            ndft8(v);
-            float2 *out = B + 80 * g + k;
+            for (int q = 1; q < 8; q++) t[q] = nmul(t[q], w[q]);
+            ndft8(t);
+            float2 *out = B + 80 * gq + k;
 #pragma unroll
-            for (int q = 0; q < 8; q++) out[10 * q] = v[q];
+            for (int q = 0; q < 8; q++) out[10 * q] = t[q];
         }
         __syncwarp();
         // pass 3: radix 8, ns = 80: only |X|^2 is kept, as float[640] in A
         float *mag = reinterpret_cast<float *>(A);
 #pragma unroll 1
         for (int j = lane; j < 80; j += 32) {
-            float2 v[8], w[8];
+            float2 t[8], w[8];
 #pragma unroll
-            for (int q = 0; q < 8; q++) v[q] = B[j + 80 * q];
+            for (int q = 0; q < 8; q++) t[q] = B[j + 80 * q];
             npowers7(__ldg(&P.tw_pf[j]), w);                              // W640^{j q}
 #pragma unroll
-            for (int q = 1; q < 8; q++) v[q] = nmul(v[q], w[q]);
-            ndft8(v);
+            for (int q = 1; q < 8; q++) t[q] = nmul(t[q], w[q]);
+            ndft8(t);
 #pragma unroll
-            for (int q = 0; q < 8; q++) { const float2 sq = p_mul(v[q], v[q]); mag[j + 80 * q] = sq.x + sq.y; }
+            for (int q = 0; q < 8; q++) {
+                if (q == 3 || q == 4) continue;        // bins 240..399: no pilot window reaches them (fft-shifted 134..297, 339..502)
+                const float2 sq = p_mul(t[q], t[q]);
+                mag[j + 80 * q] = sq.x + sq.y;
+            }
         }
         __syncwarp();
-        // arg-max of |spectrum| in the pilot windows, first maximum wins (Frame.hpp:311-331); warp arg-max by two hardware
-        // reductions: the magnitudes are non-negative floats, so their bit patterns order like unsigned integers
-        const int np = P.num_pilot_subc, half = P.pf_size / 2;
+        // arg-max of |spectrum| in the eight pilot windows, first maximum wins (Frame.hpp:311-331).  The windows are fixed by the
+        // geometry (41 bins each from fft-shifted index 134, the DC window skipped; checked by build_tables), none straddles
+        // the fft-shift seam.  Warp arg-max by two hardware reductions: the magnitudes are non-negative floats, so their bit
+        // patterns order like unsigned integers; among the lanes holding the maximum the smallest index wins.
+        constexpr int np = 8, half = kF512PfSize / 2;
         int ksum = 0;
+#pragma unroll
         for (int wi = 0; wi < np; wi++) {
             const int win = wi < np / 2 ? wi : wi + 1;                     // window np/2 (DC) is skipped
-            int lo = P.pf_border0 + win * P.pf_pilot_w;
-            const int hi = lo + P.pf_pilot_w;
-            if (win == 0 && lo < 0) lo = 0;
-            float best = -1.0f;
-            int bi = 0x7fffffff;
-            for (int ks = lo + lane; ks < hi; ks += 32) {                  // ks = fft-shifted index
-                const float mv = mag[ks < half ? ks + half : ks - half];
-                if (mv > best) { best = mv; bi = ks; }
-            }
-            const unsigned bb = best < 0.f ? 0u : __float_as_uint(best);
+            const int lo = kF512PfBorder0 + win * kF512PfW;                // fft-shifted index of the window's first bin
+            const float *mw = mag + (lo < half ? lo + half : lo - half);
+            const float m1 = mw[lane];
+            const float m2 = lane < kF512PfW - 32 ? mw[32 + lane] : -1.0f;
+            const bool second = m2 > m1;
+            const unsigned bb = __float_as_uint(second ? m2 : m1);
+            const int bi = lo + lane + (second ? 32 : 0);
             const unsigned mx = __reduce_max_sync(0xffffffffu, bb);
             ksum += __reduce_min_sync(0xffffffffu, bb == mx ? bi : 0x7fffffff);
         }
@@ -514,68 +502,58 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
         __syncwarp();                                                      // the planes are free again
     }
 
-    // ================= fine CFO of the preamble (cp_freq_sinh): CP sample j pairs with body sample j + 512 (q = 8, 9) =================
+    // ================= fine CFO of the preamble (cp_freq_sinh): CP sample j pairs with body sample j + 512 (u = 16 + c) =================
     float theta0 = 0.f;
     int m0 = 0;
     if (!sync_less) {
-        float2 c = nmac_conj(nmac_conj(make_float2(0.f, 0.f), ra[0], ra[8]), rb[0], rb[8]);
-        c = nmac_conj(nmac_conj(c, ra[1], ra[9]), rb[1], rb[9]);
+        float2 c = nmac_conj(nmac_conj(make_float2(0.f, 0.f), raw[0], raw[16]), raw[1], raw[17]);
+        c = nmac_conj(nmac_conj(c, raw[2], raw[18]), raw[3], raw[19]);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) c = nadd(c, make_float2(__shfl_xor_sync(0xffffffffu, c.x, o), __shfl_xor_sync(0xffffffffu, c.y, o)));
         theta0 = fast_atan2_turns(c.y, c.x);
         m0 = (int)ceilf(-(theta0 - (float)kc * P.pf_bins512) - 0.5f);
     }
-    // rotation phasors (see rx_demod512_kernel): table entry `lane` = exp(-j 2 pi beta J / 512)
     float2 *qt = reinterpret_cast<float2 *>(S);
-    {
-        const int J = lane < 8 ? 64 * lane : (lane == 8 ? 1 : (lane < 13 ? 16 * (lane - 9) : 128 + 2 * (lane - 13)));
-        const float2 ph = rot_phasor(theta0, m0, J);
-        if (lane < 21) qt[lane] = ph;
-    }
-    __syncwarp();
-    const float2 pa = nmul(qt[13 + (lane & 7)], qt[9 + (lane >> 3)]);
-    const float2 pb = nmul(pa, qt[8]);
-    // CP samples j = t + 64 c rotated: exp(-j 2 pi beta j / 512) = P(t) conj(Q^(2 - c))
-    const float2 y0a = nmul(nmulc(ra[0], qt[2]), pa), y0b = nmul(nmulc(rb[0], qt[2]), pb);
-    const float2 y1a = nmul(nmulc(ra[1], qt[1]), pa), y1b = nmul(nmulc(rb[1], qt[1]), pb);
-    float2 va[8], vb[8];
-    va[0] = ra[2]; vb[0] = rb[2];
+    float2 v[16], rp[5];
 #pragma unroll
-    for (int r = 1; r < 8; r++) { va[r] = nmul(ra[r + 2], qt[r]); vb[r] = nmul(rb[r + 2], qt[r]); }
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = raw[4 + n1];
+    const float2 pl = rotate_body(v, theta0, m0, qt, lane, rp);
+    // CP sample j = lane + 32 c rotated: exp(-j 2 pi beta j / 512) = P(lane) conj(R^(4 - c))
+    float2 ycp[4];
+#pragma unroll
+    for (int c = 0; c < 4; c++) ycp[c] = nmul(nmulc(raw[c], rp[4 - c]), pl);
     if (TAPS && taps.synced != nullptr) {
         // debug tap, completed by rx_synced_fixup2_kernel (theta; the preamble has no other constant phase)
         float2 *d = taps.synced + (size_t)frame * P.rx_len;
-        const int t = 2 * lane;
 #pragma unroll
-        for (int r = 0; r < 8; r++) { d[128 + t + 64 * r] = nmul(va[r], pa); d[129 + t + 64 * r] = nmul(vb[r], pb); }
-        d[t] = y0a; d[t + 1] = y0b; d[t + 64] = y1a; d[t + 65] = y1b;
+        for (int n1 = 0; n1 < 16; n1++) d[128 + lane + 32 * n1] = nmul(v[n1], pl);
+#pragma unroll
+        for (int c = 0; c < 4; c++) d[lane + 32 * c] = ycp[c];
     }
-    __syncwarp();                                                          // everybody has read the phasor table: A / S are free
-    warp_fft512(va, vb, pa, pb, A, P.tw_fft, lane);
-    // now va[k3] = Y[c0 + 64 k3], vb[k3] = Y[c0 + 1 + 64 k3], the true spectrum of the preamble (symbol 0 has no constant phase)
+    float2 mn[8], ot[8];
+    warp_fft512(v, pl, A, P.tw_fft, lane, mn, ot);
+    // now mn[] / ot[] hold the true spectrum Y of the preamble (symbol 0 has no constant phase)
+    const float2 osel = (lane & 1) ? ot[0] : ot[7];                        // the only ot[] registers that hold used bins
 
-    const int c0 = fft512w_c0(lane);
     if (sync_less) {
         // PREAMBLE_FORM::chan_char (Frame.hpp:375-385) on the preamble as it stands: pr = preamble.fft() (own pilot
         // normalisation, Frame.cpp:76-84; coef == 1), chan_est[i] = pr[i] / mod_preamble[i]
         if (TAPS && taps.chan != nullptr) {
             float pm = 0.f;
-#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pm = sqrtf(cnorm2((f512_slot(bin) ? vb : va)[f512_k3(bin)]));
+#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pm = sqrtf(cnorm2(f512_main(bin) ? mn[f512_i(bin)] : osel));
             COFDM_F512_PILOTS(COFDM_X)
 #undef COFDM_X
             pm = warp_sum(pm);
             const float igp = (8.0f * P.pilot_ampl) / pm;
+            const int k1 = lane >> 1, gg = lane & 1;
 #pragma unroll
-            for (int k3 = 0; k3 < 8; k3++) {
-                if (k3 == 3 || k3 == 4) continue;
-#pragma unroll
-                for (int sl = 0; sl < 2; sl++) {
-                    const int k = c0 + sl + 64 * k3, i = __ldg(&P.bin_map[k]);
-                    if (i >= 0) {
-                        const float2 mp = __ldg(&P.mod_preamble[i]);
-                        const float2 y = cscale(sl ? vb[k3] : va[k3], igp);
-                        taps.chan[(size_t)frame * 256 + i] = cscale(cmulc(y, mp), 1.0f / cnorm2(mp));
-                    }
+            for (int i = 0; i < 9; i++) {
+                const int k = i < 8 ? k1 + 16 * i + (gg ? 384 : 0) : k1 + (gg ? 128 : 256 + 112);
+                const int di = __ldg(&P.bin_map[k]);
+                if (di >= 0) {
+                    const float2 mp = __ldg(&P.mod_preamble[di]);
+                    const float2 y = cscale(i < 8 ? mn[i < 8 ? i : 0] : osel, igp);
+                    taps.chan[(size_t)frame * 256 + di] = cscale(cmulc(y, mp), 1.0f / cnorm2(mp));
                 }
             }
         }
@@ -583,30 +561,26 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
     }
 
     // ================= pr_phase_sinh: z = sum_{i<640} conj(ref[i]) y[i]; body by Parseval: (1/sqrt 512) sum_k conj(G[k]) Y[k],
-    //                   G = tx grid of the preamble (P.grid_conj = conj(G) / sqrt 512, zero on unused bins) =================
-    float2 prod[4];                                    // Y conj(G) of the slots k3 = 0, 1 (x slot a, b): the first 128 data sub-carriers live there
+    //                   G = tx grid of the preamble (P.grid_lane: conj(G) / sqrt 512 in lane order, zero on unused bins) =================
+    float2 prod[8];                                    // Y conj(G) of mn[0..7]: the first 128 data sub-carriers are mn[] of the even lanes
     float2 z;
     {
-        const float4 *g4 = reinterpret_cast<const float4 *>(P.grid_conj) + (c0 >> 1);
-        const float4 g0 = __ldg(g4), g1 = __ldg(g4 + 32), g2 = __ldg(g4 + 64), g5 = __ldg(g4 + 160), g6 = __ldg(g4 + 192), g7 = __ldg(g4 + 224);
-        prod[0] = nmul(va[0], make_float2(g0.x, g0.y)); prod[1] = nmul(vb[0], make_float2(g0.z, g0.w));
-        prod[2] = nmul(va[1], make_float2(g1.x, g1.y)); prod[3] = nmul(vb[1], make_float2(g1.z, g1.w));
-        const float2 s2a = nmul(va[2], make_float2(g2.x, g2.y)), s2b = nmul(vb[2], make_float2(g2.z, g2.w));
-        z = nadd(nadd(prod[0], prod[1]), nadd(prod[2], prod[3]));
-        z = nadd(z, nadd(s2a, s2b));
-        z = nmac(nmac(z, va[5], make_float2(g5.x, g5.y)), vb[5], make_float2(g5.z, g5.w));
-        z = nmac(nmac(z, va[6], make_float2(g6.x, g6.y)), vb[6], make_float2(g6.z, g6.w));
-        z = nmac(nmac(z, va[7], make_float2(g7.x, g7.y)), vb[7], make_float2(g7.z, g7.w));
-        // CP part: conj(ref[j]) y[j], j = 2 lane (+1), 64 + 2 lane (+1)
-        const float4 *r4 = reinterpret_cast<const float4 *>(P.preamble_td) + lane;
-        const float4 r0 = __ldg(r4), r1 = __ldg(r4 + 32);
-        z = nmac_conj(nmac_conj(z, make_float2(r0.x, r0.y), y0a), make_float2(r0.z, r0.w), y0b);
-        z = nmac_conj(nmac_conj(z, make_float2(r1.x, r1.y), y1a), make_float2(r1.z, r1.w), y1b);
-        // the data bins 128..131 (k3 = 2 of lanes 0 and 8) belong to the first 128 sub-carriers too: their products travel
-        // through shared memory to the four lanes whose slot holds no data (bin 0 and the pilots 33, 66, 99)
-        float2 *sx = qt + 24;
-        if (lane == f512_lane(128)) { sx[0] = s2a; sx[1] = s2b; }
-        if (lane == f512_lane(130)) { sx[2] = s2a; sx[3] = s2b; }
+        const float4 *g4 = reinterpret_cast<const float4 *>(P.grid_lane) + 5 * lane;   // mn[0..7], osel, pad
+        const float4 ga = __ldg(g4), gb = __ldg(g4 + 1), gc = __ldg(g4 + 2), gd = __ldg(g4 + 3), ge = __ldg(g4 + 4);
+        prod[0] = nmul(mn[0], make_float2(ga.x, ga.y)); prod[1] = nmul(mn[1], make_float2(ga.z, ga.w));
+        prod[2] = nmul(mn[2], make_float2(gb.x, gb.y)); prod[3] = nmul(mn[3], make_float2(gb.z, gb.w));
+        prod[4] = nmul(mn[4], make_float2(gc.x, gc.y)); prod[5] = nmul(mn[5], make_float2(gc.z, gc.w));
+        prod[6] = nmul(mn[6], make_float2(gd.x, gd.y)); prod[7] = nmul(mn[7], make_float2(gd.z, gd.w));
+        const float2 ps = nmul(osel, make_float2(ge.x, ge.y));
+        z = nadd(nadd(nadd(prod[0], prod[1]), nadd(prod[2], prod[3])), nadd(nadd(prod[4], prod[5]), nadd(prod[6], prod[7])));
+        z = nadd(z, ps);
+        // CP part: conj(ref[j]) y[j], j = lane + 32 c
+#pragma unroll
+        for (int c = 0; c < 4; c++) z = nmac_conj(z, __ldg(&P.preamble_td[lane + 32 * c]), ycp[c]);
+        // the data bins 128..131 (ot[0] of lanes 1, 3, 5, 7) belong to the first 128 sub-carriers too: their products travel
+        // through shared memory to the four phase slots that hold no data (bin 0 and the pilots 33, 66, 99)
+        float2 *sx = qt + 16;
+        if ((lane & 1) && lane < 8) sx[lane >> 1] = ps;
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) z = nadd(z, make_float2(__shfl_xor_sync(0xffffffffu, z.x, o), __shfl_xor_sync(0xffffffffu, z.y, o)));
@@ -614,16 +588,24 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
     const float2 rot = make_float2(z.x * inv, -z.y * inv);               // exp(-j theta)
     const float theta = TAPS ? atan2f(z.y, z.x) : 0.f;
 
-    // ================= chan_char_lq: phase[i] = arg(pr[i] / mod_preamble[i]), i < 128 (Frame.hpp:403-405) =================
+    // ================= chan_char_lq: phase[i] = arg(pr[i] / mod_preamble[i]), i < 128 (Frame.hpp:403-405).  The 128 products sit
+    //                   in mn[] of the 16 even lanes; each hands mn[4..7] to its odd neighbour so that every lane evaluates four =================
     const float TWO_PI_F = 6.28318530717958647692f, PI_F = 3.14159265358979323846f;
     float *phs = reinterpret_cast<float *>(qt + 32);                      // 128 phases
     {
-        const uint2 ad = __ldg(&P.acq_desc[lane]);   // 4 x 16 bits (k3 = 0 a, b; k3 = 1 a, b): [7:0] phase index, [15] straggler, [9:8] which
-        const float2 *sx = qt + 24;
+        float2 pp[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            const float2 up = make_float2(__shfl_sync(0xffffffffu, prod[4 + u].x, lane & ~1), __shfl_sync(0xffffffffu, prod[4 + u].y, lane & ~1));
+            pp[u] = (lane & 1) ? up : prod[u];
+        }
+        __syncwarp();                                                     // sx[] is visible
+        const uint2 ad = __ldg(&P.acq_desc[lane]);   // 4 x 16 bits: [7:0] phase index, [15] take straggler product [9:8] instead
+        const float2 *sx = qt + 16;
 #pragma unroll
         for (int u = 0; u < 4; u++) {
             const unsigned d = ((u < 2 ? ad.x : ad.y) >> (16 * (u & 1))) & 0xffffu;
-            float2 pr = prod[u];
+            float2 pr = pp[u];
             if (d & 0x8000u) pr = sx[(d >> 8) & 3u];
             const float2 dr = nmul(pr, rot);
             phs[d & 0xffu] = fast_atan2_turns(dr.y, dr.x) * TWO_PI_F;

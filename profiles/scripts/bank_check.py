@@ -1,8 +1,8 @@
-"""Brute-force bank-conflict check of the shared-memory exchange layouts of the one-warp FFT-512
-(c-ofdm_b200/csrc/fft512w.cuh).  A 128-bit warp access is served in 4 phases of 8 lanes; a phase is
-conflict-free when its 8 lanes touch 8 different 16-byte bank groups (address/16 mod 8).  A 64-bit
-access is served in 2 phases of 16 lanes that must touch 16 different 8-byte groups (address/8 mod 16).
-Addresses below are float2 (8-byte) slot indices.  Run: python bank_check.py"""
+"""Brute-force bank-conflict check of the shared-memory exchange of the one-warp FFT-512
+(c-ofdm_b200/csrc/fft512w.cuh, radix 16 x 16 x 2).  A 128-bit warp access is served in 4 phases of 8
+lanes; a phase is conflict-free when its 8 lanes touch 8 different 16-byte bank groups (address/16
+mod 8).  A 64-bit access is served in 2 phases of 16 lanes that must touch 16 different 8-byte groups
+(address/8 mod 16).  Addresses below are float2 (8-byte) slot indices.  Run: python bank_check.py"""
 
 
 def phases128(addrs):
@@ -27,37 +27,28 @@ def phases64(addrs):
     return worst
 
 
-def e1(k1, t):                       # plane B (t odd) starts at slot 324
-    return 324 * (t & 1) + 40 * k1 + (t >> 1)
-
-
-def e2(k1, k2, n3):                  # plane A: n3 in {0,1,4,5}; plane B (slot 272 on): n3 in {2,3,6,7}
-    return 272 * ((n3 >> 1) & 1) + 34 * k2 + 4 * k1 + (n3 & 1) + 2 * (n3 >> 2)
+def ex(g, k1, m):                    # element A'[k1; 2m + g]
+    return 296 * g + 18 * k1 + m
 
 
 def main():
     w = 1
-    for k1 in range(8):              # E1 write: lane l stores t = 2l (plane A) and t = 2l + 1 (plane B)
-        w = max(w, phases64([e1(k1, 2 * l) for l in range(32)]), phases64([e1(k1, 2 * l + 1) for l in range(32)]))
-    n3a = lambda j: (j & 1) + 4 * (j >> 1)
-    for n2 in range(8):              # E1 read: lane l' = 4 k1 + j reads (t, t + 2), t = 8 n2 + n3a(j)
-        addrs = [e1(l >> 2, 8 * n2 + n3a(l & 3)) for l in range(32)]
-        assert all(e1(l >> 2, 8 * n2 + n3a(l & 3) + 2) == addrs[l] + 1 for l in range(32))
-        w = max(w, phases128(addrs))
-    print("E1 worst ways:", w)
-    assert len({e1(k1, t) for k1 in range(8) for t in range(64)}) == 512
-    assert max(e1(k1, t) for k1 in range(8) for t in range(64)) < 644
+    for k1 in range(16):             # write: lane l = 2m + g stores its k1-th output
+        w = max(w, phases64([ex(l & 1, k1, l >> 1) for l in range(32)]))
+    print("exchange write worst ways:", w)
     w = 1
-    for k2 in range(8):              # E2 write: lane l' = 4 k1 + j stores n3a(j) (plane A) and n3a(j) + 2 (plane B)
-        w = max(w, phases64([e2(l >> 2, k2, n3a(l & 3)) for l in range(32)]), phases64([e2(l >> 2, k2, n3a(l & 3) + 2) for l in range(32)]))
-    for b in range(2):               # E2 read: lane l'' = k2 + 8 a reads pairs (n3, n3 + 1), n3 in {0, 4, 2, 6}, of k1 = 2a + b
-        for n3 in (0, 4, 2, 6):
-            addrs = [e2(2 * (l >> 3) + b, l & 7, n3) for l in range(32)]
-            assert all(e2(2 * (l >> 3) + b, l & 7, n3 + 1) == addrs[l] + 1 for l in range(32))
-            w = max(w, phases128(addrs))
-    print("E2 worst ways:", w)
-    assert len({e2(k1, k2, n3) for k1 in range(8) for k2 in range(8) for n3 in range(8)}) == 512
-    assert max(e2(k1, k2, n3) for k1 in range(8) for k2 in range(8) for n3 in range(8)) < 644
+    for mm in range(8):              # read: lane l' = 2 k1 + g loads (m, m + 1) = (2 mm, 2 mm + 1)
+        addrs = [ex(l & 1, l >> 1, 2 * mm) for l in range(32)]
+        assert all(ex(l & 1, l >> 1, 2 * mm + 1) == addrs[l] + 1 for l in range(32))
+        w = max(w, phases128(addrs))
+    print("exchange read worst ways:", w)
+    assert len({ex(g, k1, m) for g in range(2) for k1 in range(16) for m in range(16)}) == 512
+    assert max(ex(g, k1, m) for g in range(2) for k1 in range(16) for m in range(16)) < 584
+    # coarse 640-point transform of the acquire kernel: pass-1 output 10 j + q at slot 11 j + q (lanes j, j + 32)
+    w = 1
+    for q in range(10):
+        w = max(w, phases64([11 * l + q for l in range(32)]), phases64([11 * (l + 32) + q for l in range(32)]))
+    print("coarse pass-1 write worst ways:", w)
 
 
 if __name__ == "__main__":

@@ -18,12 +18,12 @@ static void wire(EmuHandle *h) {
     HostTables &T = h->T;
     h->P = T.p;
     Params &P = h->P;
-    P.tw_fft = T.tw_fft.data(); P.tw_p1 = T.tw_p1.data(); P.tw_p2 = T.tw_p2.data(); P.tw_p2w = T.tw_p2w.data();
+    P.tw_fft = T.tw_fft.data(); P.tw_p1 = T.tw_p1.data(); P.tw_p2 = T.tw_p2.data();
     P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
     P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
-    P.lane_desc = T.lane_desc.data(); P.acq_desc = T.acq_desc.data(); P.grid_conj = T.grid_conj.data();
+    P.lane_desc = T.lane_desc.data(); P.lane_aux = T.lane_aux.data(); P.acq_desc = T.acq_desc.data(); P.grid_lane = T.grid_lane.data();
 }
 
 // the one-warp-per-frame acquire kernel (rx512n.cuh)
