@@ -188,6 +188,17 @@ inline void build_f512_roles(HostTables &T) {
     p.n_combos = (int)c_seg.size();
     if (p.n_combos > 24) throw std::runtime_error("fft-512 map: more than 24 combinations");
     for (int q = 0; q < p.n_combos; q++) T.lane_aux[q].x = (unsigned)c_seg[q] | ((unsigned)(c_off[q] & 0xffff) << 16);
+    // routing bits of the lanes that hold a pilot or a straggler bin (a lane holds at most one of them)
+    for (int q = 0; q < 8; q++) {
+        unsigned &x = T.lane_aux[lane_of(pil[q])].x;
+        if (x & 0x300u) throw std::runtime_error("fft-512 map: a lane holds two special bins");
+        x |= 0x100u | ((unsigned)q << 4);
+    }
+    for (int q = 0; q < 7; q++) {
+        unsigned &x = T.lane_aux[lane_of(strag[q])].x;
+        if (x & 0x300u) throw std::runtime_error("fft-512 map: a lane holds two special bins");
+        x |= 0x200u | ((unsigned)q << 4);
+    }
     // acquire kernel: the first 128 data sub-carriers (segments 0..3) are mn[] of the even lanes (bins k1 + 16 i < 128) -- except bins
     // 128..131, whose phases are produced by the four phase slots that hold no data (bin 0 and the pilots 33, 66, 99).  Even lane:
     // slots mn[0..3]; odd lane: slots mn[4..7] of its even neighbour.

@@ -58,7 +58,8 @@ struct Params {
     // A COMBINATION is a set of data bins that share (array, g, i, segment): inside it the data index i' (minus 256 in the
     // negative half: the channel line's abscissa, Frame.hpp:425-430) is k1 + off.
     const uint4 *lane_desc;      // [32] per lane 8 x 16 bits for mn[0..7]: [15:7] data index in the symbol (256: no data), [6:2] combination
-    const uint2 *lane_aux;       // [32] .x: combination number `lane`: [2:0] segment, [31:16] off (signed); .y (lanes 0..6): the straggler
+    const uint2 *lane_aux;       // [32] .x: combination number `lane`: [2:0] segment, [31:16] off (signed); and the LANE's routing: [9:8] 1 = it holds
+                                 //      pilot [7:4] (in mn[], or in its used ot[] register), 2 = it holds straggler bin [7:4]; .y (lanes 0..6): the straggler
                                  //      data bin number `lane` (bins 128..131, 381..383, held in ot[]): descriptor as above | (its k1) << 16
     const uint2 *acq_desc;       // [32] acquire kernel: per lane 4 x 16 bits (even lane: mn[0..3]; odd lane: mn[4..7] of lane - 1): [7:0] index of
                                  //      the phase the slot produces (0..127), [15] take the product of straggler bin 128 + [9:8] instead

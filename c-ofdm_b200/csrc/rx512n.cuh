@@ -191,7 +191,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     if (!sync_less && lane < 5) fsw = __ldg(reinterpret_cast<const uint2 *>(fscal + frame) + lane);
     if (sync_less && lane == 2) fsw.x = 0x3f800000u;        // sync-less: kc = m0 = 0, th0 = theta = 0, rot_theta = 1, a = b = 0
     const int kc = (int)__shfl_sync(0xffffffffu, fsw.x, 0);
-    const uint2 aux = __ldg(&P.lane_aux[lane]);             // .x: combination `lane` (segment, offset); .y: straggler `lane`
+    const uint2 aux = __ldg(&P.lane_aux[lane]);             // .x: combination `lane` (segment, offset) + the lane's routing bits; .y: straggler `lane`
     if (tid >= nw && tid < kRxMaxSym) M->pabs[tid] = 0.f;   // unused entries (the others are written by their warps); ordered by the block barrier
     if (warp == 0) {
         // exp(-j b k1), k1 = 0..15
@@ -261,13 +261,15 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     float2 *scratch = reinterpret_cast<float2 *>(region);
     {
         float2 *pil = M->pil[warp];
-        const float2 osel = (lane & 1) ? ot[0] : ot[7];          // the only ot[] registers that hold used bins
-#define COFDM_X(p, bin) if (lane == f512_lane(bin)) pil[p] = f512_main(bin) ? mn[f512_i(bin)] : osel;
+        // Each of the 8 pilots and 7 straggler bins sits in ONE lane, in a register fixed by the geometry: the lane picks its
+        // value by selects (no branches) and its destination from the routing bits of lane_aux, then one store serves all 15.
+        float2 val = (lane & 1) ? ot[0] : ot[7];                 // the only ot[] registers that hold used bins (pilots 132, 380; stragglers)
+#define COFDM_X(p, bin) if (f512_main(bin)) val = lane == f512_lane(bin) ? mn[f512_i(bin)] : val;
         COFDM_F512_PILOTS(COFDM_X)
 #undef COFDM_X
-#define COFDM_X(q, bin) if (lane == f512_lane(bin)) scratch[q] = osel;
-        COFDM_F512_STRAG(COFDM_X)
-#undef COFDM_X
+        const unsigned route = aux.x >> 3;                       // [4:1] pilot / straggler number, [6:5] 0 none, 1 pilot, 2 straggler
+        float2 *dst = ((route >> 5) & 2u) ? scratch + ((route >> 1) & 15u) : pil + ((route >> 1) & 15u);
+        if ((route >> 5) & 3u) *dst = val;
         __syncwarp();
         float pm = 0.f;
         if (lane < 8) pm = sqrtf(cnorm2(pil[lane]));
