@@ -36,7 +36,7 @@ CONFIG = os.path.join(ROOT, "config", "config.txt")
 RX_BYTES_PER_FRAME = 46080 + 1024      # (N+CP)(NS+NPR)*8 read + ND*NS*mod/8 written, 16-QAM
 TX_BYTES_PER_FRAME = 1024 + 6016 * 8   # payload read + frame written
 MOD_NAME = {1: "BPSK", 2: "QPSK", 4: "16-QAM", 6: "64-QAM", 8: "256-QAM"}
-RX_DRAM_BYTES_PER_FRAME_NCU = 47359     # measured DRAM read+write of the rx pass (acquire + demod kernels), see roofline.traffic_source
+RX_DRAM_BYTES_PER_FRAME_NCU = 47495     # measured DRAM read+write of the rx pass (acquire + demod kernels), see roofline.traffic_source
 
 
 def n_cores():
@@ -288,10 +288,10 @@ def native_arm(args):
             "rx_frames_s": world * F / (rx_ms * 1e-3), "rx_ms": rx_ms, "tx_ms": tx_ms,
             "bit_errors": bit_err, "frames_with_errors": frames_bad, "frames_checked": frames_all,
             "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb,
-            "roofline": {"bound": "hbm", "kernel": "rx pass = rx_acquire512x2_kernel + rx_fused512_kernel<demod> (together they read every sample exactly once)", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "rx pass = rx_acquire512w_kernel + rx_demod512_kernel (together they read every sample exactly once)", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
                          "frac": rx_gbs / peak, "traffic": RX_DRAM_BYTES_PER_FRAME_NCU * F if s.mod_type == 4 else None, "peak_source": peak_src,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the two rx kernels over 32768 frames "
-                                           "(profiles/r01_final_ncu_summary.txt) = 47359 B/frame, scaled to this launch's frames",
+                                           "(profiles/r02_rx_warp_ncu_summary.txt) = 47495 B/frame, scaled to this launch's frames",
                          "algorithmic_bytes_per_frame": RX_BYTES_PER_FRAME, "tx_kernel_gbs": tx_gbs, "tx_frac": tx_gbs / peak},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_step": E, "ms_per_step": e_dt * 1e3, "payload_roundtrip_ok": e_ok, "host_sample_format": "ci16 (SDR wire format)",

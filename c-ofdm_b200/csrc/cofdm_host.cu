@@ -59,10 +59,10 @@ struct cofdm {
     cudaStream_t pipe_stream[kPipe] = {};
     DevBuf pipe_in[kPipe], pipe_out[kPipe];
     DevBuf scratch_a, scratch_b, scratch_c;
-    DevBuf gen_frames, gen_spec, gen_pre;        // generic path intermediates
-    DevBuf fscal;                                // per-frame scalars handed from the acquire to the demod kernel
-    int rx_split = 1;                            // 1: acquire + demod kernels, 0: single fused kernel
-    int rx_warp = 1;                             // 1: one-warp-per-symbol demod kernel (rx512n.cuh), 0: two-warp-team kernel (env COFDM_RX_WARP)
+    // intermediates between the kernels of one rx pass, ONE SET PER PIPELINE SLOT: the COFDM_HOST pipeline runs consecutive
+    // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
+    DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
+    DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
     int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
                                                  // 2 reaches the PCIe full-duplex ceiling, 3 and more lose 10-15 %
@@ -104,100 +104,57 @@ size_t sample_bytes(int fmt) { return fmt == COFDM_CI16 ? 4 : 8; }
 
 // ---- device-side launches (all pointers are device pointers, stream given) ----------------------
 int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps);
+                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot);
 int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt);
 int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0) {
+              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0, int slot = 0) {
     if (n_frames == 0) return COFDM_OK;
     if (!h->T.fused512_ok) {
-        if (h->T.generic_ok && !sync_less) return launch_rx_generic(h, st, samples, fmt, n_frames, stride, bytes, amb, taps);
+        if (h->T.generic_ok && !sync_less) return launch_rx_generic(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot);
         return fail(COFDM_ERR_UNSUPPORTED, "rx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
     }
-    const int nsym = h->P.n_sym_rx;
     if ((uintptr_t)bytes & 3) return fail(COFDM_ERR_ARG, "rx: the output byte buffer must be 4-byte aligned");
-    const bool small = nsym <= 9;
+    const Params &P = h->P;
     const bool want = taps.scal || taps.grid || taps.chan || taps.constell || taps.synced;
-    const bool tma = fmt == COFDM_CF32 && ((uintptr_t)samples & 15) == 0 && (stride * 8) % 16 == 0;
-    // records that are not 16-byte aligned (a frame cut out of a capture at an arbitrary sample) use plain loads;
-    // aligned int16 records are bulk-copied as raw wire data and widened when read (split path only)
-    const bool tma16 = fmt == COFDM_CI16 && ((uintptr_t)samples & 15) == 0 && (stride * 4) % 16 == 0;
-    const bool split = h->rx_split && small;
+    // records that are 16-byte aligned are staged by TMA bulk copies (cf32, or raw int16 wire data widened when read);
+    // a frame cut out of a capture at an arbitrary sample is staged by the warp with plain loads
+    const size_t sb = sample_bytes(fmt);
+    const bool al = ((uintptr_t)samples & 15) == 0 && (stride * sb) % 16 == 0;
+    // the acquire kernel's hand-over (40 bytes per frame), in the buffer of this pipeline slot
     FrameScal *fsc = nullptr;
-    if (split) {
-        CU_TRY(h->fscal.reserve(n_frames * sizeof(FrameScal)));
-        fsc = (FrameScal *)h->fscal.p;
+    if (!sync_less) {
+        CU_TRY(h->fscal[slot].reserve(n_frames * sizeof(FrameScal)));
+        fsc = (FrameScal *)h->fscal[slot].p;
     }
-#define COFDM_RX_LAUNCH(F, T, S, W, MD) \
-    rx_fused512_kernel<F, T, S, W, MD><<<(unsigned)n_frames, rx512_threads(nsym, MD), rx512_smem_bytes(nsym, MD), st>>>( \
-        h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
-#define COFDM_RX_PICK(F, T, MD)                                                                \
-    do {                                                                                       \
-        if (small) { if (want) COFDM_RX_LAUNCH(F, T, 9, true, MD); else COFDM_RX_LAUNCH(F, T, 9, false, MD); } \
-        else { if (want) COFDM_RX_LAUNCH(F, T, kRxMaxSym, true, 0); else COFDM_RX_LAUNCH(F, T, kRxMaxSym, false, 0); } \
-    } while (0)
-#define COFDM_RX_MODE(MD)                                   \
-    do {                                                    \
-        if (fmt == COFDM_CI16) COFDM_RX_PICK(kCI16, false, MD); \
-        else if (tma) COFDM_RX_PICK(kCF32, true, MD);       \
-        else COFDM_RX_PICK(kCF32, false, MD);               \
-    } while (0)
-    if (split) {
-        // acquire: preamble -> 48 bytes of scalars per frame; two frames per CTA unless every synchronisation stage is off
-        if (!sync_less && h->rx_warp) {
-            // one warp per frame (rx512n.cuh)
-            const bool al = fmt == COFDM_CI16 ? tma16 : tma;
-            const unsigned g4 = (unsigned)((n_frames + kAcqwWarps - 1) / kAcqwWarps);
+    // ---- acquire: the preamble -> 40 bytes of scalars per frame, one warp per frame.  The sync-less form (FRAME_FORM::read)
+    //      has no synchronisation stage at all; its preamble is only looked at for the chan_char tap ----
+    if (!sync_less || taps.chan != nullptr) {
+        const unsigned g4 = (unsigned)((n_frames + kAcqwWarps - 1) / kAcqwWarps);
 #define COFDM_ACQW(F, T) \
-            do { if (want) rx_acquire512w_kernel<F, T, true><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc, 0); \
-                 else rx_acquire512w_kernel<F, T, false><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc, 0); } while (0)
-            if (fmt == COFDM_CI16) { if (al) COFDM_ACQW(kCI16, true); else COFDM_ACQW(kCI16, false); }
-            else { if (al) COFDM_ACQW(kCF32, true); else COFDM_ACQW(kCF32, false); }
+        do { if (want) rx_acquire512w_kernel<F, T, true><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc, sync_less); \
+             else rx_acquire512w_kernel<F, T, false><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc, sync_less); } while (0)
+        if (fmt == COFDM_CI16) { if (al) COFDM_ACQW(kCI16, true); else COFDM_ACQW(kCI16, false); }
+        else { if (al) COFDM_ACQW(kCF32, true); else COFDM_ACQW(kCF32, false); }
 #undef COFDM_ACQW
-        } else if (!sync_less) {
-            const unsigned g2 = (unsigned)((n_frames + 1) / 2);
-#define COFDM_ACQ(F, T) \
-            do { if (want) rx_acquire512x2_kernel<F, T, true><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); \
-                 else rx_acquire512x2_kernel<F, T, false><<<g2, kAcqThreads, rx512_acquire_smem_bytes(), st>>>(h->P, samples, (long long)stride, (int)n_frames, taps, fsc); } while (0)
-            if (fmt == COFDM_CI16) { if (tma16) COFDM_ACQ(kCI16, true); else COFDM_ACQ(kCI16, false); }
-            else if (tma) COFDM_ACQ(kCF32, true);
-            else COFDM_ACQ(kCF32, false);
-#undef COFDM_ACQ
-        } else {
-            COFDM_RX_MODE(1);
-        }
-        if (int rc = check_launch(h, "rx512_acquire")) return rc;
-        // demod: message symbols -> payload bytes
-        if (h->rx_warp && !sync_less) {
-            const bool al = fmt == COFDM_CI16 ? tma16 : tma;
-            const size_t sm = rx_demod512_smem_bytes(h->P.num_symb);
-            const unsigned thr = 32u * (unsigned)h->P.num_symb;
-#define COFDM_DM(F, T, W, MW, MD) rx_demod512_kernel<F, T, W, MW, MD><<<(unsigned)n_frames, thr, sm, st>>>(h->P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
-            // production instances are specialised on the modulation order (QPSK, 16-QAM); everything else reads it from the configuration
-#define COFDM_DM_PICK(F, T) do { if (h->P.num_symb <= 8) { if (want) COFDM_DM(F, T, true, 8, 0); else if (h->P.mod_type == 4) COFDM_DM(F, T, false, 8, 4); \
-                                                           else if (h->P.mod_type == 2) COFDM_DM(F, T, false, 8, 2); else COFDM_DM(F, T, false, 8, 0); } \
-                                 else { if (want) COFDM_DM(F, T, true, kMaxFusedSymb, 0); else COFDM_DM(F, T, false, kMaxFusedSymb, 0); } } while (0)
-            if (fmt == COFDM_CI16) { if (al) COFDM_DM_PICK(kCI16, true); else COFDM_DM_PICK(kCI16, false); }
-            else { if (al) COFDM_DM_PICK(kCF32, true); else COFDM_DM_PICK(kCF32, false); }
+        if (int rc = check_launch(h, "rx_acquire512w")) return rc;
+    }
+    // ---- demod: the message symbols -> payload bytes, one warp per symbol ----
+    {
+        const size_t sm = rx_demod512_smem_bytes(P.num_symb);
+        const unsigned thr = 32u * (unsigned)P.num_symb;
+#define COFDM_DM(F, T, W, MW, MD) rx_demod512_kernel<F, T, W, MW, MD><<<(unsigned)n_frames, thr, sm, st>>>(P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
+        // production instances are specialised on the modulation order (QPSK, 16-QAM); everything else reads it from the configuration
+#define COFDM_DM_PICK(F, T) do { if (P.num_symb <= 8) { if (want) COFDM_DM(F, T, true, 8, 0); else if (P.mod_type == 4) COFDM_DM(F, T, false, 8, 4); \
+                                                       else if (P.mod_type == 2) COFDM_DM(F, T, false, 8, 2); else COFDM_DM(F, T, false, 8, 0); } \
+                             else { if (want) COFDM_DM(F, T, true, kMaxFusedSymb, 0); else COFDM_DM(F, T, false, kMaxFusedSymb, 0); } } while (0)
+        if (fmt == COFDM_CI16) { if (al) COFDM_DM_PICK(kCI16, true); else COFDM_DM_PICK(kCI16, false); }
+        else { if (al) COFDM_DM_PICK(kCF32, true); else COFDM_DM_PICK(kCF32, false); }
 #undef COFDM_DM_PICK
 #undef COFDM_DM
-            if (int rc = check_launch(h, "rx_demod512")) return rc;
-            if (taps.synced != nullptr && taps.scal != nullptr) {
-                rx_synced_fixup2_kernel<<<(unsigned)n_frames, 128, 0, st>>>(h->P, (int)n_frames, taps, 0);
-                return check_launch(h, "rx_synced_fixup2");
-            }
-            return COFDM_OK;
-        }
-        if (tma16) { if (want) COFDM_RX_LAUNCH(kCI16, true, 9, true, 2); else COFDM_RX_LAUNCH(kCI16, true, 9, false, 2); }   // split implies <= 9 symbols
-        else COFDM_RX_MODE(2);
-    } else {
-        COFDM_RX_MODE(0);
+        if (int rc = check_launch(h, "rx_demod512")) return rc;
     }
-#undef COFDM_RX_MODE
-#undef COFDM_RX_PICK
-#undef COFDM_RX_LAUNCH
-    if (int rc = check_launch(h, "rx_fused512")) return rc;
     if (taps.synced != nullptr && taps.scal != nullptr && !sync_less) {
-        rx_synced_fixup_kernel<<<(unsigned)n_frames, 128, 0, st>>>(h->P, (int)n_frames, taps);
+        rx_synced_fixup_kernel<<<(unsigned)n_frames, 128, 0, st>>>(P, (int)n_frames, taps);
         return check_launch(h, "rx_synced_fixup");
     }
     return COFDM_OK;
@@ -205,15 +162,15 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 
 // the any-size path (generic.cuh): five kernels per sub-batch with the spectra in HBM between them
 int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps) {
+                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot) {
     const Params &P = h->P;
     const size_t sub = 512, N = (size_t)P.fft_size, L = (size_t)P.ofdm_len, nsym = (size_t)P.n_sym_rx;
     const size_t nb = std::min(sub, n_frames);
-    CU_TRY(h->gen_frames.reserve(nb * sizeof(GenFrame)));
-    CU_TRY(h->gen_spec.reserve(nb * nsym * N * sizeof(float2)));
-    CU_TRY(h->gen_pre.reserve(nb * L * sizeof(float2)));
-    GenFrame *gf = (GenFrame *)h->gen_frames.p;
-    float2 *spec = (float2 *)h->gen_spec.p, *pre = (float2 *)h->gen_pre.p;
+    CU_TRY(h->gen_frames[slot].reserve(nb * sizeof(GenFrame)));
+    CU_TRY(h->gen_spec[slot].reserve(nb * nsym * N * sizeof(float2)));
+    CU_TRY(h->gen_pre[slot].reserve(nb * L * sizeof(float2)));
+    GenFrame *gf = (GenFrame *)h->gen_frames[slot].p;
+    float2 *spec = (float2 *)h->gen_spec[slot].p, *pre = (float2 *)h->gen_pre[slot].p;
     const size_t sm_c = 2 * (size_t)P.pf_size * sizeof(float2), sm_s = (L + N) * sizeof(float2), sm_h = (size_t)P.num_data_subc / 2 * sizeof(float) + 16;
     const size_t sb = sample_bytes(fmt);
     for (size_t f0 = 0; f0 < n_frames; f0 += sub) {
@@ -331,7 +288,7 @@ void cofdm_destroy(cofdm_t *h) {
         if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
     }
     h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release();
-    h->gen_frames.release(); h->gen_spec.release(); h->gen_pre.release(); h->fscal.release();
+    for (int i = 0; i < kPipe; i++) { h->gen_frames[i].release(); h->gen_spec[i].release(); h->gen_pre[i].release(); h->fscal[i].release(); }
     if (h->amb_dev) cudaFree(h->amb_dev);
     if (h->pos_dev) cudaFree(h->pos_dev);
     if (h->ev0) cudaEventDestroy(h->ev0);
@@ -390,10 +347,6 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         const int smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
         cudaError_t a = cudaSuccess, b = cudaSuccess;
         {
-            const char *e = std::getenv("COFDM_RX_SPLIT");
-            if (e) h->rx_split = std::atoi(e) != 0;
-            const char *rw = std::getenv("COFDM_RX_WARP");
-            if (rw) h->rx_warp = std::atoi(rw) != 0;
             const char *tb = std::getenv("COFDM_TX_BULK");
             if (tb) h->tx_bulk = std::atoi(tb) != 0;
             const char *c = std::getenv("COFDM_PIPE_CHUNK");
@@ -401,19 +354,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             const char *d = std::getenv("COFDM_PIPE_DEPTH");
             if (d && std::atoi(d) > 0) h->pipe_depth = std::min(std::atoi(d), kPipe);
         }
-        // maximum shared-memory carve-out: occupancy of every mode is bounded by shared memory, not by L1
-#define COFDM_RX_ATTR(F, T, S, W, MD) \
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<F, T, S, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rx512_smem_bytes(P.n_sym_rx, MD)); \
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_fused512_kernel<F, T, S, W, MD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-#define COFDM_RX_ATTR_ALL(F, T) \
-        COFDM_RX_ATTR(F, T, 9, true, 0); COFDM_RX_ATTR(F, T, 9, false, 0); COFDM_RX_ATTR(F, T, kRxMaxSym, true, 0); COFDM_RX_ATTR(F, T, kRxMaxSym, false, 0); \
-        COFDM_RX_ATTR(F, T, 9, true, 1); COFDM_RX_ATTR(F, T, 9, false, 1); COFDM_RX_ATTR(F, T, 9, true, 2); COFDM_RX_ATTR(F, T, 9, false, 2)
-        COFDM_RX_ATTR_ALL(kCF32, true);
-        COFDM_RX_ATTR_ALL(kCF32, false);
-        COFDM_RX_ATTR_ALL(kCI16, false);
-        COFDM_RX_ATTR(kCI16, true, 9, true, 2); COFDM_RX_ATTR(kCI16, true, 9, false, 2);
-#undef COFDM_RX_ATTR_ALL
-#undef COFDM_RX_ATTR
+        // maximum shared-memory carve-out: occupancy of both rx kernels is bounded by shared memory and registers, not by L1
         {
             const int smd = (int)rx_demod512_smem_bytes(P.num_symb);
 #define COFDM_DM_ATTR(F, T, W, MW, MD) \
@@ -431,12 +372,6 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         COFDM_ACQW_ATTR(kCF32, true, true); COFDM_ACQW_ATTR(kCF32, true, false); COFDM_ACQW_ATTR(kCF32, false, true); COFDM_ACQW_ATTR(kCF32, false, false);
         COFDM_ACQW_ATTR(kCI16, true, true); COFDM_ACQW_ATTR(kCI16, true, false); COFDM_ACQW_ATTR(kCI16, false, true); COFDM_ACQW_ATTR(kCI16, false, false);
 #undef COFDM_ACQW_ATTR
-#define COFDM_ACQ_ATTR(F, T, W) \
-        if (a == cudaSuccess) a = cudaFuncSetAttribute(rx_acquire512x2_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-        COFDM_ACQ_ATTR(kCF32, true, true); COFDM_ACQ_ATTR(kCF32, true, false); COFDM_ACQ_ATTR(kCF32, false, true);
-        COFDM_ACQ_ATTR(kCF32, false, false); COFDM_ACQ_ATTR(kCI16, false, true); COFDM_ACQ_ATTR(kCI16, false, false);
-        COFDM_ACQ_ATTR(kCI16, true, true); COFDM_ACQ_ATTR(kCI16, true, false);
-#undef COFDM_ACQ_ATTR
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         if (c == cudaSuccess) c = cudaFuncSetAttribute(tx512_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
@@ -589,17 +524,24 @@ int cofdm_tx_batch(cofdm_t *h, const uint8_t *payload, size_t n_frames, void *fr
     const size_t bpf = (size_t)h->P.bytes_per_frame, fb = (size_t)h->P.frame_len * sample_bytes(fmt);
     const size_t chunk = std::min<size_t>(n_frames, h->pipe_chunk);
     for (int i = 0; i < h->pipe_depth; i++) { CU_TRY(h->pipe_in[i].reserve(chunk * bpf)); CU_TRY(h->pipe_out[i].reserve(chunk * fb)); }
-    size_t c = 0;
-    for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
-        const size_t n = std::min(chunk, n_frames - f0);
-        const int s = (int)(c % h->pipe_depth);
-        cudaStream_t st = h->pipe_stream[s];
-        CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, payload + f0 * bpf, n * bpf, cudaMemcpyHostToDevice, st));
-        if (int rc = launch_tx(h, st, (const uint8_t *)h->pipe_in[s].p, n, h->pipe_out[s].p, fmt)) return rc;
-        CU_TRY(cudaMemcpyAsync((char *)frames + f0 * fb, h->pipe_out[s].p, n * fb, cudaMemcpyDeviceToHost, st));
+    auto run_chunks = [&]() -> int {
+        size_t c = 0;
+        for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
+            const size_t n = std::min(chunk, n_frames - f0);
+            const int s = (int)(c % h->pipe_depth);
+            cudaStream_t st = h->pipe_stream[s];
+            CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, payload + f0 * bpf, n * bpf, cudaMemcpyHostToDevice, st));
+            if (int rc = launch_tx(h, st, (const uint8_t *)h->pipe_in[s].p, n, h->pipe_out[s].p, fmt)) return rc;
+            CU_TRY(cudaMemcpyAsync((char *)frames + f0 * fb, h->pipe_out[s].p, n * fb, cudaMemcpyDeviceToHost, st));
+        }
+        return COFDM_OK;
+    };
+    const int rc_chunks = run_chunks();       // on failure the queued copies are drained before returning (they touch the caller's buffers)
+    for (int i = 0; i < kPipe; i++) {
+        const cudaError_t e = cudaStreamSynchronize(h->pipe_stream[i]);
+        if (e != cudaSuccess && rc_chunks == COFDM_OK) return fail(COFDM_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     }
-    for (int i = 0; i < kPipe; i++) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));
-    return COFDM_OK;
+    return rc_chunks;
 }
 
 static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_frames, size_t frame_stride,
@@ -669,18 +611,28 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
         t.scal = (float *)b; t.grid = (float2 *)(b + off_grid); t.chan = (float2 *)(b + off_ch);
         t.constell = (float2 *)(b + off_con); t.synced = (float2 *)(b + off_syn);
     }
-    size_t c = 0;
-    for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
-        const size_t n = std::min(chunk, n_frames - f0);
-        const int s = (int)(c % h->pipe_depth);
-        cudaStream_t st = h->pipe_stream[s];
-        // the last record only needs rx_len samples (the caller's buffer may end there)
-        const size_t in_bytes = ((n - 1) * frame_stride + (size_t)P.rx_len) * sb;
-        CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, (const char *)samples + f0 * frame_stride * sb, in_bytes, cudaMemcpyHostToDevice, st));
-        if (int rc = launch_rx(h, st, h->pipe_in[s].p, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t, sync_less)) return rc;
-        CU_TRY(cudaMemcpyAsync(bytes + f0 * bpf, h->pipe_out[s].p, n * bpf, cudaMemcpyDeviceToHost, st));
+    // (on any failure the copies already queued on the other pipe streams are drained before returning: they touch the
+    //  caller's buffers and the handle's staging buffers)
+    auto run_chunks = [&]() -> int {
+        size_t c = 0;
+        for (size_t f0 = 0; f0 < n_frames; f0 += chunk, c++) {
+            const size_t n = std::min(chunk, n_frames - f0);
+            const int s = (int)(c % h->pipe_depth);
+            cudaStream_t st = h->pipe_stream[s];
+            // the last record only needs rx_len samples (the caller's buffer may end there)
+            const size_t in_bytes = ((n - 1) * frame_stride + (size_t)P.rx_len) * sb;
+            CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, (const char *)samples + f0 * frame_stride * sb, in_bytes, cudaMemcpyHostToDevice, st));
+            if (int rc = launch_rx(h, st, h->pipe_in[s].p, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t, sync_less, s)) return rc;
+            CU_TRY(cudaMemcpyAsync(bytes + f0 * bpf, h->pipe_out[s].p, n * bpf, cudaMemcpyDeviceToHost, st));
+        }
+        return COFDM_OK;
+    };
+    const int rc_chunks = run_chunks();
+    for (int i = 0; i < kPipe; i++) {
+        const cudaError_t e = cudaStreamSynchronize(h->pipe_stream[i]);
+        if (e != cudaSuccess && rc_chunks == COFDM_OK) return fail(COFDM_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     }
-    for (int i = 0; i < kPipe; i++) CU_TRY(cudaStreamSynchronize(h->pipe_stream[i]));
+    if (rc_chunks) return rc_chunks;
     if (want_taps) {
         char *b = (char *)h->scratch_c.p;
         if (taps->scal) CU_TRY(cudaMemcpy(taps->scal, b, n_frames * n_sc * sizeof(float), cudaMemcpyDeviceToHost));

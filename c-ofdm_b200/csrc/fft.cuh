@@ -274,6 +274,7 @@ COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2
 // each of which maps the 32 lanes of a 64-bit access onto the 16 bank pairs exactly twice.
 // ------------------------------------------------------------------------------------------------
 constexpr int kFft512Slots = 640;
+constexpr int kPairSlots = 2 * kFft512Slots;   // float2 slots of one symbol pair (re plane + im plane)
 COFDM_DEV int spec_slot(int k) { return k ^ (((k >> 3) & 7) << 1); }
 
 // ------------------------------------------------------------------------------------------------

@@ -28,8 +28,8 @@ struct GenFrame {
     float theta;            // pr_phase_sinh angle (radians)
     float2 rot_theta;       // exp(-j theta)
     double a, b;            // chan_char_lq line
-    float phit[32];         // the reference's wrapped CP angle per symbol, in turns
-    double psi[32];         // constant phase carried into symbol s, in turns
+    float phit[kGenMaxSym];         // the reference's wrapped CP angle per symbol, in turns
+    double psi[kGenMaxSym];         // constant phase carried into symbol s, in turns
 };
 
 template <bool INV>

@@ -1,6 +1,6 @@
 // kernels.cuh -- the sm_100a kernels of the C-OFDM hot path.
 //
-//   rx_fused512_kernel   aligned frame -> payload bytes in ONE pass over the samples:
+//   rx_acquire512w_kernel + rx_demod512_kernel (rx512n.cuh)   aligned frame -> payload bytes, every sample read once:
 //                        coarse CFO (pilot_freq_sinh), fine CFO (cp_freq_sinh), preamble phase lock
 //                        (pr_phase_sinh), 9 FFT-512, pilot normalisation + segment correction
 //                        (FFT_FORM::read), linear-phase channel fit (chan_char_lq), equalise, hard demap.
@@ -17,8 +17,6 @@
 #include "params.h"
 #include "fft.cuh"
 #include "modem.cuh"
-#include "rx512.cuh"
-#include "rx512_acquire.cuh"
 #include "rx512n.cuh"
 #include "generic.cuh"
 

@@ -7,6 +7,7 @@
 namespace cofdmk {
 
 constexpr int kMaxPilots = 128;
+constexpr int kGenMaxSym = 32;      // frame symbols (preamble + message) the any-size path keeps per-symbol scalars for (GenFrame)
 constexpr int kMaxFusedSymb = 15;   // message symbols per frame the fused 512 kernels accept (one warp each)
 
 struct Params {

@@ -27,9 +27,34 @@
 #include "params.h"
 #include "fft512w.cuh"
 #include "modem.cuh"
-#include "rx512.cuh"     // FrameScal, sym_turns
 
 namespace cofdmk {
+
+constexpr int kRxMaxSym = 16;        // frame symbols (preamble + message) the kernels are dimensioned for
+
+// what the acquire kernel hands to the demod kernel, per frame (five 8-byte words)
+struct FrameScal {
+    int kc, m0;             // coarse shift numerator (shift = kc / pf_den); whole-bin shift of the preamble
+    float th0, theta;       // Arg of the preamble's CP correlation (turns); pr_phase_sinh angle (radians, taps only)
+    float2 rot_theta;       // exp(-j theta)
+    double a, b;            // chan_char_lq line
+};
+
+// Constant phase (turns, mod 1) carried into symbol s by freq_shift's global sample index (Frame.hpp:341-347)
+// and by cp_freq_sinh's accumulated `shift` (Frame.hpp:248,261):
+//     Psi_s = shift*640*s + (640/512) * sum_{t<s} phi_t,   phi_t = theta_t - 512*shift + m_t  (turns)
+//           = (640/512) * sum_{t<s} (theta_t + m_t)
+// -- the coarse shift cancels exactly; the integer part is reduced mod 1 in integers.
+COFDM_DEV float sym_turns(const float *theta_t, const int *mshift, int s) {
+    float acc = 0.f;
+    int msum = 0;
+    for (int t = 0; t < s; t++) {
+        acc += theta_t[t] * (640.0f / 512.0f);
+        acc -= rintf(acc);                       // stay within half a turn: keeps the float spacing at ~3e-8 turns
+        msum += mshift[t];
+    }
+    return acc + (float)((5 * msum) & 3) * 0.25f;
+}
 
 // The fft-512 / 256 data / 8 pilot sub-carrier map (Frame.cpp:31-44) is fixed by the geometry; build_tables() checks
 // these lists against the tables it derives from the config.
@@ -245,7 +270,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     float2 rp[5];
     const float2 pl = rotate_body(v, theta, m, reinterpret_cast<float2 *>(region + kDemodTabOff), lane, rp);
     if (TAPS && taps.synced != nullptr) {
-        // debug tap, completed by rx_synced_fixup2_kernel (per-symbol constant phase and theta)
+        // debug tap, completed by rx_synced_fixup_kernel (per-symbol constant phase and theta)
         float2 *d = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) d[128 + lane + 32 * n1] = nmul(v[n1], pl);
@@ -525,7 +550,7 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
 #pragma unroll
     for (int c = 0; c < 4; c++) ycp[c] = nmul(nmulc(raw[c], rp[4 - c]), pl);
     if (TAPS && taps.synced != nullptr) {
-        // debug tap, completed by rx_synced_fixup2_kernel (theta; the preamble has no other constant phase)
+        // debug tap, completed by rx_synced_fixup_kernel (theta; the preamble has no other constant phase)
         float2 *d = taps.synced + (size_t)frame * P.rx_len;
 #pragma unroll
         for (int n1 = 0; n1 < 16; n1++) d[128 + lane + 32 * n1] = nmul(v[n1], pl);
@@ -704,8 +729,7 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
 // Completes the `synced` debug tap of rx_demod512_kernel / rx_acquire512w_kernel: they store every sample with the symbol's
 // full rotation exp(-j 2 pi beta_s j / 512); apply the per-symbol constant phase Psi_s and theta so that the tap equals
 // the reference's buffer after freq_shift + cp_freq_sinh + pr_phase_sinh.
-// Symbols below `first_full` (the preamble while the paired acquire kernel serves it) carry the fractional-bin part only.
-__global__ void rx_synced_fixup2_kernel(const Params P, int n_frames, const RxTaps taps, int first_full) {
+__global__ void rx_synced_fixup_kernel(const Params P, int n_frames, const RxTaps taps) {
     const int frame = blockIdx.x;
     if (frame >= n_frames || taps.synced == nullptr || taps.scal == nullptr) return;
     const float *sc = taps.scal + (size_t)frame * 48;
@@ -716,12 +740,9 @@ __global__ void rx_synced_fixup2_kernel(const Params P, int n_frames, const RxTa
     for (int t = 0; t < nsym; t++) mi[t] = (int)sc[16 + t];
     for (int s = 0; s < nsym; s++) {
         const float psi = sym_turns(sc + 32, mi, s);
-        const double ms = s < first_full ? (double)mi[s] : 0.0;
+        const float2 r = cmul(cis_neg_turns((double)psi), make_float2(c_th, s_th));
         float2 *x = taps.synced + (size_t)frame * P.rx_len + (size_t)s * 640;
-        for (int j = threadIdx.x; j < 640; j += blockDim.x) {
-            const float2 r = cmul(cis_neg_turns((double)psi + ms * (double)j / 512.0), make_float2(c_th, s_th));
-            x[j] = cmul(x[j], r);
-        }
+        for (int j = threadIdx.x; j < 640; j += blockDim.x) x[j] = cmul(x[j], r);
     }
 }
 

@@ -41,10 +41,10 @@ static void emu_acquire512w(const Params &P, const void *samples, int fmt, int u
 // the one-warp-per-symbol demod kernel (rx512n.cuh), production instantiations
 template <bool TAPS>
 static void emu_demod512(const Params &P, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
-                         uint8_t *out, unsigned long long *amb, const RxTaps &taps, const FrameScal *fs) {
+                         uint8_t *out, unsigned long long *amb, const RxTaps &taps, const FrameScal *fs, int sync_less) {
     const dim3 grid(n_frames), block(32 * P.num_symb);
     const size_t sm = rx_demod512_smem_bytes(P.num_symb);
-#define EMU_DM(F, T, MW, MD) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW, MD>(P, samples, stride, n_frames, out, amb, taps, 0, fs); })
+#define EMU_DM(F, T, MW, MD) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW, MD>(P, samples, stride, n_frames, out, amb, taps, sync_less, fs); })
     // as launch_rx does: production instances specialised on QPSK / 16-QAM, everything else generic
 #define EMU_DM_PICK(F, T) do { if (P.num_symb <= 8) { if (!TAPS && P.mod_type == 4) EMU_DM(F, T, 8, TAPS ? 0 : 4); else if (!TAPS && P.mod_type == 2) EMU_DM(F, T, 8, TAPS ? 0 : 2); else EMU_DM(F, T, 8, 0); } \
                                else EMU_DM(F, T, kMaxFusedSymb, 0); } while (0)
@@ -52,6 +52,19 @@ static void emu_demod512(const Params &P, const void *samples, int fmt, int use_
     else { if (use_tma) EMU_DM_PICK(kCF32, true); else EMU_DM_PICK(kCF32, false); }
 #undef EMU_DM_PICK
 #undef EMU_DM
+}
+
+// the receive chain as launch_rx (cofdm_host.cu) runs it: acquire (one warp per frame) + demod (one warp per symbol)
+template <bool TAPS>
+static int emu_rx_chain(EmuHandle *h, const void *samples, int fmt, int use_tma, int n_frames, long long stride, int sync_less,
+                        uint8_t *out, unsigned long long *amb, const RxTaps &taps) {
+    if (!h->T.fused512_ok) return -1;
+    const Params P = h->P;
+    std::vector<FrameScal> fs(n_frames);
+    if (!sync_less || taps.chan != nullptr) emu_acquire512w<TAPS>(P, samples, fmt, use_tma, n_frames, stride, taps, fs.data(), sync_less);
+    emu_demod512<TAPS>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data(), sync_less);
+    if (taps.synced && taps.scal && !sync_less) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup_kernel(P, n_frames, taps); });
+    return 0;
 }
 
 extern "C" {
@@ -66,8 +79,6 @@ void *emu_create(const char *config_path) {
 void emu_destroy(void *h) { delete (EmuHandle *)h; }
 int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
-static int g_emu_split = 0;
-void emu_set_split(int on) { g_emu_split = on; }
 static int g_emu_pc_plain = 0;
 void emu_set_pc_plain(int on) { g_emu_pc_plain = on; }
 static int g_emu_tx_bulk = 1;
@@ -76,50 +87,8 @@ void emu_set_tx_bulk(int on) { g_emu_tx_bulk = on; }
 int emu_rx_fused512_mode(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride, int sync_less,
                     uint8_t *out, unsigned long long *amb, float *scal, float2 *grid, float2 *chan,
                     float2 *constell, float2 *synced) {
-    auto *h = (EmuHandle *)hv;
-    if (!h->T.fused512_ok) return -1;
-    const Params P = h->P;
     RxTaps taps{scal, grid, chan, constell, synced};
-    const int nsym = P.n_sym_rx;
-    std::vector<FrameScal> fs(n_frames);
-    auto run = [&](int md, auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym, md)), rx512_smem_bytes(nsym, md), kern); };
-#define EMU_RX(F, T, MD) run(MD, [&] { rx_fused512_kernel<F, T, 9, true, MD>(P, samples, stride, n_frames, out, amb, taps, sync_less, fs.data()); })
-#define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
-    auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
-    if (g_emu_split == 3 && !sync_less) {             // product: one warp per frame (acquire) + one warp per symbol (demod)
-        emu_acquire512w<true>(P, samples, fmt, use_tma, n_frames, stride, taps, fs.data(), 0);
-        emu_demod512<true>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
-        if (synced && scal) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup2_kernel(P, n_frames, taps, 0); });
-        return 0;
-    }
-    if (g_emu_split && nsym <= 9 && !sync_less) {     // production split: paired acquire + demod
-        if (fmt == kCI16 && use_tma) {                // raw int16 bulk copies, widened when read
-            acq2([&] { rx_acquire512x2_kernel<kCI16, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
-            if (g_emu_split == 2) emu_demod512<true>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
-            else EMU_RX(kCI16, true, 2);
-        } else {
-            if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
-            else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, true>(P, samples, stride, n_frames, taps, fs.data()); });
-            else acq2([&] { rx_acquire512x2_kernel<kCF32, false, true>(P, samples, stride, n_frames, taps, fs.data()); });
-            if (g_emu_split == 2) emu_demod512<true>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
-            else EMU_RX_MODE(2);
-        }
-        if (g_emu_split == 2) {
-            if (synced && scal) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup2_kernel(P, n_frames, taps, 1); });
-            return 0;
-        }
-    }
-    else if (g_emu_split && nsym <= 9) { EMU_RX_MODE(1); EMU_RX_MODE(2); }
-    else if (nsym <= 9) EMU_RX_MODE(0);
-    else {
-        if (fmt == kCI16) run(0, [&] { rx_fused512_kernel<kCI16, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
-        else if (use_tma) run(0, [&] { rx_fused512_kernel<kCF32, true, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
-        else run(0, [&] { rx_fused512_kernel<kCF32, false, kRxMaxSym, true>(P, samples, stride, n_frames, out, amb, taps, sync_less); });
-    }
-#undef EMU_RX_MODE
-#undef EMU_RX
-    if (synced && scal && !sync_less) emu::launch(dim3(n_frames), dim3(128), 0, [&] { rx_synced_fixup_kernel(P, n_frames, taps); });
-    return 0;
+    return emu_rx_chain<true>((EmuHandle *)hv, samples, fmt, use_tma, n_frames, stride, sync_less, out, amb, taps);
 }
 
 int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
@@ -128,38 +97,11 @@ int emu_rx_fused512(void *hv, const void *samples, int fmt, int use_tma, int n_f
     return emu_rx_fused512_mode(hv, samples, fmt, use_tma, n_frames, stride, 0, out, amb, scal, grid, chan, constell, synced);
 }
 
-// the production instantiation (no taps, pruned last FFT pass)
+// the production instantiation (no taps; specialised on the modulation order where launch_rx does so)
 int emu_rx_fused512_notaps(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride,
                            uint8_t *out, unsigned long long *amb) {
-    auto *h = (EmuHandle *)hv;
-    if (!h->T.fused512_ok) return -1;
-    const Params P = h->P;
     RxTaps taps{};
-    const int nsym = P.n_sym_rx;
-    std::vector<FrameScal> fs(n_frames);
-    auto run = [&](int md, auto kern) { emu::launch(dim3(n_frames), dim3(rx512_threads(nsym, md)), rx512_smem_bytes(nsym, md), kern); };
-#define EMU_RX(F, T, MD) run(MD, [&] { rx_fused512_kernel<F, T, 9, false, MD>(P, samples, stride, n_frames, out, amb, taps, 0, fs.data()); })
-#define EMU_RX_MODE(MD) do { if (fmt == kCI16) EMU_RX(kCI16, false, MD); else if (use_tma) EMU_RX(kCF32, true, MD); else EMU_RX(kCF32, false, MD); } while (0)
-    if (g_emu_split == 3) {
-        emu_acquire512w<false>(P, samples, fmt, use_tma, n_frames, stride, taps, fs.data(), 0);
-        emu_demod512<false>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
-    } else if (g_emu_split) {
-        auto acq2 = [&](auto kern) { emu::launch(dim3((n_frames + 1) / 2), dim3(kAcqThreads), rx512_acquire_smem_bytes(), kern); };
-        if (fmt == kCI16 && use_tma) {
-            acq2([&] { rx_acquire512x2_kernel<kCI16, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
-            if (g_emu_split == 2) emu_demod512<false>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
-            else EMU_RX(kCI16, true, 2);
-        } else {
-            if (fmt == kCI16) acq2([&] { rx_acquire512x2_kernel<kCI16, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
-            else if (use_tma) acq2([&] { rx_acquire512x2_kernel<kCF32, true, false>(P, samples, stride, n_frames, taps, fs.data()); });
-            else acq2([&] { rx_acquire512x2_kernel<kCF32, false, false>(P, samples, stride, n_frames, taps, fs.data()); });
-            if (g_emu_split == 2) emu_demod512<false>(P, samples, fmt, use_tma, n_frames, stride, out, amb, taps, fs.data());
-            else EMU_RX_MODE(2);
-        }
-    } else EMU_RX_MODE(0);
-#undef EMU_RX_MODE
-#undef EMU_RX
-    return 0;
+    return emu_rx_chain<false>((EmuHandle *)hv, samples, fmt, use_tma, n_frames, stride, 0, out, amb, taps);
 }
 
 int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int fmt) {

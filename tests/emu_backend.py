@@ -49,14 +49,9 @@ class EmuModem:
             setattr(s, n, getattr(o, n))
         s.rx_len = o.preamble_size + o.message_size
         self.use_tma = 1
-        L.emu_set_split.argtypes = [C.c_int]
         L.emu_stream_scan.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]
         self.fused = bool(L.emu_fused_ok(self.h))
         s.fused_path = 1 if self.fused else 0
-
-    def set_split(self, on):
-        """1: acquire + demod kernels (the product default), 0: the single fused kernel"""
-        self.lib.emu_set_split(int(on))
 
     def set_pc_plain(self, on):
         """1: the one-lag-per-slot preamble search kernel (fallback for odd sizes), 0: the 4-lags-per-thread one"""

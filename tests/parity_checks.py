@@ -89,14 +89,37 @@ def check_tx(m, o, n_frames=3, seed=1):
         ref, q = o.tx(pay[i])
         worst = max(worst, rel_l2(f32[i], ref))
         d = i16[i].reshape(-1).astype(np.int32) - q.astype(np.int32)
-        # int16 = trunc(x*mult): an fp32 sample may sit on the other side of an integer than the fp64 one
+        # int16 = trunc(x*mult): an fp32 sample may sit on the other side of an integer than the fp64 one -- but only where the
+        # fp64 value lies closer to that integer than the fp32 error of this very frame (measured on its cf32 form, x2 margin)
         assert np.abs(d).max() <= 1
         frac = np.abs(np.stack([ref.real, ref.imag], -1).reshape(-1) * s.mult)
-        near = np.abs(frac - np.rint(frac)) < 2e-3
+        err = np.abs(f32[i].astype(np.complex128) - ref)
+        window = 2.0 * s.mult * float(max(err.real.max(), err.imag.max(), np.abs(err).max()))
+        assert window < 1e-3, window
+        near = np.abs(frac - np.rint(frac)) < window
         assert not np.any((d != 0) & ~near), "int16 frame differs away from a truncation boundary"
         flips += int(np.count_nonzero(d))
     assert worst < TOL, worst
     return dict(rel_l2=worst, int16_boundary_flips=flips)
+
+
+def coarse_cfo_near_tie(rec_c, s, rel_gap=1e-5):
+    """pilot_freq_sinh (Frame.hpp:285-337) restated in numpy fp64 on one received preamble: True when, in at least one of
+    the arg-max windows, the runner-up |X| lies within `rel_gap` of the maximum -- the only situation in which an fp32
+    spectrum may legitimately pick another bin than the reference's fp64 one"""
+    size = s.preamble_size
+    x = np.fft.fftshift(np.abs(np.fft.fft(np.asarray(rec_c[:size], dtype=np.complex128))))
+    rel_bw = (s.num_data_subc + s.num_pilot_subc) / s.fft_size
+    rel_pw = rel_bw / s.num_pilot_subc
+    w = int(size * rel_pw)
+    b0 = int((1.0 - rel_bw - rel_pw) / 2.0 * size)
+    for win in range(s.num_pilot_subc + 1):
+        if win == s.num_pilot_subc // 2:
+            continue
+        seg = np.sort(x[max(0, b0 + win * w): b0 + (win + 1) * w])
+        if seg[-1] > 0 and (seg[-1] - seg[-2]) <= rel_gap * seg[-1]:
+            return True
+    return False
 
 
 def impaired_records(o, n_frames, seed, cfo_max=0.003, noise=1.5, taps=(1.0, 0.2 - 0.1j, 0.05j), early=2):
@@ -126,9 +149,13 @@ def check_rx_against_oracle(m, o, rec_i16, fmt="i16", want=None):
     for i in range(len(rec_c)):
         r = want[i] if want is not None else o.rx_aligned(rec_c[i])
         if taps["scal"][i, 0] != np.float32(r["scal"][0]):
-            # coarse-CFO arg-max landed on a neighbouring bin (near-tie between two fp32 magnitudes):
-            # boundary-ambiguous frame, counted, later stages are then not comparable sample by sample
+            # The coarse-CFO arg-max landed on another bin.  Legitimate ONLY for a near-tie between two magnitudes of the
+            # reference's own fp64 spectrum; anything else is a bug and fails here.  Such a frame is counted; its later
+            # stages follow another (equally valid) estimate, so they are not comparable sample by sample -- the decoded
+            # bytes still are (the fine CFO stage absorbs one step of the coarse grid), up to boundary-ambiguous symbols.
+            assert coarse_cfo_near_tie(rec_c[i], s), f"frame {i}: coarse CFO {taps['scal'][i, 0]} != {r['scal'][0]} without a near-tie"
             stats["shift_mismatch"] += 1
+            stats["differing"] += assert_bytes_match(out[i], r["bytes"], r["constell"], s.mod_type, f"rx frame {i} (coarse near-tie)")
             continue
         for k in ("synced", "grid", "chan", "constell"):
             if k not in taps:

@@ -7,12 +7,9 @@ import parity_checks as pc
 from emu_backend import EmuModem
 
 
-@pytest.fixture(scope="module", params=[1, 0], ids=["split", "fused"])
-def emu(cfg_dir, port, request):
-    """every test runs on both forms of the receive chain: acquire + demod kernels (product default) and the
-    single fused kernel"""
+@pytest.fixture(scope="module")
+def emu(cfg_dir, port):
     ms = {mt: EmuModem(cfg_dir[mt], port[mt].sizes) for mt in (1, 2, 4, 6, 8)}
-    ms[4].set_split(request.param)
     yield ms
     for m in ms.values():
         m.close()
@@ -180,3 +177,19 @@ def test_stream_scan_kernel_matches_reference_loop(cfg_dir, oracle_lib):
     dummy = [np.zeros((len(l), s.usefull_size), np.uint8) for l in lists]
     pos, _, unmerged = st.merge_shards([(l, d, b0, b1) for l, d, (_, _, b0, b1) in zip(lists, dummy, shards)], s)
     assert unmerged == 0 and pos.tolist() == want_pos.tolist()
+
+
+@pytest.mark.parametrize("ns", [3, 12])
+def test_rx_other_symbol_counts(oracle_lib, tmp_path, ns):
+    """the demod kernel runs one warp per message symbol: fewer than 8 (part of the shared arrays unused) and more than
+    8 (the 15-warp instance) against the oracle, every tap; then the production instance without taps"""
+    cfg = pc.synth.write_config(str(tmp_path / f"config_ns{ns}.txt"), num_symb=ns)
+    o = oracle_lib.Oracle("port", cfg)
+    m = EmuModem(cfg, o.sizes)
+    assert m.fused
+    pay, rec = pc.impaired_records(o, 2, seed=40 + ns)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["differing"] == 0
+    out, _ = m.rx_aligned_batch(pc.cplx(rec).astype(np.complex64))
+    assert np.array_equal(out, np.stack([o.rx_aligned(pc.cplx(r))["bytes"] for r in rec]))
+    m.close()

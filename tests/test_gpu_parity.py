@@ -70,6 +70,57 @@ def test_rx_fused_against_oracle(modems, port, mt, fmt):
     assert max(st["synced"], st["grid"], st["constell"]) < 5e-6      # north-star bound is 1e-5
 
 
+@pytest.mark.parametrize("ns", [1, 3, 12, 15])
+def test_rx_other_symbol_counts(oracle_lib, tmp_path, ns):
+    """one warp per message symbol: 1..15 symbols per frame (the 8-warp and the 15-warp instances), every tap against
+    the oracle, then the production instance without taps"""
+    cfg = pc.synth.write_config(str(tmp_path / f"config_ns{ns}.txt"), num_symb=ns)
+    o = oracle_lib.Oracle("port", cfg)
+    m = cb.Modem(cfg, device=0)
+    assert m.sizes.fused_path == 1
+    pay, rec = pc.impaired_records(o, 6, seed=40 + ns)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    # (check_rx_against_oracle has already asserted that any differing symbol is one the ORACLE places within AMBIG_MARGIN of a
+    #  decision boundary; with up to 15 x 256 points per frame behind a 3-tap channel one such point per run does occur)
+    assert st["shift_mismatch"] == 0 and st["differing"] <= 1
+    out, _ = m.rx_aligned_batch(pc.cplx(rec).astype(np.complex64))
+    for i, r in enumerate(rec):
+        ref = o.rx_aligned(pc.cplx(r))
+        pc.assert_bytes_match(out[i], ref["bytes"], ref["constell"], m.sizes.mod_type, f"ns={ns} frame {i} (no taps)")
+    m.close()
+
+
+def test_configs_beyond_both_paths_are_refused(tmp_path):
+    """40 message symbols: beyond the fft-512 kernels (15) and beyond the any-size path's per-symbol scalars (32 frame
+    symbols): the library must refuse, not overrun (advisor finding, round 1)"""
+    cfg = pc.synth.write_config(str(tmp_path / "config_ns40.txt"), num_symb=40)
+    m = cb.Modem(cfg, device=0)
+    s = m.sizes
+    assert s.fused_path == -1
+    with pytest.raises(cb.CofdmError):
+        m.rx_aligned_batch(np.zeros((1, s.rx_len, 2), np.int16))
+    with pytest.raises(cb.CofdmError):
+        m.tx_batch(np.zeros((1, s.usefull_size), np.uint8))
+    m.close()
+
+
+def test_host_pipeline_many_small_chunks(cfg_dir, port, monkeypatch):
+    """COFDM_HOST calls run chunk c on pipeline slot c mod depth, each slot with its own staging buffers AND its own
+    inter-kernel scratch (the acquire kernel's hand-over): 37 frames in chunks of 8 over two slots, bytes equal to the
+    one-chunk device call (advisor finding, round 1: a shared hand-over buffer could be overwritten by the next chunk)"""
+    monkeypatch.setenv("COFDM_PIPE_CHUNK", "8")
+    m = cb.Modem(cfg_dir[4], device=0)
+    o = port[4]
+    pay, rec = pc.impaired_records(o, 37, seed=77)
+    want = np.stack([o.rx_aligned(pc.cplx(r))["bytes"] for r in rec])
+    for _ in range(3):
+        out, _ = m.rx_aligned_batch(rec)
+        assert np.array_equal(out, want)
+    fr = m.tx_batch(pay, cb.CI16)
+    assert np.array_equal(fr, np.stack([o.tx(p)[1] for p in pay]).reshape(fr.shape)) or np.abs(fr.astype(np.int32) - np.stack([o.tx(p)[1] for p in pay]).reshape(fr.shape)).max() <= 1
+    m.close()
+
+
 def test_rx_fused_golden_vectors_of_compiled_reference(modems, port, golden_vectors):
     g = golden_vectors
     for mt in (1, 2, 4, 6, 8):
