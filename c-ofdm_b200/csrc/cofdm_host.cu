@@ -63,6 +63,7 @@ struct cofdm {
     // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
     DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
+    int tx_warp = 1;                             // tx: one warp per symbol (tx512w.cuh); env COFDM_TX_WARP=0: the two-warp-team kernel
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
     int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
                                                  // 2 reaches the PCIe full-duplex ceiling, 3 and more lose 10-15 %
@@ -219,11 +220,22 @@ int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames
         if (h->T.generic_ok) return launch_tx_generic(h, st, payload, n_frames, frames, fmt);
         return fail(COFDM_ERR_UNSUPPORTED, "tx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
     }
-    const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
-    const dim3 grid((unsigned)n_frames), block(tx512_threads(h->P.num_symb));
     // frames leave the SM as TMA bulk stores when the buffer is 16-byte aligned (frame and symbol sizes are multiples of 16 bytes)
     const bool bulk = h->tx_bulk && ((uintptr_t)frames & 15) == 0 && ((size_t)h->P.frame_len * sample_bytes(fmt)) % 16 == 0 &&
                       ((size_t)(h->P.t2sin_size + h->P.pf_size) * sample_bytes(fmt)) % 16 == 0;
+    if (h->tx_warp) {
+        // one warp per symbol (tx512w.cuh)
+        const size_t smw = tx512w_smem_bytes(h->P.num_symb);
+        const unsigned thr = (unsigned)tx512w_threads(h->P.num_symb);
+#define COFDM_TXW(F, B) do { if (h->P.num_symb <= 8) tx512w_kernel<F, B, 8><<<(unsigned)n_frames, thr, smw, st>>>(h->P, payload, (int)n_frames, frames); \
+                             else tx512w_kernel<F, B, kMaxFusedSymb><<<(unsigned)n_frames, thr, smw, st>>>(h->P, payload, (int)n_frames, frames); } while (0)
+        if (fmt == COFDM_CI16) { if (bulk) COFDM_TXW(kCI16, true); else COFDM_TXW(kCI16, false); }
+        else { if (bulk) COFDM_TXW(kCF32, true); else COFDM_TXW(kCF32, false); }
+#undef COFDM_TXW
+        return check_launch(h, "tx512w");
+    }
+    const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
+    const dim3 grid((unsigned)n_frames), block(tx512_threads(h->P.num_symb));
     if (bulk) {
         if (fmt == COFDM_CI16) tx512_kernel<kCI16, true><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
         else tx512_kernel<kCF32, true><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
@@ -331,7 +343,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
     rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
     rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.lane_aux, &P.lane_aux); rc |= upload(h, T.acq_desc, &P.acq_desc);
-    rc |= upload(h, T.grid_lane, &P.grid_lane);
+    rc |= upload(h, T.grid_lane, &P.grid_lane); rc |= upload(h, T.tx_desc, &P.tx_desc);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
     if (rc) return bail(COFDM_ERR_CUDA);
     P.constell = h->constell_dev[P.mod_type];
@@ -349,6 +361,8 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         {
             const char *tb = std::getenv("COFDM_TX_BULK");
             if (tb) h->tx_bulk = std::atoi(tb) != 0;
+            const char *tw = std::getenv("COFDM_TX_WARP");
+            if (tw) h->tx_warp = std::atoi(tw) != 0;
             const char *c = std::getenv("COFDM_PIPE_CHUNK");
             if (c && std::atoll(c) > 0) h->pipe_chunk = (size_t)std::atoll(c);
             const char *d = std::getenv("COFDM_PIPE_DEPTH");
@@ -372,6 +386,16 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         COFDM_ACQW_ATTR(kCF32, true, true); COFDM_ACQW_ATTR(kCF32, true, false); COFDM_ACQW_ATTR(kCF32, false, true); COFDM_ACQW_ATTR(kCF32, false, false);
         COFDM_ACQW_ATTR(kCI16, true, true); COFDM_ACQW_ATTR(kCI16, true, false); COFDM_ACQW_ATTR(kCI16, false, true); COFDM_ACQW_ATTR(kCI16, false, false);
 #undef COFDM_ACQW_ATTR
+        {
+            const int smw = (int)tx512w_smem_bytes(P.num_symb);
+#define COFDM_TXW_ATTR(F, B, MW) \
+            if (a == cudaSuccess) a = cudaFuncSetAttribute(tx512w_kernel<F, B, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smw); \
+            if (a == cudaSuccess) a = cudaFuncSetAttribute(tx512w_kernel<F, B, MW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+            COFDM_TXW_ATTR(kCF32, true, 8); COFDM_TXW_ATTR(kCF32, false, 8); COFDM_TXW_ATTR(kCI16, true, 8); COFDM_TXW_ATTR(kCI16, false, 8);
+            COFDM_TXW_ATTR(kCF32, true, kMaxFusedSymb); COFDM_TXW_ATTR(kCF32, false, kMaxFusedSymb);
+            COFDM_TXW_ATTR(kCI16, true, kMaxFusedSymb); COFDM_TXW_ATTR(kCI16, false, kMaxFusedSymb);
+#undef COFDM_TXW_ATTR
+        }
         cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
         if (c == cudaSuccess) c = cudaFuncSetAttribute(tx512_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);

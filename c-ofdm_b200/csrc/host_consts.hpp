@@ -100,6 +100,7 @@ struct HostTables {
     std::vector<uint4> lane_desc;     // rx512n.cuh: per lane, the roles of its registers after warp_fft512
     std::vector<uint2> lane_aux;      //             combinations and straggler bins
     std::vector<uint2> acq_desc;      //             acquire kernel: which phase each slot produces
+    std::vector<uint4> tx_desc;       // tx512w.cuh: per lane, what sits at the bins lane + 32 n1
     std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N), by bin
     std::vector<float2> grid_lane;    //             the same in lane order
     bool fused512_ok = false;         // the specialised kernels apply to this config
@@ -220,6 +221,19 @@ inline void build_f512_roles(HostTables &T) {
             u[u4 >> 1] |= d << (16 * (u4 & 1));
         }
         if (idle != 4) throw std::runtime_error("fft-512 map differs from the acquire kernel's straggler bins");
+    }
+    // transmit side: lane l feeds bins l + 32 n1 to the transform; rows n1 = 5..10 (bins 160..351) must be unused
+    T.tx_desc.assign(64, make_uint4(0x40004000u, 0x40004000u, 0x40004000u, 0x40004000u));
+    for (int k = 0; k < 512; k++) {
+        const int m = T.bin_map[k], lane = k & 31, n1 = k >> 5;
+        if (n1 >= 5 && n1 <= 10) {
+            if (m != -1) throw std::runtime_error("fft-512 map: a used bin in rows 5..10 of the transmit grid");
+            continue;
+        }
+        const int sl = n1 < 5 ? n1 : n1 - 6;
+        const unsigned d = m >= 0 ? (unsigned)m : (m == -2 ? 0x8000u : 0x4000u);
+        unsigned *u = &T.tx_desc[2 * lane].x;                  // 8 consecutive words per lane
+        u[sl >> 1] = (u[sl >> 1] & ~(0xffffu << (16 * (sl & 1)))) | (d << (16 * (sl & 1)));
     }
     // conj(tx grid) / sqrt(N) in lane order: mn[0..7], the used ot[] register, padding
     T.grid_lane.assign(32 * 10, make_float2(0.f, 0.f));

@@ -570,3 +570,5 @@ __global__ void i16_to_cf32_kernel(const unsigned *__restrict__ in, float2 *__re
 }
 
 }  // namespace cofdmk
+
+#include "tx512w.cuh"   // uses store_sample_pair

@@ -64,6 +64,8 @@ struct Params {
                                  //      data bin number `lane` (bins 128..131, 381..383, held in ot[]): descriptor as above | (its k1) << 16
     const uint2 *acq_desc;       // [32] acquire kernel: per lane 4 x 16 bits (even lane: mn[0..3]; odd lane: mn[4..7] of lane - 1): [7:0] index of
                                  //      the phase the slot produces (0..127), [15] take the product of straggler bin 128 + [9:8] instead
+    const uint4 *tx_desc;        // [32][2] tx512w.cuh: per lane 10 x 16 bits, the grid rows n1 = 0..4, 11..15 of bins lane + 32 n1: data index (0..255),
+                                 //      0x4000 = null, 0x8000 = pilot (rows 5..10 are never used by the sub-carrier map)
     const float2 *grid_lane;     // [32][10] conj(tx grid of the preamble) / sqrt(fft_size) at the bins of mn[0..7] and of the used ot[] register
     int n_combos;
 };

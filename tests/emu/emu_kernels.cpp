@@ -23,7 +23,7 @@ static void wire(EmuHandle *h) {
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
     P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
-    P.lane_desc = T.lane_desc.data(); P.lane_aux = T.lane_aux.data(); P.acq_desc = T.acq_desc.data(); P.grid_lane = T.grid_lane.data();
+    P.lane_desc = T.lane_desc.data(); P.lane_aux = T.lane_aux.data(); P.acq_desc = T.acq_desc.data(); P.grid_lane = T.grid_lane.data(); P.tx_desc = T.tx_desc.data();
 }
 
 // the one-warp-per-frame acquire kernel (rx512n.cuh)
@@ -81,6 +81,8 @@ int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
 static int g_emu_pc_plain = 0;
 void emu_set_pc_plain(int on) { g_emu_pc_plain = on; }
+static int g_emu_tx_warp = 1;
+void emu_set_tx_warp(int on) { g_emu_tx_warp = on; }
 static int g_emu_tx_bulk = 1;
 void emu_set_tx_bulk(int on) { g_emu_tx_bulk = on; }
 
@@ -108,6 +110,17 @@ int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int 
     auto *h = (EmuHandle *)hv;
     if (!h->T.fused512_ok) return -1;
     const Params P = h->P;
+    if (g_emu_tx_warp) {
+        // the product default: one warp per symbol (tx512w.cuh); g_emu_tx_bulk picks the bulk-store or the plain-store output stage
+        const size_t smw = tx512w_smem_bytes(P.num_symb);
+        const dim3 blk(tx512w_threads(P.num_symb));
+#define EMU_TXW(F, B) do { if (P.num_symb <= 8) emu::launch(dim3(n_frames), blk, smw, [&] { tx512w_kernel<F, B, 8>(P, payload, n_frames, frames); }); \
+                           else emu::launch(dim3(n_frames), blk, smw, [&] { tx512w_kernel<F, B, kMaxFusedSymb>(P, payload, n_frames, frames); }); } while (0)
+        if (fmt == kCI16) { if (g_emu_tx_bulk) EMU_TXW(kCI16, true); else EMU_TXW(kCI16, false); }
+        else { if (g_emu_tx_bulk) EMU_TXW(kCF32, true); else EMU_TXW(kCF32, false); }
+#undef EMU_TXW
+        return 0;
+    }
     const size_t sm = tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
     // both output stages: register stores (tx_bulk = 0) and the TMA bulk store of linear images (the product default)
     if (g_emu_tx_bulk) {
