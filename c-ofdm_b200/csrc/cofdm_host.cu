@@ -63,7 +63,7 @@ struct cofdm {
     // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
     DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
-    int tx_warp = 1;                             // tx: one warp per symbol (tx512w.cuh); env COFDM_TX_WARP=0: the two-warp-team kernel
+    int tx_ctas = 148 * 4;                       // CTAs of the persistent tx kernel (SMs x resident CTAs per SM, measured at create)
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
     int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
                                                  // 2 reaches the PCIe full-duplex ceiling, 3 and more lose 10-15 %
@@ -223,27 +223,19 @@ int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames
     // frames leave the SM as TMA bulk stores when the buffer is 16-byte aligned (frame and symbol sizes are multiples of 16 bytes)
     const bool bulk = h->tx_bulk && ((uintptr_t)frames & 15) == 0 && ((size_t)h->P.frame_len * sample_bytes(fmt)) % 16 == 0 &&
                       ((size_t)(h->P.t2sin_size + h->P.pf_size) * sample_bytes(fmt)) % 16 == 0;
-    if (h->tx_warp) {
+    {
         // one warp per symbol (tx512w.cuh)
-        const size_t smw = tx512w_smem_bytes(h->P.num_symb);
+        // persistent CTAs: as many as fit on the device at once, each walks over frames
+        const size_t smw = tx512w_smem_bytes(h->P.num_symb, h->P.t2sin_size + h->P.pf_size);
         const unsigned thr = (unsigned)tx512w_threads(h->P.num_symb);
-#define COFDM_TXW(F, B) do { if (h->P.num_symb <= 8) tx512w_kernel<F, B, 8><<<(unsigned)n_frames, thr, smw, st>>>(h->P, payload, (int)n_frames, frames); \
-                             else tx512w_kernel<F, B, kMaxFusedSymb><<<(unsigned)n_frames, thr, smw, st>>>(h->P, payload, (int)n_frames, frames); } while (0)
+        const unsigned grd = (unsigned)std::min<size_t>(n_frames, (size_t)h->tx_ctas);
+#define COFDM_TXW(F, B) do { if (h->P.num_symb <= 8) tx512w_kernel<F, B, 8><<<grd, thr, smw, st>>>(h->P, payload, (int)n_frames, frames); \
+                             else tx512w_kernel<F, B, kMaxFusedSymb><<<grd, thr, smw, st>>>(h->P, payload, (int)n_frames, frames); } while (0)
         if (fmt == COFDM_CI16) { if (bulk) COFDM_TXW(kCI16, true); else COFDM_TXW(kCI16, false); }
         else { if (bulk) COFDM_TXW(kCF32, true); else COFDM_TXW(kCF32, false); }
 #undef COFDM_TXW
         return check_launch(h, "tx512w");
     }
-    const size_t sm = tx512_smem_bytes(h->P.num_symb, h->P.bytes_per_frame);
-    const dim3 grid((unsigned)n_frames), block(tx512_threads(h->P.num_symb));
-    if (bulk) {
-        if (fmt == COFDM_CI16) tx512_kernel<kCI16, true><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
-        else tx512_kernel<kCF32, true><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
-    } else {
-        if (fmt == COFDM_CI16) tx512_kernel<kCI16><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
-        else tx512_kernel<kCF32><<<grid, block, sm, st>>>(h->P, payload, (int)n_frames, frames);
-    }
-    return check_launch(h, "tx512");
 }
 
 int launch_t2(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t start, size_t n_blocks, float *rel) {
@@ -337,7 +329,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     h->P = T.p;
     Params &P = h->P;
     int rc = 0;
-    rc |= upload(h, T.tw_fft, &P.tw_fft);   rc |= upload(h, T.tw_p1, &P.tw_p1);   rc |= upload(h, T.tw_p2, &P.tw_p2);
+    rc |= upload(h, T.tw_fft, &P.tw_fft);
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
@@ -356,13 +348,10 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     if (T.fused512_ok) {
-        const int smt = (int)tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
         cudaError_t a = cudaSuccess, b = cudaSuccess;
         {
             const char *tb = std::getenv("COFDM_TX_BULK");
             if (tb) h->tx_bulk = std::atoi(tb) != 0;
-            const char *tw = std::getenv("COFDM_TX_WARP");
-            if (tw) h->tx_warp = std::atoi(tw) != 0;
             const char *c = std::getenv("COFDM_PIPE_CHUNK");
             if (c && std::atoll(c) > 0) h->pipe_chunk = (size_t)std::atoll(c);
             const char *d = std::getenv("COFDM_PIPE_DEPTH");
@@ -387,7 +376,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         COFDM_ACQW_ATTR(kCI16, true, true); COFDM_ACQW_ATTR(kCI16, true, false); COFDM_ACQW_ATTR(kCI16, false, true); COFDM_ACQW_ATTR(kCI16, false, false);
 #undef COFDM_ACQW_ATTR
         {
-            const int smw = (int)tx512w_smem_bytes(P.num_symb);
+            const int smw = (int)tx512w_smem_bytes(P.num_symb, P.t2sin_size + P.pf_size);
 #define COFDM_TXW_ATTR(F, B, MW) \
             if (a == cudaSuccess) a = cudaFuncSetAttribute(tx512w_kernel<F, B, MW>, cudaFuncAttributeMaxDynamicSharedMemorySize, smw); \
             if (a == cudaSuccess) a = cudaFuncSetAttribute(tx512w_kernel<F, B, MW>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
@@ -395,13 +384,17 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             COFDM_TXW_ATTR(kCF32, true, kMaxFusedSymb); COFDM_TXW_ATTR(kCF32, false, kMaxFusedSymb);
             COFDM_TXW_ATTR(kCI16, true, kMaxFusedSymb); COFDM_TXW_ATTR(kCI16, false, kMaxFusedSymb);
 #undef COFDM_TXW_ATTR
+            int per_sm = 0;
+            if (a == cudaSuccess) {
+                if (P.num_symb <= 8) a = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tx512w_kernel<kCF32, true, 8>, tx512w_threads(P.num_symb), smw);
+                else a = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tx512w_kernel<kCF32, true, kMaxFusedSymb>, tx512w_threads(P.num_symb), smw);
+            }
+            const char *tc = std::getenv("COFDM_TX_CTAS_PER_SM");
+            if (tc && std::atoi(tc) > 0) per_sm = std::atoi(tc);
+            h->tx_ctas = prop.multiProcessorCount * std::max(per_sm, 1);
         }
-        cudaError_t c = cudaFuncSetAttribute(tx512_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
-        cudaError_t d = cudaFuncSetAttribute(tx512_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
-        if (c == cudaSuccess) c = cudaFuncSetAttribute(tx512_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
-        if (d == cudaSuccess) d = cudaFuncSetAttribute(tx512_kernel<kCI16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smt);
-        if (a != cudaSuccess || b != cudaSuccess || c != cudaSuccess || d != cudaSuccess)
-            return bail(fail(COFDM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(a != cudaSuccess ? a : (b != cudaSuccess ? b : (c != cudaSuccess ? c : d)))));
+        if (a != cudaSuccess || b != cudaSuccess)
+            return bail(fail(COFDM_ERR_CUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(a != cudaSuccess ? a : b)));
     }
     if (!T.fused512_ok && T.generic_ok) {
         const int sm_c = (int)(2 * (size_t)P.pf_size * sizeof(float2)), sm_s = (int)((size_t)(P.ofdm_len + P.fft_size) * sizeof(float2));

@@ -238,6 +238,8 @@ COFDM_DEV void mbar_wait(uint64_t *, uint32_t) {}
 COFDM_DEV void tma_store_fence() {}
 COFDM_DEV void tma_store_1d(void *dst, const void *src, uint32_t bytes) { memcpy(dst, src, bytes); }
 COFDM_DEV void tma_store_commit_and_wait_read() {}
+COFDM_DEV void tma_store_commit() {}
+COFDM_DEV void tma_store_wait_read() {}
 #else
 COFDM_DEV uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 COFDM_DEV void mbar_init(uint64_t *bar, int count) {
@@ -276,6 +278,8 @@ COFDM_DEV void tma_store_commit_and_wait_read() {
     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
     asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
+COFDM_DEV void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+COFDM_DEV void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 #endif
 
 }  // namespace cofdmk

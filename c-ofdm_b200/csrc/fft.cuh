@@ -1,12 +1,9 @@
 // fft.cuh -- hand-written FFT building blocks (no cuFFT).
 //
 //  * dft2/4/5/8/16: in-register butterflies, forward (W = e^{-j2pi/R}) or inverse (conjugate).
-//  * team_fft512p<INV>: a team of two warps computes TWO 512-point FFTs at once (packed f32x2, one in each half
-//    of every register pair) as radix 8x8x8.  Each lane owns one radix-8 butterfly per pass; the two exchanges
-//    go through two 640-slot float2 planes in shared memory with layouts chosen so that every 64-bit access
-//    of a warp is bank-conflict free (see the address maps below); the two warps meet at a named barrier.
-//  * stockham_pass<R>: generic mixed-radix autosort pass over a thread group, used for the
-//    640-point (10x8x8) coarse-CFO spectrum, the 256-point sync-tone detector and the generic path.
+//  * stockham_pass<R>: generic mixed-radix autosort pass over a thread group, used for the 256-point sync-tone
+//    detector and the any-size path.
+//  (the fft-512 kernels use the one-warp radix 16 x 16 x 2 transform of fft512w.cuh)
 //
 // These replace the reference's FFTW plans F1-F5 (OFDM/Frame.cpp:16-24,108-112,147-150;
 // OFDM/Frame.hpp:289-295).  All transforms are unnormalised like FFTW's.
@@ -253,134 +250,6 @@ COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2
 #pragma unroll
         for (int q = 0; q < R; q++) { out_re[pad_slot<PADSH>(o + q * ns)] = v[q].re; out_im[pad_slot<PADSH>(o + q * ns)] = v[q].im; }
     }
-}
-
-// ------------------------------------------------------------------------------------------------
-// FFT-512 as radix 8x8x8 over a team of two warps
-//
-// Index algebra: n = 64*n1 + 8*n2 + n3, k = k1 + 8*k2 + 64*k3 (all digits 0..7)
-//   pass 1  A [k1;n2,n3] = sum_n1 x[n]          W8^{n1 k1}   then * W512^{(8 n2+n3) k1}
-//   pass 2  B [k1,k2;n3] = sum_n2 A'[k1;n2,n3]  W8^{n2 k2}   then * W64^{n3 k2}
-//   pass 3  X [k]        = sum_n3 B'[k1,k2;n3]  W8^{n3 k3}
-// Lane l, half h in {0,1}:  q = l & 7,  p = (l >> 3) + 4h.
-//   pass 1 butterfly (n2=p, n3=q)  i.e. t = 8p+q = l + 32h, inputs at t + 64*n1
-//   pass 2 butterfly (k1=p, n3=q)
-//   pass 3 butterfly (k1=p, k2=q)  -> outputs k = p + 8q + 64*k3
-// Exchange layouts (float2 slots inside the warp's 640-slot region):
-//   E1(k1,n2,n3) = n3 + 8*n2 + 72*k1      writer: fixed k1 -> q + 8p   reader: fixed n2 -> q + 72p
-//   E2(k1,k2,n3) = n3 + 9*k2 + 72*k1      writer: fixed k2 -> q + 72p  reader: fixed n3 -> 9q + 72p
-//   spectrum slot(k) = k ^ (((k >> 3) & 7) << 1)   writer: fixed k3 -> (p + 8q) ^ 2q (+64 k3); readers of 16 consecutive,
-//                                                  16-aligned bins (64- or 128-bit accesses) are conflict-free as well
-// each of which maps the 32 lanes of a 64-bit access onto the 16 bank pairs exactly twice.
-// ------------------------------------------------------------------------------------------------
-constexpr int kFft512Slots = 640;
-constexpr int kPairSlots = 2 * kFft512Slots;   // float2 slots of one symbol pair (re plane + im plane)
-COFDM_DEV int spec_slot(int k) { return k ^ (((k >> 3) & 7) << 1); }
-
-// ------------------------------------------------------------------------------------------------
-// team_fft512p: two packed transforms at once; the 64 butterflies of a pass are spread over a TEAM of two warps
-// (warp h owns butterflies 32h..32h+31, one per lane), which halves the registers and the dependent
-// chain per warp.  The exchanges are shared by the team, so each is fenced by the team's named barrier.
-// ------------------------------------------------------------------------------------------------
-template <bool INV>
-COFDM_DEV void team_fft512p_head(pc (&v)[8], const float2 *tw_p1, int t /* = lane + 32h */) {
-    dft8<INV>(v);
-#pragma unroll
-    for (int k1 = 1; k1 < 8; k1++) v[k1] = cmul(v[k1], twid<INV>(__ldg(&tw_p1[k1 * 64 + t])));
-}
-
-// On entry v[k1] = twiddled pass-1 outputs; the caller has already made sure (team barrier) that nobody
-// still reads the planes.  On exit the spectrum of both symbols sits at spec_slot(k) and is visible to the team.
-// PRUNE: outputs k = k0 + 64*k3 with k3 = 3, 4 (bins 192..319) are not stored; the receiver never looks at
-// them (data and pilots live in bins 1..132 and 380..511, and the coarse shift moves them by < 60 bins).
-template <bool INV, int MAXT, bool PRUNE = false>
-COFDM_DEV void team_fft512p_tail(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int team) {
-    const int q = lane & 7, p = (lane >> 3) + 4 * h;
-    {
-        const int b = q + 8 * p;
-#pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[k1].re; Wim[b + 72 * k1] = v[k1].im; }
-    }
-    team_bar_sync<MAXT>(team);
-    {
-        const int b = q + 72 * p;
-#pragma unroll
-        for (int n2 = 0; n2 < 8; n2++) { v[n2].re = Wre[b + 8 * n2]; v[n2].im = Wim[b + 8 * n2]; }
-    }
-    team_bar_sync<MAXT>(team);
-    dft8<INV>(v);
-#pragma unroll
-    for (int k2 = 1; k2 < 8; k2++) v[k2] = cmul(v[k2], twid<INV>(__ldg(&tw_p2[k2 * 8 + q])));
-    {
-        const int b = q + 72 * p;
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) { Wre[b + 9 * k2] = v[k2].re; Wim[b + 9 * k2] = v[k2].im; }
-    }
-    team_bar_sync<MAXT>(team);
-    {
-        const int b = 9 * q + 72 * p;
-#pragma unroll
-        for (int n3 = 0; n3 < 8; n3++) { v[n3].re = Wre[b + n3]; v[n3].im = Wim[b + n3]; }
-    }
-    team_bar_sync<MAXT>(team);
-    dft8<INV>(v);
-    {
-        const int k0 = p + 8 * q;
-        const int s0 = k0 ^ (q << 1);               // spec_slot(k0 + 64*k3) = s0 + 64*k3
-#pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) {
-            if (PRUNE && (k3 == 3 || k3 == 4)) continue;
-            Wre[s0 + 64 * k3] = v[k3].re; Wim[s0 + 64 * k3] = v[k3].im;
-        }
-    }
-    team_bar_sync<MAXT>(team);
-}
-
-// ------------------------------------------------------------------------------------------------
-// team_fft512p_tail_linear: the tail for a transform whose result leaves the SM as a LINEAR image (tx).
-// Passes 2 and 3 as above, but the second exchange uses a layout that lets the last pass be done by
-// lane (k1 = lane & 7, k2 = (lane >> 3) + 4h), so that a half-warp owns 16 CONSECUTIVE outputs
-// n = k1 + 8 k2 + 64 k3 and can store them to a linear buffer without bank conflicts:
-//   E2'(k1,k2,n3) = (n3 ^ ((k1 >> 1) | ((k2 & 1) << 2))) + 8 k1 + 64 k2
-//   writer (pass-2 butterfly k1 = p, n3 = q, fixed k2): half-warp = q 0..7 x p {even, even+1}  -> banks (q^g) + 8 (p&1)
-//   reader (fixed n3): half-warp = k1 0..7 x k2 {c, c+1}: g takes 8 values x (k1 & 1)           -> 16 distinct banks
-// On exit v[k3] = X[k1 + 8 k2 + 64 k3] in registers; the planes are free (every lane has passed the last barrier).
-// ------------------------------------------------------------------------------------------------
-template <bool INV, int MAXT>
-COFDM_DEV void team_fft512p_tail_linear(pc (&v)[8], float2 *Wre, float2 *Wim, const float2 *tw_p2, int lane, int h, int team) {
-    const int q = lane & 7, p = (lane >> 3) + 4 * h;
-    {
-        const int b = q + 8 * p;
-#pragma unroll
-        for (int k1 = 0; k1 < 8; k1++) { Wre[b + 72 * k1] = v[k1].re; Wim[b + 72 * k1] = v[k1].im; }
-    }
-    team_bar_sync<MAXT>(team);
-    {
-        const int b = q + 72 * p;
-#pragma unroll
-        for (int n2 = 0; n2 < 8; n2++) { v[n2].re = Wre[b + 8 * n2]; v[n2].im = Wim[b + 8 * n2]; }
-    }
-    team_bar_sync<MAXT>(team);
-    dft8<INV>(v);
-#pragma unroll
-    for (int k2 = 1; k2 < 8; k2++) v[k2] = cmul(v[k2], twid<INV>(__ldg(&tw_p2[k2 * 8 + q])));
-    {
-        const int b0 = (q ^ (p >> 1)) + 8 * p, b1 = (q ^ ((p >> 1) | 4)) + 8 * p;      // even / odd k2
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) {
-            const int a = ((k2 & 1) ? b1 : b0) + 64 * k2;
-            Wre[a] = v[k2].re; Wim[a] = v[k2].im;
-        }
-    }
-    team_bar_sync<MAXT>(team);
-    {
-        const int k1 = lane & 7, k2 = (lane >> 3) + 4 * h;
-        const int g = (k1 >> 1) | ((k2 & 1) << 2), b = 8 * k1 + 64 * k2;
-#pragma unroll
-        for (int n3 = 0; n3 < 8; n3++) { v[n3].re = Wre[b + (n3 ^ g)]; v[n3].im = Wim[b + (n3 ^ g)]; }
-    }
-    team_bar_sync<MAXT>(team);
-    dft8<INV>(v);
 }
 
 }  // namespace cofdmk

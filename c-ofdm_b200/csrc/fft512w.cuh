@@ -126,13 +126,13 @@ COFDM_HD constexpr int f512_i(int k) { return (k & 127) >> 4; }
 // of the rx chain contributes exp(-j 2 pi beta (128 + lane) / 512) there); pass make_float2(1, 0) for a plain transform.
 // w512 = exp(-j 2 pi k / 512) table (global).  E: the warp's exchange region; the caller guarantees (by __syncwarp) that nobody
 // still reads it.  On exit mn[] / ot[] as described at the top of this file; v[] is consumed.
-COFDM_DEV void warp_fft512(float2 (&v)[16], float2 p, float2 *E, const float2 *__restrict__ w512, int lane,
+// (second form: the caller supplies V = W512^lane and V8 = W512^{8 lane} itself, e.g. loaded once for many transforms)
+COFDM_DEV void warp_fft512(float2 (&v)[16], float2 p, float2 *E, const float2 V, const float2 V8, int lane,
                            float2 (&mn)[8], float2 (&ot)[8]) {
     const int g = lane & 1, m = lane >> 1;
     ndft16(v);
     {   // pass-1 twiddles by recurrence: T[k1] = p V^k1, V = W512^lane; restarted at k1 = 8 from the table (V^8 = W512^{8 lane}),
         // so no factor carries more than eight roundings
-        const float2 V = __ldg(w512 + lane), V8 = __ldg(w512 + 8 * lane);
         if ((lane & 3) == 3) p = make_float2(-p.x, -p.y);                       // g = 1, m odd (see above)
         float2 t = p;
         v[0] = nmul(v[0], t);
@@ -174,6 +174,11 @@ COFDM_DEV void warp_fft512(float2 (&v)[16], float2 p, float2 *E, const float2 *_
         mn[i] = p_fma(v[i], p_bcast(sg), recv);                                     // g = 0: Y0 + W Y1 (k3 = 0);  g = 1: Y0 - W Y1 (k3 = 1)
         ot[i] = p_fma(recv, p_bcast(-sg), v[i]);                                    // g = 0: Y0 - W Y1 (k3 = 1);  g = 1: Y0 + W Y1 (k3 = 0)
     }
+}
+
+COFDM_DEV void warp_fft512(float2 (&v)[16], float2 p, float2 *E, const float2 *__restrict__ w512, int lane,
+                           float2 (&mn)[8], float2 (&ot)[8]) {
+    warp_fft512(v, p, E, __ldg(w512 + lane), __ldg(w512 + 8 * lane), lane, mn, ot);
 }
 
 }  // namespace cofdmk

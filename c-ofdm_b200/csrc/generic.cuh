@@ -1,4 +1,4 @@
-// generic.cuh -- the any-size path: the same reference chain as rx512.cuh / tx512_kernel for configurations
+// generic.cuh -- the any-size path: the same reference chain as rx512n.cuh / tx512w.cuh for configurations
 // the fused fft-512 kernels do not cover (e.g. BASELINE.json configs[4]: fft 4096, cp 1024, 1920 data and 128
 // pilot sub-carriers, 64-QAM).  One OFDM symbol does not fit a warp's registers and one frame does not fit an
 // SM's shared memory here, so the chain is split into five kernels with the spectra kept in HBM between them

@@ -89,7 +89,7 @@ inline void host_dft(std::vector<cd> &x, int sign) {
 struct HostTables {
     Params p{};                       // sizes filled, device pointers left null
     ConfigMap cfg;
-    std::vector<float2> tw_fft, tw_p1, tw_p2, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
+    std::vector<float2> tw_fft, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
     std::vector<float2> constell[9];  // index = mod type 1,2,4,6,8
     std::vector<float> t2_mask;
     std::vector<int16_t> bin_map, data_bin, pilot_bin;
@@ -231,7 +231,11 @@ inline void build_f512_roles(HostTables &T) {
             continue;
         }
         const int sl = n1 < 5 ? n1 : n1 - 6;
-        const unsigned d = m >= 0 ? (unsigned)m : (m == -2 ? 0x8000u : 0x4000u);
+        // data: [7:0] byte offset of the symbol's bits in the staged payload, [11:8] right shift of the byte (of the 16-bit window
+        // when modType does not divide 8: a 6-bit symbol may straddle two bytes)
+        const int mod = p.mod_type, bit = (m >= 0 ? m : 0) * mod;
+        const unsigned shf = (8 % mod) != 0 ? (unsigned)(16 - mod - (bit & 7)) : (unsigned)(8 - mod - (bit & 7));
+        const unsigned d = m >= 0 ? ((unsigned)(bit >> 3) | (shf << 8)) : (m == -2 ? 0x8000u : 0x4000u);
         unsigned *u = &T.tx_desc[2 * lane].x;                  // 8 consecutive words per lane
         u[sl >> 1] = (u[sl >> 1] & ~(0xffffu << (16 * (sl & 1)))) | (d << (16 * (sl & 1)));
     }
@@ -314,18 +318,6 @@ inline HostTables build_tables(const ConfigMap &cfg) {
     T.tw_fft = twiddles(N);
     T.tw_pf = twiddles(p.pf_size);
     T.tw_t2 = twiddles(p.t2sin_size);
-    T.tw_p1.resize(8 * 64);
-    T.tw_p2.resize(8 * 8);
-    for (int k1 = 0; k1 < 8; k1++)
-        for (int t = 0; t < 64; t++) {
-            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((t * k1) % 512) / 512.0L;
-            T.tw_p1[k1 * 64 + t] = make_float2((float)cosl(ang), (float)sinl(ang));
-        }
-    for (int k2 = 0; k2 < 8; k2++)
-        for (int n3 = 0; n3 < 8; n3++) {
-            const long double ang = -2.0L * 3.14159265358979323846264338327950288L * ((n3 * k2) % 64) / 64.0L;
-            T.tw_p2[k2 * 8 + n3] = make_float2((float)cosl(ang), (float)sinl(ang));
-        }
 
     for (int m : {1, 2, 4, 6, 8}) {
         T.constell_d[m] = constellation_d(m);

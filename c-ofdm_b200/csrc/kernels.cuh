@@ -4,7 +4,7 @@
 //                        coarse CFO (pilot_freq_sinh), fine CFO (cp_freq_sinh), preamble phase lock
 //                        (pr_phase_sinh), 9 FFT-512, pilot normalisation + segment correction
 //                        (FFT_FORM::read), linear-phase channel fit (chan_char_lq), equalise, hard demap.
-//   tx512_kernel         payload bytes -> QAM map -> pilot insertion -> 8 IFFT-512 -> CP -> frame
+//   tx512w_kernel (tx512w.cuh)   payload bytes -> QAM map -> pilot insertion -> 8 IFFT-512 -> CP -> frame
 //   t2sin_metric_kernel  sync-tone block detector metric (T2SIN_FORM::corr / find_t2sin)
 //   preamble_corr_kernel tiled sliding dot product + sliding energy (find_corr / find_preamble)
 //   mod_kernel / demod_kernel, int16 <-> cf32 converters
@@ -22,16 +22,6 @@
 
 namespace cofdmk {
 
-// ------------------------------------------------------------------------------------------------
-// tx512_kernel: FRAME_FORM::write + get / get_int16 (Frame.cpp:185-198, 54-70, 244-256)
-// one CTA per frame; warp 0 copies the frame-invariant sync tone + preamble, warps 1..num_symb
-// build one OFDM symbol each: map bits, insert pilots, IFFT-512, /sqrt(512), prepend CP.
-// ------------------------------------------------------------------------------------------------
-COFDM_HD int tx512_threads(int num_symb) { return 32 * (2 * ((num_symb + 1) / 2) + 1); }
-COFDM_HD size_t tx512_smem_bytes(int num_symb, int bytes_per_frame) {
-    return (size_t)((num_symb + 1) / 2) * kPairSlots * sizeof(float2) + (size_t)((bytes_per_frame + 15) & ~15) + 16;   // +16: a straddling 6-bit symbol reads one byte on
-}
-
 // wide: the frame buffer is 16-byte aligned (one 16- / 8-byte store for the pair); otherwise one store per sample
 template <int FMT>
 COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/, float2 a, float2 b, float mult, bool wide) {
@@ -47,141 +37,6 @@ COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/,
     } else {
         if (wide) reinterpret_cast<float4 *>(frame_out)[idx >> 1] = make_float4(a.x, a.y, b.x, b.y);
         else { reinterpret_cast<float2 *>(frame_out)[idx] = a; reinterpret_cast<float2 *>(frame_out)[idx + 1] = b; }
-    }
-}
-
-// the 8 frequency-domain points (bins t + 64 r) of symbols A and B that one lane feeds to the first IFFT pass:
-// null, pilot, or the constellation point of MOD payload bits (Frame.cpp:55-62 + modulation.cpp:39-50)
-template <int MOD>
-COFDM_DEV void tx512_grid_points(const Params &P, const uint8_t *pl, int A, int B, bool hasB, const int (&mm)[8], pc (&v)[8]) {
-    // Branch-free: a warp's 32 bins mix data, a pilot and nulls, so a branch per kind would run every path anyway.
-    // The payload holds exactly num_data_subc * num_symb * MOD bits, so no bounds checks; symbol s starts at byte
-    // s * num_data_subc * MOD / 8 (num_data_subc is a multiple of 8), and the bit offset inside is the same for A and B.
-    const int sym_bytes = P.num_data_subc * MOD / 8;
-    const uint8_t *pa = pl + A * sym_bytes, *pb = pl + (hasB ? B : A) * sym_bytes;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-        const int m = mm[r];                                                         // bin_map[t + 64 r]: data index, -2 pilot, -1 null
-        const bool isdata = m >= 0;
-        const int bit = (isdata ? m : 0) * MOD, b0 = bit >> 3, sh = 16 - MOD - (bit & 7);
-        unsigned wa = (unsigned)pa[b0] << 8, wb = (unsigned)pb[b0] << 8;
-        if ((8 % MOD) != 0) { wa |= pa[b0 + 1]; wb |= pb[b0 + 1]; }                  // a 6-bit symbol may straddle two bytes (the
-                                                                                     // staging buffer is padded by 16 bytes)
-        const float2 ca = __ldg(&P.constell[(wa >> sh) & ((1u << MOD) - 1u)]);       // Frame.cpp:59-62 + modulation.cpp:39-50
-        const float2 cb = __ldg(&P.constell[(wb >> sh) & ((1u << MOD) - 1u)]);
-        const float alt = m == -2 ? P.pilot_ampl : 0.f;                              // Frame.cpp:55-57
-        const float2 va = make_float2(isdata ? ca.x : alt, isdata ? ca.y : 0.f);
-        const float2 vb = hasB ? make_float2(isdata ? cb.x : alt, isdata ? cb.y : 0.f) : make_float2(0.f, 0.f);
-        v[r] = make_pc(va, vb);
-    }
-}
-
-// One CTA per frame.  The last warp copies the frame-invariant sync tone + preamble; the other warps form
-// teams of two per PAIR of OFDM symbols (packed f32x2 arithmetic, symbol A in the low half, B in the high
-// half, exactly as in the rx kernel): map bits, insert pilots, IFFT-512, /sqrt(512), prepend CP.
-// BULK: the last IFFT pass writes the symbols' wire images (CP + body) straight into the shared memory the planes
-// occupied, and each symbol leaves the SM as one TMA bulk store (needs a 16-byte aligned frame buffer).
-template <int FMT, bool BULK = false>
-__global__ void __launch_bounds__(32 * (2 * ((kMaxFusedSymb + 1) / 2) + 1))
-tx512_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, void *__restrict__ frames) {
-    COFDM_DYN_SMEM(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int frame = blockIdx.x;
-    if (frame >= n_frames) return;
-    const int ns = P.num_symb, npair = (ns + 1) / 2;
-    float2 *W = reinterpret_cast<float2 *>(smem_raw);
-    uint8_t *pl = reinterpret_cast<uint8_t *>(W + (size_t)npair * kPairSlots);
-    const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
-    char *fout = reinterpret_cast<char *>(frames) + (size_t)frame * P.frame_len * sample_bytes;
-    const bool wide = (reinterpret_cast<uintptr_t>(fout) & 15) == 0;      // every pair store of this frame is then aligned
-
-    if (warp == 2 * npair) {
-        // T2SIN tone + preamble are constants of the configuration (Frame.cpp:228-229)
-        const int n_const = P.t2sin_size + P.pf_size;
-        for (int i = 2 * lane; i < n_const; i += 64) {
-            const float2 a = i < P.t2sin_size ? __ldg(&P.t2_tone[i]) : __ldg(&P.preamble_td[i - P.t2sin_size]);
-            const float2 b = i + 1 < P.t2sin_size ? __ldg(&P.t2_tone[i + 1]) : __ldg(&P.preamble_td[i + 1 - P.t2sin_size]);
-            store_sample_pair<FMT>(fout, i, a, b, P.mult, wide);
-        }
-        return;
-    }
-    // the FFT warps stage the frame's payload; the sub-carrier map is fetched while those loads are in flight
-    const int nfft = 64 * npair;
-    if ((P.bytes_per_frame & 15) == 0 && ((reinterpret_cast<uintptr_t>(payload) & 15) == 0)) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(payload + (size_t)frame * P.bytes_per_frame);
-        for (int i = tid; i < P.bytes_per_frame / 16; i += nfft) reinterpret_cast<uint4 *>(pl)[i] = __ldg(src + i);
-    } else {
-        for (int i = tid; i < P.bytes_per_frame; i += nfft) pl[i] = payload[(size_t)frame * P.bytes_per_frame + i];
-    }
-    const int team = warp >> 1, h = warp & 1;
-    constexpr int kMaxTeams = (kMaxFusedSymb + 1) / 2;
-    const int A = 2 * team, B = A + 1;
-    const bool hasB = B < ns;
-    float2 *Wre = W + (size_t)team * kPairSlots, *Wim = Wre + kFft512Slots;
-    const int mod = P.mod_type, t = lane + 32 * h;
-    int mm[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) mm[r] = __ldg(&P.bin_map[t + 64 * r]);
-    named_bar_sync(1, nfft);                        // the FFT warps only: the constant-copy warp is already on its way
-    pc v[8];
-    switch (mod) {                                  // uniform: the symbol width becomes a compile-time constant
-        case 1: tx512_grid_points<1>(P, pl, A, B, hasB, mm, v); break;
-        case 2: tx512_grid_points<2>(P, pl, A, B, hasB, mm, v); break;
-        case 4: tx512_grid_points<4>(P, pl, A, B, hasB, mm, v); break;
-        case 6: tx512_grid_points<6>(P, pl, A, B, hasB, mm, v); break;
-        default: tx512_grid_points<8>(P, pl, A, B, hasB, mm, v); break;
-    }
-    team_fft512p_head<true>(v, P.tw_p1, t);                                          // Frame.cpp:64 (backward, unnormalised)
-    if (BULK) {
-        team_fft512p_tail_linear<true, kMaxTeams>(v, Wre, Wim, P.tw_p2, lane, h, team);
-        // v[k3] = x[n], n = k0 + 64 k3; /sqrt(512) (Frame.cpp:66-68); body after the CP slot (Frame.cpp:191-192), the
-        // last 128 samples also into the CP slot (:196-197).  Image of A in the re plane's memory, of B in the im plane's.
-        const float sc = 0.04419417382415922028f;
-        const int k0 = (lane & 7) + 8 * ((lane >> 3) + 4 * h);
-#pragma unroll
-        for (int k3 = 0; k3 < 8; k3++) {
-            const int n = k0 + 64 * k3;
-            const float2 a = make_float2(v[k3].re.x * sc, v[k3].im.x * sc), b = make_float2(v[k3].re.y * sc, v[k3].im.y * sc);
-            if (FMT == kCI16) {
-                unsigned *ia = reinterpret_cast<unsigned *>(Wre), *ib = reinterpret_cast<unsigned *>(Wim);
-                const unsigned pa = ((unsigned)(unsigned short)(short)__float2int_rz(a.x * P.mult)) | ((unsigned)(unsigned short)(short)__float2int_rz(a.y * P.mult) << 16);
-                const unsigned pb = ((unsigned)(unsigned short)(short)__float2int_rz(b.x * P.mult)) | ((unsigned)(unsigned short)(short)__float2int_rz(b.y * P.mult) << 16);
-                ia[128 + n] = pa; ib[128 + n] = pb;
-                if (k3 >= 6) { ia[n - 384] = pa; ib[n - 384] = pb; }
-            } else {
-                Wre[128 + n] = a; Wim[128 + n] = b;
-                if (k3 >= 6) { Wre[n - 384] = a; Wim[n - 384] = b; }
-            }
-        }
-        tma_store_fence();
-        team_bar_sync<kMaxTeams>(team);
-        if (lane == 0 && (h == 0 || hasB)) {
-            const int base = P.t2sin_size + P.pf_size + (h ? B : A) * 640;
-            tma_store_1d(fout + (size_t)base * sample_bytes, h ? Wim : Wre, 640u * (unsigned)sample_bytes);
-            tma_store_commit_and_wait_read();
-        }
-        return;
-    }
-    team_fft512p_tail<true, kMaxTeams>(v, Wre, Wim, P.tw_p2, lane, h, team);
-    // output: warp h writes samples 256h .. 256h+255 of BOTH symbols, so every 64-bit plane word it loads
-    // (value of A, value of B) is used whole.  /sqrt(512) (Frame.cpp:66-68), body after the CP slot
-    // (Frame.cpp:191-192), the last 128 samples also into the CP slot (Frame.cpp:196-197).
-    const float sc = 0.04419417382415922028f;
-    const int baseA = P.t2sin_size + P.pf_size + A * 640, baseB = baseA + 640;
-#pragma unroll
-    for (int it = 0; it < 4; it++) {
-        const int n = 256 * h + 2 * lane + 64 * it;
-        // spec_slot(n + 1) = spec_slot(n) + 1 for even n: samples n, n+1 of both symbols in one 128-bit load per plane
-        const float4 rr = *reinterpret_cast<const float4 *>(&Wre[spec_slot(n)]);   // (reA[n], reB[n], reA[n+1], reB[n+1])
-        const float4 ii = *reinterpret_cast<const float4 *>(&Wim[spec_slot(n)]);
-        const float2 a0 = make_float2(rr.x * sc, ii.x * sc), a1 = make_float2(rr.z * sc, ii.z * sc);
-        const float2 b0 = make_float2(rr.y * sc, ii.y * sc), b1 = make_float2(rr.w * sc, ii.w * sc);
-        store_sample_pair<FMT>(fout, baseA + 128 + n, a0, a1, P.mult, wide);
-        if (n >= 384) store_sample_pair<FMT>(fout, baseA + n - 384, a0, a1, P.mult, wide);
-        if (hasB) {
-            store_sample_pair<FMT>(fout, baseB + 128 + n, b0, b1, P.mult, wide);
-            if (n >= 384) store_sample_pair<FMT>(fout, baseB + n - 384, b0, b1, P.mult, wide);
-        }
     }
 }
 

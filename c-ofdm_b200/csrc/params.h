@@ -41,8 +41,6 @@ struct Params {
     int pf_nr, pf_radix[8];
     // ---- device tables (all fp32 roundings of host fp64 values) ----
     const float2 *tw_fft;        // [fft_size]  exp(-j*2*pi*k/fft_size)
-    const float2 *tw_p1;         // [8][64]     exp(-j*2*pi*t*k1/512)     (fused 512 path, pass-1 twiddles)
-    const float2 *tw_p2;         // [8][8]      exp(-j*2*pi*n3*k2/64)     (fused 512 path, pass-2 twiddles)
     const float2 *tw_pf;         // [pf_size]   exp(-j*2*pi*k/pf_size)
     const float2 *tw_t2;         // [t2sin_size]
     const float *t2_mask;        // [t2sin_size] detect_mask (Frame.cpp:120-133)
@@ -64,8 +62,8 @@ struct Params {
                                  //      data bin number `lane` (bins 128..131, 381..383, held in ot[]): descriptor as above | (its k1) << 16
     const uint2 *acq_desc;       // [32] acquire kernel: per lane 4 x 16 bits (even lane: mn[0..3]; odd lane: mn[4..7] of lane - 1): [7:0] index of
                                  //      the phase the slot produces (0..127), [15] take the product of straggler bin 128 + [9:8] instead
-    const uint4 *tx_desc;        // [32][2] tx512w.cuh: per lane 10 x 16 bits, the grid rows n1 = 0..4, 11..15 of bins lane + 32 n1: data index (0..255),
-                                 //      0x4000 = null, 0x8000 = pilot (rows 5..10 are never used by the sub-carrier map)
+    const uint4 *tx_desc;        // [32][2] tx512w.cuh: per lane 10 x 16 bits, the grid rows n1 = 0..4, 11..15 of bins lane + 32 n1: where the symbol's
+                                 //      bits sit in the payload ([7:0] byte, [11:8] shift), 0x4000 = null, 0x8000 = pilot (rows 5..10 are never used)
     const float2 *grid_lane;     // [32][10] conj(tx grid of the preamble) / sqrt(fft_size) at the bins of mn[0..7] and of the used ot[] register
     int n_combos;
 };

@@ -18,7 +18,7 @@ static void wire(EmuHandle *h) {
     HostTables &T = h->T;
     h->P = T.p;
     Params &P = h->P;
-    P.tw_fft = T.tw_fft.data(); P.tw_p1 = T.tw_p1.data(); P.tw_p2 = T.tw_p2.data();
+    P.tw_fft = T.tw_fft.data();
     P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
@@ -81,8 +81,6 @@ int emu_fused_ok(void *h) { return ((EmuHandle *)h)->T.fused512_ok ? 1 : 0; }
 
 static int g_emu_pc_plain = 0;
 void emu_set_pc_plain(int on) { g_emu_pc_plain = on; }
-static int g_emu_tx_warp = 1;
-void emu_set_tx_warp(int on) { g_emu_tx_warp = on; }
 static int g_emu_tx_bulk = 1;
 void emu_set_tx_bulk(int on) { g_emu_tx_bulk = on; }
 
@@ -110,27 +108,17 @@ int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int 
     auto *h = (EmuHandle *)hv;
     if (!h->T.fused512_ok) return -1;
     const Params P = h->P;
-    if (g_emu_tx_warp) {
-        // the product default: one warp per symbol (tx512w.cuh); g_emu_tx_bulk picks the bulk-store or the plain-store output stage
-        const size_t smw = tx512w_smem_bytes(P.num_symb);
-        const dim3 blk(tx512w_threads(P.num_symb));
-#define EMU_TXW(F, B) do { if (P.num_symb <= 8) emu::launch(dim3(n_frames), blk, smw, [&] { tx512w_kernel<F, B, 8>(P, payload, n_frames, frames); }); \
-                           else emu::launch(dim3(n_frames), blk, smw, [&] { tx512w_kernel<F, B, kMaxFusedSymb>(P, payload, n_frames, frames); }); } while (0)
+    {
+        // one warp per symbol (tx512w.cuh); g_emu_tx_bulk picks the bulk-store or the plain-store output stage
+        const size_t smw = tx512w_smem_bytes(P.num_symb, P.t2sin_size + P.pf_size);
+        const dim3 blk(tx512w_threads(P.num_symb)), grd(std::min(n_frames, 2));     // persistent CTAs: two of them walk over the frames
+#define EMU_TXW(F, B) do { if (P.num_symb <= 8) emu::launch(grd, blk, smw, [&] { tx512w_kernel<F, B, 8>(P, payload, n_frames, frames); }); \
+                           else emu::launch(grd, blk, smw, [&] { tx512w_kernel<F, B, kMaxFusedSymb>(P, payload, n_frames, frames); }); } while (0)
         if (fmt == kCI16) { if (g_emu_tx_bulk) EMU_TXW(kCI16, true); else EMU_TXW(kCI16, false); }
         else { if (g_emu_tx_bulk) EMU_TXW(kCF32, true); else EMU_TXW(kCF32, false); }
 #undef EMU_TXW
         return 0;
     }
-    const size_t sm = tx512_smem_bytes(P.num_symb, P.bytes_per_frame);
-    // both output stages: register stores (tx_bulk = 0) and the TMA bulk store of linear images (the product default)
-    if (g_emu_tx_bulk) {
-        if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCI16, true>(P, payload, n_frames, frames); });
-        else emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCF32, true>(P, payload, n_frames, frames); });
-        return 0;
-    }
-    if (fmt == kCI16) emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCI16>(P, payload, n_frames, frames); });
-    else emu::launch(dim3(n_frames), dim3(tx512_threads(P.num_symb)), sm, [&] { tx512_kernel<kCF32>(P, payload, n_frames, frames); });
-    return 0;
 }
 
 int emu_t2sin_metric(void *hv, const void *samples, int fmt, long long start, long long n_blocks, float *rel) {
