@@ -21,7 +21,7 @@ from . import build as _build
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libcofdm_b200.so")
 
-HOST, DEVICE = 0, 1
+HOST, DEVICE, DEVICE_IN = 0, 1, 2
 CF32, CI16 = 0, 1
 NOT_FOUND_T2SIN, NOT_FOUND_PREAMBLE = -1, -10
 
@@ -77,6 +77,8 @@ def load_library():
     lib.cofdm_i16_to_cf32.argtypes = [vp, vp, vp, sz, ci]
     lib.cofdm_rx_stream.argtypes = [vp, vp, sz, sz, vp, vp, C.POINTER(sz)]
     lib.cofdm_rx_stream_sharded.argtypes = [vp, vp, sz, C.c_int, C.c_int, sz, vp, vp, C.POINTER(sz), C.POINTER(sz)]
+    lib.cofdm_ring_load.argtypes = [vp, vp, sz, C.POINTER(vp)]
+    lib.cofdm_allreduce_counters.argtypes = [vp, vp, vp, sz, vp, sz]
     lib.cofdm_enable_timing.argtypes = [vp, ci]
     lib.cofdm_last_kernel_ms.argtypes = [vp]
     lib.cofdm_last_kernel_ms.restype = C.c_float
@@ -351,6 +353,34 @@ class Modem:
                                                    out.ctypes.data if want_bytes else None, C.byref(k), C.byref(um)))
         res = (pos[:k.value].copy(), out[:k.value] if want_bytes else None)   # a view: no second pass over the payload
         return res + (um.value,) if return_unmerged else res
+
+    def ring_load(self, ring_i16):
+        """FRAME_FORM::form_int16_to_double on the receiver's ring: upload a host int16 ring [n, 2] once; returns the
+        device address, to be passed with fmt CI16 / space DEVICE_IN (see include/cofdm.h)"""
+        import numpy as np
+        a = np.ascontiguousarray(ring_i16, dtype=np.int16)
+        dev = C.c_void_p()
+        self._chk(self.lib.cofdm_ring_load(self.h, a.ctypes.data, a.size // 2, C.byref(dev)))
+        return dev.value
+
+    def ring_find(self, ring_dev, n_samples, start=0):
+        """find_t2sin then find_preamble (+1) on the resident ring; only the two 8-byte results cross PCIe"""
+        pos = C.c_longlong(-1)
+        self._chk(self.lib.cofdm_find_t2sin(self.h, ring_dev, CI16, n_samples, start, C.byref(pos), DEVICE_IN))
+        if pos.value < 0:
+            return pos.value, None
+        st, first = C.c_longlong(pos.value), C.c_longlong(-10)
+        self._chk(self.lib.cofdm_preamble_search(self.h, ring_dev, CI16, n_samples, C.byref(st), 1, None, C.byref(first), DEVICE_IN))
+        return pos.value, first.value
+
+    def allreduce_counters(self, nccl_comm, sums, maxes):
+        """SUM of integer counters and MAX of float values over the ranks of the caller's ncclComm_t (in place)"""
+        import numpy as np
+        s_ = np.ascontiguousarray(sums, dtype=np.uint64)
+        m_ = np.ascontiguousarray(maxes, dtype=np.float64)
+        self._chk(self.lib.cofdm_allreduce_counters(self.h, nccl_comm, s_.ctypes.data if s_.size else None, s_.size,
+                                                    m_.ctypes.data if m_.size else None, m_.size))
+        return s_, m_
 
     def i16_to_cf32(self, samples):
         self._follow(samples)

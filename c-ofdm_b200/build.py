@@ -36,7 +36,7 @@ def build_library(force=False, verbose=False, out=None, extra_flags=()):
     """out / extra_flags: an experimental variant beside the product library (A/B runs through COFDM_LIB_PATH)"""
     if out is None and not force and not is_stale():
         return LIB
-    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ldl",
            "-Xcompiler", "-fPIC", "-shared", "-o", out or LIB, os.path.join(HERE, "csrc", "cofdm_host.cu")] + list(extra_flags)
     if verbose:
         cmd.insert(1, "-Xptxas")

@@ -5,6 +5,7 @@
 #include "../../include/cofdm.h"
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
 
 #include <algorithm>
 #include <cstdio>
@@ -59,6 +60,8 @@ struct cofdm {
     cudaStream_t pipe_stream[kPipe] = {};
     DevBuf pipe_in[kPipe], pipe_out[kPipe];
     DevBuf scratch_a, scratch_b, scratch_c;
+    DevBuf ring;                                 // cofdm_ring_load: the receiver's int16 ring, resident
+    DevBuf coll;                                 // cofdm_allreduce_counters staging
     // intermediates between the kernels of one rx pass, ONE SET PER PIPELINE SLOT: the COFDM_HOST pipeline runs consecutive
     // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
@@ -291,7 +294,7 @@ void cofdm_destroy(cofdm_t *h) {
         h->pipe_in[i].release(); h->pipe_out[i].release();
         if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
     }
-    h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release();
+    h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release(); h->ring.release(); h->coll.release();
     for (int i = 0; i < kPipe; i++) { h->gen_frames[i].release(); h->gen_spec[i].release(); h->gen_pre[i].release(); h->fscal[i].release(); }
     if (h->amb_dev) cudaFree(h->amb_dev);
     if (h->pos_dev) cudaFree(h->pos_dev);
@@ -609,7 +612,7 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
     const size_t chunk = want_taps ? n_frames : std::min<size_t>(n_frames, h->pipe_chunk);
     if (n_frames == 0) return COFDM_OK;
     for (int i = 0; i < (want_taps ? 1 : h->pipe_depth); i++) {
-        CU_TRY(h->pipe_in[i].reserve(chunk * frame_stride * sb));
+        if (space != COFDM_DEVICE_IN) CU_TRY(h->pipe_in[i].reserve(chunk * frame_stride * sb));
         CU_TRY(h->pipe_out[i].reserve(chunk * bpf));
     }
     CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
@@ -638,8 +641,12 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
             cudaStream_t st = h->pipe_stream[s];
             // the last record only needs rx_len samples (the caller's buffer may end there)
             const size_t in_bytes = ((n - 1) * frame_stride + (size_t)P.rx_len) * sb;
-            CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, (const char *)samples + f0 * frame_stride * sb, in_bytes, cudaMemcpyHostToDevice, st));
-            if (int rc = launch_rx(h, st, h->pipe_in[s].p, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t, sync_less, s)) return rc;
+            const void *dsamp = (const char *)samples + f0 * frame_stride * sb;
+            if (space != COFDM_DEVICE_IN) {
+                CU_TRY(cudaMemcpyAsync(h->pipe_in[s].p, dsamp, in_bytes, cudaMemcpyHostToDevice, st));
+                dsamp = h->pipe_in[s].p;
+            }
+            if (int rc = launch_rx(h, st, dsamp, fmt, n, frame_stride, (uint8_t *)h->pipe_out[s].p, h->amb_dev, t, sync_less, s)) return rc;
             CU_TRY(cudaMemcpyAsync(bytes + f0 * bpf, h->pipe_out[s].p, n * bpf, cudaMemcpyDeviceToHost, st));
         }
         return COFDM_OK;
@@ -677,9 +684,14 @@ int cofdm_t2sin_metric(cofdm_t *h, const void *samples, int fmt, size_t n_sample
         return launch_t2(h, h->stream, samples, fmt, start, n_blocks, rel);
     }
     const size_t sb = sample_bytes(fmt);
-    CU_TRY(h->scratch_a.reserve(n_samples * sb)); CU_TRY(h->scratch_b.reserve(n_blocks * sizeof(float)));
-    CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
-    if (int rc = launch_t2(h, h->stream, h->scratch_a.p, fmt, start, n_blocks, (float *)h->scratch_b.p)) return rc;
+    CU_TRY(h->scratch_b.reserve(n_blocks * sizeof(float)));
+    const void *dsamp = samples;
+    if (space != COFDM_DEVICE_IN) {
+        CU_TRY(h->scratch_a.reserve(n_samples * sb));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
+        dsamp = h->scratch_a.p;
+    }
+    if (int rc = launch_t2(h, h->stream, dsamp, fmt, start, n_blocks, (float *)h->scratch_b.p)) return rc;
     CU_TRY(cudaMemcpyAsync(rel, h->scratch_b.p, n_blocks * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     return COFDM_OK;
@@ -723,12 +735,16 @@ int cofdm_preamble_search(cofdm_t *h, const void *samples, int fmt, size_t n_sam
     }
     const size_t sb = sample_bytes(fmt), ncor = (size_t)h->P.cor_size;
     const size_t o_first = n_starts * sizeof(long long), o_cor = 2 * o_first;
-    CU_TRY(h->scratch_a.reserve(n_samples * sb));
     CU_TRY(h->scratch_b.reserve(o_cor + n_starts * ncor * sizeof(float)));
     char *b = (char *)h->scratch_b.p;
-    CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
+    const void *dsamp = samples;
+    if (space != COFDM_DEVICE_IN) {
+        CU_TRY(h->scratch_a.reserve(n_samples * sb));
+        CU_TRY(cudaMemcpyAsync(h->scratch_a.p, samples, n_samples * sb, cudaMemcpyHostToDevice, h->stream));
+        dsamp = h->scratch_a.p;
+    }
     CU_TRY(cudaMemcpyAsync(b, starts, o_first, cudaMemcpyHostToDevice, h->stream));
-    if (int rc = launch_pc(h, h->stream, h->scratch_a.p, fmt, n_samples, (const long long *)b, n_starts,
+    if (int rc = launch_pc(h, h->stream, dsamp, fmt, n_samples, (const long long *)b, n_starts,
                            cor ? (float *)(b + o_cor) : nullptr, (long long *)(b + o_first))) return rc;
     if (first) CU_TRY(cudaMemcpyAsync(first, b + o_first, o_first, cudaMemcpyDeviceToHost, h->stream));
     if (cor) CU_TRY(cudaMemcpyAsync(cor, b + o_cor, n_starts * ncor * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
@@ -996,6 +1012,51 @@ int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n, int s
         CU_TRY(cudaMemcpyAsync(out, dout, n * 8, cudaMemcpyDeviceToHost, h->stream));
         CU_TRY(cudaStreamSynchronize(h->stream));
     }
+    return COFDM_OK;
+}
+
+int cofdm_ring_load(cofdm_t *h, const int16_t *ring_host, size_t n_samples, const int16_t **ring_dev) {
+    if (!h || !ring_host || !ring_dev) return fail(COFDM_ERR_ARG, "cofdm_ring_load: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    // (+ one frame of slack: the searches read up to cor_size + pr_sin_len samples past their start, like the reference)
+    CU_TRY(h->ring.reserve((n_samples + (size_t)h->P.frame_len) * 4));
+    CU_TRY(cudaMemcpyAsync(h->ring.p, ring_host, n_samples * 4, cudaMemcpyHostToDevice, h->stream));
+    CU_TRY(cudaMemsetAsync((char *)h->ring.p + n_samples * 4, 0, (size_t)h->P.frame_len * 4, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));                     // the caller may overwrite its ring right away
+    *ring_dev = (const int16_t *)h->ring.p;
+    return COFDM_OK;
+}
+
+// ncclAllReduce resolved at run time from the libnccl.so.2 of the process: the library itself links the CUDA runtime only
+namespace {
+typedef int (*nccl_allreduce_fn)(const void *, void *, size_t, int /*ncclDataType_t*/, int /*ncclRedOp_t*/, void * /*ncclComm_t*/, cudaStream_t);
+nccl_allreduce_fn resolve_nccl_allreduce() {
+    static nccl_allreduce_fn fn = [] {
+        void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
+        if (!lib) lib = dlopen("libnccl.so.2", RTLD_NOW);
+        if (!lib) lib = dlopen("libnccl.so", RTLD_NOW);
+        return lib ? (nccl_allreduce_fn)dlsym(lib, "ncclAllReduce") : (nccl_allreduce_fn) nullptr;
+    }();
+    return fn;
+}
+}  // namespace
+
+int cofdm_allreduce_counters(cofdm_t *h, void *nccl_comm, unsigned long long *sum_counters, size_t n_sum, double *max_values, size_t n_max) {
+    if (!h || !nccl_comm || (n_sum && !sum_counters) || (n_max && !max_values)) return fail(COFDM_ERR_ARG, "cofdm_allreduce_counters: bad argument");
+    if (set_device(h)) return COFDM_ERR_CUDA;
+    nccl_allreduce_fn ar = resolve_nccl_allreduce();
+    if (!ar) return fail(COFDM_ERR_UNSUPPORTED, "cofdm_allreduce_counters: libnccl.so.2 (ncclAllReduce) not found in this process");
+    CU_TRY(h->coll.reserve((n_sum + n_max) * 8 + 16));
+    unsigned long long *ds = (unsigned long long *)h->coll.p;
+    double *dm = (double *)(ds + n_sum);
+    if (n_sum) CU_TRY(cudaMemcpyAsync(ds, sum_counters, n_sum * 8, cudaMemcpyHostToDevice, h->stream));
+    if (n_max) CU_TRY(cudaMemcpyAsync(dm, max_values, n_max * 8, cudaMemcpyHostToDevice, h->stream));
+    const int kNcclUint64 = 5, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2;      // nccl.h: ncclDataType_t / ncclRedOp_t
+    if (n_sum) if (int rc = ar(ds, ds, n_sum, kNcclUint64, kNcclSum, nccl_comm, h->stream)) return fail(COFDM_ERR_CUDA, "ncclAllReduce(sum) failed: " + std::to_string(rc));
+    if (n_max) if (int rc = ar(dm, dm, n_max, kNcclFloat64, kNcclMax, nccl_comm, h->stream)) return fail(COFDM_ERR_CUDA, "ncclAllReduce(max) failed: " + std::to_string(rc));
+    if (n_sum) CU_TRY(cudaMemcpyAsync(sum_counters, ds, n_sum * 8, cudaMemcpyDeviceToHost, h->stream));
+    if (n_max) CU_TRY(cudaMemcpyAsync(max_values, dm, n_max * 8, cudaMemcpyDeviceToHost, h->stream));
+    CU_TRY(cudaStreamSynchronize(h->stream));
     return COFDM_OK;
 }
 

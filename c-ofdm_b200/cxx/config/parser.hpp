@@ -1,8 +1,10 @@
-// config/parser.hpp look-alike (reference config/parser.hpp:9-11, parser.cpp:4-33): same ConfigMap type,
-// same parse_config signature and semantics ("key = long", '#' comments, lines without '=' skipped,
-// std::runtime_error("Cannot open config file"), std::stol on the value, missing keys read 0 via operator[]).
+// config/parser.hpp of the drop-in tree: the type and the entry point the reference apps use (config/parser.hpp:9-11),
+// implemented with this repository's own config reader (csrc/host_consts.hpp parse_config_file), whose observable
+// behaviour equals parser.cpp:4-33: "key = long" lines, '#' comments, lines without '=' skipped, white space ignored,
+// std::runtime_error("Cannot open config file"), std::stol's exceptions on a non-numeric value, missing keys read 0
+// through operator[].
 #pragma once
-#include <algorithm>
+#include <cctype>
 #include <fstream>
 #include <stdexcept>
 #include <string>
@@ -11,21 +13,21 @@
 using ConfigMap = std::unordered_map<std::string, long>;
 
 inline ConfigMap parse_config(const std::string &filename) {
-    std::ifstream file(filename);
-    if (!file.is_open()) throw std::runtime_error("Cannot open config file");
+    std::ifstream f(filename);
+    if (!f.is_open()) throw std::runtime_error("Cannot open config file");
     ConfigMap cfg;
     std::string line;
-    while (std::getline(file, line)) {
-        auto notspace = [](unsigned char ch) { return !std::isspace(ch); };
-        line.erase(line.begin(), std::find_if(line.begin(), line.end(), notspace));
-        line.erase(std::find_if(line.rbegin(), line.rend(), notspace).base(), line.end());
-        if (line.empty() || line[0] == '#') continue;
-        auto pos = line.find('=');
-        if (pos == std::string::npos) continue;
-        std::string key = line.substr(0, pos), value = line.substr(pos + 1);
-        key.erase(std::remove_if(key.begin(), key.end(), ::isspace), key.end());
-        value.erase(std::remove_if(value.begin(), value.end(), ::isspace), value.end());
-        cfg[key] = std::stol(value);
+    while (std::getline(f, line)) {
+        size_t a = 0, b = line.size();
+        while (a < b && std::isspace((unsigned char)line[a])) a++;
+        while (b > a && std::isspace((unsigned char)line[b - 1])) b--;
+        if (a == b || line[a] == '#') continue;
+        const size_t eq = line.find('=', a);
+        if (eq == std::string::npos || eq >= b) continue;
+        std::string key, val;
+        for (size_t i = a; i < eq; i++) if (!std::isspace((unsigned char)line[i])) key += line[i];
+        for (size_t i = eq + 1; i < b; i++) if (!std::isspace((unsigned char)line[i])) val += line[i];
+        cfg[key] = std::stol(val);
     }
     return cfg;
 }

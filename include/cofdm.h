@@ -12,10 +12,16 @@
  * Conventions
  *   status     0 = COFDM_OK, negative = error; text via cofdm_last_error() (thread local).
  *   space      every data pointer of a call lives in the memory space given by `space`:
- *              COFDM_HOST   ordinary host memory; the library stages it through pinned buffers and
- *                           copies results back (H2D/D2H inside the call, call returns when done).
+ *              COFDM_HOST   host memory; the library copies it to device staging buffers and copies the results
+ *                           back (H2D/D2H inside the call, call returns when done).  The caller's pointers go
+ *                           straight to cudaMemcpyAsync: PINNED host memory (cudaHostAlloc, torch pin_memory)
+ *                           gives asynchronous, full-rate, double-buffered copies; pageable memory works too,
+ *                           at the driver's staged-copy rate.
  *              COFDM_DEVICE device memory of the handle's GPU; the call only enqueues kernels on the
  *                           handle's stream (cofdm_set_stream) and returns.
+ *              COFDM_DEVICE_IN  the SAMPLE input is device memory (e.g. the ring of cofdm_ring_load), every other
+ *                           pointer of the call (results, taps, starts) is host memory: per-frame calls on a
+ *                           resident capture move only their small results over PCIe.
  *   samples    COFDM_CF32 interleaved float32 (re,im)  |  COFDM_CI16 interleaved int16 (I,Q), the
  *              SDR wire format of FRAME_FORM::get_int16 / from_sdr_int16_buf.
  *   threading  one handle per host thread / CUDA stream (the reference's FRAME_FORM is not
@@ -39,6 +45,7 @@ extern "C" {
 
 #define COFDM_HOST 0
 #define COFDM_DEVICE 1
+#define COFDM_DEVICE_IN 2
 #define COFDM_CF32 0
 #define COFDM_CI16 1
 
@@ -171,8 +178,23 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
 /* FRAME_FORM::form_int16_to_double  OFDM/Frame.hpp:472-481 (fp32 on the device) */
 int cofdm_i16_to_cf32(cofdm_t *h, const int16_t *in, float *out, size_t n_samples, int space);
 
-/* Device time of the kernels of the last COFDM_HOST / COFDM_DEVICE call on this handle, measured with
- * CUDA events on the handle's stream (milliseconds; < 0 if timing is disabled). */
+/* FRAME_FORM::form_int16_to_double on the receiver's ring  OFDM/Frame.hpp:472-481 (rx.cpp:89,110 call it once per
+ * SDR block): uploads from_sdr_int16_buf (host, n_samples int16 I,Q pairs) into a device buffer owned by the handle and
+ * returns its device address.  The searches and the receive chain then read it in place with fmt = COFDM_CI16,
+ * space = COFDM_DEVICE_IN (`ring_dev + 2 * sample_index`), so a frame costs three small result copies instead of
+ * three uploads of the whole ring. */
+int cofdm_ring_load(cofdm_t *h, const int16_t *ring_host, size_t n_samples, const int16_t **ring_dev);
+
+/* the one collective of a multi-GPU job -- SUM of n_sum integer counters (bit errors, bits, frames,
+ * samples ...) and MAX of n_max values (elapsed times) over the ranks of an NCCL communicator, in place, host arrays.
+ * nccl_comm is the caller's ncclComm_t (passed as void*) whose rank uses this handle's device; the library resolves
+ * ncclAllReduce from the libnccl.so.2 already in the process (dlopen), it does not link NCCL. */
+int cofdm_allreduce_counters(cofdm_t *h, void *nccl_comm, unsigned long long *sum_counters, size_t n_sum,
+                             double *max_values, size_t n_max);
+
+/* Device time of the kernels of the last COFDM_DEVICE call on this handle (and of the single-stream COFDM_HOST calls: the
+ * searches), measured with CUDA events on the handle's stream (milliseconds; < 0 if timing is disabled or the last call
+ * was a chunked COFDM_HOST tx/rx pipeline, which runs on several streams). */
 int cofdm_enable_timing(cofdm_t *h, int on);
 float cofdm_last_kernel_ms(const cofdm_t *h);
 /* number of kernels this library has launched on the handle since creation */

@@ -61,3 +61,50 @@ def test_cxx_facade_compiles_against_the_abi(tmp_path):
     r = subprocess.run(["g++", "-std=c++17", "-O1", f"-I{ROOT}/include", f"-I{ROOT}/c-ofdm_b200/cxx", f"{ROOT}/tests/cxx/main_like.cpp",
                         "-o", str(tmp_path / "main_like"), f"-L{ROOT}/c-ofdm_b200", "-lcofdm_b200"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
+
+
+def test_txrx_lookalike_with_mac_header_compiles(tmp_path):
+    """tx.cpp / rx.cpp look-alike: the drop-in tree now carries mac/mac_frame.hpp (missing from the reference's own tree)"""
+    import subprocess
+    cb.build.build_library()
+    r = subprocess.run(["g++", "-std=c++17", "-O1", f"-I{ROOT}/include", f"-I{ROOT}/c-ofdm_b200/cxx", f"{ROOT}/tests/cxx/txrx_like.cpp",
+                        "-o", str(tmp_path / "txrx_like"), f"-L{ROOT}/c-ofdm_b200", "-lcofdm_b200"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+
+
+def test_mac_header_reproduces_the_golden_frame(tmp_path):
+    """MAC::write on the recorded payload gives the recorded frame (header 01 00 00 00 00 00 7E 57), MAC::read returns it"""
+    import subprocess
+    import numpy as np
+    g = np.load(os.path.join(ROOT, "tests", "golden", "ref_capture.npz"))
+    mf = g["mac_frame"].astype(np.uint8)
+    src = tmp_path / "mac_check.cpp"
+    src.write_text(r'''
+#include <cstdio>
+#include <fstream>
+#include <iterator>
+#include "mac/mac_frame.hpp"
+int main(int argc, char **argv) {
+    std::ifstream f(argv[1], std::ios::binary);
+    std::vector<uint8_t> frame((std::istreambuf_iterator<char>(f)), {});
+    MAC mac(1, 0, frame.size());
+    std::vector<uint8_t> pay(frame.begin() + 8, frame.end());
+    auto w = mac.write(pay, 0);
+    if (w != frame) { std::printf("write differs\n"); return 1; }
+    MAC r(1, 0, frame.size());
+    auto back = r.read(frame);
+    if (back != pay || !r.checksum_ok() || r.input_tx_id != 1 || r.input_rx_id != 0 || r.input_seq_num != 0) { std::printf("read differs\n"); return 1; }
+    frame[20] ^= 1;
+    r.read(frame);
+    if (r.checksum_ok()) { std::printf("corruption not seen\n"); return 1; }
+    auto w2 = mac.write(pay, 0);
+    if (w2[4] != 1) { std::printf("seq does not advance\n"); return 1; }
+    std::printf("ok %zu\n", mac.payload);
+    return 0;
+}''')
+    exe = tmp_path / "mac_check"
+    r = subprocess.run(["g++", "-std=c++17", "-O1", f"-I{ROOT}/c-ofdm_b200/cxx", str(src), "-o", str(exe)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    mf.tofile(tmp_path / "frame.bin")
+    r = subprocess.run([str(exe), str(tmp_path / "frame.bin")], capture_output=True, text=True)
+    assert r.returncode == 0 and "ok 248" in r.stdout, r.stdout + r.stderr
