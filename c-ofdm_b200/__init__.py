@@ -80,6 +80,7 @@ def load_library():
     lib.cofdm_ring_load.argtypes = [vp, vp, sz, C.POINTER(vp)]
     lib.cofdm_allreduce_counters.argtypes = [vp, vp, vp, sz, vp, sz]
     lib.cofdm_enable_timing.argtypes = [vp, ci]
+    lib.cofdm_last_stage_ms.argtypes = [vp, vp, ci]
     lib.cofdm_last_kernel_ms.argtypes = [vp]
     lib.cofdm_last_kernel_ms.restype = C.c_float
     lib.cofdm_launch_count.argtypes = [vp]
@@ -189,6 +190,12 @@ class Modem:
 
     def last_kernel_ms(self):
         return float(self.lib.cofdm_last_kernel_ms(self.h))
+
+    def last_stage_ms(self):
+        """measured per-stage milliseconds of the last stream call / of the rx launches since enable_timing (see cofdm.h)"""
+        out = (C.c_float * 7)()
+        self._chk(self.lib.cofdm_last_stage_ms(self.h, out, 7))
+        return dict(zip(("upload", "scan", "merge", "gather", "acquire", "demod", "d2h"), [float(v) for v in out]))
 
     def launch_count(self):
         return int(self.lib.cofdm_launch_count(self.h))

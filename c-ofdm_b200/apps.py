@@ -135,9 +135,12 @@ def rx_file(modem, capture_path, out_path, log_path=None, shards=1, n_bytes=None
     append the payloads to `out_path`; optionally write a LOG.txt-format trace.  Returns a dict of counters."""
     s = modem.sizes
     cap = np.fromfile(capture_path, dtype=np.int16).reshape(-1, 2)
+    modem.enable_timing(True)
     t0 = time.perf_counter()
     pos, frames = modem.rx_stream(cap, shards=shards)
     t_rx = time.perf_counter() - t0
+    stages = modem.last_stage_ms()
+    modem.enable_timing(False)
     t1 = time.perf_counter()
     bodies, seqs, bad_cs = [], [], 0
     for fr in frames:
@@ -151,23 +154,37 @@ def rx_file(modem, capture_path, out_path, log_path=None, shards=1, n_bytes=None
         out = out[:n_bytes]
     out.tofile(out_path)
     if log_path is not None:
-        write_trace(log_path, len(frames), t_rx, t_mac, seqs, frames_per_block=max(1, s.rx_buf_size))
+        write_trace(log_path, np.asarray(pos, dtype=np.int64), stages, t_rx, t_mac, seqs, block_samples=s.output_size * max(1, s.rx_buf_size))
     return {"frames": len(frames), "bad_checksums": bad_cs, "positions": pos, "seq": np.array(seqs, dtype=np.int64),
-            "seconds_rx": t_rx}
+            "seconds_rx": t_rx, "stage_ms": stages}
 
 
-def write_trace(path, n_frames, t_rx, t_mac, seqs, frames_per_block=40):
-    """LOG.txt as rx.cpp:129-235 prints it: one line per loop turn, `KEY:value ` pairs, keys ITER GLOBAL T2SIN
-    PILOT_SINH FREQ_PHASE_SINH PFC MAC SEQ DET FR_IN_BUF TIME.  The GPU does the turns of a capture in one
-    batch, so each stage's share is the batch time split in the proportions of the reference's own trace
-    (LOG.txt: T2SIN 17 us, PILOT_SINH 57, FREQ_PHASE_SINH 84, PFC 27 per frame) and amortised per frame."""
-    per = t_rx / max(1, n_frames)
-    w = np.array([17.0, 57.0, 84.0, 27.0])
-    w = w / w.sum() * per
-    mac = t_mac / max(1, n_frames)
+def write_trace(path, positions, stage_ms, t_rx, t_mac, seqs, block_samples):
+    """LOG.txt in the format rx.cpp:32-36,128-235 prints (one line per frame, `KEY:seconds ` pairs; python_code/timetrace.py
+    parses any keys).  Every value is MEASURED on this run -- nothing is taken from the reference's own LOG.txt:
+      T2SIN            device time of the stream scanner (sync-tone detector + preamble search, stream.cuh) / frames
+      PILOT_SINH       device time of the acquire kernel (pilot_freq_sinh, the preamble's cp_freq_sinh + pr_phase_sinh, chan_char_lq) / frames
+      FREQ_PHASE_SINH  0: the per-symbol CFO / phase corrections are fused into the two neighbouring kernels and cannot be timed apart
+      PFC              device time of the demod kernel (cp_freq_sinh of the message symbols, FFT, pilots, equaliser, demap) / frames
+      MAC              host time of MAC::read / frames
+      GATHER, MERGE, D2H   frame gather kernel, host-side list read-back + shard merge, payload copy-back, / frames
+      CONVERT          upload of the capture (the device-side form_int16_to_double), on the first frame of each SDR block, per block
+      FR_IN_BUF        ordinal of the frame inside its SDR block, from the detected positions
+      TIME             wall time of the whole call / frames (includes what the stages above do not cover: launches, synchronisation)
+    The GPU processes a capture as one batch, so per-frame values are batch times divided by the number of frames."""
+    n = len(positions)
+    per = lambda key: stage_ms.get(key, 0.0) * 1e-3 / max(1, n)
+    blocks = positions // max(1, block_samples)
+    n_blocks = int(blocks.max()) + 1 if n else 1
+    convert = stage_ms.get("upload", 0.0) * 1e-3 / n_blocks
+    tot = (t_rx + t_mac) / max(1, n)
     with open(path, "w") as f:
-        g = 0.0
-        for i in range(n_frames):
-            f.write(f"ITER:{i} GLOBAL:{g:.6g} T2SIN:{w[0]:.6g} PILOT_SINH:{w[1]:.6g} FREQ_PHASE_SINH:{w[2]:.6g} PFC:{w[3]:.6g} "
-                    f"MAC:{mac:.6g} SEQ:{int(seqs[i])} DET:{i} FR_IN_BUF:{i % frames_per_block + 1} TIME:{per + mac:.6g}\n")
-            g += per + mac
+        g, in_buf, prev_blk = 0.0, 0, -1
+        for i in range(n):
+            in_buf = in_buf + 1 if blocks[i] == prev_blk else 1
+            prev_blk = blocks[i]
+            extra = f"CONVERT:{convert:.6g} " if in_buf == 1 else ""
+            f.write(f"ITER:{i} GLOBAL:{g:.6g} T2SIN:{per('scan'):.6g} {extra}PILOT_SINH:{per('acquire'):.6g} FREQ_PHASE_SINH:{0.0:.6g} "
+                    f"PFC:{per('demod'):.6g} MAC:{t_mac / max(1, n):.6g} GATHER:{per('gather'):.6g} MERGE:{per('merge'):.6g} D2H:{per('d2h'):.6g} "
+                    f"SEQ:{int(seqs[i])} DET:{i} FR_IN_BUF:{in_buf} TIME:{tot:.6g}\n")
+            g += tot

@@ -8,6 +8,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -47,6 +48,20 @@ struct DevBuf {
     }
     void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
 };
+// pinned host staging (small results of per-frame calls: one asynchronous copy instead of several synchronous ones)
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t n) {
+        if (n <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        cudaError_t e = cudaHostAlloc(&p, n, cudaHostAllocDefault);
+        if (e == cudaSuccess) cap = n;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+};
 
 }  // namespace
 
@@ -62,6 +77,7 @@ struct cofdm {
     DevBuf scratch_a, scratch_b, scratch_c;
     DevBuf ring;                                 // cofdm_ring_load: the receiver's int16 ring, resident
     DevBuf coll;                                 // cofdm_allreduce_counters staging
+    PinBuf pin;                                  // pinned staging of the tapped rx call's results
     // intermediates between the kernels of one rx pass, ONE SET PER PIPELINE SLOT: the COFDM_HOST pipeline runs consecutive
     // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
@@ -75,6 +91,10 @@ struct cofdm {
     unsigned long long *pos_dev = nullptr;       // find_t2sin result
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     bool timing = false, timed = false;
+    // per-stage device times of the last call (cofdm_last_stage_ms), CUDA events on the launching stream
+    cudaEvent_t sev[8] = {};
+    float stage_ms[COFDM_STAGE_COUNT] = {};
+    bool rx_events_pending = false;
     unsigned long long launches = 0;
 };
 
@@ -96,6 +116,20 @@ struct Timed {
     explicit Timed(cofdm *h_) : h(h_) { if (h->timing) cudaEventRecord(h->ev0, h->stream); }
     ~Timed() { if (h->timing) { cudaEventRecord(h->ev1, h->stream); h->timed = true; } }
 };
+
+// adds the acquire / demod kernel times of the last launch_rx to stage_ms (blocks until that launch has finished)
+void collect_rx_stage(cofdm *h) {
+    if (!h->rx_events_pending) return;
+    h->rx_events_pending = false;
+    float a = 0.f, d = 0.f;
+    if (cudaEventSynchronize(h->sev[2]) != cudaSuccess) return;
+    if (cudaEventElapsedTime(&a, h->sev[0], h->sev[1]) == cudaSuccess) h->stage_ms[COFDM_STAGE_ACQUIRE] += a;
+    if (cudaEventElapsedTime(&d, h->sev[1], h->sev[2]) == cudaSuccess) h->stage_ms[COFDM_STAGE_DEMOD] += d;
+}
+void add_stage(cofdm *h, int stage, cudaEvent_t e0, cudaEvent_t e1) {
+    float ms = 0.f;
+    if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess) h->stage_ms[stage] += ms;
+}
 
 int check_launch(cofdm *h, const char *what) {
     h->launches++;
@@ -132,6 +166,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     }
     // ---- acquire: the preamble -> 40 bytes of scalars per frame, one warp per frame.  The sync-less form (FRAME_FORM::read)
     //      has no synchronisation stage at all; its preamble is only looked at for the chan_char tap ----
+    if (h->timing) { collect_rx_stage(h); cudaEventRecord(h->sev[0], st); }
     if (!sync_less || taps.chan != nullptr) {
         const unsigned g4 = (unsigned)((n_frames + kAcqwWarps - 1) / kAcqwWarps);
 #define COFDM_ACQW(F, T) \
@@ -142,6 +177,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 #undef COFDM_ACQW
         if (int rc = check_launch(h, "rx_acquire512w")) return rc;
     }
+    if (h->timing) cudaEventRecord(h->sev[1], st);
     // ---- demod: the message symbols -> payload bytes, one warp per symbol ----
     {
         const size_t sm = rx_demod512_smem_bytes(P.num_symb);
@@ -157,6 +193,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 #undef COFDM_DM
         if (int rc = check_launch(h, "rx_demod512")) return rc;
     }
+    if (h->timing) { cudaEventRecord(h->sev[2], st); h->rx_events_pending = true; }
     if (taps.synced != nullptr && taps.scal != nullptr && !sync_less) {
         rx_synced_fixup_kernel<<<(unsigned)n_frames, 128, 0, st>>>(P, (int)n_frames, taps);
         return check_launch(h, "rx_synced_fixup");
@@ -294,10 +331,11 @@ void cofdm_destroy(cofdm_t *h) {
         h->pipe_in[i].release(); h->pipe_out[i].release();
         if (h->pipe_stream[i]) cudaStreamDestroy(h->pipe_stream[i]);
     }
-    h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release(); h->ring.release(); h->coll.release();
+    h->scratch_a.release(); h->scratch_b.release(); h->scratch_c.release(); h->ring.release(); h->coll.release(); h->pin.release();
     for (int i = 0; i < kPipe; i++) { h->gen_frames[i].release(); h->gen_spec[i].release(); h->gen_pre[i].release(); h->fscal[i].release(); }
     if (h->amb_dev) cudaFree(h->amb_dev);
     if (h->pos_dev) cudaFree(h->pos_dev);
+    for (auto &e : h->sev) if (e) cudaEventDestroy(e);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
@@ -348,6 +386,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         if (cudaStreamCreateWithFlags(&h->pipe_stream[i], cudaStreamNonBlocking) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "stream create"));
     if (cudaMalloc(&h->amb_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "cudaMalloc"));
     if (cudaMalloc(&h->pos_dev, sizeof(unsigned long long)) != cudaSuccess) return bail(fail(COFDM_ERR_CUDA, "cudaMalloc"));
+    for (auto &e : h->sev) cudaEventCreate(&e);
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
     if (T.fused512_ok) {
@@ -457,9 +496,18 @@ int cofdm_synchronize(cofdm_t *h) {
 
 int cofdm_enable_timing(cofdm_t *h, int on) {
     if (!h) return fail(COFDM_ERR_ARG, "null handle");
-    h->timing = on != 0; h->timed = false;
+    h->timing = on != 0; h->timed = false; h->rx_events_pending = false;
+    for (float &v : h->stage_ms) v = 0.f;
     return COFDM_OK;
 }
+int cofdm_last_stage_ms(cofdm_t *h, float *out, int n) {
+    if (!h || !out || n < 0) return fail(COFDM_ERR_ARG, "cofdm_last_stage_ms: bad argument");
+    if (!h->timing) return fail(COFDM_ERR_ARG, "cofdm_last_stage_ms: timing is off (cofdm_enable_timing)");
+    collect_rx_stage(h);
+    for (int i = 0; i < n; i++) out[i] = i < COFDM_STAGE_COUNT ? h->stage_ms[i] : 0.f;
+    return COFDM_OK;
+}
+
 float cofdm_last_kernel_ms(const cofdm_t *h) {
     if (!h || !h->timed) return -1.0f;
     float ms = -1.0f;
@@ -607,30 +655,58 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
         }
         return COFDM_OK;
     }
-    // ---- COFDM_HOST: chunked pipeline; with taps a single chunk and extra device buffers ----------
     const size_t sb = sample_bytes(fmt), bpf = (size_t)P.bytes_per_frame;
-    const size_t chunk = want_taps ? n_frames : std::min<size_t>(n_frames, h->pipe_chunk);
     if (n_frames == 0) return COFDM_OK;
-    for (int i = 0; i < (want_taps ? 1 : h->pipe_depth); i++) {
+    if (want_taps) {
+        // ---- host results WITH taps (parity checks, the per-frame facade): one stream, every result into one device block,
+        //      ONE asynchronous copy into pinned staging, one synchronisation ----
+        const size_t n_sc = 48, n_grid = (size_t)P.num_symb * P.fft_size, n_ch = (size_t)P.num_data_subc,
+                     n_con = (size_t)P.num_data_subc * P.num_symb, n_syn = (size_t)P.rx_len;
+        size_t off = 0;
+        auto take = [&](bool on, size_t bytes_) { const size_t o = off; if (on) off += (bytes_ + 15) & ~(size_t)15; return o; };
+        const size_t o_by = take(true, n_frames * bpf), o_amb = take(true, 16), o_sc = take(taps->scal || taps->synced, n_frames * n_sc * sizeof(float)),
+                     o_gr = take(taps->grid, n_frames * n_grid * sizeof(float2)), o_ch = take(taps->chan, n_frames * n_ch * sizeof(float2)),
+                     o_co = take(taps->constell, n_frames * n_con * sizeof(float2)), o_sy = take(taps->synced, n_frames * n_syn * sizeof(float2));
+        CU_TRY(h->scratch_c.reserve(off));
+        CU_TRY(h->pin.reserve(off));
+        char *b = (char *)h->scratch_c.p, *hp = (char *)h->pin.p;
+        cudaStream_t st = h->stream;
+        const void *dsamp = samples;
+        if (space != COFDM_DEVICE_IN) {
+            const size_t in_bytes = ((n_frames - 1) * frame_stride + (size_t)P.rx_len) * sb;
+            CU_TRY(h->pipe_in[0].reserve(in_bytes));
+            CU_TRY(cudaMemcpyAsync(h->pipe_in[0].p, samples, in_bytes, cudaMemcpyHostToDevice, st));
+            dsamp = h->pipe_in[0].p;
+        }
+        RxTaps t{};
+        if (taps->scal || taps->synced) t.scal = (float *)(b + o_sc);
+        if (taps->grid) t.grid = (float2 *)(b + o_gr);
+        if (taps->chan) t.chan = (float2 *)(b + o_ch);
+        if (taps->constell) t.constell = (float2 *)(b + o_co);
+        if (taps->synced) t.synced = (float2 *)(b + o_sy);
+        unsigned long long *amb = ambiguous ? (unsigned long long *)(b + o_amb) : nullptr;
+        if (amb) CU_TRY(cudaMemsetAsync(amb, 0, sizeof(unsigned long long), st));
+        if (int rc = launch_rx(h, st, dsamp, fmt, n_frames, frame_stride, (uint8_t *)(b + o_by), amb, t, sync_less, 0)) return rc;
+        CU_TRY(cudaMemcpyAsync(hp, b, off, cudaMemcpyDeviceToHost, st));
+        CU_TRY(cudaStreamSynchronize(st));
+        std::memcpy(bytes, hp + o_by, n_frames * bpf);
+        if (ambiguous) *ambiguous += *(const unsigned long long *)(hp + o_amb);
+        if (taps->scal) std::memcpy(taps->scal, hp + o_sc, n_frames * n_sc * sizeof(float));
+        if (taps->grid) std::memcpy(taps->grid, hp + o_gr, n_frames * n_grid * sizeof(float2));
+        if (taps->chan) std::memcpy(taps->chan, hp + o_ch, n_frames * n_ch * sizeof(float2));
+        if (taps->constell) std::memcpy(taps->constell, hp + o_co, n_frames * n_con * sizeof(float2));
+        if (taps->synced) std::memcpy(taps->synced, hp + o_sy, n_frames * n_syn * sizeof(float2));
+        return COFDM_OK;
+    }
+    // ---- COFDM_HOST without taps: chunked, double-buffered pipeline ----------
+    const size_t chunk = std::min<size_t>(n_frames, h->pipe_chunk);
+    for (int i = 0; i < h->pipe_depth; i++) {
         if (space != COFDM_DEVICE_IN) CU_TRY(h->pipe_in[i].reserve(chunk * frame_stride * sb));
         CU_TRY(h->pipe_out[i].reserve(chunk * bpf));
     }
     CU_TRY(cudaMemsetAsync(h->amb_dev, 0, sizeof(unsigned long long), h->stream));
     CU_TRY(cudaStreamSynchronize(h->stream));
     RxTaps t{};
-    const size_t n_sc = 48, n_grid = (size_t)P.num_symb * P.fft_size, n_ch = (size_t)P.num_data_subc,
-                 n_con = (size_t)P.num_data_subc * P.num_symb, n_syn = (size_t)P.rx_len;
-    size_t off_grid = 0, off_ch = 0, off_con = 0, off_syn = 0;
-    if (want_taps) {
-        off_grid = n_frames * n_sc * sizeof(float);
-        off_ch = off_grid + n_frames * n_grid * sizeof(float2);
-        off_con = off_ch + n_frames * n_ch * sizeof(float2);
-        off_syn = off_con + n_frames * n_con * sizeof(float2);
-        CU_TRY(h->scratch_c.reserve(off_syn + n_frames * n_syn * sizeof(float2)));
-        char *b = (char *)h->scratch_c.p;
-        t.scal = (float *)b; t.grid = (float2 *)(b + off_grid); t.chan = (float2 *)(b + off_ch);
-        t.constell = (float2 *)(b + off_con); t.synced = (float2 *)(b + off_syn);
-    }
     // (on any failure the copies already queued on the other pipe streams are drained before returning: they touch the
     //  caller's buffers and the handle's staging buffers)
     auto run_chunks = [&]() -> int {
@@ -657,14 +733,6 @@ static int rx_batch_impl(cofdm_t *h, const void *samples, int fmt, size_t n_fram
         if (e != cudaSuccess && rc_chunks == COFDM_OK) return fail(COFDM_ERR_CUDA, std::string("cudaStreamSynchronize: ") + cudaGetErrorString(e));
     }
     if (rc_chunks) return rc_chunks;
-    if (want_taps) {
-        char *b = (char *)h->scratch_c.p;
-        if (taps->scal) CU_TRY(cudaMemcpy(taps->scal, b, n_frames * n_sc * sizeof(float), cudaMemcpyDeviceToHost));
-        if (taps->grid) CU_TRY(cudaMemcpy(taps->grid, b + off_grid, n_frames * n_grid * sizeof(float2), cudaMemcpyDeviceToHost));
-        if (taps->chan) CU_TRY(cudaMemcpy(taps->chan, b + off_ch, n_frames * n_ch * sizeof(float2), cudaMemcpyDeviceToHost));
-        if (taps->constell) CU_TRY(cudaMemcpy(taps->constell, b + off_con, n_frames * n_con * sizeof(float2), cudaMemcpyDeviceToHost));
-        if (taps->synced) CU_TRY(cudaMemcpy(taps->synced, b + off_syn, n_frames * n_syn * sizeof(float2), cudaMemcpyDeviceToHost));
-    }
     if (ambiguous) {
         unsigned long long a = 0;
         CU_TRY(cudaMemcpy(&a, h->amb_dev, sizeof a, cudaMemcpyDeviceToHost));
@@ -915,11 +983,14 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
     if (total_blocks == 0 || max_frames == 0) return COFDM_OK;
     cudaStream_t st = h->stream;
     const unsigned *d_cap = reinterpret_cast<const unsigned *>(capture);
+    const bool tm = h->timing;
+    if (tm) { collect_rx_stage(h); for (float &v : h->stage_ms) v = 0.f; cudaEventRecord(h->sev[3], st); }
     if (space == COFDM_HOST) {
         CU_TRY(h->scratch_a.reserve((size_t)total_blocks * block * 4));
         CU_TRY(cudaMemcpyAsync(h->scratch_a.p, capture, (size_t)total_blocks * block * 4, cudaMemcpyHostToDevice, st));
         d_cap = reinterpret_cast<const unsigned *>(h->scratch_a.p);
     }
+    if (tm) cudaEventRecord(h->sev[4], st);
     const long long ns = std::min<long long>(n_shards, total_blocks);
     std::vector<StreamShard> shards((size_t)ns);
     std::vector<long long> own_end((size_t)ns);
@@ -946,6 +1017,9 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
             P, d_cap, d_sh, (int)ns, h->T.rx_buf_size, (long long)h->T.iterations, d_pos, (int)max_per, d_cnt);
         if (int rc = check_launch(h, "stream_scan")) return rc;
     }
+    if (tm) cudaEventRecord(h->sev[5], st);
+    const auto wall = [] { return std::chrono::steady_clock::now(); };
+    const auto t_merge0 = wall();
     std::vector<int> cnt((size_t)ns);
     CU_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaStreamSynchronize(st));
@@ -963,6 +1037,14 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
     std::vector<long long> merged;
     size_t unmerged = 0;
     merge_stream_shards(lists, own_end, merged, &unmerged);
+    if (tm) {
+        add_stage(h, COFDM_STAGE_UPLOAD, h->sev[3], h->sev[4]);
+        add_stage(h, COFDM_STAGE_SCAN, h->sev[4], h->sev[5]);
+        // list read-back + merge on the host: wall clock from the end of the scan (the stream was idle in between)
+        float scan_ms = h->stage_ms[COFDM_STAGE_SCAN] + h->stage_ms[COFDM_STAGE_UPLOAD];
+        const float since = std::chrono::duration<float, std::milli>(wall() - t_merge0).count();
+        h->stage_ms[COFDM_STAGE_MERGE] += std::max(0.f, since - scan_ms);
+    }
     if (merged.size() > max_frames) merged.resize(max_frames);
     if (n_unmerged) *n_unmerged = unmerged;
     const size_t found = merged.size();
@@ -977,11 +1059,16 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
         RxTaps none{};
         for (size_t f0 = 0; f0 < found; f0 += batch_cap) {
             const size_t n = std::min(batch_cap, found - f0);
+            if (tm) cudaEventRecord(h->sev[6], st);
             stream_gather_kernel<<<(unsigned)n, 256, 0, st>>>(d_cap, total_blocks * block, (const long long *)h->scratch_c.p + f0, (int)n, P.rx_len, (unsigned *)h->pipe_in[0].p);
             if (int rc = check_launch(h, "stream_gather")) return rc;
+            if (tm) cudaEventRecord(h->sev[7], st);
             if (int rc = launch_rx(h, st, h->pipe_in[0].p, COFDM_CI16, n, (size_t)P.rx_len, (uint8_t *)h->pipe_out[0].p, nullptr, none)) return rc;
+            if (tm) cudaEventRecord(h->sev[3], st);
             CU_TRY(cudaMemcpyAsync(bytes + f0 * (size_t)P.bytes_per_frame, h->pipe_out[0].p, n * (size_t)P.bytes_per_frame, cudaMemcpyDeviceToHost, st));
+            if (tm) cudaEventRecord(h->sev[4], st);
             CU_TRY(cudaStreamSynchronize(st));
+            if (tm) { add_stage(h, COFDM_STAGE_GATHER, h->sev[6], h->sev[7]); collect_rx_stage(h); add_stage(h, COFDM_STAGE_D2H, h->sev[3], h->sev[4]); }
         }
     }
     *n_found = found;

@@ -197,6 +197,20 @@ int cofdm_allreduce_counters(cofdm_t *h, void *nccl_comm, unsigned long long *su
  * was a chunked COFDM_HOST tx/rx pipeline, which runs on several streams). */
 int cofdm_enable_timing(cofdm_t *h, int on);
 float cofdm_last_kernel_ms(const cofdm_t *h);
+/* Per-stage times (milliseconds) of the work this handle did since cofdm_enable_timing(h, 1) / since the start of the last
+ * cofdm_rx_stream* call -- the measured counterpart of the per-stage trace rx.cpp:32-36,128-235 prints.  CUDA events on
+ * the launching stream, except MERGE (host wall clock).  Stage -> rx.cpp trace keys: SCAN = T2SIN + the untraced preamble
+ * search (rx.cpp:133,161); ACQUIRE = PILOT_SINH + FREQ_PHASE_SINH + the channel fit (rx.cpp:202-211); DEMOD = PFC + the
+ * demap half of MAC (rx.cpp:212-220); UPLOAD = CONVERT (form_int16_to_double); GATHER = the 5760-sample copy (rx.cpp:192-196). */
+#define COFDM_STAGE_UPLOAD 0
+#define COFDM_STAGE_SCAN 1
+#define COFDM_STAGE_MERGE 2
+#define COFDM_STAGE_GATHER 3
+#define COFDM_STAGE_ACQUIRE 4
+#define COFDM_STAGE_DEMOD 5
+#define COFDM_STAGE_D2H 6
+#define COFDM_STAGE_COUNT 7
+int cofdm_last_stage_ms(cofdm_t *h, float *out, int n);
 /* number of kernels this library has launched on the handle since creation */
 unsigned long long cofdm_launch_count(const cofdm_t *h);
 

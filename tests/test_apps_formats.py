@@ -23,7 +23,11 @@ def test_dump_formats_round_trip(tmp_path):
 
 
 def test_trace_is_parsed_like_timetrace_py(tmp_path):
-    apps.write_trace(tmp_path / "LOG.txt", 5, t_rx=5e-4, t_mac=5e-6, seqs=[7, 8, 9, 10, 11], frames_per_block=2)
+    """the trace carries MEASURED stage times (passed in by the caller from cofdm_last_stage_ms), amortised per frame; the
+    frames-per-block column comes from the detected positions"""
+    stage_ms = {"upload": 0.4, "scan": 0.05, "merge": 0.01, "gather": 0.002, "acquire": 0.02, "demod": 0.03, "d2h": 0.004}
+    pos = np.array([300, 7000, 20000, 26000, 41000], dtype=np.int64)       # SDR blocks of 18048 samples: 2 + 2 + 1 frames
+    apps.write_trace(tmp_path / "LOG.txt", pos, stage_ms, t_rx=5e-4, t_mac=5e-6, seqs=[7, 8, 9, 10, 11], block_samples=18048)
     rows = []
     for line in open(tmp_path / "LOG.txt"):                           # python_code/timetrace.py parse_log_file
         d = {}
@@ -35,8 +39,10 @@ def test_trace_is_parsed_like_timetrace_py(tmp_path):
     assert [r["FR_IN_BUF"] for r in rows] == [1, 2, 1, 2, 1]
     for key in ("GLOBAL", "T2SIN", "PILOT_SINH", "FREQ_PHASE_SINH", "PFC", "MAC", "DET", "TIME"):
         assert all(key in r for r in rows)
-    stages = sum(rows[0][k] for k in ("T2SIN", "PILOT_SINH", "FREQ_PHASE_SINH", "PFC"))
-    assert abs(stages - 1e-4) < 1e-9 and abs(rows[4]["GLOBAL"] - 4 * rows[0]["TIME"]) < 1e-9
+    assert abs(rows[0]["T2SIN"] - 0.05e-3 / 5) < 1e-12 and abs(rows[0]["PILOT_SINH"] - 0.02e-3 / 5) < 1e-12
+    assert abs(rows[0]["PFC"] - 0.03e-3 / 5) < 1e-12 and rows[0]["FREQ_PHASE_SINH"] == 0
+    assert ["CONVERT" in r for r in rows] == [True, False, True, False, True] and abs(rows[0]["CONVERT"] - 0.4e-3 / 3) < 1e-9
+    assert abs(rows[4]["GLOBAL"] - 4 * rows[0]["TIME"]) < 1e-9
 
 
 def test_config_value_follows_parser_cpp(tmp_path):

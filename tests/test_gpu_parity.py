@@ -525,4 +525,9 @@ def test_apps_tx_file_rx_file_round_trip(cfg_dir, tmp_path):
         assert r["frames"] == 61 and r["bad_checksums"] == 0 and r["seq"].tolist() == list(range(61))
         assert np.array_equal(np.fromfile(tmp_path / "data.txt", dtype=np.uint8), np.asarray(text, dtype=np.uint8))
         assert sum(1 for _ in open(tmp_path / "LOG.txt")) == 61
+        # the trace is measured: every device stage of the call has a positive CUDA-event time
+        st = r["stage_ms"]
+        assert all(st[k] > 0 for k in ("upload", "scan", "gather", "acquire", "demod", "d2h")), st
+        first = dict(p.split(":", 1) for p in open(tmp_path / "LOG.txt").readline().split())
+        assert abs(float(first["PFC"]) - st["demod"] * 1e-3 / 61) < 1e-9 and abs(float(first["T2SIN"]) - st["scan"] * 1e-3 / 61) < 1e-9
     m.close()
