@@ -16,6 +16,7 @@
 #include <vector>
 
 #include "kernels.cuh"
+#include "big.cuh"
 #include "stream.cuh"
 #include "host_consts.hpp"
 
@@ -82,6 +83,7 @@ struct cofdm {
     // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
     DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
+    int big_on = 1;                              // fft-4096 configurations use the cluster kernels of big.cuh (env COFDM_BIG=0: the any-size path)
     int tx_ctas = 148 * 4;                       // CTAs of the persistent tx kernel (SMs x resident CTAs per SM, measured at create)
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
     int pipe_depth = 2;                          // streams in flight (env COFDM_PIPE_DEPTH, <= kPipe); measured on B200:
@@ -143,11 +145,14 @@ size_t sample_bytes(int fmt) { return fmt == COFDM_CI16 ? 4 : 8; }
 // ---- device-side launches (all pointers are device pointers, stream given) ----------------------
 int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
                       uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot);
+int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
+                  uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot);
 int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt);
 int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
               uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0, int slot = 0) {
     if (n_frames == 0) return COFDM_OK;
     if (!h->T.fused512_ok) {
+        if (h->T.big_ok && h->big_on && !sync_less) return launch_rx_big(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot);
         if (h->T.generic_ok && !sync_less) return launch_rx_generic(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot);
         return fail(COFDM_ERR_UNSUPPORTED, "rx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
     }
@@ -201,6 +206,77 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     return COFDM_OK;
 }
 
+// the fft-4096 path (big.cuh): acquisition -> FrameScal, then one cluster of num_symb CTAs per frame
+template <int FMT, bool TMA, bool TAPS>
+int launch_big_demod(cofdm *h, cudaStream_t st, const void *samples, size_t n_frames, size_t stride, uint8_t *bytes,
+                     unsigned long long *amb, const RxTaps &taps, const FrameScal *fsc) {
+    const Params &P = h->P;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)(n_frames * (size_t)P.num_symb));
+    cfg.blockDim = dim3(kBigThreads);
+    cfg.dynamicSmemBytes = big_smem_bytes();
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)P.num_symb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, big_demod_kernel<FMT, TMA, TAPS>, P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, fsc);
+    if (e != cudaSuccess) return fail(COFDM_ERR_CUDA, std::string("big_demod launch: ") + cudaGetErrorString(e));
+    return check_launch(h, "big_demod");
+}
+
+int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
+                  uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot) {
+    const Params &P = h->P;
+    const size_t N = (size_t)P.fft_size, L = (size_t)P.ofdm_len;
+    const size_t sb = sample_bytes(fmt);
+    const bool want = taps.scal || taps.chan || taps.constell;
+    const bool al = ((uintptr_t)samples & 15) == 0 && (stride * sb) % 16 == 0;
+    CU_TRY(h->fscal[slot].reserve(n_frames * sizeof(FrameScal)));
+    FrameScal *fsc = (FrameScal *)h->fscal[slot].p;
+    if (h->timing) { collect_rx_stage(h); cudaEventRecord(h->sev[0], st); }
+    {
+        // acquisition by the any-size kernels on the preamble only (sub-batches bound their scratch memory)
+        const size_t sub = 4096, nb = std::min(sub, n_frames);
+        CU_TRY(h->gen_frames[slot].reserve(nb * sizeof(GenFrame)));
+        CU_TRY(h->gen_spec[slot].reserve(nb * N * sizeof(float2)));
+        CU_TRY(h->gen_pre[slot].reserve(nb * L * sizeof(float2)));
+        GenFrame *gf = (GenFrame *)h->gen_frames[slot].p;
+        float2 *spec = (float2 *)h->gen_spec[slot].p, *pre = (float2 *)h->gen_pre[slot].p;
+        const size_t sm_c = 2 * (size_t)P.pf_size * sizeof(float2), sm_s = (L + N) * sizeof(float2), sm_h = (size_t)P.num_data_subc / 2 * sizeof(float) + 16;
+        for (size_t f0 = 0; f0 < n_frames; f0 += sub) {
+            const int n = (int)std::min(sub, n_frames - f0);
+            const void *src = (const char *)samples + f0 * stride * sb;
+            RxTaps t = taps;
+            if (t.scal) t.scal += f0 * 48;
+            if (t.chan) t.chan += f0 * (size_t)P.num_data_subc;
+            if (fmt == COFDM_CI16) {
+                gen_coarse_kernel<kCI16><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
+                if (int rc = check_launch(h, "gen_coarse")) return rc;
+                gen_symbol_kernel<kCI16, true><<<dim3(1, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
+            } else {
+                gen_coarse_kernel<kCF32><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
+                if (int rc = check_launch(h, "gen_coarse")) return rc;
+                gen_symbol_kernel<kCF32, true><<<dim3(1, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
+            }
+            if (int rc = check_launch(h, "gen_symbol")) return rc;
+            gen_chan_kernel<true><<<n, kGenThreads, sm_h, st>>>(P, n, gf, spec, pre);
+            if (int rc = check_launch(h, "gen_chan")) return rc;
+            big_bridge_kernel<<<(n + 127) / 128, 128, 0, st>>>(P, n, gf, fsc + f0, t);
+            if (int rc = check_launch(h, "big_bridge")) return rc;
+        }
+    }
+    if (h->timing) cudaEventRecord(h->sev[1], st);
+    int rc;
+#define COFDM_BIG(F, T) (want ? launch_big_demod<F, T, true>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
+                              : launch_big_demod<F, T, false>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc))
+    if (fmt == COFDM_CI16) rc = al ? COFDM_BIG(kCI16, true) : COFDM_BIG(kCI16, false);
+    else rc = al ? COFDM_BIG(kCF32, true) : COFDM_BIG(kCF32, false);
+#undef COFDM_BIG
+    if (h->timing) { cudaEventRecord(h->sev[2], st); h->rx_events_pending = true; }
+    return rc;
+}
+
 // the any-size path (generic.cuh): five kernels per sub-batch with the spectra in HBM between them
 int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
                       uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot) {
@@ -231,7 +307,7 @@ int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, s
             gen_symbol_kernel<kCF32><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
         }
         if (int rc = check_launch(h, "gen_symbol")) return rc;
-        gen_chan_kernel<<<n, kGenThreads, sm_h, st>>>(P, n, gf, spec, pre);
+        gen_chan_kernel<false><<<n, kGenThreads, sm_h, st>>>(P, n, gf, spec, pre);
         if (int rc = check_launch(h, "gen_chan")) return rc;
         gen_demap_kernel<<<dim3((unsigned)P.num_symb, n), kGenThreads, 0, st>>>(P, n, gf, spec, bytes + f0 * (size_t)P.bytes_per_frame, amb, t);
         if (int rc = check_launch(h, "gen_demap")) return rc;
@@ -374,7 +450,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
-    rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
+    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
     rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.lane_aux, &P.lane_aux); rc |= upload(h, T.acq_desc, &P.acq_desc);
     rc |= upload(h, T.grid_lane, &P.grid_lane); rc |= upload(h, T.tx_desc, &P.tx_desc);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
@@ -447,6 +523,19 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
         cudaFuncSetAttribute(gen_symbol_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
         cudaFuncSetAttribute(gen_tx_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_t);
         cudaFuncSetAttribute(gen_tx_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_t);
+        if (T.big_ok) {
+            const char *bg = std::getenv("COFDM_BIG");
+            if (bg) h->big_on = std::atoi(bg) != 0;
+            cudaFuncSetAttribute(gen_symbol_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
+            cudaFuncSetAttribute(gen_symbol_kernel<kCI16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
+            const int smb = (int)big_smem_bytes();
+#define COFDM_BIG_ATTR(F, T, W) \
+            cudaFuncSetAttribute(big_demod_kernel<F, T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \
+            cudaFuncSetAttribute(big_demod_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+            COFDM_BIG_ATTR(kCF32, true, true); COFDM_BIG_ATTR(kCF32, true, false); COFDM_BIG_ATTR(kCF32, false, true); COFDM_BIG_ATTR(kCF32, false, false);
+            COFDM_BIG_ATTR(kCI16, true, true); COFDM_BIG_ATTR(kCI16, true, false); COFDM_BIG_ATTR(kCI16, false, true); COFDM_BIG_ATTR(kCI16, false, false);
+#undef COFDM_BIG_ATTR
+        }
     }
     cudaFuncSetAttribute(stream_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_scan_smem_bytes(P.cor_size, P.pr_sin_len));
     {

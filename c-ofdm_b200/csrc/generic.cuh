@@ -119,7 +119,8 @@ gen_coarse_kernel(const Params P, const void *__restrict__ samples, long long fr
 
 // ---- per symbol: CP correlation, rotation, FFT ------------------------------------------------------------------
 // spec[frame][sym][fft_size]; pre_rot[frame][ofdm_len] = fully frequency-corrected preamble samples (symbol 0)
-template <int FMT>
+// PRE_ONLY: only symbol 0 is transformed (its spectrum at spec[frame][fft_size]): the acquisition stage of the fft-4096 path
+template <int FMT, bool PRE_ONLY = false>
 __global__ void __launch_bounds__(kGenThreads)
 gen_symbol_kernel(const Params P, const void *__restrict__ samples, long long frame_stride, int n_frames,
                   GenFrame *__restrict__ gf, float2 *__restrict__ spec, float2 *__restrict__ pre_rot) {
@@ -160,11 +161,12 @@ gen_symbol_kernel(const Params P, const void *__restrict__ samples, long long fr
     }
     __syncthreads();
     float2 *X = cta_fft<false>(B, A, N, P.fft_radix, P.fft_nr, P.tw_fft, tid, nthr);
-    float2 *dst = spec + ((size_t)frame * P.n_sym_rx + sym) * N;
+    float2 *dst = spec + ((size_t)frame * (PRE_ONLY ? 1 : P.n_sym_rx) + sym) * N;
     for (int k = tid; k < N; k += nthr) dst[k] = X[k];
 }
 
 // ---- per frame: theta, channel line, pilot normaliser, per-symbol constant phases ------------------------------------
+template <bool PRE_ONLY = false>
 __global__ void __launch_bounds__(kGenThreads)
 gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const float2 *__restrict__ spec,
                 const float2 *__restrict__ pre_rot) {
@@ -191,7 +193,7 @@ gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const f
     const float2 rot = make_float2(z.x * inv, -z.y * inv);
     // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
     float pa = 0.f;
-    for (int i = tid; i < (nsym - 1) * NP; i += nthr) {
+    for (int i = tid; i < (PRE_ONLY ? 0 : (nsym - 1) * NP); i += nthr) {
         const int s = 1 + i / NP, p = i % NP;
         pa += sqrtf(cnorm2(spec[((size_t)frame * nsym + s) * N + __ldg(&P.pilot_bin[p])]));
     }
@@ -199,7 +201,7 @@ gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const f
     // chan_char_lq (Frame.hpp:389-434): phases of the first ND/2 data sub-carriers of the preamble
     float *ph = reinterpret_cast<float *>(smem_raw);
     const int nph = ND / 2;
-    const float2 *S0 = spec + (size_t)frame * nsym * N;
+    const float2 *S0 = spec + (size_t)frame * (PRE_ONLY ? 1 : nsym) * N;
     for (int i = tid; i < nph; i += nthr) {
         const float2 d = cmulc(cmul(S0[__ldg(&P.data_bin[i])], rot), __ldg(&P.mod_preamble[i]));
         ph[i] = atan2f(d.y, d.x);

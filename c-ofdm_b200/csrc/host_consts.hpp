@@ -92,7 +92,7 @@ struct HostTables {
     std::vector<float2> tw_fft, tw_pf, tw_t2, t2_tone, preamble_td, matched, mod_preamble;
     std::vector<float2> constell[9];  // index = mod type 1,2,4,6,8
     std::vector<float> t2_mask;
-    std::vector<int16_t> bin_map, data_bin, pilot_bin;
+    std::vector<int16_t> bin_map, data_bin, pilot_bin, bin_role;
     std::vector<uint8_t> preamble_bytes;
     // fp64 originals for the double-precision facade
     std::vector<cd> t2_tone_d, preamble_td_d, matched_d, mod_preamble_d, constell_d[9];
@@ -105,6 +105,7 @@ struct HostTables {
     std::vector<float2> grid_lane;    //             the same in lane order
     bool fused512_ok = false;         // the specialised kernels apply to this config
     bool generic_ok = false;          // the any-size multi-kernel path applies to this config
+    bool big_ok = false;              // the fft-4096 cluster kernels (big.cuh) apply to this config
 };
 
 inline float2 f2(cd v) { return make_float2((float)v.re, (float)v.im); }
@@ -293,6 +294,7 @@ inline HostTables build_tables(const ConfigMap &cfg) {
         p.pf_border0 = int((1.0 - rel_bw - rel_pilot_w) / 2.0 * p.pf_size);
         p.pf_den = NP * p.pf_size;
         p.pf_bins512 = 512.0f / (float)p.pf_den;
+        p.pf_binsN = (float)N / (float)p.pf_den;
         p.inv_pilot_norm = 1.0f / ((float)(p.num_symb * NP) * p.pilot_ampl);
     }
 
@@ -397,6 +399,13 @@ inline HostTables build_tables(const ConfigMap &cfg) {
     T.fused512_ok = (N == 512 && p.cp_size == 128 && ND == 256 && NP == 8 && p.num_pr_symb == 1 &&
                      p.num_symb >= 1 && p.num_symb <= kMaxFusedSymb && p.t2sin_size % 2 == 0 && p.pr_sin_len <= 128 * 5);
     if (T.fused512_ok) build_f512_roles(T);
+    T.bin_role.assign((size_t)N, (int16_t)-1);
+    for (int k = 0; k < N; k++) T.bin_role[(size_t)k] = T.bin_map[(size_t)k];
+    for (int q = 0; q < NP; q++) T.bin_role[(size_t)T.pilot_bin[(size_t)q]] = (int16_t)(-2 - q);
+    // big.cuh: fft 4096 / cp 1024 (ofdm_len / fft_size = 5 / 4 like the fft-512 geometry), one preamble symbol, up to 8 message
+    // symbols (one CTA each, a portable cluster), at most 128 pilots and 3840 data sub-carriers per symbol
+    T.big_ok = T.generic_ok && N == 4096 && p.cp_size == 1024 && p.num_pr_symb == 1 && p.num_symb >= 1 && p.num_symb <= 8 &&
+               NP <= kMaxPilots && ND <= 3840 && ND % 8 == 0 && ND % NP == 0;
     return T;
 }
 

@@ -35,6 +35,7 @@ struct Params {
     // pf_num = sum_argmax - num_pilot_subc*(pf_size/2), pf_den = num_pilot_subc*pf_size
     int pf_den;
     float pf_bins512;      // 512 / pf_den: whole fft-512 bins per unit of the coarse-shift numerator
+    float pf_binsN;        // fft_size / pf_den: the same for the configuration's own transform size (big.cuh)
     float inv_pilot_norm;  // 1 / (num_symb * num_pilot_subc * pilot_ampl): pilot amplitude normaliser (Frame.cpp:76-80)
     // ---- radix schedules of the generic (any-size) path: products equal fft_size resp. pf_size ----
     int fft_nr, fft_radix[8];
@@ -52,6 +53,7 @@ struct Params {
     const int16_t *bin_map;      // [fft_size] -1 null, -2 pilot, else data index within the symbol
     const int16_t *data_bin;     // [num_data_subc] bin of data index i
     const int16_t *pilot_bin;    // [num_pilot_subc]
+    const int16_t *bin_role;     // [fft_size] >= 0 data index within the symbol, -1 null, -2 - p pilot number p (big.cuh)
     // ---- one-warp-per-symbol receive kernels of the fft-512 geometry (rx512n.cuh) ----
     // After warp_fft512 lane 2 k1 + g holds mn[i] = X[k1 + 16 i + (g ? 384 : 0)] and ot[i] = X[k1 + 16 i + (g ? 128 : 256)].
     // A COMBINATION is a set of data bins that share (array, g, i, segment): inside it the data index i' (minus 256 in the

@@ -52,7 +52,12 @@ def main():
         frames *= float(s.mult)
         rx_ms = timed(lambda: m.rx_aligned_batch(frames, n_frames=n, frame_stride=s.output_size, offset=s.t2sin_size, out=out, count_ambiguous=False))
         bad = int((out != pay).any(dim=1).sum().item())
-        rows.append({"frames": n, "tx_ms": tx_ms, "rx_ms": rx_ms, "frames_with_errors": bad,
+        m.enable_timing(True)
+        m.rx_aligned_batch(frames, n_frames=n, frame_stride=s.output_size, offset=s.t2sin_size, out=out, count_ambiguous=False)
+        torch.cuda.synchronize()
+        st = m.last_stage_ms()
+        m.enable_timing(False)
+        rows.append({"frames": n, "tx_ms": tx_ms, "rx_ms": rx_ms, "frames_with_errors": bad, "rx_acquire_ms": st["acquire"], "rx_demod_ms": st["demod"],
                      "tx_gbs": tx_bytes * n / tx_ms / 1e6, "rx_gbs": rx_bytes * n / rx_ms / 1e6,
                      "tx_frac": tx_bytes * n / tx_ms / 1e6 / peak, "rx_frac": rx_bytes * n / rx_ms / 1e6 / peak,
                      "rx_msamples_s": n * s.output_size / rx_ms / 1e3})

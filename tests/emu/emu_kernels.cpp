@@ -4,6 +4,7 @@
 #define COFDM_EMU 1
 #include "cuda_emu.h"
 #include "kernels.cuh"
+#include "big.cuh"
 #include "stream.cuh"
 #include "host_consts.hpp"
 
@@ -22,7 +23,7 @@ static void wire(EmuHandle *h) {
     P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
-    P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
+    P.bin_role = T.bin_role.data(); P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
     P.lane_desc = T.lane_desc.data(); P.lane_aux = T.lane_aux.data(); P.acq_desc = T.acq_desc.data(); P.grid_lane = T.grid_lane.data(); P.tx_desc = T.tx_desc.data();
 }
 
@@ -201,8 +202,47 @@ int emu_rx_generic(void *hv, const void *samples, int fmt, int n_frames, long lo
         emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCF32>(P, samples, stride, n_frames, gf.data()); });
         emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCF32>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
     }
-    emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel(P, n_frames, gf.data(), spec.data(), pre.data()); });
+    emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel<false>(P, n_frames, gf.data(), spec.data(), pre.data()); });
     emu::launch(dim3(P.num_symb, n_frames), blk, 0, [&] { gen_demap_kernel(P, n_frames, gf.data(), spec.data(), out, amb, taps); });
+    return 0;
+}
+
+int emu_big_ok(void *h) { return ((EmuHandle *)h)->T.big_ok ? 1 : 0; }
+
+// the fft-4096 path (big.cuh) as launch_rx_big runs it; mode 0: acquisition by the any-size kernels + bridge, 1: big_acquire_kernel.
+// One emulated block of num_symb * 256 threads stands for the cluster of big_demod_kernel.
+int emu_rx_big(void *hv, const void *samples, int fmt, int use_tma, int n_frames, long long stride, int mode, uint8_t *out,
+               unsigned long long *amb, float *scal, float2 *chan, float2 *constell) {
+    auto *h = (EmuHandle *)hv;
+    if (!h->T.big_ok) return -1;
+    const Params P = h->P;
+    const size_t N = P.fft_size, L = P.ofdm_len;
+    RxTaps taps{scal, nullptr, chan, constell, nullptr};
+    const bool want = scal || chan || constell;
+    std::vector<FrameScal> fs(n_frames);
+    if (mode == 0) {
+        std::vector<GenFrame> gf(n_frames);
+        std::vector<float2> spec((size_t)n_frames * N), pre((size_t)n_frames * L);
+        const dim3 blk(kGenThreads);
+        if (fmt == kCI16) {
+            emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCI16>(P, samples, stride, n_frames, gf.data()); });
+            emu::launch(dim3(1, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCI16, true>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
+        } else {
+            emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCF32>(P, samples, stride, n_frames, gf.data()); });
+            emu::launch(dim3(1, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCF32, true>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
+        }
+        emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel<true>(P, n_frames, gf.data(), spec.data(), pre.data()); });
+        emu::launch(dim3((n_frames + 127) / 128), dim3(128), 0, [&] { big_bridge_kernel(P, n_frames, gf.data(), fs.data(), taps); });
+    } else {
+        return -2;
+    }
+    const dim3 grid(n_frames), blk((unsigned)P.num_symb * kBigThreads);
+    const size_t sm = (size_t)P.num_symb * big_smem_bytes();
+#define EMU_BIG(F, T) do { if (want) emu::launch(grid, blk, sm, [&] { big_demod_kernel<F, T, true>(P, samples, stride, n_frames, out, amb, taps, fs.data()); }); \
+                           else emu::launch(grid, blk, sm, [&] { big_demod_kernel<F, T, false>(P, samples, stride, n_frames, out, amb, taps, fs.data()); }); } while (0)
+    if (fmt == kCI16) { if (use_tma) EMU_BIG(kCI16, true); else EMU_BIG(kCI16, false); }
+    else { if (use_tma) EMU_BIG(kCF32, true); else EMU_BIG(kCF32, false); }
+#undef EMU_BIG
     return 0;
 }
 

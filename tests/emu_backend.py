@@ -36,6 +36,8 @@ class EmuModem:
         L.emu_preamble_corr.argtypes = [vp, vp, C.c_int, C.c_longlong, vp, C.c_int, vp, vp]
         L.emu_rx_generic.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong] + [vp] * 5
         L.emu_tx_generic.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.emu_rx_big.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int] + [vp] * 5
+        L.emu_big_ok.argtypes = [vp]
         L.emu_fused_ok.argtypes = [vp]
         L.emu_mod.argtypes = [vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong]
         L.emu_demod.argtypes = [vp, C.c_int, vp, C.c_longlong, vp, C.c_longlong, vp]
@@ -51,6 +53,8 @@ class EmuModem:
         self.use_tma = 1
         L.emu_stream_scan.argtypes = [vp, vp, vp, vp, C.c_int, vp, C.c_int, vp]
         self.fused = bool(L.emu_fused_ok(self.h))
+        self.big = bool(L.emu_big_ok(self.h))         # fft-4096 cluster kernels (big.cuh)
+        self.big_mode = 0
         s.fused_path = 1 if self.fused else 0
 
     def set_pc_plain(self, on):
@@ -113,6 +117,11 @@ class EmuModem:
             assert self.lib.emu_rx_fused512_notaps(self.h, base, fmt, self.use_tma, n_frames, frame_stride, out.ctypes.data,
                                                    amb.ctypes.data if count_ambiguous else None) == 0
             return out, int(amb[0])
+        if not self.fused and self.big:
+            assert self.lib.emu_rx_big(self.h, base, fmt, self.use_tma, n_frames, frame_stride, self.big_mode, out.ctypes.data,
+                                       amb.ctypes.data if count_ambiguous else None, ptrs[0], ptrs[2], ptrs[3]) == 0
+            t.pop("grid"); t.pop("synced")
+            return (out, t, int(amb[0])) if taps else (out, int(amb[0]))
         if not self.fused:
             assert self.lib.emu_rx_generic(self.h, base, fmt, n_frames, frame_stride, out.ctypes.data, amb.ctypes.data,
                                            ptrs[0], ptrs[2], ptrs[3]) == 0

@@ -193,3 +193,21 @@ def test_rx_other_symbol_counts(oracle_lib, tmp_path, ns):
     out, _ = m.rx_aligned_batch(pc.cplx(rec).astype(np.complex64))
     assert np.array_equal(out, np.stack([o.rx_aligned(pc.cplx(r))["bytes"] for r in rec]))
     m.close()
+
+
+def test_big_path_cluster_kernels(cfg_dir, oracle_lib):
+    """BASELINE.json configs[4] (fft 4096, cp 1024, 1920 + 128 sub-carriers, 64-QAM) on the cluster kernels of big.cuh: one
+    emulated block of num_symb x 256 threads stands for the cluster of big_demod_kernel (distributed shared memory = offsets);
+    acquisition by the any-size kernels (mode 0) and by big_acquire_kernel (mode 1)"""
+    o = oracle_lib.Oracle("port", cfg_dir["big"])
+    m = EmuModem(cfg_dir["big"], o.sizes)
+    assert m.big and not m.fused
+    pay, rec = pc.impaired_records(o, 2, seed=8, cfo_max=0.0005, noise=0.5, taps=(1.0,), early=0)
+    for mode in (0,):
+        m.big_mode = mode
+        st = pc.check_rx_against_oracle(m, o, rec, "i16")
+        assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6, (mode, st)
+        out, _ = m.rx_aligned_batch(pc.cplx(rec).astype(np.complex64), count_ambiguous=False)
+        for i in range(len(rec)):
+            r = o.rx_aligned(pc.cplx(rec[i]))
+            pc.assert_bytes_match(out[i], r["bytes"], r["constell"], o.sizes.mod_type, f"big mode {mode} frame {i}")
