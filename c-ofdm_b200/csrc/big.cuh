@@ -280,6 +280,285 @@ big_demod_kernel(const Params P, const void *__restrict__ samples, long long fra
     }
 }
 
+// forward 20-point DFT in place, natural layout: X[k], X[k + 10] = E[k] +- W20^k O[k], E / O = DFT-10 of the even / odd inputs
+COFDM_DEV void ndft20(float2 (&v)[20]) {
+    float2 e[10], o[10];
+#pragma unroll
+    for (int q = 0; q < 10; q++) { e[q] = v[2 * q]; o[q] = v[2 * q + 1]; }
+    ndft10(e);
+    ndft10(o);
+    o[1] = nmul(o[1], make_float2(0.95105651629515353118f, -0.30901699437494739575f));
+    o[2] = nmul(o[2], make_float2(0.80901699437494745126f, -0.58778525229247313710f));
+    o[3] = nmul(o[3], make_float2(0.58778525229247313710f, -0.80901699437494745126f));
+    o[4] = nmul(o[4], make_float2(0.30901699437494745126f, -0.95105651629515353118f));
+    o[5] = make_float2(o[5].y, -o[5].x);                                      // W20^5 = -j
+    o[6] = nmul(o[6], make_float2(-0.30901699437494734024f, -0.95105651629515364220f));
+    o[7] = nmul(o[7], make_float2(-0.58778525229247302608f, -0.80901699437494745126f));
+    o[8] = nmul(o[8], make_float2(-0.80901699437494734024f, -0.58778525229247324813f));
+    o[9] = nmul(o[9], make_float2(-0.95105651629515353118f, -0.30901699437494750677f));
+#pragma unroll
+    for (int k = 0; k < 10; k++) { v[k] = nadd(e[k], o[k]); v[k + 10] = nsub(e[k], o[k]); }
+}
+
+// ================================================================================================================
+// big_acquire_kernel: the preamble of one frame per CTA (256 threads) -> FrameScal.
+//   coarse CFO   pilot_freq_sinh (Frame.hpp:285-337): 5120-point spectrum of the received preamble, CP included, as radix
+//                20 x 16 x 16 (Stockham; first exchange padded 20 -> 21 so that every access is conflict-free; the radix-16
+//                passes have 320 butterflies: 256 + 64), |X|^2, arg-max in the pilot windows -> kc
+//   fine CFO     cp_freq_sinh (:238-263) on the preamble: CP correlation -> theta_0, m_0; rotation; FFT-4096
+//   phase lock   pr_phase_sinh (:265-274): theta = arg sum conj(ref) y over the 5120 rotated samples
+//   channel fit  chan_char_lq (:389-434): ND / 2 phases, the reference's one-step unwrap, the (bug-compatible) line
+// Shared memory: Y (43008 B: first coarse exchange -> |X|^2 -> FFT-4096 exchange) and Z (40960 B: staged preamble -> second
+// coarse exchange -> staged preamble again (second bulk copy, an L2 hit) -> the phases).
+// ================================================================================================================
+constexpr int kBigAcqY = (5120 + 256) * 8, kBigAcqZ = 5120 * 8;
+struct alignas(16) BigAcqShared {
+    float2 red[8];
+    int ksum;
+    int pad_[3];
+    uint64_t mbar[2];
+};
+COFDM_HD constexpr size_t big_acquire_smem_bytes() { return (size_t)kBigAcqY + kBigAcqZ + sizeof(BigAcqShared); }
+
+// one radix-16 Stockham butterfly of a 5120-point transform: bf in [0, 320), Ns = 20 (PASS 1) or 320 (PASS 2)
+template <int PASS>
+COFDM_DEV void big_coarse_bf(const float2 *in, float2 *out, float *mag, const float2 *__restrict__ w5120, int bf) {
+    float2 t[16], w[16];
+    if (PASS == 1) {
+        const int k = bf % 20;
+        const float2 *r = in + bf + bf / 20;                                 // y[bf + 320 q] at slot i + i / 20
+#pragma unroll
+        for (int q = 0; q < 16; q++) t[q] = r[336 * q];
+        npowers15(__ldg(w5120 + 16 * k), w);                                 // W320^{k q}
+#pragma unroll
+        for (int q = 1; q < 16; q++) t[q] = nmul(t[q], w[q]);
+        ndft16(t);
+        float2 *o = out + (bf - k) * 16 + k;
+#pragma unroll
+        for (int q = 0; q < 16; q++) o[20 * q] = t[q];
+    } else {
+#pragma unroll
+        for (int q = 0; q < 16; q++) t[q] = in[bf + 320 * q];
+        npowers15(__ldg(w5120 + bf), w);                                     // W5120^{bf q}
+#pragma unroll
+        for (int q = 1; q < 16; q++) t[q] = nmul(t[q], w[q]);
+        ndft16(t);
+#pragma unroll
+        for (int q = 0; q < 16; q++) { const float2 sq = p_mul(t[q], t[q]); mag[bf + 320 * q] = sq.x + sq.y; }
+    }
+}
+
+template <int FMT, bool USE_TMA, bool TAPS>
+__global__ void __launch_bounds__(kBigThreads, 2)
+big_acquire_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
+                   const RxTaps taps, FrameScal *__restrict__ fscal) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int frame = blockIdx.x;
+    if (frame >= n_frames) return;
+    float2 *Y = reinterpret_cast<float2 *>(smem_raw);
+    unsigned char *Zb = reinterpret_cast<unsigned char *>(smem_raw) + kBigAcqY;
+    float2 *Z = reinterpret_cast<float2 *>(Zb);
+    BigAcqShared *M = reinterpret_cast<BigAcqShared *>(Zb + kBigAcqZ);
+    const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
+    const char *src = reinterpret_cast<const char *>(samples) + (size_t)frame * (size_t)frame_stride * sample_bytes;
+    auto stage_issue = [&](int which) {
+        if (USE_TMA) {
+            if (tid == 0) {
+                mbar_init(&M->mbar[which], 1);
+                mbar_fence_init();
+                mbar_arrive_expect_tx(&M->mbar[which], kBigL * (unsigned)sample_bytes);
+                tma_load_1d(Zb, src, kBigL * (unsigned)sample_bytes, &M->mbar[which]);
+            }
+        } else {
+            if (FMT == kCI16) for (int i = tid; i < kBigL; i += kBigThreads) reinterpret_cast<unsigned *>(Zb)[i] = __ldg(reinterpret_cast<const unsigned *>(src) + i);
+            else for (int i = tid; i < kBigL; i += kBigThreads) Z[i] = __ldg(reinterpret_cast<const float2 *>(src) + i);
+        }
+    };
+    stage_issue(0);
+    if (tid == 0) M->ksum = 0;
+    __syncthreads();
+    if (USE_TMA) mbar_wait(&M->mbar[0], 0);
+
+    // ================= coarse CFO + the preamble's CP correlation =================
+    float2 cc;
+    {
+        float2 t[20];
+#pragma unroll
+        for (int u = 0; u < 20; u++) t[u] = staged_at<FMT>(Zb, tid + 256 * u);
+        // CP sample j = tid + 256 c pairs with sample j + 4096 (u = 16 + c)  (Frame.hpp:251-253)
+        cc = nmac_conj(nmac_conj(make_float2(0.f, 0.f), t[0], t[16]), t[1], t[17]);
+        cc = nmac_conj(nmac_conj(cc, t[2], t[18]), t[3], t[19]);
+        ndft20(t);
+#pragma unroll
+        for (int u = 0; u < 20; u++) Y[21 * tid + u] = t[u];                  // y[20 j + u] at slot i + i / 20
+    }
+    cc = warp_sum(cc);
+    if (lane == 0) M->red[warp] = cc;
+    __syncthreads();
+    big_coarse_bf<1>(Y, Z, nullptr, P.tw_pf, tid);
+    if (tid < 64) big_coarse_bf<1>(Y, Z, nullptr, P.tw_pf, tid + 256);
+    __syncthreads();
+    float *mag = reinterpret_cast<float *>(Y);
+    big_coarse_bf<2>(Z, nullptr, mag, P.tw_pf, tid);
+    if (tid < 64) big_coarse_bf<2>(Z, nullptr, mag, P.tw_pf, tid + 256);
+    __syncthreads();
+    stage_issue(1);                                                           // the raw preamble again (Z is free; the copy hits L2)
+    {
+        // arg-max of |spectrum| in the pilot windows, first maximum wins (Frame.hpp:311-331); window np/2 (DC) is skipped
+        const int np = P.num_pilot_subc, half = P.pf_size / 2;
+        int acc = 0;
+        for (int wi = warp; wi < np; wi += kBigThreads / 32) {
+            const int win = wi < np / 2 ? wi : wi + 1;
+            int lo = P.pf_border0 + win * P.pf_pilot_w;
+            const int hi = lo + P.pf_pilot_w;
+            if (win == 0 && lo < 0) lo = 0;
+            float best = -1.0f;
+            int besti = 0x7fffffff;
+            for (int ks = lo + lane; ks < hi; ks += 32) {
+                const float mv = mag[ks < half ? ks + half : ks - half];
+                if (mv > best) { best = mv; besti = ks; }
+            }
+            const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(best, 0.0f)));
+            acc += __reduce_min_sync(0xffffffffu, (best >= 0.0f && __float_as_uint(best) == mx) ? besti : 0x7fffffff);
+        }
+        if (lane == 0) atomicAdd(&M->ksum, acc);
+    }
+    __syncthreads();
+    if (USE_TMA) mbar_wait(&M->mbar[1], 0);
+    const int kc = M->ksum - P.num_pilot_subc * (P.pf_size / 2);              // shift = kc / pf_den (Frame.hpp:332-334)
+    cc = M->red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) cc = nadd(cc, M->red[w]);
+    const float theta0 = fast_atan2_turns(cc.y, cc.x);
+    const int m0 = (int)ceilf(-(theta0 - (float)kc * P.pf_binsN) - 0.5f);
+
+    // ================= rotation, pr_phase_sinh partial sums, FFT-4096 =================
+    float2 v[16];
+    float2 z = make_float2(0.f, 0.f);
+    {
+        float2 rp[16];
+        npowers15(big_phasor(theta0, m0, 256), rp);
+        const float2 pl = big_phasor(theta0, m0, kBigCP + tid);
+#pragma unroll
+        for (int c = 0; c < 4; c++) {
+            // CP sample j = tid + 256 c: exp(-j 2 pi beta j / 4096) = P(tid) conj(R^(4 - c))
+            const float2 y = nmul(nmulc(staged_at<FMT>(Zb, tid + 256 * c), rp[4 - c]), pl);
+            z = nmac_conj(z, __ldg(&P.preamble_td[tid + 256 * c]), y);
+        }
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            v[u] = nmul(staged_at<FMT>(Zb, kBigCP + tid + 256 * u), pl);
+            if (u) v[u] = nmul(v[u], rp[u]);
+            z = nmac_conj(z, __ldg(&P.preamble_td[kBigCP + tid + 256 * u]), v[u]);
+        }
+    }
+    z = warp_sum(z);
+    __syncthreads();                                                          // red[] and mag have been read by everybody
+    if (lane == 0) M->red[warp] = z;
+    auto sync = [&]() { __syncthreads(); };
+    cta_fft4096(v, Y, P.tw_fft, tid, sync);                                   // (its first barrier also publishes red[])
+    z = M->red[0];
+#pragma unroll
+    for (int w = 1; w < 8; w++) z = nadd(z, M->red[w]);
+    const float inv = rsqrtf(fmaxf(cnorm2(z), 1e-30f));
+    const float2 rot = make_float2(z.x * inv, -z.y * inv);                    // exp(-j theta)
+    const float theta = TAPS ? atan2f(z.y, z.x) : 0.f;
+
+    // ================= chan_char_lq: phase[i] = arg(pr[i] / mod_preamble[i]), i < ND / 2 (Frame.hpp:403-405) =================
+    const float TWO_PI_F = 6.28318530717958647692f, PI_F = 3.14159265358979323846f;
+    const int nph = P.num_data_subc / 2;
+    float *phs = reinterpret_cast<float *>(Zb);                              // the staged preamble has been consumed (barriers of the FFT)
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const int role = (int)__ldg(&P.bin_role[tid + 256 * t]);
+        if (role >= 0 && role < nph) {
+            const float2 d = nmulc(nmul(v[t], rot), __ldg(&P.mod_preamble[role]));
+            phs[role] = fast_atan2_turns(d.y, d.x) * TWO_PI_F;
+        }
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    // one-step unwrap (Frame.hpp:407-414) and the sums of Frame.hpp:416-421 by one warp: lane l owns elements [l E, (l + 1) E).
+    // The adjustment is a 3-state chain (state = multiple of 2 pi carried by the previous element).
+    const int E = (nph + 31) / 32, i0 = lane * E, i1 = min(nph, i0 + E);
+    const float prev_raw = i0 > 0 && i0 < nph ? phs[i0 - 1] : 0.f;
+    bool jump = false;
+    {
+        float pv = prev_raw;
+        for (int i = i0; i < i1; i++) { const float p = phs[i]; if (i > 0 && fabsf(p - pv) > PI_F) jump = true; pv = p; }
+    }
+    const bool any = __ballot_sync(0xffffffffu, jump) != 0u;
+    int cstart = 0;                                                           // state entering this lane's range
+    if (any) {
+        unsigned map = 0;
+        for (int cin = 0; cin < 3; cin++) {
+            int cs = cin - 1;
+            float pv = prev_raw;
+            for (int i = i0; i < i1; i++) {
+                const float p = phs[i];
+                if (i == 0) { cs = 0; pv = p; continue; }
+                const float dlt = p - (pv + (float)cs * TWO_PI_F);
+                cs = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                pv = p;
+            }
+            map |= (unsigned)(cs + 1) << (2 * cin);
+        }
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
+            if (lane >= o) {
+                unsigned comp = 0;
+#pragma unroll
+                for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
+                map = comp;
+            }
+        }
+        const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
+        cstart = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;            // the chain starts in state 0 (entry [1] of the composed map)
+    }
+    double ssy = 0.0, ssxy = 0.0;
+    {
+        int cs = cstart;
+        float pv = prev_raw;
+        for (int i = i0; i < i1; i++) {
+            const float p = phs[i];
+            float val = p;
+            if (i > 0) {
+                const float dlt = p - (pv + (float)cs * TWO_PI_F);
+                cs = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                val = p + (float)cs * TWO_PI_F;
+            } else {
+                cs = 0;
+            }
+            pv = p;
+            ssy += (double)val;
+            ssxy += (double)val * (double)i;
+        }
+    }
+    const double tsy = warp_sum(ssy), tsxy = warp_sum(ssxy);
+    const double n = (double)nph, sx1 = n * (n - 1.0) / 2.0, sx2 = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
+    const double lb = (tsxy - sx1 * tsy) / (sx2 - sx1 * sx1);               // Frame.hpp:422 (sums, not means)
+    const double la = tsy - lb * sx1;                                        // Frame.hpp:423
+    if (lane == 0) {
+        FrameScal f;
+        f.kc = kc; f.m0 = m0; f.th0 = theta0; f.theta = theta; f.rot_theta = rot; f.a = la; f.b = lb;
+        fscal[frame] = f;
+    }
+    if (TAPS) {
+        if (taps.scal != nullptr && lane == 0) {
+            float *sc = taps.scal + (size_t)frame * 48;
+            sc[0] = (float)((double)kc / (double)P.pf_den); sc[1] = (float)la; sc[2] = (float)lb; sc[3] = theta;
+            sc[5] = (float)kc; sc[6] = 0.f; sc[7] = 0.f; sc[16] = (float)m0; sc[32] = theta0;
+        }
+        if (taps.chan != nullptr) {
+            const int ND = P.num_data_subc;
+            for (int i = lane; i < ND; i += 32)
+                taps.chan[(size_t)frame * ND + i] = cis_turns((lb * (double)(i < nph ? i : i - ND) + la) * 0.15915494309189533577);
+        }
+    }
+}
+
 // Bridge: the any-size path's per-frame record (generic.cuh GenFrame) -> FrameScal, so that big_demod_kernel can run behind
 // the any-size acquisition kernels (COFDM_BIG_ACQUIRE=0).  th0 carries theta_0 + m_0 whole (m0 = 0).
 __global__ void big_bridge_kernel(const Params P, int n_frames, const GenFrame *__restrict__ gf, FrameScal *__restrict__ fscal, const RxTaps taps) {

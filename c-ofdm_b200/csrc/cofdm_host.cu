@@ -83,6 +83,7 @@ struct cofdm {
     // chunks on different streams, so chunk c + 1's first kernel must not overwrite what chunk c's last kernel still reads
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
     DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
+    int big_acquire = 1;                         // ... including their own acquisition kernel (env COFDM_BIG_ACQUIRE=0: the any-size kernels + bridge)
     int big_on = 1;                              // fft-4096 configurations use the cluster kernels of big.cuh (env COFDM_BIG=0: the any-size path)
     int tx_ctas = 148 * 4;                       // CTAs of the persistent tx kernel (SMs x resident CTAs per SM, measured at create)
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
@@ -235,7 +236,14 @@ int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_
     CU_TRY(h->fscal[slot].reserve(n_frames * sizeof(FrameScal)));
     FrameScal *fsc = (FrameScal *)h->fscal[slot].p;
     if (h->timing) { collect_rx_stage(h); cudaEventRecord(h->sev[0], st); }
-    {
+    if (h->big_acquire) {
+#define COFDM_BACQ(F, T) do { if (want) big_acquire_kernel<F, T, true><<<(unsigned)n_frames, kBigThreads, big_acquire_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc); \
+                              else big_acquire_kernel<F, T, false><<<(unsigned)n_frames, kBigThreads, big_acquire_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc); } while (0)
+        if (fmt == COFDM_CI16) { if (al) COFDM_BACQ(kCI16, true); else COFDM_BACQ(kCI16, false); }
+        else { if (al) COFDM_BACQ(kCF32, true); else COFDM_BACQ(kCF32, false); }
+#undef COFDM_BACQ
+        if (int rc = check_launch(h, "big_acquire")) return rc;
+    } else {
         // acquisition by the any-size kernels on the preamble only (sub-batches bound their scratch memory)
         const size_t sub = 4096, nb = std::min(sub, n_frames);
         CU_TRY(h->gen_frames[slot].reserve(nb * sizeof(GenFrame)));
@@ -528,6 +536,15 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             if (bg) h->big_on = std::atoi(bg) != 0;
             cudaFuncSetAttribute(gen_symbol_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
             cudaFuncSetAttribute(gen_symbol_kernel<kCI16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
+            const char *ba = std::getenv("COFDM_BIG_ACQUIRE");
+            if (ba) h->big_acquire = std::atoi(ba) != 0;
+            const int sma = (int)big_acquire_smem_bytes();
+#define COFDM_BACQ_ATTR(F, T, W) \
+            cudaFuncSetAttribute(big_acquire_kernel<F, T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, sma); \
+            cudaFuncSetAttribute(big_acquire_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+            COFDM_BACQ_ATTR(kCF32, true, true); COFDM_BACQ_ATTR(kCF32, true, false); COFDM_BACQ_ATTR(kCF32, false, true); COFDM_BACQ_ATTR(kCF32, false, false);
+            COFDM_BACQ_ATTR(kCI16, true, true); COFDM_BACQ_ATTR(kCI16, true, false); COFDM_BACQ_ATTR(kCI16, false, true); COFDM_BACQ_ATTR(kCI16, false, false);
+#undef COFDM_BACQ_ATTR
             const int smb = (int)big_smem_bytes();
 #define COFDM_BIG_ATTR(F, T, W) \
             cudaFuncSetAttribute(big_demod_kernel<F, T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \

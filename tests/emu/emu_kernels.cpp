@@ -234,7 +234,13 @@ int emu_rx_big(void *hv, const void *samples, int fmt, int use_tma, int n_frames
         emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel<true>(P, n_frames, gf.data(), spec.data(), pre.data()); });
         emu::launch(dim3((n_frames + 127) / 128), dim3(128), 0, [&] { big_bridge_kernel(P, n_frames, gf.data(), fs.data(), taps); });
     } else {
-        return -2;
+        const dim3 g1(n_frames), b1(kBigThreads);
+        const size_t sma = big_acquire_smem_bytes();
+#define EMU_BACQ(F, T) do { if (want) emu::launch(g1, b1, sma, [&] { big_acquire_kernel<F, T, true>(P, samples, stride, n_frames, taps, fs.data()); }); \
+                            else emu::launch(g1, b1, sma, [&] { big_acquire_kernel<F, T, false>(P, samples, stride, n_frames, taps, fs.data()); }); } while (0)
+        if (fmt == kCI16) { if (use_tma) EMU_BACQ(kCI16, true); else EMU_BACQ(kCI16, false); }
+        else { if (use_tma) EMU_BACQ(kCF32, true); else EMU_BACQ(kCF32, false); }
+#undef EMU_BACQ
     }
     const dim3 grid(n_frames), blk((unsigned)P.num_symb * kBigThreads);
     const size_t sm = (size_t)P.num_symb * big_smem_bytes();

@@ -203,7 +203,7 @@ def test_big_path_cluster_kernels(cfg_dir, oracle_lib):
     m = EmuModem(cfg_dir["big"], o.sizes)
     assert m.big and not m.fused
     pay, rec = pc.impaired_records(o, 2, seed=8, cfo_max=0.0005, noise=0.5, taps=(1.0,), early=0)
-    for mode in (0,):
+    for mode in (0, 1):
         m.big_mode = mode
         st = pc.check_rx_against_oracle(m, o, rec, "i16")
         assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6, (mode, st)
@@ -211,3 +211,14 @@ def test_big_path_cluster_kernels(cfg_dir, oracle_lib):
         for i in range(len(rec)):
             r = o.rx_aligned(pc.cplx(rec[i]))
             pc.assert_bytes_match(out[i], r["bytes"], r["constell"], o.sizes.mod_type, f"big mode {mode} frame {i}")
+
+
+def test_big_path_phase_unwrap_slow_path(cfg_dir, oracle_lib):
+    """a frame cut 6 samples early: the preamble's phases run over several turns, so chan_char_lq's one-step unwrap
+    (Frame.hpp:407-414) takes the acquire kernel's 3-state scan path; multipath and a larger CFO on top"""
+    o = oracle_lib.Oracle("port", cfg_dir["big"])
+    m = EmuModem(cfg_dir["big"], o.sizes)
+    m.big_mode = 1
+    pay, rec = pc.impaired_records(o, 2, seed=21, cfo_max=0.002, noise=0.5, taps=(1.0, 0.1j), early=6)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6 and st["chan"] < 5e-6, st
