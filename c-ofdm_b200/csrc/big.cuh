@@ -38,7 +38,8 @@ static_assert(kBigExchSlots * 8 <= kBigStageBytes, "the exchange must fit the st
 struct alignas(16) BigShared {
     float2 pil[kMaxPilots];          // this symbol's pilot bins
     float2 wseg[kMaxPilots];         // segment coefficients
-    float2 red[8];                   // per-warp partial sums
+    float2 red[8];                   // per-warp partial sums (CP correlation)
+    float psum[8];                   // per-warp partial sums (pilot amplitudes)
     float pabs;                      // sum |pilot| of this symbol (read by the other CTAs of the cluster)
     float pad_[3];
     uint64_t mbar;
@@ -63,6 +64,9 @@ COFDM_DEV BigCtx big_ctx() {
 }
 COFDM_DEV void big_cta_sync(const BigCtx &c) { emu::named_barrier(1 + c.rank, kBigThreads); }
 COFDM_DEV void big_cluster_sync(const BigCtx &) { __syncthreads(); }
+COFDM_DEV void big_cluster_arrive(const BigCtx &) {}
+COFDM_DEV void big_cluster_arrive_relaxed(const BigCtx &) {}
+COFDM_DEV void big_cluster_wait(const BigCtx &) { __syncthreads(); }
 template <class T> COFDM_DEV const T *big_remote(const BigCtx &c, const T *p, int r) {
     return reinterpret_cast<const T *>(reinterpret_cast<const unsigned char *>(p) + ((long)r - (long)c.rank) * (long)big_smem_bytes());
 }
@@ -79,6 +83,12 @@ COFDM_DEV BigCtx big_ctx() {
 }
 COFDM_DEV void big_cta_sync(const BigCtx &) { __syncthreads(); }
 COFDM_DEV void big_cluster_sync(const BigCtx &) { cooperative_groups::this_cluster().sync(); }
+// split cluster barrier: arrive (release: this thread's shared-memory writes become visible to the cluster) ... independent
+// work ... wait (acquire).  The relaxed form orders nothing: it only keeps a CTA's shared memory alive until every CTA of the
+// cluster has stopped reading it.
+COFDM_DEV void big_cluster_arrive(const BigCtx &) { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+COFDM_DEV void big_cluster_arrive_relaxed(const BigCtx &) { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
+COFDM_DEV void big_cluster_wait(const BigCtx &) { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
 template <class T> COFDM_DEV const T *big_remote(const BigCtx &, const T *p, int r) {
     return cooperative_groups::this_cluster().map_shared_rank(p, r);
 }
@@ -102,8 +112,12 @@ COFDM_DEV float2 big_phasor(float theta, int m, int J) {
 // E: kBigExchSlots float2 of shared memory nobody else touches; SYNC(): the CTA barrier.  w256 / w4096: global tables
 // exp(-j 2 pi k / 256), exp(-j 2 pi k / 4096).  Stockham autosort passes (radix 16, Ns = 1, 16, 256):
 //   pass p: thread j, k = j mod Ns: in[j + 256 t] * W_{16 Ns}^{k t} -> DFT-16 -> out[(j - k) 16 + k + Ns t'].
-template <class SYNC>
-COFDM_DEV void cta_fft4096(float2 (&v)[16], float2 *E, const float2 *__restrict__ w4096, int j, SYNC sync) {
+// ROT: the inputs of thread j' still lack a factor F(j') = pq_base * step16^(j' >> 4) ... supplied by the caller as
+// (f0, fstep): register t of the pass-1 reader j comes from writer (j >> 4) + 16 t, whose factor is f0 * fstep^t; it rides on
+// the pass-1 twiddle chain (one sequential product per register instead of a power table + a separate rotation).
+template <bool ROT, class SYNC>
+COFDM_DEV void cta_fft4096(float2 (&v)[16], float2 *E, const float2 *__restrict__ w4096, int j, SYNC sync,
+                           float2 f0 = make_float2(1.f, 0.f), float2 fstep = make_float2(1.f, 0.f)) {
     ndft16(v);
 #pragma unroll
     for (int t = 0; t < 16; t++) E[17 * j + t] = v[t];                       // y[16 j + t] at slot i + (i >> 4)
@@ -112,10 +126,18 @@ COFDM_DEV void cta_fft4096(float2 (&v)[16], float2 *E, const float2 *__restrict_
         const float2 *r = E + j + (j >> 4);
 #pragma unroll
         for (int t = 0; t < 16; t++) v[t] = r[272 * t];                      // y[j + 256 t]
-        float2 w[16];
-        npowers15(__ldg(w4096 + 16 * (j & 15)), w);                          // W256^{(j mod 16) t}
+        if (ROT) {
+            const float2 stp = nmul(__ldg(w4096 + 16 * (j & 15)), fstep);    // W256^{j mod 16} * fstep
+            float2 g = f0;
+            v[0] = nmul(v[0], g);
 #pragma unroll
-        for (int t = 1; t < 16; t++) v[t] = nmul(v[t], w[t]);
+            for (int t = 1; t < 16; t++) { g = nmul(g, stp); v[t] = nmul(v[t], g); }
+        } else {
+            float2 w[16];
+            npowers15(__ldg(w4096 + 16 * (j & 15)), w);                      // W256^{(j mod 16) t}
+#pragma unroll
+            for (int t = 1; t < 16; t++) v[t] = nmul(v[t], w[t]);
+        }
     }
     ndft16(v);
     sync();                                                                  // everybody has read the first exchange
@@ -140,7 +162,8 @@ COFDM_DEV void cta_fft4096(float2 (&v)[16], float2 *E, const float2 *__restrict_
 // big_demod_kernel: see the head of this file.  Launched with cluster dimension num_symb (<= 8); grid = n_frames * num_symb.
 // P.bin_role[k]: >= 0 data index, -1 null, -2 - p pilot number p.
 // ================================================================================================================
-template <int FMT, bool USE_TMA, bool TAPS>
+// MOD: modulation order the instance is specialised for (6), or 0 = any (read from the configuration)
+template <int FMT, bool USE_TMA, bool TAPS, int MOD>
 __global__ void __launch_bounds__(kBigThreads, 4)
 big_demod_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
                  uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous, const RxTaps taps,
@@ -191,71 +214,102 @@ big_demod_kernel(const Params P, const void *__restrict__ samples, long long fra
     const int m = (int)ceilf(-(theta - (float)fs.kc * P.pf_binsN) - 0.5f);
 
     // ---- rotation x[n] *= exp(-j 2 pi (theta + m) n / 4096), n = 1024 + tid + 256 u: P(tid) R^u ----
+    //      R^u is applied here; P rides on the pass-1 twiddles of the thread that reads this thread's pass-0 outputs: reader j gets
+    //      register t from writer (j >> 4) + 16 t, i.e. the factor P((j >> 4)) * P-step^t with P-step = exp(-j 2 pi beta 16 / 4096)
     {
-        float2 rp[16];
-        npowers15(big_phasor(theta, m, 256), rp);
-        const float2 pl = big_phasor(theta, m, kBigCP + tid);
-        v[0] = nmul(v[0], pl);
+        const float2 R = big_phasor(theta, m, 256);
+        float2 g = R;
+        v[1] = nmul(v[1], g);
 #pragma unroll
-        for (int u = 1; u < 16; u++) v[u] = nmul(nmul(v[u], rp[u]), pl);
+        for (int u = 2; u < 16; u++) { g = nmul(g, R); v[u] = nmul(v[u], g); }
     }
-    cta_fft4096(v, reinterpret_cast<float2 *>(stage), P.tw_fft, tid, sync);
+    cta_fft4096<true>(v, reinterpret_cast<float2 *>(stage), P.tw_fft, tid, sync, big_phasor(theta, m, kBigCP + (tid >> 4)), big_phasor(theta, m, 16));
     // now v[t] = X[tid + 256 t] of the rotated symbol (constant phase Psi_s still on it: it cancels against the segment pilot)
 
-    // ---- pilots and sum |pilot| (Frame.cpp:76-80) ----
+    // ---- the thread's 16 roles (bins tid + 256 t), two 128-bit loads: int16 each, >= 0 data index, -1 null, -2 - p pilot p ----
+    const uint4 ra = __ldg(&P.big_roles[2 * tid]), rb = __ldg(&P.big_roles[2 * tid + 1]);
+    const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+#define COFDM_ROLE(t) ((int)(short)((rw[(t) >> 1] >> (16 * ((t) & 1))) & 0xffffu))
+    const unsigned tmask = (unsigned)P.big_tmask;                 // rows t in which ANY thread holds a used bin (uniform)
+    // ---- pilots and sum |pilot| (Frame.cpp:76-80): only the few threads whose bins are pilots enter ----
     float pm = 0.f;
+    if (((ra.x | ra.y | ra.z | ra.w | rb.x | rb.y | rb.z | rb.w) & 0x80008000u) != 0u) {
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-        const int role = (int)__ldg(&P.bin_role[tid + 256 * t]);
-        if (role <= -2) { M->pil[-2 - role] = v[t]; pm += sqrtf(cnorm2(v[t])); }
+        for (int t = 0; t < 16; t++) {
+            if (!((tmask >> t) & 1u)) continue;
+            const int role = COFDM_ROLE(t);
+            if (role <= -2) {
+                M->pil[-2 - role] = v[t];
+                const float n2 = cnorm2(v[t]);
+                pm = fmaf(n2, rsqrtf(fmaxf(n2, 1e-30f)), pm);      // |pilot| (2 ulp: it enters g, a sum of 1024 terms)
+            }
+        }
     }
     pm = warp_sum(pm);
-    sync();                                                       // red[] has been read by everybody
-    if (lane == 0) M->red[warp].x = pm;
-    sync();
+    if (lane == 0) M->psum[warp] = pm;
+    sync();                                                       // pil[] and psum[] complete
     if (tid == 0) {
         float tot = 0.f;
-        for (int w = 0; w < 8; w++) tot += M->red[w].x;
-        M->pabs = tot;
+        for (int w = 0; w < 8; w++) tot += M->psum[w];
+        M->pabs = tot;                                            // (published by this thread's own arrive.release)
     }
-    big_cluster_sync(cx);                                         // pilots and pabs of every symbol of the frame are published
-
-    // ---- frame-wide: g (Frame.cpp:76-80) and the segment coefficients W[e] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) c_1,
-    //      c_1 = exp(-j 2 pi Psi_1) exp(-j theta_pr), Psi_1 = 1.25 (theta_0 + m_0) mod 1 (Frame.cpp:89-92 + rx.cpp:214-216) ----
-    float g = 0.f;
-    for (int r = 0; r < cx.nrank; r++) g += *big_remote(cx, &M->pabs, r);
-    g *= P.inv_pilot_norm;
-    if (tid < P.num_pilot_subc) {
+    big_cluster_arrive(cx);                                       // this symbol's pilots and pabs are published
+    const int ND = P.num_data_subc, nw = cx.nrank;
+    const float bt = (float)(fs.b * 0.15915494309189533577), at0 = (float)(fs.a * 0.15915494309189533577 - rint(fs.a * 0.15915494309189533577));
+    const int dstep = P.big_dstep;
+    const float2 hstep = cis_neg_turns_f(bt * (float)dstep);
+    float c1x, c1y;
+    {
+        // c_1 = exp(-j 2 pi Psi_1) exp(-j theta_pr), Psi_1 = 1.25 (theta_0 + m_0) mod 1
         float acc = fs.th0 * 1.25f;
         acc -= rintf(acc);
         const float psi1 = acc + (float)((5 * fs.m0) & 3) * 0.25f;
         const float2 c1 = nmul(cis_neg_turns_f(psi1), fs.rot_theta);
+        c1x = c1.x; c1y = c1.y;
+    }
+    big_cluster_wait(cx);                                         // pilots and pabs of every symbol of the frame are visible
+
+    // ---- frame-wide: g (Frame.cpp:76-80) and the segment coefficients W[e] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) c_1 (Frame.cpp:89-92) ----
+    float g = 0.f;
+    for (int r = 0; r < cx.nrank; r++) g += *big_remote(cx, &M->pabs, r);
+    g *= P.inv_pilot_norm;
+    if (tid < P.num_pilot_subc) {
         const float2 p1 = big_remote(cx, M->pil, 0)[tid], ps = M->pil[tid];
         const float2 w = nscale(nmulc(p1, ps), __fdividef(1.0f, cnorm2(ps) * g));
-        M->wseg[tid] = nmul(w, c1);
+        M->wseg[tid] = nmul(w, make_float2(c1x, c1y));
     }
-    big_cluster_sync(cx);                                         // wseg visible; nobody reads remote shared memory after this point
+    big_cluster_arrive_relaxed(cx);                               // this CTA reads no remote shared memory from here on (waited for at the end)
+    sync();                                                       // wseg visible
 
-    // ---- equalise + hard demap (modulation.cpp:53-87) straight from the registers ----
-    const int ND = P.num_data_subc, nw = cx.nrank;
+    // ---- equaliser exp(-j (b i' + a)), i' = i (i < ND / 2) or i - ND (rx.cpp:214-216, Frame.hpp:425-430), segment correction and
+    //      hard demap (modulation.cpp:53-87) straight from the registers.  A thread's data indices advance by a constant step from
+    //      row to row (big_dstep, e.g. 240 = 256 * 15 / 16): the phasor of the next row is the previous one times exp(-j b step);
+    //      any other step is evaluated directly. ----
     const DemapK dk = make_demapk(P.mod_type);
-    const float bt = (float)(fs.b * 0.15915494309189533577), at0 = (float)(fs.a * 0.15915494309189533577 - rint(fs.a * 0.15915494309189533577));
     const float inv_seg = 1.0f / (float)P.seg_size;
     float2 *ctap = (TAPS && taps.constell != nullptr) ? taps.constell + ((size_t)frame * nw + (s - 1)) * ND : nullptr;
     int n_amb = 0;
+    {
+        float2 hc = make_float2(1.f, 0.f);
+        int prev_ip = -0x40000000;
 #pragma unroll
-    for (int t = 0; t < 16; t++) {
-        const int role = (int)__ldg(&P.bin_role[tid + 256 * t]);
-        if (role >= 0) {
-            const int e = (int)(((float)role + 0.5f) * inv_seg);
-            const int ip = role < (ND >> 1) ? role : role - ND;                   // Frame.hpp:425-430
-            const float2 hc = cis_neg_turns_f(fmaf(bt, (float)ip, at0));
-            const float2 z = nmul(nmul(v[t], M->wseg[e]), hc);
-            if (TAPS && ctap != nullptr) ctap[role] = z;
-            M->sb[role] = (uint8_t)demap_n<0>(z, dk);
-            if (ambiguous != nullptr) n_amb += demap_ambiguous(z, dk) ? 1 : 0;
+        for (int t = 0; t < 16; t++) {
+            if (!((tmask >> t) & 1u)) continue;
+            const int role = COFDM_ROLE(t);
+            if (role >= 0) {
+                const int ip = role < (ND >> 1) ? role : role - ND;
+                if (ip - prev_ip == dstep) hc = nmul(hc, hstep);
+                else hc = cis_neg_turns_f(fmaf(bt, (float)ip, at0));
+                prev_ip = ip;
+                const int e = (int)(((float)role + 0.5f) * inv_seg);
+                const float2 z = nmul(nmul(v[t], hc), M->wseg[e]);
+                if (TAPS && ctap != nullptr) ctap[role] = z;
+                M->sb[role] = (uint8_t)demap_n<MOD>(z, dk);
+                if (ambiguous != nullptr) n_amb += demap_ambiguous(z, dk) ? 1 : 0;
+            }
         }
     }
+#undef COFDM_ROLE
     if (ambiguous != nullptr) {
         n_amb = (int)warp_sum((float)n_amb);
         if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
@@ -268,16 +322,28 @@ big_demod_kernel(const Params P, const void *__restrict__ samples, long long fra
     sync();
     // ---- pack: 8 consecutive symbols of `mod` bits = `mod` whole bytes, MSB first (modulation.cpp:90-125) ----
     {
-        const int mod = P.mod_type;
+        const int mod = MOD ? MOD : P.mod_type;
         uint8_t *dst = out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - 1) * (size_t)(ND * mod / 8);
         for (int grp = tid; grp < ND / 8; grp += kBigThreads) {
             const uint2 raw = *reinterpret_cast<const uint2 *>(M->sb + 8 * grp);
-            unsigned long long bits = 0;
+            if (MOD == 6 && (reinterpret_cast<uintptr_t>(dst) & 1) == 0) {
+                // 64-QAM: 8 symbols of 6 bits = 3 big-endian 16-bit words
+                const unsigned s0 = raw.x & 63u, s1 = (raw.x >> 8) & 63u, s2 = (raw.x >> 16) & 63u, s3 = raw.x >> 24;
+                const unsigned s4 = raw.y & 63u, s5 = (raw.y >> 8) & 63u, s6 = (raw.y >> 16) & 63u, s7 = raw.y >> 24;
+                const unsigned w0 = (s0 << 10) | (s1 << 4) | (s2 >> 2), w1 = ((s2 & 3u) << 14) | (s3 << 8) | (s4 << 2) | (s5 >> 4),
+                               w2 = ((s5 & 15u) << 12) | (s6 << 6) | s7;
+                unsigned short *d16 = reinterpret_cast<unsigned short *>(dst + (size_t)grp * 6);
+                d16[0] = (unsigned short)((w0 >> 8) | ((w0 & 0xffu) << 8)); d16[1] = (unsigned short)((w1 >> 8) | ((w1 & 0xffu) << 8));
+                d16[2] = (unsigned short)((w2 >> 8) | ((w2 & 0xffu) << 8));
+            } else {
+                unsigned long long bits = 0;
 #pragma unroll
-            for (int e = 0; e < 8; e++) bits = (bits << mod) | (unsigned long long)(((e < 4 ? raw.x : raw.y) >> (8 * (e & 3))) & 0xffu);
-            for (int bq = 0; bq < mod; bq++) dst[(size_t)grp * mod + bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
+                for (int e = 0; e < 8; e++) bits = (bits << mod) | (unsigned long long)(((e < 4 ? raw.x : raw.y) >> (8 * (e & 3))) & 0xffu);
+                for (int bq = 0; bq < mod; bq++) dst[(size_t)grp * mod + bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
+            }
         }
     }
+    big_cluster_wait(cx);                                         // nobody reads this CTA's shared memory any more
 }
 
 // forward 20-point DFT in place, natural layout: X[k], X[k + 10] = E[k] +- W20^k O[k], E / O = DFT-10 of the even / odd inputs
@@ -457,7 +523,7 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
     __syncthreads();                                                          // red[] and mag have been read by everybody
     if (lane == 0) M->red[warp] = z;
     auto sync = [&]() { __syncthreads(); };
-    cta_fft4096(v, Y, P.tw_fft, tid, sync);                                   // (its first barrier also publishes red[])
+    cta_fft4096<false>(v, Y, P.tw_fft, tid, sync);                            // (its first barrier also publishes red[])
     z = M->red[0];
 #pragma unroll
     for (int w = 1; w < 8; w++) z = nadd(z, M->red[w]);

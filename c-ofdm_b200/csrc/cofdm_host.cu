@@ -208,7 +208,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 }
 
 // the fft-4096 path (big.cuh): acquisition -> FrameScal, then one cluster of num_symb CTAs per frame
-template <int FMT, bool TMA, bool TAPS>
+template <int FMT, bool TMA, bool TAPS, int MOD>
 int launch_big_demod(cofdm *h, cudaStream_t st, const void *samples, size_t n_frames, size_t stride, uint8_t *bytes,
                      unsigned long long *amb, const RxTaps &taps, const FrameScal *fsc) {
     const Params &P = h->P;
@@ -221,7 +221,7 @@ int launch_big_demod(cofdm *h, cudaStream_t st, const void *samples, size_t n_fr
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)P.num_symb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, big_demod_kernel<FMT, TMA, TAPS>, P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, fsc);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, big_demod_kernel<FMT, TMA, TAPS, MOD>, P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, fsc);
     if (e != cudaSuccess) return fail(COFDM_ERR_CUDA, std::string("big_demod launch: ") + cudaGetErrorString(e));
     return check_launch(h, "big_demod");
 }
@@ -276,8 +276,10 @@ int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_
     }
     if (h->timing) cudaEventRecord(h->sev[1], st);
     int rc;
-#define COFDM_BIG(F, T) (want ? launch_big_demod<F, T, true>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
-                              : launch_big_demod<F, T, false>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc))
+    // the production instance is specialised on 64-QAM; everything else reads the modulation order from the configuration
+#define COFDM_BIG(F, T) (want ? launch_big_demod<F, T, true, 0>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
+                              : (P.mod_type == 6 ? launch_big_demod<F, T, false, 6>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
+                                                 : launch_big_demod<F, T, false, 0>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc)))
     if (fmt == COFDM_CI16) rc = al ? COFDM_BIG(kCI16, true) : COFDM_BIG(kCI16, false);
     else rc = al ? COFDM_BIG(kCF32, true) : COFDM_BIG(kCF32, false);
 #undef COFDM_BIG
@@ -458,7 +460,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
-    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
+    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.big_roles, &P.big_roles); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
     rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.lane_aux, &P.lane_aux); rc |= upload(h, T.acq_desc, &P.acq_desc);
     rc |= upload(h, T.grid_lane, &P.grid_lane); rc |= upload(h, T.tx_desc, &P.tx_desc);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
@@ -546,11 +548,12 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             COFDM_BACQ_ATTR(kCI16, true, true); COFDM_BACQ_ATTR(kCI16, true, false); COFDM_BACQ_ATTR(kCI16, false, true); COFDM_BACQ_ATTR(kCI16, false, false);
 #undef COFDM_BACQ_ATTR
             const int smb = (int)big_smem_bytes();
-#define COFDM_BIG_ATTR(F, T, W) \
-            cudaFuncSetAttribute(big_demod_kernel<F, T, W>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \
-            cudaFuncSetAttribute(big_demod_kernel<F, T, W>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-            COFDM_BIG_ATTR(kCF32, true, true); COFDM_BIG_ATTR(kCF32, true, false); COFDM_BIG_ATTR(kCF32, false, true); COFDM_BIG_ATTR(kCF32, false, false);
-            COFDM_BIG_ATTR(kCI16, true, true); COFDM_BIG_ATTR(kCI16, true, false); COFDM_BIG_ATTR(kCI16, false, true); COFDM_BIG_ATTR(kCI16, false, false);
+#define COFDM_BIG_ATTR1(F, T, W, MD) \
+            cudaFuncSetAttribute(big_demod_kernel<F, T, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \
+            cudaFuncSetAttribute(big_demod_kernel<F, T, W, MD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+#define COFDM_BIG_ATTR(F, T) COFDM_BIG_ATTR1(F, T, true, 0); COFDM_BIG_ATTR1(F, T, false, 0); COFDM_BIG_ATTR1(F, T, false, 6)
+            COFDM_BIG_ATTR(kCF32, true); COFDM_BIG_ATTR(kCF32, false); COFDM_BIG_ATTR(kCI16, true); COFDM_BIG_ATTR(kCI16, false);
+#undef COFDM_BIG_ATTR1
 #undef COFDM_BIG_ATTR
         }
     }

@@ -100,6 +100,7 @@ struct HostTables {
     std::vector<uint4> lane_desc;     // rx512n.cuh: per lane, the roles of its registers after warp_fft512
     std::vector<uint2> lane_aux;      //             combinations and straggler bins
     std::vector<uint2> acq_desc;      //             acquire kernel: which phase each slot produces
+    std::vector<uint4> big_roles;     // big.cuh: per thread, the roles of its 16 bins
     std::vector<uint4> tx_desc;       // tx512w.cuh: per lane, what sits at the bins lane + 32 n1
     std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N), by bin
     std::vector<float2> grid_lane;    //             the same in lane order
@@ -404,6 +405,17 @@ inline HostTables build_tables(const ConfigMap &cfg) {
     for (int q = 0; q < NP; q++) T.bin_role[(size_t)T.pilot_bin[(size_t)q]] = (int16_t)(-2 - q);
     // big.cuh: fft 4096 / cp 1024 (ofdm_len / fft_size = 5 / 4 like the fft-512 geometry), one preamble symbol, up to 8 message
     // symbols (one CTA each, a portable cluster), at most 128 pilots and 3840 data sub-carriers per symbol
+    if (N == 4096) {
+        p.big_tmask = 0;
+        for (int k = 0; k < N; k++) if (T.bin_role[(size_t)k] != -1) p.big_tmask |= 1 << (k >> 8);
+        p.big_dstep = (256 % p.seg_step) == 0 ? 256 / p.seg_step * p.seg_size : 0;
+        T.big_roles.assign(512, make_uint4(0, 0, 0, 0));
+        for (int j = 0; j < 256; j++)
+            for (int t = 0; t < 16; t++) {
+                unsigned *u = &T.big_roles[2 * (size_t)j].x;          // 8 consecutive words per thread
+                u[t >> 1] |= ((unsigned)(uint16_t)T.bin_role[(size_t)(j + 256 * t)]) << (16 * (t & 1));
+            }
+    }
     T.big_ok = T.generic_ok && N == 4096 && p.cp_size == 1024 && p.num_pr_symb == 1 && p.num_symb >= 1 && p.num_symb <= 8 &&
                NP <= kMaxPilots && ND <= 3840 && ND % 8 == 0 && ND % NP == 0;
     return T;

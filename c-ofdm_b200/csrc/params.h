@@ -53,6 +53,9 @@ struct Params {
     const int16_t *bin_map;      // [fft_size] -1 null, -2 pilot, else data index within the symbol
     const int16_t *data_bin;     // [num_data_subc] bin of data index i
     const int16_t *pilot_bin;    // [num_pilot_subc]
+    int big_tmask;               // big.cuh: bit t set <=> some bin j + 256 t is used (data or pilot)
+    int big_dstep;               // big.cuh: data-index step between consecutive rows of one thread (0: none)
+    const uint4 *big_roles;      // [256][2] big.cuh: the 16 roles of thread j (bins j + 256 t, t = 0..15) as int16, packed (fft 4096 only)
     const int16_t *bin_role;     // [fft_size] >= 0 data index within the symbol, -1 null, -2 - p pilot number p (big.cuh)
     // ---- one-warp-per-symbol receive kernels of the fft-512 geometry (rx512n.cuh) ----
     // After warp_fft512 lane 2 k1 + g holds mn[i] = X[k1 + 16 i + (g ? 384 : 0)] and ot[i] = X[k1 + 16 i + (g ? 128 : 256)].

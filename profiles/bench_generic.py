@@ -44,7 +44,8 @@ def main():
     tx_bytes = s.usefull_size + s.output_size * 8
     rows = []
     g = torch.Generator(device="cuda").manual_seed(7)
-    for n in (64, 256, 1024, 4096):
+    batches = [int(x) for x in os.environ.get("BIG_BATCHES", "64,256,1024,4096,16384").split(",")]
+    for n in batches:
         pay = torch.randint(0, 256, (n, s.usefull_size), dtype=torch.uint8, device="cuda", generator=g)
         frames = torch.empty((n, s.output_size), dtype=torch.complex64, device="cuda")
         out = torch.empty((n, s.usefull_size), dtype=torch.uint8, device="cuda")
