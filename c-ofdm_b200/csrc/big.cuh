@@ -625,6 +625,81 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
     }
 }
 
+// ================================================================================================================
+// big_tx_kernel: FRAME_FORM::write + get / get_int16 (Frame.cpp:185-198, 54-70, 244-256) for the fft-4096 geometry.
+// grid (num_symb + 1, n_frames): CTA (s, f) builds message symbol s of frame f -- the symbol's payload bytes staged in shared
+// memory, the thread's 16 grid points (bins j + 256 u: data point, pilot or null, from the packed role table) conjugated,
+// conj(FFT(conj G)) = the backward transform, / sqrt(4096), coalesced stores of body and cyclic prefix straight from the
+// registers (thread j holds samples j + 256 t: a warp stores 32 consecutive samples); CTA (num_symb, f) copies the constant
+// sync tone + preamble.
+// ================================================================================================================
+constexpr int kBigTxPayMax = kBigMaxData + 16;
+COFDM_HD constexpr size_t big_tx_smem_bytes() { return (size_t)kBigExchSlots * 8 + kBigTxPayMax; }
+
+template <int FMT>
+COFDM_DEV void big_store(void *frame_out, long long idx, float2 v, float mult) {
+    if (FMT == kCI16) {
+        // Frame.cpp:252: int16(trunc(re*mult)), int16(trunc(im*mult))
+        const unsigned pk = ((unsigned)(unsigned short)(short)__float2int_rz(v.x * mult)) | ((unsigned)(unsigned short)(short)__float2int_rz(v.y * mult) << 16);
+        reinterpret_cast<unsigned *>(frame_out)[idx] = pk;
+    } else {
+        reinterpret_cast<float2 *>(frame_out)[idx] = v;
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kBigThreads, 4)
+big_tx_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, void *__restrict__ frames) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int s = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x;
+    if (frame >= n_frames) return;
+    const size_t sb = (FMT == kCI16) ? 4 : 8;
+    char *fout = reinterpret_cast<char *>(frames) + (size_t)frame * P.frame_len * sb;
+    if (s == P.num_symb) {
+        for (int i = tid; i < P.t2sin_size + P.pf_size; i += kBigThreads)
+            big_store<FMT>(fout, i, i < P.t2sin_size ? __ldg(&P.t2_tone[i]) : __ldg(&P.preamble_td[i - P.t2sin_size]), P.mult);
+        return;
+    }
+    float2 *E = reinterpret_cast<float2 *>(smem_raw);
+    uint8_t *pl = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)kBigExchSlots * 8;
+    const int mod = P.mod_type, ND = P.num_data_subc, sym_bytes = ND * mod / 8;
+    {
+        const uint8_t *src = payload + (size_t)frame * P.bytes_per_frame + (size_t)s * sym_bytes;
+        if (((reinterpret_cast<uintptr_t>(src) | (unsigned)sym_bytes) & 3) == 0) {
+            for (int i = tid; i < sym_bytes / 4; i += kBigThreads) reinterpret_cast<unsigned *>(pl)[i] = __ldg(reinterpret_cast<const unsigned *>(src) + i);
+        } else {
+            for (int i = tid; i < sym_bytes; i += kBigThreads) pl[i] = __ldg(src + i);
+        }
+        if (tid < 4) reinterpret_cast<unsigned *>(pl + ((sym_bytes + 3) & ~3))[tid] = 0u;   // the byte a straddling 6-bit symbol reads past the end
+    }
+    const uint4 ra = __ldg(&P.big_roles[2 * tid]), rb = __ldg(&P.big_roles[2 * tid + 1]);
+    const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    __syncthreads();
+    float2 v[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        const int role = (int)(short)((rw[u >> 1] >> (16 * (u & 1))) & 0xffffu);
+        float2 g = make_float2(0.f, 0.f);                                          // Frame.cpp:55
+        if (role <= -2) g = make_float2(P.pilot_ampl, 0.f);                         // Frame.cpp:56-57
+        else if (role >= 0) {
+            const float2 c = __ldg(&P.constell[extract_bits_sw(pl, sym_bytes + 4, role * mod, mod)]);   // Frame.cpp:59-62 + modulation.cpp:39-50
+            g = make_float2(c.x, -c.y);                                            // conjugated: the backward transform is conj(FFT(conj G))
+        }
+        v[u] = g;
+    }
+    auto sync = [&]() { __syncthreads(); };
+    cta_fft4096<false>(v, E, P.tw_fft, tid, sync);
+    const float sc = 0.015625f;                                                    // 1 / sqrt(4096)  (Frame.cpp:66-68)
+    const float2 scj = make_float2(sc, -sc);
+    const long long base = P.t2sin_size + P.pf_size + (long long)s * kBigL;
+#pragma unroll
+    for (int t = 0; t < 16; t++) {
+        const float2 y = p_mul(v[t], scj);
+        big_store<FMT>(fout, base + kBigCP + tid + 256 * t, y, P.mult);              // Frame.cpp:191-192
+        if (t >= 12) big_store<FMT>(fout, base + tid + 256 * (t - 12), y, P.mult);   // Frame.cpp:196-197
+    }
+}
+
 // Bridge: the any-size path's per-frame record (generic.cuh GenFrame) -> FrameScal, so that big_demod_kernel can run behind
 // the any-size acquisition kernels (COFDM_BIG_ACQUIRE=0).  th0 carries theta_0 + m_0 whole (m0 = 0).
 __global__ void big_bridge_kernel(const Params P, int n_frames, const GenFrame *__restrict__ gf, FrameScal *__restrict__ fscal, const RxTaps taps) {

@@ -327,6 +327,19 @@ int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, s
 
 int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt) {
     const Params &P = h->P;
+    if (h->T.big_ok && h->big_on) {
+        // the fft-4096 geometry (big.cuh): one 256-thread CTA per symbol, FFT in registers
+        for (size_t f0 = 0; f0 < n_frames; f0 += 32768) {              // grid.y limit
+            const int n = (int)std::min<size_t>(32768, n_frames - f0);
+            const uint8_t *pl = payload + f0 * (size_t)P.bytes_per_frame;
+            void *out = (char *)frames + f0 * (size_t)P.frame_len * sample_bytes(fmt);
+            const dim3 grid((unsigned)P.num_symb + 1, n);
+            if (fmt == COFDM_CI16) big_tx_kernel<kCI16><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out);
+            else big_tx_kernel<kCF32><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out);
+            if (int rc = check_launch(h, "big_tx")) return rc;
+        }
+        return COFDM_OK;
+    }
     const size_t sm = 2 * (size_t)P.fft_size * sizeof(float2);
     for (size_t f0 = 0; f0 < n_frames; f0 += 32768) {                  // grid.y limit
         const int n = (int)std::min<size_t>(32768, n_frames - f0);
@@ -547,6 +560,10 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             COFDM_BACQ_ATTR(kCF32, true, true); COFDM_BACQ_ATTR(kCF32, true, false); COFDM_BACQ_ATTR(kCF32, false, true); COFDM_BACQ_ATTR(kCF32, false, false);
             COFDM_BACQ_ATTR(kCI16, true, true); COFDM_BACQ_ATTR(kCI16, true, false); COFDM_BACQ_ATTR(kCI16, false, true); COFDM_BACQ_ATTR(kCI16, false, false);
 #undef COFDM_BACQ_ATTR
+            cudaFuncSetAttribute(big_tx_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_tx_smem_bytes());
+            cudaFuncSetAttribute(big_tx_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_tx_smem_bytes());
+            cudaFuncSetAttribute(big_tx_kernel<kCF32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+            cudaFuncSetAttribute(big_tx_kernel<kCI16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
             const int smb = (int)big_smem_bytes();
 #define COFDM_BIG_ATTR1(F, T, W, MD) \
             cudaFuncSetAttribute(big_demod_kernel<F, T, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \

@@ -207,6 +207,8 @@ int emu_rx_generic(void *hv, const void *samples, int fmt, int n_frames, long lo
     return 0;
 }
 
+static int g_emu_big_tx = 1;
+void emu_set_big_tx(int on) { g_emu_big_tx = on; }
 int emu_big_ok(void *h) { return ((EmuHandle *)h)->T.big_ok ? 1 : 0; }
 
 // the fft-4096 path (big.cuh) as launch_rx_big runs it; mode 0: acquisition by the any-size kernels + bridge, 1: big_acquire_kernel.
@@ -257,6 +259,11 @@ int emu_tx_generic(void *hv, const uint8_t *payload, int n_frames, void *frames,
     auto *h = (EmuHandle *)hv;
     if (!h->T.generic_ok) return -1;
     const Params P = h->P;
+    if (h->T.big_ok && g_emu_big_tx) {
+        if (fmt == kCI16) emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kBigThreads), big_tx_smem_bytes(), [&] { big_tx_kernel<kCI16>(P, payload, n_frames, frames); });
+        else emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kBigThreads), big_tx_smem_bytes(), [&] { big_tx_kernel<kCF32>(P, payload, n_frames, frames); });
+        return 0;
+    }
     const size_t sm = 2 * (size_t)P.fft_size * sizeof(float2);
     if (fmt == kCI16) emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kGenThreads), sm, [&] { gen_tx_kernel<kCI16>(P, payload, n_frames, frames); });
     else emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kGenThreads), sm, [&] { gen_tx_kernel<kCF32>(P, payload, n_frames, frames); });
