@@ -33,9 +33,11 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 CONFIG = os.path.join(ROOT, "config", "config.txt")
 
-RX_BYTES_PER_FRAME = 46080 + 1024      # (N+CP)(NS+NPR)*8 read + ND*NS*mod/8 written, 16-QAM
+RX_BYTES_PER_FRAME = 46080 + 1024      # (N+CP)(NS+NPR)*8 read + ND*NS*mod/8 written, 16-QAM (recomputed from the sizes at run time)
 TX_BYTES_PER_FRAME = 1024 + 6016 * 8   # payload read + frame written
+WORKLOAD = "default"                   # "big": BASELINE.json configs[4] (fft 4096, cp 1024, 1920 + 128 sub-carriers, 64-QAM)
 MOD_NAME = {1: "BPSK", 2: "QPSK", 4: "16-QAM", 6: "64-QAM", 8: "256-QAM"}
+RX_DRAM_BYTES_PER_FRAME_NCU_BIG = 381757  # big workload: acquire 40991 + 1057, demod 327738 + 11971 (profiles/r02_big_ncu_summary.txt)
 RX_DRAM_BYTES_PER_FRAME_NCU = 47495     # measured DRAM read+write of the rx pass (acquire + demod kernels), see roofline.traffic_source
 
 
@@ -122,12 +124,20 @@ def cpu_run(n_frames_total, threads, seed=0):
     return dt, kind, per * threads, sum(errs), s
 
 
+def workload_name(s, native=False):
+    geo = f"fft{s.fft_size} cp{s.cp_size} {s.num_symb}sym+preamble {s.num_data_subc}+{s.num_pilot_subc} sub-carriers " + MOD_NAME.get(s.mod_type, "?")
+    which = "default config.txt" if WORKLOAD == "default" else "BASELINE configs[4] large-FFT dense-pilot config"
+    if native:
+        return f"synthetic batched tx + fused aligned rx, {which} ({geo}), complex64 in HBM"
+    return f"batched tx + aligned rx, {which} ({geo})"
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = n_cores()
-    frames = args.cpu_frames or 4000 * cores
+    frames = args.cpu_frames or (4000 if WORKLOAD == "default" else 500) * cores
     times = []
     for _ in range(args.warmup):
         cpu_run(max(cores, frames // 8), cores)
@@ -141,9 +151,8 @@ def reference_arm(args):
     line = {"impl": "reference", "metric": "tx+rx Msamples/s", "value": v, "unit": "Msamples/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "batched tx + aligned rx, default config.txt (fft512 cp128 8sym+preamble " + MOD_NAME.get(s.mod_type, "?") + ")",
-                       "frames_per_step": n_done, "frame_samples": s.output_size},
-            "ofdm_symbols_s": 2 * n_done * 9 / dt,
+            "config": {"workload": workload_name(s), "frames_per_step": n_done, "frame_samples": s.output_size},
+            "ofdm_symbols_s": 2 * n_done * (s.num_symb + s.num_pr_symb) / dt,
             "cpu_baseline": {"value": v, "unit": "Msamples/s", "cores": cores, "kind": kind,
                              "sample": f"{n_done} frames tx+rx per step on {cores} threads; FFT = stand-in mixed-radix (FFTW3 not installed)"},
             "e2e": {"value": v, "unit": "Msamples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -209,6 +218,10 @@ def native_arm(args):
     m.use_torch_stream()
     s = m.sizes
     F = args.frames
+    global RX_BYTES_PER_FRAME, TX_BYTES_PER_FRAME
+    RX_BYTES_PER_FRAME = s.rx_len * 8 + s.usefull_size           # every rx sample read once + the payload written
+    TX_BYTES_PER_FRAME = s.usefull_size + s.output_size * 8
+    n_sym = s.num_symb + s.num_pr_symb
     # ---- workload: payloads -> tx kernel -> light channel (untimed) -----------------------------------
     g = torch.Generator(device=dev).manual_seed(1234 + rank)
     payload = torch.randint(0, 256, (F, s.usefull_size), dtype=torch.uint8, device=dev, generator=g)
@@ -216,14 +229,16 @@ def native_arm(args):
     tx_out = torch.empty((F, s.output_size), dtype=torch.complex64, device=dev)
     m.tx_batch(payload, cb.CF32, out=rx_in)
     n = torch.arange(s.output_size, device=dev, dtype=torch.float64)
-    CH = 8192
+    CH = max(64, 8192 * 6016 // s.output_size)
+    # CFO range: well inside the coarse estimator's window (+-10 bins of the preamble-length grid); noise on the int16 grid
+    cfo_max, noise_sigma = (0.003, 1.5) if WORKLOAD == "default" else (0.0005, 0.5)
     for f0 in range(0, F, CH):
         f1 = min(F, f0 + CH)
-        cfo = (torch.rand((f1 - f0, 1), device=dev, generator=g, dtype=torch.float64) - 0.5) * 0.006
+        cfo = (torch.rand((f1 - f0, 1), device=dev, generator=g, dtype=torch.float64) - 0.5) * (2 * cfo_max)
         ph = torch.rand((f1 - f0, 1), device=dev, generator=g, dtype=torch.float64)
         rot = torch.polar(torch.ones_like(cfo * n), 2 * torch.pi * (cfo * n + ph)).to(torch.complex64)
         blk = rx_in[f0:f1] * rot * float(s.mult)
-        noise = torch.randn((f1 - f0, s.output_size, 2), device=dev, generator=g) * 1.5
+        noise = torch.randn((f1 - f0, s.output_size, 2), device=dev, generator=g) * noise_sigma
         rx_in[f0:f1] = torch.view_as_complex(torch.round(torch.view_as_real(blk) + noise))   # int16-grid samples, like an ADC
     out_bytes = torch.empty((F, s.usefull_size), dtype=torch.uint8, device=dev)
     torch.cuda.synchronize()
@@ -329,20 +344,26 @@ def native_arm(args):
             "metric": "tx+rx Msamples/s", "value": value, "unit": "Msamples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "synthetic batched tx + fused aligned rx, default config.txt (fft512 cp128 8sym+preamble " + MOD_NAME.get(s.mod_type, "?") + "), complex64 in HBM",
+            "config": {"workload": workload_name(s, native=True),
                        "frames_per_gpu": F, "frame_samples": s.output_size, "l2": "inputs (GBs) far larger than the 126 MB L2, no flush needed",
-                       "channel": "per-frame CFO +-0.003 cyc/sample, random phase, AWGN sigma 1.5 LSB, int16 grid"},
-            "ofdm_symbols_s": world * 2 * F * 9 / (step_ms * 1e-3),
+                       "channel": f"per-frame CFO +-{cfo_max} cyc/sample, random phase, AWGN sigma {noise_sigma} LSB, int16 grid"},
+            "ofdm_symbols_s": world * 2 * F * n_sym / (step_ms * 1e-3),
             "rx_msamples_s": world * F * s.output_size / (rx_ms * 1e-3) / 1e6,
             "tx_msamples_s": world * F * s.output_size / (tx_ms * 1e-3) / 1e6,
             "rx_frames_s": world * F / (rx_ms * 1e-3), "rx_ms": rx_ms, "tx_ms": tx_ms,
             "rx_msamples_s_on_rx_len": world * F * s.rx_len / (rx_ms * 1e-3) / 1e6,
             "bit_errors": bit_err, "frames_with_errors": frames_bad, "frames_checked": frames_all, "oracle_check": oracle_check,
             "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb,
-            "roofline": {"bound": "hbm", "kernel": "rx pass = rx_acquire512w_kernel + rx_demod512_kernel (together they read every sample exactly once)", "achieved": rx_gbs, "peak": peak, "unit": "GB/s",
-                         "frac": rx_gbs / peak, "traffic": RX_DRAM_BYTES_PER_FRAME_NCU * F if s.mod_type == 4 else None, "peak_source": peak_src,
-                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the two rx kernels over 32768 frames "
-                                           "(profiles/r02_rx_warp_ncu_summary.txt) = 47495 B/frame, scaled to this launch's frames",
+            "roofline": {"bound": "hbm",
+                         "kernel": ("rx pass = rx_acquire512w_kernel + rx_demod512_kernel" if WORKLOAD == "default" else "rx pass = big_acquire_kernel + big_demod_kernel (cluster of 8 CTAs per frame)")
+                                   + " (together they read every sample exactly once)",
+                         "achieved": rx_gbs, "peak": peak, "unit": "GB/s", "frac": rx_gbs / peak,
+                         "traffic": (RX_DRAM_BYTES_PER_FRAME_NCU * F if (WORKLOAD == "default" and s.mod_type == 4) else
+                                     (RX_DRAM_BYTES_PER_FRAME_NCU_BIG * F if WORKLOAD == "big" else None)),
+                         "peak_source": peak_src,
+                         "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the two rx kernels "
+                                           + ("over 32768 frames (profiles/r02_rx_warp_ncu_summary.txt) = 47495 B/frame" if WORKLOAD == "default"
+                                              else "over 4096 frames (profiles/r02_big_ncu_summary.txt) = 381757 B/frame") + ", scaled to this launch's frames",
                          "algorithmic_bytes_per_frame": RX_BYTES_PER_FRAME, "tx_kernel_gbs": tx_gbs, "tx_frac": tx_gbs / peak},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_step": E, "ms_per_step": e_dt * 1e3, "payload_roundtrip_ok": e_ok, "host_sample_format": "ci16 (SDR wire format)",
@@ -351,10 +372,10 @@ def native_arm(args):
         }
         if not args.no_cpu and world == 1:
             cores = n_cores()
-            cf = args.cpu_frames or 10000 * cores
+            cf = args.cpu_frames or (10000 if WORKLOAD == "default" else 1200) * cores
             cpu_run(max(cores, cf // 8), cores)
             dt, kind, n_done, errs, cs = cpu_run(cf, cores)
-            dt1, _, n1, errs1, _ = cpu_run(2000, 1)                       # (i) one thread, (ii) every core
+            dt1, _, n1, errs1, _ = cpu_run(2000 if WORKLOAD == "default" else 250, 1)                       # (i) one thread, (ii) every core
             line["cpu_baseline"] = {"value": 2 * n_done * cs.output_size / dt / 1e6, "unit": "Msamples/s", "cores": cores, "kind": kind,
                                     "sample": f"{n_done} frames tx+rx on {cores} threads in {dt:.1f} s; FFT = stand-in mixed-radix (FFTW3 not installed)",
                                     "payload_bytes_wrong": errs + errs1,
@@ -372,8 +393,10 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--frames", type=int, default=1 << 20, help="frames per GPU per step")
-    ap.add_argument("--e2e-frames", type=int, default=1 << 15)
+    ap.add_argument("--workload", default="default", choices=["default", "big"],
+                    help="default: BASELINE configs[2] (the headline, shipped config.txt); big: configs[4] (fft 4096, cp 1024, 1920 + 128 sub-carriers, 64-QAM)")
+    ap.add_argument("--frames", type=int, default=0, help="frames per GPU per step (default 1 Mi; big workload: 16384 = 6 GB of samples)")
+    ap.add_argument("--e2e-frames", type=int, default=0)
     ap.add_argument("--cpu-frames", type=int, default=0)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--oracle-frames", type=int, default=1024, help="frames of the timed batch re-decoded by the oracle (0: skip)")
@@ -381,14 +404,25 @@ def main():
                     help="0: the shipped config.txt (16-QAM, the headline workload); otherwise the same geometry with this modType "
                          "(BASELINE configs[2] also names QPSK)")
     args = ap.parse_args()
+    global WORKLOAD, CONFIG
+    WORKLOAD = args.workload
+    if not args.frames:
+        args.frames = (1 << 20) if WORKLOAD == "default" else 16384
+    if not args.e2e_frames:
+        args.e2e_frames = (1 << 15) if WORKLOAD == "default" else 4096
+    if WORKLOAD == "big":
+        import tempfile
+        from cofdm_b200 import synth
+        rank = os.environ.get("RANK", "0")
+        CONFIG = synth.write_config(os.path.join(tempfile.mkdtemp(), f"config_big_{rank}.txt"), fft_size=4096, cp_size=1024, num_data_subc=1920,
+                                    num_pilot_subc=128, num_symb=8, pr_sin_len=128, modType=args.mod_type or 6)
+        args.oracle_frames = min(args.oracle_frames, 64)
+        args.mod_type = 0
     if args.mod_type:
         import tempfile
         from cofdm_b200 import synth
-        global CONFIG, RX_BYTES_PER_FRAME, TX_BYTES_PER_FRAME
         rank = os.environ.get("RANK", "0")
         CONFIG = synth.write_config(os.path.join(tempfile.mkdtemp(), f"config_mod{args.mod_type}_{rank}.txt"), modType=args.mod_type)
-        payload = 256 * 8 * args.mod_type // 8
-        RX_BYTES_PER_FRAME, TX_BYTES_PER_FRAME = 46080 + payload, payload + 6016 * 8
     if args.impl == "reference":
         reference_arm(args)
     else:

@@ -488,15 +488,19 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     for (auto &e : h->sev) cudaEventCreate(&e);
     cudaEventCreate(&h->ev0);
     cudaEventCreate(&h->ev1);
+    {
+        // host pipeline: chunks of about 2048 default-size frames (49 MB of int16 samples), whatever the frame size
+        h->pipe_chunk = std::max<size_t>(1, (size_t)2048 * 6016 / (size_t)std::max(1, P.frame_len));
+        const char *c = std::getenv("COFDM_PIPE_CHUNK");
+        if (c && std::atoll(c) > 0) h->pipe_chunk = (size_t)std::atoll(c);
+        const char *d = std::getenv("COFDM_PIPE_DEPTH");
+        if (d && std::atoi(d) > 0) h->pipe_depth = std::min(std::atoi(d), kPipe);
+    }
     if (T.fused512_ok) {
         cudaError_t a = cudaSuccess, b = cudaSuccess;
         {
             const char *tb = std::getenv("COFDM_TX_BULK");
             if (tb) h->tx_bulk = std::atoi(tb) != 0;
-            const char *c = std::getenv("COFDM_PIPE_CHUNK");
-            if (c && std::atoll(c) > 0) h->pipe_chunk = (size_t)std::atoll(c);
-            const char *d = std::getenv("COFDM_PIPE_DEPTH");
-            if (d && std::atoi(d) > 0) h->pipe_depth = std::min(std::atoi(d), kPipe);
         }
         // maximum shared-memory carve-out: occupancy of both rx kernels is bounded by shared memory and registers, not by L1
         {
