@@ -1150,19 +1150,18 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
     if (tm) cudaEventRecord(h->sev[5], st);
     const auto wall = [] { return std::chrono::steady_clock::now(); };
     const auto t_merge0 = wall();
-    std::vector<int> cnt((size_t)ns);
-    CU_TRY(cudaMemcpyAsync(cnt.data(), d_cnt, (size_t)ns * sizeof(int), cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
     std::vector<std::vector<long long>> lists((size_t)ns);
     {
-        // one strided copy: the first max(cnt) entries of every shard's list
-        const size_t w = (size_t)*std::max_element(cnt.begin(), cnt.end());
-        std::vector<long long> all((size_t)ns * std::max<size_t>(w, 1));
-        if (w) CU_TRY(cudaMemcpy2DAsync(all.data(), w * sizeof(long long), d_pos, (size_t)max_per * sizeof(long long), w * sizeof(long long),
-                                        (size_t)ns, cudaMemcpyDeviceToHost, st));
+        // ONE read-back of the shards' lists and counts into pinned memory, one synchronisation (a few hundred KB at most:
+        // a frame occupies at least message.size samples of its shard)
+        const size_t tail_bytes = (size_t)ns * sizeof(StreamShard) + (size_t)ns * sizeof(int);
+        CU_TRY(h->pin.reserve(list_bytes + tail_bytes));
+        CU_TRY(cudaMemcpyAsync(h->pin.p, d_pos, list_bytes + tail_bytes, cudaMemcpyDeviceToHost, st));
         CU_TRY(cudaStreamSynchronize(st));
+        const long long *all = (const long long *)h->pin.p;
+        const int *cnt = (const int *)((const char *)h->pin.p + list_bytes + (size_t)ns * sizeof(StreamShard));
         for (long long r = 0; r < ns; r++)
-            lists[(size_t)r].assign(all.begin() + (long)((size_t)r * w), all.begin() + (long)((size_t)r * w + (size_t)cnt[(size_t)r]));
+            lists[(size_t)r].assign(all + (size_t)r * (size_t)max_per, all + (size_t)r * (size_t)max_per + (size_t)cnt[(size_t)r]);
     }
     std::vector<long long> merged;
     size_t unmerged = 0;

@@ -82,22 +82,53 @@ def rx_stream_sharded(run, capture_i16, sizes, world):
     return merge_shards(shards, sizes)
 
 
+def gather_frame_lists(pos_abs, b0, b1, device=None):
+    """The one exchange of the sharded stream receiver: every rank contributes its list of absolute preamble positions
+    (int64) and its block range; every rank gets all of them back.  Two fixed-size collectives (all_gather of the counts,
+    all_gather of the lists padded to the longest) on the process group's own backend -- NCCL over NVLink on GPUs, gloo on
+    CPU -- no pickling, no payload bytes.  Returns a list over ranks of (positions, tags, b0, b1), tags[i] = (rank, i)."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    pos_abs = np.asarray(pos_abs, dtype=np.int64)
+    head = torch.tensor([len(pos_abs), b0, b1], dtype=torch.int64, device=device)
+    heads = torch.empty(world * 3, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(heads, head)
+    heads = heads.cpu().numpy().reshape(world, 3)
+    width = max(1, int(heads[:, 0].max()))
+    mine = torch.full((width,), -1, dtype=torch.int64, device=device)
+    if len(pos_abs):
+        mine[: len(pos_abs)] = torch.from_numpy(pos_abs).to(device)
+    allp = torch.empty(world * width, dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allp, mine)
+    allp = allp.cpu().numpy().reshape(world, width)
+    out = []
+    for r in range(world):
+        n = int(heads[r, 0])
+        tag = np.stack([np.full(n, r, np.int64), np.arange(n, dtype=np.int64)], axis=1)
+        out.append((allp[r, :n].copy(), tag, int(heads[r, 1]), int(heads[r, 2])))
+    return out
+
+
 def rx_stream_distributed(modem, capture_i16, shards=1):
     """torchrun entry: every rank receives its slice of the capture (a numpy array, or a torch tensor already on
-    its GPU) on its own GPU -- itself cut into `shards` ranges scanned concurrently -- and rank 0 merges.
-    The only communication is the gather of the per-rank frame lists.  Returns (positions, bytes, unmerged)
-    on rank 0 and (None, None, None) elsewhere."""
+    its GPU) on its own GPU -- itself cut into `shards` ranges scanned concurrently.  The only communication is
+    gather_frame_lists (positions, a few bytes per frame); every rank then merges the chains itself and learns which
+    of ITS frames belong to the merged list.  Payloads never leave the rank that decoded them.
+    Returns (positions_of_the_whole_capture, tags [n, 2] = (rank, index in that rank's list), my_bytes, unmerged)."""
     import torch.distributed as dist
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     s = modem.sizes
     s0, s1, b0, b1 = shard_slice(capture_i16.shape[0], s, rank, world)
     pos, by = modem.rx_stream(capture_i16[s0:s1], shards=shards)
-    mine = (np.asarray(pos) + s0, by, b0, b1)
+    pos_abs = np.asarray(pos, dtype=np.int64) + s0
     if world == 1:
-        return merge_shards([mine], s)
-    gathered = [None] * world if rank == 0 else None
-    dist.gather_object(mine, gathered, dst=0)
-    if rank != 0:
-        return None, None, None
-    return merge_shards(gathered, s)
+        tag = np.stack([np.zeros(len(pos_abs), np.int64), np.arange(len(pos_abs), dtype=np.int64)], axis=1)
+        lists = [(pos_abs, tag, b0, b1)]
+    else:
+        lists = gather_frame_lists(pos_abs, b0, b1)
+    mpos, mtag, unmerged = merge_shards(lists, s)
+    return mpos, mtag, by, unmerged
