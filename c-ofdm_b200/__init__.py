@@ -305,7 +305,7 @@ class Modem:
         n = _n_samples(frames, fmt) // s.output_size
         out = self._new(frames, (n, s.usefull_size), "uint8")
         restored = self._new(frames, (n, s.constell_size), "complex64") if taps else None
-        chan = self._new(frames, (n, s.num_data_subc), "complex64") if taps else None
+        chan = self._new(frames, (n, s.num_data_subc), "complex64") if (taps and s.fused_path == 1) else None   # chan_char: fft-512 kernels only
         amb = C.c_ulonglong(0)
         self._chk(self.lib.cofdm_read_batch(self.h, _ptr(frames), fmt, n, _ptr(out), C.addressof(amb), _ptr(restored), _ptr(chan), _space(frames, out)))
         return (out, restored, chan, int(amb.value)) if taps else (out, int(amb.value))

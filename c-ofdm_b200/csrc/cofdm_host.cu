@@ -145,7 +145,7 @@ size_t sample_bytes(int fmt) { return fmt == COFDM_CI16 ? 4 : 8; }
 
 // ---- device-side launches (all pointers are device pointers, stream given) ----------------------
 int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot);
+                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot, int sync_less = 0);
 int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
                   uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot);
 int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt);
@@ -154,7 +154,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     if (n_frames == 0) return COFDM_OK;
     if (!h->T.fused512_ok) {
         if (h->T.big_ok && h->big_on && !sync_less) return launch_rx_big(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot);
-        if (h->T.generic_ok && !sync_less) return launch_rx_generic(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot);
+        if (h->T.generic_ok) return launch_rx_generic(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot, sync_less);
         return fail(COFDM_ERR_UNSUPPORTED, "rx: configuration outside both the fused fft-512 path and the generic path (see DESIGN.md section 7)");
     }
     if ((uintptr_t)bytes & 3) return fail(COFDM_ERR_ARG, "rx: the output byte buffer must be 4-byte aligned");
@@ -289,13 +289,15 @@ int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_
 
 // the any-size path (generic.cuh): five kernels per sub-batch with the spectra in HBM between them
 int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot) {
+                      uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot, int sync_less) {
     const Params &P = h->P;
+    if (sync_less && taps.chan != nullptr)
+        return fail(COFDM_ERR_UNSUPPORTED, "read: the chan_char output is only built for the fft-512 geometry");
     const size_t sub = 512, N = (size_t)P.fft_size, L = (size_t)P.ofdm_len, nsym = (size_t)P.n_sym_rx;
     const size_t nb = std::min(sub, n_frames);
     CU_TRY(h->gen_frames[slot].reserve(nb * sizeof(GenFrame)));
     CU_TRY(h->gen_spec[slot].reserve(nb * nsym * N * sizeof(float2)));
-    CU_TRY(h->gen_pre[slot].reserve(nb * L * sizeof(float2)));
+    CU_TRY(h->gen_pre[slot].reserve(nb * (size_t)P.pf_size * sizeof(float2)));
     GenFrame *gf = (GenFrame *)h->gen_frames[slot].p;
     float2 *spec = (float2 *)h->gen_spec[slot].p, *pre = (float2 *)h->gen_pre[slot].p;
     const size_t sm_c = 2 * (size_t)P.pf_size * sizeof(float2), sm_s = (L + N) * sizeof(float2), sm_h = (size_t)P.num_data_subc / 2 * sizeof(float) + 16;
@@ -307,17 +309,18 @@ int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, s
         if (t.scal) t.scal += f0 * 48;
         if (t.chan) t.chan += f0 * (size_t)P.num_data_subc;
         if (t.constell) t.constell += f0 * (size_t)P.num_data_subc * P.num_symb;
+        // (the sync-less form, FRAME_FORM::read, has no coarse-CFO stage and no rotation)
         if (fmt == COFDM_CI16) {
-            gen_coarse_kernel<kCI16><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
+            if (!sync_less) gen_coarse_kernel<kCI16><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
             if (int rc = check_launch(h, "gen_coarse")) return rc;
-            gen_symbol_kernel<kCI16><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
+            gen_symbol_kernel<kCI16><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre, sync_less);
         } else {
-            gen_coarse_kernel<kCF32><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
+            if (!sync_less) gen_coarse_kernel<kCF32><<<n, kGenThreads, sm_c, st>>>(P, src, (long long)stride, n, gf);
             if (int rc = check_launch(h, "gen_coarse")) return rc;
-            gen_symbol_kernel<kCF32><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre);
+            gen_symbol_kernel<kCF32><<<dim3((unsigned)nsym, n), kGenThreads, sm_s, st>>>(P, src, (long long)stride, n, gf, spec, pre, sync_less);
         }
         if (int rc = check_launch(h, "gen_symbol")) return rc;
-        gen_chan_kernel<false><<<n, kGenThreads, sm_h, st>>>(P, n, gf, spec, pre);
+        gen_chan_kernel<false><<<n, kGenThreads, sm_h, st>>>(P, n, gf, spec, pre, sync_less);
         if (int rc = check_launch(h, "gen_chan")) return rc;
         gen_demap_kernel<<<dim3((unsigned)P.num_symb, n), kGenThreads, 0, st>>>(P, n, gf, spec, bytes + f0 * (size_t)P.bytes_per_frame, amb, t);
         if (int rc = check_launch(h, "gen_demap")) return rc;
@@ -378,8 +381,16 @@ int launch_tx(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames
 }
 
 int launch_t2(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t start, size_t n_blocks, float *rel) {
-    if (h->P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "t2sin: only T2sin_size = 256 is built so far");
     if (n_blocks == 0) return COFDM_OK;
+    if (h->P.t2sin_size != 256) {
+        // any power-of-two block size from 16 to 1024: one warp per block, every bin evaluated
+        const int n = h->P.t2sin_size;
+        if (n < 16 || n > 1024 || (n & (n - 1)) != 0) return fail(COFDM_ERR_UNSUPPORTED, "t2sin: T2sin_size must be a power of two in [16, 1024]");
+        const unsigned grid = (unsigned)((n_blocks + kT2AnyWarps - 1) / kT2AnyWarps);
+        if (fmt == COFDM_CI16) t2sin_metric_any_kernel<kCI16><<<grid, 32 * kT2AnyWarps, t2sin_any_smem_bytes(n), st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
+        else t2sin_metric_any_kernel<kCF32><<<grid, 32 * kT2AnyWarps, t2sin_any_smem_bytes(n), st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
+        return check_launch(h, "t2sin_metric_any");
+    }
     if (n_blocks >= 64) {                            // two blocks per warp, packed arithmetic
         const unsigned g2 = (unsigned)(((n_blocks + 1) / 2 + kT2PairWarps - 1) / kT2PairWarps);
         if (fmt == COFDM_CI16) t2sin_metric2_kernel<kCI16><<<g2, 32 * kT2PairWarps, 0, st>>>(h->P, samples, (long long)start, (long long)n_blocks, rel);
@@ -577,6 +588,10 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
 #undef COFDM_BIG_ATTR1
 #undef COFDM_BIG_ATTR
         }
+    }
+    if (P.t2sin_size != 256 && P.t2sin_size >= 16 && P.t2sin_size <= 1024) {
+        cudaFuncSetAttribute(t2sin_metric_any_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2sin_any_smem_bytes(P.t2sin_size));
+        cudaFuncSetAttribute(t2sin_metric_any_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)t2sin_any_smem_bytes(P.t2sin_size));
     }
     cudaFuncSetAttribute(stream_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)stream_scan_smem_bytes(P.cor_size, P.pr_sin_len));
     {
@@ -963,7 +978,7 @@ static int rx_stream_hostseq(cofdm_t *h, const int16_t *capture, size_t n_sample
     // device ring (int16 I,Q = 4 bytes per sample) + batch of frames awaiting demodulation
     const size_t batch_cap = 1024;
     CU_TRY(h->scratch_a.reserve((size_t)ring * 4));
-    CU_TRY(h->scratch_b.reserve((size_t)ring / 256 * sizeof(float) + 64));
+    CU_TRY(h->scratch_b.reserve((size_t)ring / (size_t)std::max(16, P.t2sin_size) * sizeof(float) + 64));
     CU_TRY(h->pipe_in[0].reserve(batch_cap * (size_t)P.rx_len * 4));
     CU_TRY(h->pipe_out[0].reserve(batch_cap * (size_t)P.bytes_per_frame));
     CU_TRY(h->scratch_c.reserve(64));
@@ -995,12 +1010,12 @@ static int rx_stream_hostseq(cofdm_t *h, const int16_t *capture, size_t n_sample
     // T2SIN_FORM::find_t2sin on the ring from `start` (Frame.hpp:150-197), in windows of 64 blocks
     auto find_t2 = [&](long long start, long long *pos) -> int {
         *pos = -1;
-        const long long cycles = (ring - start) / 256;
+        const long long t2n = P.t2sin_size, cycles = (ring - start) / t2n;
         for (long long c0 = 0; c0 < cycles; c0 += 64) {
             const long long nb = std::min<long long>(64, cycles - c0);
             if (cudaMemsetAsync(h->pos_dev, 0xff, sizeof(unsigned long long), st) != cudaSuccess) return fail(COFDM_ERR_CUDA, "memset");
-            if (int rc = launch_t2(h, st, d_ring, COFDM_CI16, (size_t)(start + c0 * 256), (size_t)nb, (float *)h->scratch_b.p)) return rc;
-            first_above_kernel<<<1, 64, 0, st>>>((const float *)h->scratch_b.p, nb, P.t2_level, start + c0 * 256, 256, h->pos_dev);
+            if (int rc = launch_t2(h, st, d_ring, COFDM_CI16, (size_t)(start + c0 * t2n), (size_t)nb, (float *)h->scratch_b.p)) return rc;
+            first_above_kernel<<<1, 64, 0, st>>>((const float *)h->scratch_b.p, nb, P.t2_level, start + c0 * t2n, (int)t2n, h->pos_dev);
             if (int rc = check_launch(h, "first_above")) return rc;
             unsigned long long v = 0;
             if (cudaMemcpyAsync(&v, h->pos_dev, sizeof v, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)
@@ -1102,8 +1117,10 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
     if (n_unmerged) *n_unmerged = 0;
     if (set_device(h)) return COFDM_ERR_CUDA;
     const Params &P = h->P;
-    if (!h->T.fused512_ok || P.t2sin_size != 256) return fail(COFDM_ERR_UNSUPPORTED, "rx_stream: configuration not built yet");
-    const bool scanner_ok = (P.pr_sin_len % 4) == 0 && (P.cor_size % 4) == 0 && h->T.rx_buf_size >= 1;
+    if (!h->T.fused512_ok && !h->T.generic_ok) return fail(COFDM_ERR_UNSUPPORTED, "rx_stream: configuration outside both receive paths");
+    // the device scanner is built for the fft-512 geometry with T2sin_size = 256; everything else (other sync-tone sizes, the
+    // any-size / fft-4096 receive paths) runs the host-sequenced form of the same loop (one search launch per step)
+    const bool scanner_ok = h->T.fused512_ok && P.t2sin_size == 256 && (P.pr_sin_len % 4) == 0 && (P.cor_size % 4) == 0 && h->T.rx_buf_size >= 1;
     static const bool force_hostseq = [] { const char *e = std::getenv("COFDM_STREAM_HOSTSEQ"); return e && std::atoi(e) != 0; }();
     if ((!scanner_ok || force_hostseq) && space == COFDM_HOST && n_shards == 1)
         return rx_stream_hostseq(h, capture, n_samples, max_frames, pr_begin_abs, bytes, n_found);

@@ -123,7 +123,7 @@ gen_coarse_kernel(const Params P, const void *__restrict__ samples, long long fr
 template <int FMT, bool PRE_ONLY = false>
 __global__ void __launch_bounds__(kGenThreads)
 gen_symbol_kernel(const Params P, const void *__restrict__ samples, long long frame_stride, int n_frames,
-                  GenFrame *__restrict__ gf, float2 *__restrict__ spec, float2 *__restrict__ pre_rot) {
+                  GenFrame *__restrict__ gf, float2 *__restrict__ spec, float2 *__restrict__ pre_rot, const int sync_less = 0) {
     COFDM_DYN_SMEM(smem_raw);
     const int sym = blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
     if (frame >= n_frames) return;
@@ -136,10 +136,11 @@ gen_symbol_kernel(const Params P, const void *__restrict__ samples, long long fr
     float2 c = make_float2(0.f, 0.f);
     for (int j = tid; j < CP; j += nthr) cmac_conj(c, A[j], A[j + N]);        // Frame.hpp:251-253
     c = block_sum(c, red);
-    const double fc = (double)gf[frame].kc / (double)P.pf_den;                // coarse shift, cycles per sample
+    // (sync-less form, FRAME_FORM::read: no synchronisation stage at all -- the samples are transformed as they stand)
+    const double fc = sync_less ? 0.0 : (double)gf[frame].kc / (double)P.pf_den;   // coarse shift, cycles per sample
     // the reference correlates after freq_shift: its angle is Arg(C exp(-j 2pi fc N)) (Frame.hpp:254)
     const float2 cr = cmul(c, cis_neg_turns(fc * (double)N));
-    const double phit = (double)atan2f(cr.y, cr.x) * 0.15915494309189533577;
+    const double phit = sync_less ? 0.0 : (double)atan2f(cr.y, cr.x) * 0.15915494309189533577;
     if (tid == 0) gf[frame].phit[sym] = (float)phit;
     const double nu = fc + phit / (double)N;                                   // total rotation, turns per sample
     __syncthreads();
@@ -153,7 +154,7 @@ gen_symbol_kernel(const Params P, const void *__restrict__ samples, long long fr
                 const int j = j0 + e * nthr;
                 if (j >= L) break;
                 const float2 y = cmul(A[j], ph);
-                if (sym == 0 && pre_rot != nullptr) pre_rot[(size_t)frame * L + j] = y;
+                if (sym < P.num_pr_symb && pre_rot != nullptr) pre_rot[((size_t)frame * P.num_pr_symb + sym) * L + j] = y;   // the preamble's symbols
                 if (j >= CP) B[j - CP] = y;                                    // CP strip (Frame.hpp:278-279)
                 ph = cmul(ph, step);
             }
@@ -169,32 +170,39 @@ gen_symbol_kernel(const Params P, const void *__restrict__ samples, long long fr
 template <bool PRE_ONLY = false>
 __global__ void __launch_bounds__(kGenThreads)
 gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const float2 *__restrict__ spec,
-                const float2 *__restrict__ pre_rot) {
+                const float2 *__restrict__ pre_rot, const int sync_less = 0) {
     COFDM_DYN_SMEM(smem_raw);
     const int frame = blockIdx.x, tid = threadIdx.x, nthr = blockDim.x;
     if (frame >= n_frames) return;
     __shared__ float2 red[32];
-    const int N = P.fft_size, L = P.ofdm_len, nsym = P.n_sym_rx, ND = P.num_data_subc, NP = P.num_pilot_subc;
+    const int N = P.fft_size, L = P.ofdm_len, nsym = P.n_sym_rx, ND = P.num_data_subc, NP = P.num_pilot_subc, npr = P.num_pr_symb;
     GenFrame &G = gf[frame];
+    __shared__ float2 psi_rot[kGenMaxSym];
     // constant phase carried into symbol s (turns): freq_shift's global index + cp_freq_sinh's accumulated shift
     if (tid == 0) {
         const double fc = (double)G.kc / (double)P.pf_den;
         double acc = 0.0;
         for (int s = 0; s < nsym; s++) {
-            G.psi[s] = fc * (double)L * (double)s + acc;
+            G.psi[s] = sync_less ? 0.0 : fc * (double)L * (double)s + acc;
             acc += (double)G.phit[s] * (double)L / (double)N;
+            if (s < npr) psi_rot[s] = cis_neg_turns(G.psi[s]);
         }
     }
-    // pr_phase_sinh (Frame.hpp:265-274): symbol 0 carries no constant phase, pre_rot is already fully corrected
-    float2 z = make_float2(0.f, 0.f);
-    for (int j = tid; j < P.pf_size; j += nthr) cmac_conj(z, __ldg(&P.preamble_td[j]), pre_rot[(size_t)frame * L + j]);
+    __syncthreads();
+    // pr_phase_sinh (Frame.hpp:265-274) over the whole preamble: symbol s of it still lacks its constant phase Psi_s (0 for s = 0)
+    float2 z = make_float2(1.f, 0.f);
+    if (!sync_less) {
+        z = make_float2(0.f, 0.f);
+        for (int j = tid; j < P.pf_size; j += nthr) cmac_conj(z, __ldg(&P.preamble_td[j]), cmul(pre_rot[(size_t)frame * P.pf_size + j], psi_rot[j / L]));
+    }
     z = block_sum(z, red);
+    if (sync_less) z = make_float2(1.f, 0.f);
     const float inv = rsqrtf(fmaxf(cnorm2(z), 1e-30f));
     const float2 rot = make_float2(z.x * inv, -z.y * inv);
     // pilot amplitude normaliser over all message symbols (Frame.cpp:76-80)
     float pa = 0.f;
-    for (int i = tid; i < (PRE_ONLY ? 0 : (nsym - 1) * NP); i += nthr) {
-        const int s = 1 + i / NP, p = i % NP;
+    for (int i = tid; i < (PRE_ONLY ? 0 : (nsym - npr) * NP); i += nthr) {
+        const int s = npr + i / NP, p = i % NP;
         pa += sqrtf(cnorm2(spec[((size_t)frame * nsym + s) * N + __ldg(&P.pilot_bin[p])]));
     }
     const float2 pas = block_sum(make_float2(pa, 0.f), red);
@@ -202,7 +210,7 @@ gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const f
     float *ph = reinterpret_cast<float *>(smem_raw);
     const int nph = ND / 2;
     const float2 *S0 = spec + (size_t)frame * (PRE_ONLY ? 1 : nsym) * N;
-    for (int i = tid; i < nph; i += nthr) {
+    for (int i = tid; i < (sync_less ? 0 : nph); i += nthr) {
         const float2 d = cmulc(cmul(S0[__ldg(&P.data_bin[i])], rot), __ldg(&P.mod_preamble[i]));
         ph[i] = atan2f(d.y, d.x);
     }
@@ -211,7 +219,7 @@ gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const f
         const float PI_F = 3.14159265358979323846f, TWO_PI_F = 6.28318530717958647692f;
         double sy = 0.0, sxy = 0.0, sx = 0.0, sx2 = 0.0;
         float prev = 0.f;
-        for (int i = 0; i < nph; i++) {                                        // Frame.hpp:407-421
+        for (int i = 0; i < (sync_less ? 0 : nph); i++) {                      // Frame.hpp:407-421
             float v = ph[i];
             if (i > 0) {
                 const float d = v - prev;
@@ -220,12 +228,12 @@ gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const f
             prev = v;
             sy += (double)v; sxy += (double)v * (double)i; sx += (double)i; sx2 += (double)i * (double)i;
         }
-        const double b = (sxy - sx * sy) / (sx2 - sx * sx);                    // Frame.hpp:422 (sums, not means)
+        const double b = sync_less ? 0.0 : (sxy - sx * sy) / (sx2 - sx * sx);  // Frame.hpp:422 (sums, not means)
         G.b = b;
-        G.a = sy - b * sx;                                                     // Frame.hpp:423
+        G.a = sync_less ? 0.0 : sy - b * sx;                                   // Frame.hpp:423
         G.rot_theta = rot;
         G.theta = atan2f(z.y, z.x);
-        G.g = pas.x / ((float)((nsym - 1) * NP) * P.pilot_ampl);
+        G.g = pas.x / ((float)((nsym - npr) * NP) * P.pilot_ampl);
     }
 }
 
@@ -233,17 +241,18 @@ gen_chan_kernel(const Params P, int n_frames, GenFrame *__restrict__ gf, const f
 __global__ void __launch_bounds__(kGenThreads)
 gen_demap_kernel(const Params P, int n_frames, const GenFrame *__restrict__ gf, const float2 *__restrict__ spec,
                  uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous, const RxTaps taps) {
-    const int s = 1 + blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
+    const int npr = P.num_pr_symb;
+    const int s = npr + blockIdx.x, frame = blockIdx.y, tid = threadIdx.x, nthr = blockDim.x;
     if (frame >= n_frames) return;
     const int N = P.fft_size, nsym = P.n_sym_rx, ND = P.num_data_subc, mod = P.mod_type;
     const GenFrame &G = gf[frame];
-    const float2 *S1 = spec + ((size_t)frame * nsym + 1) * N, *Ss = spec + ((size_t)frame * nsym + s) * N;
+    const float2 *S1 = spec + ((size_t)frame * nsym + npr) * N, *Ss = spec + ((size_t)frame * nsym + s) * N;
     // constant rotation of message symbol 0, whose pilots are the reference of every segment (Frame.cpp:89)
-    const float2 rot1 = cmul(cis_neg_turns(G.psi[1]), G.rot_theta);
+    const float2 rot1 = cmul(cis_neg_turns(G.psi[npr]), G.rot_theta);
     const DemapK dk = make_demapk(mod);
     const int half = ND / 2;
     int n_amb = 0;
-    uint8_t *dst = out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - 1) * (ND * mod / 8);
+    uint8_t *dst = out_bytes + (size_t)frame * P.bytes_per_frame + (size_t)(s - npr) * (ND * mod / 8);
     for (int grp = tid; grp < ND / 8; grp += nthr) {
         unsigned long long bits = 0;
 #pragma unroll 1
@@ -255,7 +264,7 @@ gen_demap_kernel(const Params P, int n_frames, const GenFrame *__restrict__ gf, 
             // 1/H_i with H_i = exp(j(b i' + a)), i' = i (i < ND/2) or i - ND (Frame.hpp:425-430)
             const float2 hc = cis_neg_turns((G.b * (double)(i < half ? i : i - ND) + G.a) * 0.15915494309189533577);
             const float2 zz = cmul(cmul(Ss[__ldg(&P.data_bin[i])], w), hc);
-            if (taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - 1) + (s - 1)) * ND + i] = zz;
+            if (taps.constell != nullptr) taps.constell[((size_t)frame * (nsym - npr) + (s - npr)) * ND + i] = zz;
             bool amb;
             bits = (bits << mod) | (unsigned long long)demap_point(zz, dk, amb);
             n_amb += amb ? 1 : 0;
@@ -263,7 +272,7 @@ gen_demap_kernel(const Params P, int n_frames, const GenFrame *__restrict__ gf, 
         for (int bq = 0; bq < mod; bq++) dst[(size_t)grp * mod + bq] = (uint8_t)(bits >> (8 * (mod - 1 - bq)));
     }
     if (ambiguous != nullptr && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
-    if (s == 1) {
+    if (s == npr) {
         if (taps.chan != nullptr)
             for (int i = tid; i < ND; i += nthr)
                 taps.chan[(size_t)frame * ND + i] = cis_turns((G.b * (double)(i < half ? i : i - ND) + G.a) * 0.15915494309189533577);

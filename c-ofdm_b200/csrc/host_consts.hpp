@@ -395,7 +395,7 @@ inline HostTables build_tables(const ConfigMap &cfg) {
             while (n % r == 0 && nr < 8 && n > 1) { rad[nr++] = r; n /= r; }
         return n == 1;
     };
-    T.generic_ok = schedule(N, p.fft_radix, p.fft_nr) && schedule(p.pf_size, p.pf_radix, p.pf_nr) && p.num_pr_symb == 1 &&
+    T.generic_ok = schedule(N, p.fft_radix, p.fft_nr) && schedule(p.pf_size, p.pf_radix, p.pf_nr) && p.num_pr_symb >= 1 &&
                    ND % 8 == 0 && ND % NP == 0 && p.pf_size <= 12288 && N <= 8192 && p.n_sym_rx <= kGenMaxSym;
     T.fused512_ok = (N == 512 && p.cp_size == 128 && ND == 256 && NP == 8 && p.num_pr_symb == 1 &&
                      p.num_symb >= 1 && p.num_symb <= kMaxFusedSymb && p.t2sin_size % 2 == 0 && p.pr_sin_len <= 128 * 5);

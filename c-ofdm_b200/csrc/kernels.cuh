@@ -116,6 +116,52 @@ t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long 
     if (lane == 0) rel_out[blk] = rel;
 }
 
+// t2sin_metric_any_kernel: the same metric for any power-of-two T2sin_size from 16 to 1024 (the reference takes the size from
+// the configuration, Frame.cpp:99-136; 256 has the two tuned kernels here).  One warp per block, radix-8 / 4 / 2 Stockham passes
+// between two buffers in the warp's shared memory, every bin evaluated.
+constexpr int kT2AnyWarps = 4;
+COFDM_HD size_t t2sin_any_smem_bytes(int size) { return (size_t)kT2AnyWarps * 2 * (size_t)size * sizeof(float2); }
+template <int FMT>
+__global__ void __launch_bounds__(32 * kT2AnyWarps)
+t2sin_metric_any_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks, float *__restrict__ rel_out) {
+    COFDM_DYN_SMEM(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n = P.t2sin_size;
+    const long long blk = (long long)blockIdx.x * kT2AnyWarps + warp;
+    if (blk >= n_blocks) return;
+    float2 *A = reinterpret_cast<float2 *>(smem_raw) + (size_t)warp * 2 * n, *B = A + n;
+    const long long s0 = start + blk * n;
+    float tot = 0.f;
+    for (int i = lane; i < n; i += 32) {
+        float2 x;
+        if (FMT == kCI16) {
+            const unsigned w = __ldg(reinterpret_cast<const unsigned *>(samples) + s0 + i);
+            x = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+        } else {
+            x = __ldg(reinterpret_cast<const float2 *>(samples) + s0 + i);
+        }
+        A[i] = x;
+        tot += cnorm2(x);                                       // Parseval: sum_k |X_k|^2 = n sum_i |x_i|^2
+    }
+    tot *= (float)n;
+    __syncwarp();
+    int ns = 1;
+    while (ns < n) {
+        const int rem = n / ns;
+        if (rem % 8 == 0) { stockham_pass<8, false>(A, B, n, ns, P.tw_t2, lane, 32); ns *= 8; }
+        else if (rem % 4 == 0) { stockham_pass<4, false>(A, B, n, ns, P.tw_t2, lane, 32); ns *= 4; }
+        else { stockham_pass<2, false>(A, B, n, ns, P.tw_t2, lane, 32); ns *= 2; }
+        __syncwarp();
+        float2 *t = A; A = B; B = t;
+    }
+    float sine = 0.f;
+    for (int k = lane; k < n; k += 32) sine += __ldg(&P.t2_mask[k]) * cnorm2(A[k]);
+    tot = warp_sum(tot);
+    sine = warp_sum(sine);
+    float rel = sine / tot;
+    if (tot == 0.f || rel != rel) rel = 0.f;                    // Frame.hpp:132-138 `continue`
+    if (lane == 0) rel_out[blk] = rel;
+}
+
 // t2sin_metric2_kernel: the same metric with TWO consecutive blocks per warp, packed f32x2 (block 2b in the low,
 // block 2b+1 in the high half of every register pair): half the FFT instructions per block.
 constexpr int kT2PairWarps = 4;

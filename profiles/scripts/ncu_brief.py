@@ -17,5 +17,6 @@ for r in rows[2:]:
         if k in d: print(f"  {k:95s} {d[k]:>16s} {u[k]}")
     inst=float(d['smsp__inst_executed.sum']); wf=float(d['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']); bc=float(d['l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum'])
     rd=tobytes(d['dram__bytes_read.sum'],u['dram__bytes_read.sum']); wr=tobytes(d['dram__bytes_write.sum'],u['dram__bytes_write.sum'])
-    print(f"  per frame ({N} frames): {inst/N:.0f} warp-instructions, {wf/N:.0f} shared-memory wavefronts ({bc/N:.0f} from bank conflicts), DRAM {rd/N:.0f} B read + {wr/N:.0f} B written")
+    unit = "per frame" if N > 1 else "per launch"
+    print(f"  {unit} ({N} frames): {inst/N:.0f} warp-instructions, {wf/N:.0f} shared-memory wavefronts ({bc/N:.0f} from bank conflicts), DRAM {rd/N:.0f} B read + {wr/N:.0f} B written")
     print()

@@ -125,7 +125,12 @@ int emu_tx512(void *hv, const uint8_t *payload, int n_frames, void *frames, int 
 int emu_t2sin_metric(void *hv, const void *samples, int fmt, long long start, long long n_blocks, float *rel) {
     auto *h = (EmuHandle *)hv;
     const Params P = h->P;
-    if (P.t2sin_size != 256) return -1;
+    if (P.t2sin_size != 256) {
+        const unsigned grid = (unsigned)((n_blocks + kT2AnyWarps - 1) / kT2AnyWarps);
+        if (fmt == kCI16) emu::launch(dim3(grid), dim3(32 * kT2AnyWarps), t2sin_any_smem_bytes(P.t2sin_size), [&] { t2sin_metric_any_kernel<kCI16>(P, samples, start, n_blocks, rel); });
+        else emu::launch(dim3(grid), dim3(32 * kT2AnyWarps), t2sin_any_smem_bytes(P.t2sin_size), [&] { t2sin_metric_any_kernel<kCF32>(P, samples, start, n_blocks, rel); });
+        return 0;
+    }
     if (n_blocks >= 64) {                            // as launch_t2 does: two blocks per warp
         const unsigned g2 = (unsigned)(((n_blocks + 1) / 2 + kT2PairWarps - 1) / kT2PairWarps);
         if (fmt == kCI16) emu::launch(dim3(g2), dim3(32 * kT2PairWarps), 0, [&] { t2sin_metric2_kernel<kCI16>(P, samples, start, n_blocks, rel); });
@@ -185,24 +190,30 @@ int emu_demod(void *, int mod, const float2 *points, long long n_points, uint8_t
 
 int emu_generic_ok(void *h) { return ((EmuHandle *)h)->T.generic_ok ? 1 : 0; }
 
+int emu_rx_generic_mode(void *hv, const void *samples, int fmt, int n_frames, long long stride, int sync_less, uint8_t *out,
+                        unsigned long long *amb, float *scal, float2 *chan, float2 *constell);
 int emu_rx_generic(void *hv, const void *samples, int fmt, int n_frames, long long stride, uint8_t *out,
                    unsigned long long *amb, float *scal, float2 *chan, float2 *constell) {
+    return emu_rx_generic_mode(hv, samples, fmt, n_frames, stride, 0, out, amb, scal, chan, constell);
+}
+int emu_rx_generic_mode(void *hv, const void *samples, int fmt, int n_frames, long long stride, int sync_less, uint8_t *out,
+                        unsigned long long *amb, float *scal, float2 *chan, float2 *constell) {
     auto *h = (EmuHandle *)hv;
     if (!h->T.generic_ok) return -1;
     const Params P = h->P;
     const size_t N = P.fft_size, L = P.ofdm_len, nsym = P.n_sym_rx;
     std::vector<GenFrame> gf(n_frames);
-    std::vector<float2> spec((size_t)n_frames * nsym * N), pre((size_t)n_frames * L);
+    std::vector<float2> spec((size_t)n_frames * nsym * N), pre((size_t)n_frames * P.pf_size);
     RxTaps taps{scal, nullptr, chan, constell, nullptr};
     const dim3 blk(kGenThreads);
     if (fmt == kCI16) {
-        emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCI16>(P, samples, stride, n_frames, gf.data()); });
-        emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCI16>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
+        if (!sync_less) emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCI16>(P, samples, stride, n_frames, gf.data()); });
+        emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCI16>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data(), sync_less); });
     } else {
-        emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCF32>(P, samples, stride, n_frames, gf.data()); });
-        emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCF32>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data()); });
+        if (!sync_less) emu::launch(dim3(n_frames), blk, 2 * P.pf_size * sizeof(float2), [&] { gen_coarse_kernel<kCF32>(P, samples, stride, n_frames, gf.data()); });
+        emu::launch(dim3(nsym, n_frames), blk, (L + N) * sizeof(float2), [&] { gen_symbol_kernel<kCF32>(P, samples, stride, n_frames, gf.data(), spec.data(), pre.data(), sync_less); });
     }
-    emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel<false>(P, n_frames, gf.data(), spec.data(), pre.data()); });
+    emu::launch(dim3(n_frames), blk, P.num_data_subc / 2 * sizeof(float) + 16, [&] { gen_chan_kernel<false>(P, n_frames, gf.data(), spec.data(), pre.data(), sync_less); });
     emu::launch(dim3(P.num_symb, n_frames), blk, 0, [&] { gen_demap_kernel(P, n_frames, gf.data(), spec.data(), out, amb, taps); });
     return 0;
 }

@@ -36,6 +36,7 @@ class EmuModem:
         L.emu_preamble_corr.argtypes = [vp, vp, C.c_int, C.c_longlong, vp, C.c_int, vp, vp]
         L.emu_rx_generic.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong] + [vp] * 5
         L.emu_tx_generic.argtypes = [vp, vp, C.c_int, vp, C.c_int]
+        L.emu_rx_generic_mode.argtypes = [vp, vp, C.c_int, C.c_int, C.c_longlong, C.c_int] + [vp] * 5
         L.emu_rx_big.argtypes = [vp, vp, C.c_int, C.c_int, C.c_int, C.c_longlong, C.c_int] + [vp] * 5
         L.emu_big_ok.argtypes = [vp]
         L.emu_fused_ok.argtypes = [vp]
@@ -141,6 +142,11 @@ class EmuModem:
         restored = np.zeros((n, s.constell_size), np.complex64)
         chan = np.zeros((n, s.num_data_subc), np.complex64)
         base = frames.ctypes.data + s.t2sin_size * (4 if fmt == CI16 else 8)
+        if not self.fused:
+            # the any-size kernels in their sync-less form (no chan_char output there)
+            assert self.lib.emu_rx_generic_mode(self.h, base, fmt, n, s.output_size, 1, out.ctypes.data, amb.ctypes.data,
+                                                None, None, restored.ctypes.data) == 0
+            return (out, restored, None, int(amb[0])) if taps else (out, int(amb[0]))
         assert self.lib.emu_rx_fused512_mode(self.h, base, fmt, self.use_tma, n, s.output_size, 1, out.ctypes.data, amb.ctypes.data,
                                              None, None, chan.ctypes.data, restored.ctypes.data, None) == 0
         return (out, restored, chan, int(amb[0])) if taps else (out, int(amb[0]))

@@ -224,3 +224,52 @@ def test_big_path_phase_unwrap_slow_path(cfg_dir, oracle_lib):
     pay, rec = pc.impaired_records(o, 2, seed=21, cfo_max=0.002, noise=0.5, taps=(1.0, 0.1j), early=6)
     st = pc.check_rx_against_oracle(m, o, rec, "i16")
     assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6 and st["chan"] < 5e-6, st
+
+
+def test_generic_path_two_preamble_symbols_and_syncless_read(cfg_dir, oracle_lib, tmp_path):
+    """configurations the reference accepts and round 1 refused: num_pr_symb = 2 (Frame.cpp:164,259-294: the preamble is two
+    OFDM symbols; the coarse spectrum spans both, the phase lock sums over both, the channel fit uses the first) on the
+    any-size kernels, and the sync-less FRAME_FORM::read (Frame.cpp:239-242) on the any-size kernels"""
+    cfg = pc.synth.write_config(str(tmp_path / "config_small_pr2.txt"), base=cfg_dir["small"], num_pr_symb=2)
+    o = oracle_lib.Oracle("port", cfg)
+    m = EmuModem(cfg, o.sizes)
+    assert not m.fused
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6
+    pay, rec = pc.impaired_records(o, 3, seed=31, cfo_max=0.004, noise=1.0, taps=(1.0, 0.1j), early=1)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6, st
+    # sync-less read on the plain small geometry and on the two-preamble one
+    for c in (cfg_dir["small"], cfg):
+        o2 = oracle_lib.Oracle("port", c)
+        m2 = EmuModem(c, o2.sizes)
+        pay2 = pc.synth.payloads(2, o2.sizes.usefull_size, seed=5)
+        frames = np.stack([o2.tx(p)[0] for p in pay2]) * 0.8
+        out, restored, _, _ = m2.read_batch(frames.astype(np.complex64), taps=True)
+        for i in range(2):
+            want_b, want_r = o2.read(frames[i])
+            assert pc.rel_l2(restored[i], want_r) < 1e-5
+            pc.assert_bytes_match(out[i], want_b, want_r, o2.sizes.mod_type, "generic read")
+            assert np.array_equal(want_b, pay2[i])
+
+
+@pytest.mark.parametrize("t2", [128, 512])
+def test_t2sin_sizes_other_than_256(oracle_lib, tmp_path, t2):
+    """T2sin_size is a configuration key (Frame.cpp:99-136): 128 and 512 run on t2sin_metric_any_kernel; tx writes the tone
+    of that size and the detector finds it where the reference does"""
+    cfg = pc.synth.write_config(str(tmp_path / f"config_t2_{t2}.txt"), T2sin_size=t2, T2_sin_f1=17 * t2 // 256, T2_sin_f2=51 * t2 // 256)
+    o = oracle_lib.Oracle("port", cfg)
+    m = EmuModem(cfg, o.sizes)
+    s = o.sizes
+    assert s.t2sin_size == t2
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6
+    pay = pc.synth.payloads(2, s.usefull_size, seed=3)
+    tx16 = np.stack([o.tx(p)[1] for p in pay]).reshape(2, -1, 2)
+    cap, _ = pc.synth.capture(tx16[..., 0].astype(np.float64) + 1j * tx16[..., 1], gaps=np.array([3 * t2 + 40, 1000]), noise_sigma=2.0, seed=2, tail=4000)
+    capc = pc.cplx(cap)
+    rel = m.t2sin_metric(cap)
+    want = o.t2sin_corr(capc)
+    assert np.nonzero(rel > 0.8)[0].tolist() == np.nonzero(want)[0].tolist() and len(np.nonzero(want)[0]) >= 1
+    assert np.abs(rel[want > 0] - want[want > 0]).max() < 1e-6
+    assert m.find_t2sin(cap, 0) == o.find_t2sin(capc, 0)

@@ -531,3 +531,73 @@ def test_apps_tx_file_rx_file_round_trip(cfg_dir, tmp_path):
         first = dict(p.split(":", 1) for p in open(tmp_path / "LOG.txt").readline().split())
         assert abs(float(first["PFC"]) - st["demod"] * 1e-3 / 61) < 1e-9 and abs(float(first["T2SIN"]) - st["scan"] * 1e-3 / 61) < 1e-9
     m.close()
+
+
+@pytest.mark.parametrize("t2", [128, 512])
+def test_t2sin_sizes_other_than_256(oracle_lib, tmp_path, t2):
+    """T2sin_size 128 / 512 (Frame.cpp:99-136): tone written by tx, block metric, find_t2sin, and the stream receiver (the
+    host-sequenced form of rx.cpp's loop serves every configuration the device scanner is not built for)"""
+    cfg = pc.synth.write_config(str(tmp_path / f"config_t2_{t2}.txt"), T2sin_size=t2, T2_sin_f1=17 * t2 // 256, T2_sin_f2=51 * t2 // 256, rx_buf_size=6)
+    o = oracle_lib.Oracle("port", cfg)
+    m = cb.Modem(cfg, device=0)
+    s = o.sizes
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6
+    n = 14
+    pay = pc.synth.payloads(n, s.usefull_size, seed=3)
+    tx16 = np.stack([o.tx(p)[1] for p in pay]).reshape(n, -1, 2)
+    rng = np.random.default_rng(4)
+    fr = pc.synth.channel(tx16, seed=4, cfo=rng.uniform(-0.002, 0.002, n), phase=rng.uniform(0, 1, n), noise_sigma=1.0)
+    cap, _ = pc.synth.capture(fr, gaps=rng.integers(3 * t2 + 40, 2500, n), noise_sigma=2.0, seed=2, tail=s.output_size * 8)
+    capc = pc.cplx(cap)
+    rel = pc.to_np(m.t2sin_metric(cap))
+    want = o.t2sin_corr(capc)
+    assert np.nonzero(rel > 0.8)[0].tolist() == np.nonzero(want)[0].tolist() and len(np.nonzero(want)[0]) >= n
+    assert np.abs(rel[want > 0] - want[want > 0]).max() < 1e-6
+    assert m.find_t2sin(cap, 0) == o.find_t2sin(capc, 0)
+    want_pos, want_by = o.rx_stream(cap)
+    pos, by = m.rx_stream(cap)
+    assert pos.tolist() == want_pos.tolist() and len(pos) == n
+    assert np.array_equal(by, want_by)
+    m.close()
+
+
+def test_two_preamble_symbols_syncless_read_and_stream_on_the_any_size_path(cfg_dir, oracle_lib, tmp_path):
+    """configurations the reference accepts and round 1 refused: num_pr_symb = 2 (Frame.cpp:164,259-294), the sync-less
+    FRAME_FORM::read (Frame.cpp:239-242) outside the fft-512 geometry (any-size kernels, incl. the fft-4096 configuration) and
+    the stream receiver outside the fft-512 geometry"""
+    cfg = pc.synth.write_config(str(tmp_path / "config_small_pr2.txt"), base=cfg_dir["small"], num_pr_symb=2, rx_buf_size=8)
+    o = oracle_lib.Oracle("port", cfg)
+    m = cb.Modem(cfg, device=0)
+    assert m.sizes.fused_path == 0
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6
+    pay, rec = pc.impaired_records(o, 4, seed=31, cfo_max=0.004, noise=1.0, taps=(1.0, 0.1j), early=1)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6, st
+    # stream receiver on this configuration
+    s = o.sizes
+    n = 12
+    pay = pc.synth.payloads(n, s.usefull_size, seed=13)
+    tx16 = np.stack([o.tx(p)[1] for p in pay]).reshape(n, -1, 2)
+    rng = np.random.default_rng(5)
+    fr = pc.synth.channel(tx16, seed=6, cfo=rng.uniform(-0.002, 0.002, n), phase=rng.uniform(0, 1, n), noise_sigma=1.0)
+    cap, _ = pc.synth.capture(fr, gaps=rng.integers(800, 2500, n), noise_sigma=2.0, seed=3, tail=s.output_size * 10)
+    want_pos, want_by = o.rx_stream(cap)
+    pos, by = m.rx_stream(cap)
+    assert pos.tolist() == want_pos.tolist() and len(pos) >= n - 1
+    assert np.array_equal(by, want_by)
+    m.close()
+    # sync-less read: small geometry, two-preamble geometry, fft-4096 geometry
+    for c in (cfg_dir["small"], cfg, cfg_dir["big"]):
+        o2 = oracle_lib.Oracle("port", c)
+        m2 = cb.Modem(c, device=0)
+        pay2 = pc.synth.payloads(2, o2.sizes.usefull_size, seed=5)
+        frames = np.stack([o2.tx(p)[0] for p in pay2]) * 0.8
+        out, restored, _, _ = m2.read_batch(frames.astype(np.complex64), taps=True)
+        for i in range(2):
+            want_b, want_r = o2.read(frames[i])
+            assert pc.rel_l2(pc.to_np(restored)[i], want_r) < 1e-5
+            pc.assert_bytes_match(pc.to_np(out)[i], want_b, want_r, o2.sizes.mod_type, "any-size read")
+            assert np.array_equal(want_b, pay2[i])
+        m2.close()
