@@ -12,5 +12,5 @@ for k in t2sin_metric2 preamble_corr4 stream_scan stream_gather; do
   python profiles/scripts/ncu_brief.py $O/prof_r02_$k.ncu-rep 1 >> $O/r02_sync_ncu_summary.txt; rm -f $O/prof_r02_$k.ncu-rep
 done
 # launch list of the default bench (per-launch durations; shares of the step)
-ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $O/r02_launch_list.csv $B > $O/ncu_r02_ll.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"tx512w|rx_acquire512w|rx_demod512" -c 60 --csv --log-file $O/r02_launch_list.csv $B > $O/ncu_r02_ll.log 2>&1
 ls -la $O | head -30
