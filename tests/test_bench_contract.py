@@ -1,5 +1,5 @@
 """bench.py's output contract: the reference arm runs here (CPU only) and prints one JSON line with the agreed keys;
-the committed native-arm line (profiles/r01_bench_1gpu.json, produced on a B200) carries every key the driver reads."""
+the committed native-arm line (profiles/r02_bench_1gpu.json, produced on a B200) carries every key the driver reads."""
 import json
 import os
 import subprocess
@@ -38,7 +38,7 @@ def test_reference_arm_other_ranks_exit_quietly():
 
 
 def test_committed_native_line_has_every_key():
-    d = json.loads(open(os.path.join(ROOT, "profiles", "r01_bench_1gpu.json")).read().strip().splitlines()[-1])
+    d = json.loads(open(os.path.join(ROOT, "profiles", "r02_bench_1gpu.json")).read().strip().splitlines()[-1])
     _check_common(d)
     assert d["n_gpus"] == 1 and d["warmup"] >= 3 and d["data"] == "synthetic" and d["dtype"] == "f32" and d["scaling"] == "weak"
     rf = d["roofline"]
