@@ -277,6 +277,13 @@ def native_arm(args):
     rx_ms = float(np.mean([ev[3 * k + 1].elapsed_time(ev[3 * k + 2]) for k in range(args.steps)]))
     # correctness of what was timed: decoded bytes vs payload (bit errors), boundary-ambiguous symbols
     _, amb = m.rx_aligned_batch(rx_in, n_frames=min(F, 65536), frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes[:min(F, 65536)])
+    # what the optional count of boundary-ambiguous decisions costs (it is off inside the timed region): one rx pass with it on
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    m.rx_aligned_batch(rx_in, n_frames=F, frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes, count_ambiguous=True)
+    eb.record()
+    torch.cuda.synchronize()
+    rx_ms_amb = ea.elapsed_time(eb)
     m.rx_aligned_batch(rx_in, n_frames=F, frame_stride=s.output_size, offset=s.t2sin_size, out=out_bytes, count_ambiguous=False)
     diff = (out_bytes ^ payload)
     bit_err = int(torch.sum(torch.bitwise_count(diff).to(torch.int64)).item()) if hasattr(torch, "bitwise_count") else int((diff != 0).sum().item())
@@ -353,7 +360,7 @@ def native_arm(args):
             "rx_frames_s": world * F / (rx_ms * 1e-3), "rx_ms": rx_ms, "tx_ms": tx_ms,
             "rx_msamples_s_on_rx_len": world * F * s.rx_len / (rx_ms * 1e-3) / 1e6,
             "bit_errors": bit_err, "frames_with_errors": frames_bad, "frames_checked": frames_all, "oracle_check": oracle_check,
-            "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb,
+            "boundary_ambiguous_symbols_in_first_64k_frames_per_gpu": amb, "rx_ms_with_ambiguity_count_on": rx_ms_amb,
             "roofline": {"bound": "hbm",
                          "kernel": ("rx pass = rx_acquire512w_kernel + rx_demod512_kernel" if WORKLOAD == "default" else "rx pass = big_acquire_kernel + big_demod_kernel (cluster of 8 CTAs per frame)")
                                    + " (together they read every sample exactly once)",
