@@ -202,8 +202,11 @@ template <int R, bool INV> COFDM_DEV void dftR(float2 *v) {
 // NOWRAP: the caller guarantees (R-1)*(ns-1)*tstep < n, so the twiddle index needs no reduction mod n.
 // PADSH > 0: element i lives at slot i + (i >> PADSH).  With PADSH = 3 the radix-8 scatter of the first passes
 // (stride 8, then stride 64 + 1) and the consecutive gathers are all free of bank conflicts; buffers need n + n/8 slots.
-template <int PADSH> COFDM_DEV int pad_slot(int i) { return PADSH > 0 ? i + (i >> PADSH) : i; }
-template <int R, bool INV, bool NOWRAP = false, int PADSH = 0>
+// padded slot of element i.  PADSH 0: none; 1..31: i + (i >> PADSH); 64: i + 8 * (i >> 6).  The 256-point detector uses none for
+// its input (consecutive reads), 4 for the pass-1 output (scatter 8 j + q and consecutive reads both conflict-free) and 64
+// for the pass-2 output (scatter (j - k) 8 + k + 8 q and consecutive reads both conflict-free): enumerated in profiles/README.md.
+template <int PADSH> COFDM_DEV int pad_slot(int i) { return PADSH == 64 ? i + ((i >> 6) << 3) : (PADSH > 0 ? i + (i >> PADSH) : i); }
+template <int R, bool INV, bool NOWRAP = false, int PADSH = 0, int PADOUT = PADSH>
 COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const float2 *tw, int tid, int nthr) {
     const int m = n / R;
     const int tstep = n / (ns * R);
@@ -222,12 +225,12 @@ COFDM_DEV void stockham_pass(const float2 *in, float2 *out, int n, int ns, const
         dftR<R, INV>(v);
         const int o = (j - k) * R + k;              // (j / ns) * ns * R + k
 #pragma unroll
-        for (int q = 0; q < R; q++) out[pad_slot<PADSH>(o + q * ns)] = v[q];
+        for (int q = 0; q < R; q++) out[pad_slot<PADOUT>(o + q * ns)] = v[q];
     }
 }
 
 // The same pass for TWO transforms at once (packed f32x2; operands in separate re / im planes of float2 pairs).
-template <int R, bool INV, bool NOWRAP = false, int PADSH = 0>
+template <int R, bool INV, bool NOWRAP = false, int PADSH = 0, int PADOUT = PADSH>
 COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2 *out_re, float2 *out_im, int n, int ns,
                                 const float2 *tw, int tid, int nthr) {
     static_assert(R == 8 || R == 4, "packed passes exist for radix 4 and 8");
@@ -248,7 +251,7 @@ COFDM_DEV void stockham_pass_pc(const float2 *in_re, const float2 *in_im, float2
         if (R == 8) dft8<INV>(v); else dft4<INV>(v);
         const int o = (j - k) * R + k;
 #pragma unroll
-        for (int q = 0; q < R; q++) { out_re[pad_slot<PADSH>(o + q * ns)] = v[q].re; out_im[pad_slot<PADSH>(o + q * ns)] = v[q].im; }
+        for (int q = 0; q < R; q++) { out_re[pad_slot<PADOUT>(o + q * ns)] = v[q].re; out_im[pad_slot<PADOUT>(o + q * ns)] = v[q].im; }
     }
 }
 

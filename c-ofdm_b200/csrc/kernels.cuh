@@ -40,19 +40,19 @@ COFDM_DEV void store_sample_pair(void *frame_out, int idx /*even sample index*/,
     }
 }
 
-// rel = sum(mask*|X|^2) / sum(|X|^2) of the 256 samples a warp has staged in A at pad_slot<3>(i) (B = scratch, both
+// rel = sum(mask*|X|^2) / sum(|X|^2) of the 256 samples a warp has staged in A at slot i (unpadded; B = scratch, both
 // kT2Slots long); every lane returns it.
 // Blocks with zero or NaN energy report 0 (Frame.hpp:132-138 `continue`).
 COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane) {
     // total spectral energy by Parseval: sum_k |X_k|^2 = 256 * sum_n |x_n|^2 (saves evaluating unmasked bins)
     float tot = 0.f;
 #pragma unroll
-    for (int i = 0; i < 8; i++) tot += cnorm2(A[pad_slot<3>(lane + 32 * i)]);
+    for (int i = 0; i < 8; i++) tot += cnorm2(A[lane + 32 * i]);
     tot *= 256.0f;
     __syncwarp();
-    stockham_pass<8, false, false, 3>(A, B, 256, 1, P.tw_t2, lane, 32);
+    stockham_pass<8, false, false, 0, 4>(A, B, 256, 1, P.tw_t2, lane, 32);
     __syncwarp();
-    stockham_pass<8, false, true, 3>(B, A, 256, 8, P.tw_t2, lane, 32);      // twiddle index <= 7*7*4 < 256
+    stockham_pass<8, false, true, 4, 64>(B, A, 256, 8, P.tw_t2, lane, 32);  // twiddle index <= 7*7*4 < 256
     __syncwarp();
     // last pass (radix 4, ns = 64): butterfly j yields bins j, j+64, j+128, j+192; only butterflies that feed a
     // masked bin are evaluated (the shipped mask covers bins 12..22 and 46..56: 22 of 64 butterflies)
@@ -68,7 +68,7 @@ COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane)
             float2 v[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                v[q] = A[pad_slot<3>(j + 64 * q)];
+                v[q] = A[pad_slot<64>(j + 64 * q)];
                 if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_t2[q * j]));           // q*j <= 3*63 < 256
             }
             dft4<false>(v);
@@ -89,7 +89,7 @@ COFDM_DEV float t2sin_block_rel(const Params &P, float2 *A, float2 *B, int lane)
 // shared memory), rel = sum(mask*|X|^2) / sum(|X|^2); blocks with zero or NaN energy report 0.
 // ------------------------------------------------------------------------------------------------
 constexpr int kT2WarpsPerCta = 8;
-constexpr int kT2Slots = 288;                  // 256 samples at pad_slot<3>: conflict-free Stockham scatter
+constexpr int kT2Slots = 288;                  // 256 samples + padding (pad_slot<4>: 271, pad_slot<64>: 280): conflict-free Stockham passes
 template <int FMT>
 __global__ void __launch_bounds__(32 * kT2WarpsPerCta)
 t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
@@ -105,12 +105,12 @@ t2sin_metric_kernel(const Params P, const void *__restrict__ samples, long long 
 #pragma unroll
         for (int i = 0; i < 8; i++) {
             const unsigned w = __ldg(src + lane + 32 * i);
-            A[pad_slot<3>(lane + 32 * i)] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+            A[lane + 32 * i] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
         }
     } else {
         const float2 *src = reinterpret_cast<const float2 *>(samples) + s0;
 #pragma unroll
-        for (int i = 0; i < 8; i++) A[pad_slot<3>(lane + 32 * i)] = __ldg(src + lane + 32 * i);
+        for (int i = 0; i < 8; i++) A[lane + 32 * i] = __ldg(src + lane + 32 * i);
     }
     const float rel = t2sin_block_rel(P, A, B, lane);
     if (lane == 0) rel_out[blk] = rel;
@@ -169,7 +169,7 @@ template <int FMT>
 __global__ void __launch_bounds__(32 * kT2PairWarps)
 t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long start, long long n_blocks,
                      float *__restrict__ rel_out) {
-    __shared__ float2 buf[kT2PairWarps][4][288];                // per warp: re / im planes of two ping-pong buffers, padded (pad_slot<3>)
+    __shared__ float2 buf[kT2PairWarps][4][288];                // per warp: re / im planes of two ping-pong buffers, padded (pad_slot<4> / <64>)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const long long blk = 2 * ((long long)blockIdx.x * kT2PairWarps + warp);
     if (blk >= n_blocks) return;
@@ -190,14 +190,14 @@ t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long
             x0 = __ldg(src);
             if (has1) x1 = __ldg(src + 256);
         }
-        Are[pad_slot<3>(lane + 32 * i)] = make_float2(x0.x, x1.x);
-        Aim[pad_slot<3>(lane + 32 * i)] = make_float2(x0.y, x1.y);
+        Are[lane + 32 * i] = make_float2(x0.x, x1.x);
+        Aim[lane + 32 * i] = make_float2(x0.y, x1.y);
         tot.x += cnorm2(x0); tot.y += cnorm2(x1);              // Parseval: sum_k |X_k|^2 = 256 sum_n |x_n|^2
     }
     __syncwarp();
-    stockham_pass_pc<8, false, false, 3>(Are, Aim, Bre, Bim, 256, 1, P.tw_t2, lane, 32);
+    stockham_pass_pc<8, false, false, 0, 4>(Are, Aim, Bre, Bim, 256, 1, P.tw_t2, lane, 32);
     __syncwarp();
-    stockham_pass_pc<8, false, true, 3>(Bre, Bim, Are, Aim, 256, 8, P.tw_t2, lane, 32);   // twiddle index <= 7*7*4 < 256
+    stockham_pass_pc<8, false, true, 4, 64>(Bre, Bim, Are, Aim, 256, 8, P.tw_t2, lane, 32);   // twiddle index <= 7*7*4 < 256
     __syncwarp();
     // last pass (radix 4, ns = 64), only butterflies that feed a masked bin (see t2sin_block_rel)
     float2 sine = make_float2(0.f, 0.f);
@@ -212,7 +212,7 @@ t2sin_metric2_kernel(const Params P, const void *__restrict__ samples, long long
             pc v[4];
 #pragma unroll
             for (int q = 0; q < 4; q++) {
-                v[q].re = Are[pad_slot<3>(j + 64 * q)]; v[q].im = Aim[pad_slot<3>(j + 64 * q)];
+                v[q].re = Are[pad_slot<64>(j + 64 * q)]; v[q].im = Aim[pad_slot<64>(j + 64 * q)];
                 if (q > 0) v[q] = cmul(v[q], __ldg(&P.tw_t2[q * j]));
             }
             dft4<false>(v);

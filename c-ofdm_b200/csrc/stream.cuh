@@ -92,7 +92,7 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
                 if (c < cyc) {
                     float2 *A = fft + (size_t)warp * 2 * kT2Slots, *B = A + kT2Slots;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) A[pad_slot<3>(lane + 32 * i)] = sample(pos + c * 256 + lane + 32 * i);
+                    for (int i = 0; i < 8; i++) A[lane + 32 * i] = sample(pos + c * 256 + lane + 32 * i);
                     rel = t2sin_block_rel(P, A, B, lane);
                 }
                 if (lane == 0) relv[warp] = rel;
