@@ -1147,7 +1147,7 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
         const long long base = total_blocks / ns, rem = total_blocks % ns;
         const long long b0 = r * base + std::min(r, rem), b1 = b0 + base + (r < rem ? 1 : 0);
         const long long b1x = std::min(total_blocks, b1 + (b1 < total_blocks ? 1 : 0));
-        shards[(size_t)r] = StreamShard{b0 * block, b1x - b0};
+        shards[(size_t)r] = StreamShard{b0 * block, b1x - b0, b1 - b0};
         own_end[(size_t)r] = b1 * block;
         max_per = std::max(max_per, (b1x - b0) * block / msg + 2);
     }

@@ -311,39 +311,58 @@ preamble_corr_kernel(const Params P, const void *__restrict__ samples, long long
 // tap is at consecutive addresses across threads (conflict-free), and each tap costs 2 shared-memory loads for
 // 4 lags instead of 5.  L (filter length) must be a multiple of 4; plane >= (4 t_max + L + 3) / 4 + 1.
 // ------------------------------------------------------------------------------------------------
-COFDM_DEV void corr4_lags(const float2 *win4, int plane, const float2 *hf, int L, int t, float2 (&a)[4], float (&e)[4]) {
+// hf4[j] = (h.x, h.y, -h.y, h.x) of filter tap j (h already conjugated, Frame.cpp:285-293): a complex multiply-accumulate
+// a += x h is then TWO packed FFMA2 with a scalar-broadcast operand, a = fma(hf4.lo, x.x, a); a = fma(hf4.hi, x.y, a).
+// The window energy E_i = sum_j |x[i + j]|^2 (Frame.cpp:305-309) is accumulated for the thread's first lag only and slid to
+// its other three lags by adding the sample that enters and removing the one that leaves -- the reference's own recurrence
+// (Frame.cpp:327-333).
+COFDM_DEV void corr4_lags(const float2 *win4, int plane, const float4 *hf4, int L, int t, float2 (&a)[4], float (&e)[4]) {
     const float2 *w0 = win4, *w1 = win4 + plane, *w2 = win4 + 2 * plane, *w3 = win4 + 3 * plane;
     float2 x0 = w0[t], x1 = w1[t], x2 = w2[t], x3 = w3[t];
+    const float f0 = cnorm2(x0), f1 = cnorm2(x1), f2 = cnorm2(x2);          // the samples that leave the window for lags 1, 2, 3
     float2 a0 = make_float2(0.f, 0.f), a1 = a0, a2 = a0, a3 = a0;
-    float e0 = 0.f, e1 = 0.f, e2 = 0.f, e3 = 0.f;
+    float e0 = 0.f;
+#define COFDM_CMAC4(A0, X0, A1, X1, A2, X2, A3, X3, H)                                             \
+    do {                                                                                           \
+        const float2 hl_ = make_float2((H).x, (H).y), hh_ = make_float2((H).z, (H).w);             \
+        A0 = p_fma(hl_, p_bcast((X0).x), A0); A1 = p_fma(hl_, p_bcast((X1).x), A1);                \
+        A2 = p_fma(hl_, p_bcast((X2).x), A2); A3 = p_fma(hl_, p_bcast((X3).x), A3);                \
+        A0 = p_fma(hh_, p_bcast((X0).y), A0); A1 = p_fma(hh_, p_bcast((X1).y), A1);                \
+        A2 = p_fma(hh_, p_bcast((X2).y), A2); A3 = p_fma(hh_, p_bcast((X3).y), A3);                \
+    } while (0)
     for (int j = 0; j < L; j += 4) {
         const int k = t + (j >> 2) + 1;
-        float2 h = hf[j];                                      // Frame.cpp:320-321 (h is already conjugated)
-        cmac(a0, x0, h); cmac(a1, x1, h); cmac(a2, x2, h); cmac(a3, x3, h);
-        e0 += cnorm2(x0); e1 += cnorm2(x1); e2 += cnorm2(x2); e3 += cnorm2(x3);   // Frame.cpp:305-309,327-333
+        float4 h = hf4[j];
+        COFDM_CMAC4(a0, x0, a1, x1, a2, x2, a3, x3, h);
+        e0 += cnorm2(x0);
         x0 = w0[k];
-        h = hf[j + 1];
-        cmac(a0, x1, h); cmac(a1, x2, h); cmac(a2, x3, h); cmac(a3, x0, h);
-        e0 += cnorm2(x1); e1 += cnorm2(x2); e2 += cnorm2(x3); e3 += cnorm2(x0);
+        h = hf4[j + 1];
+        COFDM_CMAC4(a0, x1, a1, x2, a2, x3, a3, x0, h);
+        e0 += cnorm2(x1);
         x1 = w1[k];
-        h = hf[j + 2];
-        cmac(a0, x2, h); cmac(a1, x3, h); cmac(a2, x0, h); cmac(a3, x1, h);
-        e0 += cnorm2(x2); e1 += cnorm2(x3); e2 += cnorm2(x0); e3 += cnorm2(x1);
+        h = hf4[j + 2];
+        COFDM_CMAC4(a0, x2, a1, x3, a2, x0, a3, x1, h);
+        e0 += cnorm2(x2);
         x2 = w2[k];
-        h = hf[j + 3];
-        cmac(a0, x3, h); cmac(a1, x0, h); cmac(a2, x1, h); cmac(a3, x2, h);
-        e0 += cnorm2(x3); e1 += cnorm2(x0); e2 += cnorm2(x1); e3 += cnorm2(x2);
+        h = hf4[j + 3];
+        COFDM_CMAC4(a0, x3, a1, x0, a2, x1, a3, x2, h);
+        e0 += cnorm2(x3);
         x3 = w3[k];
     }
+#undef COFDM_CMAC4
+    // after the loop x0, x1, x2 are the samples 4 t + L, + L + 1, + L + 2: the ones that enter the window for lags 1, 2, 3
     a[0] = a0; a[1] = a1; a[2] = a2; a[3] = a3;
-    e[0] = e0; e[1] = e1; e[2] = e2; e[3] = e3;
+    e[0] = e0;
+    e[1] = e0 + (cnorm2(x0) - f0);
+    e[2] = e[1] + (cnorm2(x1) - f1);
+    e[3] = e[2] + (cnorm2(x2) - f2);
 }
 
 // preamble_corr4_kernel: the same search as preamble_corr_kernel on the 4-lags-per-thread core (needs pr_sin_len and
 // the lag count to be multiples of 4).  One CTA per candidate start.
 constexpr int kPc4Threads = 160;
 COFDM_HD size_t preamble_corr4_smem_bytes(int cor_size, int pr_sin_len) {
-    return (4 * ((size_t)(cor_size + pr_sin_len) / 4 + 4) + (size_t)pr_sin_len) * sizeof(float2);
+    return (4 * ((size_t)(cor_size + pr_sin_len) / 4 + 4) + 2 * (size_t)pr_sin_len) * sizeof(float2);
 }
 template <int FMT>
 __global__ void __launch_bounds__(kPc4Threads)
@@ -357,7 +376,7 @@ preamble_corr4_kernel(const Params P, const void *__restrict__ samples, long lon
     const int tid = threadIdx.x;
     const int L = P.pr_sin_len, NC = P.cor_size, WN = NC + L, plane = WN / 4 + 4;
     float2 *win4 = reinterpret_cast<float2 *>(smem_raw);
-    float2 *hf = win4 + 4 * (size_t)plane;
+    float4 *hf = reinterpret_cast<float4 *>(win4 + 4 * (size_t)plane);       // (plane is a multiple of 2 slots: 16-byte aligned)
     __shared__ int first;
     if (tid == 0) first = 0x7fffffff;
     const long long st = starts[c];
@@ -375,7 +394,7 @@ preamble_corr4_kernel(const Params P, const void *__restrict__ samples, long lon
         }
         win4[i] = x;
     }
-    for (int i = tid; i < L; i += kPc4Threads) hf[i] = __ldg(&P.matched[i]);
+    for (int i = tid; i < L; i += kPc4Threads) { const float2 hm = __ldg(&P.matched[i]); hf[i] = make_float4(hm.x, hm.y, -hm.y, hm.x); }
     __syncthreads();
     const float lvl2 = P.pr_level * P.pr_level;
     for (int t = tid; 4 * t < NC; t += kPc4Threads) {

@@ -23,19 +23,27 @@ namespace cofdmk {
 struct StreamShard {
     long long first_sample;   // where the shard starts in the capture
     long long n_blocks;       // whole SDR blocks it spans (overlap block included)
+    long long own_blocks;     // blocks it owns; frames found beyond them only serve to meet the next shard's chain
 };
+// frames a shard keeps detecting inside its overlap block.  The next shard starts cold at that block and may miss the first
+// frame or two (its sync-tone grid is not yet aligned to the traffic); both chains coincide from the first frame both detect,
+// so a short run into the overlap is enough -- the merge counts the boundaries where the chains did not meet (none in practice).
+constexpr int kScanOverlapFrames = 16;
 
 constexpr int kScanWarps = 10;
 constexpr int kScanThreads = 32 * kScanWarps;
 
 COFDM_HD size_t stream_scan_smem_bytes(int cor_size, int pr_sin_len) {
     const size_t plane = (size_t)(cor_size + pr_sin_len) / 4 + 4;
-    return (size_t)kScanWarps * 2 * kT2Slots * sizeof(float2) + 4 * plane * sizeof(float2) + (size_t)pr_sin_len * sizeof(float2) +
+    return (size_t)kScanWarps * 2 * kT2Slots * sizeof(float2) + 4 * plane * sizeof(float2) + 2 * (size_t)pr_sin_len * sizeof(float2) +
            (size_t)kScanWarps * sizeof(float) + 16;
 }
 
 // preconditions (checked by the host): t2sin_size == 256, pr_sin_len % 4 == 0, cor_size % 4 == 0
-__global__ void __launch_bounds__(kScanThreads, 2)
+#ifndef COFDM_SCAN_MINB
+#define COFDM_SCAN_MINB 3
+#endif
+__global__ void __launch_bounds__(kScanThreads, COFDM_SCAN_MINB)
 stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16 I,Q pairs */,
                    const StreamShard *__restrict__ shards, int n_shards, int rx_buf_size, long long iterations,
                    long long *__restrict__ pos_out /* [n_shards][max_per_shard] */, int max_per_shard,
@@ -47,7 +55,7 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
     const int L = P.pr_sin_len, NC = P.cor_size, WN = NC + L, plane = WN / 4 + 4;
     float2 *fft = reinterpret_cast<float2 *>(smem_raw);                 // [kScanWarps][2][kT2Slots]
     float2 *win4 = fft + (size_t)kScanWarps * 2 * kT2Slots;                      // [4][plane]: sample idx at win4[idx & 3][idx >> 2]
-    float2 *hf = win4 + 4 * (size_t)plane;
+    float4 *hf = reinterpret_cast<float4 *>(win4 + 4 * (size_t)plane);
     float *relv = reinterpret_cast<float *>(hf + L);
     int *first = reinterpret_cast<int *>(relv + kScanWarps);
 
@@ -78,11 +86,11 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
     };
     auto carry = [&]() { carry_base = cur_block * block + (threshold - out_sz); };   // rx.cpp:149-153 / 182-186
 
-    for (int i = tid; i < L; i += kScanThreads) hf[i] = __ldg(&P.matched[i]);
-    int found = 0;
+    for (int i = tid; i < L; i += kScanThreads) { const float2 hm = __ldg(&P.matched[i]); hf[i] = make_float4(hm.x, hm.y, -hm.y, hm.x); }
+    int found = 0, in_overlap = 0;
     if (buf_update()) {                                                    // rx.cpp:103-112
         long long pos = 0;
-        for (long long it = 0; it < iterations && found < max_per_shard; it++) {   // rx.cpp:126
+        for (long long it = 0; it < iterations && found < max_per_shard && in_overlap < kScanOverlapFrames; it++) {   // rx.cpp:126
             // ---- T2SIN_FORM::find_t2sin from pos (Frame.hpp:150-197): kScanWarps blocks per round ----
             long long hit = -1;
             const long long cyc = (ring - pos) / 256;
@@ -119,20 +127,27 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
                 win4[i] = idx < WN ? sample(pos + idx) : make_float2(0.f, 0.f);
             }
             __syncthreads();
-            if (4 * tid < NC) {
-                float2 a[4];
-                float e[4];
-                corr4_lags(win4, plane, hf, L, tid, a, e);
-                const float lvl2 = P.pr_level * P.pr_level;
-                int best = 0x7fffffff;                                     // Frame.cpp:319,364: first lag with c_i > pr_level
+            // only the FIRST lag above the level matters (Frame.cpp:364-376), and it sits one sync tone behind the block
+            // find_t2sin returned: the lower half of the lags is searched first, the upper half only if it holds no hit
+            int lag = 0x7fffffff;
+            const int half_thr = (NC / 4 + 1) / 2;                         // threads (4 lags each) per half
+            for (int hp = 0; hp < 2 && lag == 0x7fffffff; hp++) {
+                const int t4 = tid + hp * half_thr;
+                if (tid < half_thr && 4 * t4 < NC) {
+                    float2 a[4];
+                    float e[4];
+                    corr4_lags(win4, plane, hf, L, t4, a, e);
+                    const float lvl2 = P.pr_level * P.pr_level;
+                    int best = 0x7fffffff;                                 // Frame.cpp:319,364: first lag with c_i > pr_level
 #pragma unroll
-                for (int q = 3; q >= 0; q--)
-                    if (e[q] > 1.0f && cnorm2(a[q]) > lvl2 * e[q]) best = 4 * tid + q;
-                if (best != 0x7fffffff) atomicMin(first, best);
+                    for (int q = 3; q >= 0; q--)
+                        if (e[q] > 1.0f && cnorm2(a[q]) > lvl2 * e[q]) best = 4 * t4 + q;
+                    if (best != 0x7fffffff) atomicMin(first, best);
+                }
+                __syncthreads();
+                lag = *first;
+                __syncthreads();
             }
-            __syncthreads();
-            const int lag = *first;
-            __syncthreads();
             const long long preamble_begin = (lag == 0x7fffffff ? -10 : pos + lag) + 1;   // rx.cpp:158
             if (preamble_begin < -2) { pos += msg; continue; }             // :160-166
             pos = preamble_begin;                                          // :168
@@ -150,6 +165,7 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
             if (tid == 0) pos_out[(size_t)s * max_per_shard + found] = sh.first_sample + cur_block * block + pos - out_sz;
             pos += msg;                                                    // :198
             found++;
+            if (cur_block >= sh.own_blocks) in_overlap++;
         }
     }
     if (tid == 0) count_out[s] = found;

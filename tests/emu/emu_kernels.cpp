@@ -166,7 +166,7 @@ int emu_stream_scan(void *hv, const void *capture_i16, const long long *shard_fi
     const Params P = h->P;
     if (P.t2sin_size != 256 || (P.pr_sin_len % 4) || (P.cor_size % 4)) return -1;
     std::vector<StreamShard> sh(n_shards);
-    for (int i = 0; i < n_shards; i++) sh[i] = StreamShard{shard_first[i], shard_blocks[i]};
+    for (int i = 0; i < n_shards; i++) sh[i] = StreamShard{shard_first[i], shard_blocks[i], shard_blocks[i]};   // (own = all: no early stop inside the overlap)
     emu::launch(dim3(n_shards), dim3(kScanThreads), stream_scan_smem_bytes(P.cor_size, P.pr_sin_len), [&] {
         stream_scan_kernel(P, (const unsigned *)capture_i16, sh.data(), n_shards, h->T.rx_buf_size, (long long)h->T.iterations,
                            pos_out, max_per_shard, count_out);
