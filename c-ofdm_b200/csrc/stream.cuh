@@ -5,8 +5,8 @@
 // one-frame carry-over each time the position passes the last frame of the ring (rx.cpp:147-156,180-189) and
 // a fresh SDR block whenever the ring is exhausted (buf_update, rx.cpp:73-91).  Where it looks next depends on
 // what it found last, so the loop itself cannot be spread over threads -- but
-//   * each of its two searches is data parallel (10 candidate sync-tone blocks at a time, one FFT-256 per warp;
-//     the 640 lags of the preamble correlation over 160 threads), and
+//   * each of its two searches is data parallel (5 candidate sync-tone blocks at a time, one FFT-256 per warp;
+//     the lags of the preamble correlation, lower half first, over 80 threads with 4 lags each), and
 //   * a long capture can be cut into shards of whole SDR blocks that are scanned independently and merged
 //     (two chains that start from different states coincide from the first frame both detect; see
 //     c-ofdm_b200/stream.py and merge_stream_shards() in cofdm_host.cu).
@@ -30,7 +30,10 @@ struct StreamShard {
 // so a short run into the overlap is enough -- the merge counts the boundaries where the chains did not meet (none in practice).
 constexpr int kScanOverlapFrames = 16;
 
-constexpr int kScanWarps = 10;
+#ifndef COFDM_SCAN_WARPS
+#define COFDM_SCAN_WARPS 5
+#endif
+constexpr int kScanWarps = COFDM_SCAN_WARPS;
 constexpr int kScanThreads = 32 * kScanWarps;
 
 COFDM_HD size_t stream_scan_smem_bytes(int cor_size, int pr_sin_len) {
@@ -41,7 +44,7 @@ COFDM_HD size_t stream_scan_smem_bytes(int cor_size, int pr_sin_len) {
 
 // preconditions (checked by the host): t2sin_size == 256, pr_sin_len % 4 == 0, cor_size % 4 == 0
 #ifndef COFDM_SCAN_MINB
-#define COFDM_SCAN_MINB 3
+#define COFDM_SCAN_MINB 6
 #endif
 __global__ void __launch_bounds__(kScanThreads, COFDM_SCAN_MINB)
 stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16 I,Q pairs */,
@@ -99,8 +102,19 @@ stream_scan_kernel(const Params P, const unsigned *__restrict__ capture /* int16
                 float rel = 0.f;
                 if (c < cyc) {
                     float2 *A = fft + (size_t)warp * 2 * kT2Slots, *B = A + kT2Slots;
+                    const long long r0 = pos + c * 256;
+                    if (r0 >= out_sz && r0 + 256 <= ring) {
+                        // the whole block lies in the current SDR block: 8 coalesced loads, no per-sample index logic
+                        const unsigned *src = base + cur_block * block + (r0 - out_sz) + lane;
 #pragma unroll
-                    for (int i = 0; i < 8; i++) A[lane + 32 * i] = sample(pos + c * 256 + lane + 32 * i);
+                        for (int i = 0; i < 8; i++) {
+                            const unsigned w = __ldg(src + 32 * i);
+                            A[lane + 32 * i] = make_float2((float)(short)(w & 0xffffu), (float)(short)(w >> 16));
+                        }
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) A[lane + 32 * i] = sample(r0 + lane + 32 * i);
+                    }
                     rel = t2sin_block_rel(P, A, B, lane);
                 }
                 if (lane == 0) relv[warp] = rel;

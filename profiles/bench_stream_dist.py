@@ -25,7 +25,7 @@ from cofdm_b200 import stream as st, synth  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2-samples", type=int, default=30)
-    ap.add_argument("--shards", type=int, default=444, help="capture ranges per GPU = scanner CTAs: 3 resident per SM x 148")
+    ap.add_argument("--shards", type=int, default=888, help="capture ranges per GPU = scanner CTAs: 6 resident per SM x 148")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
