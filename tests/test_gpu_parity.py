@@ -601,3 +601,32 @@ def test_two_preamble_symbols_syncless_read_and_stream_on_the_any_size_path(cfg_
             pc.assert_bytes_match(pc.to_np(out)[i], want_b, want_r, o2.sizes.mod_type, "any-size read")
             assert np.array_equal(want_b, pay2[i])
         m2.close()
+
+
+def test_stream_4m_sample_capture_sharded_vs_oracle_loop(oracle_lib):
+    """BASELINE configs[3] parity at a few million samples: a 2^22-sample capture (shipped config: SDR blocks of 240 640 samples,
+    ~560 frames at random gaps over a noise floor) scanned in 17 shards of one block + overlap run each, and in 5 shards, against
+    ONE sequential pass of the oracle's rx.cpp loop: identical position lists, identical bytes, no unmerged boundary"""
+    from cofdm_b200 import stream
+    cfg = os.path.join(ROOT, "config", "config.txt")
+    o = oracle_lib.Oracle("port", cfg)
+    m = cb.Modem(cfg, device=0)
+    s = o.sizes
+    n = 600
+    pay = pc.synth.payloads(n, s.usefull_size, seed=41)
+    tx16 = m.tx_batch(pay, cb.CI16)
+    rng = np.random.default_rng(43)
+    fr = pc.synth.channel(tx16, seed=8, cfo=rng.uniform(-0.003, 0.003, n), phase=rng.uniform(0, 1, n), noise_sigma=1.0)
+    cap, _ = pc.synth.capture(fr, gaps=rng.integers(260, 2500, n), noise_sigma=3.0, seed=9, tail=s.output_size * 2)
+    blk = stream.block_samples(s)
+    n_samples = min(cap.shape[0], 1 << 22) // blk * blk
+    cap = np.ascontiguousarray(cap[:n_samples])
+    assert n_samples // blk >= 17
+    want_pos, want_by = o.rx_stream(cap)
+    assert len(want_pos) > 500
+    for shards in (17, 5, 1):
+        pos, by, unmerged = m.rx_stream(cap, shards=shards, return_unmerged=True)
+        assert unmerged == 0
+        assert pos.tolist() == want_pos.tolist(), shards
+        assert np.array_equal(by, want_by)
+    m.close()
