@@ -339,10 +339,11 @@ class Modem:
                                                  _space(samples, starts, first)))
         return (first, cor) if want_cor else first
 
-    def rx_stream(self, capture_i16, max_frames=None, shards=1, want_bytes=True, return_unmerged=False):
+    def rx_stream(self, capture_i16, max_frames=None, shards=1, want_bytes=True, return_unmerged=False, bytes_on_device=False):
         """rx.cpp's acquisition loop over an int16 capture [N, 2] (numpy = host, torch cuda tensor = device)
         -> (preamble positions, payload bytes).  shards > 1: the capture is cut into that many ranges of whole
-        SDR blocks, each scanned by its own CTA, the chains merged (cofdm_rx_stream_sharded)."""
+        SDR blocks, each scanned by its own CTA, the chains merged (cofdm_rx_stream_sharded).
+        bytes_on_device (device captures only): the payloads come back as a torch cuda tensor and never cross PCIe."""
         s = self.sizes
         if isinstance(capture_i16, np.ndarray):
             cap = np.ascontiguousarray(capture_i16, dtype=np.int16).reshape(-1)
@@ -350,12 +351,19 @@ class Modem:
         else:
             self._follow(capture_i16)
             cap = capture_i16.contiguous()
-            n, space, ptr = cap.numel() // 2, DEVICE, cap.data_ptr()
+            n, space, ptr = cap.numel() // 2, DEVICE_IN, cap.data_ptr()
         if max_frames is None:
             max_frames = n // (s.ofdm_len * s.num_symb) + 2
         pos = np.zeros(max_frames, dtype=np.int64)
-        out = _host_buffer((max_frames if want_bytes else 0, s.usefull_size))
         k, um = C.c_size_t(0), C.c_size_t(0)
+        if bytes_on_device and want_bytes and space == DEVICE_IN:
+            import torch
+            dout = torch.empty((max_frames, s.usefull_size), dtype=torch.uint8, device=capture_i16.device)
+            self._chk(self.lib.cofdm_rx_stream_sharded(self.h, ptr, n, DEVICE, int(shards), max_frames, pos.ctypes.data,
+                                                       dout.data_ptr(), C.byref(k), C.byref(um)))
+            res = (pos[:k.value].copy(), dout[:k.value])
+            return res + (um.value,) if return_unmerged else res
+        out = _host_buffer((max_frames if want_bytes else 0, s.usefull_size))
         self._chk(self.lib.cofdm_rx_stream_sharded(self.h, ptr, n, space, int(shards), max_frames, pos.ctypes.data,
                                                    out.ctypes.data if want_bytes else None, C.byref(k), C.byref(um)))
         res = (pos[:k.value].copy(), out[:k.value] if want_bytes else None)   # a view: no second pass over the payload

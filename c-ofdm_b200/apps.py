@@ -167,7 +167,8 @@ def write_trace(path, positions, stage_ms, t_rx, t_mac, seqs, block_samples):
       FREQ_PHASE_SINH  0: the per-symbol CFO / phase corrections are fused into the two neighbouring kernels and cannot be timed apart
       PFC              device time of the demod kernel (cp_freq_sinh of the message symbols, FFT, pilots, equaliser, demap) / frames
       MAC              host time of MAC::read / frames
-      GATHER, MERGE, D2H   frame gather kernel, host-side list read-back + shard merge, payload copy-back, / frames
+      GATHER, MERGE, D2H   frame gather kernel (0 when every frame is demodulated in place), host-side list read-back + shard merge,
+                           payload copy-back, / frames
       CONVERT          upload of the capture (the device-side form_int16_to_double), on the first frame of each SDR block, per block
       FR_IN_BUF        ordinal of the frame inside its SDR block, from the detected positions
       TIME             wall time of the whole call / frames (includes what the stages above do not cover: launches, synchronisation)

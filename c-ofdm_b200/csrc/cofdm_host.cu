@@ -149,8 +149,11 @@ int launch_rx_generic(cofdm *h, cudaStream_t st, const void *samples, int fmt, s
 int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
                   uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int slot);
 int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t n_frames, void *frames, int fmt);
+// frame_pos (device, optional): record f starts at sample frame_pos[f] of `samples` (a buffer of buf_samples samples) instead
+// of at f * stride: the frames a scanner found are demodulated in place
 int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_frames, size_t stride,
-              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0, int slot = 0) {
+              uint8_t *bytes, unsigned long long *amb, const RxTaps &taps, int sync_less = 0, int slot = 0,
+              const long long *frame_pos = nullptr, size_t buf_samples = 0) {
     if (n_frames == 0) return COFDM_OK;
     if (!h->T.fused512_ok) {
         if (h->T.big_ok && h->big_on && !sync_less) return launch_rx_big(h, st, samples, fmt, n_frames, stride, bytes, amb, taps, slot);
@@ -163,7 +166,14 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     // records that are 16-byte aligned are staged by TMA bulk copies (cf32, or raw int16 wire data widened when read);
     // a frame cut out of a capture at an arbitrary sample is staged by the warp with plain loads
     const size_t sb = sample_bytes(fmt);
-    const bool al = ((uintptr_t)samples & 15) == 0 && (stride * sb) % 16 == 0;
+    // int16 records always take the TMA instances: the kernels copy from the aligned address below an unaligned record
+    bool al = ((uintptr_t)samples & 15) == 0 && (stride * sb) % 16 == 0 && frame_pos == nullptr;
+    if (fmt == COFDM_CI16 && ((uintptr_t)samples & 3) == 0) al = true;
+    if (frame_pos != nullptr && fmt != COFDM_CI16) return fail(COFDM_ERR_ARG, "rx: in-place frame positions need int16 records");
+    RxSrc rs{};
+    rs.frame_pos = frame_pos;
+    rs.lo = (const char *)samples;
+    rs.hi = (const char *)samples + (frame_pos != nullptr ? buf_samples : (n_frames - 1) * stride + (size_t)P.rx_len) * sb;
     // the acquire kernel's hand-over (40 bytes per frame), in the buffer of this pipeline slot
     FrameScal *fsc = nullptr;
     if (!sync_less) {
@@ -176,8 +186,8 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     if (!sync_less || taps.chan != nullptr) {
         const unsigned g4 = (unsigned)((n_frames + kAcqwWarps - 1) / kAcqwWarps);
 #define COFDM_ACQW(F, T) \
-        do { if (want) rx_acquire512w_kernel<F, T, true><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc, sync_less); \
-             else rx_acquire512w_kernel<F, T, false><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc, sync_less); } while (0)
+        do { if (want) rx_acquire512w_kernel<F, T, true><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc, sync_less, rs); \
+             else rx_acquire512w_kernel<F, T, false><<<g4, 32 * kAcqwWarps, rx_acquire512w_smem_bytes(), st>>>(P, samples, (long long)stride, (int)n_frames, taps, fsc, sync_less, rs); } while (0)
         if (fmt == COFDM_CI16) { if (al) COFDM_ACQW(kCI16, true); else COFDM_ACQW(kCI16, false); }
         else { if (al) COFDM_ACQW(kCF32, true); else COFDM_ACQW(kCF32, false); }
 #undef COFDM_ACQW
@@ -188,7 +198,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     {
         const size_t sm = rx_demod512_smem_bytes(P.num_symb);
         const unsigned thr = 32u * (unsigned)P.num_symb;
-#define COFDM_DM(F, T, W, MW, MD) rx_demod512_kernel<F, T, W, MW, MD><<<(unsigned)n_frames, thr, sm, st>>>(P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc)
+#define COFDM_DM(F, T, W, MW, MD) rx_demod512_kernel<F, T, W, MW, MD><<<(unsigned)n_frames, thr, sm, st>>>(P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, sync_less, fsc, rs)
         // production instances are specialised on the modulation order (QPSK, 16-QAM); everything else reads it from the configuration
 #define COFDM_DM_PICK(F, T) do { if (P.num_symb <= 8) { if (want) COFDM_DM(F, T, true, 8, 0); else if (P.mod_type == 4) COFDM_DM(F, T, false, 8, 4); \
                                                        else if (P.mod_type == 2) COFDM_DM(F, T, false, 8, 2); else COFDM_DM(F, T, false, 8, 0); } \
@@ -1111,8 +1121,10 @@ static void merge_stream_shards(const std::vector<std::vector<long long>> &lists
 
 int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples, int space, int n_shards, size_t max_frames,
                             long long *pr_begin_abs, uint8_t *bytes, size_t *n_found, size_t *n_unmerged) {
-    if (!h || !capture || !n_found || n_shards < 1 || (space != COFDM_HOST && space != COFDM_DEVICE))
+    if (!h || !capture || !n_found || n_shards < 1 || (space != COFDM_HOST && space != COFDM_DEVICE && space != COFDM_DEVICE_IN))
         return fail(COFDM_ERR_ARG, "cofdm_rx_stream_sharded: bad argument");
+    const bool bytes_on_device = space == COFDM_DEVICE;           // the payloads stay in device memory (4-byte aligned buffer)
+    if (bytes_on_device && bytes && ((uintptr_t)bytes & 3)) return fail(COFDM_ERR_ARG, "cofdm_rx_stream_sharded: device byte buffer must be 4-byte aligned");
     *n_found = 0;
     if (n_unmerged) *n_unmerged = 0;
     if (set_device(h)) return COFDM_ERR_CUDA;
@@ -1201,21 +1213,40 @@ int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples
         CU_TRY(h->scratch_c.reserve(found * sizeof(long long)));
         CU_TRY(cudaMemcpyAsync(h->scratch_c.p, merged.data(), found * sizeof(long long), cudaMemcpyHostToDevice, st));
         CU_TRY(h->pipe_in[0].reserve(std::min(found, batch_cap) * (size_t)P.rx_len * 4));
-        CU_TRY(h->pipe_out[0].reserve(std::min(found, batch_cap) * (size_t)P.bytes_per_frame));
+        if (!bytes_on_device) CU_TRY(h->pipe_out[0].reserve(std::min(found, batch_cap) * (size_t)P.bytes_per_frame));
         RxTaps none{};
-        for (size_t f0 = 0; f0 < found; f0 += batch_cap) {
-            const size_t n = std::min(batch_cap, found - f0);
-            if (tm) cudaEventRecord(h->sev[6], st);
-            stream_gather_kernel<<<(unsigned)n, 256, 0, st>>>(d_cap, total_blocks * block, (const long long *)h->scratch_c.p + f0, (int)n, P.rx_len, (unsigned *)h->pipe_in[0].p);
-            if (int rc = check_launch(h, "stream_gather")) return rc;
-            if (tm) cudaEventRecord(h->sev[7], st);
-            if (int rc = launch_rx(h, st, h->pipe_in[0].p, COFDM_CI16, n, (size_t)P.rx_len, (uint8_t *)h->pipe_out[0].p, nullptr, none)) return rc;
+        // Frames that lie wholly inside the capture are demodulated IN PLACE (the rx kernels take the position list; int16
+        // records need no alignment); a frame that sticks out of the capture (at most one at either end) goes through the
+        // gather kernel, which pads it with zeros like the reference's calloc'd ring.
+        static const bool inplace_on = [] { const char *e = std::getenv("COFDM_STREAM_INPLACE"); return !(e && std::atoi(e) == 0); }();
+        const long long total_samples = total_blocks * block;
+        size_t i0 = 0, i1 = found;
+        while (i0 < found && merged[i0] < 0) i0++;
+        while (i1 > i0 && merged[i1 - 1] + (long long)P.rx_len > total_samples) i1--;
+        if (!inplace_on) i0 = i1 = found;
+        auto run = [&](size_t f0, size_t n, bool inplace) -> int {
+            uint8_t *dbytes = bytes_on_device ? bytes + f0 * (size_t)P.bytes_per_frame : (uint8_t *)h->pipe_out[0].p;
+            const long long *dpos = (const long long *)h->scratch_c.p + f0;
+            if (inplace) {
+                if (int rc = launch_rx(h, st, d_cap, COFDM_CI16, n, (size_t)P.rx_len, dbytes, nullptr, none, 0, 0, dpos, (size_t)total_samples)) return rc;
+            } else {
+                if (tm) cudaEventRecord(h->sev[6], st);
+                stream_gather_kernel<<<(unsigned)n, 256, 0, st>>>(d_cap, total_samples, dpos, (int)n, P.rx_len, (unsigned *)h->pipe_in[0].p);
+                if (int rc = check_launch(h, "stream_gather")) return rc;
+                if (tm) cudaEventRecord(h->sev[7], st);
+                if (int rc = launch_rx(h, st, h->pipe_in[0].p, COFDM_CI16, n, (size_t)P.rx_len, dbytes, nullptr, none)) return rc;
+            }
             if (tm) cudaEventRecord(h->sev[3], st);
-            CU_TRY(cudaMemcpyAsync(bytes + f0 * (size_t)P.bytes_per_frame, h->pipe_out[0].p, n * (size_t)P.bytes_per_frame, cudaMemcpyDeviceToHost, st));
+            if (!bytes_on_device)
+                CU_TRY(cudaMemcpyAsync(bytes + f0 * (size_t)P.bytes_per_frame, h->pipe_out[0].p, n * (size_t)P.bytes_per_frame, cudaMemcpyDeviceToHost, st));
             if (tm) cudaEventRecord(h->sev[4], st);
             CU_TRY(cudaStreamSynchronize(st));
-            if (tm) { add_stage(h, COFDM_STAGE_GATHER, h->sev[6], h->sev[7]); collect_rx_stage(h); add_stage(h, COFDM_STAGE_D2H, h->sev[3], h->sev[4]); }
-        }
+            if (tm) { if (!inplace) add_stage(h, COFDM_STAGE_GATHER, h->sev[6], h->sev[7]); collect_rx_stage(h); add_stage(h, COFDM_STAGE_D2H, h->sev[3], h->sev[4]); }
+            return COFDM_OK;
+        };
+        for (size_t f0 = 0; f0 < i0; f0 += batch_cap) if (int rc = run(f0, std::min(batch_cap, i0 - f0), false)) return rc;
+        for (size_t f0 = i0; f0 < i1; f0 += batch_cap) if (int rc = run(f0, std::min(batch_cap, i1 - f0), true)) return rc;
+        for (size_t f0 = i1; f0 < found; f0 += batch_cap) if (int rc = run(f0, std::min(batch_cap, found - f0), false)) return rc;
     }
     *n_found = found;
     return COFDM_OK;

@@ -97,6 +97,15 @@ COFDM_DEV void warp_stage_symbol(void *dst, const char *src, int lane) {
     }
 }
 
+// Where one warp's 640 samples come from.  frame_pos (optional): record f starts at sample frame_pos[f] of `samples` instead of
+// f * frame_stride -- frames detected in a capture are demodulated IN PLACE.  int16 records need not be 16-byte aligned for
+// the TMA path: the bulk copy starts at the aligned address below the record and the warp reads its samples `off` bytes in
+// (the copy is skipped for the rare record whose aligned span would leave [lo, hi), which is staged by plain loads).
+struct RxSrc {
+    const long long *frame_pos;
+    const char *lo, *hi;
+};
+
 // sample `idx` of a symbol staged in shared memory: float2, or int16 I,Q wire data widened here
 template <int FMT>
 COFDM_DEV float2 staged_at(const void *region, int idx) {
@@ -185,7 +194,7 @@ template <int FMT, bool USE_TMA, bool TAPS, int MAXW, int MOD>
 __global__ void __launch_bounds__(32 * MAXW, MAXW <= 8 ? COFDM_DEMOD_MINB : 1)
 rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
                    uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous, const RxTaps taps,
-                   const int sync_less, const FrameScal *__restrict__ fscal) {
+                   const int sync_less, const FrameScal *__restrict__ fscal, const RxSrc rs) {
     COFDM_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // warp-uniform by construction: lets the compiler keep the warp's bases in uniform registers
@@ -196,15 +205,24 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     char *region = reinterpret_cast<char *>(smem_raw) + (size_t)warp * kDemodRegion;
     DemodShared *M = reinterpret_cast<DemodShared *>(smem_raw + (size_t)nw * kDemodRegion);
     const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
-    const char *src = reinterpret_cast<const char *>(samples) + ((size_t)frame * (size_t)frame_stride + (size_t)s * 640) * sample_bytes;
+    const size_t rec0 = rs.frame_pos != nullptr ? (size_t)__ldg(rs.frame_pos + frame) : (size_t)frame * (size_t)frame_stride;
+    const char *src = reinterpret_cast<const char *>(samples) + (rec0 + (size_t)s * 640) * sample_bytes;
 
     // ---- stage the symbol: one TMA bulk copy issued by the warp that consumes it ----
-    if (USE_TMA) {
+    unsigned off = 0;                              // int16 records: bytes between the 16-byte aligned copy start and the first sample
+    bool tma = USE_TMA;
+    if (USE_TMA && FMT == kCI16) {
+        off = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        tma = src - off >= rs.lo && src - off + ((640 * 4 + off + 15u) & ~15u) <= rs.hi;
+        if (!tma) off = 0;
+    }
+    if (tma) {
         if (lane == 0) {
+            const unsigned nb = (640 * (unsigned)sample_bytes + off + 15u) & ~15u;
             mbar_init(&M->mbar[warp], 1);
             mbar_fence_init();
-            mbar_arrive_expect_tx(&M->mbar[warp], 640 * (unsigned)sample_bytes);
-            tma_load_1d(region, src, 640 * (unsigned)sample_bytes, &M->mbar[warp]);
+            mbar_arrive_expect_tx(&M->mbar[warp], nb);
+            tma_load_1d(region, src - off, nb, &M->mbar[warp]);
         }
     } else {
         warp_stage_symbol<FMT>(region, src, lane);
@@ -243,14 +261,15 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         if (TAPS && tid == 0) { M->theta_t[0] = th0; M->mshift[0] = m0; }
     }
     __syncwarp();
-    if (USE_TMA) mbar_wait(&M->mbar[warp], 0);
+    if (tma) mbar_wait(&M->mbar[warp], 0);
 
     // ---- the lane's 16 body samples v[n1] = x[128 + lane + 32 n1] and 4 CP samples cp[c] = x[lane + 32 c] ----
     float2 v[16], cp[4];
+    const char *stg = region + off;
 #pragma unroll
-    for (int n1 = 0; n1 < 16; n1++) v[n1] = staged_at<FMT>(region, 128 + lane + 32 * n1);
+    for (int n1 = 0; n1 < 16; n1++) v[n1] = staged_at<FMT>(stg, 128 + lane + 32 * n1);
 #pragma unroll
-    for (int c = 0; c < 4; c++) cp[c] = staged_at<FMT>(region, lane + 32 * c);
+    for (int c = 0; c < 4; c++) cp[c] = staged_at<FMT>(stg, lane + 32 * c);
     __syncwarp();                                  // the region may now be reused (phasor table, exchange)
 
     // ---- CP correlation (Frame.hpp:251-253): CP sample j pairs with body sample j + 512, i.e. n1 = 12 + c ----
@@ -422,7 +441,7 @@ COFDM_HD constexpr size_t rx_acquire512w_smem_bytes() { return (size_t)kAcqwWarp
 template <int FMT, bool USE_TMA, bool TAPS>
 __global__ void __launch_bounds__(32 * kAcqwWarps, 5)
 rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
-                      const RxTaps taps, FrameScal *__restrict__ fscal, const int sync_less) {
+                      const RxTaps taps, FrameScal *__restrict__ fscal, const int sync_less, const RxSrc rs) {
     COFDM_DYN_SMEM(smem_raw);
     const int tid = threadIdx.x, lane = tid & 31;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
@@ -432,23 +451,32 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
     float2 *A = reinterpret_cast<float2 *>(S + kAcqwS);
     uint64_t *mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kAcqwWarps * kAcqwRegion) + warp;
     const size_t sample_bytes = (FMT == kCI16) ? 4 : 8;
-    const char *src = reinterpret_cast<const char *>(samples) + (size_t)frame * (size_t)frame_stride * sample_bytes;
-    if (USE_TMA) {
+    const size_t rec0 = rs.frame_pos != nullptr ? (size_t)__ldg(rs.frame_pos + frame) : (size_t)frame * (size_t)frame_stride;
+    const char *src = reinterpret_cast<const char *>(samples) + rec0 * sample_bytes;
+    unsigned off = 0;                                  // see RxSrc
+    bool tma = USE_TMA;
+    if (USE_TMA && FMT == kCI16) {
+        off = (unsigned)(reinterpret_cast<uintptr_t>(src) & 15u);
+        tma = src - off >= rs.lo && src - off + ((640 * 4 + off + 15u) & ~15u) <= rs.hi;
+        if (!tma) off = 0;
+    }
+    if (tma) {
         if (lane == 0) {
+            const unsigned nb = (640 * (unsigned)sample_bytes + off + 15u) & ~15u;
             mbar_init(mbar, 1);
             mbar_fence_init();
-            mbar_arrive_expect_tx(mbar, 640 * (unsigned)sample_bytes);
-            tma_load_1d(S, src, 640 * (unsigned)sample_bytes, mbar);
+            mbar_arrive_expect_tx(mbar, nb);
+            tma_load_1d(S, src - off, nb, mbar);
         }
     } else {
         warp_stage_symbol<FMT>(S, src, lane);
     }
     __syncwarp();
-    if (USE_TMA) mbar_wait(mbar, 0);
+    if (tma) mbar_wait(mbar, 0);
     // ---- the lane's 20 raw samples raw[u] = x[lane + 32 u] ----
     float2 raw[20];
 #pragma unroll
-    for (int u = 0; u < 20; u++) raw[u] = staged_at<FMT>(S, lane + 32 * u);
+    for (int u = 0; u < 20; u++) raw[u] = staged_at<FMT>(S + off, lane + 32 * u);
     __syncwarp();                                      // S may be overwritten from here on
 
     int kc = 0;

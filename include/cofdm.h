@@ -168,8 +168,10 @@ int cofdm_rx_stream(cofdm_t *h, const int16_t *capture, size_t n_samples, size_t
  * every range scanned by its own CTA running the state machine of rx.cpp:126-198 on the device (stream.cuh), the
  * per-range chains merged on the host: the earlier range's chain is followed until it meets a preamble position the
  * later range also found (two chains coincide from the first frame both detect); a frame belongs to the range
- * that contains its preamble.  n_shards = 1 is exactly cofdm_rx_stream.  `capture` is a host pointer (COFDM_HOST,
- * uploaded once) or a device pointer (COFDM_DEVICE); pr_begin_abs / bytes / counters are host memory.
+ * that contains its preamble.  n_shards = 1 is exactly cofdm_rx_stream.  space: COFDM_HOST = `capture` and `bytes` are host
+ * memory (the capture is uploaded once); COFDM_DEVICE_IN = `capture` on the device, `bytes` on the host; COFDM_DEVICE =
+ * `capture` AND `bytes` on the device (the payloads never cross PCIe; 4-byte aligned, max_frames * usefull_size bytes).
+ * pr_begin_abs and the counters are always host memory.
  * *n_unmerged = boundaries whose chains did not meet inside the overlap (0 in practice). */
 int cofdm_rx_stream_sharded(cofdm_t *h, const int16_t *capture, size_t n_samples, int space, int n_shards,
                             size_t max_frames, long long *pr_begin_abs, uint8_t *bytes, size_t *n_found,

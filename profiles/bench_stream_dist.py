@@ -25,6 +25,7 @@ from cofdm_b200 import stream as st, synth  # noqa: E402
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--log2-samples", type=int, default=30)
+    ap.add_argument("--host-bytes", action="store_true", help="copy the payloads back to (pinned) host memory instead of leaving them on the GPU")
     ap.add_argument("--shards", type=int, default=888, help="capture ranges per GPU = scanner CTAs: 6 resident per SM x 148")
     args = ap.parse_args()
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
@@ -56,7 +57,7 @@ def main():
     del cap_d
 
     def one_pass():
-        pos, by = m.rx_stream(mine, shards=args.shards)
+        pos, by = m.rx_stream(mine, shards=args.shards, bytes_on_device=not args.host_bytes)
         pos_abs = np.asarray(pos, dtype=np.int64) + s0
         if world == 1:
             tag = np.stack([np.zeros(len(pos_abs), np.int64), np.arange(len(pos_abs), dtype=np.int64)], axis=1)
@@ -84,7 +85,11 @@ def main():
     r = pos_abs % L
     j = np.clip(np.searchsorted(starts + s.t2sin_size - 64, r) - 1, 0, nfr - 1)
     near = np.abs(r - (starts[j] + s.t2sin_size)) < 64
-    good = int((near & (by == pay[j]).all(axis=1)).sum())
+    if args.host_bytes:
+        good = int((near & (by == pay[j]).all(axis=1)).sum())
+    else:   # payloads are on the GPU: compare there
+        pay_d = torch.from_numpy(pay).to(dev)
+        good = int((torch.from_numpy(near).to(dev) & (by == pay_d[torch.from_numpy(j).to(dev)]).all(dim=1)).sum().item())
     tot = torch.tensor([good, len(pos_abs), int(t_local * 1e6), int(stages["scan"] * 1e3)], dtype=torch.int64, device=dev)
     mx = tot.clone()
     if world > 1:
@@ -98,6 +103,7 @@ def main():
                           "seconds_max_rank_local": mx[2].item() / 1e6, "frames_s": len(mpos) / dt, "msamples_s": n_total / dt / 1e6,
                           "scan_kernel_ms_max_rank": scan_ms, "scan_gbs_aggregate": n_total * 4 / (scan_ms * 1e-3) / 1e9 if scan_ms > 0 else None,
                           "stage_ms_rank0": stages, "shards_per_gpu": args.shards, "scaling": "strong",
+                          "payloads": "host (pinned)" if args.host_bytes else "device",
                           "note": "wall clock incl. per-rank scan + gather + demod of device-resident int16, NCCL all_gather of the int64 position lists, merge on every rank; payloads stay on their rank"}))
     if world > 1:
         dist.destroy_process_group()

@@ -33,7 +33,9 @@ static void emu_acquire512w(const Params &P, const void *samples, int fmt, int u
                             const RxTaps &taps, FrameScal *fs, int sync_less) {
     const dim3 grid((n_frames + kAcqwWarps - 1) / kAcqwWarps), block(32 * kAcqwWarps);
     const size_t sm = rx_acquire512w_smem_bytes();
-#define EMU_AQ(F, T) emu::launch(grid, block, sm, [&] { rx_acquire512w_kernel<F, T, TAPS>(P, samples, stride, n_frames, taps, fs, sync_less); })
+    const size_t sbytes = fmt == kCI16 ? 4 : 8;
+    const RxSrc rs{nullptr, (const char *)samples, (const char *)samples + ((size_t)(n_frames - 1) * (size_t)stride + (size_t)P.rx_len) * sbytes};
+#define EMU_AQ(F, T) emu::launch(grid, block, sm, [&] { rx_acquire512w_kernel<F, T, TAPS>(P, samples, stride, n_frames, taps, fs, sync_less, rs); })
     if (fmt == kCI16) { if (use_tma) EMU_AQ(kCI16, true); else EMU_AQ(kCI16, false); }
     else { if (use_tma) EMU_AQ(kCF32, true); else EMU_AQ(kCF32, false); }
 #undef EMU_AQ
@@ -45,7 +47,9 @@ static void emu_demod512(const Params &P, const void *samples, int fmt, int use_
                          uint8_t *out, unsigned long long *amb, const RxTaps &taps, const FrameScal *fs, int sync_less) {
     const dim3 grid(n_frames), block(32 * P.num_symb);
     const size_t sm = rx_demod512_smem_bytes(P.num_symb);
-#define EMU_DM(F, T, MW, MD) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW, MD>(P, samples, stride, n_frames, out, amb, taps, sync_less, fs); })
+    const size_t sbytes = fmt == kCI16 ? 4 : 8;
+    const RxSrc rs{nullptr, (const char *)samples, (const char *)samples + ((size_t)(n_frames - 1) * (size_t)stride + (size_t)P.rx_len) * sbytes};
+#define EMU_DM(F, T, MW, MD) emu::launch(grid, block, sm, [&] { rx_demod512_kernel<F, T, TAPS, MW, MD>(P, samples, stride, n_frames, out, amb, taps, sync_less, fs, rs); })
     // as launch_rx does: production instances specialised on QPSK / 16-QAM, everything else generic
 #define EMU_DM_PICK(F, T) do { if (P.num_symb <= 8) { if (!TAPS && P.mod_type == 4) EMU_DM(F, T, 8, TAPS ? 0 : 4); else if (!TAPS && P.mod_type == 2) EMU_DM(F, T, 8, TAPS ? 0 : 2); else EMU_DM(F, T, 8, 0); } \
                                else EMU_DM(F, T, kMaxFusedSymb, 0); } while (0)

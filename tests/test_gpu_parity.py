@@ -527,7 +527,8 @@ def test_apps_tx_file_rx_file_round_trip(cfg_dir, tmp_path):
         assert sum(1 for _ in open(tmp_path / "LOG.txt")) == 61
         # the trace is measured: every device stage of the call has a positive CUDA-event time
         st = r["stage_ms"]
-        assert all(st[k] > 0 for k in ("upload", "scan", "gather", "acquire", "demod", "d2h")), st
+        # (gather is 0 unless a frame sticks out of the capture: the frames are demodulated in place)
+        assert all(st[k] > 0 for k in ("upload", "scan", "acquire", "demod", "d2h")), st
         first = dict(p.split(":", 1) for p in open(tmp_path / "LOG.txt").readline().split())
         assert abs(float(first["PFC"]) - st["demod"] * 1e-3 / 61) < 1e-9 and abs(float(first["T2SIN"]) - st["scan"] * 1e-3 / 61) < 1e-9
     m.close()
@@ -629,4 +630,7 @@ def test_stream_4m_sample_capture_sharded_vs_oracle_loop(oracle_lib):
         assert unmerged == 0
         assert pos.tolist() == want_pos.tolist(), shards
         assert np.array_equal(by, want_by)
+    # capture resident on the device, payloads left on the device (COFDM_DEVICE: nothing but the position list crosses PCIe)
+    pos, by_d = m.rx_stream(torch.from_numpy(cap).cuda(), shards=17, bytes_on_device=True)
+    assert pos.tolist() == want_pos.tolist() and by_d.is_cuda and np.array_equal(by_d.cpu().numpy(), want_by)
     m.close()
