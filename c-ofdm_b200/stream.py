@@ -46,7 +46,9 @@ def merge_shards(shards, sizes):
         start = 0
         if len(carry_pos):
             # follow the previous (true) chain until it meets this rank's chain
-            hit = np.nonzero(np.isin(carry_pos, pos, assume_unique=True))[0]
+            # (positions are increasing: a binary search of the short carry list in this rank's list, no sort)
+            at = np.searchsorted(pos, carry_pos)
+            hit = np.nonzero((at < len(pos)) & (pos[np.minimum(at, max(len(pos) - 1, 0))] == carry_pos))[0] if len(pos) else np.zeros(0, np.int64)
             if len(hit):
                 k = int(hit[0])
                 out_pos.append(carry_pos[:k])
