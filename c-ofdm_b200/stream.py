@@ -73,6 +73,60 @@ def merge_shards(shards, sizes):
     return np.concatenate(out_pos) if out_pos else np.zeros(0, np.int64), b, unmerged
 
 
+def merge_ranges(lists, sizes):
+    """The merge of merge_shards without per-frame rows: lists = [(positions, b0, b1)] over ranks in order.  The frames of
+    rank r that belong to the merged list are ONE contiguous slice [lo_r, hi_r) of its own list (its own range from where the
+    previous rank's chain met it, plus the first frames of its overlap run up to where the next rank's chain meets it).
+    Returns (merged positions, [(lo_r, hi_r)], unmerged boundaries)."""
+    blk = block_samples(sizes)
+    ranges, unmerged = [], 0
+    prev = None                                   # (pos, n_own) of the previous rank
+    starts = []
+    for pos, b0, b1 in lists:
+        pos = np.asarray(pos, dtype=np.int64)
+        start = 0
+        if prev is not None:
+            ppos, pn_own = prev
+            carry = ppos[pn_own:]
+            k = len(carry)                        # frames of the previous rank's overlap run that stay
+            if len(carry):
+                at = np.searchsorted(pos, carry)
+                hit = np.nonzero((at < len(pos)) & (pos[np.minimum(at, max(len(pos) - 1, 0))] == carry))[0] if len(pos) else np.zeros(0, np.int64)
+                if len(hit):
+                    k = int(hit[0])
+                    start = int(at[k])
+                else:
+                    unmerged += 1
+                    start = int(np.searchsorted(pos, carry[-1] + 1))
+            ranges[-1] = (ranges[-1][0], pn_own + k)
+        n_own = max(start, int(np.searchsorted(pos, b1 * blk)))
+        ranges.append((start, n_own))
+        prev = (pos, n_own)
+    if prev is not None:
+        ranges[-1] = (ranges[-1][0], len(prev[0]))     # the last rank keeps everything it found
+    mpos = np.concatenate([np.asarray(p, dtype=np.int64)[lo:hi] for (p, _, _), (lo, hi) in zip(lists, ranges)]) if lists else np.zeros(0, np.int64)
+    return mpos, ranges, unmerged
+
+
+def gather_positions(pos_abs, b0, b1, max_frames, device=None):
+    """ONE fixed-size collective: every rank contributes [count, b0, b1, positions padded to max_frames] (int64) and gets
+    everybody's back.  max_frames = an upper bound known to all ranks (samples per slice / message.size + 2)."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size()
+    if device is None:
+        device = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    pos_abs = np.asarray(pos_abs, dtype=np.int64)
+    rec = np.full(max_frames + 3, -1, dtype=np.int64)
+    rec[0], rec[1], rec[2] = len(pos_abs), b0, b1
+    rec[3:3 + len(pos_abs)] = pos_abs
+    mine = torch.from_numpy(rec).to(device)
+    allr = torch.empty(world * (max_frames + 3), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(allr, mine)
+    allr = allr.cpu().numpy().reshape(world, max_frames + 3)
+    return [(allr[r, 3:3 + int(allr[r, 0])], int(allr[r, 1]), int(allr[r, 2])) for r in range(world)]
+
+
 def rx_stream_sharded(run, capture_i16, sizes, world):
     """run(capture_slice) -> (positions, bytes).  Emulates `world` ranks in one process (tests, single GPU)."""
     n = capture_i16.shape[0]

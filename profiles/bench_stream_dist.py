@@ -56,15 +56,15 @@ def main():
         mine[a - s0:e - s0] = cap_d[torch.arange(a, e, device=dev) % L]
     del cap_d
 
+    max_frames = (n_total // world + 2 * blk) // (s.ofdm_len * s.num_symb) + 2       # upper bound on a rank's frames, the same on every rank
+
     def one_pass():
         pos, by = m.rx_stream(mine, shards=args.shards, bytes_on_device=not args.host_bytes)
         pos_abs = np.asarray(pos, dtype=np.int64) + s0
         if world == 1:
-            tag = np.stack([np.zeros(len(pos_abs), np.int64), np.arange(len(pos_abs), dtype=np.int64)], axis=1)
-            lists = [(pos_abs, tag, b0, b1)]
-        else:
-            lists = st.gather_frame_lists(pos_abs, b0, b1, device=dev)
-        return pos_abs, by, st.merge_shards(lists, s)
+            return pos_abs, by, (pos_abs, [(0, len(pos_abs))], 0)
+        lists = st.gather_positions(pos_abs, b0, b1, max_frames, device=dev)      # the one collective of the job
+        return pos_abs, by, st.merge_ranges(lists, s)
 
     for _ in range(2):
         one_pass()
@@ -73,7 +73,7 @@ def main():
         dist.barrier()
     m.enable_timing(True)
     t0 = time.perf_counter()
-    pos_abs, by, (mpos, mtag, unmerged) = one_pass()
+    pos_abs, by, (mpos, ranges, unmerged) = one_pass()
     torch.cuda.synchronize()
     t_local = time.perf_counter() - t0
     if world > 1:

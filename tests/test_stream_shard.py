@@ -26,6 +26,16 @@ def test_sharded_stream_equals_sequential(oracle_lib, cfg_dir, world):
     assert unmerged == 0
     assert pos.tolist() == want_pos.tolist()
     assert np.array_equal(by, want_by)
+    # merge_ranges (what the multi-GPU job uses: no per-frame rows, one contiguous slice of every rank's list) gives the same
+    lists, rows = [], []
+    for r in range(world):
+        s0, s1, b0, b1 = stream.shard_slice(cap.shape[0], s, r, world)
+        p, b = o.rx_stream(cap[s0:s1])
+        lists.append((np.asarray(p, dtype=np.int64) + s0, b0, b1))
+        rows.append(b)
+    mpos, ranges, um = stream.merge_ranges(lists, s)
+    assert um == 0 and mpos.tolist() == want_pos.tolist()
+    assert np.array_equal(np.concatenate([rows[r][lo:hi] for r, (lo, hi) in enumerate(ranges)]), want_by)
 
 
 def _gather_worker(rank, world, port, cfg, q):
@@ -53,6 +63,11 @@ def _gather_worker(rank, world, port, cfg, q):
     lists = stream.gather_frame_lists(np.asarray(pos, dtype=np.int64) + s0, b0, b1)
     mpos, mtag, unmerged = stream.merge_shards(lists, s)
     mine = mtag[mtag[:, 0] == rank][:, 1]                    # which of MY frames belong to the merged list
+    # the one-collective form: fixed-width gather + range merge must agree
+    l2 = stream.gather_positions(np.asarray(pos, dtype=np.int64) + s0, b0, b1, max_frames=200)
+    mpos2, ranges, um2 = stream.merge_ranges(l2, s)
+    assert um2 == unmerged and mpos2.tolist() == mpos.tolist()
+    assert mine.tolist() == list(range(*ranges[rank]))
     want_pos, want_by = o.rx_stream(cap) if rank == 0 else (None, None)
     q.put((rank, mpos.tolist(), unmerged, by[mine].tolist(), mpos[mtag[:, 0] == rank].tolist(),
            None if want_pos is None else want_pos.tolist(), None if want_by is None else want_by.tolist()))
