@@ -609,6 +609,7 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
     if (lane == 0) {
         FrameScal f;
         f.kc = kc; f.m0 = m0; f.th0 = theta0; f.theta = theta; f.rot_theta = rot; f.a = la; f.b = lb;
+        f.eb1 = make_float2(1.f, 0.f); f.eb8 = f.eb1;             // (fft-512 demod kernel only)
         fscal[frame] = f;
     }
     if (TAPS) {
@@ -710,6 +711,7 @@ __global__ void big_bridge_kernel(const Params P, int n_frames, const GenFrame *
     f.kc = G.kc; f.m0 = 0;
     f.th0 = (float)((double)G.phit[0] + (double)P.fft_size * (double)G.kc / (double)P.pf_den);
     f.theta = G.theta; f.rot_theta = G.rot_theta; f.a = G.a; f.b = G.b;
+    f.eb1 = make_float2(1.f, 0.f); f.eb8 = f.eb1;
     fscal[frame] = f;
     if (taps.scal != nullptr) {
         float *sc = taps.scal + (size_t)frame * 48;

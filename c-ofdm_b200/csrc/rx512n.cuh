@@ -32,12 +32,14 @@ namespace cofdmk {
 
 constexpr int kRxMaxSym = 16;        // frame symbols (preamble + message) the kernels are dimensioned for
 
-// what the acquire kernel hands to the demod kernel, per frame (five 8-byte words)
+// what the acquire kernel hands to the demod kernel, per frame (seven 8-byte words)
 struct FrameScal {
     int kc, m0;             // coarse shift numerator (shift = kc / pf_den); whole-bin shift of the preamble
     float th0, theta;       // Arg of the preamble's CP correlation (turns); pr_phase_sinh angle (radians, taps only)
     float2 rot_theta;       // exp(-j theta)
     double a, b;            // chan_char_lq line
+    float2 eb1, eb8;        // exp(-j b), exp(-j 8 b): the equaliser's per-lane phasor exp(-j b k1) rides on the demod kernel's
+                            // pass-1 twiddle recurrence (V^k1 -> (V exp(-j b))^k1), so it costs two products instead of nine
 };
 
 // Constant phase (turns, mod 1) carried into symbol s by freq_shift's global sample index (Frame.hpp:341-347)
@@ -236,7 +238,15 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     const int kc = (int)__shfl_sync(0xffffffffu, fsw.x, 0);
     const uint2 aux = __ldg(&P.lane_aux[lane]);             // .x: combination `lane` (segment, offset) + the lane's routing bits; .y: straggler `lane`
     if (tid >= nw && tid < kRxMaxSym) M->pabs[tid] = 0.f;   // unused entries (the others are written by their warps); ordered by the block barrier
-    if (warp == 0) {
+    // The equaliser's factor exp(-j b i') splits into exp(-j b k1) per lane (k1 = lane >> 1 after the transform) and a factor per
+    // combination.  Production instances fold the per-lane part into the transform's pass-1 twiddles (eb1, eb8 from the acquire
+    // kernel); the instances with taps keep the spectrum untouched and multiply afterwards (table lcl).
+    float2 eb1 = make_float2(1.f, 0.f), eb8 = eb1;
+    if (!TAPS && !sync_less) {
+        eb1 = __ldg(&fscal[frame].eb1);
+        eb8 = __ldg(&fscal[frame].eb8);
+    }
+    if (TAPS && warp == 0) {
         // exp(-j b k1), k1 = 0..15
         const double fb = __hiloint2double((int)__shfl_sync(0xffffffffu, fsw.y, 4), (int)__shfl_sync(0xffffffffu, fsw.x, 4));
         const float bt = (float)fb * 0.15915494309189533577f;           // channel-line slope in turns per data index
@@ -298,8 +308,13 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         for (int c = 0; c < 4; c++) d[lane + 32 * c] = nmul(nmulc(cp[c], rp[4 - c]), pl);
     }
     float2 mn[8], ot[8];
-    warp_fft512(v, pl, reinterpret_cast<float2 *>(region), P.tw_fft, lane, mn, ot);
-    // now mn[i] = X[k1 + 16 i + (g ? 384 : 0)], ot[i] = X[k1 + 16 i + (g ? 128 : 256)], lane = 2 k1 + g; the region is free again
+    {
+        float2 V = __ldg(P.tw_fft + lane), V8 = __ldg(P.tw_fft + 8 * lane);
+        if (!TAPS) { V = nmul(V, eb1); V8 = nmul(V8, eb8); }
+        warp_fft512(v, pl, reinterpret_cast<float2 *>(region), V, V8, lane, mn, ot);
+    }
+    // now mn[i] = X[k1 + 16 i + (g ? 384 : 0)], ot[i] = X[k1 + 16 i + (g ? 128 : 256)], lane = 2 k1 + g (production instances:
+    // times exp(-j b k1)); the region is free again
 
     // ---- pilots and sum |pilot| (Frame.cpp:76-80) to the CTA's shared memory; the straggler data bins to the warp's region ----
     float2 *scratch = reinterpret_cast<float2 *>(region);
@@ -331,7 +346,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         for (int o = kRxMaxSym / 2; o > 0; o >>= 1) pv += __shfl_xor_sync(0xffffffffu, pv, o);
         g = pv * P.inv_pilot_norm;
     }
-    const float2 lc = M->lcl[lane >> 1];
+    const float2 lc = TAPS ? M->lcl[lane >> 1] : make_float2(1.f, 0.f);
 
     // ---- the segment coefficients of this symbol (Frame.cpp:89-92 + rx.cpp:214-216), one per combination:
     //      W[q] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) * ftab[q],  e = segment of combination q ----
@@ -378,7 +393,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
     unsigned ds = 256u << 7;                       // dummy slot
     if (lane < kF512Strag) {
         ds = aux.y & 0xffffu;                      // descriptor | (k1 of the lane that held the bin) << 16
-        xs = nmul(scratch[lane], M->lcl[aux.y >> 16]);
+        xs = TAPS ? nmul(scratch[lane], M->lcl[aux.y >> 16]) : scratch[lane];
     }
 #define COFDM_EQ(X, D16)                                                                         \
     do {                                                                                         \
@@ -389,11 +404,12 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         sb[i_] = (uint8_t)demap_n<MOD>(z_, dk);                                                  \
     } while (0)
 #define COFDM_EQ_ALL(F)                                                                          \
-    F(nmul(mn[0], lc), desc.x & 0xffffu); F(nmul(mn[1], lc), desc.x >> 16);                      \
-    F(nmul(mn[2], lc), desc.y & 0xffffu); F(nmul(mn[3], lc), desc.y >> 16);                      \
-    F(nmul(mn[4], lc), desc.z & 0xffffu); F(nmul(mn[5], lc), desc.z >> 16);                      \
-    F(nmul(mn[6], lc), desc.w & 0xffffu); F(nmul(mn[7], lc), desc.w >> 16);                      \
+    F(COFDM_LC(mn[0]), desc.x & 0xffffu); F(COFDM_LC(mn[1]), desc.x >> 16);                      \
+    F(COFDM_LC(mn[2]), desc.y & 0xffffu); F(COFDM_LC(mn[3]), desc.y >> 16);                      \
+    F(COFDM_LC(mn[4]), desc.z & 0xffffu); F(COFDM_LC(mn[5]), desc.z >> 16);                      \
+    F(COFDM_LC(mn[6]), desc.w & 0xffffu); F(COFDM_LC(mn[7]), desc.w >> 16);                      \
     F(xs, ds)
+#define COFDM_LC(X) (TAPS ? nmul((X), lc) : (X))
     COFDM_EQ_ALL(COFDM_EQ);
 #undef COFDM_EQ
     if (ambiguous != nullptr) {
@@ -411,6 +427,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         if (lane == 0 && n_amb) atomicAdd(ambiguous, (unsigned long long)n_amb);
     }
 #undef COFDM_EQ_ALL
+#undef COFDM_LC
     __syncwarp();
     // ---- pack: 8 consecutive symbols of `mod` bits = `mod` whole bytes, MSB first (modulation.cpp:90-125) ----
     {
@@ -732,14 +749,18 @@ rx_acquire512w_kernel(const Params P, const void *__restrict__ samples, long lon
     const double lb = ((double)tsxy - sx1 * (double)tsy) / (sx2 - sx1 * sx1);   // Frame.hpp:422 (sums, not means)
     const double la = (double)tsy - lb * sx1;                                    // Frame.hpp:423
     {
-        // FrameScal as five 8-byte words: {kc, m0} {th0, theta} {rot_theta} {a} {b}
+        // FrameScal as seven 8-byte words: {kc, m0} {th0, theta} {rot_theta} {a} {b} {exp(-j b)} {exp(-j 8 b)}
         uint2 wv;
         if (lane == 0) wv = make_uint2((unsigned)kc, (unsigned)m0);
         else if (lane == 1) wv = make_uint2(__float_as_uint(theta0), __float_as_uint(theta));
         else if (lane == 2) wv = make_uint2(__float_as_uint(rot.x), __float_as_uint(rot.y));
         else if (lane == 3) wv = make_uint2((unsigned)__double2loint(la), (unsigned)__double2hiint(la));
-        else wv = make_uint2((unsigned)__double2loint(lb), (unsigned)__double2hiint(lb));
-        if (lane < 5) reinterpret_cast<uint2 *>(fscal + frame)[lane] = wv;
+        else if (lane == 4) wv = make_uint2((unsigned)__double2loint(lb), (unsigned)__double2hiint(lb));
+        else {
+            const float2 e = cis_neg_turns(lb * (lane == 5 ? 1.0 : 8.0) * 0.15915494309189533577);
+            wv = make_uint2(__float_as_uint(e.x), __float_as_uint(e.y));
+        }
+        if (lane < 7) reinterpret_cast<uint2 *>(fscal + frame)[lane] = wv;
     }
     if (TAPS) {
         if (taps.scal != nullptr && lane == 0) {
