@@ -174,13 +174,13 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
     rs.frame_pos = frame_pos;
     rs.lo = (const char *)samples;
     rs.hi = (const char *)samples + (frame_pos != nullptr ? buf_samples : (n_frames - 1) * stride + (size_t)P.rx_len) * sb;
-    // the acquire kernel's hand-over (40 bytes per frame), in the buffer of this pipeline slot
+    // the acquire kernel's hand-over (56 bytes per frame), in the buffer of this pipeline slot
     FrameScal *fsc = nullptr;
     if (!sync_less) {
         CU_TRY(h->fscal[slot].reserve(n_frames * sizeof(FrameScal)));
         fsc = (FrameScal *)h->fscal[slot].p;
     }
-    // ---- acquire: the preamble -> 40 bytes of scalars per frame, one warp per frame.  The sync-less form (FRAME_FORM::read)
+    // ---- acquire: the preamble -> 56 bytes of scalars per frame, one warp per frame.  The sync-less form (FRAME_FORM::read)
     //      has no synchronisation stage at all; its preamble is only looked at for the chan_char tap ----
     if (h->timing) { collect_rx_stage(h); cudaEventRecord(h->sev[0], st); }
     if (!sync_less || taps.chan != nullptr) {

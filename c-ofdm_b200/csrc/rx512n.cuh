@@ -5,7 +5,7 @@
 // the equaliser loop (rx.cpp:214-216) and Modulation::demod (modulation.cpp:53-87).
 //
 // Two kernels that together read every sample exactly once:
-//   rx_acquire512w_kernel  the preamble of one frame per WARP -> 40 bytes of scalars (FrameScal)
+//   rx_acquire512w_kernel  the preamble of one frame per WARP -> 56 bytes of scalars (FrameScal)
 //   rx_demod512_kernel     the message symbols of one frame per CTA, one WARP per symbol -> payload bytes
 // Both use warp_fft512 (fft512w.cuh): radix 16 x 16 x 2 on natural-layout packed f32x2 complex numbers, one shared-memory
 // exchange private to the warp.  After the transform every sub-carrier sits in a FIXED lane and register (the acquire
@@ -230,7 +230,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
         warp_stage_symbol<FMT>(region, src, lane);
     }
     // ---- while the copy is in flight: the acquire kernel's scalars and the frame-wide tables ----
-    // (FrameScal is 40 bytes: lanes 0..4 fetch 8 bytes each -- {kc, m0} {th0, theta} {rot_theta} {a} {b} -- and the fields
+    // (lanes 0..4 fetch the first five 8-byte words of FrameScal -- {kc, m0} {th0, theta} {rot_theta} {a} {b} -- and the fields
     //  travel by shuffle to the few lanes that need them; every lane needs kc only)
     uint2 fsw = make_uint2(0u, 0u);
     if (!sync_less && lane < 5) fsw = __ldg(reinterpret_cast<const uint2 *>(fscal + frame) + lane);
@@ -444,7 +444,7 @@ rx_demod512_kernel(const Params P, const void *__restrict__ samples, long long f
 //   fine CFO     cp_freq_sinh (:238-263) on the preamble: CP correlation -> theta_0, m_0; rotation, warp FFT-512
 //   phase lock   pr_phase_sinh (:265-274): theta = arg sum conj(ref) y, body part by Parseval on the used bins
 //   channel fit  chan_char_lq (:389-434): 128 phases, the reference's one-step unwrap, the (bug-compatible) line
-// and hands 40 bytes of scalars (FrameScal) to the demod kernel.  The lane's 20 raw samples x[lane + 32 u] are the inputs of
+// and hands 56 bytes of scalars (FrameScal) to the demod kernel.  The lane's 20 raw samples x[lane + 32 u] are the inputs of
 // BOTH transforms (radix-10 first pass of the 640-point one: butterflies lane and lane + 32; CP + radix-16 first pass of the
 // 512-point one): they are read from the staged copy once and stay in registers.
 // Shared memory per warp: S (5120 B: staged samples -> second coarse plane -> phasor table, phases) and A (5632 B:
