@@ -39,7 +39,6 @@ struct alignas(16) BigShared {
     float2 pil[kMaxPilots];          // this symbol's pilot bins
     float2 wseg[kMaxPilots];         // segment coefficients
     float2 red[8];                   // per-warp partial sums (CP correlation)
-    float psum[8];                   // per-warp partial sums (pilot amplitudes)
     float pabs;                      // sum |pilot| of this symbol (read by the other CTAs of the cluster)
     float pad_[3];
     uint64_t mbar;
@@ -72,12 +71,13 @@ template <class T> COFDM_DEV const T *big_remote(const BigCtx &c, const T *p, in
 }
 #else
 COFDM_DEV BigCtx big_ctx() {
-    namespace cg = cooperative_groups;
-    cg::cluster_group cl = cg::this_cluster();
     extern __shared__ __align__(128) unsigned char big_smem_raw[];
     BigCtx c;
-    c.tid = (int)threadIdx.x; c.rank = (int)cl.block_rank(); c.nrank = (int)cl.num_blocks();
-    c.frame = (int)(blockIdx.x / cl.num_blocks());
+    unsigned rank, nrank, cid;                                  // 1-D clusters: rank in the cluster, its size, its index = the frame
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(nrank));
+    asm("mov.u32 %0, %%clusterid.x;" : "=r"(cid));
+    c.tid = (int)threadIdx.x; c.rank = (int)rank; c.nrank = (int)nrank; c.frame = (int)cid;
     c.smem = big_smem_raw;
     return c;
 }
@@ -106,6 +106,18 @@ COFDM_DEV void npowers15(float2 w1, float2 (&w)[16]) {
 // exp(-j 2 pi (theta + m) J / 4096) for an integer sample index J: the whole-bin part is reduced exactly in integers
 COFDM_DEV float2 big_phasor(float theta, int m, int J) {
     return fast_cis_turns(-(theta * ((float)J * (1.0f / 4096.0f)) + (float)((m * J) & 4095) * (1.0f / 4096.0f)));
+}
+
+// The two per-frame phasors of the demod kernel, computed once by whoever writes the FrameScal (its eb1 / eb8 fields, which only
+// the fft-512 kernels use otherwise):
+//   eb1 = c_1 = exp(-j 2 pi Psi_1) exp(-j theta_pr), Psi_1 = 1.25 (theta_0 + m_0) mod 1: the constant phase of message symbol 1
+//   eb8 = exp(-j b big_dstep): the equaliser's step from one row of a thread's bins to the next
+COFDM_DEV void big_frame_phasors(FrameScal &f, const Params &P) {
+    float acc = f.th0 * 1.25f;
+    acc -= rintf(acc);
+    const float psi1 = acc + (float)((5 * f.m0) & 3) * 0.25f;
+    f.eb1 = nmul(cis_neg_turns_f(psi1), f.rot_theta);
+    f.eb8 = cis_neg_turns_f((float)(f.b * 0.15915494309189533577) * (float)P.big_dstep);
 }
 
 // Forward FFT-4096 over the 256 threads of a CTA.  In: v[u] = x[j + 256 u] (thread j).  Out: v[t] = X[j + 256 t], unnormalised.
@@ -163,11 +175,15 @@ COFDM_DEV void cta_fft4096(float2 (&v)[16], float2 *E, const float2 *__restrict_
 // P.bin_role[k]: >= 0 data index, -1 null, -2 - p pilot number p.
 // ================================================================================================================
 // MOD: modulation order the instance is specialised for (6), or 0 = any (read from the configuration)
-template <int FMT, bool USE_TMA, bool TAPS, int MOD>
+// LAY: the instance is compiled for the row layout kBigLayData / kBigLayUsed (P.big_lay; the production geometry's 1920 + 128
+//      sub-carriers): unused rows of the last FFT pass are never computed, the equaliser runs branch-free from P.big_eq
+constexpr unsigned kBigLayData = 0xF00Fu, kBigLayUsed = 0xF01Fu;
+template <int FMT, bool USE_TMA, bool TAPS, int MOD, bool LAY = false>
 __global__ void __launch_bounds__(kBigThreads, 4)
 big_demod_kernel(const Params P, const void *__restrict__ samples, long long frame_stride /*samples*/, int n_frames,
                  uint8_t *__restrict__ out_bytes, unsigned long long *__restrict__ ambiguous, const RxTaps taps,
                  const FrameScal *__restrict__ fscal) {
+    static_assert(!(LAY && TAPS), "the layout-specialised instance has no taps");
     const BigCtx cx = big_ctx();
     const int tid = cx.tid, lane = tid & 31, warp = tid >> 5;
     const int frame = cx.frame;                                   // whole clusters only: every CTA of a cluster sees the same frame
@@ -230,53 +246,61 @@ big_demod_kernel(const Params P, const void *__restrict__ samples, long long fra
     const uint4 ra = __ldg(&P.big_roles[2 * tid]), rb = __ldg(&P.big_roles[2 * tid + 1]);
     const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
 #define COFDM_ROLE(t) ((int)(short)((rw[(t) >> 1] >> (16 * ((t) & 1))) & 0xffffu))
-    const unsigned tmask = (unsigned)P.big_tmask;                 // rows t in which ANY thread holds a used bin (uniform)
-    // ---- pilots and sum |pilot| (Frame.cpp:76-80): only the few threads whose bins are pilots enter ----
-    float pm = 0.f;
+    const unsigned tmask = LAY ? kBigLayUsed : (unsigned)P.big_tmask;   // rows t in which ANY thread holds a used bin (uniform)
+    // ---- pilots (Frame.cpp:76-80): the few threads whose bins are pilots put them side by side; warp 0 then sums |pilot| ----
     if (((ra.x | ra.y | ra.z | ra.w | rb.x | rb.y | rb.z | rb.w) & 0x80008000u) != 0u) {
 #pragma unroll
         for (int t = 0; t < 16; t++) {
             if (!((tmask >> t) & 1u)) continue;
             const int role = COFDM_ROLE(t);
-            if (role <= -2) {
-                M->pil[-2 - role] = v[t];
-                const float n2 = cnorm2(v[t]);
-                pm = fmaf(n2, rsqrtf(fmaxf(n2, 1e-30f)), pm);      // |pilot| (2 ulp: it enters g, a sum of 1024 terms)
-            }
+            if (role <= -2) M->pil[-2 - role] = v[t];
         }
     }
-    pm = warp_sum(pm);
-    if (lane == 0) M->psum[warp] = pm;
-    sync();                                                       // pil[] and psum[] complete
-    if (tid == 0) {
-        float tot = 0.f;
-        for (int w = 0; w < 8; w++) tot += M->psum[w];
-        M->pabs = tot;                                            // (published by this thread's own arrive.release)
+    sync();                                                       // pil[] complete
+    if (warp == 0) {
+        float pm = 0.f;
+        for (int q = lane; q < P.num_pilot_subc; q += 32) {
+            const float n2 = cnorm2(M->pil[q]);
+            pm = fmaf(n2, rsqrtf(fmaxf(n2, 1e-30f)), pm);          // |pilot| (2 ulp: it enters g, a sum of 1024 terms)
+        }
+        pm = warp_sum(pm);
+        if (lane == 0) M->pabs = pm;                              // (published by this warp's own arrive.release)
     }
-    big_cluster_arrive(cx);                                       // this symbol's pilots and pabs are published
+    // this symbol's pilots and pabs are published: warp 0 arrives with release semantics -- it wrote pabs, and the other warps'
+    // pilots reached it through the CTA barrier above (release is cumulative) -- so the other warps need no fence of their own
+    if (warp == 0) big_cluster_arrive(cx); else big_cluster_arrive_relaxed(cx);
     const int ND = P.num_data_subc, nw = cx.nrank;
     const float bt = (float)(fs.b * 0.15915494309189533577), at0 = (float)(fs.a * 0.15915494309189533577 - rint(fs.a * 0.15915494309189533577));
     const int dstep = P.big_dstep;
-    const float2 hstep = cis_neg_turns_f(bt * (float)dstep);
-    float c1x, c1y;
-    {
-        // c_1 = exp(-j 2 pi Psi_1) exp(-j theta_pr), Psi_1 = 1.25 (theta_0 + m_0) mod 1
-        float acc = fs.th0 * 1.25f;
-        acc -= rintf(acc);
-        const float psi1 = acc + (float)((5 * fs.m0) & 3) * 0.25f;
-        const float2 c1 = nmul(cis_neg_turns_f(psi1), fs.rot_theta);
-        c1x = c1.x; c1y = c1.y;
+    const float2 hstep = fs.eb8, c1 = fs.eb1;                     // exp(-j b dstep), c_1 (big_frame_phasors)
+    uint4 qa = make_uint4(0, 0, 0, 0), qb = qa;
+    if (LAY) {
+        // The row layout is known: the thread's data sit in rows 0..3 and 12..15 and its abscissa advances by big_dstep inside each
+        // group; one table word per row says where the symbol goes (a dump slot when the bin holds no data) and which segment
+        // coefficient it takes.  The equaliser's own factor exp(-j (b i' + a)) needs nothing from the other symbols: it is applied
+        // here, while the cluster barrier completes -- two phasors evaluated, six by recurrence, no branches.
+        qa = __ldg(&P.big_eq[3 * tid]); qb = __ldg(&P.big_eq[3 * tid + 1]);
+        const unsigned hw = __ldg(&P.big_eq[3 * tid + 2].x);
+        float2 hc = cis_neg_turns_f(fmaf(bt, (float)(short)(hw & 0xffffu), at0));
+        v[0] = nmul(v[0], hc);  hc = nmul(hc, hstep); v[1] = nmul(v[1], hc);
+        hc = nmul(hc, hstep);   v[2] = nmul(v[2], hc);  hc = nmul(hc, hstep); v[3] = nmul(v[3], hc);
+        hc = cis_neg_turns_f(fmaf(bt, (float)((int)hw >> 16), at0));
+        v[12] = nmul(v[12], hc); hc = nmul(hc, hstep); v[13] = nmul(v[13], hc);
+        hc = nmul(hc, hstep);    v[14] = nmul(v[14], hc); hc = nmul(hc, hstep); v[15] = nmul(v[15], hc);
     }
     big_cluster_wait(cx);                                         // pilots and pabs of every symbol of the frame are visible
 
     // ---- frame-wide: g (Frame.cpp:76-80) and the segment coefficients W[e] = P_1[e] conj(P_s[e]) / (|P_s[e]|^2 g) c_1 (Frame.cpp:89-92) ----
-    float g = 0.f;
-    for (int r = 0; r < cx.nrank; r++) g += *big_remote(cx, &M->pabs, r);
-    g *= P.inv_pilot_norm;
+    //      (lane r fetches symbol r's sum; a fixed tree over the 8 lanes, the same in every CTA of the frame)
+    float g = lane < cx.nrank ? *big_remote(cx, &M->pabs, lane) : 0.f;
+    g += __shfl_xor_sync(0xffffffffu, g, 4);
+    g += __shfl_xor_sync(0xffffffffu, g, 2);
+    g += __shfl_xor_sync(0xffffffffu, g, 1);
+    g = __shfl_sync(0xffffffffu, g, 0) * P.inv_pilot_norm;
     if (tid < P.num_pilot_subc) {
         const float2 p1 = big_remote(cx, M->pil, 0)[tid], ps = M->pil[tid];
         const float2 w = nscale(nmulc(p1, ps), __fdividef(1.0f, cnorm2(ps) * g));
-        M->wseg[tid] = nmul(w, make_float2(c1x, c1y));
+        M->wseg[tid] = nmul(w, c1);
     }
     big_cluster_arrive_relaxed(cx);                               // this CTA reads no remote shared memory from here on (waited for at the end)
     sync();                                                       // wseg visible
@@ -289,7 +313,23 @@ big_demod_kernel(const Params P, const void *__restrict__ samples, long long fra
     const float inv_seg = 1.0f / (float)P.seg_size;
     float2 *ctap = (TAPS && taps.constell != nullptr) ? taps.constell + ((size_t)frame * nw + (s - 1)) * ND : nullptr;
     int n_amb = 0;
-    {
+    if (LAY) {
+        // segment correction and hard demap of the 8 rows (equalised above)
+        const unsigned char *wsb = reinterpret_cast<const unsigned char *>(M->wseg);
+#define COFDM_BIG_Z(T, W) nmul(v[T], *reinterpret_cast<const float2 *>(wsb + ((W) >> 16)))
+#define COFDM_BIG_ROWS(F) { F(0, qa.x); F(1, qa.y); F(2, qa.z); F(3, qa.w); F(12, qb.x); F(13, qb.y); F(14, qb.z); F(15, qb.w); }
+#define COFDM_BIG_EQ(T, W) M->sb[(W) & 0xffffu] = (uint8_t)demap_n<MOD>(COFDM_BIG_Z(T, W), dk)
+        COFDM_BIG_ROWS(COFDM_BIG_EQ)
+        if (ambiguous != nullptr) {
+            // optional count of boundary-ambiguous decisions: the points are recomputed, off the fast path
+#define COFDM_BIG_AMB(T, W) n_amb += (((W) & 0xffffu) < (unsigned)ND && demap_ambiguous(COFDM_BIG_Z(T, W), dk)) ? 1 : 0
+            COFDM_BIG_ROWS(COFDM_BIG_AMB)
+#undef COFDM_BIG_AMB
+        }
+#undef COFDM_BIG_EQ
+#undef COFDM_BIG_ROWS
+#undef COFDM_BIG_Z
+    } else {
         float2 hc = make_float2(1.f, 0.f);
         int prev_ip = -0x40000000;
 #pragma unroll
@@ -381,8 +421,10 @@ constexpr int kBigAcqY = (5120 + 256) * 8, kBigAcqZ = 5120 * 8;
 struct alignas(16) BigAcqShared {
     float2 red[8];
     int ksum;
-    int pad_[3];
+    int anyjump;                     // some neighbouring phases differ by more than pi: the unwrap's slow path
+    int pad_[2];
     uint64_t mbar[2];
+    double dsum[8][2];               // per-warp partial sums of the channel-line fit
 };
 COFDM_HD constexpr size_t big_acquire_smem_bytes() { return (size_t)kBigAcqY + kBigAcqZ + sizeof(BigAcqShared); }
 
@@ -442,7 +484,7 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
         }
     };
     stage_issue(0);
-    if (tid == 0) M->ksum = 0;
+    if (tid == 0) { M->ksum = 0; M->anyjump = 0; }
     __syncthreads();
     if (USE_TMA) mbar_wait(&M->mbar[0], 0);
 
@@ -471,23 +513,28 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
     __syncthreads();
     stage_issue(1);                                                           // the raw preamble again (Z is free; the copy hits L2)
     {
-        // arg-max of |spectrum| in the pilot windows, first maximum wins (Frame.hpp:311-331); window np/2 (DC) is skipped
+        // arg-max of |spectrum| in the pilot windows, first maximum wins (Frame.hpp:311-331); window np/2 (DC) is skipped.
+        // The windows are short (pf_pilot_w = 20 bins here): TWO THREADS per window scan one half each, the lower half wins ties.
         const int np = P.num_pilot_subc, half = P.pf_size / 2;
-        int acc = 0;
-        for (int wi = warp; wi < np; wi += kBigThreads / 32) {
+        const int wi = tid >> 1, part = tid & 1;
+        float best = -1.0f;
+        int besti = 0;
+        if (wi < np) {
             const int win = wi < np / 2 ? wi : wi + 1;
             int lo = P.pf_border0 + win * P.pf_pilot_w;
             const int hi = lo + P.pf_pilot_w;
             if (win == 0 && lo < 0) lo = 0;
-            float best = -1.0f;
-            int besti = 0x7fffffff;
-            for (int ks = lo + lane; ks < hi; ks += 32) {
+            const int mid = lo + ((hi - lo + 1) >> 1);
+            const int k0 = part ? mid : lo, k1 = part ? hi : mid;
+            for (int ks = k0; ks < k1; ks++) {
                 const float mv = mag[ks < half ? ks + half : ks - half];
                 if (mv > best) { best = mv; besti = ks; }
             }
-            const unsigned mx = __reduce_max_sync(0xffffffffu, __float_as_uint(fmaxf(best, 0.0f)));
-            acc += __reduce_min_sync(0xffffffffu, (best >= 0.0f && __float_as_uint(best) == mx) ? besti : 0x7fffffff);
         }
+        const float obest = __shfl_xor_sync(0xffffffffu, best, 1);
+        const int oi = __shfl_xor_sync(0xffffffffu, besti, 1);
+        if (obest > best) besti = oi;
+        const int acc = __reduce_add_sync(0xffffffffu, (part == 0 && wi < np) ? besti : 0);
         if (lane == 0) atomicAdd(&M->ksum, acc);
     }
     __syncthreads();
@@ -544,72 +591,93 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
         }
     }
     __syncthreads();
-    if (warp != 0) return;
-    // one-step unwrap (Frame.hpp:407-414) and the sums of Frame.hpp:416-421 by one warp: lane l owns elements [l E, (l + 1) E).
-    // The adjustment is a 3-state chain (state = multiple of 2 pi carried by the previous element).
-    const int E = (nph + 31) / 32, i0 = lane * E, i1 = min(nph, i0 + E);
-    const float prev_raw = i0 > 0 && i0 < nph ? phs[i0 - 1] : 0.f;
-    bool jump = false;
+    // The one-step unwrap (Frame.hpp:407-414) changes nothing unless two neighbouring phases differ by more than pi.  All 256
+    // threads look for such a pair in their own stretch and add up the sums of Frame.hpp:416-421 as if there were none -- the
+    // common case, finished here in parallel; otherwise warp 0 redoes the sums with the unwrap's 3-state chain below.
+    double tsy, tsxy;
     {
-        float pv = prev_raw;
-        for (int i = i0; i < i1; i++) { const float p = phs[i]; if (i > 0 && fabsf(p - pv) > PI_F) jump = true; pv = p; }
+        const int E8 = (nph + kBigThreads - 1) / kBigThreads, a0 = tid * E8, a1 = min(nph, a0 + E8);
+        float pv = a0 > 0 && a0 < nph ? phs[a0 - 1] : 0.f;
+        bool jump = false;
+        double ssy = 0.0, ssxy = 0.0;
+        for (int i = a0; i < a1; i++) {
+            const float p = phs[i];
+            if (i > 0 && fabsf(p - pv) > PI_F) jump = true;
+            pv = p;
+            ssy += (double)p;
+            ssxy += (double)p * (double)i;
+        }
+        if (jump) M->anyjump = 1;
+        ssy = warp_sum(ssy); ssxy = warp_sum(ssxy);
+        if (lane == 0) { M->dsum[warp][0] = ssy; M->dsum[warp][1] = ssxy; }
     }
-    const bool any = __ballot_sync(0xffffffffu, jump) != 0u;
-    int cstart = 0;                                                           // state entering this lane's range
-    if (any) {
-        unsigned map = 0;
-        for (int cin = 0; cin < 3; cin++) {
-            int cs = cin - 1;
+    __syncthreads();
+    if (warp != 0) return;
+    if (M->anyjump == 0) {
+        tsy = warp_sum(lane < kBigThreads / 32 ? M->dsum[lane][0] : 0.0);
+        tsxy = warp_sum(lane < kBigThreads / 32 ? M->dsum[lane][1] : 0.0);
+    } else {
+        // by one warp: lane l owns elements [l E, (l + 1) E).  The adjustment is a 3-state chain (state = multiple of 2 pi
+        // carried by the previous element): every lane maps the three possible entry states of its range to exit states,
+        // the maps are composed across the lanes, then each lane replays its range from its true entry state.
+        const int E = (nph + 31) / 32, i0 = lane * E, i1 = min(nph, i0 + E);
+        const float prev_raw = i0 > 0 && i0 < nph ? phs[i0 - 1] : 0.f;
+        int cstart = 0;                                                       // state entering this lane's range
+        {
+            unsigned map = 0;
+            for (int cin = 0; cin < 3; cin++) {
+                int cs = cin - 1;
+                float pv = prev_raw;
+                for (int i = i0; i < i1; i++) {
+                    const float p = phs[i];
+                    if (i == 0) { cs = 0; pv = p; continue; }
+                    const float dlt = p - (pv + (float)cs * TWO_PI_F);
+                    cs = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                    pv = p;
+                }
+                map |= (unsigned)(cs + 1) << (2 * cin);
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
+                if (lane >= o) {
+                    unsigned comp = 0;
+#pragma unroll
+                    for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
+                    map = comp;
+                }
+            }
+            const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
+            cstart = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;        // the chain starts in state 0 (entry [1] of the composed map)
+        }
+        double ssy = 0.0, ssxy = 0.0;
+        {
+            int cs = cstart;
             float pv = prev_raw;
             for (int i = i0; i < i1; i++) {
                 const float p = phs[i];
-                if (i == 0) { cs = 0; pv = p; continue; }
-                const float dlt = p - (pv + (float)cs * TWO_PI_F);
-                cs = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                float val = p;
+                if (i > 0) {
+                    const float dlt = p - (pv + (float)cs * TWO_PI_F);
+                    cs = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
+                    val = p + (float)cs * TWO_PI_F;
+                } else {
+                    cs = 0;
+                }
                 pv = p;
-            }
-            map |= (unsigned)(cs + 1) << (2 * cin);
-        }
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned up = __shfl_up_sync(0xffffffffu, map, o);
-            if (lane >= o) {
-                unsigned comp = 0;
-#pragma unroll
-                for (int cin = 0; cin < 3; cin++) comp |= ((map >> (2 * ((up >> (2 * cin)) & 3u))) & 3u) << (2 * cin);
-                map = comp;
+                ssy += (double)val;
+                ssxy += (double)val * (double)i;
             }
         }
-        const unsigned before = __shfl_up_sync(0xffffffffu, map, 1);
-        cstart = lane == 0 ? 0 : (int)((before >> 2) & 3u) - 1;            // the chain starts in state 0 (entry [1] of the composed map)
+        tsy = warp_sum(ssy); tsxy = warp_sum(ssxy);
     }
-    double ssy = 0.0, ssxy = 0.0;
-    {
-        int cs = cstart;
-        float pv = prev_raw;
-        for (int i = i0; i < i1; i++) {
-            const float p = phs[i];
-            float val = p;
-            if (i > 0) {
-                const float dlt = p - (pv + (float)cs * TWO_PI_F);
-                cs = dlt > PI_F ? -1 : (dlt < -PI_F ? 1 : 0);
-                val = p + (float)cs * TWO_PI_F;
-            } else {
-                cs = 0;
-            }
-            pv = p;
-            ssy += (double)val;
-            ssxy += (double)val * (double)i;
-        }
-    }
-    const double tsy = warp_sum(ssy), tsxy = warp_sum(ssxy);
     const double n = (double)nph, sx1 = n * (n - 1.0) / 2.0, sx2 = (n - 1.0) * n * (2.0 * n - 1.0) / 6.0;
     const double lb = (tsxy - sx1 * tsy) / (sx2 - sx1 * sx1);               // Frame.hpp:422 (sums, not means)
     const double la = tsy - lb * sx1;                                        // Frame.hpp:423
     if (lane == 0) {
         FrameScal f;
         f.kc = kc; f.m0 = m0; f.th0 = theta0; f.theta = theta; f.rot_theta = rot; f.a = la; f.b = lb;
-        f.eb1 = make_float2(1.f, 0.f); f.eb8 = f.eb1;             // (fft-512 demod kernel only)
+        big_frame_phasors(f, P);
         fscal[frame] = f;
     }
     if (TAPS) {
@@ -711,7 +779,7 @@ __global__ void big_bridge_kernel(const Params P, int n_frames, const GenFrame *
     f.kc = G.kc; f.m0 = 0;
     f.th0 = (float)((double)G.phit[0] + (double)P.fft_size * (double)G.kc / (double)P.pf_den);
     f.theta = G.theta; f.rot_theta = G.rot_theta; f.a = G.a; f.b = G.b;
-    f.eb1 = make_float2(1.f, 0.f); f.eb8 = f.eb1;
+    big_frame_phasors(f, P);
     fscal[frame] = f;
     if (taps.scal != nullptr) {
         float *sc = taps.scal + (size_t)frame * 48;

@@ -84,6 +84,7 @@ struct cofdm {
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
     DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
     int big_acquire = 1;                         // ... including their own acquisition kernel (env COFDM_BIG_ACQUIRE=0: the any-size kernels + bridge)
+    int big_lay_on = 1;                          // ... the layout-specialised demod instance where the map allows it (env COFDM_BIG_LAY=0: off)
     int big_on = 1;                              // fft-4096 configurations use the cluster kernels of big.cuh (env COFDM_BIG=0: the any-size path)
     int tx_ctas = 148 * 4;                       // CTAs of the persistent tx kernel (SMs x resident CTAs per SM, measured at create)
     int tx_bulk = 1;                             // tx: symbols leave the SM as TMA bulk stores (env COFDM_TX_BULK=0: register stores)
@@ -218,7 +219,7 @@ int launch_rx(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_t n_
 }
 
 // the fft-4096 path (big.cuh): acquisition -> FrameScal, then one cluster of num_symb CTAs per frame
-template <int FMT, bool TMA, bool TAPS, int MOD>
+template <int FMT, bool TMA, bool TAPS, int MOD, bool LAY = false>
 int launch_big_demod(cofdm *h, cudaStream_t st, const void *samples, size_t n_frames, size_t stride, uint8_t *bytes,
                      unsigned long long *amb, const RxTaps &taps, const FrameScal *fsc) {
     const Params &P = h->P;
@@ -231,7 +232,7 @@ int launch_big_demod(cofdm *h, cudaStream_t st, const void *samples, size_t n_fr
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)P.num_symb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, big_demod_kernel<FMT, TMA, TAPS, MOD>, P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, fsc);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, big_demod_kernel<FMT, TMA, TAPS, MOD, LAY>, P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, fsc);
     if (e != cudaSuccess) return fail(COFDM_ERR_CUDA, std::string("big_demod launch: ") + cudaGetErrorString(e));
     return check_launch(h, "big_demod");
 }
@@ -286,9 +287,12 @@ int launch_rx_big(cofdm *h, cudaStream_t st, const void *samples, int fmt, size_
     }
     if (h->timing) cudaEventRecord(h->sev[1], st);
     int rc;
-    // the production instance is specialised on 64-QAM; everything else reads the modulation order from the configuration
+    // the production instance is specialised on 64-QAM and, when the sub-carrier map has it (P.big_lay), on the row layout;
+    // everything else reads the modulation order and the roles from the configuration
+    const bool lay = P.big_lay && h->big_lay_on;
 #define COFDM_BIG(F, T) (want ? launch_big_demod<F, T, true, 0>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
-                              : (P.mod_type == 6 ? launch_big_demod<F, T, false, 6>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
+                              : (P.mod_type == 6 ? (lay ? launch_big_demod<F, T, false, 6, true>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc) \
+                                                        : launch_big_demod<F, T, false, 6>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc)) \
                                                  : launch_big_demod<F, T, false, 0>(h, st, samples, n_frames, stride, bytes, amb, taps, fsc)))
     if (fmt == COFDM_CI16) rc = al ? COFDM_BIG(kCI16, true) : COFDM_BIG(kCI16, false);
     else rc = al ? COFDM_BIG(kCF32, true) : COFDM_BIG(kCF32, false);
@@ -494,7 +498,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
-    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.big_roles, &P.big_roles); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
+    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.big_roles, &P.big_roles); rc |= upload(h, T.big_eq, &P.big_eq); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
     rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.lane_aux, &P.lane_aux); rc |= upload(h, T.acq_desc, &P.acq_desc);
     rc |= upload(h, T.grid_lane, &P.grid_lane); rc |= upload(h, T.tx_desc, &P.tx_desc);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
@@ -576,6 +580,8 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             if (bg) h->big_on = std::atoi(bg) != 0;
             cudaFuncSetAttribute(gen_symbol_kernel<kCF32, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
             cudaFuncSetAttribute(gen_symbol_kernel<kCI16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
+            const char *bl = std::getenv("COFDM_BIG_LAY");           // 0: the layout-specialised demod instance off (A/B runs)
+            if (bl) h->big_lay_on = std::atoi(bl) != 0;
             const char *ba = std::getenv("COFDM_BIG_ACQUIRE");
             if (ba) h->big_acquire = std::atoi(ba) != 0;
             const int sma = (int)big_acquire_smem_bytes();
@@ -593,7 +599,9 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
 #define COFDM_BIG_ATTR1(F, T, W, MD) \
             cudaFuncSetAttribute(big_demod_kernel<F, T, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \
             cudaFuncSetAttribute(big_demod_kernel<F, T, W, MD>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
-#define COFDM_BIG_ATTR(F, T) COFDM_BIG_ATTR1(F, T, true, 0); COFDM_BIG_ATTR1(F, T, false, 0); COFDM_BIG_ATTR1(F, T, false, 6)
+#define COFDM_BIG_ATTR(F, T) COFDM_BIG_ATTR1(F, T, true, 0); COFDM_BIG_ATTR1(F, T, false, 0); COFDM_BIG_ATTR1(F, T, false, 6); \
+            cudaFuncSetAttribute(big_demod_kernel<F, T, false, 6, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \
+            cudaFuncSetAttribute(big_demod_kernel<F, T, false, 6, true>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
             COFDM_BIG_ATTR(kCF32, true); COFDM_BIG_ATTR(kCF32, false); COFDM_BIG_ATTR(kCI16, true); COFDM_BIG_ATTR(kCI16, false);
 #undef COFDM_BIG_ATTR1
 #undef COFDM_BIG_ATTR

@@ -101,6 +101,7 @@ struct HostTables {
     std::vector<uint2> lane_aux;      //             combinations and straggler bins
     std::vector<uint2> acq_desc;      //             acquire kernel: which phase each slot produces
     std::vector<uint4> big_roles;     // big.cuh: per thread, the roles of its 16 bins
+    std::vector<uint4> big_eq;        //          per thread, the equaliser's table of the specialised row layout
     std::vector<uint4> tx_desc;       // tx512w.cuh: per lane, what sits at the bins lane + 32 n1
     std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N), by bin
     std::vector<float2> grid_lane;    //             the same in lane order
@@ -415,6 +416,37 @@ inline HostTables build_tables(const ConfigMap &cfg) {
                 unsigned *u = &T.big_roles[2 * (size_t)j].x;          // 8 consecutive words per thread
                 u[t >> 1] |= ((unsigned)(uint16_t)T.bin_role[(size_t)(j + 256 * t)]) << (16 * (t & 1));
             }
+    }
+    // The specialised demod instance (big_demod_kernel<.., LAY = true>): data sub-carriers only in rows 0..3 and 12..15 of the
+    // 256 x 16 bin matrix, pilots also in row 4 (1920 + 128 sub-carriers: bins 1..1024 and 3072..4095), and inside each of the
+    // two row groups every thread's channel-line abscissa i' advances by big_dstep per row.  The table carries, per thread, where
+    // each of its 8 data rows goes and the abscissa at the head of each group (extrapolated when the head itself holds no data).
+    p.big_lay = 0;
+    if (N == 4096 && p.big_dstep > 0 && ND <= 3840) {
+        unsigned dmask = 0;
+        for (int k = 0; k < N; k++) if (T.bin_role[(size_t)k] >= 0) dmask |= 1u << (k >> 8);
+        bool ok = dmask == 0xF00Fu && (unsigned)p.big_tmask == 0xF01Fu;
+        T.big_eq.assign(768, make_uint4(0, 0, 0, 0));
+        for (int j = 0; j < 256 && ok; j++) {
+            int head[2] = {0, 0};
+            for (int grp = 0; grp < 2; grp++) {
+                bool have = false;
+                for (int r = 0; r < 4; r++) {
+                    const int t = (grp ? 12 : 0) + r, role = T.bin_role[(size_t)(j + 256 * t)];
+                    unsigned word = (unsigned)(3840 + (j & 15));                          // dump slot, coefficient 0
+                    if (role >= 0) {
+                        const int ip = role < ND / 2 ? role : role - ND, h0 = ip - r * p.big_dstep;
+                        if (have && h0 != head[grp]) ok = false;
+                        head[grp] = h0; have = true;
+                        word = (unsigned)role | ((unsigned)(role / p.seg_size) * 8u) << 16;
+                    }
+                    (&T.big_eq[3 * (size_t)j + grp].x)[r] = word;
+                }
+                if (head[grp] < -32768 || head[grp] > 32767) ok = false;
+            }
+            T.big_eq[3 * (size_t)j + 2].x = ((unsigned)head[0] & 0xffffu) | ((unsigned)head[1] << 16);
+        }
+        p.big_lay = ok ? 1 : 0;
     }
     T.big_ok = T.generic_ok && N == 4096 && p.cp_size == 1024 && p.num_pr_symb == 1 && p.num_symb >= 1 && p.num_symb <= 8 &&
                NP <= kMaxPilots && ND <= 3840 && ND % 8 == 0 && ND % NP == 0;

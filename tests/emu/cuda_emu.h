@@ -124,6 +124,10 @@ static inline unsigned __reduce_max_sync(unsigned, unsigned v) {
     for (int o = 16; o > 0; o >>= 1) v = std::max(v, emu::shfl_idx(v, (int)(emu::t_tid & 31) ^ o));
     return v;
 }
+static inline int __reduce_add_sync(unsigned, int v) {
+    for (int o = 16; o > 0; o >>= 1) v += emu::shfl_idx(v, (int)(emu::t_tid & 31) ^ o);
+    return v;
+}
 static inline int __reduce_min_sync(unsigned, int v) {
     for (int o = 16; o > 0; o >>= 1) v = std::min(v, emu::shfl_idx(v, (int)(emu::t_tid & 31) ^ o));
     return v;

@@ -23,7 +23,7 @@ static void wire(EmuHandle *h) {
     P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
-    P.bin_role = T.bin_role.data(); P.big_roles = T.big_roles.data(); P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
+    P.bin_role = T.bin_role.data(); P.big_roles = T.big_roles.data(); P.big_eq = T.big_eq.data(); P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
     P.lane_desc = T.lane_desc.data(); P.lane_aux = T.lane_aux.data(); P.acq_desc = T.acq_desc.data(); P.grid_lane = T.grid_lane.data(); P.tx_desc = T.tx_desc.data();
 }
 
@@ -222,7 +222,9 @@ int emu_rx_generic_mode(void *hv, const void *samples, int fmt, int n_frames, lo
     return 0;
 }
 
-static int g_emu_big_tx = 1;
+static int g_emu_big_tx = 1, g_emu_big_lay = 1;
+void emu_set_big_lay(int on) { g_emu_big_lay = on; }
+int emu_big_lay(void *h) { return ((EmuHandle *)h)->T.p.big_lay; }
 void emu_set_big_tx(int on) { g_emu_big_tx = on; }
 int emu_big_ok(void *h) { return ((EmuHandle *)h)->T.big_ok ? 1 : 0; }
 
@@ -262,6 +264,7 @@ int emu_rx_big(void *hv, const void *samples, int fmt, int use_tma, int n_frames
     const dim3 grid(n_frames), blk((unsigned)P.num_symb * kBigThreads);
     const size_t sm = (size_t)P.num_symb * big_smem_bytes();
 #define EMU_BIG(F, T) do { if (want) emu::launch(grid, blk, sm, [&] { big_demod_kernel<F, T, true, 0>(P, samples, stride, n_frames, out, amb, taps, fs.data()); }); \
+                           else if (P.mod_type == 6 && P.big_lay && g_emu_big_lay) emu::launch(grid, blk, sm, [&] { big_demod_kernel<F, T, false, 6, true>(P, samples, stride, n_frames, out, amb, taps, fs.data()); }); \
                            else if (P.mod_type == 6) emu::launch(grid, blk, sm, [&] { big_demod_kernel<F, T, false, 6>(P, samples, stride, n_frames, out, amb, taps, fs.data()); }); \
                            else emu::launch(grid, blk, sm, [&] { big_demod_kernel<F, T, false, 0>(P, samples, stride, n_frames, out, amb, taps, fs.data()); }); } while (0)
     if (fmt == kCI16) { if (use_tma) EMU_BIG(kCI16, true); else EMU_BIG(kCI16, false); }

@@ -63,6 +63,15 @@ class EmuModem:
         self.lib.emu_set_pc_plain.argtypes = [C.c_int]
         self.lib.emu_set_pc_plain(int(on))
 
+    def set_big_lay(self, on):
+        """1: fft-4096 configurations whose map allows it run the layout-specialised demod instance (the product default)"""
+        self.lib.emu_set_big_lay.argtypes = [C.c_int]
+        self.lib.emu_set_big_lay(int(on))
+
+    def big_lay(self):
+        self.lib.emu_big_lay.argtypes = [C.c_void_p]
+        return int(self.lib.emu_big_lay(self.h))
+
     def set_tx_bulk(self, on):
         """1: tx symbols leave as TMA bulk stores of linear images (the product default), 0: register stores"""
         self.lib.emu_set_tx_bulk.argtypes = [C.c_int]

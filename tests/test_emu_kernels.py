@@ -209,10 +209,19 @@ def test_big_path_cluster_kernels(cfg_dir, oracle_lib):
         m.big_mode = mode
         st = pc.check_rx_against_oracle(m, o, rec, "i16")
         assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6, (mode, st)
-        out, _ = m.rx_aligned_batch(pc.cplx(rec).astype(np.complex64), count_ambiguous=False)
-        for i in range(len(rec)):
-            r = o.rx_aligned(pc.cplx(rec[i]))
-            pc.assert_bytes_match(out[i], r["bytes"], r["constell"], o.sizes.mod_type, f"big mode {mode} frame {i}")
+        # the production instances (no taps): compiled for this map's row layout (P.big_lay), and the any-layout one
+        assert m.big_lay() == 1
+        for lay in (1, 0):
+            m.set_big_lay(lay)
+            out, _ = m.rx_aligned_batch(pc.cplx(rec).astype(np.complex64), count_ambiguous=False)
+            out2, amb = m.rx_aligned_batch(rec, count_ambiguous=True)
+            for i in range(len(rec)):
+                r = o.rx_aligned(pc.cplx(rec[i]))
+                pc.assert_bytes_match(out[i], r["bytes"], r["constell"], o.sizes.mod_type, f"big mode {mode} lay {lay} frame {i}")
+                pc.assert_bytes_match(out2[i], r["bytes"], r["constell"], o.sizes.mod_type, f"big mode {mode} lay {lay} i16 frame {i}")
+            namb = sum(int(pc.ambiguous_symbols(o.rx_aligned(pc.cplx(x))["constell"], o.sizes.mod_type).sum()) for x in rec)
+            assert abs(amb - namb) <= 2, (amb, namb)      # the optional count of decisions near a boundary (margin-level agreement)
+        m.set_big_lay(1)
 
 
 def test_big_path_phase_unwrap_slow_path(cfg_dir, oracle_lib):
