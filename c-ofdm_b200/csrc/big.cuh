@@ -567,6 +567,8 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
         }
     }
     z = warp_sum(z);
+    // the roles of the thread's 16 bins (needed after the transform; fetched here so that nothing waits for them there)
+    const uint4 ra = __ldg(&P.big_roles[2 * tid]), rb = __ldg(&P.big_roles[2 * tid + 1]);
     __syncthreads();                                                          // red[] and mag have been read by everybody
     if (lane == 0) M->red[warp] = z;
     auto sync = [&]() { __syncthreads(); };
@@ -582,9 +584,12 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
     const float TWO_PI_F = 6.28318530717958647692f, PI_F = 3.14159265358979323846f;
     const int nph = P.num_data_subc / 2;
     float *phs = reinterpret_cast<float *>(Zb);                              // the staged preamble has been consumed (barriers of the FFT)
+    const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
+    const unsigned phmask = (unsigned)P.big_phmask;                          // rows in which ANY thread holds one of these bins (uniform)
 #pragma unroll
     for (int t = 0; t < 16; t++) {
-        const int role = (int)__ldg(&P.bin_role[tid + 256 * t]);
+        if (!((phmask >> t) & 1u)) continue;
+        const int role = (int)(short)((rw[t >> 1] >> (16 * (t & 1))) & 0xffffu);
         if (role >= 0 && role < nph) {
             const float2 d = nmulc(nmul(v[t], rot), __ldg(&P.mod_preamble[role]));
             phs[role] = fast_atan2_turns(d.y, d.x) * TWO_PI_F;
@@ -696,14 +701,13 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
 
 // ================================================================================================================
 // big_tx_kernel: FRAME_FORM::write + get / get_int16 (Frame.cpp:185-198, 54-70, 244-256) for the fft-4096 geometry.
-// grid (num_symb + 1, n_frames): CTA (s, f) builds message symbol s of frame f -- the symbol's payload bytes staged in shared
-// memory, the thread's 16 grid points (bins j + 256 u: data point, pilot or null, from the packed role table) conjugated,
-// conj(FFT(conj G)) = the backward transform, / sqrt(4096), coalesced stores of body and cyclic prefix straight from the
+// grid (num_symb + 1, n_frames): CTA (s, f) builds message symbol s of frame f -- the thread's 16 grid points (bins j + 256 u:
+// data point, pilot or null, from the descriptor table P.big_txd) conjugated, conj(FFT(conj G)) = the backward transform, / sqrt(4096), coalesced stores of body and cyclic prefix straight from the
 // registers (thread j holds samples j + 256 t: a warp stores 32 consecutive samples); CTA (num_symb, f) copies the constant
 // sync tone + preamble.
 // ================================================================================================================
-constexpr int kBigTxPayMax = kBigMaxData + 16;
-COFDM_HD constexpr size_t big_tx_smem_bytes() { return (size_t)kBigExchSlots * 8 + kBigTxPayMax; }
+constexpr int kBigTxPoints = 256 + 2;                        // the point table: up to 256-QAM, the pilot, zero
+COFDM_HD constexpr size_t big_tx_smem_bytes() { return (size_t)kBigExchSlots * 8 + (size_t)kBigTxPoints * 8; }
 
 template <int FMT>
 COFDM_DEV void big_store(void *frame_out, long long idx, float2 v, float mult) {
@@ -716,7 +720,13 @@ COFDM_DEV void big_store(void *frame_out, long long idx, float2 v, float mult) {
     }
 }
 
-template <int FMT>
+// MOD: modulation order the instance is specialised for (6), or 0 = any; LAY: compiled for the row layout kBigLayUsed (rows
+// 5..11 of the grid are empty: the first FFT pass never touches them).
+// P.big_txd: per thread 16 words, one per row: [15:0] byte of the symbol's payload where the sub-carrier's bits start,
+// [18:16] bit offset in that byte, [25:24] 1 = pilot, 2 = null.  The bytes come straight from global memory (two byte loads per
+// row, neighbouring threads read neighbouring bytes; all of a thread's loads are in flight together), the points from a small
+// table in shared memory: conj(constellation), then the pilot and zero.
+template <int FMT, int MOD = 0, bool LAY = false>
 __global__ void __launch_bounds__(kBigThreads, 4)
 big_tx_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, void *__restrict__ frames) {
     COFDM_DYN_SMEM(smem_raw);
@@ -730,31 +740,36 @@ big_tx_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames,
         return;
     }
     float2 *E = reinterpret_cast<float2 *>(smem_raw);
-    uint8_t *pl = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)kBigExchSlots * 8;
-    const int mod = P.mod_type, ND = P.num_data_subc, sym_bytes = ND * mod / 8;
-    {
-        const uint8_t *src = payload + (size_t)frame * P.bytes_per_frame + (size_t)s * sym_bytes;
-        if (((reinterpret_cast<uintptr_t>(src) | (unsigned)sym_bytes) & 3) == 0) {
-            for (int i = tid; i < sym_bytes / 4; i += kBigThreads) reinterpret_cast<unsigned *>(pl)[i] = __ldg(reinterpret_cast<const unsigned *>(src) + i);
-        } else {
-            for (int i = tid; i < sym_bytes; i += kBigThreads) pl[i] = __ldg(src + i);
-        }
-        if (tid < 4) reinterpret_cast<unsigned *>(pl + ((sym_bytes + 3) & ~3))[tid] = 0u;   // the byte a straddling 6-bit symbol reads past the end
+    float2 *ct = reinterpret_cast<float2 *>(smem_raw + (size_t)kBigExchSlots * 8);
+    const int mod = MOD ? MOD : P.mod_type, npts = 1 << mod, ND = P.num_data_subc, sym_bytes = ND * mod / 8;
+    for (int i = tid; i < npts + 2; i += kBigThreads) {
+        float2 c = make_float2(0.f, 0.f);                                          // Frame.cpp:55
+        if (i < npts) { c = __ldg(&P.constell[i]); c.y = -c.y; }                   // conjugated: the backward transform is conj(FFT(conj G))
+        else if (i == npts) c = make_float2(P.pilot_ampl, 0.f);                    // Frame.cpp:56-57
+        ct[i] = c;
     }
-    const uint4 ra = __ldg(&P.big_roles[2 * tid]), rb = __ldg(&P.big_roles[2 * tid + 1]);
-    const unsigned rw[8] = {ra.x, ra.y, ra.z, ra.w, rb.x, rb.y, rb.z, rb.w};
-    __syncthreads();
+    const unsigned tmask = LAY ? kBigLayUsed : (unsigned)P.big_tmask;
+    const uint8_t *src = payload + (size_t)frame * P.bytes_per_frame + (size_t)s * sym_bytes;
+    const uint4 da = __ldg(&P.big_txd[4 * tid]), db = __ldg(&P.big_txd[4 * tid + 1]), dc = __ldg(&P.big_txd[4 * tid + 2]), dd = __ldg(&P.big_txd[4 * tid + 3]);
+    const unsigned dw[16] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w, dc.x, dc.y, dc.z, dc.w, dd.x, dd.y, dd.z, dd.w};
+    unsigned wb[16];
+#pragma unroll
+    for (int u = 0; u < 16; u++) {
+        wb[u] = 0u;
+        if (!((tmask >> u) & 1u)) continue;
+        const int b0 = (int)(dw[u] & 0xffffu);
+        // (the second byte is read at a clamped position: when the bits end inside the first byte it is shifted out anyway)
+        wb[u] = ((unsigned)__ldg(src + b0) << 8) | (unsigned)__ldg(src + min(b0 + 1, sym_bytes - 1));
+    }
+    __syncthreads();                                                              // ct[] complete
     float2 v[16];
 #pragma unroll
     for (int u = 0; u < 16; u++) {
-        const int role = (int)(short)((rw[u >> 1] >> (16 * (u & 1))) & 0xffffu);
-        float2 g = make_float2(0.f, 0.f);                                          // Frame.cpp:55
-        if (role <= -2) g = make_float2(P.pilot_ampl, 0.f);                         // Frame.cpp:56-57
-        else if (role >= 0) {
-            const float2 c = __ldg(&P.constell[extract_bits_sw(pl, sym_bytes + 4, role * mod, mod)]);   // Frame.cpp:59-62 + modulation.cpp:39-50
-            g = make_float2(c.x, -c.y);                                            // conjugated: the backward transform is conj(FFT(conj G))
-        }
-        v[u] = g;
+        v[u] = make_float2(0.f, 0.f);
+        if (!((tmask >> u) & 1u)) continue;
+        const unsigned off = (dw[u] >> 16) & 7u, flag = dw[u] >> 24;
+        const unsigned sym = (wb[u] >> (16u - (unsigned)mod - off)) & (unsigned)(npts - 1);      // Frame.cpp:59-62 + modulation.cpp:39-50
+        v[u] = ct[flag ? (unsigned)npts - 1u + flag : sym];
     }
     auto sync = [&]() { __syncthreads(); };
     cta_fft4096<false>(v, E, P.tw_fft, tid, sync);

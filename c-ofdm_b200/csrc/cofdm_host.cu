@@ -351,8 +351,12 @@ int launch_tx_generic(cofdm *h, cudaStream_t st, const uint8_t *payload, size_t 
             const uint8_t *pl = payload + f0 * (size_t)P.bytes_per_frame;
             void *out = (char *)frames + f0 * (size_t)P.frame_len * sample_bytes(fmt);
             const dim3 grid((unsigned)P.num_symb + 1, n);
-            if (fmt == COFDM_CI16) big_tx_kernel<kCI16><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out);
-            else big_tx_kernel<kCF32><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out);
+            // the production instance is specialised on 64-QAM and on the row layout (P.big_lay); everything else reads both from the configuration
+            const bool spec = P.mod_type == 6 && P.big_lay && h->big_lay_on;
+            if (fmt == COFDM_CI16) { if (spec) big_tx_kernel<kCI16, 6, true><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out);
+                                     else big_tx_kernel<kCI16><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out); }
+            else { if (spec) big_tx_kernel<kCF32, 6, true><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out);
+                   else big_tx_kernel<kCF32><<<grid, kBigThreads, big_tx_smem_bytes(), st>>>(P, pl, n, out); }
             if (int rc = check_launch(h, "big_tx")) return rc;
         }
         return COFDM_OK;
@@ -498,7 +502,7 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
     rc |= upload(h, T.tw_pf, &P.tw_pf);     rc |= upload(h, T.tw_t2, &P.tw_t2);   rc |= upload(h, T.t2_mask, &P.t2_mask);
     rc |= upload(h, T.t2_tone, &P.t2_tone); rc |= upload(h, T.preamble_td, &P.preamble_td);
     rc |= upload(h, T.matched, &P.matched); rc |= upload(h, T.mod_preamble, &P.mod_preamble);
-    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.big_roles, &P.big_roles); rc |= upload(h, T.big_eq, &P.big_eq); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
+    rc |= upload(h, T.bin_role, &P.bin_role); rc |= upload(h, T.big_roles, &P.big_roles); rc |= upload(h, T.big_eq, &P.big_eq); rc |= upload(h, T.big_txd, &P.big_txd); rc |= upload(h, T.bin_map, &P.bin_map); rc |= upload(h, T.data_bin, &P.data_bin); rc |= upload(h, T.pilot_bin, &P.pilot_bin);
     rc |= upload(h, T.lane_desc, &P.lane_desc); rc |= upload(h, T.lane_aux, &P.lane_aux); rc |= upload(h, T.acq_desc, &P.acq_desc);
     rc |= upload(h, T.grid_lane, &P.grid_lane); rc |= upload(h, T.tx_desc, &P.tx_desc);
     for (int m : {1, 2, 4, 6, 8}) rc |= upload(h, T.constell[m], &h->constell_dev[m]);
@@ -591,10 +595,11 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             COFDM_BACQ_ATTR(kCF32, true, true); COFDM_BACQ_ATTR(kCF32, true, false); COFDM_BACQ_ATTR(kCF32, false, true); COFDM_BACQ_ATTR(kCF32, false, false);
             COFDM_BACQ_ATTR(kCI16, true, true); COFDM_BACQ_ATTR(kCI16, true, false); COFDM_BACQ_ATTR(kCI16, false, true); COFDM_BACQ_ATTR(kCI16, false, false);
 #undef COFDM_BACQ_ATTR
-            cudaFuncSetAttribute(big_tx_kernel<kCF32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_tx_smem_bytes());
-            cudaFuncSetAttribute(big_tx_kernel<kCI16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_tx_smem_bytes());
-            cudaFuncSetAttribute(big_tx_kernel<kCF32>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-            cudaFuncSetAttribute(big_tx_kernel<kCI16>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+#define COFDM_BTX_ATTR(...) \
+            cudaFuncSetAttribute(big_tx_kernel<__VA_ARGS__>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)big_tx_smem_bytes()); \
+            cudaFuncSetAttribute(big_tx_kernel<__VA_ARGS__>, cudaFuncAttributePreferredSharedMemoryCarveout, 100)
+            COFDM_BTX_ATTR(kCF32); COFDM_BTX_ATTR(kCI16); COFDM_BTX_ATTR(kCF32, 6, true); COFDM_BTX_ATTR(kCI16, 6, true);
+#undef COFDM_BTX_ATTR
             const int smb = (int)big_smem_bytes();
 #define COFDM_BIG_ATTR1(F, T, W, MD) \
             cudaFuncSetAttribute(big_demod_kernel<F, T, W, MD>, cudaFuncAttributeMaxDynamicSharedMemorySize, smb); \

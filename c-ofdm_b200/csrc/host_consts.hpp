@@ -101,6 +101,7 @@ struct HostTables {
     std::vector<uint2> lane_aux;      //             combinations and straggler bins
     std::vector<uint2> acq_desc;      //             acquire kernel: which phase each slot produces
     std::vector<uint4> big_roles;     // big.cuh: per thread, the roles of its 16 bins
+    std::vector<uint4> big_txd;       //          per thread, where the bits of its 16 grid points sit in the symbol's payload
     std::vector<uint4> big_eq;        //          per thread, the equaliser's table of the specialised row layout
     std::vector<uint4> tx_desc;       // tx512w.cuh: per lane, what sits at the bins lane + 32 n1
     std::vector<float2> grid_conj;    // conj(tx grid of the preamble) / sqrt(N), by bin
@@ -409,7 +410,18 @@ inline HostTables build_tables(const ConfigMap &cfg) {
     if (N == 4096) {
         p.big_tmask = 0;
         for (int k = 0; k < N; k++) if (T.bin_role[(size_t)k] != -1) p.big_tmask |= 1 << (k >> 8);
+        p.big_phmask = 0;
+        for (int k = 0; k < N; k++) if (T.bin_role[(size_t)k] >= 0 && T.bin_role[(size_t)k] < ND / 2) p.big_phmask |= 1 << (k >> 8);
         p.big_dstep = (256 % p.seg_step) == 0 ? 256 / p.seg_step * p.seg_size : 0;
+        T.big_txd.assign(1024, make_uint4(0, 0, 0, 0));
+        for (int j = 0; j < 256; j++)
+            for (int u = 0; u < 16; u++) {
+                const int role = T.bin_role[(size_t)(j + 256 * u)];
+                unsigned w = 2u << 24;                                          // null
+                if (role <= -2) w = 1u << 24;                                   // pilot
+                else if (role >= 0) w = (unsigned)((role * p.mod_type) >> 3) | (unsigned)((role * p.mod_type) & 7) << 16;
+                (&T.big_txd[4 * (size_t)j + (u >> 2)].x)[u & 3] = w;
+            }
         T.big_roles.assign(512, make_uint4(0, 0, 0, 0));
         for (int j = 0; j < 256; j++)
             for (int t = 0; t < 16; t++) {

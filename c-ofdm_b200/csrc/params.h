@@ -54,11 +54,14 @@ struct Params {
     const int16_t *data_bin;     // [num_data_subc] bin of data index i
     const int16_t *pilot_bin;    // [num_pilot_subc]
     int big_tmask;               // big.cuh: bit t set <=> some bin j + 256 t is used (data or pilot)
+    int big_phmask;              // big.cuh: bit t set <=> some bin j + 256 t carries a data index below num_data_subc / 2 (chan_char_lq's bins)
     int big_dstep;               // big.cuh: data-index step between consecutive rows of one thread (0: none)
     int big_lay;                 // big.cuh: 1 = the sub-carrier map has the row layout the specialised demod instance is compiled for (kBigLay*)
     const uint4 *big_eq;         // [256][3] big.cuh, big_lay only: per thread .x .. .w of entries 0 / 1 = its data rows 0..3 / 12..15: [15:0] byte the
                                  //      demapped symbol goes to (data index, or a dump slot behind the data), [31:16] byte offset of the segment
                                  //      coefficient; entry 2 .x: the (extrapolated) channel-line abscissa i' at rows 0 [15:0] and 12 [31:16], signed
+    const uint4 *big_txd;        // [256][4] big.cuh, big_tx_kernel: per thread one word per row (bins j + 256 u): [15:0] byte of the symbol's payload where
+                                 //      the sub-carrier's bits start, [18:16] bit offset in that byte, [25:24] 1 = pilot, 2 = null
     const uint4 *big_roles;      // [256][2] big.cuh: the 16 roles of thread j (bins j + 256 t, t = 0..15) as int16, packed (fft 4096 only)
     const int16_t *bin_role;     // [fft_size] >= 0 data index within the symbol, -1 null, -2 - p pilot number p (big.cuh)
     // ---- one-warp-per-symbol receive kernels of the fft-512 geometry (rx512n.cuh) ----

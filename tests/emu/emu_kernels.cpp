@@ -23,7 +23,7 @@ static void wire(EmuHandle *h) {
     P.tw_pf = T.tw_pf.data(); P.tw_t2 = T.tw_t2.data(); P.t2_mask = T.t2_mask.data();
     P.t2_tone = T.t2_tone.data(); P.preamble_td = T.preamble_td.data(); P.matched = T.matched.data();
     P.mod_preamble = T.mod_preamble.data(); P.constell = T.constell[T.p.mod_type].data();
-    P.bin_role = T.bin_role.data(); P.big_roles = T.big_roles.data(); P.big_eq = T.big_eq.data(); P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
+    P.bin_role = T.bin_role.data(); P.big_roles = T.big_roles.data(); P.big_eq = T.big_eq.data(); P.big_txd = T.big_txd.data(); P.bin_map = T.bin_map.data(); P.data_bin = T.data_bin.data(); P.pilot_bin = T.pilot_bin.data();
     P.lane_desc = T.lane_desc.data(); P.lane_aux = T.lane_aux.data(); P.acq_desc = T.acq_desc.data(); P.grid_lane = T.grid_lane.data(); P.tx_desc = T.tx_desc.data();
 }
 
@@ -278,8 +278,12 @@ int emu_tx_generic(void *hv, const uint8_t *payload, int n_frames, void *frames,
     if (!h->T.generic_ok) return -1;
     const Params P = h->P;
     if (h->T.big_ok && g_emu_big_tx) {
-        if (fmt == kCI16) emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kBigThreads), big_tx_smem_bytes(), [&] { big_tx_kernel<kCI16>(P, payload, n_frames, frames); });
-        else emu::launch(dim3(P.num_symb + 1, n_frames), dim3(kBigThreads), big_tx_smem_bytes(), [&] { big_tx_kernel<kCF32>(P, payload, n_frames, frames); });
+        const bool spec = P.mod_type == 6 && P.big_lay && g_emu_big_lay;
+        const dim3 g(P.num_symb + 1, n_frames), b(kBigThreads);
+        if (fmt == kCI16) { if (spec) emu::launch(g, b, big_tx_smem_bytes(), [&] { big_tx_kernel<kCI16, 6, true>(P, payload, n_frames, frames); });
+                            else emu::launch(g, b, big_tx_smem_bytes(), [&] { big_tx_kernel<kCI16>(P, payload, n_frames, frames); }); }
+        else { if (spec) emu::launch(g, b, big_tx_smem_bytes(), [&] { big_tx_kernel<kCF32, 6, true>(P, payload, n_frames, frames); });
+               else emu::launch(g, b, big_tx_smem_bytes(), [&] { big_tx_kernel<kCF32>(P, payload, n_frames, frames); }); }
         return 0;
     }
     const size_t sm = 2 * (size_t)P.fft_size * sizeof(float2);

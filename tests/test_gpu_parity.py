@@ -465,6 +465,21 @@ def test_generic_path(cfg_dir, oracle_lib, which):
     m.close()
 
 
+def test_big_path_large_batch(cfg_dir):
+    """fft-4096 configuration, a batch of several thousand frames through the production instances (no taps, no ambiguity
+    count: the demod instance compiled for this map's row layout): the payload comes back"""
+    m = cb.Modem(cfg_dir["big"], device=0)
+    s = m.sizes
+    n = 4096 + 37
+    pay = torch.from_numpy(pc.synth.payloads(n, s.usefull_size, seed=77)).cuda()
+    fr = m.tx_batch(pay, cb.CI16)
+    out, _ = m.rx_aligned_batch(fr.reshape(-1, 2), n_frames=n, frame_stride=s.output_size, offset=s.t2sin_size, count_ambiguous=False)
+    assert torch.equal(out, pay)
+    out, amb = m.rx_aligned_batch(fr.reshape(-1, 2), n_frames=n, frame_stride=s.output_size, offset=s.t2sin_size, count_ambiguous=True)
+    assert torch.equal(out, pay) and amb == 0
+    m.close()
+
+
 def test_stream_sharded_over_ranks_on_gpu(cfg_dir, oracle_lib):
     """config 4: the acquisition loop sharded over 3 (emulated) ranks, GPU engine, vs one sequential oracle pass"""
     from cofdm_b200 import stream
