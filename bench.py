@@ -37,7 +37,7 @@ RX_BYTES_PER_FRAME = 46080 + 1024      # (N+CP)(NS+NPR)*8 read + ND
 TX_BYTES_PER_FRAME = 1024 + 6016 * 8   # payload read + frame written
 WORKLOAD = "default"                   # "big": BASELINE.json configs[4] (fft 4096, cp 1024, 1920 + 128 sub-carriers, 64-QAM)
 MOD_NAME = {1: "BPSK", 2: "QPSK", 4: "16-QAM", 6: "64-QAM", 8: "256-QAM"}
-RX_DRAM_BYTES_PER_FRAME_NCU_BIG = 381757  # big workload: acquire 40991 + 1057, demod 327738 + 11971 (profiles/r02_big_ncu_summary.txt)
+RX_DRAM_BYTES_PER_FRAME_NCU_BIG = 381789  # big workload: acquire 40992 + 1204, demod 327763 + 11830 (profiles/r02_big_ncu_summary.txt)
 RX_DRAM_BYTES_PER_FRAME_NCU = 47361     # measured DRAM read+write of the rx pass (acquire + demod kernels), see roofline.traffic_source
 
 
@@ -370,7 +370,7 @@ def native_arm(args):
                          "peak_source": peak_src,
                          "traffic_source": "ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of the two rx kernels "
                                            + ("over 32768 frames (profiles/r02_final_ncu_summary.txt) = 47361 B/frame" if WORKLOAD == "default"
-                                              else "over 4096 frames (profiles/r02_big_ncu_summary.txt) = 381757 B/frame") + ", scaled to this launch's frames",
+                                              else "over 4096 frames (profiles/r02_big_ncu_summary.txt) = 381789 B/frame") + ", scaled to this launch's frames",
                          "algorithmic_bytes_per_frame": RX_BYTES_PER_FRAME, "tx_kernel_gbs": tx_gbs, "tx_frac": tx_gbs / peak},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "frames_per_step": E, "ms_per_step": e_dt * 1e3, "payload_roundtrip_ok": e_ok, "host_sample_format": "ci16 (SDR wire format)",

@@ -706,8 +706,10 @@ big_acquire_kernel(const Params P, const void *__restrict__ samples, long long f
 // registers (thread j holds samples j + 256 t: a warp stores 32 consecutive samples); CTA (num_symb, f) copies the constant
 // sync tone + preamble.
 // ================================================================================================================
-constexpr int kBigTxPoints = 256 + 2;                        // the point table: up to 256-QAM, the pilot, zero
-COFDM_HD constexpr size_t big_tx_smem_bytes() { return (size_t)kBigExchSlots * 8 + (size_t)kBigTxPoints * 8; }
+// shared memory behind the exchange: the point table (up to 64-QAM: 66 entries x 16 lane slots, so that lane l of a half-warp
+// always reads bank pair l & 15 -- no conflicts whatever the data; 256-QAM: 258 plain entries), the staged payload, the mbarrier
+constexpr int kBigTxTabBytes = 66 * 16 * 8, kBigTxPayMax = kBigMaxData + 16;
+COFDM_HD constexpr size_t big_tx_smem_bytes() { return (size_t)kBigExchSlots * 8 + kBigTxTabBytes + kBigTxPayMax + 16; }
 
 template <int FMT>
 COFDM_DEV void big_store(void *frame_out, long long idx, float2 v, float mult) {
@@ -724,8 +726,9 @@ COFDM_DEV void big_store(void *frame_out, long long idx, float2 v, float mult) {
 // 5..11 of the grid are empty: the first FFT pass never touches them).
 // P.big_txd: per thread 16 words, one per row: [15:0] byte of the symbol's payload where the sub-carrier's bits start,
 // [18:16] bit offset in that byte, [25:24] 1 = pilot, 2 = null.  The bytes come straight from global memory (two byte loads per
-// row, neighbouring threads read neighbouring bytes; all of a thread's loads are in flight together), the points from a small
-// table in shared memory: conj(constellation), then the pilot and zero.
+// row, neighbouring threads read neighbouring bytes; all of a thread's loads are in flight together) -- or, when the symbol's
+// bytes are 16-byte aligned (the production geometry: 1440 bytes per symbol), from a copy one bulk load (TMA) put in shared
+// memory; the points from a small table in shared memory: conj(constellation), then the pilot and zero.
 template <int FMT, int MOD = 0, bool LAY = false>
 __global__ void __launch_bounds__(kBigThreads, 4)
 big_tx_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames, void *__restrict__ frames) {
@@ -741,35 +744,72 @@ big_tx_kernel(const Params P, const uint8_t *__restrict__ payload, int n_frames,
     }
     float2 *E = reinterpret_cast<float2 *>(smem_raw);
     float2 *ct = reinterpret_cast<float2 *>(smem_raw + (size_t)kBigExchSlots * 8);
+    uint8_t *pl = reinterpret_cast<uint8_t *>(smem_raw) + (size_t)kBigExchSlots * 8 + kBigTxTabBytes;
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(pl + kBigTxPayMax);
     const int mod = MOD ? MOD : P.mod_type, npts = 1 << mod, ND = P.num_data_subc, sym_bytes = ND * mod / 8;
-    for (int i = tid; i < npts + 2; i += kBigThreads) {
-        float2 c = make_float2(0.f, 0.f);                                          // Frame.cpp:55
-        if (i < npts) { c = __ldg(&P.constell[i]); c.y = -c.y; }                   // conjugated: the backward transform is conj(FFT(conj G))
-        else if (i == npts) c = make_float2(P.pilot_ampl, 0.f);                    // Frame.cpp:56-57
-        ct[i] = c;
+    const uint8_t *src = payload + (size_t)frame * P.bytes_per_frame + (size_t)s * sym_bytes;
+    const bool staged = ((reinterpret_cast<uintptr_t>(src) | (unsigned)sym_bytes) & 15u) == 0u && sym_bytes <= kBigTxPayMax;
+    if (staged && tid == 0) {
+        mbar_init(mbar, 1);
+        mbar_fence_init();
+        mbar_arrive_expect_tx(mbar, (unsigned)sym_bytes);
+        tma_load_1d(pl, src, (unsigned)sym_bytes, mbar);
+    }
+    // the point table; up to 64-QAM every entry is repeated for the 16 lane slots (entry e, slot q at e * 16 + q)
+    const bool skew = mod <= 6;
+    if (skew) {
+        // one load per thread: entry tid / 4, lane slots 4 (tid % 4) .. + 3; the pilot and zero by the first warp
+        const int e = tid >> 2;
+        if (e < npts) {
+            float2 c = __ldg(&P.constell[e]);
+            c.y = -c.y;                                                            // conjugated: the backward transform is conj(FFT(conj G))
+            float4 *d = reinterpret_cast<float4 *>(ct + e * 16 + (tid & 3) * 4);
+            d[0] = make_float4(c.x, c.y, c.x, c.y); d[1] = d[0];
+        }
+        if (tid < 32) ct[(npts + (tid >> 4)) * 16 + (tid & 15)] = make_float2((tid >> 4) ? 0.f : P.pilot_ampl, 0.f);   // Frame.cpp:55-57
+    } else {
+        for (int i = tid; i < npts + 2; i += kBigThreads) {
+            float2 c = make_float2(0.f, 0.f);                                      // Frame.cpp:55
+            if (i < npts) { c = __ldg(&P.constell[i]); c.y = -c.y; }
+            else if (i == npts) c = make_float2(P.pilot_ampl, 0.f);                // Frame.cpp:56-57
+            ct[i] = c;
+        }
     }
     const unsigned tmask = LAY ? kBigLayUsed : (unsigned)P.big_tmask;
-    const uint8_t *src = payload + (size_t)frame * P.bytes_per_frame + (size_t)s * sym_bytes;
     const uint4 da = __ldg(&P.big_txd[4 * tid]), db = __ldg(&P.big_txd[4 * tid + 1]), dc = __ldg(&P.big_txd[4 * tid + 2]), dd = __ldg(&P.big_txd[4 * tid + 3]);
     const unsigned dw[16] = {da.x, da.y, da.z, da.w, db.x, db.y, db.z, db.w, dc.x, dc.y, dc.z, dc.w, dd.x, dd.y, dd.z, dd.w};
     unsigned wb[16];
+    // (the second byte is read at a clamped position: when the bits end inside the first byte it is shifted out anyway)
+    if (!staged) {
 #pragma unroll
-    for (int u = 0; u < 16; u++) {
-        wb[u] = 0u;
-        if (!((tmask >> u) & 1u)) continue;
-        const int b0 = (int)(dw[u] & 0xffffu);
-        // (the second byte is read at a clamped position: when the bits end inside the first byte it is shifted out anyway)
-        wb[u] = ((unsigned)__ldg(src + b0) << 8) | (unsigned)__ldg(src + min(b0 + 1, sym_bytes - 1));
+        for (int u = 0; u < 16; u++) {
+            wb[u] = 0u;
+            if (!((tmask >> u) & 1u)) continue;
+            const int b0 = (int)(dw[u] & 0xffffu);
+            wb[u] = ((unsigned)__ldg(src + b0) << 8) | (unsigned)__ldg(src + min(b0 + 1, sym_bytes - 1));
+        }
     }
-    __syncthreads();                                                              // ct[] complete
+    __syncthreads();                                                              // ct[] complete, the mbarrier initialised
+    if (staged) {
+        mbar_wait(mbar, 0);
+#pragma unroll
+        for (int u = 0; u < 16; u++) {
+            wb[u] = 0u;
+            if (!((tmask >> u) & 1u)) continue;
+            const int b0 = (int)(dw[u] & 0xffffu);
+            wb[u] = ((unsigned)pl[b0] << 8) | (unsigned)pl[min(b0 + 1, sym_bytes - 1)];
+        }
+    }
     float2 v[16];
+    const float2 *ctl = skew ? ct + (tid & 15) : ct;
+    const int csh = skew ? 4 : 0;
 #pragma unroll
     for (int u = 0; u < 16; u++) {
         v[u] = make_float2(0.f, 0.f);
         if (!((tmask >> u) & 1u)) continue;
         const unsigned off = (dw[u] >> 16) & 7u, flag = dw[u] >> 24;
         const unsigned sym = (wb[u] >> (16u - (unsigned)mod - off)) & (unsigned)(npts - 1);      // Frame.cpp:59-62 + modulation.cpp:39-50
-        v[u] = ct[flag ? (unsigned)npts - 1u + flag : sym];
+        v[u] = ctl[(flag ? (unsigned)npts - 1u + flag : sym) << csh];
     }
     auto sync = [&]() { __syncthreads(); };
     cta_fft4096<false>(v, E, P.tw_fft, tid, sync);
