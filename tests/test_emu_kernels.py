@@ -227,6 +227,38 @@ def test_big_path_cluster_kernels(cfg_dir, oracle_lib):
         m.set_big_lay(1)
 
 
+def test_big_path_other_map_and_unaligned_payload(cfg_dir, oracle_lib, tmp_path):
+    """an fft-4096 configuration whose sub-carrier map is NOT the one the specialised instances are compiled for (64 pilots,
+    960 data sub-carriers: rows 0..2 and 14..15 of the bin matrix) runs the general instances of big_demod_kernel /
+    big_tx_kernel; and a payload that is not 16-byte aligned takes big_tx_kernel's byte-load path instead of the bulk copy"""
+    cfg = pc.synth.write_config(str(tmp_path / "config_big_np64.txt"), base=cfg_dir["big"], num_data_subc=960, num_pilot_subc=64, num_symb=4)
+    o = oracle_lib.Oracle("port", cfg)
+    m = EmuModem(cfg, o.sizes)
+    assert m.big and m.big_lay() == 0
+    st = pc.check_tx(m, o, n_frames=2)
+    assert st["rel_l2"] < 1e-6, st
+    m.big_mode = 1
+    pay, rec = pc.impaired_records(o, 2, seed=12, cfo_max=0.0005, noise=0.5, taps=(1.0,), early=0)
+    st = pc.check_rx_against_oracle(m, o, rec, "i16")
+    assert st["shift_mismatch"] == 0 and st["constell"] < 5e-6, st
+    out, _ = m.rx_aligned_batch(rec, count_ambiguous=False)
+    for i in range(len(rec)):
+        r = o.rx_aligned(pc.cplx(rec[i]))
+        pc.assert_bytes_match(out[i], r["bytes"], r["constell"], o.sizes.mod_type, f"np64 frame {i}")
+    m.close()
+    # the production map, payload one byte off alignment: same samples as from the aligned copy
+    o = oracle_lib.Oracle("port", cfg_dir["big"])
+    m = EmuModem(cfg_dir["big"], o.sizes)
+    pay = pc.synth.payloads(2, o.sizes.usefull_size, seed=5)
+    buf = np.zeros(pay.size + 1, np.uint8)
+    buf[1:] = pay.ravel()
+    off = buf[1:].reshape(pay.shape)
+    assert off.ctypes.data % 16 != 0
+    for fmt in (0, 1):
+        assert np.array_equal(m.tx_batch(off, fmt), m.tx_batch(pay, fmt))
+    m.close()
+
+
 def test_big_path_phase_unwrap_slow_path(cfg_dir, oracle_lib):
     """a frame cut 6 samples early: the preamble's phases run over several turns, so chan_char_lq's one-step unwrap
     (Frame.hpp:407-414) takes the acquire kernel's 3-state scan path; multipath and a larger CFO on top"""
