@@ -84,6 +84,8 @@ struct cofdm {
     DevBuf gen_frames[kPipe], gen_spec[kPipe], gen_pre[kPipe];   // any-size path
     DevBuf fscal[kPipe];                         // per-frame scalars handed from the acquire to the demod kernel
     int big_acquire = 1;                         // ... including their own acquisition kernel (env COFDM_BIG_ACQUIRE=0: the any-size kernels + bridge)
+    int big_cluster_policy = 2;                  // ... cluster scheduling policy preference of the demod launch: load balancing (measured 2.44 vs 2.48 ms
+                                                 //     per 16 384 frames against the default and "spread"; env COFDM_BIG_CLUSTER_POLICY = 0 / 1 / 2)
     int big_lay_on = 1;                          // ... the layout-specialised demod instance where the map allows it (env COFDM_BIG_LAY=0: off)
     int big_on = 1;                              // fft-4096 configurations use the cluster kernels of big.cuh (env COFDM_BIG=0: the any-size path)
     int tx_ctas = 148 * 4;                       // CTAs of the persistent tx kernel (SMs x resident CTAs per SM, measured at create)
@@ -228,10 +230,12 @@ int launch_big_demod(cofdm *h, cudaStream_t st, const void *samples, size_t n_fr
     cfg.blockDim = dim3(kBigThreads);
     cfg.dynamicSmemBytes = big_smem_bytes();
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)P.num_symb; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeClusterSchedulingPolicyPreference;     // 0 the driver's default, 1 spread, 2 load balancing
+    attr[1].val.clusterSchedulingPolicyPreference = (cudaClusterSchedulingPolicy)h->big_cluster_policy;
+    cfg.attrs = attr; cfg.numAttrs = h->big_cluster_policy ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, big_demod_kernel<FMT, TMA, TAPS, MOD, LAY>, P, samples, (long long)stride, (int)n_frames, bytes, amb, taps, fsc);
     if (e != cudaSuccess) return fail(COFDM_ERR_CUDA, std::string("big_demod launch: ") + cudaGetErrorString(e));
     return check_launch(h, "big_demod");
@@ -586,6 +590,8 @@ int cofdm_create(const char *config_path, int device, cofdm_t **out) {
             cudaFuncSetAttribute(gen_symbol_kernel<kCI16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, sm_s);
             const char *bl = std::getenv("COFDM_BIG_LAY");           // 0: the layout-specialised demod instance off (A/B runs)
             if (bl) h->big_lay_on = std::atoi(bl) != 0;
+            const char *bp = std::getenv("COFDM_BIG_CLUSTER_POLICY");
+            if (bp) h->big_cluster_policy = std::max(0, std::min(2, std::atoi(bp)));
             const char *ba = std::getenv("COFDM_BIG_ACQUIRE");
             if (ba) h->big_acquire = std::atoi(ba) != 0;
             const int sma = (int)big_acquire_smem_bytes();
